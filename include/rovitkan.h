@@ -1,0 +1,132 @@
+/* rovitkan.h -- C ABI of the B200 (sm_100a) implementation of the RoViT-KAN forward/backward path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every function
+ *   - takes DEVICE pointers unless the parameter name ends in `_host`,
+ *   - enqueues work on `stream` (a cudaStream_t passed as void*) and returns immediately,
+ *   - never allocates device memory (the caller owns outputs and workspaces) and never synchronises,
+ *   - returns 0 on success or an RvkStatus code; rvk_strerror()/rvk_last_error() describe it.
+ * The Python nn.Module mirror of the reference (rovitkan_b200.models.*) is a thin ctypes client of
+ * exactly these symbols; tests/test_abi.py checks that the built library exports every one of them.
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the reference repo).
+ */
+#ifndef ROVITKAN_H_
+#define ROVITKAN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RVK_ABI_VERSION 1
+
+/* ---- status ------------------------------------------------------------------------------------- */
+int rvk_abi_version(void);
+const char* rvk_strerror(int status);
+const char* rvk_last_error(void);            /* detail of the last failure on the calling thread */
+int rvk_device_check(void);                  /* 0 iff the current device is compute capability 10.x */
+
+/* ---- KAN severity path ----------------------------------------------------------------------------
+ * Replaces KANLayer.forward (models/kan.py:70-95) incl. BSplineBasis.compute_basis (:10-44), and the
+ * inter-layer ReLU / final 3*sigmoid of KANSeverityModule.forward (:138-149) through `act`
+ * (0 none, 1 relu, 2 3*sigmoid).  spline [in,out,7], lin_w [out,in], lin_b [out] are the reference
+ * parameters unchanged; knots_host are the 11 values of the reference's `knots` buffer.
+ * Only the reference configuration (num_knots=5, degree=3 -> 11 knots, 7 basis functions) is built. */
+int64_t rvk_kan_layer_workspace_floats(int in_features, int out_features, int with_backward);
+/* BSplineBasis.compute_basis (models/kan.py:10-44): t holds n already-normalised inputs, out is [n,7]. */
+int rvk_kan_basis(const float* t, const float* knots_host, int num_knots_total, int64_t n, float* out,
+                  void* stream);
+int rvk_kan_layer_forward(const float* x, const float* spline, const float* lin_w, const float* lin_b,
+                          const float* knots_host, int num_knots_total, int batch, int in_features,
+                          int out_features, int act, float* y, float* workspace, int with_backward,
+                          void* stream);
+/* Gradient of the same layer (what autograd derives from kan.py:70-95).  gy = dL/dy (activated output).
+ * dx [batch,in] is overwritten; dspline/dlin_w/dlin_b are accumulated into (+=); any of them may be NULL.
+ * `workspace` must be the one the matching forward call (with_backward=1) filled. */
+int rvk_kan_layer_backward(const float* x, const float* y, const float* gy, const float* spline,
+                           const float* lin_w, const float* knots_host, int num_knots_total, int batch,
+                           int in_features, int out_features, int act, float* dx, float* dspline,
+                           float* dlin_w, float* dlin_b, float* workspace, void* stream);
+
+/* ---- MLP heads ----------------------------------------------------------------------------------
+ * y = epilogue(x W^T + b): one Linear of ClassificationHead / OrdinalHead / UncertaintyHead
+ * (models/heads.py:17-22, 38-43, 91-102).  relu!=0 applies ReLU; drop_p>0 applies inverted dropout with
+ * a Philox stream keyed by (seed, offset); clamp_lo<clamp_hi clamps (the log-variance head, heads.py:100). */
+int rvk_linear_forward(const float* x, const float* w, const float* b, int batch, int in_features,
+                       int out_features, int relu, float drop_p, uint64_t seed, uint64_t offset,
+                       float clamp_lo, float clamp_hi, float* y, void* stream);
+/* y is the forward output (its zeros/saturation encode the ReLU, dropout and clamp masks).
+ * dx overwritten (or accumulated when accumulate_dx!=0); dw, db accumulated (+=); gpre_ws [batch,out] scratch. */
+int rvk_linear_backward(const float* x, const float* w, const float* y, const float* gy, int batch,
+                        int in_features, int out_features, int relu, float drop_p, float clamp_lo,
+                        float clamp_hi, float* dx, int accumulate_dx, float* dw, float* db, float* gpre_ws,
+                        void* stream);
+
+/* ---- joint loss -----------------------------------------------------------------------------------
+ * Replaces JointLoss.forward (training/losses.py:139-181) = FocalLoss (:15-38) + OrdinalBCELoss (:48-72)
+ * + UncertaintyLoss (:80-101) + KANRegressionLoss (:109-114).  NULL outputs are the stage-gated heads.
+ * out5 = {cls, ord, unc, kan, total}; d_* receive the LOCAL gradients d(term)/d(head output). */
+int rvk_joint_loss_forward(const float* cls_logits, int num_classes, const float* ord_logits, const float* mu,
+                           const float* log_var, const float* kan, const int64_t* class_targets,
+                           const int64_t* severity_targets, const float* alpha, float gamma, float lambda_ord,
+                           float mu_unc, float nu_kan, int batch, float* sums_ws4, float* out5, float* d_cls,
+                           float* d_ord, float* d_mu, float* d_lv, float* d_kan, void* stream);
+/* dst = local * (upstream5[term] + w_total * upstream5[4]); upstream5 lives on the device (no host sync). */
+int rvk_joint_loss_backward(const float* local, const float* upstream5, int term, float w_total, float* dst,
+                            int n, void* stream);
+
+/* ---- DeiT-Tiny trunk ------------------------------------------------------------------------------
+ * Replaces DeiTTinyBackbone.forward (models/backbone.py:23-25), i.e. the forward of
+ * timm.create_model('deit_tiny_patch16_224', num_classes=0) (models/backbone.py:12-16), and its autograd
+ * backward.  `params` / `grads` are HOST arrays of 150 device pointers in timm state_dict order:
+ *   0 cls_token, 1 pos_embed, 2 patch_embed.proj.weight, 3 patch_embed.proj.bias,
+ *   4+12*i.. : blocks.i.{norm1.weight,norm1.bias,attn.qkv.weight,attn.qkv.bias,attn.proj.weight,
+ *              attn.proj.bias,norm2.weight,norm2.bias,mlp.fc1.weight,mlp.fc1.bias,mlp.fc2.weight,mlp.fc2.bias},
+ *   148 norm.weight, 149 norm.bias                                     (all fp32, reference shapes)
+ * prepare_weights casts the GEMM weights to bf16 (plus transposed copies when training) into `wbuf`
+ * and folds cls_token/pos_embed/patch bias into the token table; call it whenever parameters change.
+ * images: fp32 NCHW [batch,3,224,224]; features: fp32 [batch,192].
+ * chunk_images: images per pass through the 12 blocks (0 = whole batch); sized so that a chunk's
+ * activations stay L2-resident between kernels. */
+#define RVK_ENCODER_NUM_PARAMS 150
+int64_t rvk_encoder_weight_bytes(int training);
+int64_t rvk_encoder_workspace_bytes(int batch, int training, int chunk_images);
+int rvk_encoder_prepare_weights(const void* const* params_host, void* wbuf, int training, void* stream);
+int rvk_encoder_forward(const void* const* params_host, const void* wbuf, const float* images, int batch,
+                        int training, int chunk_images, void* workspace, float* features, void* stream);
+/* Needs the workspace of the matching forward (training=1).  Gradients are accumulated (+=). */
+int rvk_encoder_backward(const void* const* params_host, const void* wbuf, void* workspace,
+                         const float* dfeatures, int batch, int chunk_images, void* const* grads_host,
+                         void* stream);
+
+/* ---- individual encoder kernels (exposed for parity tests and microbenchmarks) ---------------------- */
+/* C = epilogue(A[M,K] B[N,K]^T), bf16 operands, tcgen05/TMEM.  mode: 0 bf16(acc+bias), 1 gelu (+z in out2),
+ * 2 acc*gelu'(aux z), 3 fp32(acc+bias), 4 fp32 acc+bias+residual(aux or table) with optional fused LayerNorm
+ * (out2 bf16, gamma/beta, mean/rstd).  N must be a multiple of 192 (<= 768), K a multiple of 64. */
+int rvk_gemm_nt(int mode, const void* a_bf16, int64_t lda, const void* b_bf16, int64_t ldb, void* out, int64_t ldo,
+                void* out2, int64_t ldo2, const void* aux, int64_t ldaux, int m, int n, int k, const float* bias,
+                const float* gamma, const float* beta, const float* res_table, int table_rows, float ln_eps,
+                float* mean_out, float* rstd_out, void* stream);
+/* C[P,Q] (fp32) += scale * A[M,P]^T B[M,Q], bf16 operands (weight gradients). */
+int rvk_gemm_tn(const void* a_bf16, int64_t lda, const void* b_bf16, int64_t ldb, float* c, int64_t ldc, int m,
+                int p, int q, float scale, void* stream);
+/* softmax(q k^T / 8) v per (image, head); qkv bf16 [batch*197,576], ctx bf16 [batch*197,192], lse fp32
+ * [batch,3,197] (log2 domain) or NULL. */
+int rvk_attention_forward(const void* qkv, void* ctx, float* lse, int batch, void* stream);
+int rvk_attention_backward(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
+                           int batch, void* stream);
+int rvk_layernorm_forward(const float* x, int64_t x_row_stride, const float* gamma, const float* beta, float eps,
+                          void* y, int y_is_bf16, int64_t y_row_stride, float* mean, float* rstd, int rows,
+                          void* stream);
+int rvk_layernorm_backward(const void* g, int g_is_bf16, int64_t g_row_stride, const float* x, int64_t x_row_stride,
+                           const float* mean, const float* rstd, const float* gamma, const float* dx_in,
+                           float* dx_out, int64_t dx_row_stride, void* dx_out_bf16, float* dgamma, float* dbeta,
+                           int rows, void* stream);
+int rvk_im2col(const float* images, void* patches_bf16, int batch, void* stream);
+int rvk_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ROVITKAN_H_ */

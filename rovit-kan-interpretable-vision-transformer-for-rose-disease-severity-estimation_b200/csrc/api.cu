@@ -1,0 +1,236 @@
+// extern "C" surface declared in include/rovitkan.h: argument checking + dispatch to the launchers.
+#include "../../include/rovitkan.h"
+
+#include "encoder.h"
+#include "kernels.h"
+
+const char* rvk_last_error_cstr();
+
+namespace {
+inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+int fill_kan_desc(KanLayerDesc& L, const float* spline, const float* lin_w, const float* lin_b,
+                  const float* knots_host, int num_knots_total, int in_features, int out_features) {
+  if (knots_host == nullptr || in_features <= 0 || out_features <= 0) return RVK_ERR_BAD_ARG;
+  if (num_knots_total != 11) return RVK_ERR_UNSUPPORTED_SHAPE;   // reference config: 5 + 2*3 knots, 7 basis functions
+  L.spline = spline; L.lin_w = lin_w; L.lin_b = lin_b;
+  for (int i = 0; i < 11; ++i) L.knots_host[i] = knots_host[i];
+  L.num_knots = 11; L.num_basis = 7;
+  L.in_features = in_features; L.out_features = out_features;
+  return RVK_OK;
+}
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int rvk_abi_version(void) { return RVK_ABI_VERSION; }
+
+const char* rvk_strerror(int status) {
+  switch (status) {
+    case RVK_OK: return "ok";
+    case RVK_ERR_BAD_ARG: return "bad argument (null pointer or non-positive size)";
+    case RVK_ERR_CUDA: return "CUDA runtime error (see rvk_last_error)";
+    case RVK_ERR_UNSUPPORTED_SHAPE: return "shape not supported by the sm_100a kernels";
+    case RVK_ERR_TMA_ENCODE: return "cuTensorMapEncodeTiled failed (see rvk_last_error)";
+    case RVK_ERR_NO_DRIVER: return "CUDA driver entry point cuTensorMapEncodeTiled unavailable (no GPU driver?)";
+    case RVK_ERR_WORKSPACE: return "workspace too small";
+    case RVK_ERR_ALIGNMENT: return "pointer or leading dimension not 16-byte aligned";
+    default: return "unknown status";
+  }
+}
+const char* rvk_last_error(void) { return rvk_last_error_cstr(); }
+
+int rvk_device_check(void) {
+  int dev = 0;
+  RVK_CUDA_TRY(cudaGetDevice(&dev));
+  int major = 0;
+  RVK_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  return major == 10 ? RVK_OK : RVK_ERR_UNSUPPORTED_SHAPE;
+}
+
+// ---- KAN
+int64_t rvk_kan_layer_workspace_floats(int in_features, int out_features, int with_backward) {
+  return rvk_kan_workspace_floats(in_features, out_features, with_backward);
+}
+int rvk_kan_layer_forward(const float* x, const float* spline, const float* lin_w, const float* lin_b,
+                          const float* knots_host, int num_knots_total, int batch, int in_features,
+                          int out_features, int act, float* y, float* workspace, int with_backward, void* stream) {
+  if (batch == 0) return RVK_OK;
+  if (x == nullptr || spline == nullptr || lin_w == nullptr || lin_b == nullptr || y == nullptr ||
+      workspace == nullptr || batch < 0 || act < 0 || act > 2)
+    return RVK_ERR_BAD_ARG;
+  KanLayerDesc L;
+  RVK_TRY(fill_kan_desc(L, spline, lin_w, lin_b, knots_host, num_knots_total, in_features, out_features));
+  return rvk_kan_layer_fwd_launch(L, x, y, act, batch, workspace, with_backward, S(stream));
+}
+int rvk_kan_layer_backward(const float* x, const float* y, const float* gy, const float* spline, const float* lin_w,
+                           const float* knots_host, int num_knots_total, int batch, int in_features,
+                           int out_features, int act, float* dx, float* dspline, float* dlin_w, float* dlin_b,
+                           float* workspace, void* stream) {
+  if (batch == 0) return RVK_OK;
+  if (x == nullptr || y == nullptr || gy == nullptr || workspace == nullptr || batch < 0 || act < 0 || act > 2)
+    return RVK_ERR_BAD_ARG;
+  if ((dspline == nullptr) != (dlin_w == nullptr) || (dspline == nullptr) != (dlin_b == nullptr)) return RVK_ERR_BAD_ARG;
+  KanLayerDesc L;
+  RVK_TRY(fill_kan_desc(L, spline, lin_w, nullptr, knots_host, num_knots_total, in_features, out_features));
+  return rvk_kan_layer_bwd_launch(L, x, y, gy, act, dx, dspline, dlin_w, dlin_b, batch, workspace, S(stream));
+}
+
+int rvk_kan_basis(const float* t, const float* knots_host, int num_knots_total, int64_t n, float* out, void* stream) {
+  if (n == 0) return RVK_OK;
+  if (t == nullptr || knots_host == nullptr || out == nullptr || n < 0) return RVK_ERR_BAD_ARG;
+  if (num_knots_total != 11) return RVK_ERR_UNSUPPORTED_SHAPE;
+  return rvk_kan_basis_launch(t, knots_host, out, n, S(stream));
+}
+
+// ---- heads
+int rvk_linear_forward(const float* x, const float* w, const float* b, int batch, int in_features, int out_features,
+                       int relu, float drop_p, uint64_t seed, uint64_t offset, float clamp_lo, float clamp_hi,
+                       float* y, void* stream) {
+  if (batch == 0) return RVK_OK;
+  if (x == nullptr || w == nullptr || y == nullptr || batch < 0 || in_features <= 0 || out_features <= 0 ||
+      drop_p < 0.0f || drop_p >= 1.0f)
+    return RVK_ERR_BAD_ARG;
+  SgemmArgs a;
+  a.A = x; a.lda = in_features; a.transA = 0;
+  a.B = w; a.ldb = in_features; a.transB = 1;
+  a.C = y; a.ldc = out_features;
+  a.M = batch; a.N = out_features; a.K = in_features;
+  a.bias = b; a.relu = relu;
+  a.clamp_lo = clamp_lo; a.clamp_hi = clamp_hi;
+  a.drop_p = drop_p; a.seed = seed; a.offset = offset;
+  return rvk_sgemm_launch(a, S(stream));
+}
+int rvk_linear_backward(const float* x, const float* w, const float* y, const float* gy, int batch, int in_features,
+                        int out_features, int relu, float drop_p, float clamp_lo, float clamp_hi, float* dx,
+                        int accumulate_dx, float* dw, float* db, float* gpre_ws, void* stream) {
+  if (batch == 0) return RVK_OK;
+  if (x == nullptr || w == nullptr || y == nullptr || gy == nullptr || gpre_ws == nullptr || batch < 0 ||
+      in_features <= 0 || out_features <= 0 || drop_p < 0.0f || drop_p >= 1.0f)
+    return RVK_ERR_BAD_ARG;
+  cudaStream_t s = S(stream);
+  const float* gpre = gy;
+  if (relu || clamp_lo < clamp_hi) {
+    RVK_TRY(rvk_epilogue_grad_launch(y, gy, gpre_ws, relu, 1.0f / (1.0f - drop_p), clamp_lo, clamp_hi,
+                                     batch * out_features, s));
+    gpre = gpre_ws;
+  }
+  if (dx != nullptr) {   // dx = gpre W
+    SgemmArgs a;
+    a.A = gpre; a.lda = out_features; a.B = w; a.ldb = in_features; a.C = dx; a.ldc = in_features;
+    a.M = batch; a.N = in_features; a.K = out_features; a.accumulate = accumulate_dx;
+    RVK_TRY(rvk_sgemm_launch(a, s));
+  }
+  if (dw != nullptr) {   // dW += gpre^T x   (reduction over the batch, split across CTAs)
+    SgemmArgs a;
+    a.A = gpre; a.lda = out_features; a.transA = 1; a.B = x; a.ldb = in_features; a.C = dw; a.ldc = in_features;
+    a.M = out_features; a.N = in_features; a.K = batch; a.accumulate = 1; a.split_k = 1;
+    RVK_TRY(rvk_sgemm_launch(a, s));
+  }
+  if (db != nullptr) RVK_TRY(rvk_colsum_small_launch(gpre, out_features, batch, out_features, db, s));
+  return RVK_OK;
+}
+
+// ---- loss
+int rvk_joint_loss_forward(const float* cls_logits, int num_classes, const float* ord_logits, const float* mu,
+                           const float* log_var, const float* kan, const int64_t* class_targets,
+                           const int64_t* severity_targets, const float* alpha, float gamma, float lambda_ord,
+                           float mu_unc, float nu_kan, int batch, float* sums_ws4, float* out5, float* d_cls,
+                           float* d_ord, float* d_mu, float* d_lv, float* d_kan, void* stream) {
+  JointLossArgs a;
+  a.cls_logits = cls_logits; a.num_classes = num_classes; a.ord_logits = ord_logits;
+  a.mu = mu; a.log_var = log_var; a.kan = kan;
+  a.class_t = class_targets; a.sev_t = severity_targets; a.alpha = alpha;
+  a.gamma = gamma; a.lambda_ord = lambda_ord; a.mu_unc = mu_unc; a.nu_kan = nu_kan;
+  a.batch = batch; a.sums_ws = sums_ws4; a.out = out5;
+  a.d_cls = d_cls; a.d_ord = d_ord; a.d_mu = d_mu; a.d_lv = d_lv; a.d_kan = d_kan;
+  return rvk_joint_loss_launch(a, S(stream));
+}
+int rvk_joint_loss_backward(const float* local, const float* upstream5, int term, float w_total, float* dst, int n,
+                            void* stream) {
+  if (n == 0) return RVK_OK;
+  if (local == nullptr || upstream5 == nullptr || dst == nullptr || term < 0 || term > 3 || n < 0) return RVK_ERR_BAD_ARG;
+  return rvk_loss_scale_grad_launch(local, upstream5, term, w_total, dst, n, S(stream));
+}
+
+// ---- encoder
+int64_t rvk_encoder_weight_bytes(int training) { return rvk_encoder_weight_bytes_impl(training); }
+int64_t rvk_encoder_workspace_bytes(int batch, int training, int chunk_images) {
+  return rvk_encoder_workspace_bytes_impl(batch, training, chunk_images);
+}
+int rvk_encoder_prepare_weights(const void* const* params_host, void* wbuf, int training, void* stream) {
+  return rvk_encoder_prepare_weights_impl(params_host, wbuf, training, S(stream));
+}
+int rvk_encoder_forward(const void* const* params_host, const void* wbuf, const float* images, int batch, int training,
+                        int chunk_images, void* workspace, float* features, void* stream) {
+  if (batch < 0) return RVK_ERR_BAD_ARG;
+  return rvk_encoder_forward_impl(params_host, wbuf, images, batch, training, chunk_images, workspace, features, S(stream));
+}
+int rvk_encoder_backward(const void* const* params_host, const void* wbuf, void* workspace, const float* dfeatures,
+                         int batch, int chunk_images, void* const* grads_host, void* stream) {
+  if (batch < 0) return RVK_ERR_BAD_ARG;
+  return rvk_encoder_backward_impl(params_host, wbuf, workspace, dfeatures, batch, chunk_images, grads_host, S(stream));
+}
+
+// ---- individual kernels
+int rvk_gemm_nt(int mode, const void* a_bf16, int64_t lda, const void* b_bf16, int64_t ldb, void* out, int64_t ldo,
+                void* out2, int64_t ldo2, const void* aux, int64_t ldaux, int m, int n, int k, const float* bias,
+                const float* gamma, const float* beta, const float* res_table, int table_rows, float ln_eps,
+                float* mean_out, float* rstd_out, void* stream) {
+  if (m < 0) return RVK_ERR_BAD_ARG;
+  GemmNtArgs a;
+  a.mode = mode;
+  a.A = a_bf16; a.lda = lda; a.B = b_bf16; a.ldb = ldb; a.out = out; a.ldo = ldo;
+  a.out2 = out2; a.ldo2 = ldo2; a.aux = aux; a.ldaux = ldaux;
+  a.p = GemmNtParams{};
+  a.p.M = m; a.p.N = n; a.p.K = k; a.p.bias = bias; a.p.gamma = gamma; a.p.beta = beta;
+  a.p.res_table = res_table; a.p.table_rows = table_rows; a.p.ln_eps = ln_eps;
+  a.p.mean_out = mean_out; a.p.rstd_out = rstd_out;
+  a.p.has_out2 = out2 != nullptr ? 1 : 0;
+  a.p.has_res = (aux != nullptr || res_table != nullptr) ? 1 : 0;
+  return rvk_gemm_nt_launch(a, S(stream));
+}
+int rvk_gemm_tn(const void* a_bf16, int64_t lda, const void* b_bf16, int64_t ldb, float* c, int64_t ldc, int m, int p,
+                int q, float scale, void* stream) {
+  if (m < 0) return RVK_ERR_BAD_ARG;
+  return rvk_gemm_tn_launch(a_bf16, lda, b_bf16, ldb, c, ldc, m, p, q, scale, S(stream));
+}
+int rvk_attention_forward(const void* qkv, void* ctx, float* lse, int batch, void* stream) {
+  if (batch < 0 || (batch > 0 && (qkv == nullptr || ctx == nullptr))) return RVK_ERR_BAD_ARG;
+  return rvk_attention_fwd_launch(qkv, ctx, lse, batch, S(stream));
+}
+int rvk_attention_backward(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv, int batch,
+                           void* stream) {
+  if (batch < 0 || (batch > 0 && (qkv == nullptr || ctx == nullptr || dctx == nullptr || lse == nullptr || dqkv == nullptr)))
+    return RVK_ERR_BAD_ARG;
+  return rvk_attention_bwd_launch(qkv, ctx, dctx, lse, dqkv, batch, S(stream));
+}
+int rvk_layernorm_forward(const float* x, int64_t x_row_stride, const float* gamma, const float* beta, float eps,
+                          void* y, int y_is_bf16, int64_t y_row_stride, float* mean, float* rstd, int rows,
+                          void* stream) {
+  if (rows < 0 || (rows > 0 && (x == nullptr || gamma == nullptr || beta == nullptr || y == nullptr))) return RVK_ERR_BAD_ARG;
+  return rvk_layernorm_fwd_launch(x, x_row_stride, gamma, beta, eps, y, y_is_bf16, y_row_stride, mean, rstd, rows, S(stream));
+}
+int rvk_layernorm_backward(const void* g, int g_is_bf16, int64_t g_row_stride, const float* x, int64_t x_row_stride,
+                           const float* mean, const float* rstd, const float* gamma, const float* dx_in, float* dx_out,
+                           int64_t dx_row_stride, void* dx_out_bf16, float* dgamma, float* dbeta, int rows,
+                           void* stream) {
+  if (rows < 0 || (rows > 0 && (g == nullptr || x == nullptr || mean == nullptr || rstd == nullptr || gamma == nullptr ||
+                                dx_out == nullptr)))
+    return RVK_ERR_BAD_ARG;
+  if ((dgamma == nullptr) != (dbeta == nullptr)) return RVK_ERR_BAD_ARG;
+  return rvk_layernorm_bwd_launch(g, g_is_bf16, g_row_stride, x, x_row_stride, mean, rstd, gamma, dx_in, dx_out,
+                                  dx_row_stride, dx_out_bf16, dgamma, dbeta, rows, S(stream));
+}
+int rvk_im2col(const float* images, void* patches_bf16, int batch, void* stream) {
+  if (batch < 0 || (batch > 0 && (images == nullptr || patches_bf16 == nullptr))) return RVK_ERR_BAD_ARG;
+  return rvk_im2col_launch(images, patches_bf16, batch, S(stream));
+}
+int rvk_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream) {
+  if (n < 0 || (n > 0 && (src == nullptr || dst_bf16 == nullptr))) return RVK_ERR_BAD_ARG;
+  return rvk_cast_bf16_launch(src, dst_bf16, n, S(stream));
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,284 @@
+// HBM-bound kernels of the DeiT-Tiny token stream: patch extraction, the folded cls/pos/bias table,
+// LayerNorm forward/backward (warp per 192-wide row), bf16 casts, column sums for bias gradients and
+// the batch reduction of the token-0 gradients.  All rows are 192 fp32 = 768 B = 6 coalesced 128 B
+// lines; a warp owns a row and each lane 6 columns (lane + 32*i), so every access is a full line.
+#include "kernels.h"
+
+namespace {
+
+constexpr int kD = 192;
+constexpr int kTok = 197;
+constexpr int kPatchK = 768;
+
+// ------------------------------------------------------------------ patch extraction (im2col)
+// One warp per (image, token, channel): reads 16 image-row segments of 64 B, writes 512 contiguous
+// bytes of the bf16 patch matrix [B*197, 768] (column = c*256 + ky*16 + kx, the flattening of the
+// Conv2d(3,192,16,16) weight).  Token 0 (cls slot) is an all-zero row: the class token enters
+// through the additive token table, so the patch GEMM can emit the [B*197,192] stream directly.
+__global__ void im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int batch) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long total = static_cast<long long>(batch) * kTok * 3;
+  if (w >= total) return;
+  const int c = static_cast<int>(w % 3);
+  const int tok = static_cast<int>((w / 3) % kTok);
+  const int b = static_cast<int>(w / (3 * kTok));
+  uint4 v = make_uint4(0u, 0u, 0u, 0u);
+  const int ky = lane >> 1, half = lane & 1;
+  if (tok > 0) {
+    const int p = tok - 1, py = p / 14, px = p % 14;
+    const float* src = img + ((static_cast<size_t>(b) * 3 + c) * 224 + (py * 16 + ky)) * 224 + px * 16 + half * 8;
+    const float4 a = *reinterpret_cast<const float4*>(src);
+    const float4 d = *reinterpret_cast<const float4*>(src + 4);
+    v = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(d.x, d.y), pack_bf16x2(d.z, d.w));
+  }
+  __nv_bfloat16* dst = out + (static_cast<size_t>(b) * kTok + tok) * kPatchK + c * 256 + ky * 16 + half * 8;
+  *reinterpret_cast<uint4*>(dst) = v;
+}
+
+// table[0] = cls_token + pos[0]; table[i] = patch_bias + pos[i]
+__global__ void token_table_kernel(const float* __restrict__ cls, const float* __restrict__ pos,
+                                   const float* __restrict__ pbias, float* __restrict__ table) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kTok * kD) return;
+  const int tok = i / kD, c = i % kD;
+  table[i] = pos[i] + (tok == 0 ? cls[c] : pbias[c]);
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+  } else {
+    for (long long j = i; j < n; ++j) dst[j] = __float2bfloat16(src[j]);
+  }
+}
+
+// dst[c][r] = bf16(src[r][c]) through a padded 32x32 tile
+__global__ void cast_transpose_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows,
+                                      int cols) {
+  __shared__ float tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[static_cast<size_t>(r) * cols + c] : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[static_cast<size_t>(c) * rows + r] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm forward
+template <bool OUT_BF16>
+__global__ void layernorm_fwd_kernel(const float* __restrict__ x, long long xs, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, float eps, void* __restrict__ y, long long ys,
+                                     float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_block) {
+    const float* xr = x + static_cast<size_t>(r) * xs;
+    float v[6];
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { v[i] = xr[lane + 32 * i]; s += v[i]; }
+    const float mean = warp_sum(s) * (1.0f / kD);
+    float q = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { const float d = v[i] - mean; q = fmaf(d, d, q); }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / kD) + eps);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int c = lane + 32 * i;
+      const float o = (v[i] - mean) * rstd * gamma[c] + beta[c];
+      if (OUT_BF16) static_cast<__nv_bfloat16*>(y)[static_cast<size_t>(r) * ys + c] = __float2bfloat16(o);
+      else static_cast<float*>(y)[static_cast<size_t>(r) * ys + c] = o;
+    }
+    if (lane == 0) {
+      if (mean_out != nullptr) mean_out[r] = mean;
+      if (rstd_out != nullptr) rstd_out[r] = rstd;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm backward
+// dx = rstd * (g*gamma - mean(g*gamma) - xhat * mean(g*gamma*xhat)); dgamma += g*xhat; dbeta += g
+template <bool G_BF16>
+__global__ void layernorm_bwd_kernel(const void* __restrict__ g, long long gs, const float* __restrict__ x,
+                                     long long xs, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                     const float* __restrict__ gamma, const float* dx_in,
+                                     float* dx_out, long long dxs, __nv_bfloat16* __restrict__ dx_bf16,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int rows) {
+  __shared__ float s_dg[kD], s_db[kD];
+  for (int i = threadIdx.x; i < kD; i += blockDim.x) { s_dg[i] = 0.0f; s_db[i] = 0.0f; }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  float gam[6], dg[6], db[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { gam[i] = gamma[lane + 32 * i]; dg[i] = 0.0f; db[i] = 0.0f; }
+  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_block) {
+    const float mu = mean[r], rs = rstd[r];
+    float gv[6], xh[6];
+    float c1 = 0.0f, c2 = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int c = lane + 32 * i;
+      gv[i] = G_BF16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(g)[static_cast<size_t>(r) * gs + c])
+                     : static_cast<const float*>(g)[static_cast<size_t>(r) * gs + c];
+      xh[i] = (x[static_cast<size_t>(r) * xs + c] - mu) * rs;
+      const float gg = gv[i] * gam[i];
+      c1 += gg;
+      c2 = fmaf(gg, xh[i], c2);
+      dg[i] = fmaf(gv[i], xh[i], dg[i]);
+      db[i] += gv[i];
+    }
+    c1 = warp_sum(c1) * (1.0f / kD);
+    c2 = warp_sum(c2) * (1.0f / kD);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int c = lane + 32 * i;
+      float d = rs * (gv[i] * gam[i] - c1 - xh[i] * c2);
+      if (dx_in != nullptr) d += dx_in[static_cast<size_t>(r) * dxs + c];
+      dx_out[static_cast<size_t>(r) * dxs + c] = d;
+      if (dx_bf16 != nullptr) dx_bf16[static_cast<size_t>(r) * dxs + c] = __float2bfloat16(d);
+    }
+  }
+  if (dgamma != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      atomicAdd(&s_dg[lane + 32 * i], dg[i]);
+      atomicAdd(&s_db[lane + 32 * i], db[i]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kD; i += blockDim.x) {
+      atomicAdd(&dgamma[i], s_dg[i]);
+      atomicAdd(&dbeta[i], s_db[i]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ column sums (bias gradients)
+// out[c] += scale * sum_r src[r, c]; each block reduces a row chunk, thread = pair of columns
+template <bool SRC_BF16>
+__global__ void colsum_kernel(const void* __restrict__ src, long long ld, int rows, int cols, float* __restrict__ out,
+                              float scale, int rows_per_block) {
+  const int r0 = blockIdx.x * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  for (int cp = threadIdx.x; cp * 2 < cols; cp += blockDim.x) {
+    const int c = cp * 2;
+    float a0 = 0.0f, a1 = 0.0f;
+    for (int r = r0; r < r1; ++r) {
+      if (SRC_BF16) {
+        const float2 v = unpack_bf16x2(
+            *reinterpret_cast<const uint32_t*>(static_cast<const __nv_bfloat16*>(src) + static_cast<size_t>(r) * ld + c));
+        a0 += v.x; a1 += v.y;
+      } else {
+        const float2 v = *reinterpret_cast<const float2*>(static_cast<const float*>(src) + static_cast<size_t>(r) * ld + c);
+        a0 += v.x; a1 += v.y;
+      }
+    }
+    atomicAdd(&out[c], a0 * scale);
+    if (c + 1 < cols) atomicAdd(&out[c + 1], a1 * scale);
+  }
+}
+
+// ------------------------------------------------------------------ gradients of cls_token / pos_embed / patch bias
+// S[tok, c] = sum_b dx0[b, tok, c];  dpos += S, dcls += S[0], dpatch_bias += sum_{tok>=1} S[tok]
+__global__ void token_grad_reduce_kernel(const float* __restrict__ dx0, int batch, int b_per_block,
+                                         float* __restrict__ dpos, float* __restrict__ dcls,
+                                         float* __restrict__ dpbias) {
+  const int tok = blockIdx.x;
+  const int b0 = blockIdx.y * b_per_block, b1 = min(batch, b0 + b_per_block);
+  const int c = threadIdx.x;
+  float acc = 0.0f;
+  for (int b = b0; b < b1; ++b) acc += dx0[(static_cast<size_t>(b) * kTok + tok) * kD + c];
+  atomicAdd(&dpos[tok * kD + c], acc);
+  // 196 tokens fold into one bias vector: reduce over the tokens of this block column first
+  if (tok == 0) atomicAdd(&dcls[c], acc);
+  else atomicAdd(&dpbias[c], acc);
+}
+
+}  // namespace
+
+int rvk_im2col_launch(const float* images, void* patches_bf16, int batch, cudaStream_t stream) {
+  if (batch <= 0) return RVK_OK;
+  const long long warps = static_cast<long long>(batch) * kTok * 3;
+  const int threads = 256;
+  const long long blocks = (warps * 32 + threads - 1) / threads;
+  im2col_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(images, static_cast<__nv_bfloat16*>(patches_bf16),
+                                                                       batch);
+  return rvk_launch_check();
+}
+
+int rvk_token_table_launch(const float* cls_token, const float* pos_embed, const float* patch_bias, float* table,
+                           cudaStream_t stream) {
+  token_table_kernel<<<(kTok * kD + 255) / 256, 256, 0, stream>>>(cls_token, pos_embed, patch_bias, table);
+  return rvk_launch_check();
+}
+
+int rvk_cast_bf16_launch(const float* src, void* dst, int64_t n, cudaStream_t stream) {
+  if (n <= 0) return RVK_OK;
+  const long long quads = (n + 3) / 4;
+  cast_bf16_kernel<<<static_cast<unsigned>((quads + 255) / 256), 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst), n);
+  return rvk_launch_check();
+}
+
+int rvk_cast_transpose_bf16_launch(const float* src, void* dst, int rows, int cols, cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return RVK_OK;
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  cast_transpose_kernel<<<grid, block, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst), rows, cols);
+  return rvk_launch_check();
+}
+
+int rvk_layernorm_fwd_launch(const float* x, int64_t x_row_stride, const float* gamma, const float* beta, float eps,
+                             void* y, int y_is_bf16, int64_t y_row_stride, float* mean, float* rstd, int rows,
+                             cudaStream_t stream) {
+  if (rows <= 0) return RVK_OK;
+  const int blocks = min((rows + 7) / 8, kNumSMsB200 * 8);
+  if (y_is_bf16)
+    layernorm_fwd_kernel<true><<<blocks, 256, 0, stream>>>(x, x_row_stride, gamma, beta, eps, y, y_row_stride, mean, rstd, rows);
+  else
+    layernorm_fwd_kernel<false><<<blocks, 256, 0, stream>>>(x, x_row_stride, gamma, beta, eps, y, y_row_stride, mean, rstd, rows);
+  return rvk_launch_check();
+}
+
+int rvk_layernorm_bwd_launch(const void* g, int g_is_bf16, int64_t g_row_stride, const float* x, int64_t x_row_stride,
+                             const float* mean, const float* rstd, const float* gamma, const float* dx_in,
+                             float* dx_out, int64_t dx_row_stride, void* dx_out_bf16, float* dgamma, float* dbeta,
+                             int rows, cudaStream_t stream) {
+  if (rows <= 0) return RVK_OK;
+  const int blocks = min((rows + 7) / 8, kNumSMsB200 * 4);
+  auto* dxb = static_cast<__nv_bfloat16*>(dx_out_bf16);
+  if (g_is_bf16)
+    layernorm_bwd_kernel<true><<<blocks, 256, 0, stream>>>(g, g_row_stride, x, x_row_stride, mean, rstd, gamma, dx_in,
+                                                           dx_out, dx_row_stride, dxb, dgamma, dbeta, rows);
+  else
+    layernorm_bwd_kernel<false><<<blocks, 256, 0, stream>>>(g, g_row_stride, x, x_row_stride, mean, rstd, gamma, dx_in,
+                                                            dx_out, dx_row_stride, dxb, dgamma, dbeta, rows);
+  return rvk_launch_check();
+}
+
+int rvk_colsum_launch(const void* src, int src_is_bf16, int64_t ld, int rows, int cols, float* out, float scale,
+                      cudaStream_t stream) {
+  if (rows <= 0 || cols <= 0) return RVK_OK;
+  if (cols % 2 != 0 || ld % 2 != 0) return RVK_ERR_UNSUPPORTED_SHAPE;
+  int blocks = kNumSMsB200 * 2;
+  int rpb = (rows + blocks - 1) / blocks;
+  if (rpb < 8) rpb = 8;
+  blocks = (rows + rpb - 1) / rpb;
+  if (src_is_bf16) colsum_kernel<true><<<blocks, 256, 0, stream>>>(src, ld, rows, cols, out, scale, rpb);
+  else colsum_kernel<false><<<blocks, 256, 0, stream>>>(src, ld, rows, cols, out, scale, rpb);
+  return rvk_launch_check();
+}
+
+int rvk_token_grad_reduce_launch(const float* dx0, int batch, float* dpos, float* dcls, float* dpatch_bias,
+                                 cudaStream_t stream) {
+  if (batch <= 0) return RVK_OK;
+  const int bpb = 32;
+  dim3 grid(kTok, (batch + bpb - 1) / bpb);
+  token_grad_reduce_kernel<<<grid, kD, 0, stream>>>(dx0, batch, bpb, dpos, dcls, dpatch_bias);
+  return rvk_launch_check();
+}

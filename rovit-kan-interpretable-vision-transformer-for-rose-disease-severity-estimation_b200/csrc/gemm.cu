@@ -1,0 +1,95 @@
+// Host launchers for the tcgen05 GEMM kernels: build the TMA tensor maps, pick the grid, launch.
+#include "kernels.h"
+#include "tma_host.h"
+
+namespace {
+
+constexpr int kBN = 192;       // every N on this path (192, 576, 768) is a multiple of 192
+constexpr int kNtStages = 4;
+constexpr int kBQ = 192;
+constexpr int kTnStages = 4;
+
+template <int MODE>
+int launch_nt(const GemmNtArgs& a, cudaStream_t stream) {
+  using L = GemmNtSmem<kBN, kNtStages>;
+  auto kernel = gemm_nt_kernel<kBN, MODE, kNtStages>;
+  static bool configured = false;
+  if (!configured) {
+    RVK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  const GemmNtParams& p = a.p;
+  CUtensorMap tmA, tmB, tmOut, tmOut2, tmAux;
+  RVK_TRY(rvk_make_tmap_2d(&tmA, a.A, RVK_BF16, p.M, p.K, a.lda, 128, 64));
+  RVK_TRY(rvk_make_tmap_2d(&tmB, a.B, RVK_BF16, p.N, p.K, a.ldb, kBN, 64));
+  const bool out_f32 = (MODE == EPI_F32 || MODE == EPI_RES_LN);
+  RVK_TRY(rvk_make_tmap_2d(&tmOut, a.out, out_f32 ? RVK_F32 : RVK_BF16, p.M, p.N, a.ldo, 128, out_f32 ? 32 : 64));
+  tmOut2 = tmOut;
+  tmAux = tmOut;
+  if (p.has_out2) {
+    if (a.out2 == nullptr) return RVK_ERR_BAD_ARG;
+    RVK_TRY(rvk_make_tmap_2d(&tmOut2, a.out2, RVK_BF16, p.M, p.N, a.ldo2, 128, 64));
+  }
+  if (MODE == EPI_DGELU) {
+    if (a.aux == nullptr) return RVK_ERR_BAD_ARG;
+    RVK_TRY(rvk_make_tmap_2d(&tmAux, a.aux, RVK_BF16, p.M, p.N, a.ldaux, 128, 64));
+  } else if (MODE == EPI_RES_LN && p.has_res && p.res_table == nullptr) {
+    if (a.aux == nullptr) return RVK_ERR_BAD_ARG;
+    RVK_TRY(rvk_make_tmap_2d(&tmAux, a.aux, RVK_F32, p.M, p.N, a.ldaux, 128, 32));
+  }
+  const int tiles = ((p.M + 127) / 128) * (p.N / kBN);
+  const int grid = tiles < kNumSMsB200 ? tiles : kNumSMsB200;
+  kernel<<<grid, kGemmThreads, L::kTotal, stream>>>(tmA, tmB, tmOut, tmOut2, tmAux, p);
+  return rvk_launch_check();
+}
+
+}  // namespace
+
+int rvk_gemm_nt_launch(const GemmNtArgs& a, cudaStream_t stream) {
+  const GemmNtParams& p = a.p;
+  if (p.M <= 0) return RVK_OK;
+  if (p.N <= 0 || p.K <= 0 || a.A == nullptr || a.B == nullptr || a.out == nullptr) return RVK_ERR_BAD_ARG;
+  if (p.N % kBN != 0 || p.N > 768 || p.K % 64 != 0) return RVK_ERR_UNSUPPORTED_SHAPE;
+  switch (a.mode) {
+    case EPI_BF16: return launch_nt<EPI_BF16>(a, stream);
+    case EPI_GELU: return launch_nt<EPI_GELU>(a, stream);
+    case EPI_DGELU: return launch_nt<EPI_DGELU>(a, stream);
+    case EPI_F32: return launch_nt<EPI_F32>(a, stream);
+    case EPI_RES_LN:
+      if (p.N != 192) return RVK_ERR_UNSUPPORTED_SHAPE;
+      if (p.res_table != nullptr && p.table_rows <= 0) return RVK_ERR_BAD_ARG;
+      return launch_nt<EPI_RES_LN>(a, stream);
+    default: return RVK_ERR_BAD_ARG;
+  }
+}
+
+int rvk_gemm_tn_launch(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int M, int P,
+                       int Q, float scale, cudaStream_t stream) {
+  if (M <= 0 || P <= 0 || Q <= 0) return RVK_OK;
+  if (A == nullptr || B == nullptr || C == nullptr) return RVK_ERR_BAD_ARG;
+  if (P % 64 != 0 || Q % 64 != 0) return RVK_ERR_UNSUPPORTED_SHAPE;
+  using L = GemmTnSmem<kBQ, kTnStages>;
+  auto kernel = gemm_tn_kernel<kBQ, kTnStages>;
+  static bool configured = false;
+  if (!configured) {
+    RVK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  CUtensorMap tmA, tmB;
+  RVK_TRY(rvk_make_tmap_2d(&tmA, A, RVK_BF16, M, P, lda, 64, 64));
+  RVK_TRY(rvk_make_tmap_2d(&tmB, B, RVK_BF16, M, Q, ldb, 64, 64));
+  const int tiles = ((P + 127) / 128) * ((Q + kBQ - 1) / kBQ);
+  const int total_chunks = (M + 63) / 64;
+  int splits = (2 * kNumSMsB200 + tiles - 1) / tiles;
+  if (splits > total_chunks) splits = total_chunks;
+  if (splits < 1) splits = 1;
+  GemmTnParams p;
+  p.M = M; p.P = P; p.Q = Q;
+  p.ldc = static_cast<int>(ldc);
+  p.chunks_per_split = (total_chunks + splits - 1) / splits;
+  p.C = C;
+  p.scale = scale;
+  splits = (total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
+  kernel<<<dim3(tiles, splits), kTnThreads, L::kTotal, stream>>>(tmA, tmB, p);
+  return rvk_launch_check();
+}

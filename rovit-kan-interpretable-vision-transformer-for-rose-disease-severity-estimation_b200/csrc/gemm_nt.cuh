@@ -1,0 +1,401 @@
+// Persistent tcgen05/TMEM GEMM  C[M,N] = A[M,K] * B[N,K]^T  with fused epilogues, sm_100a.
+//
+//   A  activations  bf16 row-major [M, K]   (K-major UMMA operand, TMA box 64 x 128, 128B swizzle)
+//   B  weights      bf16 row-major [N, K]   (= torch Linear.weight layout; TMA box 64 x BN)
+//   D  fp32 accumulators in TMEM, two stages of 256 columns so the epilogue of tile t overlaps
+//      the MMAs of tile t+1.
+//
+// Warp roles (224 threads): w0 operand TMA producer, w1 UMMA issuer (one elected lane) + TMEM
+// owner, w2 epilogue-panel producer (TMA loads of residual / pre-activation panels), w3..w6
+// epilogue (TMEM lane quadrant = warp_id % 4, one accumulator row per thread).
+//
+// All epilogue I/O moves through a ring of [128 rows x 128 B] shared-memory panels in the TMA
+// 128-byte swizzle: auxiliary inputs arrive by TMA load, are rewritten in place by the row
+// owner, and leave by TMA store (tail rows are clipped by the tensor map).
+//
+// Epilogue modes (the encoder's fused ops):
+//   EPI_BF16     out = bf16(acc + bias)                               qkv, generic dgrad
+//   EPI_GELU     h = bf16(gelu(acc + bias)), optionally z = bf16(acc + bias)     fc1
+//   EPI_DGELU    out = bf16(acc * gelu'(z))                           dgrad through fc2's input
+//   EPI_F32      out = fp32(acc + bias)
+//   EPI_RES_LN   x' = acc + bias + residual (fp32, BN = 192 = full row); optionally
+//                y = bf16(LayerNorm(x') * gamma + beta) and per-row mean / rstd.
+//                The residual is a TMA-loaded tile of the token stream, or a per-position table
+//                (row % table_rows) for the patch-embedding GEMM (cls/pos/bias folded in).
+#pragma once
+
+#include "common.cuh"
+
+enum GemmEpilogue : int { EPI_BF16 = 0, EPI_GELU = 1, EPI_DGELU = 2, EPI_F32 = 3, EPI_RES_LN = 4 };
+
+struct GemmNtParams {
+  int M, N, K;
+  const float* bias;        // [N] or nullptr
+  const float* gamma;       // [192] (EPI_RES_LN with LN)
+  const float* beta;        // [192]
+  const float* res_table;   // [table_rows, 192] or nullptr (then residual comes by TMA)
+  int table_rows;
+  float ln_eps;
+  float* mean_out;          // [M] or nullptr
+  float* rstd_out;          // [M] or nullptr
+  int has_out2;             // EPI_GELU: also store z;  EPI_RES_LN: also store LN output
+  int has_res;              // EPI_RES_LN: 0 = no residual at all
+};
+
+constexpr int kGemmThreads = 224;
+constexpr int kPanelBytes = 128 * 128;   // 16 KB
+constexpr int kNumSlots = 3;
+
+template <int BN, int STAGES>
+struct GemmNtSmem {
+  static constexpr int kABytes = 128 * 64 * 2;
+  static constexpr int kBBytes = BN * 64 * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kOperandBytes = STAGES * kStageBytes;
+  static constexpr int kSlotBytes = kNumSlots * kPanelBytes;
+  static constexpr int kVecBytes = 3 * 768 * 4;   // bias / gamma / beta
+  static constexpr int kBarBytes = 256;
+  static constexpr int kTotal = 1024 /*align slack*/ + kOperandBytes + kSlotBytes + kVecBytes + kBarBytes;
+};
+
+#ifdef __CUDACC__
+
+// number of epilogue panels per output tile and whether panel `i` needs a TMA aux load
+template <int BN, int MODE>
+__device__ __forceinline__ int panels_per_tile(const GemmNtParams& p) {
+  if (MODE == EPI_BF16 || MODE == EPI_DGELU) return BN / 64;
+  if (MODE == EPI_GELU) return (BN / 64) * (p.has_out2 ? 2 : 1);
+  if (MODE == EPI_F32) return BN / 32;
+  return 6 + (p.has_out2 ? 3 : 0);   // EPI_RES_LN
+}
+template <int BN, int MODE>
+__device__ __forceinline__ bool panel_has_aux(const GemmNtParams& p, int i) {
+  if (MODE == EPI_DGELU) return true;
+  if (MODE == EPI_RES_LN) return i < 6 && p.has_res && p.res_table == nullptr;
+  return false;
+}
+
+template <int BN, int MODE, int STAGES>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2,
+               const __grid_constant__ CUtensorMap tmAux, const GemmNtParams p) {
+  using L = GemmNtSmem<BN, STAGES>;
+  static_assert(BN % 64 == 0 && BN <= 256, "BN must be a multiple of 64 up to 256");
+  static_assert(MODE != EPI_RES_LN || BN == 192, "fused LayerNorm needs the whole 192-wide row in one tile");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sOperands = smem;
+  uint8_t* sSlots = smem + L::kOperandBytes;
+  float* sBias = reinterpret_cast<float*>(sSlots + L::kSlotBytes);
+  float* sGamma = sBias + 768;
+  float* sBeta = sGamma + 768;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBeta + 768);
+  uint64_t* full = bars;                       // [STAGES]
+  uint64_t* empty = full + STAGES;             // [STAGES]
+  uint64_t* tmem_full = empty + STAGES;        // [2]
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]
+  uint64_t* slot_full = tmem_empty + 2;        // [kNumSlots]
+  uint64_t* slot_empty = slot_full + kNumSlots;  // [kNumSlots]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(slot_empty + kNumSlots);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int num_m_tiles = (p.M + 127) / 128;
+  const int num_n_tiles = p.N / BN;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+  const int num_kb = p.K / 64;
+
+  // ---- one-time setup
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+    sBias[i] = (p.bias != nullptr && i < p.N) ? p.bias[i] : 0.0f;
+    sGamma[i] = (p.gamma != nullptr && i < 192) ? p.gamma[i] : 1.0f;
+    sBeta[i] = (p.beta != nullptr && i < 192) ? p.beta[i] : 0.0f;
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmOut);
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 128);
+    }
+    for (int i = 0; i < kNumSlots; ++i) {
+      mbar_init(&slot_full[i], 1);
+      mbar_init(&slot_empty[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================================================================= operand producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (t / num_n_tiles) * 128;
+        const int n0 = (t % num_n_tiles) * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], L::kStageBytes);
+          uint8_t* a = sOperands + s * L::kStageBytes;
+          tma_load_2d(a, &tmA, &full[s], kb * 64, m0);
+          tma_load_2d(a + L::kABytes, &tmB, &full[s], kb * 64, n0);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================= UMMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 256;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sOperands + s * L::kStageBytes);
+          const uint32_t b_addr = a_addr + L::kABytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t ad = umma_smem_desc(a_addr + k * 32, 16, 1024);
+            const uint64_t bd = umma_smem_desc(b_addr + k * 32, 16, 1024);
+            umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      }
+    }
+  } else if (warp == 2) {
+    // ================================================================= epilogue-panel producer
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (t / num_n_tiles) * 128;
+        const int n0 = (t % num_n_tiles) * BN;
+        const int np = panels_per_tile<BN, MODE>(p);
+        for (int i = 0; i < np; ++i, ++cnt) {
+          const int slot = cnt % kNumSlots;
+          const uint32_t par = (cnt / kNumSlots) & 1;
+          mbar_wait(&slot_empty[slot], par ^ 1);
+          if (panel_has_aux<BN, MODE>(p, i)) {
+            mbar_arrive_expect_tx(&slot_full[slot], kPanelBytes);
+            const int c0 = (MODE == EPI_DGELU) ? n0 + i * 64 : n0 + i * 32;
+            tma_load_2d(sSlots + slot * kPanelBytes, &tmAux, &slot_full[slot], c0, m0);
+          } else {
+            mbar_arrive(&slot_full[slot]);
+          }
+        }
+      }
+    }
+  } else {
+    // ================================================================= epilogue warps
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;                 // accumulator row == TMEM lane
+    const bool store_thread = (warp == 3 && lane == 0);
+    const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
+    uint32_t cnt = 0;
+    int prev_slot = -1;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+
+    auto acquire = [&](int& slot) -> uint8_t* {
+      slot = cnt % kNumSlots;
+      mbar_wait(&slot_full[slot], (cnt / kNumSlots) & 1);
+      ++cnt;
+      return sSlots + slot * kPanelBytes;
+    };
+    auto publish = [&](const CUtensorMap* tm, int slot, int c0, int r0) {
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (store_thread) {
+        tma_store_2d(tm, sSlots + slot * kPanelBytes, c0, r0);
+        tma_store_commit();
+        if (prev_slot >= 0) {
+          tma_store_wait_read<1>();
+          mbar_arrive(&slot_empty[prev_slot]);
+        }
+        prev_slot = slot;
+      }
+    };
+
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m0 = (t / num_n_tiles) * 128;
+      const int n0 = (t % num_n_tiles) * BN;
+      mbar_wait(&tmem_full[acc], acc_ph);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + acc * 256 + lane_sel;
+
+      if constexpr (MODE == EPI_BF16 || MODE == EPI_GELU || MODE == EPI_DGELU) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; ++c) {
+          float v[2][32];
+          tmem_ld32(tacc + c * 64, v[0]);
+          tmem_ld32(tacc + c * 64 + 32, v[1]);
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[h][i] += sBias[n0 + c * 64 + h * 32 + i];
+          int slot;
+          if constexpr (MODE == EPI_GELU) {
+            if (p.has_out2) {   // pre-activation panel first
+              uint8_t* pz = acquire(slot);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float* s = &v[j >> 2][(j & 3) * 8];
+                uint4 q = make_uint4(pack_bf16x2(s[0], s[1]), pack_bf16x2(s[2], s[3]), pack_bf16x2(s[4], s[5]),
+                                     pack_bf16x2(s[6], s[7]));
+                *reinterpret_cast<uint4*>(pz + sw128_offset(row, j)) = q;
+              }
+              publish(&tmOut2, slot, n0 + c * 64, m0);
+            }
+          }
+          uint8_t* po = acquire(slot);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float s[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s[e] = v[j >> 2][(j & 3) * 8 + e];
+            if constexpr (MODE == EPI_GELU) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) s[e] = gelu_erf(s[e]);
+            }
+            if constexpr (MODE == EPI_DGELU) {
+              const uint4 zq = *reinterpret_cast<const uint4*>(po + sw128_offset(row, j));
+              const uint32_t zw[4] = {zq.x, zq.y, zq.z, zq.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 z = unpack_bf16x2(zw[e]);
+                s[2 * e] *= gelu_erf_grad(z.x);
+                s[2 * e + 1] *= gelu_erf_grad(z.y);
+              }
+            }
+            uint4 q = make_uint4(pack_bf16x2(s[0], s[1]), pack_bf16x2(s[2], s[3]), pack_bf16x2(s[4], s[5]),
+                                 pack_bf16x2(s[6], s[7]));
+            *reinterpret_cast<uint4*>(po + sw128_offset(row, j)) = q;
+          }
+          publish(&tmOut, slot, n0 + c * 64, m0);
+        }
+      } else if constexpr (MODE == EPI_F32) {
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          float v[32];
+          tmem_ld32(tacc + c * 32, v);
+          int slot;
+          uint8_t* po = acquire(slot);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 q;
+            q.x = v[j * 4 + 0] + sBias[n0 + c * 32 + j * 4 + 0];
+            q.y = v[j * 4 + 1] + sBias[n0 + c * 32 + j * 4 + 1];
+            q.z = v[j * 4 + 2] + sBias[n0 + c * 32 + j * 4 + 2];
+            q.w = v[j * 4 + 3] + sBias[n0 + c * 32 + j * 4 + 3];
+            *reinterpret_cast<float4*>(po + sw128_offset(row, j)) = q;
+          }
+          publish(&tmOut, slot, n0 + c * 32, m0);
+        }
+      } else {   // EPI_RES_LN
+        float sum = 0.0f;
+        const bool tma_res = p.has_res && p.res_table == nullptr;
+        const float* trow =
+            (p.res_table != nullptr) ? p.res_table + static_cast<size_t>((m0 + row) % p.table_rows) * 192 : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < 6; ++c) {
+          float v[32];
+          tmem_ld32(tacc + c * 32, v);
+          int slot;
+          uint8_t* po = acquire(slot);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tma_res) r = *reinterpret_cast<const float4*>(po + sw128_offset(row, j));
+            else if (trow != nullptr) r = *reinterpret_cast<const float4*>(trow + c * 32 + j * 4);
+            float4 q;
+            q.x = v[j * 4 + 0] + sBias[c * 32 + j * 4 + 0] + r.x;
+            q.y = v[j * 4 + 1] + sBias[c * 32 + j * 4 + 1] + r.y;
+            q.z = v[j * 4 + 2] + sBias[c * 32 + j * 4 + 2] + r.z;
+            q.w = v[j * 4 + 3] + sBias[c * 32 + j * 4 + 3] + r.w;
+            v[j * 4 + 0] = q.x; v[j * 4 + 1] = q.y; v[j * 4 + 2] = q.z; v[j * 4 + 3] = q.w;
+            sum += (q.x + q.y) + (q.z + q.w);
+            *reinterpret_cast<float4*>(po + sw128_offset(row, j)) = q;
+          }
+          if (p.has_out2) tmem_st32(tacc + c * 32, v);   // keep x' on chip for the LayerNorm passes
+          publish(&tmOut, slot, c * 32, m0);
+        }
+        if (p.has_out2) {
+          const float mean = sum * (1.0f / 192.0f);
+          float var = 0.0f;
+#pragma unroll 1
+          for (int c = 0; c < 6; ++c) {
+            float v[32];
+            tmem_ld32(tacc + c * 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { const float d = v[i] - mean; var = fmaf(d, d, var); }
+          }
+          const float rstd = rsqrtf(var * (1.0f / 192.0f) + p.ln_eps);
+          if (m0 + row < p.M) {
+            if (p.mean_out != nullptr) p.mean_out[m0 + row] = mean;
+            if (p.rstd_out != nullptr) p.rstd_out[m0 + row] = rstd;
+          }
+#pragma unroll 1
+          for (int c = 0; c < 3; ++c) {
+            float v[2][32];
+            tmem_ld32(tacc + c * 64, v[0]);
+            tmem_ld32(tacc + c * 64 + 32, v[1]);
+            int slot;
+            uint8_t* po = acquire(slot);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float s[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int col = c * 64 + j * 8 + e;
+                s[e] = (v[j >> 2][(j & 3) * 8 + e] - mean) * rstd * sGamma[col] + sBeta[col];
+              }
+              uint4 q = make_uint4(pack_bf16x2(s[0], s[1]), pack_bf16x2(s[2], s[3]), pack_bf16x2(s[4], s[5]),
+                                   pack_bf16x2(s[6], s[7]));
+              *reinterpret_cast<uint4*>(po + sw128_offset(row, j)) = q;
+            }
+            publish(&tmOut2, slot, c * 64, m0);
+          }
+        }
+      }
+
+      // accumulator stage drained: hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+    if (store_thread) tma_store_wait_all<0>();
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+#endif  // __CUDACC__

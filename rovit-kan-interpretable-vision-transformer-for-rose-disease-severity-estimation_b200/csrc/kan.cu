@@ -1,0 +1,413 @@
+// Fused KAN layer (reference models/kan.py:70-95), forward and backward, fp32.
+//
+//   y[b,o] = bias[o] + sum_i x[b,i]*Wl[o,i] + sum_i sum_k N_k(tanh x[b,i]) * W[i,o,k]
+//
+// The reference builds a (B,in,7) basis tensor with ~150 elementwise launches and contracts it in
+// a Python double loop.  Here the truncated cubic B-spline is evaluated in closed form per
+// (sample, input) -- interval j on the fp32 knot buffer, u = (t - knot_j)/h, four live cubics, all
+// zero for j >= 7 (the reference's missing degree-0 seeds, kan.py:12-13,23-25,39-40) -- and the
+// basis values never leave the SM: each (sample, input) expands to 8 "activations"
+// [N_0..N_6, x] written to shared memory and contracted immediately against a packed weight
+//   Wp[i*8 + k][o] = W[i,o,k] (k < 7),  Wp[i*8 + 7][o] = Wl[o,i]
+// with a register-tiled outer-product loop (4 samples x 4 outputs per thread).
+//
+// Backward: gpre = gy * act'(y);   dWp = A^T gpre  (batch-split, register tile 8 x 4, atomics);
+//           G = gpre * Wp^T,  dx[b,i] = G[b,i,7] + (1 - t^2) * sum_k G[b,i,k] * N'_k(t).
+#include "kernels.h"
+
+namespace {
+
+constexpr int kNB = 7;          // basis functions
+constexpr int kKW = 8;          // packed width per input: 7 basis + raw x
+constexpr int kKnots = 11;
+constexpr int kIC = 8;          // inputs per chunk -> 64 packed rows
+constexpr int kKC = kIC * kKW;  // 64
+constexpr int kTS = 64;         // samples per CTA tile
+constexpr int kTO = 64;         // outputs per CTA tile
+
+struct Knots { float k[kKnots]; };
+
+// basis values (and optionally d/dt) of the truncated cubic B-spline family at normalised input t;
+// a[7] / da[7] are left untouched
+template <bool DERIV>
+__device__ __forceinline__ void kan_basis_at(float t, const Knots& kn, float (&a)[kKW], float (&da)[kKW]) {
+#pragma unroll
+  for (int k = 0; k < kNB; ++k) { a[k] = 0.0f; if (DERIV) da[k] = 0.0f; }
+  int j = 0;
+#pragma unroll
+  for (int m = 1; m < kKnots; ++m) j += (t >= kn.k[m]) ? 1 : 0;
+  if (j < kNB && t >= kn.k[0]) {
+    const float k0 = kn.k[j];
+    const float h = kn.k[j + 1] - k0;
+    const float u = (t - k0) / h;
+    const float u2 = u * u, u3 = u2 * u;
+    const float om = 1.0f - u;
+    float v[4], d[4];
+    v[0] = u3 * (1.0f / 6.0f);
+    v[1] = (1.0f + 3.0f * u + 3.0f * u2 - 3.0f * u3) * (1.0f / 6.0f);
+    v[2] = (4.0f - 6.0f * u2 + 3.0f * u3) * (1.0f / 6.0f);
+    v[3] = om * om * om * (1.0f / 6.0f);
+    if (DERIV) {
+      const float ih = 1.0f / h;
+      d[0] = 0.5f * u2 * ih;
+      d[1] = (3.0f + 6.0f * u - 9.0f * u2) * (1.0f / 6.0f) * ih;
+      d[2] = (-12.0f * u + 9.0f * u2) * (1.0f / 6.0f) * ih;
+      d[3] = -0.5f * om * om * ih;
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int idx = j - m;
+#pragma unroll
+      for (int k = 0; k < kNB; ++k)
+        if (idx == k) { a[k] = v[m]; if (DERIV) da[k] = d[m]; }
+    }
+  }
+}
+
+// the 8 packed activations [N_0(tanh x) .. N_6(tanh x), x] of scalar input x
+template <bool DERIV>
+__device__ __forceinline__ void kan_expand(float x, const Knots& kn, float (&a)[kKW], float (&da)[kKW], float& dtdx) {
+  const float t = tanhf(x);                 // precise tanhf: a 1-ulp move across 0.4 flips a term by O(0.1)
+  kan_basis_at<DERIV>(t, kn, a, da);
+  a[7] = x;
+  if (DERIV) { da[7] = 0.0f; dtdx = 1.0f - t * t; }
+}
+
+// BSplineBasis.compute_basis (kan.py:10-44) on already-normalised inputs: out[n,7]
+__global__ void kan_basis_kernel(const float* __restrict__ t, Knots kn, float* __restrict__ out, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a[kKW], da[kKW];
+  const float tc = fminf(fmaxf(t[i], kn.k[0]), kn.k[kKnots - 1]);     // kan.py:16
+  kan_basis_at<false>(tc, kn, a, da);
+#pragma unroll
+  for (int k = 0; k < kNB; ++k) out[i * kNB + k] = a[k];
+}
+
+__device__ __forceinline__ float act_grad(int act, float y) {
+  if (act == 1) return y > 0.0f ? 1.0f : 0.0f;            // relu
+  if (act == 2) return y * (3.0f - y) * (1.0f / 3.0f);    // y = 3*sigmoid(z): dy/dz = y*(1 - y/3)
+  return 1.0f;
+}
+
+// ------------------------------------------------------------------ weight packing
+// Wp[(i*8+k) * out_pad + o], WpT[o * (in_pad*8) + i*8+k]; pads are zero.
+__global__ void kan_pack_kernel(const float* __restrict__ spline, const float* __restrict__ lin_w, int n_in, int n_out,
+                                int in_pad, int out_pad, float* __restrict__ Wp, float* __restrict__ WpT) {
+  const long long total = static_cast<long long>(in_pad) * kKW * out_pad;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int o = static_cast<int>(idx % out_pad);
+    const int kk = static_cast<int>(idx / out_pad);
+    const int i = kk / kKW, k = kk % kKW;
+    float v = 0.0f;
+    if (i < n_in && o < n_out)
+      v = (k < kNB) ? spline[(static_cast<size_t>(i) * n_out + o) * kNB + k] : lin_w[static_cast<size_t>(o) * n_in + i];
+    Wp[idx] = v;
+    if (WpT != nullptr) WpT[static_cast<size_t>(o) * (in_pad * kKW) + kk] = v;
+  }
+}
+
+// dspline[i,o,k] += dWp[i*8+k][o]; dlin_w[o,i] += dWp[i*8+7][o]
+__global__ void kan_unpack_grad_kernel(const float* __restrict__ dWp, int n_in, int n_out, int out_pad,
+                                       float* __restrict__ dspline, float* __restrict__ dlin_w) {
+  const long long total = static_cast<long long>(n_in) * n_out * kKW;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(idx % kKW);
+    const int o = static_cast<int>((idx / kKW) % n_out);
+    const int i = static_cast<int>(idx / (static_cast<long long>(kKW) * n_out));
+    const float v = dWp[(static_cast<size_t>(i) * kKW + k) * out_pad + o];
+    if (k < kNB) dspline[(static_cast<size_t>(i) * n_out + o) * kNB + k] += v;
+    else dlin_w[static_cast<size_t>(o) * n_in + i] += v;
+  }
+}
+
+// ------------------------------------------------------------------ forward
+// grid (sample tiles of 64, output tiles of 64); 256 threads; thread (ty, tx) owns samples ty*4..+3,
+// outputs tx*4..+3.  Per chunk of 8 inputs: expand activations into sA, copy the packed weight rows
+// into sW, then 64 rank-1 updates of the 4x4 register tile.
+__global__ void __launch_bounds__(256)
+kan_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wp, const float* __restrict__ bias, Knots kn,
+               float* __restrict__ y, int act, int batch, int n_in, int n_out, int in_pad, int out_pad) {
+  __shared__ __align__(16) float sA[kKC][kTS];   // [packed row][sample]   16 KB
+  __shared__ __align__(16) float sW[kKC][kTO];   // [packed row][output]   16 KB
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int s0 = blockIdx.x * kTS, o0 = blockIdx.y * kTO;
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
+
+  for (int i0 = 0; i0 < in_pad; i0 += kIC) {
+    // expand: thread handles (sample = tid/4, inputs (tid%4)*2, +1): 8 consecutive floats of x per 4 threads
+    {
+      const int sl = tid >> 2, q = tid & 3;
+      const int sg = s0 + sl;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int il = q * 2 + e, ig = i0 + il;
+        float a[kKW], da[kKW], dt;
+        if (sg < batch && ig < n_in) {
+          kan_expand<false>(x[static_cast<size_t>(sg) * n_in + ig], kn, a, da, dt);
+        } else {
+#pragma unroll
+          for (int k = 0; k < kKW; ++k) a[k] = 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < kKW; ++k) sA[il * kKW + k][sl] = a[k];
+      }
+    }
+    // weights: rows i0*8 .. +64 of Wp, columns o0 .. o0+64 (pads are zero-filled by the packer)
+    for (int idx = tid; idx < kKC * (kTO / 4); idx += 256) {
+      const int r = idx >> 4, c4 = idx & 15;
+      *reinterpret_cast<float4*>(&sW[r][c4 * 4]) =
+          *reinterpret_cast<const float4*>(Wp + static_cast<size_t>(i0 * kKW + r) * out_pad + o0 + c4 * 4);
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < kKC; ++kk) {
+      const float4 av = *reinterpret_cast<const float4*>(&sA[kk][ty * 4]);
+      const float4 wv = *reinterpret_cast<const float4*>(&sW[kk][tx * 4]);
+      const float a4[4] = {av.x, av.y, av.z, av.w}, w4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(a4[a], w4[b], acc[a][b]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int sg = s0 + ty * 4 + a;
+    if (sg >= batch) continue;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int og = o0 + tx * 4 + b;
+      if (og >= n_out) continue;
+      float v = acc[a][b] + bias[og];
+      if (act == 1) v = fmaxf(v, 0.0f);
+      else if (act == 2) v = 3.0f / (1.0f + expf(-v));
+      y[static_cast<size_t>(sg) * n_out + og] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ backward: weight gradient
+// grid (input chunks of 8 -> 64 packed rows, output tiles of 64, batch splits); thread (ty, tx) owns packed rows
+// ty*4..+3 and outputs tx*4..+3; reduction over samples in sub-tiles of 64.
+__global__ void __launch_bounds__(256)
+kan_bwd_w_kernel(const float* __restrict__ x, const float* __restrict__ yv, const float* __restrict__ gy, int act,
+                 Knots kn, float* __restrict__ dWp, float* __restrict__ dbias, int batch, int n_in, int n_out,
+                 int out_pad, int samples_per_split) {
+  __shared__ __align__(16) float sA[kTS][kKC];   // [sample][packed row]
+  __shared__ __align__(16) float sG[kTS][kTO];   // [sample][output]
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int i0 = blockIdx.x * kIC, o0 = blockIdx.y * kTO;
+  const int b_begin = blockIdx.z * samples_per_split;
+  const int b_end = min(batch, b_begin + samples_per_split);
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
+  float bsum = 0.0f;   // thread tid < 64 accumulates dbias[o0 + tid] when blockIdx.x == 0
+
+  for (int s0 = b_begin; s0 < b_end; s0 += kTS) {
+    {
+      const int sl = tid >> 2, q = tid & 3;
+      const int sg = s0 + sl;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int il = q * 2 + e, ig = i0 + il;
+        float a[kKW], da[kKW], dt;
+        if (sg < b_end && ig < n_in) {
+          kan_expand<false>(x[static_cast<size_t>(sg) * n_in + ig], kn, a, da, dt);
+        } else {
+#pragma unroll
+          for (int k = 0; k < kKW; ++k) a[k] = 0.0f;
+        }
+        *reinterpret_cast<float4*>(&sA[sl][il * kKW]) = make_float4(a[0], a[1], a[2], a[3]);
+        *reinterpret_cast<float4*>(&sA[sl][il * kKW + 4]) = make_float4(a[4], a[5], a[6], a[7]);
+      }
+    }
+    for (int idx = tid; idx < kTS * kTO; idx += 256) {
+      const int sl = idx >> 6, ol = idx & 63;
+      const int sg = s0 + sl, og = o0 + ol;
+      float g = 0.0f;
+      if (sg < b_end && og < n_out) {
+        const size_t off = static_cast<size_t>(sg) * n_out + og;
+        g = gy[off] * act_grad(act, yv[off]);
+      }
+      sG[sl][ol] = g;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0 && tid < kTO) {
+      for (int sl = 0; sl < kTS; ++sl) bsum += sG[sl][tid];
+    }
+#pragma unroll 8
+    for (int sl = 0; sl < kTS; ++sl) {
+      const float4 av = *reinterpret_cast<const float4*>(&sA[sl][ty * 4]);
+      const float4 gv = *reinterpret_cast<const float4*>(&sG[sl][tx * 4]);
+      const float a4[4] = {av.x, av.y, av.z, av.w}, g4[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(a4[a], g4[b], acc[a][b]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      atomicAdd(&dWp[static_cast<size_t>(i0 * kKW + ty * 4 + a) * out_pad + o0 + tx * 4 + b], acc[a][b]);
+  if (blockIdx.x == 0 && tid < kTO && o0 + tid < n_out) atomicAdd(&dbias[o0 + tid], bsum);
+}
+
+// ------------------------------------------------------------------ backward: input gradient
+// grid (sample tiles of 64); per chunk of 16 inputs thread (ty, tx) owns samples ty*4..+3 and input tx;
+// G[s, i, 0..7] = sum_o gpre[s,o] * Wp[i*8+k][o], contracted in output sub-tiles of 64.
+constexpr int kDxIC = 16;
+__global__ void __launch_bounds__(256)
+kan_bwd_x_kernel(const float* __restrict__ x, const float* __restrict__ yv, const float* __restrict__ gy, int act,
+                 Knots kn, const float* __restrict__ WpT, float* __restrict__ dx, int batch, int n_in, int n_out,
+                 int in_pad, int out_pad) {
+  __shared__ __align__(16) float sG[kTO][kTS];              // [output][sample]        16 KB
+  __shared__ __align__(16) float sWT[kTO][kDxIC * kKW];     // [output][packed row]    32 KB
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  const int s0 = blockIdx.x * kTS;
+  const int ldT = in_pad * kKW;
+
+  for (int i0 = 0; i0 < n_in; i0 += kDxIC) {
+    float acc[4][kKW];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int k = 0; k < kKW; ++k) acc[a][k] = 0.0f;
+    for (int o0 = 0; o0 < n_out; o0 += kTO) {
+      for (int idx = tid; idx < kTO * kTS; idx += 256) {
+        const int sl = idx >> 6, ol = idx & 63;       // coalesced over outputs in global memory
+        const int sg = s0 + sl, og = o0 + ol;
+        float g = 0.0f;
+        if (sg < batch && og < n_out) {
+          const size_t off = static_cast<size_t>(sg) * n_out + og;
+          g = gy[off] * act_grad(act, yv[off]);
+        }
+        sG[ol][sl] = g;
+      }
+      for (int idx = tid; idx < kTO * (kDxIC * kKW / 4); idx += 256) {
+        const int ol = idx >> 5, c4 = idx & 31;
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (o0 + ol < out_pad && i0 * kKW + c4 * 4 < ldT)
+          w = *reinterpret_cast<const float4*>(WpT + static_cast<size_t>(o0 + ol) * ldT + i0 * kKW + c4 * 4);
+        *reinterpret_cast<float4*>(&sWT[ol][c4 * 4]) = w;
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int ol = 0; ol < kTO; ++ol) {
+        const float4 gv = *reinterpret_cast<const float4*>(&sG[ol][ty * 4]);
+        const float4 w0 = *reinterpret_cast<const float4*>(&sWT[ol][tx * kKW]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&sWT[ol][tx * kKW + 4]);
+        const float g4[4] = {gv.x, gv.y, gv.z, gv.w};
+        const float w8[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int k = 0; k < kKW; ++k) acc[a][k] = fmaf(g4[a], w8[k], acc[a][k]);
+      }
+      __syncthreads();
+    }
+    const int ig = i0 + tx;
+    if (ig < n_in) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        const int sg = s0 + ty * 4 + a;
+        if (sg >= batch) continue;
+        float av[kKW], da[kKW], dt;
+        kan_expand<true>(x[static_cast<size_t>(sg) * n_in + ig], kn, av, da, dt);
+        float sp = 0.0f;
+#pragma unroll
+        for (int k = 0; k < kNB; ++k) sp = fmaf(acc[a][k], da[k], sp);
+        dx[static_cast<size_t>(sg) * n_in + ig] = acc[a][7] + dt * sp;
+      }
+    }
+  }
+}
+
+int pad_to(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+// workspace floats needed by forward (packed weights) and backward (transposed pack + packed gradient)
+int64_t rvk_kan_workspace_floats(int n_in, int n_out, int with_backward) {
+  const int64_t in_pad = pad_to(n_in, 16), out_pad = pad_to(n_out, 64);
+  const int64_t wp = in_pad * 8 * out_pad;
+  return with_backward ? 3 * wp : wp;
+}
+
+int rvk_kan_basis_launch(const float* t, const float* knots_host, float* out, int64_t n, cudaStream_t stream) {
+  if (n <= 0) return RVK_OK;
+  Knots kn;
+  for (int i = 0; i < kKnots; ++i) kn.k[i] = knots_host[i];
+  kan_basis_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(t, kn, out, n);
+  return rvk_launch_check();
+}
+
+int rvk_kan_layer_fwd_launch(const KanLayerDesc& L, const float* x, float* y, int act, int batch, float* workspace,
+                             int with_backward, cudaStream_t stream) {
+  if (batch <= 0) return RVK_OK;
+  if (L.num_basis != kNB || L.num_knots != kKnots) return RVK_ERR_UNSUPPORTED_SHAPE;
+  const int in_pad = pad_to(L.in_features, 16), out_pad = pad_to(L.out_features, 64);
+  const int64_t wp = static_cast<int64_t>(in_pad) * 8 * out_pad;
+  float* Wp = workspace;
+  float* WpT = with_backward ? workspace + wp : nullptr;
+  Knots kn;
+  for (int i = 0; i < kKnots; ++i) kn.k[i] = L.knots_host[i];
+  const int pack_blocks = static_cast<int>((wp + 255) / 256 < 1184 ? (wp + 255) / 256 : 1184);
+  kan_pack_kernel<<<pack_blocks, 256, 0, stream>>>(L.spline, L.lin_w, L.in_features, L.out_features, in_pad, out_pad, Wp, WpT);
+  RVK_TRY(rvk_launch_check());
+  dim3 grid((batch + kTS - 1) / kTS, out_pad / kTO);
+  kan_fwd_kernel<<<grid, 256, 0, stream>>>(x, Wp, L.lin_b, kn, y, act, batch, L.in_features, L.out_features, in_pad, out_pad);
+  return rvk_launch_check();
+}
+
+int rvk_kan_layer_bwd_launch(const KanLayerDesc& L, const float* x, const float* y, const float* gy, int act,
+                             float* dx, float* dspline, float* dlin_w, float* dlin_b, int batch, float* workspace,
+                             cudaStream_t stream) {
+  if (batch <= 0) return RVK_OK;
+  if (L.num_basis != kNB || L.num_knots != kKnots) return RVK_ERR_UNSUPPORTED_SHAPE;
+  const int in_pad = pad_to(L.in_features, 16), out_pad = pad_to(L.out_features, 64);
+  const int64_t wp = static_cast<int64_t>(in_pad) * 8 * out_pad;
+  const float* WpT = workspace + wp;      // written by the forward launch
+  float* dWp = workspace + 2 * wp;
+  Knots kn;
+  for (int i = 0; i < kKnots; ++i) kn.k[i] = L.knots_host[i];
+  if (dspline != nullptr) {
+    RVK_CUDA_TRY(cudaMemsetAsync(dWp, 0, wp * sizeof(float), stream));
+    const int tiles = (in_pad / kIC) * (out_pad / kTO);
+    int splits = (2 * kNumSMsB200 + tiles - 1) / tiles;
+    const int sub_tiles = (batch + kTS - 1) / kTS;
+    if (splits > sub_tiles) splits = sub_tiles;
+    const int sps = ((sub_tiles + splits - 1) / splits) * kTS;
+    splits = (batch + sps - 1) / sps;
+    dim3 grid(in_pad / kIC, out_pad / kTO, splits);
+    kan_bwd_w_kernel<<<grid, 256, 0, stream>>>(x, y, gy, act, kn, dWp, dlin_b, batch, L.in_features, L.out_features,
+                                               out_pad, sps);
+    RVK_TRY(rvk_launch_check());
+    const int64_t tot = static_cast<int64_t>(L.in_features) * L.out_features * 8;
+    const int ub = static_cast<int>((tot + 255) / 256 < 1184 ? (tot + 255) / 256 : 1184);
+    kan_unpack_grad_kernel<<<ub, 256, 0, stream>>>(dWp, L.in_features, L.out_features, out_pad, dspline, dlin_w);
+    RVK_TRY(rvk_launch_check());
+  }
+  if (dx != nullptr) {
+    kan_bwd_x_kernel<<<(batch + kTS - 1) / kTS, 256, 0, stream>>>(x, y, gy, act, kn, WpT, dx, batch, L.in_features,
+                                                                   L.out_features, in_pad, out_pad);
+    RVK_TRY(rvk_launch_check());
+  }
+  return RVK_OK;
+}

@@ -1,0 +1,111 @@
+// Internal (C++) launch interface of the sm_100a kernels.  Everything takes raw device pointers,
+// sizes and a stream, never allocates or synchronises, and returns an RvkStatus.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "gemm_nt.cuh"
+#include "gemm_tn.cuh"
+
+// ---- tcgen05 GEMMs -----------------------------------------------------------------------------
+struct GemmNtArgs {
+  int mode = EPI_BF16;            // GemmEpilogue
+  const void* A = nullptr;        // bf16 [M, K], row stride lda
+  int64_t lda = 0;
+  const void* B = nullptr;        // bf16 [N, K], row stride ldb
+  int64_t ldb = 0;
+  void* out = nullptr;            // bf16 or fp32 [M, N], row stride ldo
+  int64_t ldo = 0;
+  void* out2 = nullptr;           // EPI_GELU: pre-activation z (bf16); EPI_RES_LN: LayerNorm output (bf16)
+  int64_t ldo2 = 0;
+  const void* aux = nullptr;      // EPI_DGELU: z (bf16 [M,N]); EPI_RES_LN: residual (fp32 [M,192])
+  int64_t ldaux = 0;
+  GemmNtParams p{};
+};
+int rvk_gemm_nt_launch(const GemmNtArgs& a, cudaStream_t stream);
+
+// C[P,Q] (fp32, ldc) += scale * A[M,P]^T B[M,Q]; A, B bf16 row-major
+int rvk_gemm_tn_launch(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int M, int P,
+                       int Q, float scale, cudaStream_t stream);
+
+// ---- attention -----------------------------------------------------------------------------------
+int rvk_attention_fwd_launch(const void* qkv, void* ctx, float* lse, int batch, cudaStream_t stream);
+int rvk_attention_bwd_launch(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
+                             int batch, cudaStream_t stream);
+
+// ---- token-stream kernels (encoder_kernels.cu) -----------------------------------------------------
+int rvk_im2col_launch(const float* images, void* patches_bf16, int batch, cudaStream_t stream);
+int rvk_token_table_launch(const float* cls_token, const float* pos_embed, const float* patch_bias, float* table,
+                           cudaStream_t stream);
+int rvk_cast_bf16_launch(const float* src, void* dst, int64_t n, cudaStream_t stream);
+int rvk_cast_transpose_bf16_launch(const float* src, void* dst, int rows, int cols, cudaStream_t stream);
+int rvk_layernorm_fwd_launch(const float* x, int64_t x_row_stride, const float* gamma, const float* beta, float eps,
+                             void* y, int y_is_bf16, int64_t y_row_stride, float* mean, float* rstd, int rows,
+                             cudaStream_t stream);
+// dx_out = dx_in + LN'(g) (dx_in may be null; dx_out may alias dx_in); g is bf16 or fp32 with row stride g_stride
+int rvk_layernorm_bwd_launch(const void* g, int g_is_bf16, int64_t g_row_stride, const float* x, int64_t x_row_stride,
+                             const float* mean, const float* rstd, const float* gamma, const float* dx_in,
+                             float* dx_out, int64_t dx_row_stride, void* dx_out_bf16, float* dgamma, float* dbeta,
+                             int rows, cudaStream_t stream);
+int rvk_colsum_launch(const void* src, int src_is_bf16, int64_t ld, int rows, int cols, float* out, float scale,
+                      cudaStream_t stream);
+int rvk_token_grad_reduce_launch(const float* dx0, int batch, float* dpos, float* dcls, float* dpatch_bias,
+                                 cudaStream_t stream);
+
+// ---- KAN ---------------------------------------------------------------------------------------------
+struct KanLayerDesc {
+  const float* spline = nullptr;   // [in, out, 7]   (reference KANLayer.spline_weights)
+  const float* lin_w = nullptr;    // [out, in]
+  const float* lin_b = nullptr;    // [out]
+  float knots_host[11] = {};       // values of the reference's `knots` buffer (host copy)
+  int num_knots = 11, num_basis = 7;
+  int in_features = 0, out_features = 0;
+};
+int64_t rvk_kan_workspace_floats(int n_in, int n_out, int with_backward);
+int rvk_kan_basis_launch(const float* t, const float* knots_host, float* out, int64_t n, cudaStream_t stream);
+// act: 0 none, 1 relu, 2 3*sigmoid.  `workspace` holds the packed weights (see rvk_kan_workspace_floats).
+int rvk_kan_layer_fwd_launch(const KanLayerDesc& L, const float* x, float* y, int act, int batch, float* workspace,
+                             int with_backward, cudaStream_t stream);
+// gy: gradient w.r.t. the activated output y.  dspline/dlin_w/dlin_b are accumulated into (+=); dx is overwritten.
+// Needs the workspace of the matching forward launch (with_backward = 1).
+int rvk_kan_layer_bwd_launch(const KanLayerDesc& L, const float* x, const float* y, const float* gy, int act,
+                             float* dx, float* dspline, float* dlin_w, float* dlin_b, int batch, float* workspace,
+                             cudaStream_t stream);
+
+// ---- heads (fp32 SIMT GEMM with fused epilogues) and joint loss -------------------------------------------
+struct SgemmArgs {
+  const float* A = nullptr; int64_t lda = 0; int transA = 0;
+  const float* B = nullptr; int64_t ldb = 0; int transB = 0;
+  float* C = nullptr; int64_t ldc = 0;
+  int M = 0, N = 0, K = 0;
+  const float* bias = nullptr;
+  int relu = 0;
+  float clamp_lo = 0.0f, clamp_hi = 0.0f;
+  float drop_p = 0.0f;
+  unsigned long long seed = 0, offset = 0;
+  const float* mask_src = nullptr; int64_t ld_mask = 0; float mask_scale = 1.0f;
+  int accumulate = 0;
+  int split_k = 0;
+};
+int rvk_sgemm_launch(const SgemmArgs& a, cudaStream_t stream);
+int rvk_colsum_small_launch(const float* src, int64_t ld, int rows, int cols, float* out, cudaStream_t stream);
+int rvk_epilogue_grad_launch(const float* y, const float* g, float* out, int relu, float scale, float lo, float hi,
+                             int n, cudaStream_t stream);
+
+struct JointLossArgs {
+  const float* cls_logits = nullptr; int num_classes = 4;
+  const float* ord_logits = nullptr;
+  const float* mu = nullptr; const float* log_var = nullptr;
+  const float* kan = nullptr;
+  const int64_t* class_t = nullptr; const int64_t* sev_t = nullptr;
+  const float* alpha = nullptr;
+  float gamma = 2.0f, lambda_ord = 1.0f, mu_unc = 0.5f, nu_kan = 0.5f;
+  int batch = 0;
+  float* sums_ws = nullptr;    // [4] scratch
+  float* out = nullptr;        // [5] cls, ord, unc, kan, total
+  float* d_cls = nullptr; float* d_ord = nullptr; float* d_mu = nullptr; float* d_lv = nullptr; float* d_kan = nullptr;
+};
+int rvk_joint_loss_launch(const JointLossArgs& a, cudaStream_t stream);
+int rvk_loss_scale_grad_launch(const float* local, const float* upstream5, int term, float w_total, float* dst, int n,
+                               cudaStream_t stream);

@@ -1,0 +1,53 @@
+#include "tma_host.h"
+
+#include <mutex>
+#include <string>
+
+#include "common.cuh"
+
+namespace {
+
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn g_encode = nullptr;
+std::once_flag g_once;
+
+void resolve_encode() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) g_encode = reinterpret_cast<EncodeFn>(fn);
+}
+
+thread_local std::string g_last_error;
+
+}  // namespace
+
+void rvk_set_last_cuda_error(int code, const char* what) {
+  g_last_error = std::string(what) + ": " + cudaGetErrorString(static_cast<cudaError_t>(code));
+}
+const char* rvk_last_error_cstr() { return g_last_error.c_str(); }
+
+int rvk_make_tmap_2d(CUtensorMap* out, const void* base, int dtype, int64_t rows, int64_t cols, int64_t ld,
+                     int box_rows, int box_cols) {
+  std::call_once(g_once, resolve_encode);
+  if (g_encode == nullptr) return RVK_ERR_NO_DRIVER;
+  const int esz = (dtype == RVK_BF16) ? 2 : 4;
+  if (box_cols * esz != 128 || box_rows > 256 || box_rows < 1) return RVK_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((ld * esz) & 15) != 0) return RVK_ERR_ALIGNMENT;
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ld) * esz};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = g_encode(out, dtype == RVK_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                        2, const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    g_last_error = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r));
+    return RVK_ERR_TMA_ENCODE;
+  }
+  return RVK_OK;
+}

@@ -1,0 +1,118 @@
+"""Parameter container + fused forward for timm's `deit_tiny_patch16_224` (num_classes=0).
+
+The reference gets this trunk from `timm.create_model` (models/backbone.py:12-16).  timm is a
+third-party dependency that is not part of the reference tree; this module keeps timm's module tree
+and parameter names (`cls_token`, `pos_embed`, `patch_embed.proj`, `blocks.{i}.{norm1,attn.qkv,
+attn.proj,norm2,mlp.fc1,mlp.fc2}`, `norm`) so timm / reference checkpoints load unchanged, and runs
+the whole trunk as one launch sequence of sm_100a kernels (csrc/encoder.cu).
+
+The submodules are parameter holders: the fused path never calls `blocks[i].forward`, so forward
+hooks on `blocks[i].attn` / `.norm1` (reference explainability code) do not fire -- documented
+limitation, see DESIGN.md.
+"""
+
+import warnings
+
+import torch
+import torch.nn as nn
+
+from ._bootstrap import ops as _ops
+
+EMBED, HEADS, DEPTH, MLP, PATCH, TOKENS = 192, 3, 12, 768, 16, 197
+
+
+class _Holder(nn.Module):
+    def forward(self, *a, **k):
+        raise RuntimeError(f'{type(self).__name__} is a parameter holder of the fused DeiT-Tiny trunk; '
+                           'call the trunk (DeiTTinyBackbone / VisionTransformerB200) instead.')
+
+
+class Attention(_Holder):
+    def __init__(self):
+        super().__init__()
+        self.num_heads = HEADS
+        self.head_dim = EMBED // HEADS
+        self.scale = self.head_dim ** -0.5
+        self.qkv = nn.Linear(EMBED, EMBED * 3, bias=True)
+        self.attn_drop = nn.Dropout(0.0)
+        self.proj = nn.Linear(EMBED, EMBED)
+        self.proj_drop = nn.Dropout(0.0)
+
+
+class Mlp(_Holder):
+    def __init__(self):
+        super().__init__()
+        self.fc1 = nn.Linear(EMBED, MLP)
+        self.act = nn.GELU()
+        self.fc2 = nn.Linear(MLP, EMBED)
+
+
+class Block(_Holder):
+    def __init__(self):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(EMBED, eps=1e-6)
+        self.attn = Attention()
+        self.norm2 = nn.LayerNorm(EMBED, eps=1e-6)
+        self.mlp = Mlp()
+
+
+class PatchEmbed(_Holder):
+    def __init__(self):
+        super().__init__()
+        self.proj = nn.Conv2d(3, EMBED, kernel_size=PATCH, stride=PATCH, bias=True)
+
+
+_BLOCK_PARAMS = ['norm1.weight', 'norm1.bias', 'attn.qkv.weight', 'attn.qkv.bias', 'attn.proj.weight',
+                 'attn.proj.bias', 'norm2.weight', 'norm2.bias', 'mlp.fc1.weight', 'mlp.fc1.bias',
+                 'mlp.fc2.weight', 'mlp.fc2.bias']
+
+
+def param_names():
+    """The 150 trunk tensors in the order the C ABI expects (== timm's state_dict order)."""
+    names = ['cls_token', 'pos_embed', 'patch_embed.proj.weight', 'patch_embed.proj.bias']
+    for i in range(DEPTH):
+        names += [f'blocks.{i}.{n}' for n in _BLOCK_PARAMS]
+    return names + ['norm.weight', 'norm.bias']
+
+
+class VisionTransformerB200(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.num_features = EMBED
+        self.embed_dim = EMBED
+        self.num_classes = 0
+        self.patch_embed = PatchEmbed()
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, EMBED))
+        self.pos_embed = nn.Parameter(torch.zeros(1, TOKENS, EMBED))
+        self.blocks = nn.Sequential(*[Block() for _ in range(DEPTH)])
+        self.norm = nn.LayerNorm(EMBED, eps=1e-6)
+        # timm init: trunc_normal(.02) on pos_embed / Linear weights, zero biases, cls ~ N(0, 1e-6)
+        nn.init.trunc_normal_(self.pos_embed, std=0.02)
+        nn.init.normal_(self.cls_token, std=1e-6)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.trunc_normal_(m.weight, std=0.02)
+                nn.init.zeros_(m.bias)
+        self._state = None
+        self._names = param_names()
+
+    def _ordered_params(self):
+        named = dict(self.named_parameters())
+        return [named[n] for n in self._names]
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        ops = _ops()
+        if self._state is None:
+            self._state = ops.EncoderState()
+        return ops.EncoderFn.apply(self._state, x, *self._ordered_params())
+
+
+def create_model(name: str = 'deit_tiny_patch16_224', pretrained: bool = False, num_classes: int = 0, **kwargs):
+    """Stand-in for the one `timm.create_model` call the reference makes (models/backbone.py:12-16)."""
+    if name != 'deit_tiny_patch16_224' or num_classes != 0:
+        raise NotImplementedError('only deit_tiny_patch16_224 with num_classes=0 (what RoViT-KAN uses) is built')
+    if pretrained:
+        warnings.warn('pretrained=True: no network access from this implementation; the trunk is randomly '
+                      'initialised. Load a timm deit_tiny_patch16_224 checkpoint with load_state_dict '
+                      '(parameter names are timm\'s).', stacklevel=3)
+    return VisionTransformerB200()

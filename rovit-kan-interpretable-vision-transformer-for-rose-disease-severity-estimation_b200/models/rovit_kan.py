@@ -1,0 +1,108 @@
+"""RoViT-KAN -- mirror of reference `models/rovit_kan.py` (rovit_kan.py:9-181) on the sm_100a kernels.
+
+Same constructor (first argument a Config, an int or None; additionally accepts `embed_dim=` because
+the reference's own scripts call it that way, scripts/train.py:88-97), same attributes
+(`backbone`, `classification_head`, `ordinal_head`, `uncertainty_head`, `kan_module`,
+`curriculum_stage`), same output dict keys and stage gating, same state_dict keys.
+"""
+
+from typing import Dict
+
+import torch
+import torch.nn as nn
+
+from .backbone import DeiTTinyBackbone
+from .heads import ClassificationHead, OrdinalHead, UncertaintyHead
+from .kan import KANSeverityModule
+
+
+class RoViTKAN(nn.Module):
+    def __init__(self, config_or_embed_dim=None, hidden_dim: int = 128, num_classes: int = 4,
+                 kan_layers: list = None, kan_num_knots: int = 5, kan_degree: int = 3, dropout: float = 0.3,
+                 pretrained: bool = True, embed_dim: int = None):
+        super().__init__()
+        if hasattr(config_or_embed_dim, 'model'):
+            cfg = config_or_embed_dim
+            embed_dim = cfg.model.embed_dim
+            hidden_dim = cfg.model.hidden_dim
+            num_classes = cfg.data.num_classes
+            kan_layers = cfg.model.kan_layers
+            kan_num_knots = cfg.model.kan_num_knots
+            kan_degree = cfg.model.kan_degree
+            dropout = cfg.model.dropout
+            pretrained = cfg.model.pretrained
+        elif config_or_embed_dim is not None:
+            embed_dim = config_or_embed_dim
+
+        self.backbone = DeiTTinyBackbone(pretrained=pretrained, freeze=False)
+        if embed_dim is None:
+            embed_dim = self.backbone.embed_dim
+        if kan_layers is None:
+            kan_layers = [embed_dim, 64, 16, 1]
+
+        self.classification_head = ClassificationHead(embed_dim=embed_dim, hidden_dim=hidden_dim,
+                                                      num_classes=num_classes, dropout=dropout)
+        self.ordinal_head = OrdinalHead(embed_dim=embed_dim, hidden_dim=hidden_dim, num_classes=num_classes,
+                                        dropout=dropout)
+        self.uncertainty_head = UncertaintyHead(embed_dim=embed_dim, hidden_dim=hidden_dim, dropout=dropout)
+        self.kan_module = KANSeverityModule(layers=kan_layers, num_knots=kan_num_knots, degree=kan_degree)
+        self._curriculum_stage = 4
+
+    @property
+    def curriculum_stage(self) -> int:
+        return self._curriculum_stage
+
+    @curriculum_stage.setter
+    def curriculum_stage(self, stage: int):
+        assert 1 <= stage <= 4, "Stage must be between 1 and 4"
+        self._curriculum_stage = stage
+
+    def forward(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
+        features = self.backbone(x)
+        stage = self._curriculum_stage
+        out = {'cls_logits': self.classification_head(features), 'features': features,
+               'ordinal_logits': None, 'mu': None, 'log_var': None, 'kan_severity': None}
+        if stage >= 2:
+            out['ordinal_logits'] = self.ordinal_head(features)
+        if stage >= 3:
+            out['mu'], out['log_var'] = self.uncertainty_head(features)
+        if stage >= 4:
+            out['kan_severity'] = self.kan_module(features)
+        return out
+
+    def predict(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
+        self.eval()
+        with torch.no_grad():
+            out = self.forward(x)
+            probs = torch.softmax(out['cls_logits'], dim=1)
+            pred = {'class': torch.argmax(probs, dim=1), 'class_probs': probs, 'features': out['features']}
+            if out['ordinal_logits'] is not None:
+                # the reference re-runs the ordinal head twice here (rovit_kan.py:143-148); in eval mode that
+                # recomputes the same logits, so decode the ones already in hand
+                p = OrdinalHead.probabilities_from_logits(out['ordinal_logits'])
+                levels = torch.arange(p.shape[1], dtype=torch.float32, device=p.device)
+                pred['ordinal_probs'] = p
+                pred['ordinal_severity'] = (p * levels).sum(dim=1, keepdim=True)
+            if out['mu'] is not None:
+                pred['uncertainty_mu'] = out['mu']
+                pred['uncertainty_std'] = torch.exp(0.5 * out['log_var'])
+            if out['kan_severity'] is not None:
+                pred['kan_severity'] = out['kan_severity']
+            return pred
+
+    def freeze_backbone(self):
+        self.backbone.freeze()
+
+    def unfreeze_backbone(self):
+        self.backbone.unfreeze()
+
+    def get_attention_maps(self, x: torch.Tensor):
+        return self.backbone.get_attention_maps(x)
+
+    def count_parameters(self) -> Dict[str, int]:
+        n = lambda m: sum(p.numel() for p in m.parameters() if p.requires_grad)
+        counts = {'backbone': n(self.backbone), 'classification_head': n(self.classification_head),
+                  'ordinal_head': n(self.ordinal_head), 'uncertainty_head': n(self.uncertainty_head),
+                  'kan_module': n(self.kan_module)}
+        counts['total'] = sum(counts.values())
+        return counts

@@ -1,0 +1,276 @@
+"""torch.autograd glue over the C ABI (include/rovitkan.h).
+
+Every op here allocates its outputs/workspaces with torch, passes raw device pointers plus the
+current CUDA stream to librovitkan.so, and raises on CPU tensors: the path has no CPU fallback.
+PyTorch is used for device memory, streams and autograd bookkeeping only.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+from torch.amp import custom_bwd, custom_fwd
+
+from . import _lib
+
+CHUNK_IMAGES = int(os.environ.get('ROVITKAN_CHUNK_IMAGES', '192'))
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f'{what}: got a {t.device.type} tensor. rovitkan_b200 runs only on CUDA (sm_100a) through '
+            f'librovitkan.so and has no CPU fallback; move the module and its inputs to a B200 device.')
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _host_floats(values):
+    return (C.c_float * len(values))(*values)
+
+
+def _rng_keys():
+    """(seed, offset) for the Philox dropout stream, drawn from torch's CPU generator so that
+    torch.manual_seed() controls it and no device sync is needed."""
+    r = torch.randint(0, 2 ** 62, (2,), dtype=torch.int64)
+    return int(r[0]), int(r[1])
+
+
+# --------------------------------------------------------------------------------------------- KAN
+def kan_basis(t: torch.Tensor, knots_host) -> torch.Tensor:
+    """BSplineBasis.compute_basis (reference models/kan.py:10-44) for already-normalised inputs."""
+    require_cuda(t, 'BSplineBasis.compute_basis')
+    tc = _f32c(t)
+    out = torch.empty(*tc.shape, 7, device=tc.device, dtype=torch.float32)
+    with torch.cuda.device(tc.device):
+        _lib.call('rvk_kan_basis', _p(tc), _host_floats(knots_host), len(knots_host), tc.numel(), _p(out), _stream())
+    return out
+
+
+class KanLayerFn(torch.autograd.Function):
+    """One fused KAN layer: y = act(Linear(x) + sum_i sum_k N_k(tanh x_i) W[i,:,k]) (kan.py:70-95)."""
+
+    @staticmethod
+    @custom_fwd(device_type='cuda', cast_inputs=torch.float32)
+    def forward(ctx, x, spline, lin_w, lin_b, knots_host, act):
+        require_cuda(x, 'KANLayer.forward')
+        xc, sw, lw, lb = _f32c(x), _f32c(spline), _f32c(lin_w), _f32c(lin_b)
+        batch, n_in = xc.shape
+        n_out = lw.shape[0]
+        need_bwd = any(ctx.needs_input_grad[:4])
+        lib = _lib.load()
+        ws = torch.empty(lib.rvk_kan_layer_workspace_floats(n_in, n_out, int(need_bwd)), device=xc.device,
+                         dtype=torch.float32)
+        y = torch.empty(batch, n_out, device=xc.device, dtype=torch.float32)
+        kh = _host_floats(knots_host)
+        with torch.cuda.device(xc.device):
+            _lib.call('rvk_kan_layer_forward', _p(xc), _p(sw), _p(lw), _p(lb), kh, len(knots_host), batch, n_in, n_out,
+                      int(act), _p(y), _p(ws), int(need_bwd), _stream())
+        if need_bwd:
+            ctx.save_for_backward(xc, y, sw, lw)
+            ctx.ws, ctx.knots_host, ctx.act = ws, tuple(knots_host), int(act)
+        return y
+
+    @staticmethod
+    @custom_bwd(device_type='cuda')
+    def backward(ctx, gy):
+        xc, y, sw, lw = ctx.saved_tensors
+        batch, n_in = xc.shape
+        n_out = lw.shape[0]
+        g = _f32c(gy)
+        need_x = ctx.needs_input_grad[0]
+        need_w = any(ctx.needs_input_grad[1:4])
+        dx = torch.empty_like(xc) if need_x else None
+        dsw = torch.zeros_like(sw) if need_w else None
+        dlw = torch.zeros_like(lw) if need_w else None
+        dlb = torch.zeros(n_out, device=xc.device, dtype=torch.float32) if need_w else None
+        with torch.cuda.device(xc.device):
+            _lib.call('rvk_kan_layer_backward', _p(xc), _p(y), _p(g), _p(sw), _p(lw), _host_floats(ctx.knots_host),
+                      len(ctx.knots_host), batch, n_in, n_out, ctx.act, _p(dx), _p(dsw), _p(dlw), _p(dlb), _p(ctx.ws),
+                      _stream())
+        return dx, dsw, dlw, dlb, None, None
+
+
+# --------------------------------------------------------------------------------------------- heads
+class LinearFn(torch.autograd.Function):
+    """y = epilogue(x W^T + b) with fused ReLU / dropout / clamp (heads.py:17-22, 38-43, 91-102)."""
+
+    @staticmethod
+    @custom_fwd(device_type='cuda', cast_inputs=torch.float32)
+    def forward(ctx, x, w, b, relu, drop_p, clamp):
+        require_cuda(x, 'Linear head forward')
+        xc, wc, bc = _f32c(x), _f32c(w), _f32c(b)
+        batch, n_in = xc.shape
+        n_out = wc.shape[0]
+        lo, hi = (float(clamp[0]), float(clamp[1])) if clamp is not None else (0.0, 0.0)
+        seed, offset = _rng_keys() if drop_p > 0.0 else (0, 0)
+        y = torch.empty(batch, n_out, device=xc.device, dtype=torch.float32)
+        with torch.cuda.device(xc.device):
+            _lib.call('rvk_linear_forward', _p(xc), _p(wc), _p(bc), batch, n_in, n_out, int(relu), float(drop_p), seed,
+                      offset, lo, hi, _p(y), _stream())
+        if any(ctx.needs_input_grad[:3]):
+            ctx.save_for_backward(xc, wc, y)
+            ctx.cfg = (int(relu), float(drop_p), lo, hi)
+        return y
+
+    @staticmethod
+    @custom_bwd(device_type='cuda')
+    def backward(ctx, gy):
+        xc, wc, y = ctx.saved_tensors
+        relu, drop_p, lo, hi = ctx.cfg
+        batch, n_in = xc.shape
+        n_out = wc.shape[0]
+        g = _f32c(gy)
+        dx = torch.empty_like(xc) if ctx.needs_input_grad[0] else None
+        dw = torch.zeros_like(wc) if ctx.needs_input_grad[1] else None
+        db = torch.zeros(n_out, device=xc.device, dtype=torch.float32) if ctx.needs_input_grad[2] else None
+        ws = torch.empty(batch, n_out, device=xc.device, dtype=torch.float32)
+        with torch.cuda.device(xc.device):
+            _lib.call('rvk_linear_backward', _p(xc), _p(wc), _p(y), _p(g), batch, n_in, n_out, relu, drop_p, lo, hi,
+                      _p(dx), 0, _p(dw), _p(db), _p(ws), _stream())
+        return dx, dw, db, None, None, None
+
+
+# --------------------------------------------------------------------------------------------- loss
+class JointLossFn(torch.autograd.Function):
+    """Fused JointLoss.forward (training/losses.py:139-181): returns [cls, ord, unc, kan, total]."""
+
+    @staticmethod
+    @custom_fwd(device_type='cuda', cast_inputs=torch.float32)
+    def forward(ctx, cls_logits, ord_logits, mu, log_var, kan, class_t, sev_t, alpha, gamma, lambda_ord, mu_unc, nu_kan):
+        require_cuda(cls_logits, 'JointLoss.forward')
+        dev = cls_logits.device
+        batch, ncls = cls_logits.shape
+        need = any(ctx.needs_input_grad[:5])
+        t = lambda v: None if v is None else _f32c(v)
+        cl, ol, m, lv, kn = t(cls_logits), t(ord_logits), t(mu), t(log_var), t(kan)
+        ct = class_t.to(device=dev, dtype=torch.int64).contiguous()
+        st = sev_t.to(device=dev, dtype=torch.int64).contiguous()
+        al = None if alpha is None else alpha.to(device=dev, dtype=torch.float32).contiguous()
+        out = torch.empty(5, device=dev, dtype=torch.float32)
+        sums = torch.empty(4, device=dev, dtype=torch.float32)
+        mk = lambda v: torch.empty_like(v) if (need and v is not None) else None
+        d_cls, d_ord, d_mu, d_lv, d_kan = mk(cl), mk(ol), mk(m), mk(lv), mk(kn)
+        with torch.cuda.device(dev):
+            _lib.call('rvk_joint_loss_forward', _p(cl), ncls, _p(ol), _p(m), _p(lv), _p(kn), _p(ct), _p(st), _p(al),
+                      float(gamma), float(lambda_ord), float(mu_unc), float(nu_kan), batch, _p(sums), _p(out),
+                      _p(d_cls), _p(d_ord), _p(d_mu), _p(d_lv), _p(d_kan), _stream())
+        if need:
+            ctx.local = (d_cls, d_ord, d_mu, d_lv, d_kan)
+            ctx.weights = (1.0, float(lambda_ord), float(mu_unc), float(mu_unc), float(nu_kan))
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type='cuda')
+    def backward(ctx, g5):
+        g = _f32c(g5)
+        terms = (0, 1, 2, 2, 3)
+        grads = []
+        with torch.cuda.device(g.device):
+            for i, (loc, w, term) in enumerate(zip(ctx.local, ctx.weights, terms)):
+                if loc is None or not ctx.needs_input_grad[i]:
+                    grads.append(None)
+                    continue
+                dst = torch.empty_like(loc)
+                _lib.call('rvk_joint_loss_backward', _p(loc), _p(g), term, w, _p(dst), loc.numel(), _stream())
+                grads.append(dst)
+        return (*grads, None, None, None, None, None, None, None)
+
+
+# --------------------------------------------------------------------------------------------- encoder
+class EncoderState:
+    """Per-module cache for the trunk: bf16 weight buffer, inference workspace, pointer tables."""
+
+    def __init__(self):
+        self.wbuf = None
+        self.wkey = None
+        self.infer_ws = None
+        self.infer_key = None
+
+    def param_table(self, tensors):
+        return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+    def weights(self, params, training: bool, device):
+        key = (training, tuple(p.data_ptr() for p in params), tuple(p._version for p in params))
+        if self.wbuf is None or self.wkey != key:
+            lib = _lib.load()
+            nbytes = lib.rvk_encoder_weight_bytes(int(training))
+            if self.wbuf is None or self.wbuf.numel() != nbytes or self.wbuf.device != device:
+                self.wbuf = torch.empty(nbytes, device=device, dtype=torch.uint8)
+            _lib.call('rvk_encoder_prepare_weights', self.param_table(params), _p(self.wbuf), int(training), _stream())
+            self.wkey = key
+        return self.wbuf
+
+    def inference_workspace(self, batch: int, chunk: int, device):
+        key = (batch, chunk, device)
+        if self.infer_ws is None or self.infer_key != key:
+            nbytes = _lib.load().rvk_encoder_workspace_bytes(batch, 0, chunk)
+            self.infer_ws = torch.empty(nbytes, device=device, dtype=torch.uint8)
+            self.infer_key = key
+        return self.infer_ws
+
+
+class EncoderFn(torch.autograd.Function):
+    """DeiT-Tiny trunk forward/backward (replaces timm's VisionTransformer.forward that
+    reference models/backbone.py:23-25 calls).  `params`: the 150 trunk tensors in timm order."""
+
+    @staticmethod
+    @custom_fwd(device_type='cuda', cast_inputs=torch.float32)
+    def forward(ctx, state, images, *params):
+        require_cuda(images, 'DeiTTinyBackbone.forward')
+        if images.dim() != 4 or tuple(images.shape[1:]) != (3, 224, 224):
+            raise ValueError(f'expected images of shape (B, 3, 224, 224), got {tuple(images.shape)}')
+        for p in params:
+            require_cuda(p, 'DeiTTinyBackbone parameters')
+        img = _f32c(images)
+        batch = img.shape[0]
+        dev = img.device
+        training = any(ctx.needs_input_grad[2:])
+        chunk = CHUNK_IMAGES
+        feats = torch.empty(batch, 192, device=dev, dtype=torch.float32)
+        pc = [p.detach() for p in params]
+        with torch.cuda.device(dev):
+            wbuf = state.weights(pc, training, dev)
+            if training:
+                nbytes = _lib.load().rvk_encoder_workspace_bytes(batch, 1, chunk)
+                ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
+            else:
+                ws = state.inference_workspace(batch, chunk, dev)
+            _lib.call('rvk_encoder_forward', state.param_table(pc), _p(wbuf), _p(img), batch, int(training), chunk,
+                      _p(ws), _p(feats), _stream())
+        if training:
+            ctx.state, ctx.ws, ctx.wbuf, ctx.batch, ctx.chunk = state, ws, wbuf, batch, chunk
+            ctx.params = pc
+        return feats
+
+    @staticmethod
+    @custom_bwd(device_type='cuda')
+    def backward(ctx, dfeat):
+        g = _f32c(dfeat)
+        params = ctx.params
+        sizes = [p.numel() for p in params]
+        flat = torch.zeros(sum(sizes), device=g.device, dtype=torch.float32)
+        views, off = [], 0
+        for p, n in zip(params, sizes):
+            views.append(flat[off:off + n].view(p.shape))
+            off += n
+        with torch.cuda.device(g.device):
+            _lib.call('rvk_encoder_backward', ctx.state.param_table(params), _p(ctx.wbuf), _p(ctx.ws), _p(g), ctx.batch,
+                      ctx.chunk, ctx.state.param_table(views), _stream())
+        ctx.ws = None
+        return (None, None, *views)
