@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""Benchmark of the RoViT-KAN hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode infer|train] [--batch B] [--impl ours|reference]
+
+Default = BASELINE.json configs[1]: RoViT-KAN inference, batch 1024 per GPU, bf16 tensor-core trunk, all four
+heads (KAN severity enabled), random-init weights, synthetic 224x224 images.  A "step" is one forward pass
+of the whole model over one batch.  With --gpus N > 1 (launched by torch.distributed.run) every rank runs its
+own batch: the path is data parallel with no data-path collective in inference ("scaling": "weak"); in
+--mode train ranks all-reduce the flat gradient once per step over NCCL.
+
+Timing: W untimed steps, then K steps bracketed by barrier + cuda synchronize, CUDA events on the launch
+stream, max over ranks.  The 1024-image input (616 MB fp32) and every inter-kernel tensor set exceed the
+126 MB L2, so no L2 flush is needed between iterations ("l2": "inputs larger than L2").
+
+One JSON line is printed by rank 0; see the task contract for the keys.  `roofline` describes the dominant
+kernel (the tcgen05 GEMM family: 49 launches per 192-image chunk); its per-launch device time is measured
+in-situ with CUDA events by librovitkan (rvk_gemm_timing_*) in K extra steps after the timed region.
+`cpu_baseline` / `--impl reference` time the reference's CPU algorithm (oracle port incl. the reference's
+per-(input,output) Python loop in the KAN, models/kan.py:85-89) on the host cores, batch 32 per step.
+"""
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FWD_FLOP_PER_IMG = 2.507e9          # 1253.7 M MAC per image, forward
+TRAIN_FLOP_PER_IMG = 7.52e9
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {'hbm_gbs': d['hbm_gbs'], 'tflops_sustained': d['bf16_tflops_sustained'], 'tflops_burst': d['bf16_tflops'],
+                'source': 'measured'}
+    return {'hbm_gbs': 6650.0, 'tflops_sustained': 1400.0, 'tflops_burst': 1590.0, 'source': 'fallback'}
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference(steps, warmup, batch=32, quiet=False):
+    """Reference algorithm on the host cores: oracle port with the reference's KAN double loop."""
+    import torch
+    from oracle import model as omodel
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = omodel.random_state_dict(0)
+    x = torch.randn(batch, 3, 224, 224, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        for _ in range(warmup):
+            omodel.forward(sd, x, stage=4, kan_loop=True)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            omodel.forward(sd, x, stage=4, kan_loop=True)
+        dt = time.perf_counter() - t0
+    return {'value': batch * steps / dt, 'unit': 'images/sec', 'cores': cores, 'kind': 'port',
+            'sample': f'{steps} eval forwards of batch {batch} (fp32, stage 4, KAN via the reference\'s per-(input,output) '
+                      f'loop) after {warmup} warm-up; {dt:.1f} s of CPU work', 'ms_per_step': dt / steps * 1e3}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    r = cpu_reference(steps, warmup)
+    line = {'impl': 'reference', 'metric': 'images/sec (224^2) RoViT-KAN eval forward, reference CPU path', 'value': r['value'],
+            'unit': 'images/sec', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': r['ms_per_step'],
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
+            'config': {'workload': 'RoViT-KAN eval forward, all four heads, batch 32 per step on host cores (bounded '
+                                   'sample of the inference workload)', 'batch': 32},
+            'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+            'e2e': {'value': r['value'], 'unit': 'images/sec', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from rovitkan_b200 import _lib
+    from rovitkan_b200.models import RoViTKAN
+    from rovitkan_b200.training.losses import JointLoss
+
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    lib = _lib.load()
+    train = args.mode == 'train'
+    batch = args.batch or (256 if train else 1024)
+    K, W = args.steps, max(3, args.warmup)
+
+    torch.manual_seed(0)
+    model = RoViTKAN(pretrained=False).to(dev)
+    g = torch.Generator().manual_seed(1000 + rank)
+    host_images = torch.randn(batch, 3, 224, 224, generator=g).pin_memory()
+    labels = torch.randint(0, 4, (batch,), generator=g)
+    images = host_images.to(dev)
+    yd = labels.to(dev)
+
+    if train:
+        model.train()
+        loss_fn = JointLoss(focal_alpha=torch.ones(4))
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-4, fused=True)
+        params = [p for p in model.parameters()]
+
+        def step(x):
+            out = model(x)
+            loss = loss_fn(out, yd, yd, 4)['total_loss']
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            if world > 1:
+                from rovitkan_b200.dist import all_reduce_gradients
+                all_reduce_gradients(params, world)
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
+            opt.step()
+            return loss
+    else:
+        model.eval()
+
+        def step(x):
+            with torch.no_grad():
+                return model(x)['kan_severity']
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    for _ in range(W):
+        step(images)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = lib.rvk_launch_count()
+    ms_total = timed(lambda: step(images), K)
+    launches = lib.rvk_launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    value = batch * world * K / (ms_total / 1e3)
+
+    # end-to-end through the public API: pinned host -> device copy of the batch and device -> host read of
+    # the result inside the timed region, every step
+    def e2e_step():
+        x = host_images.to(dev, non_blocking=True)
+        r = step(x)
+        return r.float().cpu()
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, K)
+    e2e_value = batch * world * K / (ms_e2e / 1e3)
+    d2h = 4 if train else batch * 4
+
+    # in-situ device time of the dominant kernel family (tcgen05 GEMMs), K more steps
+    lib.rvk_gemm_timing_enable(1)
+    torch.cuda.synchronize()
+    for _ in range(K):
+        step(images)
+    torch.cuda.synchronize()
+    t_ms, t_fl = ctypes.c_double(0), ctypes.c_double(0)
+    n_gemm = lib.rvk_gemm_timing_collect(ctypes.byref(t_ms), ctypes.byref(t_fl))
+    lib.rvk_gemm_timing_enable(0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    gemm_tflops = (t_fl.value / (t_ms.value * 1e-3) / 1e12) if t_ms.value > 0 else 0.0
+    flop_img = TRAIN_FLOP_PER_IMG if train else FWD_FLOP_PER_IMG
+    line = {
+        'metric': 'images/sec (224^2, device-timed) RoViT-KAN ' + ('train step' if train else 'inference forward'),
+        'value': value, 'unit': 'images/sec', 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_total / K,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+        'config': {'workload': ('RoViT-KAN curriculum stage-4 training step (all losses, AdamW), batch %d/GPU' % batch) if train
+                   else 'RoViT-KAN inference, batch %d per GPU, bf16 tensor-core trunk, all four heads (KAN severity enabled)' % batch,
+                   'batch_per_gpu': batch, 'global_batch': batch * world, 'image': '3x224x224', 'chunk_images': 192,
+                   'parallelism': f'dp{world}', 'l2': 'inputs larger than L2 (616 MB per batch), no flush needed',
+                   'weights': 'random init (timm init laws), seed 0'},
+        'e2e': {'value': e2e_value, 'unit': 'images/sec', 'h2d_bytes_per_step': host_images.numel() * 4,
+                'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / K},
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+        'roofline': {'bound': 'tensor', 'achieved': gemm_tflops, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
+                     'frac': gemm_tflops / pk['tflops_sustained'], 'traffic': None,
+                     'kernel': 'gemm_nt_kernel / gemm_tn_kernel (tcgen05, all launches)', 'launches_timed': int(n_gemm),
+                     'gemm_ms_per_step': t_ms.value / K, 'peak_source': pk['source'] + ' sustained bf16',
+                     'whole_step_tflops': value / world * flop_img / 1e12,
+                     'whole_step_frac': value / world * flop_img / 1e12 / pk['tflops_sustained']},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference(steps=2, warmup=1)
+        line['cpu_baseline'] = {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--mode', default='infer', choices=['infer', 'train'])
+    ap.add_argument('--batch', type=int, default=0)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == '__main__':
+    main()

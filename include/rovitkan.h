@@ -27,6 +27,15 @@ const char* rvk_strerror(int status);
 const char* rvk_last_error(void);            /* detail of the last failure on the calling thread */
 int rvk_device_check(void);                  /* 0 iff the current device is compute capability 10.x */
 
+/* ---- measurement hooks (bench.py) -------------------------------------------------------------------
+ * rvk_launch_count: kernels this library has launched in this process so far.
+ * rvk_gemm_timing_enable(1): bracket every tensor-core GEMM launch with CUDA events on its own stream;
+ * rvk_gemm_timing_collect (after a stream sync) returns the launch count and sums their device time and
+ * algorithmic FLOPs (2*M*N*K) since the previous collect. */
+int64_t rvk_launch_count(void);
+void rvk_gemm_timing_enable(int on);
+int rvk_gemm_timing_collect(double* total_ms_host, double* total_flops_host);
+
 /* ---- KAN severity path ----------------------------------------------------------------------------
  * Replaces KANLayer.forward (models/kan.py:70-95) incl. BSplineBasis.compute_basis (:10-44), and the
  * inter-layer ReLU / final 3*sigmoid of KANSeverityModule.forward (:138-149) through `act`

@@ -136,13 +136,11 @@ def layer_forward_loop(x: torch.Tensor, spline_weights: torch.Tensor,
     baseline times."""
     n_in, n_out, _ = spline_weights.shape
     basis = basis_literal(torch.tanh(x), knots, degree)
-    cols = [torch.zeros(x.shape[0], dtype=torch.float32, device=x.device)
-            for _ in range(n_out)]
+    spline = torch.zeros(x.shape[0], n_out, dtype=torch.float32, device=x.device)
     for i in range(n_in):
-        b_i = basis[:, i, :]
         for o in range(n_out):
-            cols[o] = cols[o] + (b_i * spline_weights[i, o]).sum(dim=1)
-    spline = torch.stack(cols, dim=1)
+            # same op sequence per pair as the reference: slice, multiply, reduce, in-place column add
+            spline[:, o] += (basis[:, i, :] * spline_weights[i, o]).sum(dim=1)
     return torch.nn.functional.linear(x, lin_weight, lin_bias) + spline
 
 

@@ -20,6 +20,9 @@ SIGNATURES = {
     'rvk_strerror': (C.c_char_p, [_I]),
     'rvk_last_error': (C.c_char_p, []),
     'rvk_device_check': (_I, []),
+    'rvk_launch_count': (_L, []),
+    'rvk_gemm_timing_enable': (None, [_I]),
+    'rvk_gemm_timing_collect': (_I, [_P, _P]),
     'rvk_kan_layer_workspace_floats': (_L, [_I, _I, _I]),
     'rvk_kan_basis': (_I, [_P, _P, _I, _L, _P, _P]),
     'rvk_kan_layer_forward': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P]),

@@ -5,6 +5,9 @@
 #include "kernels.h"
 
 const char* rvk_last_error_cstr();
+long long rvk_launch_count_impl();
+void rvk_gemm_timing_enable_impl(int on);
+int rvk_gemm_timing_collect_impl(double* total_ms, double* total_flops);
 
 namespace {
 inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
@@ -47,6 +50,12 @@ int rvk_device_check(void) {
   int major = 0;
   RVK_CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
   return major == 10 ? RVK_OK : RVK_ERR_UNSUPPORTED_SHAPE;
+}
+
+int64_t rvk_launch_count(void) { return rvk_launch_count_impl(); }
+void rvk_gemm_timing_enable(int on) { rvk_gemm_timing_enable_impl(on); }
+int rvk_gemm_timing_collect(double* total_ms_host, double* total_flops_host) {
+  return rvk_gemm_timing_collect_impl(total_ms_host, total_flops_host);
 }
 
 // ---- KAN

@@ -38,8 +38,10 @@ enum RvkStatus : int {
   } while (0)
 
 void rvk_set_last_cuda_error(int code, const char* what);
+void rvk_count_launch();   // every kernel launch of this library is counted (bench.py reports it)
 
 static inline int rvk_launch_check() {
+  rvk_count_launch();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     rvk_set_last_cuda_error((int)e, "kernel launch");

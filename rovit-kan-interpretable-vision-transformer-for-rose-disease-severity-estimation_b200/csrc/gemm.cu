@@ -2,7 +2,39 @@
 #include "kernels.h"
 #include "tma_host.h"
 
+#include <vector>
+
 namespace {
+
+// ---- optional in-situ timing of the tensor-core GEMM launches (bench.py roofline) -------------------
+struct TimedLaunch { cudaEvent_t beg, end; double flops; };
+bool g_timing = false;
+std::vector<TimedLaunch> g_timed;
+std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_event_pool;
+
+struct ScopedTimer {
+  cudaStream_t s;
+  bool on;
+  TimedLaunch t{};
+  ScopedTimer(cudaStream_t stream, double flops) : s(stream), on(g_timing) {
+    if (!on) return;
+    if (g_event_pool.empty()) {
+      cudaEventCreate(&t.beg);
+      cudaEventCreate(&t.end);
+    } else {
+      t.beg = g_event_pool.back().first;
+      t.end = g_event_pool.back().second;
+      g_event_pool.pop_back();
+    }
+    t.flops = flops;
+    cudaEventRecord(t.beg, s);
+  }
+  ~ScopedTimer() {
+    if (!on) return;
+    cudaEventRecord(t.end, s);
+    g_timed.push_back(t);
+  }
+};
 
 constexpr int kBN = 192;       // every N on this path (192, 576, 768) is a multiple of 192
 constexpr int kNtStages = 4;
@@ -39,6 +71,7 @@ int launch_nt(const GemmNtArgs& a, cudaStream_t stream) {
   }
   const int tiles = ((p.M + 127) / 128) * (p.N / kBN);
   const int grid = tiles < kNumSMsB200 ? tiles : kNumSMsB200;
+  ScopedTimer timer(stream, 2.0 * p.M * p.N * p.K);
   kernel<<<grid, kGemmThreads, L::kTotal, stream>>>(tmA, tmB, tmOut, tmOut2, tmAux, p);
   return rvk_launch_check();
 }
@@ -90,6 +123,25 @@ int rvk_gemm_tn_launch(const void* A, int64_t lda, const void* B, int64_t ldb, f
   p.C = C;
   p.scale = scale;
   splits = (total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
+  ScopedTimer timer(stream, 2.0 * M * P * Q);
   kernel<<<dim3(tiles, splits), kTnThreads, L::kTotal, stream>>>(tmA, tmB, p);
   return rvk_launch_check();
+}
+
+void rvk_gemm_timing_enable_impl(int on) { g_timing = on != 0; }
+
+// Sums the device time of every GEMM launch recorded since the last collect (caller must have
+// synchronised the stream).  Returns the number of launches.
+int rvk_gemm_timing_collect_impl(double* total_ms, double* total_flops) {
+  double ms = 0.0, fl = 0.0;
+  int n = 0;
+  for (auto& t : g_timed) {
+    float e = 0.0f;
+    if (cudaEventElapsedTime(&e, t.beg, t.end) == cudaSuccess) { ms += e; fl += t.flops; ++n; }
+    g_event_pool.emplace_back(t.beg, t.end);
+  }
+  g_timed.clear();
+  if (total_ms) *total_ms = ms;
+  if (total_flops) *total_flops = fl;
+  return n;
 }

@@ -1,5 +1,6 @@
 #include "tma_host.h"
 
+#include <atomic>
 #include <mutex>
 #include <string>
 
@@ -22,6 +23,7 @@ void resolve_encode() {
 }
 
 thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
 
 }  // namespace
 
@@ -29,6 +31,8 @@ void rvk_set_last_cuda_error(int code, const char* what) {
   g_last_error = std::string(what) + ": " + cudaGetErrorString(static_cast<cudaError_t>(code));
 }
 const char* rvk_last_error_cstr() { return g_last_error.c_str(); }
+void rvk_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long rvk_launch_count_impl() { return g_launches.load(std::memory_order_relaxed); }
 
 int rvk_make_tmap_2d(CUtensorMap* out, const void* base, int dtype, int64_t rows, int64_t cols, int64_t ld,
                      int box_rows, int box_cols) {

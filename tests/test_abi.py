@@ -1,0 +1,99 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/rovitkan.h declares, the ctypes binding covers the same set, and the product path refuses
+to run without CUDA (no silent fallback).  No compute calls are made here."""
+
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'rovitkan.h')
+
+
+def declared_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(rvk_[a-z0-9_]+)\s*\(', text)))
+
+
+@pytest.fixture(scope='module')
+def lib_path():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    ge.build()
+    from rovitkan_b200 import _lib
+    return _lib.LIB_PATH
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f'{n} declared in rovitkan.h but not exported by librovitkan.so'
+
+
+def test_binding_covers_header(lib_path):
+    from rovitkan_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == declared_symbols()
+    lib = _lib.load()
+    assert lib.rvk_abi_version() == 1
+    assert b'ok' == lib.rvk_strerror(0)
+    assert lib.rvk_kan_layer_workspace_floats(192, 64, 0) == 192 * 8 * 64
+    assert lib.rvk_encoder_workspace_bytes(0, 0, 0) == 0
+    assert lib.rvk_encoder_weight_bytes(1) > lib.rvk_encoder_weight_bytes(0) > 5_400_000 * 2
+
+
+def test_only_c_symbols_are_exported(lib_path):
+    out = subprocess.run(['nm', '-D', '--defined-only', lib_path], capture_output=True, text=True).stdout
+    exported = [l.split()[-1] for l in out.splitlines() if ' T ' in l]
+    assert exported and all(s.startswith('rvk_') for s in exported), exported
+
+
+def test_sass_contains_blackwell_tensor_and_tma_instructions(lib_path):
+    out = subprocess.run(['cuobjdump', '-sass', lib_path], capture_output=True, text=True).stdout
+    for mnemonic in ('UTCHMMA', 'UTMALDG', 'UTMASTG', 'LDTM'):
+        assert mnemonic in out, f'{mnemonic} missing from SASS: not a tcgen05/TMA build'
+
+
+def test_module_mirror_matches_reference_layout_and_rejects_cpu():
+    from rovitkan_b200.models import KANLayer, RoViTKAN
+    m = RoViTKAN(pretrained=False)
+    want = [l.split(' ', 1) for l in open(os.path.join(ROOT, 'tests', 'golden', 'state_dict_keys.txt')).read().splitlines()]
+    sd = m.state_dict()
+    assert list(sd) == [k for k, _ in want]
+    assert all(str(tuple(sd[k].shape)) == s for k, s in want)
+    assert m.count_parameters()['total'] == 5706394
+    assert RoViTKAN(embed_dim=192, pretrained=False).classification_head.fc1.in_features == 192   # scripts/train.py:88
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        m(torch.randn(1, 3, 224, 224))
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        KANLayer(8, 4)(torch.randn(2, 8))
+    with pytest.raises(NotImplementedError):
+        KANLayer(8, 4, num_knots=7)
+
+
+def test_reference_config_object_is_accepted():
+    class _NS:
+        pass
+    cfg = _NS(); cfg.model = _NS(); cfg.data = _NS()
+    cfg.model.embed_dim, cfg.model.hidden_dim, cfg.model.kan_layers = 192, 128, [192, 64, 16, 1]
+    cfg.model.kan_num_knots, cfg.model.kan_degree, cfg.model.dropout, cfg.model.pretrained = 5, 3, 0.3, False
+    cfg.data.num_classes = 4
+    from rovitkan_b200.models import RoViTKAN
+    m = RoViTKAN(cfg)
+    assert m.kan_module.layers_dims == [192, 64, 16, 1] and m.curriculum_stage == 4
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'rovit-kan-interpretable-vision-transformer-for-rose-disease-severity-estimation_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), os.path.join(dirpath, f)

@@ -1,0 +1,51 @@
+"""world_size-2 gloo test (CPU) of the data-parallel gradient all-reduce helper."""
+
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from rovitkan_b200.dist import _contiguous_run, all_reduce_gradients
+    torch.manual_seed(0)
+    # 150 "trunk" params whose grads are views of one flat buffer + 5 separately allocated "head" params
+    shapes = [(3, 4), (7,), (2, 5, 2)] * 50
+    params = [torch.nn.Parameter(torch.zeros(s)) for s in shapes] + [torch.nn.Parameter(torch.zeros(6, 3)) for _ in range(5)]
+    flat = torch.zeros(sum(p.numel() for p in params[:150]))
+    off = 0
+    for p in params[:150]:
+        p.grad = flat[off:off + p.numel()].view(p.shape)
+        off += p.numel()
+    for p in params[150:]:
+        p.grad = torch.zeros_like(p)
+    for i, p in enumerate(params):
+        p.grad.fill_(float((rank + 1) * (i + 1)))
+    assert _contiguous_run([p.grad for p in params[:150]])
+    calls = all_reduce_gradients(params, world)
+    want = [(1 + 2) / 2 * (i + 1) for i in range(len(params))]
+    ok = all(torch.allclose(p.grad, torch.full_like(p.grad, w)) for p, w in zip(params, want))
+    q.put((rank, ok, calls))
+    dist.destroy_process_group()
+
+
+def test_all_reduce_gradients_world2_gloo():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+    assert all(calls == 2 for _, _, calls in res), res      # one flat trunk reduce + one coalesced heads reduce

@@ -1,0 +1,193 @@
+"""GPU parity of the KAN, MLP-head and joint-loss kernels through the nn.Module mirror of the
+reference API, against (a) golden vectors produced by the reference's own modules
+(tests/golden/*.npz) and (b) the CPU oracle on larger seeded inputs.  fp32 path: tolerance
+|a-b| <= 1e-3*|b| + atol, the north_star's fp32 bound."""
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import T, assert_close, load_golden
+from oracle import heads as oheads
+from oracle import kan as okan
+from oracle import losses as olosses
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from rovitkan_b200.models.heads import ClassificationHead, OrdinalHead, UncertaintyHead
+    from rovitkan_b200.models.kan import BSplineBasis, KANLayer, KANSeverityModule
+    from rovitkan_b200.training.losses import JointLoss
+
+DEV = 'cuda'
+
+
+def test_basis_matches_reference_vectors():
+    g = load_golden('kan_basis.npz')
+    got = BSplineBasis.compute_basis(T(g['t']).to(DEV), T(g['knots']).to(DEV), 3)
+    assert_close(got, T(g['basis']), rtol=0, atol=2e-6, what='compute_basis')
+
+
+def _load_layer(g, tag, n_in, n_out):
+    layer = KANLayer(n_in, n_out).to(DEV)
+    with torch.no_grad():
+        layer.spline_weights.copy_(T(g[f'{tag}_sw']))
+        layer.linear.weight.copy_(T(g[f'{tag}_lw']))
+        layer.linear.bias.copy_(T(g[f'{tag}_lb']))
+    return layer
+
+
+@pytest.mark.parametrize('tag,n_in,n_out', [('l0', 192, 64), ('l1', 64, 16), ('l2', 16, 1), ('odd', 10, 3)])
+def test_kan_layer_matches_reference(tag, n_in, n_out):
+    g = load_golden('kan_layers.npz')
+    layer = _load_layer(g, tag, n_in, n_out)
+    x = T(g[f'{tag}_x']).to(DEV).requires_grad_(True)
+    y = layer(x)
+    assert_close(y, T(g[f'{tag}_y']), rtol=1e-3, atol=1e-5, what='y')
+    y.backward(T(g[f'{tag}_gy']).to(DEV))
+    assert_close(x.grad, T(g[f'{tag}_dx']), rtol=1e-3, atol=2e-5, what='dx')
+    assert_close(layer.spline_weights.grad, T(g[f'{tag}_dsw']), rtol=1e-3, atol=2e-5, what='dW')
+    assert_close(layer.linear.weight.grad, T(g[f'{tag}_dlw']), rtol=1e-3, atol=2e-5, what='dWl')
+    assert_close(layer.linear.bias.grad, T(g[f'{tag}_dlb']), rtol=1e-3, atol=2e-5, what='db')
+
+
+def test_kan_module_matches_reference():
+    g = load_golden('kan_layers.npz')
+    mod = KANSeverityModule([192, 64, 16, 1]).to(DEV)
+    with torch.no_grad():
+        for i, l in enumerate(mod.kan_layers):
+            l.spline_weights.copy_(T(g[f'mod_sw{i}']))
+            l.linear.weight.copy_(T(g[f'mod_lw{i}']))
+            l.linear.bias.copy_(T(g[f'mod_lb{i}']))
+    x = T(g['mod_x']).to(DEV).requires_grad_(True)
+    traj = mod.get_activation_trajectory(x)
+    for i, a in enumerate(traj):
+        assert_close(a, T(g[f'mod_traj{i}']), rtol=1e-3, atol=1e-5, what=f'trajectory {i}')
+    y = mod(x)
+    y.backward(T(g['mod_gy']).to(DEV))
+    assert_close(x.grad, T(g['mod_dx']), rtol=1e-3, atol=2e-5, what='dx')
+    for i, l in enumerate(mod.kan_layers):
+        assert_close(l.spline_weights.grad, T(g[f'mod_dsw{i}']), rtol=1e-3, atol=2e-5, what=f'dW{i}')
+        assert_close(l.linear.weight.grad, T(g[f'mod_dlw{i}']), rtol=1e-3, atol=2e-5, what=f'dWl{i}')
+        assert_close(l.linear.bias.grad, T(g[f'mod_dlb{i}']), rtol=1e-3, atol=2e-5, what=f'db{i}')
+    assert mod.count_parameters() == 106705
+
+
+@pytest.mark.parametrize('batch,dims', [(1, [192, 64, 16, 1]), (1000, [192, 64, 1]), (4099, [192, 64, 16, 1])])
+def test_kan_module_vs_oracle_large(batch, dims):
+    torch.manual_seed(5)
+    mod = KANSeverityModule(dims).to(DEV)
+    x = (torch.randn(batch, dims[0]) * 1.3)
+    gy = torch.randn(batch, 1)
+    xg = x.to(DEV).requires_grad_(True)
+    y = mod(xg)
+    y.backward(gy.to(DEV))
+    layers = [tuple(p.detach().cpu().clone().requires_grad_(True) for p in (l.spline_weights, l.linear.weight, l.linear.bias))
+              for l in mod.kan_layers]
+    xc = x.clone().requires_grad_(True)
+    yr = okan.severity_forward(xc, layers, okan.make_knots())
+    yr.backward(gy)
+    assert_close(y, yr, rtol=1e-3, atol=2e-5, what='y')
+    assert_close(xg.grad, xc.grad, rtol=1e-3, atol=1e-5, scale_tol=1e-4, what='dx')
+    for i, (l, (sw, lw, lb)) in enumerate(zip(mod.kan_layers, layers)):
+        assert_close(l.spline_weights.grad, sw.grad, rtol=1e-3, atol=1e-5, scale_tol=2e-4, what=f'dW{i}')
+        assert_close(l.linear.weight.grad, lw.grad, rtol=1e-3, atol=1e-5, scale_tol=2e-4, what=f'dWl{i}')
+        assert_close(l.linear.bias.grad, lb.grad, rtol=1e-3, atol=1e-5, scale_tol=2e-4, what=f'db{i}')
+
+
+def test_kan_dead_zone_property():
+    """For every input with tanh(x) >= knots[7] the spline branch is exactly zero, so the layer
+    reduces to its linear branch -- a size-independent property checked at the microbenchmark batch."""
+    torch.manual_seed(6)
+    layer = KANLayer(192, 64).to(DEV)
+    x = torch.rand(65536, 192, device=DEV) * 3 + 0.45          # tanh(x) > 0.42 > knots[7]
+    y = layer(x)
+    ref = torch.nn.functional.linear(x.double(), layer.linear.weight.double(), layer.linear.bias.double())
+    assert_close(y, ref.float(), rtol=1e-4, atol=1e-4, what='dead-zone == linear branch')
+
+
+def test_heads_match_reference():
+    g = load_golden('heads.npz')
+    ch, oh, uh = (ClassificationHead(192, 128, 4, dropout=0.0).to(DEV), OrdinalHead(192, 128, 4, dropout=0.0).to(DEV),
+                  UncertaintyHead(192, 128, dropout=0.0).to(DEV))
+    for name, m in (('cls', ch), ('ord', oh), ('unc', uh)):
+        m.train()
+        with torch.no_grad():
+            for k, p in m.named_parameters():
+                p.copy_(T(g[f'{name}.{k}']))
+    x = T(g['x']).to(DEV).requires_grad_(True)
+    cls, ordl = ch(x), oh(x)
+    mu, lv = uh(x)
+    for got, key in ((cls, 'cls'), (ordl, 'ord'), (mu, 'mu'), (lv, 'lv')):
+        assert_close(got, T(g[key]), rtol=1e-3, atol=1e-5, what=key)
+    assert_close(oh.predict_probabilities(x), T(g['ord_probs']), rtol=1e-3, atol=1e-5, what='ordinal probs')
+    assert_close(oh.predict_severity(x), T(g['ord_sev']), rtol=1e-3, atol=1e-5, what='ordinal severity')
+    loss = ((cls * T(g['g_cls']).to(DEV)).sum() + (ordl * T(g['g_ord']).to(DEV)).sum() +
+            (mu * T(g['g_mu']).to(DEV)).sum() + (lv * T(g['g_lv']).to(DEV)).sum())
+    loss.backward()
+    assert_close(x.grad, T(g['dx']), rtol=1e-3, atol=1e-5, scale_tol=1e-5, what='dx')
+    for name, m in (('cls', ch), ('ord', oh), ('unc', uh)):
+        for k, p in m.named_parameters():
+            assert_close(p.grad, T(g[f'{name}.{k}.grad']), rtol=1e-3, atol=1e-5, scale_tol=1e-5, what=f'{name}.{k}')
+
+
+def test_dropout_statistics_and_eval_identity():
+    torch.manual_seed(7)
+    head = ClassificationHead(192, 128, 4, dropout=0.3).to(DEV)
+    x = torch.randn(4096, 192, device=DEV)
+    head.eval()
+    a, b = head(x), head(x)
+    assert torch.equal(a, b)
+    head.train()
+    h = head._hidden(x)
+    h_eval = torch.relu(torch.nn.functional.linear(x, head.fc1.weight, head.fc1.bias))
+    active = h_eval > 0
+    kept = (h != 0) & active
+    frac = kept.sum().item() / active.sum().item()
+    assert abs(frac - 0.7) < 0.01, frac                                   # keep probability 1-p
+    assert_close(h[kept], h_eval[kept] / 0.7, rtol=1e-5, atol=1e-6, what='inverted-dropout scale')
+    torch.manual_seed(8)
+    h1 = head._hidden(x)
+    torch.manual_seed(8)
+    h2 = head._hidden(x)
+    assert torch.equal(h1, h2)                                            # torch.manual_seed controls the mask
+
+
+@pytest.mark.parametrize('stage', [1, 2, 3, 4])
+def test_losses_match_reference(stage):
+    g = load_golden('losses.npz')
+    names = ['cls_logits', 'ordinal_logits', 'mu', 'log_var', 'kan_severity']
+    o = {k: T(g['in_' + k]).to(DEV).requires_grad_(True) for k in names}
+    loss = JointLoss(focal_alpha=T(g['alpha']))
+    r = loss(o, T(g['yc']).to(DEV), T(g['ys']).to(DEV), stage)
+    for k in ('cls_loss', 'ord_loss', 'unc_loss', 'kan_loss', 'total_loss'):
+        assert_close(r[k], T(g[f's{stage}_{k}']), rtol=1e-3, atol=1e-6, what=k)
+    r['total_loss'].backward()
+    for k in names:
+        got = o[k].grad if o[k].grad is not None else torch.zeros_like(o[k])
+        assert_close(got, T(g[f's{stage}_d_{k}']), rtol=1e-3, atol=1e-7, what='d' + k)
+
+
+def test_loss_known_answer_and_cutmix_blend():
+    o = {'cls_logits': torch.tensor([[2, .5, -1, 0], [.1, .2, .3, .4]], device=DEV),
+         'ordinal_logits': torch.tensor([[1., -1, -2], [.5, .5, -.5]], device=DEV),
+         'mu': torch.tensor([[.5], [2.5]], device=DEV), 'log_var': torch.tensor([[0.], [-1.]], device=DEV),
+         'kan_severity': torch.tensor([[.3], [2.]], device=DEV)}
+    y = torch.tensor([0, 3], device=DEV)
+    r = JointLoss(focal_alpha=None)(o, y, y, 4)
+    want = {'cls_loss': 0.328758, 'ord_loss': 0.612614, 'unc_loss': -0.017607, 'kan_loss': 0.545000,
+            'total_loss': 1.205068}
+    for k, v in want.items():
+        assert abs(float(r[k]) - v) < 2e-6, (k, float(r[k]))
+    # trainer.py:104-111 blend: lam*L(a) + (1-lam)*L(b) for every key, gradients through both calls
+    oo = {k: v.clone().requires_grad_(True) for k, v in o.items()}
+    ya, yb, lam = torch.tensor([0, 3], device=DEV), torch.tensor([2, 1], device=DEV), 0.7
+    loss = JointLoss()
+    la, lb = loss(oo, ya, y, 4), loss(oo, yb, y, 4)
+    tot = lam * la['total_loss'] + (1 - lam) * lb['total_loss']
+    tot.backward()
+    oc = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in o.items()}
+    ra, rb = olosses.joint(oc, ya.cpu(), y.cpu(), 4), olosses.joint(oc, yb.cpu(), y.cpu(), 4)
+    (lam * ra['total_loss'] + (1 - lam) * rb['total_loss']).backward()
+    for k in oo:
+        assert_close(oo[k].grad, oc[k].grad, rtol=1e-3, atol=1e-7, what='blend d' + k)

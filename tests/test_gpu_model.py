@@ -1,0 +1,243 @@
+"""GPU parity of the whole RoViT-KAN forward / loss / backward through the nn.Module mirror of the
+reference API.
+
+Checkers: (a) tests/golden/model_b2.npz -- outputs, losses and gradients of the REFERENCE's own
+RoViTKAN / JointLoss code (trunk = oracle restatement of timm) on the same seeded weights and images;
+(b) the fp32 oracle evaluated on the GPU box for larger batches; (c) size-independent properties at
+the benchmark batch (per-image results do not depend on batch size, chunking or position).
+
+Tolerances.  Heads/KAN/loss run in fp32 (1e-3 relative, see test_gpu_heads.py).  The trunk computes
+its GEMMs and attention with bf16 operands and fp32 accumulation; the fp32 residual stream sums 25
+such products, so trunk outputs are compared with the STATED bf16 tolerance
+    |a - b| <= BF16_RTOL*|b| + BF16_STOL*max|b|      (BF16_RTOL = BF16_STOL = 3e-2)
+and gradients with a relative L2 bound of GRAD_REL_L2 = 6e-2 per tensor.
+"""
+
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, T, assert_close, load_golden
+from oracle import losses as olosses
+from oracle import model as omodel
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from rovitkan_b200.models import RoViTKAN
+    from rovitkan_b200.training.losses import JointLoss
+
+DEV = 'cuda'
+BF16_RTOL = 3e-2
+BF16_STOL = 3e-2
+GRAD_REL_L2 = 6e-2
+
+
+def rel_l2(a, b):
+    a, b = a.detach().double().cpu().flatten(), b.detach().double().cpu().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def build_model(sd, dropout=0.0):
+    m = RoViTKAN(pretrained=False, dropout=dropout)
+    res = m.load_state_dict(sd, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    return m.to(DEV)
+
+
+@pytest.fixture(scope='module')
+def golden_setup():
+    g = load_golden('model_b2.npz')
+    sd = omodel.random_state_dict(int(g['seed']))
+    cs = sum(float(sd[k].double().abs().sum()) for k in sorted(sd))
+    if abs(cs - float(g['checksum'])) > 1e-6 * float(g['checksum']):
+        pytest.skip('torch RNG stream differs from the one the golden file was made with')
+    images = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(int(g['images_seed'])))
+    return g, sd, images
+
+
+def test_state_dict_keys_and_param_counts(golden_setup):
+    g, sd, _ = golden_setup
+    m = build_model(sd)
+    want = [l.split(' ', 1)[0] for l in open(os.path.join(GOLDEN, 'state_dict_keys.txt')).read().splitlines()]
+    assert list(m.state_dict().keys()) == want
+    c = m.count_parameters()
+    assert [c[k] for k in ('backbone', 'classification_head', 'ordinal_head', 'uncertainty_head', 'kan_module',
+                           'total')] == list(g['param_counts'])
+
+
+def test_forward_matches_reference(golden_setup):
+    g, sd, images = golden_setup
+    m = build_model(sd).eval()
+    with torch.no_grad():
+        o = m(images.to(DEV))
+        p = m.predict(images.to(DEV))
+    report = {}
+    for k in ('features', 'cls_logits', 'ordinal_logits', 'mu', 'log_var', 'kan_severity'):
+        report[k] = rel_l2(o[k], T(g['fwd_' + k]))
+        assert_close(o[k], T(g['fwd_' + k]), rtol=BF16_RTOL, atol=0, scale_tol=BF16_STOL, what=k)
+    print('forward rel-L2 vs reference:', {k: f'{v:.2e}' for k, v in report.items()})
+    # bit-exact class decision wherever the reference's own top-2 margin exceeds the bf16 tolerance
+    ref_logits = T(g['fwd_cls_logits'])
+    top2 = ref_logits.topk(2, dim=1).values
+    margin = top2[:, 0] - top2[:, 1]
+    decided = margin > 2 * BF16_STOL * float(ref_logits.abs().max())
+    assert torch.equal(p['class'].cpu()[decided], T(g['pred_class'])[decided])
+    for k in ('class_probs', 'ordinal_probs', 'ordinal_severity', 'uncertainty_mu', 'uncertainty_std', 'kan_severity'):
+        assert_close(p[k], T(g['pred_' + k]), rtol=BF16_RTOL, atol=0, scale_tol=BF16_STOL, what='predict.' + k)
+
+
+def test_heads_exact_given_reference_features(golden_setup):
+    """With the reference's own features as input the fp32 heads/KAN reproduce the reference outputs to
+    1e-3 relative, and argmax / ordinal decisions bit-exactly."""
+    g, sd, _ = golden_setup
+    m = build_model(sd).eval()
+    f = T(g['fwd_features']).to(DEV)
+    with torch.no_grad():
+        cls = m.classification_head(f)
+        ordl = m.ordinal_head(f)
+        mu, lv = m.uncertainty_head(f)
+        kan = m.kan_module(f)
+    for got, k in ((cls, 'cls_logits'), (ordl, 'ordinal_logits'), (mu, 'mu'), (lv, 'log_var'), (kan, 'kan_severity')):
+        assert_close(got, T(g['fwd_' + k]), rtol=1e-3, atol=1e-5, what=k)
+    assert torch.equal(cls.argmax(1).cpu(), T(g['pred_class']))
+    assert torch.equal((ordl > 0).sum(1).cpu(), (T(g['fwd_ordinal_logits']) > 0).sum(1))
+    assert torch.equal(m.ordinal_head.probabilities_from_logits(ordl).argmax(1).cpu(), T(g['pred_ordinal_probs']).argmax(1))
+
+
+def test_loss_and_gradients_match_reference(golden_setup):
+    g, sd, images = golden_setup
+    m = build_model(sd).train()
+    y = torch.tensor([1, 3], device=DEV)
+    o = m(images.to(DEV))
+    r = JointLoss(focal_alpha=None)(o, y, y, 4)
+    for k in ('cls_loss', 'ord_loss', 'unc_loss', 'kan_loss', 'total_loss'):
+        assert_close(r[k], T(g['loss_' + k]), rtol=BF16_RTOL, atol=2e-3, what=k)
+    r['total_loss'].backward()
+    named = dict(m.named_parameters())
+    report = {}
+    for k in g.files:
+        if not k.startswith('grad_'):
+            continue
+        got = named[k[5:]].grad
+        assert got is not None, k
+        report[k[5:]] = rel_l2(got, T(g[k]))
+    print('gradient rel-L2 vs reference:', {k: f'{v:.2e}' for k, v in report.items()})
+    bad = {k: v for k, v in report.items() if not v < GRAD_REL_L2}
+    assert not bad, bad
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+
+
+@pytest.mark.parametrize('batch', [5, 33])
+def test_forward_backward_vs_oracle_on_device(batch):
+    """Same check against the fp32 oracle evaluated on the GPU box (TF32 off) for batches that are not
+    tile multiples."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sd = omodel.random_state_dict(3)
+    torch.manual_seed(4)
+    with torch.no_grad():      # non-trivial biases/affines so every term matters
+        for k, v in sd.items():
+            if k.startswith('backbone') and (k.endswith('bias') or 'norm' in k):
+                v.add_(torch.randn_like(v) * 0.05)
+    images = torch.randn(batch, 3, 224, 224)
+    yc = torch.randint(0, 4, (batch,))
+    m = build_model(sd).train()
+    o = m(images.to(DEV))
+    r = JointLoss()(o, yc.to(DEV), yc.to(DEV), 4)
+    r['total_loss'].backward()
+    sdd = {k: (v.to(DEV).requires_grad_(True) if not k.endswith('knots') else v.to(DEV)) for k, v in sd.items()}
+    oo = omodel.forward(sdd, images.to(DEV))
+    rr = olosses.joint(oo, yc.to(DEV), yc.to(DEV), 4)
+    rr['total_loss'].backward()
+    for k in ('features', 'cls_logits', 'ordinal_logits', 'mu', 'log_var', 'kan_severity'):
+        assert_close(o[k], oo[k], rtol=BF16_RTOL, atol=0, scale_tol=BF16_STOL, what=k)
+    assert_close(r['total_loss'], rr['total_loss'], rtol=BF16_RTOL, atol=2e-3, what='total_loss')
+    named = dict(m.named_parameters())
+    worst = max(((rel_l2(named[k].grad, sdd[k].grad), k) for k in named), key=lambda t: t[0])
+    print('worst gradient rel-L2 vs oracle:', worst)
+    assert worst[0] < GRAD_REL_L2, worst
+
+
+def test_batch_and_chunk_invariance_at_benchmark_size():
+    """Size-independent property at the headline size (B=1024): every image's result is independent of
+    the batch it travels in, so a 1024-image pass (6 L2-resident chunks) and a 70-image pass over a subset
+    must agree bit for bit."""
+    torch.manual_seed(0)
+    m = RoViTKAN(pretrained=False).to(DEV).eval()
+    images = torch.randn(1024, 3, 224, 224, device=DEV)
+    idx = torch.arange(3, 1024, 15, device=DEV)[:70]
+    with torch.no_grad():
+        big = m(images)
+        small = m(images[idx].contiguous())
+    for k in ('features', 'cls_logits', 'ordinal_logits', 'mu', 'log_var', 'kan_severity'):
+        assert torch.isfinite(big[k]).all()
+        assert torch.equal(big[k][idx], small[k]), k
+    assert float(big['kan_severity'].min()) >= 0.0 and float(big['kan_severity'].max()) <= 3.0
+    assert float(big['log_var'].abs().max()) <= 10.0
+
+
+def test_stage_gating_and_frozen_backbone():
+    torch.manual_seed(1)
+    m = RoViTKAN(pretrained=False, dropout=0.0).to(DEV).train()
+    x = torch.randn(3, 3, 224, 224, device=DEV)
+    y = torch.tensor([0, 1, 2], device=DEV)
+    present = {1: ['cls_logits'], 2: ['cls_logits', 'ordinal_logits'], 3: ['cls_logits', 'ordinal_logits', 'mu', 'log_var'],
+               4: ['cls_logits', 'ordinal_logits', 'mu', 'log_var', 'kan_severity']}
+    for stage in (1, 2, 3, 4):
+        m.curriculum_stage = stage
+        o = m(x)
+        for k in ('cls_logits', 'ordinal_logits', 'mu', 'log_var', 'kan_severity'):
+            assert (o[k] is not None) == (k in present[stage]), (stage, k)
+        r = JointLoss()(o, y, y, stage)
+        assert sum(float(r[k]) != 0.0 for k in ('cls_loss', 'ord_loss', 'unc_loss', 'kan_loss')) == min(stage, 4)
+    with pytest.raises(AssertionError):
+        m.curriculum_stage = 5
+    m.curriculum_stage = 4
+    m.freeze_backbone()
+    m.zero_grad()
+    JointLoss()(m(x), y, y, 4)['total_loss'].backward()
+    assert all(p.grad is None for p in m.backbone.parameters())
+    assert all(p.grad is not None for n, p in m.named_parameters() if not n.startswith('backbone'))
+    assert m.count_parameters()['total'] == 181978                 # results/evaluation_results.txt (frozen run)
+    m.unfreeze_backbone()
+    m.zero_grad()
+    JointLoss()(m(x), y, y, 4)['total_loss'].backward()
+    assert all(p.grad is not None for p in m.parameters())
+
+
+def test_autocast_gradscaler_step_like_the_trainer():
+    """trainer.py:99-129: autocast('cuda') forward, GradScaler backward, unscale, clip, AdamW step."""
+    torch.manual_seed(2)
+    m = RoViTKAN(pretrained=False).to(DEV).train()
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-4, weight_decay=1e-4)
+    scaler = torch.amp.GradScaler('cuda')
+    loss_fn = JointLoss(focal_alpha=torch.ones(4))
+    x = torch.randn(4, 3, 224, 224, device=DEV)
+    y = torch.tensor([0, 1, 2, 3], device=DEV)
+    before = m.backbone.model.blocks[3].mlp.fc1.weight.detach().clone()
+    losses = []
+    for _ in range(3):
+        with torch.autocast('cuda'):
+            out = m(x)
+            la, lb = loss_fn(out, y, y, 4), loss_fn(out, y.flip(0), y, 4)
+            loss = 0.7 * la['total_loss'] + 0.3 * lb['total_loss']
+        opt.zero_grad()
+        scaler.scale(loss).backward()
+        scaler.unscale_(opt)
+        norm = torch.nn.utils.clip_grad_norm_(m.parameters(), 1.0)
+        scaler.step(opt)
+        scaler.update()
+        assert torch.isfinite(norm)
+        losses.append(float(loss))
+    assert not torch.equal(before, m.backbone.model.blocks[3].mlp.fc1.weight)
+    assert all(np.isfinite(losses)), losses
+    assert out['features'].dtype == torch.float32 and out['kan_severity'].dtype == torch.float32
+
+
+def test_cpu_input_is_rejected_not_emulated():
+    m = RoViTKAN(pretrained=False)
+    with pytest.raises(RuntimeError, match='no CPU fallback'):
+        m(torch.randn(1, 3, 224, 224))
