@@ -37,7 +37,7 @@ struct ScopedTimer {
 };
 
 constexpr int kBN = 192;       // every N on this path (192, 576, 768) is a multiple of 192
-constexpr int kNtStages = 4;
+constexpr int kNtStages = 3;
 constexpr int kBQ = 192;
 constexpr int kTnStages = 4;
 
@@ -55,12 +55,13 @@ int launch_nt(const GemmNtArgs& a, cudaStream_t stream) {
   RVK_TRY(rvk_make_tmap_2d(&tmA, a.A, RVK_BF16, p.M, p.K, a.lda, 128, 64));
   RVK_TRY(rvk_make_tmap_2d(&tmB, a.B, RVK_BF16, p.N, p.K, a.ldb, kBN, 64));
   const bool out_f32 = (MODE == EPI_F32 || MODE == EPI_RES_LN);
-  RVK_TRY(rvk_make_tmap_2d(&tmOut, a.out, out_f32 ? RVK_F32 : RVK_BF16, p.M, p.N, a.ldo, 128, out_f32 ? 32 : 64));
+  // stores go out per epilogue warp: 32-row boxes
+  RVK_TRY(rvk_make_tmap_2d(&tmOut, a.out, out_f32 ? RVK_F32 : RVK_BF16, p.M, p.N, a.ldo, 32, out_f32 ? 32 : 64));
   tmOut2 = tmOut;
   tmAux = tmOut;
   if (p.has_out2) {
     if (a.out2 == nullptr) return RVK_ERR_BAD_ARG;
-    RVK_TRY(rvk_make_tmap_2d(&tmOut2, a.out2, RVK_BF16, p.M, p.N, a.ldo2, 128, 64));
+    RVK_TRY(rvk_make_tmap_2d(&tmOut2, a.out2, RVK_BF16, p.M, p.N, a.ldo2, 32, 64));
   }
   if (MODE == EPI_DGELU) {
     if (a.aux == nullptr) return RVK_ERR_BAD_ARG;

@@ -9,9 +9,11 @@
 // owner, w2 epilogue-panel producer (TMA loads of residual / pre-activation panels), w3..w6
 // epilogue (TMEM lane quadrant = warp_id % 4, one accumulator row per thread).
 //
-// All epilogue I/O moves through a ring of [128 rows x 128 B] shared-memory panels in the TMA
-// 128-byte swizzle: auxiliary inputs arrive by TMA load, are rewritten in place by the row
-// owner, and leave by TMA store (tail rows are clipped by the tensor map).
+// All epilogue I/O moves through a ring of six [128 rows x 128 B] shared-memory panels in the TMA
+// 128-byte swizzle: auxiliary inputs arrive by TMA load (up to four panels ahead of their use), are
+// rewritten in place by the row owner, and leave by TMA store (tail rows are clipped by the tensor
+// map).  Each epilogue warp owns its 32 rows end to end -- it stores its own [32 x 128 B] sub-panel
+// and retires it with its own bulk-group -- so the epilogue has no CTA-wide barrier.
 //
 // Epilogue modes (the encoder's fused ops):
 //   EPI_BF16     out = bf16(acc + bias)                               qkv, generic dgrad
@@ -44,7 +46,7 @@ struct GemmNtParams {
 
 constexpr int kGemmThreads = 224;
 constexpr int kPanelBytes = 128 * 128;   // 16 KB
-constexpr int kNumSlots = 3;
+constexpr int kNumSlots = 6;
 
 template <int BN, int STAGES>
 struct GemmNtSmem {
@@ -53,7 +55,7 @@ struct GemmNtSmem {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kOperandBytes = STAGES * kStageBytes;
   static constexpr int kSlotBytes = kNumSlots * kPanelBytes;
-  static constexpr int kVecBytes = 3 * 768 * 4;   // bias / gamma / beta
+  static constexpr int kVecBytes = (768 + 192 + 192) * 4;   // bias / gamma / beta
   static constexpr int kBarBytes = 256;
   static constexpr int kTotal = 1024 /*align slack*/ + kOperandBytes + kSlotBytes + kVecBytes + kBarBytes;
 };
@@ -90,8 +92,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* sSlots = smem + L::kOperandBytes;
   float* sBias = reinterpret_cast<float*>(sSlots + L::kSlotBytes);
   float* sGamma = sBias + 768;
-  float* sBeta = sGamma + 768;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sBeta + 768);
+  float* sBeta = sGamma + 192;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sBeta + 192);
   uint64_t* full = bars;                       // [STAGES]
   uint64_t* empty = full + STAGES;             // [STAGES]
   uint64_t* tmem_full = empty + STAGES;        // [2]
@@ -111,8 +113,10 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // ---- one-time setup
   for (int i = threadIdx.x; i < 768; i += blockDim.x) {
     sBias[i] = (p.bias != nullptr && i < p.N) ? p.bias[i] : 0.0f;
-    sGamma[i] = (p.gamma != nullptr && i < 192) ? p.gamma[i] : 1.0f;
-    sBeta[i] = (p.beta != nullptr && i < 192) ? p.beta[i] : 0.0f;
+    if (i < 192) {
+      sGamma[i] = (p.gamma != nullptr) ? p.gamma[i] : 1.0f;
+      sBeta[i] = (p.beta != nullptr) ? p.beta[i] : 0.0f;
+    }
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -128,7 +132,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < kNumSlots; ++i) {
       mbar_init(&slot_full[i], 1);
-      mbar_init(&slot_empty[i], 1);
+      mbar_init(&slot_empty[i], 4);     // one arrival per epilogue warp
     }
     fence_mbar_init();
   }
@@ -215,7 +219,6 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ================================================================= epilogue warps
     const int quad = warp & 3;
     const int row = quad * 32 + lane;                 // accumulator row == TMEM lane
-    const bool store_thread = (warp == 3 && lane == 0);
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
     uint32_t cnt = 0;
     int prev_slot = -1;
@@ -228,18 +231,21 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ++cnt;
       return sSlots + slot * kPanelBytes;
     };
+    // this warp's 32 rows of the panel are final: store them, then retire the previous panel's sub-store
+    // (one panel of slack keeps the wait off the critical path) and hand that slot back to the producer
     auto publish = [&](const CUtensorMap* tm, int slot, int c0, int r0) {
       fence_proxy_async_smem();
-      named_bar_sync(1, 128);
-      if (store_thread) {
-        tma_store_2d(tm, sSlots + slot * kPanelBytes, c0, r0);
+      __syncwarp();
+      if (lane == 0) {
+        if (r0 + quad * 32 < p.M)
+          tma_store_2d(tm, sSlots + slot * kPanelBytes + quad * 32 * 128, c0, r0 + quad * 32);
         tma_store_commit();
         if (prev_slot >= 0) {
           tma_store_wait_read<1>();
           mbar_arrive(&slot_empty[prev_slot]);
         }
-        prev_slot = slot;
       }
+      prev_slot = slot;
     };
 
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
@@ -389,7 +395,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_ph ^= 1; }
     }
-    if (store_thread) tma_store_wait_all<0>();
+    if (lane == 0) tma_store_wait_all<0>();
   }
 
   // ---- teardown

@@ -192,6 +192,20 @@ def gen_model():
               'classification_head.fc1.weight', 'ordinal_head.fc2.weight', 'uncertainty_head.fc_logvar.weight',
               'kan_module.kan_layers.0.spline_weights', 'kan_module.kan_layers.2.linear.weight']:
         out['grad_' + k] = npy(named[k].grad)
+    # same pass at curriculum stage 3 (no KAN branch): the KAN's discontinuity at tanh(x)=0.4 makes stage-4
+    # gradients hypersensitive to bf16-sized feature noise, stage-3 gradients are the well-conditioned check
+    model.zero_grad()
+    model.curriculum_stage = 3
+    o3 = model(images)
+    res3 = JointLoss(focal_alpha=None)(o3, yc, yc, 3)
+    res3['total_loss'].backward()
+    for k, v in res3.items():
+        out['loss3_' + k] = npy(v)
+    for k in [n for n in out if n.startswith('grad_')]:
+        g3 = named[k[5:]].grad
+        if g3 is not None and not k[5:].startswith('kan_module'):
+            out['grad3_' + k[5:]] = npy(g3)
+    model.curriculum_stage = 4
     out['param_count'] = np.int64(sum(p.numel() for p in model.parameters()))
     out['param_counts'] = np.array([model.count_parameters()[k] for k in
                                     ['backbone', 'classification_head', 'ordinal_head', 'uncertainty_head',
