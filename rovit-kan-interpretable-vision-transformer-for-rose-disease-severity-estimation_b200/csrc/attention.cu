@@ -1,12 +1,8 @@
-// Short-sequence multi-head attention for DeiT-Tiny (197 tokens, 3 heads of 64), forward and backward.
+// Attention BACKWARD for DeiT-Tiny (197 tokens, 3 heads of 64); the forward lives in attention_tc.cu
+// (tcgen05).  One CTA per (image, head).  Q, K, V, dO of that head (197 x 64 bf16, padded to 208 rows) live in
+// shared memory with a 16-byte-chunk XOR swizzle and feed mma.sync m16n8k16 tiles.
 //
-// One CTA per (image, head).  Q, K, V of that head (197 x 64 bf16, padded to 208 rows) live in shared
-// memory with a 16-byte-chunk XOR swizzle; each warp owns 16-query row tiles and keeps the WHOLE score
-// row (208 keys) in registers, so softmax is a single pass in fp32 registers (no online rescaling),
-// and the probabilities feed the P*V product straight from registers.
-// Restates timm Attention.forward: softmax(q k^T * 64^-0.5) v  (oracle/vit.py::_Attention).
-//
-// Backward (recompute, no atomics, no stored probabilities):
+// Backward (recompute from the saved log-sum-exp, no atomics, no stored probabilities):
 //   phase K  (warp = 16 keys)   S^T = K Q^T, P^T = exp(S^T*scale - lse), dV = P^T dO,
 //                               dP^T = V dO^T, dS^T = P^T o (dP^T - delta), dK = scale * dS^T Q
 //   phase Q  (warp = 16 queries) S, P, dP = dO V^T, dS = P o (dP - delta), dQ = scale * dS K
@@ -87,15 +83,25 @@ __device__ __forceinline__ void mma_p_times_cols(float (&out)[8][4], const uint3
   }
 }
 
-// copy a head's [197 x 64] slice (row stride ld elements) into a swizzled, zero-padded [208][64] tile
-__device__ __forceinline__ void load_head_tile(uint8_t* dst, const __nv_bfloat16* src, int ld, int tid, int nthreads) {
-  for (int i = tid; i < kPad * 8; i += nthreads) {
+// copy a head's [197 x 64] slice (row stride ld elements) into a swizzled [208][64] tile with cp.async: every
+// 16-byte request is in flight at once (the pad rows 197..207 are zeroed once per buffer by zero_pad_rows)
+__device__ __forceinline__ void load_head_tile_async(uint8_t* dst, const __nv_bfloat16* src, int ld, int tid,
+                                                     int nthreads) {
+  const uint32_t base = smem_u32(dst);
+  for (int i = tid; i < kTok * 8; i += nthreads) {
     const int r = i >> 3, c = i & 7;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (r < kTok) v = *reinterpret_cast<const uint4*>(src + static_cast<size_t>(r) * ld + c * 8);
-    *reinterpret_cast<uint4*>(dst + tile_off(r, c)) = v;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(base + tile_off(r, c)),
+                 "l"(src + static_cast<size_t>(r) * ld + c * 8)
+                 : "memory");
   }
 }
+__device__ __forceinline__ void zero_pad_rows(uint8_t* dst, int tid, int nthreads) {
+  for (int i = kTok * 8 + tid; i < kPad * 8; i += nthreads)
+    *reinterpret_cast<uint4*>(dst + tile_off(i >> 3, i & 7)) = make_uint4(0u, 0u, 0u, 0u);
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // one 16-column chunk `j` of "A times rows of T": acc2 (16 x 16) = A(16 x 64) * T[j*16 .. j*16+16, :]^T
 __device__ __forceinline__ void mma_a_times_rows_chunk(float (&acc2)[2][4], const uint32_t (&a)[4][4],
@@ -146,80 +152,6 @@ __device__ __forceinline__ void store_tile_bf16(uint8_t* stage, const float (&o)
   __syncwarp();
 }
 
-// ------------------------------------------------------------------------------------------- forward
-__global__ void __launch_bounds__(kAttnThreads, 1)
-attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kPad * 128;
-  uint8_t* sV = sK + kPad * 128;
-  uint8_t* sStage = sV + kPad * 128;     // 7 warps x [16][64] bf16
-  const int b = blockIdx.x / kHeads, h = blockIdx.x % kHeads;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const __nv_bfloat16* base = qkv + static_cast<size_t>(b) * kTok * kQkvLd + h * kHd;
-  load_head_tile(sQ, base, kQkvLd, threadIdx.x, kAttnThreads);
-  load_head_tile(sK, base + 192, kQkvLd, threadIdx.x, kAttnThreads);
-  load_head_tile(sV, base + 384, kQkvLd, threadIdx.x, kAttnThreads);
-  __syncthreads();
-
-  const int g = lane >> 2, t = lane & 3;
-  uint8_t* stage = sStage + warp * 2048;
-  for (int rt = warp; rt < 13; rt += 7) {
-    uint32_t qf[4][4];
-    load_a_frags(smem_u32(sQ), rt, lane, qf);
-    float s[26][4];
-#pragma unroll
-    for (int i = 0; i < 26; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.0f;
-    mma_a_times_rows<26>(s, qf, smem_u32(sK), lane);
-
-    // softmax over the 197 real keys, base-2 exponent domain
-    float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-    for (int nt = 0; nt < 26; ++nt) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int key = nt * 8 + 2 * t + (e & 1);
-        s[nt][e] = (key < kTok) ? s[nt][e] * (kScale * kLog2e) : -INFINITY;
-      }
-      m0 = fmaxf(m0, fmaxf(s[nt][0], s[nt][1]));
-      m1 = fmaxf(m1, fmaxf(s[nt][2], s[nt][3]));
-    }
-    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
-    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
-    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
-    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
-    float l0 = 0.0f, l1 = 0.0f;
-    uint32_t pf[13][4];
-#pragma unroll
-    for (int nt = 0; nt < 26; ++nt) {
-      const float p0 = exp2f(s[nt][0] - m0), p1 = exp2f(s[nt][1] - m0);
-      const float p2 = exp2f(s[nt][2] - m1), p3 = exp2f(s[nt][3] - m1);
-      l0 += p0 + p1;
-      l1 += p2 + p3;
-      pf[nt >> 1][(nt & 1) * 2 + 0] = pack_bf16x2(p0, p1);
-      pf[nt >> 1][(nt & 1) * 2 + 1] = pack_bf16x2(p2, p3);
-    }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-
-    float o[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.0f;
-    mma_p_times_cols(o, pf, smem_u32(sV), lane);
-
-    store_tile_bf16(stage, o, rt, lane, ctx + static_cast<size_t>(b) * kTok * kCtxLd + h * kHd, kCtxLd, 1.0f / l0,
-                    1.0f / l1);
-    if (lse != nullptr && t == 0) {
-      const int r0 = rt * 16 + g, r1 = r0 + 8;
-      float* L = lse + static_cast<size_t>(blockIdx.x) * kTok;
-      if (r0 < kTok) L[r0] = m0 + log2f(l0);     // log2-domain log-sum-exp of the scaled scores
-      if (r1 < kTok) L[r1] = m1 + log2f(l1);
-    }
-  }
-}
-
 // ------------------------------------------------------------------------------------------- backward
 // smem tiles: Q, K, V, dO (bf16 [208][64] swizzled), per-warp staging, lse[208], delta[208] (fp32)
 __global__ void __launch_bounds__(kAttnThreads, 1)
@@ -240,10 +172,15 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
   const __nv_bfloat16* base = qkv + tok0 * kQkvLd + h * kHd;
   const __nv_bfloat16* dO = dctx + tok0 * kCtxLd + h * kHd;
   const __nv_bfloat16* O = ctx + tok0 * kCtxLd + h * kHd;
-  load_head_tile(sQ, base, kQkvLd, threadIdx.x, kAttnThreads);
-  load_head_tile(sK, base + 192, kQkvLd, threadIdx.x, kAttnThreads);
-  load_head_tile(sV, base + 384, kQkvLd, threadIdx.x, kAttnThreads);
-  load_head_tile(sDO, dO, kCtxLd, threadIdx.x, kAttnThreads);
+  load_head_tile_async(sQ, base, kQkvLd, threadIdx.x, kAttnThreads);
+  load_head_tile_async(sK, base + 192, kQkvLd, threadIdx.x, kAttnThreads);
+  load_head_tile_async(sV, base + 384, kQkvLd, threadIdx.x, kAttnThreads);
+  load_head_tile_async(sDO, dO, kCtxLd, threadIdx.x, kAttnThreads);
+  cp_async_commit();
+  zero_pad_rows(sQ, threadIdx.x, kAttnThreads);
+  zero_pad_rows(sK, threadIdx.x, kAttnThreads);
+  zero_pad_rows(sV, threadIdx.x, kAttnThreads);
+  zero_pad_rows(sDO, threadIdx.x, kAttnThreads);
   // delta[q] = <dO[q,:], O[q,:]>; one 8-lane group per row
   for (int r = threadIdx.x >> 3; r < kPad; r += kAttnThreads >> 3) {
     float acc = 0.0f;
@@ -266,6 +203,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
       sLse[r] = (r < kTok) ? lse[static_cast<size_t>(blockIdx.x) * kTok + r] : 0.0f;
     }
   }
+  cp_async_wait<0>();
   __syncthreads();
 
   const int g = lane >> 2, t = lane & 3;
@@ -356,20 +294,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
 }  // namespace
 
 // ------------------------------------------------------------------------------------------- launchers
-constexpr int kAttnFwdSmem = 3 * kPad * 128 + 7 * 2048;
 constexpr int kAttnBwdSmem = 4 * kPad * 128 + 7 * 2048 + 2 * kPad * 4;
-
-int rvk_attention_fwd_launch(const void* qkv, void* ctx, float* lse, int batch, cudaStream_t stream) {
-  if (batch <= 0) return RVK_OK;
-  static bool configured = false;
-  if (!configured) {
-    RVK_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnFwdSmem));
-    configured = true;
-  }
-  attn_fwd_kernel<<<batch * kHeads, kAttnThreads, kAttnFwdSmem, stream>>>(
-      static_cast<const __nv_bfloat16*>(qkv), static_cast<__nv_bfloat16*>(ctx), lse);
-  return rvk_launch_check();
-}
 
 int rvk_attention_bwd_launch(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
                              int batch, cudaStream_t stream) {

@@ -5,9 +5,12 @@
 //   D  fp32 accumulators in TMEM, two stages of 256 columns so the epilogue of tile t overlaps
 //      the MMAs of tile t+1.
 //
-// Warp roles (224 threads): w0 operand TMA producer, w1 UMMA issuer (one elected lane) + TMEM
-// owner, w2 epilogue-panel producer (TMA loads of residual / pre-activation panels), w3..w6
-// epilogue (TMEM lane quadrant = warp_id % 4, one accumulator row per thread).
+// Warp roles (480 threads): w0 operand TMA producer, w1 UMMA issuer (one elected lane) + TMEM
+// owner, w2 epilogue-panel producer (TMA loads of residual / pre-activation panels), w3..w14
+// epilogue: three teams of four warps (TMEM lane quadrant = warp_id % 4, one accumulator row per
+// thread); the teams take the 128-byte column panels round-robin, so every SM sub-partition has
+// three epilogue warps to overlap TMEM loads, MUFU latency and shared-memory traffic (the epilogues
+// are bound by instruction issue, not by the tensor pipe: ncu in profiles/).
 //
 // All epilogue I/O moves through a ring of six [128 rows x 128 B] shared-memory panels in the TMA
 // 128-byte swizzle: auxiliary inputs arrive by TMA load (up to four panels ahead of their use), are
@@ -44,7 +47,8 @@ struct GemmNtParams {
   int has_res;              // EPI_RES_LN: 0 = no residual at all
 };
 
-constexpr int kGemmThreads = 224;
+constexpr int kGemmThreads = 480;
+constexpr int kNumTeams = 3;
 constexpr int kPanelBytes = 128 * 128;   // 16 KB
 constexpr int kNumSlots = 6;
 
@@ -57,7 +61,8 @@ struct GemmNtSmem {
   static constexpr int kSlotBytes = kNumSlots * kPanelBytes;
   static constexpr int kVecBytes = (768 + 192 + 192) * 4;   // bias / gamma / beta
   static constexpr int kBarBytes = 256;
-  static constexpr int kTotal = 1024 /*align slack*/ + kOperandBytes + kSlotBytes + kVecBytes + kBarBytes;
+  static constexpr int kPartBytes = 2 * kNumTeams * 128 * 4;   // LayerNorm partial sums [pass][team][row]
+  static constexpr int kTotal = 1024 /*align slack*/ + kOperandBytes + kSlotBytes + kVecBytes + kBarBytes + kPartBytes;
 };
 
 #ifdef __CUDACC__
@@ -101,6 +106,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* slot_full = tmem_empty + 2;        // [kNumSlots]
   uint64_t* slot_empty = slot_full + kNumSlots;  // [kNumSlots]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(slot_empty + kNumSlots);
+  float* sPart = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + L::kBarBytes);   // [2][2][128]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -128,7 +134,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 128);
+      mbar_init(&tmem_empty[i], 128 * kNumTeams);
     }
     for (int i = 0; i < kNumSlots; ++i) {
       mbar_init(&slot_full[i], 1);
@@ -218,13 +224,17 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ================================================================= epilogue warps
     const int quad = warp & 3;
+    const int team = (warp - 3) >> 2;                 // 0: warps 3-6, 1: warps 7-10, 2: warps 11-14
     const int row = quad * 32 + lane;                 // accumulator row == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
-    uint32_t cnt = 0;
+    uint32_t cnt = 0;                                 // global panel counter (all panels, all teams)
+    int tile_iter = 0;
     int prev_slot = -1;
     int acc = 0;
     uint32_t acc_ph = 0;
 
+    // panels go round-robin over the teams; `cnt` walks the CTA's whole panel sequence
+    auto mine = [&]() -> bool { return cnt % kNumTeams == static_cast<uint32_t>(team); };
     auto acquire = [&](int& slot) -> uint8_t* {
       slot = cnt % kNumSlots;
       mbar_wait(&slot_full[slot], (cnt / kNumSlots) & 1);
@@ -247,6 +257,30 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       prev_slot = slot;
     };
+    // the warps that share a TMEM quadrant (one per team) meet here
+    auto quad_sync = [&]() {
+      tc_fence_before();
+      named_bar_sync(2 + quad, 32 * kNumTeams);
+      tc_fence_after();
+    };
+    // 32 accumulator columns -> registers, plus bias
+    auto load32 = [&](uint32_t taddr, int col0, float (&v)[32]) {
+      tmem_ld32(taddr, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 b4 = *reinterpret_cast<const float4*>(&sBias[col0 + i * 4]);
+        v[i * 4 + 0] += b4.x; v[i * 4 + 1] += b4.y; v[i * 4 + 2] += b4.z; v[i * 4 + 3] += b4.w;
+      }
+    };
+    // 32 fp32 values -> 32 bf16 = chunks [4*half, 4*half+4) of this thread's 128-byte panel row
+    auto store_bf16_half = [&](uint8_t* panel, int half, const float (&v)[32]) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 q = make_uint4(pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]), pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
+                             pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
+        *reinterpret_cast<uint4*>(panel + sw128_offset(row, half * 4 + j)) = q;
+      }
+    };
 
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m0 = (t / num_n_tiles) * 128;
@@ -256,71 +290,57 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t tacc = tmem_base + acc * 256 + lane_sel;
 
       if constexpr (MODE == EPI_BF16 || MODE == EPI_GELU || MODE == EPI_DGELU) {
+        // panel sequence of a tile: one bf16 panel per 64-column chunk, or (EPI_GELU storing z too) a z panel
+        // and an h panel per chunk.  Which of the pair comes first flips with chunk and tile parity so that
+        // all teams get the same mix of cheap (z) and GELU (h) panels.
+        const bool two = (MODE == EPI_GELU) && p.has_out2;
+        const int np = two ? 2 * (BN / 64) : BN / 64;
 #pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
-          float v[2][32];
-          tmem_ld32(tacc + c * 64, v[0]);
-          tmem_ld32(tacc + c * 64 + 32, v[1]);
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[h][i] += sBias[n0 + c * 64 + h * 32 + i];
+        for (int pos = 0; pos < np; ++pos) {
+          if (!mine()) { ++cnt; continue; }
+          const int c = two ? (pos >> 1) : pos;
+          const bool is_z = two && ((((pos & 1) + c + tile_iter) & 1) == 0);
           int slot;
-          if constexpr (MODE == EPI_GELU) {
-            if (p.has_out2) {   // pre-activation panel first
-              uint8_t* pz = acquire(slot);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float* s = &v[j >> 2][(j & 3) * 8];
-                uint4 q = make_uint4(pack_bf16x2(s[0], s[1]), pack_bf16x2(s[2], s[3]), pack_bf16x2(s[4], s[5]),
-                                     pack_bf16x2(s[6], s[7]));
-                *reinterpret_cast<uint4*>(pz + sw128_offset(row, j)) = q;
-              }
-              publish(&tmOut2, slot, n0 + c * 64, m0);
-            }
-          }
           uint8_t* po = acquire(slot);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float s[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) s[e] = v[j >> 2][(j & 3) * 8 + e];
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            float v[32];
+            load32(tacc + c * 64 + half * 32, n0 + c * 64 + half * 32, v);
             if constexpr (MODE == EPI_GELU) {
+              if (!is_z) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) s[e] = gelu_erf(s[e]);
+                for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+              }
             }
             if constexpr (MODE == EPI_DGELU) {
-              const uint4 zq = *reinterpret_cast<const uint4*>(po + sw128_offset(row, j));
-              const uint32_t zw[4] = {zq.x, zq.y, zq.z, zq.w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 z = unpack_bf16x2(zw[e]);
-                s[2 * e] *= gelu_erf_grad(z.x);
-                s[2 * e + 1] *= gelu_erf_grad(z.y);
+              for (int j = 0; j < 4; ++j) {
+                const uint4 zq = *reinterpret_cast<const uint4*>(po + sw128_offset(row, half * 4 + j));
+                const uint32_t zw[4] = {zq.x, zq.y, zq.z, zq.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 z = unpack_bf16x2(zw[e]);
+                  v[j * 8 + 2 * e] *= gelu_erf_grad(z.x);
+                  v[j * 8 + 2 * e + 1] *= gelu_erf_grad(z.y);
+                }
               }
             }
-            uint4 q = make_uint4(pack_bf16x2(s[0], s[1]), pack_bf16x2(s[2], s[3]), pack_bf16x2(s[4], s[5]),
-                                 pack_bf16x2(s[6], s[7]));
-            *reinterpret_cast<uint4*>(po + sw128_offset(row, j)) = q;
+            store_bf16_half(po, half, v);
           }
-          publish(&tmOut, slot, n0 + c * 64, m0);
+          publish(is_z ? &tmOut2 : &tmOut, slot, n0 + c * 64, m0);
         }
       } else if constexpr (MODE == EPI_F32) {
 #pragma unroll 1
         for (int c = 0; c < BN / 32; ++c) {
+          if (!mine()) { ++cnt; continue; }
           float v[32];
-          tmem_ld32(tacc + c * 32, v);
+          load32(tacc + c * 32, n0 + c * 32, v);
           int slot;
           uint8_t* po = acquire(slot);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 q;
-            q.x = v[j * 4 + 0] + sBias[n0 + c * 32 + j * 4 + 0];
-            q.y = v[j * 4 + 1] + sBias[n0 + c * 32 + j * 4 + 1];
-            q.z = v[j * 4 + 2] + sBias[n0 + c * 32 + j * 4 + 2];
-            q.w = v[j * 4 + 3] + sBias[n0 + c * 32 + j * 4 + 3];
-            *reinterpret_cast<float4*>(po + sw128_offset(row, j)) = q;
-          }
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(po + sw128_offset(row, j)) =
+                make_float4(v[j * 4 + 0], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
           publish(&tmOut, slot, n0 + c * 32, m0);
         }
       } else {   // EPI_RES_LN
@@ -328,10 +348,12 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool tma_res = p.has_res && p.res_table == nullptr;
         const float* trow =
             (p.res_table != nullptr) ? p.res_table + static_cast<size_t>((m0 + row) % p.table_rows) * 192 : nullptr;
+        const uint32_t cnt0 = cnt;          // panel c of this tile belongs to team (cnt0 + c) % kNumTeams
 #pragma unroll 1
         for (int c = 0; c < 6; ++c) {
+          if (!mine()) { ++cnt; continue; }
           float v[32];
-          tmem_ld32(tacc + c * 32, v);
+          load32(tacc + c * 32, c * 32, v);
           int slot;
           uint8_t* po = acquire(slot);
 #pragma unroll
@@ -339,11 +361,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
             if (tma_res) r = *reinterpret_cast<const float4*>(po + sw128_offset(row, j));
             else if (trow != nullptr) r = *reinterpret_cast<const float4*>(trow + c * 32 + j * 4);
-            float4 q;
-            q.x = v[j * 4 + 0] + sBias[c * 32 + j * 4 + 0] + r.x;
-            q.y = v[j * 4 + 1] + sBias[c * 32 + j * 4 + 1] + r.y;
-            q.z = v[j * 4 + 2] + sBias[c * 32 + j * 4 + 2] + r.z;
-            q.w = v[j * 4 + 3] + sBias[c * 32 + j * 4 + 3] + r.w;
+            float4 q = make_float4(v[j * 4 + 0] + r.x, v[j * 4 + 1] + r.y, v[j * 4 + 2] + r.z, v[j * 4 + 3] + r.w);
             v[j * 4 + 0] = q.x; v[j * 4 + 1] = q.y; v[j * 4 + 2] = q.z; v[j * 4 + 3] = q.w;
             sum += (q.x + q.y) + (q.z + q.w);
             *reinterpret_cast<float4*>(po + sw128_offset(row, j)) = q;
@@ -352,38 +370,47 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           publish(&tmOut, slot, c * 32, m0);
         }
         if (p.has_out2) {
-          const float mean = sum * (1.0f / 192.0f);
+          // row statistics: every team holds a third of the row's columns
+          sPart[team * 128 + row] = sum;
+          quad_sync();
+          float tot = 0.0f;
+#pragma unroll
+          for (int tm = 0; tm < kNumTeams; ++tm) tot += sPart[tm * 128 + row];
+          const float mean = tot * (1.0f / 192.0f);
           float var = 0.0f;
 #pragma unroll 1
           for (int c = 0; c < 6; ++c) {
+            if ((cnt0 + c) % kNumTeams != static_cast<uint32_t>(team)) continue;
             float v[32];
             tmem_ld32(tacc + c * 32, v);
 #pragma unroll
             for (int i = 0; i < 32; ++i) { const float d = v[i] - mean; var = fmaf(d, d, var); }
           }
-          const float rstd = rsqrtf(var * (1.0f / 192.0f) + p.ln_eps);
-          if (m0 + row < p.M) {
+          sPart[(kNumTeams + team) * 128 + row] = var;
+          quad_sync();
+          float vtot = 0.0f;
+#pragma unroll
+          for (int tm = 0; tm < kNumTeams; ++tm) vtot += sPart[(kNumTeams + tm) * 128 + row];
+          const float rstd = rsqrtf(vtot * (1.0f / 192.0f) + p.ln_eps);
+          if (team == 0 && m0 + row < p.M) {
             if (p.mean_out != nullptr) p.mean_out[m0 + row] = mean;
             if (p.rstd_out != nullptr) p.rstd_out[m0 + row] = rstd;
           }
 #pragma unroll 1
           for (int c = 0; c < 3; ++c) {
-            float v[2][32];
-            tmem_ld32(tacc + c * 64, v[0]);
-            tmem_ld32(tacc + c * 64 + 32, v[1]);
+            if (!mine()) { ++cnt; continue; }
             int slot;
             uint8_t* po = acquire(slot);
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+              float v[32];
+              tmem_ld32(tacc + c * 64 + half * 32, v);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float s[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int col = c * 64 + j * 8 + e;
-                s[e] = (v[j >> 2][(j & 3) * 8 + e] - mean) * rstd * sGamma[col] + sBeta[col];
+              for (int i = 0; i < 32; ++i) {
+                const int col = c * 64 + half * 32 + i;
+                v[i] = (v[i] - mean) * rstd * sGamma[col] + sBeta[col];
               }
-              uint4 q = make_uint4(pack_bf16x2(s[0], s[1]), pack_bf16x2(s[2], s[3]), pack_bf16x2(s[4], s[5]),
-                                   pack_bf16x2(s[6], s[7]));
-              *reinterpret_cast<uint4*>(po + sw128_offset(row, j)) = q;
+              store_bf16_half(po, half, v);
             }
             publish(&tmOut2, slot, c * 64, m0);
           }
@@ -394,6 +421,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       mbar_arrive(&tmem_empty[acc]);
       if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      ++tile_iter;
     }
     if (lane == 0) tma_store_wait_all<0>();
   }

@@ -55,3 +55,26 @@ int rvk_make_tmap_2d(CUtensorMap* out, const void* base, int dtype, int64_t rows
   }
   return RVK_OK;
 }
+
+int rvk_make_tmap_3d(CUtensorMap* out, const void* base, int dtype, int64_t d0, int64_t d1, int64_t d2,
+                     int64_t stride1, int64_t stride2, int box_d0, int box_d1) {
+  std::call_once(g_once, resolve_encode);
+  if (g_encode == nullptr) return RVK_ERR_NO_DRIVER;
+  const int esz = (dtype == RVK_BF16) ? 2 : 4;
+  if (box_d0 * esz != 128 || box_d1 > 256 || box_d1 < 1) return RVK_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || ((stride1 * esz) & 15) != 0 || ((stride2 * esz) & 15) != 0)
+    return RVK_ERR_ALIGNMENT;
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(d0), static_cast<cuuint64_t>(d1), static_cast<cuuint64_t>(d2)};
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(stride1) * esz, static_cast<cuuint64_t>(stride2) * esz};
+  cuuint32_t box[3] = {static_cast<cuuint32_t>(box_d0), static_cast<cuuint32_t>(box_d1), 1};
+  cuuint32_t estride[3] = {1, 1, 1};
+  CUresult r = g_encode(out, dtype == RVK_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                        3, const_cast<void*>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    g_last_error = "cuTensorMapEncodeTiled(3d) failed with CUresult " + std::to_string(static_cast<int>(r));
+    return RVK_ERR_TMA_ENCODE;
+  }
+  return RVK_OK;
+}

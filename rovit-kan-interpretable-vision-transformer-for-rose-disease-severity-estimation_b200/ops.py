@@ -15,7 +15,9 @@ from torch.amp import custom_bwd, custom_fwd
 
 from . import _lib
 
-CHUNK_IMAGES = int(os.environ.get('ROVITKAN_CHUNK_IMAGES', '192'))
+# images per pass through the 12 blocks; measured on B200 (tools/sweep_chunk.sh): throughput rises monotonically
+# with the chunk (55k img/s at 48 ... 123k at 1024), so the default only bounds the workspace (1.2 GB per 1024 images)
+CHUNK_IMAGES = int(os.environ.get('ROVITKAN_CHUNK_IMAGES', '2048'))
 
 
 def _stream() -> int:
