@@ -200,6 +200,17 @@ int rvk_gemm_nt(int mode, const void* a_bf16, int64_t lda, const void* b_bf16, i
   a.p.has_res = (aux != nullptr || res_table != nullptr) ? 1 : 0;
   return rvk_gemm_nt_launch(a, S(stream));
 }
+int rvk_mlp_fused(const void* ln_in_bf16, const void* w1_bf16, const void* w2_bf16, const float* b1, const float* b2,
+                  const float* x_in_tiled, float* x_out_tiled, const float* gamma, const float* beta, float eps,
+                  void* ln_out_bf16, int m, int cta_group, void* stream) {
+  if (m < 0) return RVK_ERR_BAD_ARG;
+  MlpFusedArgs a;
+  a.ln_in = ln_in_bf16; a.w1 = w1_bf16; a.w2 = w2_bf16; a.ln_out = ln_out_bf16;
+  a.cta_group = cta_group;
+  a.p.M = m; a.p.x_in = x_in_tiled; a.p.x_out = x_out_tiled; a.p.b1 = b1; a.p.b2 = b2;
+  a.p.gamma = gamma; a.p.beta = beta; a.p.eps = eps; a.p.has_ln = ln_out_bf16 != nullptr ? 1 : 0;
+  return rvk_mlp_fused_launch(a, S(stream));
+}
 int rvk_gemm_tn(const void* a_bf16, int64_t lda, const void* b_bf16, int64_t ldb, float* c, int64_t ldc, int m, int p,
                 int q, float scale, void* stream) {
   if (m < 0) return RVK_ERR_BAD_ARG;

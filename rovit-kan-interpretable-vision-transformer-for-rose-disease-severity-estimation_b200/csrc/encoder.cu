@@ -15,6 +15,8 @@
 
 #include "kernels.h"
 
+#include <cstdlib>
+
 namespace {
 
 constexpr int kD = 192, kTok = 197, kDepth = 12, kMlp = 768, kPatchK = 768, kQkv = 576;
@@ -99,7 +101,7 @@ ActLayout act_layout(int64_t rows, int64_t images, bool training) {
     L.dqkv = take(R * kQkv * 2);
   } else {
     BlockSaved b{};
-    b.x_in = take(R * kD * 4);
+    b.x_in = take((R + 127) / 128 * 128 * kD * 4);      // tiled layout (xt_offset): rows padded to 128
     b.x_mid = b.x_in;            // in-place residual updates
     b.ln1 = take(R * kD * 2);
     b.ln2 = b.ln1;
@@ -136,7 +138,7 @@ int gemm_plain(const void* A, int64_t lda, const void* B, int64_t ldb, void* out
 
 int gemm_res_ln(const void* A, int64_t lda, int K, const void* B, const float* bias, const float* residual,
                 const float* table, float* x_out, void* ln_out, const float* gamma, const float* beta, float* mean,
-                float* rstd, int M, cudaStream_t s) {
+                float* rstd, int M, cudaStream_t s, bool tiled = false) {
   GemmNtArgs a;
   a.mode = EPI_RES_LN;
   a.A = A; a.lda = lda; a.B = B; a.ldb = K; a.out = x_out; a.ldo = kD;
@@ -149,7 +151,28 @@ int gemm_res_ln(const void* A, int64_t lda, int K, const void* B, const float* b
   a.p.mean_out = mean; a.p.rstd_out = rstd;
   a.p.has_out2 = ln_out != nullptr ? 1 : 0;
   a.p.has_res = (residual != nullptr || table != nullptr) ? 1 : 0;
+  if (tiled) {      // fp32 token stream in the tiled layout: no TMA for x
+    a.out = nullptr; a.aux = nullptr;
+    a.p.out_tiled = x_out;
+    a.p.res_tiled = residual;
+  }
   return rvk_gemm_nt_launch(a, s);
+}
+
+// inference uses the fused MLP kernel and the tiled token stream unless RVK_UNFUSED=1 (A/B switch for measurements)
+bool fused_inference() {
+  static const bool on = [] {
+    const char* e = getenv("RVK_UNFUSED");
+    return !(e != nullptr && e[0] == '1');
+  }();
+  return on;
+}
+int mlp_cta_group() {
+  static const int g = [] {
+    const char* e = getenv("RVK_MLP_CTA_GROUP");
+    return (e != nullptr && e[0] == '1') ? 1 : 2;
+  }();
+  return g;
 }
 
 }  // namespace
@@ -207,6 +230,34 @@ int rvk_encoder_forward_impl(const void* const* params, const void* wbuf, const 
 
     uint8_t* patches = b16(A.patches, kPatchK);
     RVK_TRY(rvk_im2col_launch(images + static_cast<size_t>(b0) * 3 * 224 * 224, patches, nb, s));
+    if (!train && fused_inference()) {
+      // ---- inference: tiled fp32 token stream (updated in place), fused MLP block
+      float* x = f32(A.blk[0].x_in, kD);
+      uint8_t* ln = b16(A.blk[0].ln1, kD);
+      RVK_TRY(gemm_res_ln(patches, kPatchK, kPatchK, at(wbuf, W.patch_w), nullptr, nullptr, table, x, ln,
+                          P(params, bp(0, B_N1W)), P(params, bp(0, B_N1B)), nullptr, nullptr, M, s, true));
+      for (int i = 0; i < kDepth; ++i) {
+        const BlockSaved& B = A.blk[i];
+        RVK_TRY(gemm_plain(ln, kD, at(wbuf, W.qkv[i]), kD, b16(B.qkv, kQkv), kQkv, M, kQkv, kD, P(params, bp(i, B_QKVB)), s));
+        RVK_TRY(rvk_attention_fwd_launch(b16(B.qkv, kQkv), b16(B.ctx, kD), nullptr, nb, s));
+        RVK_TRY(gemm_res_ln(b16(B.ctx, kD), kD, kD, at(wbuf, W.proj[i]), P(params, bp(i, B_PROJB)), x, nullptr, x, ln,
+                            P(params, bp(i, B_N2W)), P(params, bp(i, B_N2B)), nullptr, nullptr, M, s, true));
+        const bool last = (i == kDepth - 1);
+        MlpFusedArgs m;
+        m.ln_in = ln; m.w1 = at(wbuf, W.fc1[i]); m.w2 = at(wbuf, W.fc2[i]);
+        m.ln_out = last ? nullptr : ln;
+        m.cta_group = mlp_cta_group();
+        m.p.M = M; m.p.x_in = x; m.p.x_out = x;
+        m.p.b1 = P(params, bp(i, B_FC1B)); m.p.b2 = P(params, bp(i, B_FC2B));
+        m.p.gamma = last ? nullptr : P(params, bp(i + 1, B_N1W));
+        m.p.beta = last ? nullptr : P(params, bp(i + 1, B_N1B));
+        m.p.eps = kLnEps; m.p.has_ln = last ? 0 : 1;
+        RVK_TRY(rvk_mlp_fused_launch(m, s));
+      }
+      RVK_TRY(rvk_layernorm_fwd_tiled_launch(x, kTok, P(params, P_NORM_W), P(params, P_NORM_B), kLnEps,
+                                             features + static_cast<size_t>(b0) * kD, kD, nb, s));
+      continue;
+    }
     // patch embedding + cls/pos/bias table -> x0, fused LayerNorm (block 0 norm1) -> ln1
     RVK_TRY(gemm_res_ln(patches, kPatchK, kPatchK, at(wbuf, W.patch_w), nullptr, nullptr, table, f32(A.blk[0].x_in, kD),
                         b16(A.blk[0].ln1, kD), P(params, bp(0, B_N1W)), P(params, bp(0, B_N1B)), stat(A.blk[0].mean1),

@@ -72,7 +72,8 @@ __global__ void cast_transpose_kernel(const float* __restrict__ src, __nv_bfloat
 }
 
 // ------------------------------------------------------------------ LayerNorm forward
-template <bool OUT_BF16>
+// TILED: x is the tiled fp32 token stream (common.cuh xt_offset) and row r of this launch is token row r * xs
+template <bool OUT_BF16, bool TILED = false>
 __global__ void layernorm_fwd_kernel(const float* __restrict__ x, long long xs, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, float eps, void* __restrict__ y, long long ys,
                                      float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows) {
@@ -83,7 +84,10 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, long long xs, 
     float v[6];
     float s = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) { v[i] = xr[lane + 32 * i]; s += v[i]; }
+    for (int i = 0; i < 6; ++i) {
+      v[i] = TILED ? x[xt_elem_offset(static_cast<int>(r * xs), lane + 32 * i)] : xr[lane + 32 * i];
+      s += v[i];
+    }
     const float mean = warp_sum(s) * (1.0f / kD);
     float q = 0.0f;
 #pragma unroll
@@ -242,6 +246,15 @@ int rvk_layernorm_fwd_launch(const float* x, int64_t x_row_stride, const float* 
     layernorm_fwd_kernel<true><<<blocks, 256, 0, stream>>>(x, x_row_stride, gamma, beta, eps, y, y_row_stride, mean, rstd, rows);
   else
     layernorm_fwd_kernel<false><<<blocks, 256, 0, stream>>>(x, x_row_stride, gamma, beta, eps, y, y_row_stride, mean, rstd, rows);
+  return rvk_launch_check();
+}
+
+int rvk_layernorm_fwd_tiled_launch(const float* x_tiled, int64_t token_row_stride, const float* gamma, const float* beta,
+                                   float eps, float* y, int64_t y_row_stride, int rows, cudaStream_t stream) {
+  if (rows <= 0) return RVK_OK;
+  const int blocks = min((rows + 7) / 8, kNumSMsB200 * 8);
+  layernorm_fwd_kernel<false, true><<<blocks, 256, 0, stream>>>(x_tiled, token_row_stride, gamma, beta, eps, y,
+                                                                y_row_stride, nullptr, nullptr, rows);
   return rvk_launch_check();
 }
 

@@ -1,5 +1,6 @@
 // Host launchers for the tcgen05 GEMM kernels: build the TMA tensor maps, pick the grid, launch.
 #include "kernels.h"
+#include "mlp_fused.cuh"
 #include "tma_host.h"
 
 #include <vector>
@@ -56,7 +57,8 @@ int launch_nt(const GemmNtArgs& a, cudaStream_t stream) {
   RVK_TRY(rvk_make_tmap_2d(&tmB, a.B, RVK_BF16, p.N, p.K, a.ldb, kBN, 64));
   const bool out_f32 = (MODE == EPI_F32 || MODE == EPI_RES_LN);
   // stores go out per epilogue warp: 32-row boxes
-  RVK_TRY(rvk_make_tmap_2d(&tmOut, a.out, out_f32 ? RVK_F32 : RVK_BF16, p.M, p.N, a.ldo, 32, out_f32 ? 32 : 64));
+  if (MODE == EPI_RES_LN && p.out_tiled != nullptr) tmOut = tmA;   // x' leaves through registers, not TMA
+  else RVK_TRY(rvk_make_tmap_2d(&tmOut, a.out, out_f32 ? RVK_F32 : RVK_BF16, p.M, p.N, a.ldo, 32, out_f32 ? 32 : 64));
   tmOut2 = tmOut;
   tmAux = tmOut;
   if (p.has_out2) {
@@ -66,7 +68,7 @@ int launch_nt(const GemmNtArgs& a, cudaStream_t stream) {
   if (MODE == EPI_DGELU) {
     if (a.aux == nullptr) return RVK_ERR_BAD_ARG;
     RVK_TRY(rvk_make_tmap_2d(&tmAux, a.aux, RVK_BF16, p.M, p.N, a.ldaux, 128, 64));
-  } else if (MODE == EPI_RES_LN && p.has_res && p.res_table == nullptr) {
+  } else if (MODE == EPI_RES_LN && p.has_res && p.res_table == nullptr && p.out_tiled == nullptr) {
     if (a.aux == nullptr) return RVK_ERR_BAD_ARG;
     RVK_TRY(rvk_make_tmap_2d(&tmAux, a.aux, RVK_F32, p.M, p.N, a.ldaux, 128, 32));
   }
@@ -82,7 +84,10 @@ int launch_nt(const GemmNtArgs& a, cudaStream_t stream) {
 int rvk_gemm_nt_launch(const GemmNtArgs& a, cudaStream_t stream) {
   const GemmNtParams& p = a.p;
   if (p.M <= 0) return RVK_OK;
-  if (p.N <= 0 || p.K <= 0 || a.A == nullptr || a.B == nullptr || a.out == nullptr) return RVK_ERR_BAD_ARG;
+  const bool tiled_out = a.mode == EPI_RES_LN && p.out_tiled != nullptr;
+  if (p.N <= 0 || p.K <= 0 || a.A == nullptr || a.B == nullptr || (a.out == nullptr && !tiled_out)) return RVK_ERR_BAD_ARG;
+  if (!tiled_out && p.res_tiled != nullptr) return RVK_ERR_BAD_ARG;
+  if (tiled_out && p.has_res && p.res_table == nullptr && p.res_tiled == nullptr) return RVK_ERR_BAD_ARG;
   if (p.N % kBN != 0 || p.N > 768 || p.K % 64 != 0) return RVK_ERR_UNSUPPORTED_SHAPE;
   switch (a.mode) {
     case EPI_BF16: return launch_nt<EPI_BF16>(a, stream);
@@ -127,6 +132,56 @@ int rvk_gemm_tn_launch(const void* A, int64_t lda, const void* B, int64_t ldb, f
   ScopedTimer timer(stream, 2.0 * M * P * Q);
   kernel<<<dim3(tiles, splits), kTnThreads, L::kTotal, stream>>>(tmA, tmB, p);
   return rvk_launch_check();
+}
+
+// ---- fused MLP block (fc1 + GELU + fc2 + residual + LayerNorm), inference path ---------------------------
+template <int G>
+static int launch_mlp_fused(const MlpFusedArgs& a, cudaStream_t stream) {
+  using L = MlpSmem<G>;
+  auto kernel = mlp_fused_kernel<G>;
+  static bool configured = false;
+  if (!configured) {
+    RVK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  const MlpFusedParams& p = a.p;
+  CUtensorMap tmA, tmW1, tmW2, tmLn;
+  RVK_TRY(rvk_make_tmap_2d(&tmA, a.ln_in, RVK_BF16, p.M, 192, 192, 128, 64));
+  RVK_TRY(rvk_make_tmap_2d(&tmW1, a.w1, RVK_BF16, 768, 192, 192, 128 / G, 64));
+  RVK_TRY(rvk_make_tmap_2d(&tmW2, a.w2, RVK_BF16, 192, 768, 768, 192 / G, 64));
+  tmLn = tmA;
+  if (p.has_ln) RVK_TRY(rvk_make_tmap_2d(&tmLn, a.ln_out, RVK_BF16, p.M, 192, 192, 32, 64));
+  const int tiles = (p.M + 127) / 128;
+  const int units = (tiles + G - 1) / G;
+  const int max_clusters = kNumSMsB200 / G;
+  const int clusters = units < max_clusters ? units : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * G);
+  cfg.blockDim = dim3(kMlpThreads);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = G;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ScopedTimer timer(stream, 2.0 * p.M * 192.0 * 768.0 * 2.0);
+  RVK_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, tmA, tmW1, tmW2, tmLn, p));
+  return rvk_launch_check();
+}
+
+int rvk_mlp_fused_launch(const MlpFusedArgs& a, cudaStream_t stream) {
+  const MlpFusedParams& p = a.p;
+  if (p.M <= 0) return RVK_OK;
+  if (a.ln_in == nullptr || a.w1 == nullptr || a.w2 == nullptr || p.x_in == nullptr || p.x_out == nullptr ||
+      p.b1 == nullptr || p.b2 == nullptr)
+    return RVK_ERR_BAD_ARG;
+  if (p.has_ln && (a.ln_out == nullptr || p.gamma == nullptr || p.beta == nullptr)) return RVK_ERR_BAD_ARG;
+  if (a.cta_group == 1) return launch_mlp_fused<1>(a, stream);
+  if (a.cta_group == 2) return launch_mlp_fused<2>(a, stream);
+  return RVK_ERR_BAD_ARG;
 }
 
 void rvk_gemm_timing_enable_impl(int on) { g_timing = on != 0; }

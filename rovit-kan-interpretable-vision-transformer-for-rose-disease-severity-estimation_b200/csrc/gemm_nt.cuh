@@ -45,6 +45,11 @@ struct GemmNtParams {
   float* rstd_out;          // [M] or nullptr
   int has_out2;             // EPI_GELU: also store z;  EPI_RES_LN: also store LN output
   int has_res;              // EPI_RES_LN: 0 = no residual at all
+  // EPI_RES_LN, inference path: the fp32 token stream in the tiled layout of common.cuh (xt_offset).  With
+  // out_tiled set, x' is written straight from registers (coalesced, no smem panels / TMA) and the residual
+  // comes from res_tiled (or the table); `out` / `aux` are then unused.
+  const float* res_tiled;
+  float* out_tiled;
 };
 
 constexpr int kGemmThreads = 480;
@@ -73,12 +78,12 @@ __device__ __forceinline__ int panels_per_tile(const GemmNtParams& p) {
   if (MODE == EPI_BF16 || MODE == EPI_DGELU) return BN / 64;
   if (MODE == EPI_GELU) return (BN / 64) * (p.has_out2 ? 2 : 1);
   if (MODE == EPI_F32) return BN / 32;
-  return 6 + (p.has_out2 ? 3 : 0);   // EPI_RES_LN
+  return (p.out_tiled != nullptr ? 0 : 6) + (p.has_out2 ? 3 : 0);   // EPI_RES_LN
 }
 template <int BN, int MODE>
 __device__ __forceinline__ bool panel_has_aux(const GemmNtParams& p, int i) {
   if (MODE == EPI_DGELU) return true;
-  if (MODE == EPI_RES_LN) return i < 6 && p.has_res && p.res_table == nullptr;
+  if (MODE == EPI_RES_LN) return p.out_tiled == nullptr && i < 6 && p.has_res && p.res_table == nullptr;
   return false;
 }
 
@@ -345,15 +350,36 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       } else {   // EPI_RES_LN
         float sum = 0.0f;
-        const bool tma_res = p.has_res && p.res_table == nullptr;
+        const bool tiled = p.out_tiled != nullptr;
+        const bool tma_res = !tiled && p.has_res && p.res_table == nullptr;
         const float* trow =
             (p.res_table != nullptr) ? p.res_table + static_cast<size_t>((m0 + row) % p.table_rows) * 192 : nullptr;
-        const uint32_t cnt0 = cnt;          // panel c of this tile belongs to team (cnt0 + c) % kNumTeams
+        const uint32_t cnt0 = cnt;          // panel c of this tile belongs to team panel_team(c)
+        auto panel_team = [&](int c) -> uint32_t {
+          return tiled ? static_cast<uint32_t>(tile_iter + c) % kNumTeams : (cnt0 + c) % kNumTeams;
+        };
+        const int grow = m0 + row;
+        const bool rvalid = grow < p.M;
 #pragma unroll 1
         for (int c = 0; c < 6; ++c) {
-          if (!mine()) { ++cnt; continue; }
+          if (panel_team(c) != static_cast<uint32_t>(team)) { if (!tiled) ++cnt; continue; }
           float v[32];
           load32(tacc + c * 32, c * 32, v);
+          if (tiled) {
+            const size_t xo = xt_offset(rvalid ? grow : 0, c, 0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.res_tiled != nullptr) { if (rvalid) r = *reinterpret_cast<const float4*>(p.res_tiled + xo + j * 128); }
+              else if (trow != nullptr) r = *reinterpret_cast<const float4*>(trow + c * 32 + j * 4);
+              float4 q = make_float4(v[j * 4 + 0] + r.x, v[j * 4 + 1] + r.y, v[j * 4 + 2] + r.z, v[j * 4 + 3] + r.w);
+              v[j * 4 + 0] = q.x; v[j * 4 + 1] = q.y; v[j * 4 + 2] = q.z; v[j * 4 + 3] = q.w;
+              sum += (q.x + q.y) + (q.z + q.w);
+              if (rvalid) *reinterpret_cast<float4*>(p.out_tiled + xo + j * 128) = q;
+            }
+            if (p.has_out2) tmem_st32(tacc + c * 32, v);
+            continue;
+          }
           int slot;
           uint8_t* po = acquire(slot);
 #pragma unroll
@@ -380,7 +406,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float var = 0.0f;
 #pragma unroll 1
           for (int c = 0; c < 6; ++c) {
-            if ((cnt0 + c) % kNumTeams != static_cast<uint32_t>(team)) continue;
+            if (panel_team(c) != static_cast<uint32_t>(team)) continue;
             float v[32];
             tmem_ld32(tacc + c * 32, v);
 #pragma unroll

@@ -7,6 +7,7 @@
 
 #include "gemm_nt.cuh"
 #include "gemm_tn.cuh"
+#include "mlp_fused.cuh"
 
 // ---- tcgen05 GEMMs -----------------------------------------------------------------------------
 struct GemmNtArgs {
@@ -29,6 +30,18 @@ int rvk_gemm_nt_launch(const GemmNtArgs& a, cudaStream_t stream);
 int rvk_gemm_tn_launch(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int M, int P,
                        int Q, float scale, cudaStream_t stream);
 
+// fused MLP block of the inference path: x_out = x_in + fc2(gelu(fc1(ln_in))) (+ LayerNorm -> ln_out); the fp32
+// token stream x uses the tiled layout of common.cuh (xt_offset).  cta_group: 2 = CTA pairs (default), 1 = single CTAs.
+struct MlpFusedArgs {
+  const void* ln_in = nullptr;    // bf16 [M,192]
+  const void* w1 = nullptr;       // bf16 [768,192]
+  const void* w2 = nullptr;       // bf16 [192,768]
+  void* ln_out = nullptr;         // bf16 [M,192] (has_ln)
+  int cta_group = 2;
+  MlpFusedParams p{};
+};
+int rvk_mlp_fused_launch(const MlpFusedArgs& a, cudaStream_t stream);
+
 // ---- attention -----------------------------------------------------------------------------------
 int rvk_attention_fwd_launch(const void* qkv, void* ctx, float* lse, int batch, cudaStream_t stream);
 int rvk_attention_bwd_launch(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
@@ -43,6 +56,9 @@ int rvk_cast_transpose_bf16_launch(const float* src, void* dst, int rows, int co
 int rvk_layernorm_fwd_launch(const float* x, int64_t x_row_stride, const float* gamma, const float* beta, float eps,
                              void* y, int y_is_bf16, int64_t y_row_stride, float* mean, float* rstd, int rows,
                              cudaStream_t stream);
+// LayerNorm of rows r * token_row_stride (r < rows) of the TILED fp32 token stream (common.cuh xt_offset) -> fp32 y
+int rvk_layernorm_fwd_tiled_launch(const float* x_tiled, int64_t token_row_stride, const float* gamma, const float* beta,
+                                   float eps, float* y, int64_t y_row_stride, int rows, cudaStream_t stream);
 // dx_out = dx_in + LN'(g) (dx_in may be null; dx_out may alias dx_in); g is bf16 or fp32 with row stride g_stride
 int rvk_layernorm_bwd_launch(const void* g, int g_is_bf16, int64_t g_row_stride, const float* x, int64_t x_row_stride,
                              const float* mean, const float* rstd, const float* gamma, const float* dx_in,

@@ -1,0 +1,77 @@
+"""GPU parity of the fused MLP block kernel (fc1 + GELU + fc2 + residual + LayerNorm in one tcgen05 kernel, the
+hidden activation never leaving the SM) against an fp32 restatement of timm's Block MLP half on the same
+bf16-rounded operands (oracle/vit.py::_Block).  Both the CTA-pair (cta_group::2) and the single-CTA variant.
+Tolerances: the hidden activation is rounded to bf16 once (2^-9 relative) before fc2, as in the unfused path;
+x_out is fp32 (accumulation-order noise only on top of that), ln_out carries one more bf16 rounding."""
+
+import pytest
+import torch
+
+from conftest import assert_close
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from rovitkan_b200 import _lib
+
+DEV = 'cuda'
+
+
+def to_tiled(x):
+    """[M,192] fp32 -> tiled token stream (include/rovitkan.h, rvk_mlp_fused), rows padded to 128."""
+    M = x.shape[0]
+    Mp = (M + 127) // 128 * 128
+    xp = torch.zeros(Mp, 192, device=x.device, dtype=x.dtype)
+    xp[:M] = x
+    return xp.view(Mp // 32, 32, 6, 8, 4).permute(0, 2, 3, 1, 4).contiguous()
+
+
+def from_tiled(t, M):
+    return t.permute(0, 3, 1, 2, 4).reshape(-1, 192)[:M]
+
+
+def gelu(x):
+    return 0.5 * x * (1 + torch.erf(x / 2 ** 0.5))
+
+
+def run_case(M, G, has_ln, seed=0, inplace=False):
+    g = torch.Generator().manual_seed(seed)
+    ln_in = torch.randn(M, 192, generator=g).to(DEV).to(torch.bfloat16)
+    w1 = (torch.randn(768, 192, generator=g) * 0.08).to(DEV).to(torch.bfloat16)
+    w2 = (torch.randn(192, 768, generator=g) * 0.05).to(DEV).to(torch.bfloat16)
+    b1 = (torch.randn(768, generator=g) * 0.5).to(DEV)
+    b2 = torch.randn(192, generator=g).to(DEV)
+    gamma = (1 + 0.2 * torch.randn(192, generator=g)).to(DEV)
+    beta = (0.3 * torch.randn(192, generator=g)).to(DEV)
+    x = (2.0 * torch.randn(M, 192, generator=g)).to(DEV)
+    xt = to_tiled(x)
+    xo = xt if inplace else torch.full_like(xt, float('nan'))
+    ln_out = torch.full((M, 192), float('nan'), device=DEV, dtype=torch.bfloat16) if has_ln else None
+    _lib.call('rvk_mlp_fused', ln_in.data_ptr(), w1.data_ptr(), w2.data_ptr(), b1.data_ptr(), b2.data_ptr(),
+              xt.data_ptr(), xo.data_ptr(), gamma.data_ptr() if has_ln else 0, beta.data_ptr() if has_ln else 0, 1e-6,
+              ln_out.data_ptr() if has_ln else 0, M, G, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    h = gelu(ln_in.float() @ w1.float().t() + b1).to(torch.bfloat16).float()
+    ref = x + h @ w2.float().t() + b2
+    got = from_tiled(xo, M)
+    assert_close(got, ref, rtol=2e-3, atol=2e-3, scale_tol=1e-3, what=f'mlp_fused x_out M={M} G={G}')
+    if has_ln:
+        ref_ln = torch.nn.functional.layer_norm(ref, (192,), gamma, beta, 1e-6)
+        assert_close(ln_out.float(), ref_ln, rtol=1e-2, atol=1e-2, what=f'mlp_fused ln_out M={M} G={G}')
+        assert bool(torch.isfinite(ln_out.float()).all())
+
+
+@pytest.mark.parametrize('M', [128, 300, 1000, 197 * 64])
+def test_mlp_fused_single_cta(M):
+    run_case(M, 1, True, seed=M)
+
+
+@pytest.mark.parametrize('M', [128, 256, 300, 1000, 197 * 64, 197 * 300 + 5])
+def test_mlp_fused_cta_pair(M):
+    run_case(M, 2, True, seed=M + 1)
+
+
+@pytest.mark.parametrize('G', [1, 2])
+def test_mlp_fused_no_layernorm_in_place(G):
+    run_case(1000, G, False, seed=7, inplace=True)
+    run_case(197 * 40, G, True, seed=8, inplace=True)

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 rm -f gpurun_out/summary.txt
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.used --format=csv > gpurun_out/nvsmi.txt 2>&1
 if [ "${1:-tests}" = "tests" ]; then
-for f in test_gpu_gemm test_gpu_encoder_kernels test_gpu_heads test_gpu_model; do
+for f in ${GPU_TEST_FILES:-test_gpu_mlp_fused test_gpu_gemm test_gpu_encoder_kernels test_gpu_heads test_gpu_model}; do
   echo "=== $f" | tee -a gpurun_out/summary.txt
   timeout 420 python -m pytest tests/$f.py -q -m gpu --no-header -rN -s > gpurun_out/$f.log 2>&1
   echo "exit $?" | tee -a gpurun_out/summary.txt
