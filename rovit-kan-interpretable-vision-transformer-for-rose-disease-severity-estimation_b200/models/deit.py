@@ -104,7 +104,7 @@ class VisionTransformerB200(nn.Module):
         ops = _ops()
         if self._state is None:
             self._state = ops.EncoderState()
-        return ops.EncoderFn.apply(self._state, x, *self._ordered_params())
+        return ops.EncoderFn.apply(self._state, *ops.nograd(x, *self._ordered_params()))
 
 
 def create_model(name: str = 'deit_tiny_patch16_224', pretrained: bool = False, num_classes: int = 0, **kwargs):

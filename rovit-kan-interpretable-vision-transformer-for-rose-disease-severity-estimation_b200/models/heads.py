@@ -15,7 +15,8 @@ from ._bootstrap import ops as _ops
 
 
 def _linear(x, lin: nn.Linear, relu: bool = False, drop_p: float = 0.0, clamp=None):
-    return _ops().LinearFn.apply(x, lin.weight, lin.bias, relu, drop_p, clamp)
+    ops = _ops()
+    return ops.LinearFn.apply(*ops.nograd(x, lin.weight, lin.bias), relu, drop_p, clamp)
 
 
 class _HeadBase(nn.Module):

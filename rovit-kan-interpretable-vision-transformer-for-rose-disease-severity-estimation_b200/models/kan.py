@@ -59,8 +59,9 @@ class KANLayer(nn.Module):
         return self._knots_host
 
     def _forward_act(self, x: torch.Tensor, act: int) -> torch.Tensor:
-        return _ops().KanLayerFn.apply(x, self.spline_weights, self.linear.weight, self.linear.bias,
-                                       self.knots_host(), act)
+        ops = _ops()
+        return ops.KanLayerFn.apply(*ops.nograd(x, self.spline_weights, self.linear.weight, self.linear.bias),
+                                    self.knots_host(), act)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self._forward_act(x, 0)

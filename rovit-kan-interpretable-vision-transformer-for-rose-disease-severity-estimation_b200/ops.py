@@ -28,6 +28,14 @@ def _p(t) -> int:
     return 0 if t is None else t.data_ptr()
 
 
+def nograd(*tensors):
+    """Under torch.no_grad() hand the Functions detached tensors: `ctx.needs_input_grad` reflects requires_grad of
+    the inputs even when grad mode is off, and would otherwise select the activation-saving training kernels."""
+    if torch.is_grad_enabled():
+        return tensors
+    return tuple(t.detach() if isinstance(t, torch.Tensor) else t for t in tensors)
+
+
 def require_cuda(t: torch.Tensor, what: str) -> None:
     if not t.is_cuda:
         raise RuntimeError(
@@ -242,7 +250,7 @@ class EncoderFn(torch.autograd.Function):
         img = _f32c(images)
         batch = img.shape[0]
         dev = img.device
-        training = any(ctx.needs_input_grad[2:])
+        training = any(ctx.needs_input_grad[2:])      # callers pass detached tensors under torch.no_grad()
         chunk = CHUNK_IMAGES
         feats = torch.empty(batch, 192, device=dev, dtype=torch.float32)
         pc = [p.detach() for p in params]
