@@ -117,14 +117,19 @@ int rvk_gemm_nt(int mode, const void* a_bf16, int64_t lda, const void* b_bf16, i
                 void* out2, int64_t ldo2, const void* aux, int64_t ldaux, int m, int n, int k, const float* bias,
                 const float* gamma, const float* beta, const float* res_table, int table_rows, float ln_eps,
                 float* mean_out, float* rstd_out, void* stream);
-/* Fused MLP half of a DeiT block (timm Block.forward: x + mlp(norm2(x)), plus the NEXT LayerNorm), inference path:
- *   x_out = x_in + fc2(gelu(fc1(ln_in) + b1)) + b2;   ln_out = LayerNorm(x_out)*gamma + beta  (ln_out may be NULL).
- * ln_in / ln_out bf16 [m,192]; w1 bf16 [768,192]; w2 bf16 [192,768]; x_in / x_out fp32 in the TILED token-stream
- * layout (element (r,c) at (((r/32)*6 + c/32)*8 + (c%32)/4)*128 + (r%32)*4 + c%4, rows padded to 128; x_out may
- * alias x_in).  cta_group: 2 = CTA pairs sharing one tcgen05.mma.cta_group::2 (default), 1 = single CTAs. */
-int rvk_mlp_fused(const void* ln_in_bf16, const void* w1_bf16, const void* w2_bf16, const float* b1, const float* b2,
-                  const float* x_in_tiled, float* x_out_tiled, const float* gamma, const float* beta, float eps,
-                  void* ln_out_bf16, int m, int cta_group, void* stream);
+/* Fused MLP half of a DeiT block (timm Block.forward: x + mlp(norm2(x)), plus the NEXT block's norm1), inference path:
+ *   x_out = x_in + fc2(gelu(fc1(LayerNorm(x_in)*gamma2 + beta2) + b1)) + b2;   ln_out = LayerNorm(x_out)*gamma + beta
+ * (ln_out may be NULL).  Neither the normalised input nor the hidden activation is written to memory.
+ * x_in / x_out fp32 in the TILED token-stream layout (element (r,c) at
+ * (((r/32)*6 + c/32)*8 + (c%32)/4)*128 + (r%32)*4 + c%4, rows padded to 128; x_out may alias x_in); w1 bf16 [768,192];
+ * w2 FP16 [192,768] (the hidden activation stays on chip in fp16: GELU runs as packed half2 arithmetic); ln_out bf16
+ * [m,192].  cta_group: 2 = CTA pairs sharing one tcgen05.mma.cta_group::2 (default), 1 = single CTAs. */
+int rvk_mlp_fused(const float* x_in_tiled, float* x_out_tiled, const float* gamma2, const float* beta2,
+                  const void* w1_bf16, const float* b1, const void* w2_f16, const float* b2, const float* gamma,
+                  const float* beta, float eps, void* ln_out_bf16, int m, int cta_group, void* stream);
+/* Debugging aid: device buffer of 4*512 int64 into which the following rvk_mlp_fused launches log clock64 events
+ * of CTA 0 (NULL switches it off, the default). */
+void rvk_debug_set_mlp_trace(void* device_buf);
 /* C[P,Q] (fp32) += scale * A[M,P]^T B[M,Q], bf16 operands (weight gradients). */
 int rvk_gemm_tn(const void* a_bf16, int64_t lda, const void* b_bf16, int64_t ldb, float* c, int64_t ldc, int m,
                 int p, int q, float scale, void* stream);

@@ -1,6 +1,8 @@
 // extern "C" surface declared in include/rovitkan.h: argument checking + dispatch to the launchers.
 #include "../../include/rovitkan.h"
 
+#include <cstdlib>
+
 #include "encoder.h"
 #include "kernels.h"
 
@@ -23,6 +25,8 @@ int fill_kan_desc(KanLayerDesc& L, const float* spline, const float* lin_w, cons
   return RVK_OK;
 }
 }  // namespace
+
+static long long* g_mlp_trace = nullptr;
 
 #pragma GCC visibility push(default)
 extern "C" {
@@ -200,17 +204,21 @@ int rvk_gemm_nt(int mode, const void* a_bf16, int64_t lda, const void* b_bf16, i
   a.p.has_res = (aux != nullptr || res_table != nullptr) ? 1 : 0;
   return rvk_gemm_nt_launch(a, S(stream));
 }
-int rvk_mlp_fused(const void* ln_in_bf16, const void* w1_bf16, const void* w2_bf16, const float* b1, const float* b2,
-                  const float* x_in_tiled, float* x_out_tiled, const float* gamma, const float* beta, float eps,
-                  void* ln_out_bf16, int m, int cta_group, void* stream) {
+int rvk_mlp_fused(const float* x_in_tiled, float* x_out_tiled, const float* gamma2, const float* beta2,
+                  const void* w1_bf16, const float* b1, const void* w2_f16, const float* b2, const float* gamma,
+                  const float* beta, float eps, void* ln_out_bf16, int m, int cta_group, void* stream) {
   if (m < 0) return RVK_ERR_BAD_ARG;
   MlpFusedArgs a;
-  a.ln_in = ln_in_bf16; a.w1 = w1_bf16; a.w2 = w2_bf16; a.ln_out = ln_out_bf16;
+  a.w1 = w1_bf16; a.w2_f16 = w2_f16; a.ln_out = ln_out_bf16;
   a.cta_group = cta_group;
-  a.p.M = m; a.p.x_in = x_in_tiled; a.p.x_out = x_out_tiled; a.p.b1 = b1; a.p.b2 = b2;
-  a.p.gamma = gamma; a.p.beta = beta; a.p.eps = eps; a.p.has_ln = ln_out_bf16 != nullptr ? 1 : 0;
+  a.p.M = m; a.p.x_in = x_in_tiled; a.p.x_out = x_out_tiled; a.p.gamma2 = gamma2; a.p.beta2 = beta2;
+  a.p.b1 = b1; a.p.b2 = b2; a.p.gamma = gamma; a.p.beta = beta; a.p.eps = eps;
+  a.p.has_ln = ln_out_bf16 != nullptr ? 1 : 0;
+  a.p.trace = g_mlp_trace;
   return rvk_mlp_fused_launch(a, S(stream));
 }
+/* debugging aid (not part of the product path): device buffer of 4*512 int64 that the next rvk_mlp_fused launches log clock events into */
+void rvk_debug_set_mlp_trace(void* buf) { g_mlp_trace = static_cast<long long*>(buf); }
 int rvk_gemm_tn(const void* a_bf16, int64_t lda, const void* b_bf16, int64_t ldb, float* c, int64_t ldc, int m, int p,
                 int q, float scale, void* stream) {
   if (m < 0) return RVK_ERR_BAD_ARG;

@@ -339,8 +339,16 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t smem_addr, uint32_t cta) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta));
   return r;
 }
+// Arrive on a barrier of the pair's leader.  Default semantics (release at CTA scope): a cluster-scope release
+// compiles to MEMBAR.ALL.GPU + ERRBAR and waits for every outstanding global access of the warp (measured: 20% of
+// the fused MLP kernel's stall samples).  What the leader's UMMA needs -- this warp's shared-memory writes visible
+// to the async proxy -- is established by fence.proxy.async.shared::cta BEFORE the arrive, as CUTLASS' 2-SM
+// pipelines do.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
@@ -399,6 +407,34 @@ __device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc,
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Descriptor halves for a K-major, 128-byte-swizzled operand tile (LBO 16 B, SBO 1024 B): the high word is constant
+// and the low word is (smem address >> 4) | LBO field, so stepping K by 16 bf16 (32 bytes) is `lo + 2`.  Splitting the
+// descriptor keeps the UMMA issue loop at a few uniform-datapath instructions per MMA.
+constexpr uint32_t kUmmaDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+template <int G>
+__device__ __forceinline__ void umma_f16_split(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  if (G == 2) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHiSw128)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "mov.b64 da, {%1, %5};\n\t"
+        "mov.b64 db, {%2, %5};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHiSw128)
+        : "memory");
+  }
+}
+
 // arrives on the barrier at this smem offset in BOTH CTAs of the pair once all prior UMMAs have completed
 __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
   asm volatile(

@@ -29,6 +29,7 @@ struct WeightLayout {
   size_t patch_w;                    // [192,768]
   size_t qkv[kDepth], proj[kDepth], fc1[kDepth], fc2[kDepth];          // torch layout [out,in]
   size_t qkvT[kDepth], projT[kDepth], fc1T[kDepth], fc2T[kDepth];      // transposed [in,out] (training only)
+  size_t fc2h[kDepth];               // fp16 copy of fc2 for the fused inference MLP (hidden activation in fp16)
   size_t table;                      // fp32 [197,192]
   size_t total;
 };
@@ -42,6 +43,7 @@ WeightLayout weight_layout(bool training) {
     L.proj[i] = take(size_t(kD) * kD * 2);
     L.fc1[i] = take(size_t(kMlp) * kD * 2);
     L.fc2[i] = take(size_t(kD) * kMlp * 2);
+    if (!training) L.fc2h[i] = take(size_t(kD) * kMlp * 2);
     if (training) {
       L.qkvT[i] = take(size_t(kQkv) * kD * 2);
       L.projT[i] = take(size_t(kD) * kD * 2);
@@ -195,6 +197,7 @@ int rvk_encoder_prepare_weights_impl(const void* const* params, void* wbuf, int 
     RVK_TRY(rvk_cast_bf16_launch(P(params, bp(i, B_PROJW)), at(wbuf, W.proj[i]), int64_t(kD) * kD, s));
     RVK_TRY(rvk_cast_bf16_launch(P(params, bp(i, B_FC1W)), at(wbuf, W.fc1[i]), int64_t(kMlp) * kD, s));
     RVK_TRY(rvk_cast_bf16_launch(P(params, bp(i, B_FC2W)), at(wbuf, W.fc2[i]), int64_t(kD) * kMlp, s));
+    if (!training) RVK_TRY(rvk_cast_f16_launch(P(params, bp(i, B_FC2W)), at(wbuf, W.fc2h[i]), int64_t(kD) * kMlp, s));
     if (training) {
       RVK_TRY(rvk_cast_transpose_bf16_launch(P(params, bp(i, B_QKVW)), at(wbuf, W.qkvT[i]), kQkv, kD, s));
       RVK_TRY(rvk_cast_transpose_bf16_launch(P(params, bp(i, B_PROJW)), at(wbuf, W.projT[i]), kD, kD, s));
@@ -240,18 +243,20 @@ int rvk_encoder_forward_impl(const void* const* params, const void* wbuf, const 
         const BlockSaved& B = A.blk[i];
         RVK_TRY(gemm_plain(ln, kD, at(wbuf, W.qkv[i]), kD, b16(B.qkv, kQkv), kQkv, M, kQkv, kD, P(params, bp(i, B_QKVB)), s));
         RVK_TRY(rvk_attention_fwd_launch(b16(B.qkv, kQkv), b16(B.ctx, kD), nullptr, nb, s));
-        RVK_TRY(gemm_res_ln(b16(B.ctx, kD), kD, kD, at(wbuf, W.proj[i]), P(params, bp(i, B_PROJB)), x, nullptr, x, ln,
-                            P(params, bp(i, B_N2W)), P(params, bp(i, B_N2B)), nullptr, nullptr, M, s, true));
+        // x += proj(ctx); LayerNorm2 is applied on load by the MLP kernel, so no normalised copy is written
+        RVK_TRY(gemm_res_ln(b16(B.ctx, kD), kD, kD, at(wbuf, W.proj[i]), P(params, bp(i, B_PROJB)), x, nullptr, x, nullptr,
+                            nullptr, nullptr, nullptr, nullptr, M, s, true));
         const bool last = (i == kDepth - 1);
         MlpFusedArgs m;
-        m.ln_in = ln; m.w1 = at(wbuf, W.fc1[i]); m.w2 = at(wbuf, W.fc2[i]);
+        m.w1 = at(wbuf, W.fc1[i]); m.w2_f16 = at(wbuf, W.fc2h[i]);
         m.ln_out = last ? nullptr : ln;
         m.cta_group = mlp_cta_group();
         m.p.M = M; m.p.x_in = x; m.p.x_out = x;
+        m.p.gamma2 = P(params, bp(i, B_N2W)); m.p.beta2 = P(params, bp(i, B_N2B));
         m.p.b1 = P(params, bp(i, B_FC1B)); m.p.b2 = P(params, bp(i, B_FC2B));
         m.p.gamma = last ? nullptr : P(params, bp(i + 1, B_N1W));
         m.p.beta = last ? nullptr : P(params, bp(i + 1, B_N1B));
-        m.p.eps = kLnEps; m.p.has_ln = last ? 0 : 1;
+        m.p.eps = kLnEps; m.p.has_ln = last ? 0 : 1; m.p.trace = nullptr;
         RVK_TRY(rvk_mlp_fused_launch(m, s));
       }
       RVK_TRY(rvk_layernorm_fwd_tiled_launch(x, kTok, P(params, P_NORM_W), P(params, P_NORM_B), kLnEps,

@@ -2,6 +2,8 @@
 // LayerNorm forward/backward (warp per 192-wide row), bf16 casts, column sums for bias gradients and
 // the batch reduction of the token-0 gradients.  All rows are 192 fp32 = 768 B = 6 coalesced 128 B
 // lines; a warp owns a row and each lane 6 columns (lane + 32*i), so every access is a full line.
+#include <cuda_fp16.h>
+
 #include "kernels.h"
 
 namespace {
@@ -53,6 +55,11 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
   } else {
     for (long long j = i; j < n; ++j) dst[j] = __float2bfloat16(src[j]);
   }
+}
+
+__global__ void cast_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, long long n) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = __float2half_rn(src[i]);
 }
 
 // dst[c][r] = bf16(src[r][c]) through a padded 32x32 tile
@@ -227,6 +234,12 @@ int rvk_cast_bf16_launch(const float* src, void* dst, int64_t n, cudaStream_t st
   if (n <= 0) return RVK_OK;
   const long long quads = (n + 3) / 4;
   cast_bf16_kernel<<<static_cast<unsigned>((quads + 255) / 256), 256, 0, stream>>>(src, static_cast<__nv_bfloat16*>(dst), n);
+  return rvk_launch_check();
+}
+
+int rvk_cast_f16_launch(const float* src, void* dst, int64_t n, cudaStream_t stream) {
+  if (n <= 0) return RVK_OK;
+  cast_f16_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, stream>>>(src, static_cast<__half*>(dst), n);
   return rvk_launch_check();
 }
 

@@ -145,11 +145,10 @@ static int launch_mlp_fused(const MlpFusedArgs& a, cudaStream_t stream) {
     configured = true;
   }
   const MlpFusedParams& p = a.p;
-  CUtensorMap tmA, tmW1, tmW2, tmLn;
-  RVK_TRY(rvk_make_tmap_2d(&tmA, a.ln_in, RVK_BF16, p.M, 192, 192, 128, 64));
+  CUtensorMap tmW1, tmW2, tmLn;
   RVK_TRY(rvk_make_tmap_2d(&tmW1, a.w1, RVK_BF16, 768, 192, 192, 128 / G, 64));
-  RVK_TRY(rvk_make_tmap_2d(&tmW2, a.w2, RVK_BF16, 192, 768, 768, 192 / G, 64));
-  tmLn = tmA;
+  RVK_TRY(rvk_make_tmap_2d(&tmW2, a.w2_f16, RVK_BF16 /* 2-byte elements */, 192, 768, 768, 192 / G, 64));
+  tmLn = tmW1;
   if (p.has_ln) RVK_TRY(rvk_make_tmap_2d(&tmLn, a.ln_out, RVK_BF16, p.M, 192, 192, 32, 64));
   const int tiles = (p.M + 127) / 128;
   const int units = (tiles + G - 1) / G;
@@ -168,15 +167,15 @@ static int launch_mlp_fused(const MlpFusedArgs& a, cudaStream_t stream) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   ScopedTimer timer(stream, 2.0 * p.M * 192.0 * 768.0 * 2.0);
-  RVK_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, tmA, tmW1, tmW2, tmLn, p));
+  RVK_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, tmW1, tmW2, tmLn, p));
   return rvk_launch_check();
 }
 
 int rvk_mlp_fused_launch(const MlpFusedArgs& a, cudaStream_t stream) {
   const MlpFusedParams& p = a.p;
   if (p.M <= 0) return RVK_OK;
-  if (a.ln_in == nullptr || a.w1 == nullptr || a.w2 == nullptr || p.x_in == nullptr || p.x_out == nullptr ||
-      p.b1 == nullptr || p.b2 == nullptr)
+  if (a.w1 == nullptr || a.w2_f16 == nullptr || p.x_in == nullptr || p.x_out == nullptr || p.b1 == nullptr ||
+      p.b2 == nullptr || p.gamma2 == nullptr || p.beta2 == nullptr)
     return RVK_ERR_BAD_ARG;
   if (p.has_ln && (a.ln_out == nullptr || p.gamma == nullptr || p.beta == nullptr)) return RVK_ERR_BAD_ARG;
   if (a.cta_group == 1) return launch_mlp_fused<1>(a, stream);

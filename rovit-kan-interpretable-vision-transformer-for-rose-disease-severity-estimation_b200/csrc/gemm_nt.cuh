@@ -356,22 +356,42 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             (p.res_table != nullptr) ? p.res_table + static_cast<size_t>((m0 + row) % p.table_rows) * 192 : nullptr;
         const uint32_t cnt0 = cnt;          // panel c of this tile belongs to team panel_team(c)
         auto panel_team = [&](int c) -> uint32_t {
-          return tiled ? static_cast<uint32_t>(tile_iter + c) % kNumTeams : (cnt0 + c) % kNumTeams;
+          return tiled ? static_cast<uint32_t>(c) % kNumTeams : (cnt0 + c) % kNumTeams;   // fixed: batch-invariant sums
         };
         const int grow = m0 + row;
         const bool rvalid = grow < p.M;
+        if (tiled && p.res_tiled != nullptr && (lane & 7) == 0) {
+          // next tile's residual rows -> L2 (one 128-byte line per 8 lanes, this team's two panels)
+          const int nrow = grow + static_cast<int>(gridDim.x) * 128;
+          if (t + static_cast<int>(gridDim.x) < num_tiles && nrow < p.M) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const float* xp = p.res_tiled + xt_offset(nrow, team + 3 * k, 0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) prefetch_l2(xp + j * 128);
+            }
+          }
+        }
 #pragma unroll 1
         for (int c = 0; c < 6; ++c) {
           if (panel_team(c) != static_cast<uint32_t>(team)) { if (!tiled) ++cnt; continue; }
+          float4 res4[8];
+          if (tiled) {   // residual loads (L2-prefetched one tile ahead) are in flight while the accumulator is read
+            const size_t xo = xt_offset(rvalid ? grow : 0, c, 0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              res4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.res_tiled != nullptr) { if (rvalid) res4[j] = *reinterpret_cast<const float4*>(p.res_tiled + xo + j * 128); }
+              else if (trow != nullptr) res4[j] = *reinterpret_cast<const float4*>(trow + c * 32 + j * 4);
+            }
+          }
           float v[32];
           load32(tacc + c * 32, c * 32, v);
           if (tiled) {
             const size_t xo = xt_offset(rvalid ? grow : 0, c, 0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.res_tiled != nullptr) { if (rvalid) r = *reinterpret_cast<const float4*>(p.res_tiled + xo + j * 128); }
-              else if (trow != nullptr) r = *reinterpret_cast<const float4*>(trow + c * 32 + j * 4);
+              const float4 r = res4[j];
               float4 q = make_float4(v[j * 4 + 0] + r.x, v[j * 4 + 1] + r.y, v[j * 4 + 2] + r.z, v[j * 4 + 3] + r.w);
               v[j * 4 + 0] = q.x; v[j * 4 + 1] = q.y; v[j * 4 + 2] = q.z; v[j * 4 + 3] = q.w;
               sum += (q.x + q.y) + (q.z + q.w);

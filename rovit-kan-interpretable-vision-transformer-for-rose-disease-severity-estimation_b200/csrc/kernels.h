@@ -30,13 +30,12 @@ int rvk_gemm_nt_launch(const GemmNtArgs& a, cudaStream_t stream);
 int rvk_gemm_tn_launch(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int M, int P,
                        int Q, float scale, cudaStream_t stream);
 
-// fused MLP block of the inference path: x_out = x_in + fc2(gelu(fc1(ln_in))) (+ LayerNorm -> ln_out); the fp32
-// token stream x uses the tiled layout of common.cuh (xt_offset).  cta_group: 2 = CTA pairs (default), 1 = single CTAs.
+// fused MLP block of the inference path: x_out = x_in + fc2(gelu(fc1(LayerNorm2(x_in)))) (+ LayerNorm -> ln_out); the
+// fp32 token stream x uses the tiled layout of common.cuh (xt_offset).  cta_group: 2 = CTA pairs (default), 1 = single CTAs.
 struct MlpFusedArgs {
-  const void* ln_in = nullptr;    // bf16 [M,192]
   const void* w1 = nullptr;       // bf16 [768,192]
-  const void* w2 = nullptr;       // bf16 [192,768]
-  void* ln_out = nullptr;         // bf16 [M,192] (has_ln)
+  const void* w2_f16 = nullptr;   // fp16 [192,768] (the hidden activation is kept in fp16)
+  void* ln_out = nullptr;         // bf16 [M,192] (p.has_ln)
   int cta_group = 2;
   MlpFusedParams p{};
 };
@@ -52,6 +51,7 @@ int rvk_im2col_launch(const float* images, void* patches_bf16, int batch, cudaSt
 int rvk_token_table_launch(const float* cls_token, const float* pos_embed, const float* patch_bias, float* table,
                            cudaStream_t stream);
 int rvk_cast_bf16_launch(const float* src, void* dst, int64_t n, cudaStream_t stream);
+int rvk_cast_f16_launch(const float* src, void* dst, int64_t n, cudaStream_t stream);
 int rvk_cast_transpose_bf16_launch(const float* src, void* dst, int rows, int cols, cudaStream_t stream);
 int rvk_layernorm_fwd_launch(const float* x, int64_t x_row_stride, const float* gamma, const float* beta, float eps,
                              void* y, int y_is_bf16, int64_t y_row_stride, float* mean, float* rstd, int rows,
