@@ -51,21 +51,25 @@ struct SgemmParams {
   int k_per_split;
 };
 
+// RM rows per thread: 64-row tiles (RM = 4) for large M, 16-row tiles (RM = 1) so that a 1024-sample inference batch
+// still spreads over >= 128 CTAs instead of 32
+template <int RM>
 __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmParams p) {
-  __shared__ __align__(16) float sA[16][64];
+  constexpr int TM = 16 * RM;
+  __shared__ __align__(16) float sA[16][TM];
   __shared__ __align__(16) float sB[16][64];
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
-  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  const int m0 = blockIdx.x * TM, n0 = blockIdx.y * 64;
   const int k_begin = blockIdx.z * p.k_per_split, k_end = min(p.K, k_begin + p.k_per_split);
-  float acc[4][4];
+  float acc[RM][4];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < RM; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
   for (int k0 = k_begin; k0 < k_end; k0 += 16) {
-    for (int idx = tid; idx < 16 * 64; idx += 256) {
+    for (int idx = tid; idx < 16 * TM; idx += 256) {
       int kl, ml;
-      if (p.transA) { kl = idx >> 6; ml = idx & 63; } else { ml = idx >> 4; kl = idx & 15; }
+      if (p.transA) { kl = idx / TM; ml = idx % TM; } else { ml = idx >> 4; kl = idx & 15; }
       const int m = m0 + ml, k = k0 + kl;
       float v = 0.0f;
       if (m < p.M && k < k_end) v = p.transA ? p.A[static_cast<long long>(k) * p.lda + m] : p.A[static_cast<long long>(m) * p.lda + k];
@@ -82,11 +86,13 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmParams p) {
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
-      const float4 av = *reinterpret_cast<const float4*>(&sA[kk][ty * 4]);
-      const float4 bv = *reinterpret_cast<const float4*>(&sB[kk][tx * 4]);
-      const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+      float a4[RM];
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < RM; ++a) a4[a] = sA[kk][ty * RM + a];
+      const float4 bv = *reinterpret_cast<const float4*>(&sB[kk][tx * 4]);
+      const float b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int a = 0; a < RM; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(a4[a], b4[b], acc[a][b]);
     }
@@ -94,8 +100,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const SgemmParams p) {
   }
   const bool split = gridDim.z > 1;
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int m = m0 + ty * 4 + a;
+  for (int a = 0; a < RM; ++a) {
+    const int m = m0 + ty * RM + a;
     if (m >= p.M) continue;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
@@ -268,8 +274,13 @@ int rvk_sgemm_launch(const SgemmArgs& a, cudaStream_t stream) {
   }
   p.k_per_split = ((a.K + splits - 1) / splits + 15) / 16 * 16;
   splits = (a.K + p.k_per_split - 1) / p.k_per_split;
-  dim3 grid((a.M + 63) / 64, (a.N + 63) / 64, splits);
-  sgemm_kernel<<<grid, 256, 0, stream>>>(p);
+  if (a.M <= 4096) {
+    dim3 grid((a.M + 15) / 16, (a.N + 63) / 64, splits);
+    sgemm_kernel<1><<<grid, 256, 0, stream>>>(p);
+  } else {
+    dim3 grid((a.M + 63) / 64, (a.N + 63) / 64, splits);
+    sgemm_kernel<4><<<grid, 256, 0, stream>>>(p);
+  }
   return rvk_launch_check();
 }
 

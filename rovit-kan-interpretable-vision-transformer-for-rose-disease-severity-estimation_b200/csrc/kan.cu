@@ -124,40 +124,48 @@ __global__ void kan_unpack_grad_kernel(const float* __restrict__ dWp, int n_in, 
 }
 
 // ------------------------------------------------------------------ forward
-// grid (sample tiles of 64, output tiles of 64); 256 threads; thread (ty, tx) owns samples ty*4..+3,
+// grid (sample tiles of 16*SPT, output tiles of 64); 256 threads; thread (ty, tx) owns samples ty*SPT..+SPT-1,
 // outputs tx*4..+3.  Per chunk of 8 inputs: expand activations into sA, copy the packed weight rows
-// into sW, then 64 rank-1 updates of the 4x4 register tile.
+// into sW, then 64 rank-1 updates of the SPT x 4 register tile.  SPT = 4 (64-sample tiles) for large batches,
+// SPT = 1 (16-sample tiles) so that an inference batch of ~1000 samples still fills the machine.
+template <int SPT>
 __global__ void __launch_bounds__(256)
 kan_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wp, const float* __restrict__ bias, Knots kn,
                float* __restrict__ y, int act, int batch, int n_in, int n_out, int in_pad, int out_pad) {
-  __shared__ __align__(16) float sA[kKC][kTS];   // [packed row][sample]   16 KB
+  constexpr int TS = 16 * SPT;
+  __shared__ __align__(16) float sA[kKC][TS];    // [packed row][sample]
   __shared__ __align__(16) float sW[kKC][kTO];   // [packed row][output]   16 KB
   const int tid = threadIdx.x;
   const int ty = tid >> 4, tx = tid & 15;
-  const int s0 = blockIdx.x * kTS, o0 = blockIdx.y * kTO;
-  float acc[4][4];
+  const int s0 = blockIdx.x * TS, o0 = blockIdx.y * kTO;
+  float acc[SPT][4];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < SPT; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) acc[a][b] = 0.0f;
 
   for (int i0 = 0; i0 < in_pad; i0 += kIC) {
-    // expand: thread handles (sample = tid/4, inputs (tid%4)*2, +1): 8 consecutive floats of x per 4 threads
+    // expand: TS samples x 8 inputs per chunk.  SPT = 4: thread handles (sample tid/4, inputs (tid%4)*2, +1);
+    // SPT = 1: threads 0..127 handle (sample tid/8, input tid%8)
     {
-      const int sl = tid >> 2, q = tid & 3;
+      constexpr int PER = (SPT == 4) ? 2 : 1;
+      const int sl = (SPT == 4) ? (tid >> 2) : (tid >> 3);
       const int sg = s0 + sl;
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int il = q * 2 + e, ig = i0 + il;
-        float a[kKW], da[kKW], dt;
-        if (sg < batch && ig < n_in) {
-          kan_expand<false>(x[static_cast<size_t>(sg) * n_in + ig], kn, a, da, dt);
-        } else {
+      for (int e = 0; e < PER; ++e) {
+        const int il = (SPT == 4) ? ((tid & 3) * 2 + e) : (tid & 7);
+        const int ig = i0 + il;
+        if (sl < TS) {
+          float a[kKW], da[kKW], dt;
+          if (sg < batch && ig < n_in) {
+            kan_expand<false>(x[static_cast<size_t>(sg) * n_in + ig], kn, a, da, dt);
+          } else {
 #pragma unroll
-          for (int k = 0; k < kKW; ++k) a[k] = 0.0f;
+            for (int k = 0; k < kKW; ++k) a[k] = 0.0f;
+          }
+#pragma unroll
+          for (int k = 0; k < kKW; ++k) sA[il * kKW + k][sl] = a[k];
         }
-#pragma unroll
-        for (int k = 0; k < kKW; ++k) sA[il * kKW + k][sl] = a[k];
       }
     }
     // weights: rows i0*8 .. +64 of Wp, columns o0 .. o0+64 (pads are zero-filled by the packer)
@@ -169,19 +177,21 @@ kan_fwd_kernel(const float* __restrict__ x, const float* __restrict__ Wp, const 
     __syncthreads();
 #pragma unroll 8
     for (int kk = 0; kk < kKC; ++kk) {
-      const float4 av = *reinterpret_cast<const float4*>(&sA[kk][ty * 4]);
-      const float4 wv = *reinterpret_cast<const float4*>(&sW[kk][tx * 4]);
-      const float a4[4] = {av.x, av.y, av.z, av.w}, w4[4] = {wv.x, wv.y, wv.z, wv.w};
+      float a4[SPT];
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+      for (int a = 0; a < SPT; ++a) a4[a] = sA[kk][ty * SPT + a];
+      const float4 wv = *reinterpret_cast<const float4*>(&sW[kk][tx * 4]);
+      const float w4[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int a = 0; a < SPT; ++a)
 #pragma unroll
         for (int b = 0; b < 4; ++b) acc[a][b] = fmaf(a4[a], w4[b], acc[a][b]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int sg = s0 + ty * 4 + a;
+  for (int a = 0; a < SPT; ++a) {
+    const int sg = s0 + ty * SPT + a;
     if (sg >= batch) continue;
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
@@ -371,8 +381,13 @@ int rvk_kan_layer_fwd_launch(const KanLayerDesc& L, const float* x, float* y, in
   const int pack_blocks = static_cast<int>((wp + 255) / 256 < 1184 ? (wp + 255) / 256 : 1184);
   kan_pack_kernel<<<pack_blocks, 256, 0, stream>>>(L.spline, L.lin_w, L.in_features, L.out_features, in_pad, out_pad, Wp, WpT);
   RVK_TRY(rvk_launch_check());
-  dim3 grid((batch + kTS - 1) / kTS, out_pad / kTO);
-  kan_fwd_kernel<<<grid, 256, 0, stream>>>(x, Wp, L.lin_b, kn, y, act, batch, L.in_features, L.out_features, in_pad, out_pad);
+  if (batch <= 4096) {
+    dim3 grid((batch + 15) / 16, out_pad / kTO);
+    kan_fwd_kernel<1><<<grid, 256, 0, stream>>>(x, Wp, L.lin_b, kn, y, act, batch, L.in_features, L.out_features, in_pad, out_pad);
+  } else {
+    dim3 grid((batch + kTS - 1) / kTS, out_pad / kTO);
+    kan_fwd_kernel<4><<<grid, 256, 0, stream>>>(x, Wp, L.lin_b, kn, y, act, batch, L.in_features, L.out_features, in_pad, out_pad);
+  }
   return rvk_launch_check();
 }
 
