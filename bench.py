@@ -111,7 +111,7 @@ def cpu_reference(steps, warmup, batch=32, quiet=False):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    steps, warmup = max(1, min(args.steps, 3)), max(1, min(args.warmup, 1))
+    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 2))
     r = cpu_reference(steps, warmup)
     line = {'impl': 'reference', 'metric': 'images/sec (224^2) RoViT-KAN eval forward, reference CPU path', 'value': r['value'],
             'unit': 'images/sec', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': r['ms_per_step'],
@@ -287,11 +287,83 @@ def run_ours(args, rank, local_rank, world):
                      'whole_step_frac': value / world * flop_img / 1e12 / pk['tflops_sustained']},
     }
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference(steps=2, warmup=1)
+        r = cpu_reference(steps=args.cpu_steps, warmup=1)
         line['cpu_baseline'] = {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+
+# ------------------------------------------------------------------------------------------ KAN microbenchmark
+def run_kan(args, rank, local_rank, world):
+    """BASELINE.json configs[2]: KANSeverityModule([192,64,1]) (and the production [192,64,16,1]), grid=5 k=3, batch
+    65536, forward + backward (dx, dW, dWl, db of every layer).  Algorithmic bytes / FLOPs per fwd+bwd from
+    SURVEY.md section 8(d): 152 MB, 38.7 GFLOP for the [192,64,1] stack."""
+    import torch
+    from rovitkan_b200 import _lib
+    from rovitkan_b200.models.kan import KANSeverityModule
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    lib = _lib.load()
+    batch = args.batch or 65536
+    K, W = args.steps, max(3, args.warmup)
+    out = {}
+    for name, dims in (('192-64-1', [192, 64, 1]), ('192-64-16-1', [192, 64, 16, 1])):
+        torch.manual_seed(0)
+        m = KANSeverityModule(dims).to(dev)
+        x = torch.randn(batch, 192, generator=torch.Generator().manual_seed(0)).to(dev).requires_grad_(True)
+        gy = torch.randn(batch, 1, generator=torch.Generator().manual_seed(1)).to(dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+        def fwd():
+            with torch.no_grad():
+                return m(x)
+
+        def fwdbwd():
+            y = m(x)
+            y.backward(gy)
+            m.zero_grad(set_to_none=True)
+            x.grad = None
+
+        res = {}
+        for tag, fn in (('fwd', fwd), ('fwd_bwd', fwdbwd)):
+            for _ in range(W):
+                fn()
+            torch.cuda.synchronize()
+            tot = 0.0
+            l0 = lib.rvk_launch_count()
+            for _ in range(K):
+                flush.zero_()                      # L2 flush between timed iterations (x is 50 MB < 126 MB L2)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                tot += e0.elapsed_time(e1)
+            res[tag] = {'ms': tot / K, 'launches': (lib.rvk_launch_count() - l0) // K}
+        out[name] = res
+    if rank != 0:
+        return
+    pk = peaks()
+    r = out['192-64-1']
+    ms = r['fwd_bwd']['ms']
+    alg_bytes, alg_flops = 152.0e6 * batch / 65536, 38.7e9 * batch / 65536
+    gbs = alg_bytes / (ms * 1e-3) / 1e9
+    line = {
+        'metric': 'samples/sec KANSeverityModule([192,64,1]) forward+backward', 'value': batch / (ms * 1e-3), 'unit': 'samples/sec',
+        'n_gpus': 1, 'steps': K, 'warmup': W, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'KANLayer microbench: 192->64->1 spline head, grid=5 k=3, batch %d fwd+bwd' % batch,
+                   'l2': 'L2 flushed (256 MB memset) between timed iterations'},
+        'gpu_launches': int(r['fwd_bwd']['launches']) * K,
+        'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': gbs / pk['hbm_gbs'],
+                     'traffic': None, 'kernel': 'kan_fwd_kernel + kan_bwd_w_kernel + kan_bwd_x_kernel (fp32 FMA)',
+                     'note': 'algorithmic 152 MB / 38.7 GFLOP per fwd+bwd: 255 FLOP/B, i.e. bound by the fp32 FMA pipe '
+                             '(%.1f TFLOP/s achieved), not by HBM' % (alg_flops / (ms * 1e-3) / 1e12)},
+        'detail': out,
+    }
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -300,15 +372,19 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--mode', default='infer', choices=['infer', 'train'])
+    ap.add_argument('--mode', default='infer', choices=['infer', 'train', 'kan'])
     ap.add_argument('--batch', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-steps', type=int, default=40, help='batch-32 reference forwards timed for cpu_baseline (~10-20 s)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if args.impl == 'reference':
         run_reference(args, rank, world)
+    elif args.mode == 'kan':
+        if rank == 0:
+            run_kan(args, rank, local_rank, world)
     else:
         run_ours(args, rank, local_rank, world)
 

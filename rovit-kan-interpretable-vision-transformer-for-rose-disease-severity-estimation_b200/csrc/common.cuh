@@ -411,7 +411,9 @@ __device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc,
 // and the low word is (smem address >> 4) | LBO field, so stepping K by 16 bf16 (32 bytes) is `lo + 2`.  Splitting the
 // descriptor keeps the UMMA issue loop at a few uniform-datapath instructions per MMA.
 constexpr uint32_t kUmmaDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);
-__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes = 16) {
+  return ((smem_addr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
 template <int G>
 __device__ __forceinline__ void umma_f16_split(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
   if (G == 2) {

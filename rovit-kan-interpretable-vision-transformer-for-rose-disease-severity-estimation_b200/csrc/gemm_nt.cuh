@@ -97,7 +97,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   static_assert(MODE != EPI_RES_LN || BN == 192, "fused LayerNorm needs the whole 192-wide row in one tile");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // offset form keeps the shared address space (LDS/STS)
   uint8_t* sOperands = smem;
   uint8_t* sSlots = smem + L::kOperandBytes;
   float* sBias = reinterpret_cast<float*>(sSlots + L::kSlotBytes);
@@ -176,8 +176,11 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // ================================================================= UMMA issuer
-    if (lane == 0) {
+    // whole warp, warp-uniform values (descriptor words stay on the uniform datapath); one elected lane issues
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN, 0, 0);
+      const bool issuer = elect_one();
+      const uint32_t op_lo = umma_desc_lo(smem_u32(sOperands));
       int s = 0;
       uint32_t ph = 0;
       int acc = 0;
@@ -189,18 +192,18 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(sOperands + s * L::kStageBytes);
-          const uint32_t b_addr = a_addr + L::kABytes;
+          const uint32_t a_lo = op_lo + s * (L::kStageBytes >> 4);
+          const uint32_t b_lo = a_lo + (L::kABytes >> 4);
+          if (issuer) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t ad = umma_smem_desc(a_addr + k * 32, 16, 1024);
-            const uint64_t bd = umma_smem_desc(b_addr + k * 32, 16, 1024);
-            umma_bf16(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < 4; ++k) umma_f16_split<1>(d_tmem, a_lo + 2 * k, b_lo + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit(&empty[s]);
           }
-          umma_commit(&empty[s]);
+          __syncwarp();
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);
+        if (issuer) umma_commit(&tmem_full[acc]);
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_ph ^= 1; }
       }
     }
