@@ -17,7 +17,8 @@ constexpr int kHd = 64;
 constexpr int kHeads = 3;
 constexpr int kQkvLd = 576;
 constexpr int kCtxLd = 192;
-constexpr int kAttnThreads = 224;   // 7 warps, two 16-row tiles each (13 used)
+constexpr int kAttnWarps = 13;      // one 16-row tile per warp and phase (7 warps x 2 tiles left the SM at 7 resident warps)
+constexpr int kAttnThreads = kAttnWarps * 32;
 constexpr float kScale = 0.125f;
 constexpr float kLog2e = 1.4426950408889634f;
 
@@ -164,7 +165,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
   uint8_t* sV = sK + kPad * 128;
   uint8_t* sDO = sV + kPad * 128;
   uint8_t* sStage = sDO + kPad * 128;
-  float* sLse = reinterpret_cast<float*>(sStage + 7 * 2048);
+  float* sLse = reinterpret_cast<float*>(sStage + kAttnWarps * 2048);
   float* sDelta = sLse + kPad;
   const int b = blockIdx.x / kHeads, h = blockIdx.x % kHeads;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -213,7 +214,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
   const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aDO = smem_u32(sDO);
 
   // ---- phase K: this warp owns 16 keys; it streams over 16-query chunks of the transposed score tile
-  for (int kt = warp; kt < 13; kt += 7) {
+  for (int kt = warp; kt < 13; kt += kAttnWarps) {
     uint32_t kf[4][4], vf[4][4];
     load_a_frags(aK, kt, lane, kf);
     load_a_frags(aV, kt, lane, vf);
@@ -255,7 +256,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
   }
 
   // ---- phase Q: this warp owns 16 queries; it streams over 16-key chunks
-  for (int qt = warp; qt < 13; qt += 7) {
+  for (int qt = warp; qt < 13; qt += kAttnWarps) {
     uint32_t qf[4][4], dof[4][4];
     load_a_frags(aQ, qt, lane, qf);
     load_a_frags(aDO, qt, lane, dof);
@@ -294,7 +295,7 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
 }  // namespace
 
 // ------------------------------------------------------------------------------------------- launchers
-constexpr int kAttnBwdSmem = 4 * kPad * 128 + 7 * 2048 + 2 * kPad * 4;
+constexpr int kAttnBwdSmem = 4 * kPad * 128 + kAttnWarps * 2048 + 2 * kPad * 4;
 
 int rvk_attention_bwd_launch(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
                              int batch, cudaStream_t stream) {

@@ -172,27 +172,49 @@ __global__ void layernorm_bwd_kernel(const void* __restrict__ g, long long gs, c
 }
 
 // ------------------------------------------------------------------ column sums (bias gradients)
-// out[c] += scale * sum_r src[r, c]; each block reduces a row chunk, thread = pair of columns
+// out[c] += scale * sum_r src[r, c].  A pure streaming reduction: 16-byte loads, `tpr` threads across a row and
+// blockDim.x / tpr rows in flight per block iteration (4 independent loads per thread), partial sums combined through
+// shared memory, one atomicAdd per column and block.  cols * elem_size must be a multiple of 16 (768 / 576 bf16, 192 fp32).
 template <bool SRC_BF16>
-__global__ void colsum_kernel(const void* __restrict__ src, long long ld, int rows, int cols, float* __restrict__ out,
-                              float scale, int rows_per_block) {
+__global__ void __launch_bounds__(256)
+colsum_kernel(const void* __restrict__ src, long long ld, int rows, int cols, float* __restrict__ out, float scale,
+              int rows_per_block) {
+  constexpr int VE = SRC_BF16 ? 8 : 4;                 // elements per 16-byte load
+  __shared__ float sPart[256 * VE];
+  const int tpr = cols / VE;                           // threads across a row
+  const int ry = blockDim.x / tpr;                     // rows in flight
+  const int tx = threadIdx.x % tpr, ty = threadIdx.x / tpr;
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(rows, r0 + rows_per_block);
-  for (int cp = threadIdx.x; cp * 2 < cols; cp += blockDim.x) {
-    const int c = cp * 2;
-    float a0 = 0.0f, a1 = 0.0f;
-    for (int r = r0; r < r1; ++r) {
+  float acc[VE];
+#pragma unroll
+  for (int e = 0; e < VE; ++e) acc[e] = 0.0f;
+  if (ty < ry) {
+    const size_t esz = SRC_BF16 ? 2 : 4;
+    const uint8_t* base = static_cast<const uint8_t*>(src) + static_cast<size_t>(tx) * 16;
+    auto add_row = [&](int r) {
+      const uint4 q = *reinterpret_cast<const uint4*>(base + static_cast<size_t>(r) * ld * esz);
       if (SRC_BF16) {
-        const float2 v = unpack_bf16x2(
-            *reinterpret_cast<const uint32_t*>(static_cast<const __nv_bfloat16*>(src) + static_cast<size_t>(r) * ld + c));
-        a0 += v.x; a1 += v.y;
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float2 v = unpack_bf16x2(w[e]); acc[(2 * e) % VE] += v.x; acc[(2 * e + 1) % VE] += v.y; }
       } else {
-        const float2 v = *reinterpret_cast<const float2*>(static_cast<const float*>(src) + static_cast<size_t>(r) * ld + c);
-        a0 += v.x; a1 += v.y;
+        acc[0] += __uint_as_float(q.x); acc[1] += __uint_as_float(q.y);
+        acc[2 % VE] += __uint_as_float(q.z); acc[3 % VE] += __uint_as_float(q.w);
       }
-    }
-    atomicAdd(&out[c], a0 * scale);
-    if (c + 1 < cols) atomicAdd(&out[c + 1], a1 * scale);
+    };
+    int r = r0 + ty;
+    for (; r + 3 * ry < r1; r += 4 * ry) { add_row(r); add_row(r + ry); add_row(r + 2 * ry); add_row(r + 3 * ry); }
+    for (; r < r1; r += ry) add_row(r);
+  }
+#pragma unroll
+  for (int e = 0; e < VE; ++e) sPart[threadIdx.x * VE + e] = acc[e];
+  __syncthreads();
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    const int cx = c / VE, ce = c % VE;
+    float t = 0.0f;
+    for (int y = 0; y < ry; ++y) t += sPart[(y * tpr + cx) * VE + ce];
+    atomicAdd(&out[c], t * scale);
   }
 }
 
@@ -290,10 +312,12 @@ int rvk_layernorm_bwd_launch(const void* g, int g_is_bf16, int64_t g_row_stride,
 int rvk_colsum_launch(const void* src, int src_is_bf16, int64_t ld, int rows, int cols, float* out, float scale,
                       cudaStream_t stream) {
   if (rows <= 0 || cols <= 0) return RVK_OK;
-  if (cols % 2 != 0 || ld % 2 != 0) return RVK_ERR_UNSUPPORTED_SHAPE;
-  int blocks = kNumSMsB200 * 2;
+  const int ve = src_is_bf16 ? 8 : 4;
+  if (cols % ve != 0 || ld % ve != 0 || cols / ve > 256 || (reinterpret_cast<uintptr_t>(src) & 15) != 0)
+    return RVK_ERR_UNSUPPORTED_SHAPE;
+  int blocks = kNumSMsB200 * 4;
   int rpb = (rows + blocks - 1) / blocks;
-  if (rpb < 8) rpb = 8;
+  if (rpb < 16) rpb = 16;
   blocks = (rows + rpb - 1) / rpb;
   if (src_is_bf16) colsum_kernel<true><<<blocks, 256, 0, stream>>>(src, ld, rows, cols, out, scale, rpb);
   else colsum_kernel<false><<<blocks, 256, 0, stream>>>(src, ld, rows, cols, out, scale, rpb);
