@@ -14,6 +14,10 @@
 // Backward: gpre = gy * act'(y);   dWp = A^T gpre  (batch-split, register tile 8 x 4, atomics);
 //           G = gpre * Wp^T,  dx[b,i] = G[b,i,7] + (1 - t^2) * sum_k G[b,i,k] * N'_k(t).
 #include "kernels.h"
+#include "tma_host.h"
+
+#include <cmath>
+#include <cstdlib>
 
 namespace {
 
@@ -351,13 +355,24 @@ kan_bwd_x_kernel(const float* __restrict__ x, const float* __restrict__ yv, cons
 
 int pad_to(int v, int m) { return (v + m - 1) / m * m; }
 
+constexpr int kKanTcMinBatch = 8192;
+// RVK_KAN_SIMT=1 keeps the fp32 CUDA-core kernels for every batch size (A/B measurements)
+bool kan_tc_disabled() {
+  static const bool off = [] { const char* e = getenv("RVK_KAN_SIMT"); return e != nullptr && e[0] == '1'; }();
+  return off;
+}
+
+#include "kan_tc.cuh"
+
 }  // namespace
 
 // workspace floats needed by forward (packed weights) and backward (transposed pack + packed gradient)
 int64_t rvk_kan_workspace_floats(int n_in, int n_out, int with_backward) {
   const int64_t in_pad = pad_to(n_in, 16), out_pad = pad_to(n_out, 64);
   const int64_t wp = in_pad * 8 * out_pad;
-  return with_backward ? 3 * wp : wp;
+  // + one wp-sized block for the bf16 hi / lo split of the packed weights (tensor-core path, large batches)
+  // (+ 64 floats: interval thresholds of the tensor-core path)
+  return (with_backward ? 3 * wp : wp) + wp + 64;
 }
 
 int rvk_kan_basis_launch(const float* t, const float* knots_host, float* out, int64_t n, cudaStream_t stream) {
@@ -381,6 +396,36 @@ int rvk_kan_layer_fwd_launch(const KanLayerDesc& L, const float* x, float* y, in
   const int pack_blocks = static_cast<int>((wp + 255) / 256 < 1184 ? (wp + 255) / 256 : 1184);
   kan_pack_kernel<<<pack_blocks, 256, 0, stream>>>(L.spline, L.lin_w, L.in_features, L.out_features, in_pad, out_pad, Wp, WpT);
   RVK_TRY(rvk_launch_check());
+  if (batch >= kKanTcMinBatch && L.in_features % 8 == 0 && L.out_features <= 64 && L.in_features >= 64 && !kan_tc_disabled()) {
+    // tensor-core path: operands split hi + lo in bf16, activations generated on the fly (kan_tc.cuh)
+    const int kp = in_pad * 8;
+    auto* w_hi = reinterpret_cast<__nv_bfloat16*>(workspace + (with_backward ? 3 : 1) * wp);
+    auto* w_lo = w_hi + static_cast<size_t>(64) * kp;
+    kan_split_weights_kernel<<<pack_blocks, 256, 0, stream>>>(L.spline, L.lin_w, L.in_features, L.out_features, kp, w_hi, w_lo);
+    RVK_TRY(rvk_launch_check());
+    static bool configured = false;
+    if (!configured) {
+      RVK_CUDA_TRY(cudaFuncSetAttribute(kan_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+      configured = true;
+    }
+    CUtensorMap tmWhi, tmWlo;
+    RVK_TRY(rvk_make_tmap_2d(&tmWhi, w_hi, RVK_BF16, 64, kp, kp, 64, 64));
+    RVK_TRY(rvk_make_tmap_2d(&tmWlo, w_lo, RVK_BF16, 64, kp, kp, 64, 64));
+    const int tiles = (batch + 127) / 128;
+    const int grid = tiles < kNumSMsB200 ? tiles : kNumSMsB200;
+    KanTcTables tb;
+    float* xthr = reinterpret_cast<float*>(w_lo + static_cast<size_t>(64) * kp);     // 16 floats after the split weights
+    kan_tc_thresholds_kernel<<<1, 32, 0, stream>>>(kn, xthr);
+    RVK_TRY(rvk_launch_check());
+    tb.xthr = xthr;
+    for (int j = 0; j < 8; ++j) {
+      tb.knot[j] = L.knots_host[j];
+      tb.inv_h[j] = 1.0f / (L.knots_host[j + 1] - L.knots_host[j]);
+    }
+    kan_fwd_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(tmWhi, tmWlo, x, L.lin_b, tb, y, act, batch, L.in_features,
+                                                                 L.out_features, L.in_features / 8);
+    return rvk_launch_check();
+  }
   if (batch <= 4096) {
     dim3 grid((batch + 15) / 16, out_pad / kTO);
     kan_fwd_kernel<1><<<grid, 256, 0, stream>>>(x, Wp, L.lin_b, kn, y, act, batch, L.in_features, L.out_features, in_pad, out_pad);

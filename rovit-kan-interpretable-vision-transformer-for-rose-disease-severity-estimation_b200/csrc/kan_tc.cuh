@@ -1,0 +1,287 @@
+// Tensor-core formulation of the fused KAN layer forward for large batches (included by kan.cu inside its anonymous
+// namespace: uses Knots, kan_expand, kKW).
+//
+//   y[b, o] = act( bias[o] + sum_{i,k} A[b, i*8+k] * Wp[i*8+k, o] ),   A[b, i*8+k] = N_k(tanh x[b,i]) (k < 7), x[b,i] (k = 7)
+//
+// is a GEMM [B x 8*in] x [8*in x out] whose left operand does not exist in memory: sixteen producer warps evaluate
+// the truncated cubic B-spline (closed form, precise tanhf: the reference's basis is discontinuous at tanh x = 0.4)
+// for 128 samples x 8 inputs at a time and write the 64 packed activations per sample straight into a K-major,
+// 128-byte-swizzled UMMA operand tile in shared memory.  fp32 parity (1e-3 relative on the layer output) rules out
+// plain bf16 operands (2^-9) and TF32 (2^-11 per operand); both operands are therefore split hi + lo in bf16 and
+// the product is accumulated as  A_hi W_hi + A_hi W_lo + A_lo W_hi  (relative error ~2^-16 per term) in fp32 TMEM.
+//
+// Warp roles (576 threads): w0 TMA producer (weight chunks [64 out x 64 k] hi / lo, 4-stage ring), w1 UMMA issuer
+// (whole warp, uniform datapath), w2..w17 activation producers + epilogue (TMEM -> bias -> activation -> y).
+// Per 128-sample tile: in/8 chunks x (3 products x 4 UMMA of M=128 N=64 K=16); two TMEM accumulators so that the
+// epilogue of tile t overlaps the chunks of tile t+1.  The kernel is bound by the producers (~100 instructions per
+// (sample, input): tanhf, interval search, four cubics, hi/lo split), not by the tensor pipe or HBM.
+#pragma once
+
+constexpr int kTcThreads = 18 * 32;
+constexpr int kTcAStages = 3;
+constexpr int kTcWStages = 4;
+constexpr int kTcAStageBytes = 2 * 16384;            // A_hi | A_lo, each [128 x 64] bf16
+constexpr int kTcWStageBytes = 2 * 8192;             // W_hi | W_lo, each [64 x 64] bf16
+constexpr int kTcSmemBytes = 1024 + kTcAStages * kTcAStageBytes + kTcWStages * kTcWStageBytes + 96 * 4 + 256;
+
+// Interval search in x-space: tanh is monotone, so  tanh(x) >= knot_m  <=>  x >= atanh(knot_m).  Deciding the
+// knot interval (and with it the reference's discontinuity at tanh x = 0.4) from thresholds in x removes the
+// accuracy requirement from tanh itself: the VALUES of the cubics are continuous in t, so a branch-free
+// tanh = 1 - 2 / (2^(2 log2(e) |x|) + 1) on MUFU.EX2 / MUFU.RCP (absolute error ~3e-7) is enough for them.
+struct KanTcTables {
+  const float* xthr; // device [9]: xthr[m] = smallest float x with tanhf(x) >= knot_m (m = 1..7); xthr[0] = -inf, xthr[8] = +inf
+  float knot[8];     // knot_0 .. knot_7
+  float inv_h[8];    // 1 / (knot_{j+1} - knot_j), j = 0..6 (inv_h[7] unused)
+};
+
+// The thresholds are calibrated against the SAME tanhf the CUDA-core kernels (and the parity tests) use, so that
+// both paths take identical interval decisions even for inputs sitting exactly on a knot: scan +-32 ulps around
+// atanh(knot_m) for the smallest float whose tanhf reaches the knot.
+__global__ void kan_tc_thresholds_kernel(Knots kn, float* __restrict__ xthr) {
+  const int m = threadIdx.x;
+  if (m > 8) return;
+  if (m == 0) { xthr[0] = -INFINITY; return; }
+  if (m == 8) { xthr[8] = INFINITY; return; }
+  const float km = kn.k[m];
+  float xf = atanhf(km);
+  for (int d = 0; d < 32; ++d) xf = nextafterf(xf, -INFINITY);
+  for (int d = 0; d < 64 && tanhf(xf) < km; ++d) xf = nextafterf(xf, INFINITY);
+  xthr[m] = xf;
+}
+
+// WpT (fp32 [out_pad=64][kp]) -> bf16 hi / lo, row-major [64][kp] each
+__global__ void kan_split_weights_kernel(const float* __restrict__ spline, const float* __restrict__ lin_w, int n_in,
+                                         int n_out, int kp, __nv_bfloat16* __restrict__ w_hi,
+                                         __nv_bfloat16* __restrict__ w_lo) {
+  const long long total = 64LL * kp;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int o = static_cast<int>(idx / kp), kk = static_cast<int>(idx % kp);
+    const int i = kk >> 3, k = kk & 7;
+    float v = 0.0f;
+    if (i < n_in && o < n_out)
+      v = (k < 7) ? spline[(static_cast<size_t>(i) * n_out + o) * 7 + k] : lin_w[static_cast<size_t>(o) * n_in + i];
+    const __nv_bfloat16 hi = __float2bfloat16(v);
+    w_hi[idx] = hi;
+    w_lo[idx] = __float2bfloat16(v - __bfloat162float(hi));
+  }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+kan_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
+                  const float* __restrict__ x, const float* __restrict__ bias, const KanTcTables tb, float* __restrict__ y,
+                  int act, int batch, int n_in, int n_out, int num_chunks) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sW = sA + kTcAStages * kTcAStageBytes;
+  float* sBias = reinterpret_cast<float*>(sW + kTcWStages * kTcWStageBytes);
+  float* sXthr = sBias + 64;     // [12]
+  float* sKnot = sXthr + 12;     // [8]
+  float* sInvH = sKnot + 8;      // [8]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sInvH + 8 + 4);
+  uint64_t* a_full = bars;                       // [3]
+  uint64_t* a_empty = a_full + kTcAStages;       // [3]
+  uint64_t* w_full = a_empty + kTcAStages;       // [4]
+  uint64_t* w_empty = w_full + kTcWStages;       // [4]
+  uint64_t* d_full = w_empty + kTcWStages;       // [2]
+  uint64_t* d_empty = d_full + 2;                // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(d_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = (batch + 127) / 128;
+
+  if (threadIdx.x < 64) sBias[threadIdx.x] = (threadIdx.x < n_out) ? bias[threadIdx.x] : 0.0f;
+  if (threadIdx.x < 9) sXthr[threadIdx.x] = tb.xthr[threadIdx.x];     // written by kan_tc_thresholds_kernel on this stream
+  if (threadIdx.x < 8) { sKnot[threadIdx.x] = tb.knot[threadIdx.x]; sInvH[threadIdx.x] = tb.inv_h[threadIdx.x]; }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmWhi);
+    tma_prefetch_desc(&tmWlo);
+    for (int i = 0; i < kTcAStages; ++i) { mbar_init(&a_full[i], 16); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < kTcWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 16); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================================================================= weight producer
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        for (int c = 0; c < num_chunks; ++c) {
+          mbar_wait(&w_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&w_full[s], kTcWStageBytes);
+          tma_load_2d(sW + s * kTcWStageBytes, &tmWhi, &w_full[s], c * 64, 0);
+          tma_load_2d(sW + s * kTcWStageBytes + 8192, &tmWlo, &w_full[s], c * 64, 0);
+          if (++s == kTcWStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================= UMMA issuer (whole warp, one elected lane issues)
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+    const bool issuer = elect_one();
+    const uint32_t a_lo0 = umma_desc_lo(smem_u32(sA)), w_lo0 = umma_desc_lo(smem_u32(sW));
+    int sa = 0, sw = 0;
+    uint32_t pha = 0, phw = 0;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      mbar_wait(&d_empty[acc], acc_ph ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem_base + acc * 64;
+      for (int c = 0; c < num_chunks; ++c) {
+        mbar_wait(&a_full[sa], pha);
+        mbar_wait(&w_full[sw], phw);
+        tc_fence_after();
+        const uint32_t ahi = a_lo0 + sa * (kTcAStageBytes >> 4), alo = ahi + (16384 >> 4);
+        const uint32_t whi = w_lo0 + sw * (kTcWStageBytes >> 4), wlo = whi + (8192 >> 4);
+        if (issuer) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_split<1>(d, ahi + 2 * k, whi + 2 * k, idesc, (c | k) != 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_split<1>(d, ahi + 2 * k, wlo + 2 * k, idesc, 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_split<1>(d, alo + 2 * k, whi + 2 * k, idesc, 1u);
+          umma_commit(&a_empty[sa]);
+          umma_commit(&w_empty[sw]);
+          if (c == num_chunks - 1) umma_commit(&d_full[acc]);
+        }
+        __syncwarp();
+        if (++sa == kTcAStages) { sa = 0; pha ^= 1; }
+        if (++sw == kTcWStages) { sw = 0; phw ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+    }
+  } else {
+    // ================================================================= activation producers + epilogue
+    const int pw = warp - 2;                              // 0..15
+    const int pt = pw * 32 + lane;                        // 0..511
+    const int srow = pt >> 2;                             // sample row of the tile: 4 threads share a sample
+    const int ip = pt & 3;                                // inputs 2*ip, 2*ip+1 of the chunk (adjacent lanes: one 32-byte sector)
+    const int quad = warp & 3, cg = pw >> 2;              // epilogue: TMEM lane quadrant (= warp % 4) and 16-column group
+    const int erow = quad * 32 + lane;
+    const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
+    int sa = 0;
+    uint32_t pha = 0;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int sg = t * 128 + srow;
+      const float* xr = x + static_cast<size_t>(sg < batch ? sg : 0) * n_in + 2 * ip;
+      auto load_x = [&](int c) -> float2 {
+        float2 xv = make_float2(0.0f, 0.0f);
+        const int i0 = c * 8 + 2 * ip;
+        if (sg < batch && c < num_chunks) {
+          if (i0 + 1 < n_in) xv = *reinterpret_cast<const float2*>(xr + c * 8);
+          else if (i0 < n_in) xv.x = xr[c * 8];
+        }
+        return xv;
+      };
+      float2 xnext = load_x(0);
+#pragma unroll 1
+      for (int c = 0; c < num_chunks; ++c) {
+        const float2 xv = xnext;
+        xnext = load_x(c + 1);                       // next chunk's inputs are in flight while this one is expanded
+        mbar_wait(&a_empty[sa], pha ^ 1);
+        uint8_t* ahi = sA + sa * kTcAStageBytes;
+        uint8_t* alo = ahi + 16384;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float xe = e == 0 ? xv.x : xv.y;
+          // tanh (branch-free, MUFU): values only; the interval comes from x-space thresholds
+          const float ex = ex2_approx(fabsf(xe) * 2.8853900817779268f);
+          float rc;
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(ex + 1.0f));
+          const float tt = copysignf(fmaf(-2.0f, rc, 1.0f), xe);
+          int j = static_cast<int>((tt + 1.0f) * 5.0f);
+          j = min(max(j, 0), 7);
+          if (xe < sXthr[j]) --j;
+          else if (xe >= sXthr[j + 1]) ++j;           // j = #{m >= 1 : x >= xthr[m]}, capped at 8 (>= 7: dead zone)
+          const uint32_t off = sw128_offset(srow, 2 * ip + e);   // input (2*ip+e) of the chunk = one 16-byte K chunk
+          // slot 7 = raw x (hi / lo); slots 0..6 zero unless overwritten below
+          const __nv_bfloat16 xh = __float2bfloat16(xe);
+          const __nv_bfloat16 xl = __float2bfloat16(xe - __bfloat162float(xh));
+          *reinterpret_cast<uint4*>(ahi + off) = make_uint4(0u, 0u, 0u, static_cast<uint32_t>(__bfloat16_as_ushort(xh)) << 16);
+          *reinterpret_cast<uint4*>(alo + off) = make_uint4(0u, 0u, 0u, static_cast<uint32_t>(__bfloat16_as_ushort(xl)) << 16);
+          if (j < 7) {
+            const float u = (tt - sKnot[j]) * sInvH[j];
+            const float u2 = u * u, u3 = u2 * u, om = 1.0f - u;
+            float v[4];
+            v[0] = u3 * (1.0f / 6.0f);                                            // slot j
+            v[1] = (1.0f + 3.0f * u + 3.0f * u2 - 3.0f * u3) * (1.0f / 6.0f);     // slot j-1
+            v[2] = (4.0f - 6.0f * u2 + 3.0f * u3) * (1.0f / 6.0f);                // slot j-2
+            v[3] = om * om * om * (1.0f / 6.0f);                                  // slot j-3
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const int slot = j - m;
+              if (slot >= 0) {
+                const __nv_bfloat16 h = __float2bfloat16(v[m]);
+                const __nv_bfloat16 l = __float2bfloat16(v[m] - __bfloat162float(h));
+                *reinterpret_cast<__nv_bfloat16*>(ahi + off + slot * 2) = h;
+                *reinterpret_cast<__nv_bfloat16*>(alo + off + slot * 2) = l;
+              }
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[sa]);
+        if (++sa == kTcAStages) { sa = 0; pha ^= 1; }
+      }
+      // ---- epilogue of this tile
+      mbar_wait(&d_full[acc], acc_ph);
+      tc_fence_after();
+      float v[16];
+      {
+        uint32_t r[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(tmem_base + acc * 64 + cg * 16 + lane_sel)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&d_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      const int eg = t * 128 + erow;
+      if (eg < batch) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float u = v[i] + sBias[cg * 16 + i];
+          if (act == 1) u = fmaxf(u, 0.0f);
+          else if (act == 2) u = 3.0f / (1.0f + expf(-u));
+          v[i] = u;
+        }
+        float* yr = y + static_cast<size_t>(eg) * n_out + cg * 16;
+        if (n_out == 64) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(yr + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (cg * 16 + i < n_out) yr[i] = v[i];
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 128);
+}

@@ -44,7 +44,7 @@ def test_binding_covers_header(lib_path):
     lib = _lib.load()
     assert lib.rvk_abi_version() == 1
     assert b'ok' == lib.rvk_strerror(0)
-    assert lib.rvk_kan_layer_workspace_floats(192, 64, 0) == 192 * 8 * 64
+    assert lib.rvk_kan_layer_workspace_floats(192, 64, 0) == 2 * 192 * 8 * 64 + 64
     assert lib.rvk_encoder_workspace_bytes(0, 0, 0) == 0
     assert lib.rvk_encoder_weight_bytes(1) > lib.rvk_encoder_weight_bytes(0) > 5_400_000 * 2
 

