@@ -130,6 +130,7 @@ int rvk_mlp_fused(const float* x_in_tiled, float* x_out_tiled, const float* gamm
 /* Debugging aid: device buffer of 4*512 int64 into which the following rvk_mlp_fused launches log clock64 events
  * of CTA 0 (NULL switches it off, the default). */
 void rvk_debug_set_mlp_trace(void* device_buf);
+void rvk_debug_set_attn_trace(void* device_buf);   /* same for rvk_attention_forward */
 /* C[P,Q] (fp32) += scale * A[M,P]^T B[M,Q], bf16 operands (weight gradients). */
 int rvk_gemm_tn(const void* a_bf16, int64_t lda, const void* b_bf16, int64_t ldb, float* c, int64_t ldc, int m,
                 int p, int q, float scale, void* stream);

@@ -27,6 +27,7 @@ int fill_kan_desc(KanLayerDesc& L, const float* spline, const float* lin_w, cons
 }  // namespace
 
 static long long* g_mlp_trace = nullptr;
+void rvk_debug_set_attn_trace_impl(void* buf);
 
 #pragma GCC visibility push(default)
 extern "C" {
@@ -219,6 +220,7 @@ int rvk_mlp_fused(const float* x_in_tiled, float* x_out_tiled, const float* gamm
 }
 /* debugging aid (not part of the product path): device buffer of 4*512 int64 that the next rvk_mlp_fused launches log clock events into */
 void rvk_debug_set_mlp_trace(void* buf) { g_mlp_trace = static_cast<long long*>(buf); }
+void rvk_debug_set_attn_trace(void* buf) { rvk_debug_set_attn_trace_impl(buf); }
 int rvk_gemm_tn(const void* a_bf16, int64_t lda, const void* b_bf16, int64_t ldb, float* c, int64_t ldc, int m, int p,
                 int q, float scale, void* stream) {
   if (m < 0) return RVK_ERR_BAD_ARG;

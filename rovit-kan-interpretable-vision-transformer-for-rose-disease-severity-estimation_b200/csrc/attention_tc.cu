@@ -1,23 +1,22 @@
 // Attention forward for DeiT-Tiny (197 tokens, 3 heads of 64) on tcgen05 / TMEM, sm_100a.
 //
-// Persistent CTAs walk (image, head) items.  Per item, with queries split in two 128-row M tiles t:
-//   S_t = Q_t K^T      UMMA M=128 N=208 K=64   (Q, K: K-major bf16 tiles loaded by 3-D TMA; rows >= 197 are
-//                                               zero-filled by the tensor map, so padding never needs masking
-//                                               on the load side)
-//   P_t = softmax      SIXTEEN softmax warps: warp (quad, cg) owns the 32 query rows of TMEM lane quadrant `quad`
-//                      (of both tiles) and the key-column group cg (64 / 48 / 48 / 48 of the 208 padded keys).  A
-//                      thread's slice of its score row fits in registers, so TMEM is read exactly once; the exact
-//                      row maximum and the row sum are combined over the four column groups through shared memory
-//                      (one 128-thread named barrier per tile).  P_t is written as the K-major 128-byte-swizzled A
-//                      operand of the next UMMA.  (The first version used 8 warps with a whole 208-score row per
-//                      thread: two warps per SM sub-partition could not hide the TMEM / MUFU latencies.)
-//   O_t = P_t V        UMMA M=128 N=64 K=208, V consumed MN-major exactly as it lies in the qkv row (no
-//                      transpose); O_t aliases the first 64 TMEM columns of S_t
-//   ctx rows           O_t / rowsum -> bf16 (16 columns per warp) -> swizzled staging (P_t's first panel) ->
-//                      per-quadrant 3-D TMA store (the tensor map clips rows >= 197 of the image)
-// Warp roles (576 threads): w0-15 softmax / epilogue, w16 TMA producer, w17 UMMA issuer + TMEM owner.  Q/K are
-// released to the producer as soon as both S tiles are issued and V as soon as both PV products are, so the next
-// item's loads overlap this item's softmax.
+// Persistent CTAs walk (image, head) items; an item is two work UNITS (the 128-row query tiles t = 0, 1), and unit u
+// lives in TMEM region u & 1 (256 columns each):
+//   S = Q_t K^T        UMMA M=128 N=208 K=64 into region columns [0,208)   (Q, K: K-major bf16 tiles loaded by 3-D TMA;
+//                      rows >= 197 are zero-filled by the tensor map)
+//   P = softmax        SIXTEEN softmax warps: warp (quad, cg) owns the 32 query rows of TMEM lane quadrant `quad` and the
+//                      key-column group cg (52 of the 208 padded keys each).  The slice of a score row fits in
+//                      registers: TMEM is read once, the exact row maximum and the row sum are combined over the four
+//                      column groups through shared memory.  P is written back INTO TMEM as packed bf16 (columns
+//                      [104,208) of the region, over scores that every warp already holds in registers) with tcgen05.st ...
+//   O = P V            ... and consumed from there: tcgen05.mma with the A operand in TMEM (M=128 N=64 K=208, V MN-major
+//                      exactly as it lies in the qkv row) into region columns [0,64).  No shared memory for P.
+//   ctx rows           O / rowsum -> bf16, 16 columns (32 bytes) per thread straight to global memory
+// The loop is software-pipelined so that the tensor pipe never waits for the softmax warps and vice versa: the issuer
+// runs  PV(u), then S(u+2) as soon as O(u) has been read; the softmax warps read O(u-1) in the middle of unit u (after
+// their max exchange, when PV(u-1) has long finished), so S(u+1) is always ready when softmax(u) ends.  Q/K/V are
+// double-buffered (168 KB) and prefetched a whole item ahead.
+// Warp roles (576 threads): w0-15 softmax / epilogue, w16 TMA producer, w17 UMMA issuer (whole warp, uniform datapath).
 // Restates timm Attention.forward: softmax(q k^T * 64^-0.5) v (oracle/vit.py::_Attention).
 #include "kernels.h"
 #include "tma_host.h"
@@ -30,9 +29,8 @@ constexpr int kSmWarps = 16;
 constexpr int kThreads = (kSmWarps + 2) * 32;  // 576
 constexpr int kQBytes = 256 * 128;             // two M tiles
 constexpr int kKVBytes = kKeysPad * 128;
-constexpr int kPBytes = 4 * 128 * 128;         // four 64-key panels of [128 x 128 B]
-constexpr int kXchgBytes = 2 * 2 * 128 * 4 * 4;   // [max | sum][tile][row][column group] fp32
-constexpr int kSmemBytes = 1024 + kQBytes + 2 * kKVBytes + 2 * kPBytes + kXchgBytes + 256;
+constexpr int kXchgBytes = 2 * 2 * 128 * 4 * 4;   // [max | sum][region][row][column group] fp32
+constexpr int kSmemBytes = 1024 + 2 * kQBytes + 4 * kKVBytes + kXchgBytes + 256;
 constexpr float kScaleLog2e = 0.125f * 1.4426950408889634f;
 
 __device__ __forceinline__ void tmem_ld16f(uint32_t taddr, float* v) {
@@ -48,43 +46,76 @@ __device__ __forceinline__ void tmem_ld16f(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// 8 packed words (16 bf16 = one UMMA K step) of this thread's row -> 8 TMEM columns
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* w) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld4f(uint32_t taddr, float* v) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* w) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+               ::"r"(taddr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]),
+               "r"(w[8]), "r"(w[9]), "r"(w[10]), "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t w0, uint32_t w1) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(w0), "r"(w1) : "memory");
+}
+// D[tmem] (+)= A[tmem, K-major bf16 pairs] * B[smem desc]
+__device__ __forceinline__ void umma_ts_bf16(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHiSw128)
+      : "memory");
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
-                   const __grid_constant__ CUtensorMap tmCtx, float* __restrict__ lse, int num_items) {
+                   __nv_bfloat16* __restrict__ ctx, float* __restrict__ lse, int num_items, long long* trace_buf) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + kQBytes;
-  uint8_t* sV = sK + kKVBytes;
-  uint8_t* sP = sV + kKVBytes;                 // [2][kPBytes]
-  float* sMax = reinterpret_cast<float*>(sP + 2 * kPBytes);   // [2][128][4]
-  float* sSum = sMax + 2 * 128 * 4;                            // [2][128][4]
+  uint8_t* sQ = smem;                          // [2][kQBytes]
+  uint8_t* sK = sQ + 2 * kQBytes;              // [2][kKVBytes]
+  uint8_t* sV = sK + 2 * kKVBytes;             // [2][kKVBytes]
+  float* sMax = reinterpret_cast<float*>(sV + 2 * kKVBytes);          // [2][128][4]
+  float* sSum = sMax + 2 * 128 * 4;                                    // [2][128][4]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sSum + 2 * 128 * 4);
-  uint64_t* qk_full = bars;
-  uint64_t* v_full = bars + 1;
-  uint64_t* qk_empty = bars + 2;
-  uint64_t* v_empty = bars + 3;
-  uint64_t* s_full = bars + 4;       // [2]
-  uint64_t* p_full = bars + 6;       // [2]
-  uint64_t* o_full = bars + 8;       // [2]
-  uint64_t* tmem_free = bars + 10;   // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* qk_full = bars;          // [2] item buffers
+  uint64_t* v_full = bars + 2;       // [2]
+  uint64_t* qk_empty = bars + 4;     // [2]
+  uint64_t* v_empty = bars + 6;      // [2]
+  uint64_t* s_full = bars + 8;       // [2] TMEM regions
+  uint64_t* p_full = bars + 10;      // [2]
+  uint64_t* o_full = bars + 12;      // [2]
+  uint64_t* tmem_free = bars + 14;   // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  const int U = 2 * n_items;                    // work units of this CTA
   if (warp == kSmWarps && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
-    tma_prefetch_desc(&tmCtx);
-    mbar_init(qk_full, 1);
-    mbar_init(v_full, 1);
-    mbar_init(qk_empty, 1);
-    mbar_init(v_empty, 1);
-    for (int t = 0; t < 2; ++t) {
-      mbar_init(&s_full[t], 1);
-      mbar_init(&p_full[t], kSmWarps);
-      mbar_init(&o_full[t], 1);
-      mbar_init(&tmem_free[t], kSmWarps);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qk_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&qk_empty[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], kSmWarps);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&tmem_free[i], kSmWarps);
     }
     fence_mbar_init();
   }
@@ -96,189 +127,187 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // debugging: clock64 event log of CTA 0 (role 0 = UMMA issuer, 1 = softmax warp 0); entry = (tag << 48) | clock
+  int trace_n = 0;
+  auto trace = [&](int role, int tag) {
+    if (trace_buf != nullptr && blockIdx.x == 0 && lane == 0 && trace_n < 512)
+      trace_buf[role * 512 + trace_n++] = (static_cast<long long>(tag) << 48) | (clock64() & 0xFFFFFFFFFFFFLL);
+  };
 
   if (warp == kSmWarps) {
-    // ================================================================= TMA producer
+    // ================================================================= TMA producer (one item ahead)
     if (lane == 0) {
-      uint32_t it = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
+      for (int ii = 0; ii < n_items; ++ii) {
+        const int item = blockIdx.x + ii * gridDim.x;
         const int b = item / kHeads, h = item % kHeads;
-        mbar_wait(qk_empty, (it & 1) ^ 1);
-        mbar_arrive_expect_tx(qk_full, kQBytes + kKVBytes);
-        tma_load_3d(sQ, &tmQ, qk_full, h * kHd, 0, b);
-        tma_load_3d(sK, &tmKV, qk_full, 192 + h * kHd, 0, b);
-        mbar_wait(v_empty, (it & 1) ^ 1);
-        mbar_arrive_expect_tx(v_full, kKVBytes);
-        tma_load_3d(sV, &tmKV, v_full, 384 + h * kHd, 0, b);
+        const int qb = ii & 1;
+        const uint32_t n = static_cast<uint32_t>(ii >> 1);
+        mbar_wait(&qk_empty[qb], (n & 1) ^ 1);
+        mbar_arrive_expect_tx(&qk_full[qb], kQBytes + kKVBytes);
+        tma_load_3d(sQ + qb * kQBytes, &tmQ, &qk_full[qb], h * kHd, 0, b);
+        tma_load_3d(sK + qb * kKVBytes, &tmKV, &qk_full[qb], 192 + h * kHd, 0, b);
+        mbar_wait(&v_empty[qb], (n & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[qb], kKVBytes);
+        tma_load_3d(sV + qb * kKVBytes, &tmKV, &v_full[qb], 384 + h * kHd, 0, b);
       }
     }
   } else if (warp == kSmWarps + 1) {
-    // ================================================================= UMMA issuer
-    // The whole warp walks the loop with warp-uniform values (descriptors stay on the uniform datapath); only the
-    // tcgen05 instructions are issued by one elected lane.  Per-lane descriptor arithmetic cost ~100 cycles per MMA --
-    // three times the 32 cycles a 128x64x16 MMA takes -- and serialised the S -> softmax -> PV -> O chain of an item.
-    {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, kKeysPad, 0, 0);   // S = Q K^T
-      constexpr uint32_t idesc_o = umma_idesc_bf16(128, kHd, 0, 1);        // O = P V, V MN-major
-      const bool issuer = elect_one();
-      const uint32_t q_lo = umma_desc_lo(smem_u32(sQ)), k_lo = umma_desc_lo(smem_u32(sK));
-      const uint32_t p_lo = umma_desc_lo(smem_u32(sP)), v_lo = umma_desc_lo(smem_u32(sV), 8192);
-      uint32_t it = 0;
-      for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-        const uint32_t ph = it & 1;
-        mbar_wait(qk_full, ph);
+    // ================================================================= UMMA issuer (whole warp; one elected lane issues)
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, kKeysPad, 0, 0);   // S = Q K^T
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, kHd, 0, 1);        // O = P V, V MN-major
+    const bool issuer = elect_one();
+    const uint32_t q_lo = umma_desc_lo(smem_u32(sQ)), k_lo = umma_desc_lo(smem_u32(sK));
+    const uint32_t v_lo = umma_desc_lo(smem_u32(sV), 8192);
+    auto issue_s = [&](int u) {
+      const int ii = u >> 1, t = u & 1, qb = ii & 1;
+      if (t == 0) {
+        mbar_wait(&qk_full[qb], static_cast<uint32_t>(ii >> 1) & 1);
         tc_fence_after();
+      }
+      if (issuer) {
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(&tmem_free[t], ph ^ 1);
+        for (int k = 0; k < 4; ++k)
+          umma_f16_split<1>(tmem_base + t * 256, q_lo + qb * (kQBytes >> 4) + t * (16384 >> 4) + 2 * k,
+                            k_lo + qb * (kKVBytes >> 4) + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[t]);
+        if (t == 1) umma_commit(&qk_empty[qb]);      // Q and K of the item may be overwritten once both S tiles are done
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](int u) {
+      const int ii = u >> 1, t = u & 1, qb = ii & 1;
+      if (t == 0) mbar_wait(&v_full[qb], static_cast<uint32_t>(ii >> 1) & 1);
+      mbar_wait(&p_full[t], ii & 1);
+      tc_fence_after();
+      if (issuer) {
+#pragma unroll
+        for (int j = 0; j < 13; ++j)
+          umma_ts_bf16(tmem_base + t * 256, tmem_base + t * 256 + 104 + j * 8, v_lo + qb * (kKVBytes >> 4) + j * (2048 >> 4),
+                       idesc_o, j != 0 ? 1u : 0u);
+        umma_commit(&o_full[t]);
+        if (t == 1) umma_commit(&v_empty[qb]);
+      }
+      __syncwarp();
+    };
+    if (U > 0) {
+      issue_s(0);
+      issue_s(1);
+      for (int u = 0; u < U; ++u) {
+        issue_pv(u);
+        trace(0, 1);
+        if (u + 2 < U) {
+          mbar_wait(&tmem_free[u & 1], (u >> 1) & 1);     // O(u) has been read: the region may take S(u+2)
           tc_fence_after();
-          if (issuer) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_f16_split<1>(tmem_base + t * 256, q_lo + t * (16384 >> 4) + 2 * k, k_lo + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-            umma_commit(&s_full[t]);
-          }
-          __syncwarp();
+          trace(0, 2);
+          issue_s(u + 2);
+          trace(0, 3);
         }
-        if (issuer) umma_commit(qk_empty);            // Q and K may be overwritten once both S tiles are done
-        mbar_wait(v_full, ph);
-        tc_fence_after();
-#pragma unroll
-        for (int t = 0; t < 2; ++t) {
-          mbar_wait(&p_full[t], ph);
-          tc_fence_after();
-          if (issuer) {
-#pragma unroll
-            for (int j = 0; j < 13; ++j)
-              umma_f16_split<1>(tmem_base + t * 256, p_lo + t * (kPBytes >> 4) + (j >> 2) * (16384 >> 4) + (j & 3) * 2,
-                                v_lo + j * (2048 >> 4), idesc_o, j != 0 ? 1u : 0u);
-            umma_commit(&o_full[t]);
-          }
-          __syncwarp();
-        }
-        if (issuer) umma_commit(v_empty);
       }
     }
   } else {
     // ================================================================= softmax + epilogue warps
     const int quad = warp & 3, cg = warp >> 2;
     const int row = quad * 32 + lane;                 // TMEM lane = query row inside the tile
-    const int g0 = (cg == 0) ? 0 : 1 + 3 * cg;        // first 16-key group: groups 0-3 | 4-6 | 7-9 | 10-12
+    const int key0 = 52 * cg;                         // this warp's 52 of the 208 padded keys (13 x 4 per column group)
+    // (column group 3 ends with the 11 padded keys 197..207 = its elements 41..51)
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
 
-    uint32_t it = 0;
-    for (int item = blockIdx.x; item < num_items; item += gridDim.x, ++it) {
-      const uint32_t ph = it & 1;
-      const int b = item / kHeads, h = item % kHeads;
-#pragma unroll 1
-      for (int t = 0; t < 2; ++t) {
-        const bool valid = (t * 128 + quad * 32) < kTok;       // uniform over the four warps of a quadrant
-        uint8_t* myP = sP + t * kPBytes;
-        mbar_wait(&s_full[t], ph);
-        tc_fence_after();
-        if (valid) {
-          // the previous item's ctx store read this quadrant's rows of P_t panel 0: done before P is rewritten
-          if (cg == 0 && lane == 0) tma_store_wait_read<0>();
-          // 48 scores per thread stay in registers (column group 0 has 16 more: read twice, 7% extra TMEM traffic);
-          // only column group 3 contains padded keys (197..207 = its elements 37..47)
-          float v[48], w[16];
-          const uint32_t tS = tmem_base + t * 256 + g0 * 16 + lane_sel;
-          tmem_ld32(tS, *reinterpret_cast<float(*)[32]>(&v[0]));
-          tmem_ld16f(tS + 32, &v[32]);
-          float m = v[0];
-#pragma unroll
-          for (int i = 1; i < 32; ++i) m = fmaxf(m, v[i]);
-          if (cg == 3) {
-#pragma unroll
-            for (int i = 32; i < 37; ++i) m = fmaxf(m, v[i]);
-          } else {
-#pragma unroll
-            for (int i = 32; i < 48; ++i) m = fmaxf(m, v[i]);
-          }
-          if (cg == 0) {
-            tmem_ld16f(tS + 48, w);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) m = fmaxf(m, w[i]);
-          }
-          sMax[(t * 128 + row) * 4 + cg] = m;
-          named_bar_sync(1 + quad, 128);
-          const float4 m4 = *reinterpret_cast<const float4*>(&sMax[(t * 128 + row) * 4]);
-          const float shift = fmaxf(fmaxf(m4.x, m4.y), fmaxf(m4.z, m4.w)) * kScaleLog2e;
-          float sum = 0.0f;
-#pragma unroll
-          for (int i = 0; i < 32; ++i) { v[i] = ex2_approx(fmaf(v[i], kScaleLog2e, -shift)); sum += v[i]; }
-          if (cg == 3) {
-#pragma unroll
-            for (int i = 32; i < 48; ++i) {
-              if (i < 37) { v[i] = ex2_approx(fmaf(v[i], kScaleLog2e, -shift)); sum += v[i]; } else { v[i] = 0.0f; }
-            }
-          } else {
-#pragma unroll
-            for (int i = 32; i < 48; ++i) { v[i] = ex2_approx(fmaf(v[i], kScaleLog2e, -shift)); sum += v[i]; }
-          }
-#pragma unroll
-          for (int j = 0; j < 6; ++j) {
-            const int chunk = g0 * 2 + j;                      // 16-byte chunk (8 keys) of the 416-byte P row
-            uint4 q = make_uint4(pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]), pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]),
-                                 pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]), pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]));
-            *reinterpret_cast<uint4*>(myP + (chunk >> 3) * 16384 + sw128_offset(row, chunk & 7)) = q;
-          }
-          if (cg == 0) {
-            tmem_ld16f(tS + 48, w);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) { w[i] = ex2_approx(fmaf(w[i], kScaleLog2e, -shift)); sum += w[i]; }
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              uint4 q = make_uint4(pack_bf16x2(w[j * 8 + 0], w[j * 8 + 1]), pack_bf16x2(w[j * 8 + 2], w[j * 8 + 3]),
-                                   pack_bf16x2(w[j * 8 + 4], w[j * 8 + 5]), pack_bf16x2(w[j * 8 + 6], w[j * 8 + 7]));
-              *reinterpret_cast<uint4*>(myP + sw128_offset(row, 6 + j)) = q;     // keys 48..63: panel 0, chunks 6, 7
-            }
-          }
-          sSum[(t * 128 + row) * 4 + cg] = sum;
-        }
-        tc_fence_before();
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[t]);
+    float o[16];                                      // O slice of the previous unit, between its read and its store
+    float o_shift = 0.0f;                             // its softmax shift (for the log-sum-exp output)
+    // first half of finishing unit `u`: read its O slice (frees the TMEM region for S(u+2))
+    auto read_o = [&](int u) {
+      const int ii = u >> 1, t = u & 1;
+      mbar_wait(&o_full[t], ii & 1);          // also orders the other column groups' partial sums before us
+      tc_fence_after();
+      if ((t * 128 + quad * 32) < kTok) {
+        tmem_ld16f(tmem_base + t * 256 + cg * 16 + lane_sel, o);
+        // sMax of this region is rewritten by unit u+2, which cannot start before every warp has arrived on tmem_free below
+        const float4 m4 = *reinterpret_cast<const float4*>(&sMax[(t * 128 + row) * 4]);
+        o_shift = fmaxf(fmaxf(m4.x, m4.y), fmaxf(m4.z, m4.w)) * kScaleLog2e;
       }
-#pragma unroll 1
-      for (int t = 0; t < 2; ++t) {
-        const bool valid = (t * 128 + quad * 32) < kTok;
-        uint8_t* myP = sP + t * kPBytes;
-        mbar_wait(&o_full[t], ph);             // also orders the other column groups' partial sums before us
-        tc_fence_after();
-        float o[16];
-        if (valid) tmem_ld16f(tmem_base + t * 256 + cg * 16 + lane_sel, o);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_free[t]);   // S_t / O_t columns are free: the next item's Q K^T may start
-        if (valid) {
-          const float4 s4 = *reinterpret_cast<const float4*>(&sSum[(t * 128 + row) * 4]);
-          const float tot = (s4.x + s4.y) + (s4.z + s4.w);
-          const float inv = 1.0f / tot;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_free[t]);
+    };
+    // second half: normalise and store 16 ctx columns per thread straight to global memory (32 bytes per row: no
+    // staging, no barriers -- the two named barriers and the TMA-store wait of a staged store cost 1.2k cycles per unit)
+    auto store_o = [&](int u) {
+      const int ii = u >> 1, t = u & 1;
+      const int q = t * 128 + row;
+      if (q < kTok) {
+        const int item = blockIdx.x + ii * gridDim.x;
+        const int b = item / kHeads, h = item % kHeads;
+        const float4 s4 = *reinterpret_cast<const float4*>(&sSum[(t * 128 + row) * 4]);
+        const float tot = (s4.x + s4.y) + (s4.z + s4.w);
+        const float inv = 1.0f / tot;
+        uint4* dst = reinterpret_cast<uint4*>(ctx + (static_cast<size_t>(b) * kTok + q) * 192 + h * kHd + cg * 16);
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            uint4 q = make_uint4(pack_bf16x2(o[j * 8 + 0] * inv, o[j * 8 + 1] * inv), pack_bf16x2(o[j * 8 + 2] * inv, o[j * 8 + 3] * inv),
-                                 pack_bf16x2(o[j * 8 + 4] * inv, o[j * 8 + 5] * inv), pack_bf16x2(o[j * 8 + 6] * inv, o[j * 8 + 7] * inv));
-            *reinterpret_cast<uint4*>(myP + sw128_offset(row, cg * 2 + j)) = q;     // P_t is dead: reuse its first panel
-          }
-          fence_proxy_async_smem();
-          named_bar_sync(1 + quad, 128);
-          if (cg == 0) {
-            if (lane == 0) {
-              tma_store_3d(&tmCtx, myP + quad * 32 * 128, h * kHd, t * 128 + quad * 32, b);
-              tma_store_commit();
-            }
-            if (lse != nullptr && t * 128 + row < kTok) {
-              const float4 m4 = *reinterpret_cast<const float4*>(&sMax[(t * 128 + row) * 4]);
-              const float shift = fmaxf(fmaxf(m4.x, m4.y), fmaxf(m4.z, m4.w)) * kScaleLog2e;
-              lse[static_cast<size_t>(item) * kTok + t * 128 + row] = shift + log2f(tot);
-            }
-          }
-        }
+        for (int j = 0; j < 2; ++j)
+          dst[j] = make_uint4(pack_bf16x2(o[j * 8 + 0] * inv, o[j * 8 + 1] * inv), pack_bf16x2(o[j * 8 + 2] * inv, o[j * 8 + 3] * inv),
+                              pack_bf16x2(o[j * 8 + 4] * inv, o[j * 8 + 5] * inv), pack_bf16x2(o[j * 8 + 6] * inv, o[j * 8 + 7] * inv));
+        if (lse != nullptr && cg == 0) lse[static_cast<size_t>(item) * kTok + q] = o_shift + log2f(tot);
       }
+    };
+
+#pragma unroll 1
+    for (int u = 0; u < U; ++u) {
+      const int ii = u >> 1, t = u & 1;
+      const bool valid = (t * 128 + quad * 32) < kTok;       // uniform over the four warps of a quadrant
+      if (warp == 0) trace(1, 10);
+      mbar_wait(&s_full[t], ii & 1);
+      tc_fence_after();
+      if (warp == 0) trace(1, 11);
+      float v[52];                                    // this thread's slice of its score row: TMEM is read exactly once
+      float shift = 0.0f, sum = 0.0f;
+      const uint32_t tS = tmem_base + t * 256 + key0 + lane_sel;
+      const uint32_t tP = tmem_base + t * 256 + 104 + 26 * cg + lane_sel;   // packed bf16 pairs: key pair c -> column 104 + c
+      if (valid) {
+        tmem_ld32(tS, *reinterpret_cast<float(*)[32]>(&v[0]));
+        tmem_ld16f(tS + 32, &v[32]);
+        tmem_ld4f(tS + 48, &v[48]);
+        float m = v[0];
+#pragma unroll
+        for (int i = 1; i < 52; ++i)
+          if (i < 41 || cg != 3) m = fmaxf(m, v[i]);
+        // sMax / sSum of this region were last read while unit u-2 was finished (during unit u-1): this quadrant's
+        // barrier of that unit orders those reads before these writes
+        sMax[(t * 128 + row) * 4 + cg] = m;
+        named_bar_sync(1 + quad, 128);           // every column group has its scores in registers and its max published
+        const float4 m4 = *reinterpret_cast<const float4*>(&sMax[(t * 128 + row) * 4]);
+        shift = fmaxf(fmaxf(m4.x, m4.y), fmaxf(m4.z, m4.w)) * kScaleLog2e;
+        // first 32 exponentials (the MUFU pipe bounds this phase) ...
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { v[i] = ex2_approx(fmaf(v[i], kScaleLog2e, -shift)); sum += v[i]; }
+        uint32_t pw[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) pw[e] = pack_bf16x2(v[2 * e], v[2 * e + 1]);
+        tmem_st16(tP, pw);
+      }
+      if (warp == 0) trace(1, 12);
+      // ... meanwhile the previous unit's P V product has finished: take its O out of TMEM now, so that S(u+1) is issued
+      // while the rest of this unit's exponentials run
+      if (u > 0) read_o(u - 1);
+      if (warp == 0) trace(1, 13);
+      if (valid) {
+#pragma unroll
+        for (int i = 32; i < 52; ++i) {
+          if (i < 41 || cg != 3) { v[i] = ex2_approx(fmaf(v[i], kScaleLog2e, -shift)); sum += v[i]; } else { v[i] = 0.0f; }
+        }
+        uint32_t pw[10];
+#pragma unroll
+        for (int e = 0; e < 10; ++e) pw[e] = pack_bf16x2(v[32 + 2 * e], v[32 + 2 * e + 1]);
+        tmem_st8(tP + 16, pw);
+        tmem_st2(tP + 24, pw[8], pw[9]);
+        sSum[(t * 128 + row) * 4 + cg] = sum;
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+      if (u > 0) store_o(u - 1);
+      if (warp == 0) trace(1, 14);
     }
-    if (cg == 0 && lane == 0) tma_store_wait_all<0>();
+    if (U > 0) { read_o(U - 1); store_o(U - 1); }
   }
 
   tc_fence_before();
@@ -288,6 +317,9 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
 }  // namespace
 
+static long long* g_attn_trace = nullptr;
+void rvk_debug_set_attn_trace_impl(void* buf) { g_attn_trace = static_cast<long long*>(buf); }
+
 int rvk_attention_fwd_launch(const void* qkv, void* ctx, float* lse, int batch, cudaStream_t stream) {
   if (batch <= 0) return RVK_OK;
   static bool configured = false;
@@ -295,12 +327,11 @@ int rvk_attention_fwd_launch(const void* qkv, void* ctx, float* lse, int batch, 
     RVK_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     configured = true;
   }
-  CUtensorMap tmQ, tmKV, tmCtx;
+  CUtensorMap tmQ, tmKV;
   RVK_TRY(rvk_make_tmap_3d(&tmQ, qkv, RVK_BF16, 576, kTok, batch, 576, int64_t(kTok) * 576, 64, 256));
   RVK_TRY(rvk_make_tmap_3d(&tmKV, qkv, RVK_BF16, 576, kTok, batch, 576, int64_t(kTok) * 576, 64, kKeysPad));
-  RVK_TRY(rvk_make_tmap_3d(&tmCtx, ctx, RVK_BF16, 192, kTok, batch, 192, int64_t(kTok) * 192, 64, 32));
   const int items = batch * kHeads;
   const int grid = items < kNumSMsB200 ? items : kNumSMsB200;
-  attn_fwd_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmQ, tmKV, tmCtx, lse, items);
+  attn_fwd_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmQ, tmKV, static_cast<__nv_bfloat16*>(ctx), lse, items, g_attn_trace);
   return rvk_launch_check();
 }
