@@ -109,6 +109,18 @@ int rvk_encoder_backward(const void* const* params_host, const void* wbuf, void*
                          const float* dfeatures, int batch, int chunk_images, void* const* grads_host,
                          void* stream);
 
+/* ---- fused inference tail: all four heads of RoViTKAN.forward (models/rovit_kan.py:96-124 in eval mode) in ONE kernel:
+ * the three Linear-ReLU-Linear heads (models/heads.py:17-22, 38-43, 91-102, log_var clamped to +-10) and the KAN severity
+ * stack KAN(192,64)-ReLU-KAN(64,16)-ReLU-KAN(16,1)-3*sigmoid (models/kan.py:138-149).  Fixed reference architecture
+ * (embed 192, hidden 128, 4 classes, kan_layers [192,64,16,1]).  `params23_host`: host array of 23 DEVICE pointers in the
+ * order cls.fc1.{weight,bias}, cls.fc2.{weight,bias}, ord.fc1.*, ord.fc2.*, unc.fc1.*, unc.fc_mu.*, unc.fc_logvar.*, then
+ * {spline_weights, linear.weight, linear.bias} of kan_layers 0..2.  rvk_heads_fused_prepare repacks them into `ws`
+ * (rvk_heads_fused_workspace_floats() floats; call again whenever a parameter changes). */
+int64_t rvk_heads_fused_workspace_floats(void);
+int rvk_heads_fused_prepare(const void* const* params23_host, float* ws, void* stream);
+int rvk_heads_fused(const float* features, const float* ws, const float* knots_host, int batch, float* cls_logits,
+                    float* ordinal_logits, float* mu, float* log_var, float* kan_severity, void* stream);
+
 /* ---- individual encoder kernels (exposed for parity tests and microbenchmarks) ---------------------- */
 /* C = epilogue(A[M,K] B[N,K]^T), bf16 operands, tcgen05/TMEM.  mode: 0 bf16(acc+bias), 1 gelu (+z in out2),
  * 2 acc*gelu'(aux z), 3 fp32(acc+bias), 4 fp32 acc+bias+residual(aux or table) with optional fused LayerNorm

@@ -29,6 +29,9 @@ SIGNATURES = {
     'rvk_kan_layer_backward': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     'rvk_linear_forward': (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _U64, _U64, _F, _F, _P, _P]),
     'rvk_linear_backward': (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _F, _P, _I, _P, _P, _P, _P]),
+    'rvk_heads_fused_workspace_floats': (_L, []),
+    'rvk_heads_fused_prepare': (_I, [_P, _P, _P]),
+    'rvk_heads_fused': (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P]),
     'rvk_joint_loss_forward': (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     'rvk_joint_loss_backward': (_I, [_P, _P, _I, _F, _P, _I, _P]),
     'rvk_encoder_weight_bytes': (_L, [_I]),

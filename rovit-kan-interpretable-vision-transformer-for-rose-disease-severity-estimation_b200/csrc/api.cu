@@ -146,6 +146,18 @@ int rvk_linear_backward(const float* x, const float* w, const float* y, const fl
   return RVK_OK;
 }
 
+// ---- fused inference tail
+int64_t rvk_heads_fused_workspace_floats(void) { return rvk_heads_fused_workspace_floats_impl(); }
+int rvk_heads_fused_prepare(const void* const* params23_host, float* ws, void* stream) {
+  return rvk_heads_fused_prepare_launch(params23_host, ws, S(stream));
+}
+int rvk_heads_fused(const float* features, const float* ws, const float* knots_host, int batch, float* cls_logits,
+                    float* ordinal_logits, float* mu, float* log_var, float* kan_severity, void* stream) {
+  if (batch < 0) return RVK_ERR_BAD_ARG;
+  return rvk_heads_fused_launch(features, ws, knots_host, batch, cls_logits, ordinal_logits, mu, log_var, kan_severity,
+                                S(stream));
+}
+
 // ---- loss
 int rvk_joint_loss_forward(const float* cls_logits, int num_classes, const float* ord_logits, const float* mu,
                            const float* log_var, const float* kan, const int64_t* class_targets,

@@ -363,6 +363,7 @@ bool kan_tc_disabled() {
 }
 
 #include "kan_tc.cuh"
+#include "heads_fused.cuh"
 
 }  // namespace
 
@@ -470,4 +471,41 @@ int rvk_kan_layer_bwd_launch(const KanLayerDesc& L, const float* x, const float*
     RVK_TRY(rvk_launch_check());
   }
   return RVK_OK;
+}
+
+// ---- fused inference tail (heads_fused.cuh) ---------------------------------------------------------------
+int64_t rvk_heads_fused_workspace_floats_impl() { return kHfWsFloats; }
+
+int rvk_heads_fused_prepare_launch(const void* const* p23, float* ws, cudaStream_t stream) {
+  if (p23 == nullptr || ws == nullptr) return RVK_ERR_BAD_ARG;
+  for (int i = 0; i < 23; ++i)
+    if (p23[i] == nullptr) return RVK_ERR_BAD_ARG;
+  HeadsFusedParams p;
+  auto F = [&](int i) { return static_cast<const float*>(p23[i]); };
+  // order: cls.fc1.{w,b}, cls.fc2.{w,b}, ord.fc1.{w,b}, ord.fc2.{w,b}, unc.fc1.{w,b}, unc.fc_mu.{w,b}, unc.fc_logvar.{w,b},
+  //        kan layer l: spline, lin_w, lin_b  (l = 0, 1, 2)
+  p.fc1_w[0] = F(0); p.fc1_b[0] = F(1); p.fc2_w[0] = F(2); p.fc2_b[0] = F(3);
+  p.fc1_w[1] = F(4); p.fc1_b[1] = F(5); p.fc2_w[1] = F(6); p.fc2_b[1] = F(7);
+  p.fc1_w[2] = F(8); p.fc1_b[2] = F(9); p.fc2_w[2] = F(10); p.fc2_b[2] = F(11); p.fc2_w[3] = F(12); p.fc2_b[3] = F(13);
+  for (int l = 0; l < 3; ++l) { p.spline[l] = F(14 + 3 * l); p.lin_w[l] = F(15 + 3 * l); p.lin_b[l] = F(16 + 3 * l); }
+  heads_fused_pack_kernel<<<(kHfWsFloats + 255) / 256, 256, 0, stream>>>(p, ws);
+  return rvk_launch_check();
+}
+
+int rvk_heads_fused_launch(const float* features, const float* ws, const float* knots_host, int batch, float* cls,
+                           float* ord, float* mu, float* log_var, float* kan, cudaStream_t stream) {
+  if (batch <= 0) return RVK_OK;
+  if (features == nullptr || ws == nullptr || knots_host == nullptr || cls == nullptr || ord == nullptr || mu == nullptr ||
+      log_var == nullptr || kan == nullptr)
+    return RVK_ERR_BAD_ARG;
+  static bool configured = false;
+  if (!configured) {
+    RVK_CUDA_TRY(cudaFuncSetAttribute(heads_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHfSmemBytes));
+    configured = true;
+  }
+  Knots kn;
+  for (int i = 0; i < kKnots; ++i) kn.k[i] = knots_host[i];
+  heads_fused_kernel<<<(batch + kHfS - 1) / kHfS, kHfThreads, kHfSmemBytes, stream>>>(features, ws, kn, batch, cls, ord, mu,
+                                                                                     log_var, kan);
+  return rvk_launch_check();
 }

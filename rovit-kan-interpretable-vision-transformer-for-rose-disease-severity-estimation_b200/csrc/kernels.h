@@ -89,6 +89,14 @@ int rvk_kan_layer_bwd_launch(const KanLayerDesc& L, const float* x, const float*
                              float* dx, float* dspline, float* dlin_w, float* dlin_b, int batch, float* workspace,
                              cudaStream_t stream);
 
+// fused inference tail: all four heads in one kernel (heads_fused.cuh).  p23: 23 device pointers in the order
+// cls.fc1.{w,b}, cls.fc2.{w,b}, ord.fc1.{w,b}, ord.fc2.{w,b}, unc.fc1.{w,b}, unc.fc_mu.{w,b}, unc.fc_logvar.{w,b}, then
+// (spline, lin_w, lin_b) of the three KAN layers; fixed architecture 192 -> 128 -> {4,3,1,1} and KAN [192,64,16,1].
+int64_t rvk_heads_fused_workspace_floats_impl();
+int rvk_heads_fused_prepare_launch(const void* const* p23, float* ws, cudaStream_t stream);
+int rvk_heads_fused_launch(const float* features, const float* ws, const float* knots_host, int batch, float* cls,
+                           float* ord, float* mu, float* log_var, float* kan, cudaStream_t stream);
+
 // ---- heads (fp32 SIMT GEMM with fused epilogues) and joint loss -------------------------------------------
 struct SgemmArgs {
   const float* A = nullptr; int64_t lda = 0; int transA = 0;

@@ -11,6 +11,7 @@ from typing import Dict
 import torch
 import torch.nn as nn
 
+from ._bootstrap import ops as _ops
 from .backbone import DeiTTinyBackbone
 from .heads import ClassificationHead, OrdinalHead, UncertaintyHead
 from .kan import KANSeverityModule
@@ -57,9 +58,34 @@ class RoViTKAN(nn.Module):
         assert 1 <= stage <= 4, "Stage must be between 1 and 4"
         self._curriculum_stage = stage
 
+    def _fused_tail_params(self):
+        """The 23 head / KAN tensors in the order rvk_heads_fused expects, or None if this instance does not have the
+        reference architecture (192 -> 128 -> {4,3,1,1}, kan_layers [192,64,16,1])."""
+        c, o, u, k = self.classification_head, self.ordinal_head, self.uncertainty_head, self.kan_module
+        if (tuple(c.fc1.weight.shape) != (128, 192) or tuple(c.fc2.weight.shape) != (4, 128) or
+                tuple(o.fc2.weight.shape) != (3, 128) or list(k.layers_dims) != [192, 64, 16, 1]):
+            return None
+        if len({l.knots_host() for l in k.kan_layers}) != 1:      # the fused kernel uses one knot vector for the stack
+            return None
+        ps = [c.fc1.weight, c.fc1.bias, c.fc2.weight, c.fc2.bias, o.fc1.weight, o.fc1.bias, o.fc2.weight, o.fc2.bias,
+              u.fc1.weight, u.fc1.bias, u.fc_mu.weight, u.fc_mu.bias, u.fc_logvar.weight, u.fc_logvar.bias]
+        for l in k.kan_layers:
+            ps += [l.spline_weights, l.linear.weight, l.linear.bias]
+        return ps
+
     def forward(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
         features = self.backbone(x)
         stage = self._curriculum_stage
+        if stage == 4 and not self.training and not torch.is_grad_enabled() and features.is_cuda:
+            # inference: the whole multi-task tail is one kernel launch (csrc/heads_fused.cuh)
+            ps = self._fused_tail_params()
+            if ps is not None:
+                ops = _ops()
+                if getattr(self, '_tail_state', None) is None:
+                    self._tail_state = ops.HeadsFusedState()
+                cls, ordl, mu, lv, kan = ops.heads_fused(self._tail_state, features, ps, self.kan_module.kan_layers[0].knots_host())
+                return {'cls_logits': cls, 'features': features, 'ordinal_logits': ordl, 'mu': mu, 'log_var': lv,
+                        'kan_severity': kan}
         out = {'cls_logits': self.classification_head(features), 'features': features,
                'ordinal_logits': None, 'mu': None, 'log_var': None, 'kan_severity': None}
         if stage >= 2:

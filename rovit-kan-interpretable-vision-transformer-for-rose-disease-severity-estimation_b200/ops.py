@@ -284,3 +284,38 @@ class EncoderFn(torch.autograd.Function):
                       ctx.chunk, ctx.state.param_table(views), _stream())
         ctx.ws = None
         return (None, None, *views)
+
+
+# --------------------------------------------------------------------------------------------- fused inference tail
+class HeadsFusedState:
+    """Cache of the repacked head / KAN weights for the one-kernel inference tail (rvk_heads_fused)."""
+
+    def __init__(self):
+        self.ws = None
+        self.key = None
+
+
+def heads_fused(state: HeadsFusedState, features: torch.Tensor, params, knots_host):
+    """All four heads of RoViTKAN.forward (eval mode, reference rovit_kan.py:96-124) in one kernel launch.
+    `params`: the 23 tensors in the order documented in include/rovitkan.h."""
+    require_cuda(features, 'RoViTKAN heads')
+    f = _f32c(features)
+    batch, dev = f.shape[0], f.device
+    pc = [_f32c(p.detach()) for p in params]
+    key = (dev, tuple(p.data_ptr() for p in pc), tuple(p._version for p in params))
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        if state.ws is None or state.key != key:
+            if state.ws is None or state.ws.device != dev:
+                state.ws = torch.empty(lib.rvk_heads_fused_workspace_floats(), device=dev, dtype=torch.float32)
+            table = (C.c_void_p * len(pc))(*[p.data_ptr() for p in pc])
+            _lib.call('rvk_heads_fused_prepare', table, _p(state.ws), _stream())
+            state.key = key
+        cls = torch.empty(batch, 4, device=dev, dtype=torch.float32)
+        ordl = torch.empty(batch, 3, device=dev, dtype=torch.float32)
+        mu = torch.empty(batch, 1, device=dev, dtype=torch.float32)
+        lv = torch.empty(batch, 1, device=dev, dtype=torch.float32)
+        kan = torch.empty(batch, 1, device=dev, dtype=torch.float32)
+        _lib.call('rvk_heads_fused', _p(f), _p(state.ws), _host_floats(knots_host), batch, _p(cls), _p(ordl), _p(mu), _p(lv),
+                  _p(kan), _stream())
+    return cls, ordl, mu, lv, kan

@@ -224,3 +224,33 @@ def test_loss_known_answer_and_cutmix_blend():
     (lam * ra['total_loss'] + (1 - lam) * rb['total_loss']).backward()
     for k in oo:
         assert_close(oo[k].grad, oc[k].grad, rtol=1e-3, atol=1e-7, what='blend d' + k)
+
+
+@pytest.mark.parametrize('batch', [1, 16, 1000])
+def test_fused_inference_tail_matches_per_head_kernels_and_oracle(batch):
+    """RoViTKAN.forward in eval mode under no_grad runs all four heads in ONE kernel (rvk_heads_fused); with grad enabled
+    the same module runs the per-head kernels.  Both must agree with each other and with the CPU oracle to the fp32 bound."""
+    from rovitkan_b200.models import RoViTKAN
+    torch.manual_seed(3)
+    m = RoViTKAN(pretrained=False).to(DEV).eval()
+    feats = torch.randn(batch, 192) * 0.8
+    fd = feats.to(DEV)
+    ps = m._fused_tail_params()
+    assert ps is not None
+    from rovitkan_b200 import ops
+    st = ops.HeadsFusedState()
+    cls, ordl, mu, lv, kan = ops.heads_fused(st, fd, ps, m.kan_module.kan_layers[0].knots_host())
+    with torch.enable_grad():
+        ref = {'cls': m.classification_head(fd), 'ord': m.ordinal_head(fd), 'kan': m.kan_module(fd)}
+        ref['mu'], ref['lv'] = m.uncertainty_head(fd)
+    for name, a in (('cls', cls), ('ord', ordl), ('mu', mu), ('lv', lv), ('kan', kan)):
+        assert_close(a, ref[name].detach(), rtol=1e-3, atol=2e-5, what=f'fused tail {name} vs per-head kernels')
+    assert bool((cls.argmax(1) == ref['cls'].argmax(1)).all())
+    layers = [(l.spline_weights.detach().cpu(), l.linear.weight.detach().cpu(), l.linear.bias.detach().cpu())
+              for l in m.kan_module.kan_layers]
+    assert_close(kan, okan.severity_forward(feats, layers, okan.make_knots()), rtol=1e-3, atol=2e-5, what='fused tail kan vs oracle')
+    # weight update -> repack
+    with torch.no_grad():
+        m.classification_head.fc2.bias.add_(1.0)
+    cls2 = ops.heads_fused(st, fd, m._fused_tail_params(), m.kan_module.kan_layers[0].knots_host())[0]
+    assert_close(cls2, cls + 1.0, rtol=1e-5, atol=1e-5, what='repack after parameter update')
