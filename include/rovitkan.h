@@ -105,6 +105,10 @@ int rvk_encoder_prepare_weights(const void* const* params_host, void* wbuf, int 
 int rvk_encoder_forward(const void* const* params_host, const void* wbuf, const float* images, int batch,
                         int training, int chunk_images, void* workspace, float* features, void* stream);
 /* Needs the workspace of the matching forward (training=1).  Gradients are accumulated (+=). */
+/* Same with bf16 images (B,3,224,224): halves the host->device copy of a serving loop; the result is bit-identical
+ * to rvk_encoder_forward on the fp32 images these were rounded from (the trunk rounds pixels to bf16 first). */
+int rvk_encoder_forward_bf16(const void* const* params_host, const void* wbuf, const void* images_bf16, int batch,
+                             int training, int chunk_images, void* workspace, float* features, void* stream);
 int rvk_encoder_backward(const void* const* params_host, const void* wbuf, void* workspace,
                          const float* dfeatures, int batch, int chunk_images, void* const* grads_host,
                          void* stream);

@@ -38,6 +38,7 @@ SIGNATURES = {
     'rvk_encoder_workspace_bytes': (_L, [_I, _I, _I]),
     'rvk_encoder_prepare_weights': (_I, [_P, _P, _I, _P]),
     'rvk_encoder_forward': (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    'rvk_encoder_forward_bf16': (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     'rvk_encoder_backward': (_I, [_P, _P, _P, _P, _I, _I, _P, _P]),
     'rvk_gemm_nt': (_I, [_I, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _P, _P, _I, _F, _P, _P, _P]),
     'rvk_mlp_fused': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _I, _I, _P]),

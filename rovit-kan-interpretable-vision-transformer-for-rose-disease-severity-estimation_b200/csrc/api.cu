@@ -191,7 +191,13 @@ int rvk_encoder_prepare_weights(const void* const* params_host, void* wbuf, int 
 int rvk_encoder_forward(const void* const* params_host, const void* wbuf, const float* images, int batch, int training,
                         int chunk_images, void* workspace, float* features, void* stream) {
   if (batch < 0) return RVK_ERR_BAD_ARG;
-  return rvk_encoder_forward_impl(params_host, wbuf, images, batch, training, chunk_images, workspace, features, S(stream));
+  return rvk_encoder_forward_impl(params_host, wbuf, images, 0, batch, training, chunk_images, workspace, features, S(stream));
+}
+int rvk_encoder_forward_bf16(const void* const* params_host, const void* wbuf, const void* images_bf16, int batch,
+                             int training, int chunk_images, void* workspace, float* features, void* stream) {
+  if (batch < 0) return RVK_ERR_BAD_ARG;
+  return rvk_encoder_forward_impl(params_host, wbuf, images_bf16, 1, batch, training, chunk_images, workspace, features,
+                                  S(stream));
 }
 int rvk_encoder_backward(const void* const* params_host, const void* wbuf, void* workspace, const float* dfeatures,
                          int batch, int chunk_images, void* const* grads_host, void* stream) {
@@ -267,7 +273,7 @@ int rvk_layernorm_backward(const void* g, int g_is_bf16, int64_t g_row_stride, c
 }
 int rvk_im2col(const float* images, void* patches_bf16, int batch, void* stream) {
   if (batch < 0 || (batch > 0 && (images == nullptr || patches_bf16 == nullptr))) return RVK_ERR_BAD_ARG;
-  return rvk_im2col_launch(images, patches_bf16, batch, S(stream));
+  return rvk_im2col_launch(images, 0, patches_bf16, batch, S(stream));
 }
 int rvk_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream) {
   if (n < 0 || (n > 0 && (src == nullptr || dst_bf16 == nullptr))) return RVK_ERR_BAD_ARG;

@@ -17,7 +17,10 @@ constexpr int kPatchK = 768;
 // bytes of the bf16 patch matrix [B*197, 768] (column = c*256 + ky*16 + kx, the flattening of the
 // Conv2d(3,192,16,16) weight).  Token 0 (cls slot) is an all-zero row: the class token enters
 // through the additive token table, so the patch GEMM can emit the [B*197,192] stream directly.
-__global__ void im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int batch) {
+// IN_BF16: the images are already bf16 (a serving path that halves the host->device copy; bit-identical result, the
+// fp32 path rounds the pixels to bf16 here anyway)
+template <bool IN_BF16>
+__global__ void im2col_kernel(const void* __restrict__ img_v, __nv_bfloat16* __restrict__ out, int batch) {
   const int lane = threadIdx.x & 31;
   const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long total = static_cast<long long>(batch) * kTok * 3;
@@ -29,10 +32,15 @@ __global__ void im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __re
   const int ky = lane >> 1, half = lane & 1;
   if (tok > 0) {
     const int p = tok - 1, py = p / 14, px = p % 14;
-    const float* src = img + ((static_cast<size_t>(b) * 3 + c) * 224 + (py * 16 + ky)) * 224 + px * 16 + half * 8;
-    const float4 a = *reinterpret_cast<const float4*>(src);
-    const float4 d = *reinterpret_cast<const float4*>(src + 4);
-    v = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(d.x, d.y), pack_bf16x2(d.z, d.w));
+    const size_t off = ((static_cast<size_t>(b) * 3 + c) * 224 + (py * 16 + ky)) * 224 + px * 16 + half * 8;
+    if (IN_BF16) {
+      v = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(img_v) + off);
+    } else {
+      const float* src = static_cast<const float*>(img_v) + off;
+      const float4 a = *reinterpret_cast<const float4*>(src);
+      const float4 d = *reinterpret_cast<const float4*>(src + 4);
+      v = make_uint4(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w), pack_bf16x2(d.x, d.y), pack_bf16x2(d.z, d.w));
+    }
   }
   __nv_bfloat16* dst = out + (static_cast<size_t>(b) * kTok + tok) * kPatchK + c * 256 + ky * 16 + half * 8;
   *reinterpret_cast<uint4*>(dst) = v;
@@ -236,13 +244,15 @@ __global__ void token_grad_reduce_kernel(const float* __restrict__ dx0, int batc
 
 }  // namespace
 
-int rvk_im2col_launch(const float* images, void* patches_bf16, int batch, cudaStream_t stream) {
+int rvk_im2col_launch(const void* images, int images_bf16, void* patches_bf16, int batch, cudaStream_t stream) {
   if (batch <= 0) return RVK_OK;
   const long long warps = static_cast<long long>(batch) * kTok * 3;
   const int threads = 256;
   const long long blocks = (warps * 32 + threads - 1) / threads;
-  im2col_kernel<<<static_cast<unsigned>(blocks), threads, 0, stream>>>(images, static_cast<__nv_bfloat16*>(patches_bf16),
-                                                                       batch);
+  if (images_bf16)
+    im2col_kernel<true><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(images, static_cast<__nv_bfloat16*>(patches_bf16), batch);
+  else
+    im2col_kernel<false><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(images, static_cast<__nv_bfloat16*>(patches_bf16), batch);
   return rvk_launch_check();
 }
 

@@ -47,7 +47,7 @@ int rvk_attention_bwd_launch(const void* qkv, const void* ctx, const void* dctx,
                              int batch, cudaStream_t stream);
 
 // ---- token-stream kernels (encoder_kernels.cu) -----------------------------------------------------
-int rvk_im2col_launch(const float* images, void* patches_bf16, int batch, cudaStream_t stream);
+int rvk_im2col_launch(const void* images, int images_bf16, void* patches_bf16, int batch, cudaStream_t stream);
 int rvk_token_table_launch(const float* cls_token, const float* pos_embed, const float* patch_bias, float* table,
                            cudaStream_t stream);
 int rvk_cast_bf16_launch(const float* src, void* dst, int64_t n, cudaStream_t stream);

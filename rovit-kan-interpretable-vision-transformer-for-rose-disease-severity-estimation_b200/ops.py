@@ -240,14 +240,17 @@ class EncoderFn(torch.autograd.Function):
     reference models/backbone.py:23-25 calls).  `params`: the 150 trunk tensors in timm order."""
 
     @staticmethod
-    @custom_fwd(device_type='cuda', cast_inputs=torch.float32)
+    @custom_fwd(device_type='cuda')
     def forward(ctx, state, images, *params):
         require_cuda(images, 'DeiTTinyBackbone.forward')
         if images.dim() != 4 or tuple(images.shape[1:]) != (3, 224, 224):
             raise ValueError(f'expected images of shape (B, 3, 224, 224), got {tuple(images.shape)}')
         for p in params:
             require_cuda(p, 'DeiTTinyBackbone parameters')
-        img = _f32c(images)
+        # bf16 images are consumed as they are (the trunk rounds pixels to bf16 first anyway); anything else as fp32
+        img_bf16 = images.dtype == torch.bfloat16
+        img = images.contiguous() if img_bf16 else _f32c(images)
+        params = tuple(p.float() if p.dtype != torch.float32 else p for p in params)
         batch = img.shape[0]
         dev = img.device
         training = any(ctx.needs_input_grad[2:])      # callers pass detached tensors under torch.no_grad()
@@ -261,8 +264,8 @@ class EncoderFn(torch.autograd.Function):
                 ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
             else:
                 ws = state.inference_workspace(batch, chunk, dev)
-            _lib.call('rvk_encoder_forward', state.param_table(pc), _p(wbuf), _p(img), batch, int(training), chunk,
-                      _p(ws), _p(feats), _stream())
+            _lib.call('rvk_encoder_forward_bf16' if img_bf16 else 'rvk_encoder_forward', state.param_table(pc), _p(wbuf),
+                      _p(img), batch, int(training), chunk, _p(ws), _p(feats), _stream())
         if training:
             ctx.state, ctx.ws, ctx.wbuf, ctx.batch, ctx.chunk = state, ws, wbuf, batch, chunk
             ctx.params = pc

@@ -323,3 +323,17 @@ def test_cpu_input_is_rejected_not_emulated():
     m = RoViTKAN(pretrained=False)
     with pytest.raises(RuntimeError, match='no CPU fallback'):
         m(torch.randn(1, 3, 224, 224))
+
+
+def test_bf16_images_give_bit_identical_features():
+    """model(images.bfloat16()) (serving path: half the host->device bytes) == model(images) when the fp32 images are
+    exactly representable in bf16 -- the trunk rounds pixels to bf16 as its first step either way."""
+    from rovitkan_b200.models import RoViTKAN
+    torch.manual_seed(2)
+    m = RoViTKAN(pretrained=False).to('cuda').eval()
+    x = torch.randn(5, 3, 224, 224, device='cuda').to(torch.bfloat16)
+    with torch.no_grad():
+        a = m(x)
+        b = m(x.float())
+    for k in ('features', 'cls_logits', 'kan_severity'):
+        assert torch.equal(a[k], b[k]), k
