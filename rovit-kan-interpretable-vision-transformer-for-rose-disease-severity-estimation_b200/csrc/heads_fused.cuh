@@ -6,14 +6,18 @@
 //                    -> mu, log_var [B,1]                shared Linear(192,128) -> ReLU; two Linear(128,1); clamp +-10   heads.py:91-102
 //                    -> KAN severity [B,1]               KAN(192->64) -> ReLU -> KAN(64->16) -> ReLU -> KAN(16->1) -> 3*sigmoid   kan.py:138-149
 // (eval mode: Dropout is the identity).  Unfused this tail is 7 GEMM launches + 3 KAN launches + 3 weight packs, each
-// on a grid of a few dozen CTAs: 0.3 ms of a 5.5 ms forward at batch 1024.  Here a CTA owns 16 samples end to end: the
-// feature tile, the 3 x 128 hidden activations and the expanded KAN activations live in shared memory, all weights
-// stream from a prepacked L2-resident buffer (transposed so that consecutive threads read consecutive outputs).
-// fp32 throughout: argmax / ordinal decisions stay bit-comparable with the reference given the same features.
+// on a grid of a few dozen CTAs: 0.3 ms of a 5.5 ms forward at batch 1024.  Here a CTA of 512 threads owns 8 samples end
+// to end (128 CTAs at batch 1024): the feature tile, the 3 x 128 hidden activations and the expanded KAN activations live
+// in shared memory; the two big weight matrices (fc1 of the heads, KAN layer 0) stream from a prepacked L2-resident
+// buffer (transposed so that consecutive threads read consecutive outputs) with the contraction dimension SPLIT across
+// warps (8 resp. 4 ways, partial sums reduced through shared memory) so that the chain of dependent L2 round trips per
+// thread is 24 + 6 batches instead of 192 + 96; the small late-layer weights are prefetched into shared memory with
+// cp.async while the first phase runs.  fp32 throughout: argmax / ordinal decisions stay bit-comparable with the
+// reference given the same features.
 #pragma once
 
-constexpr int kHfS = 16;                    // samples per CTA
-constexpr int kHfThreads = 256;
+constexpr int kHfS = 8;                     // samples per CTA
+constexpr int kHfThreads = 512;
 constexpr int kHfD = 192, kHfH = 128, kHfU = 3 * kHfH;
 constexpr int kHfK0 = 192, kHfO0 = 64, kHfO1 = 16;          // KAN stack 192 -> 64 -> 16 -> 1
 // prepacked weight buffer (floats)
@@ -28,7 +32,23 @@ constexpr int kHfOffKb1 = kHfOffWp1 + kHfO0 * 8 * kHfO1;      // [16]
 constexpr int kHfOffWp2 = kHfOffKb1 + kHfO1;                  // [16*8]
 constexpr int kHfOffKb2 = kHfOffWp2 + kHfO1 * 8;              // [1] (+3 pad)
 constexpr int kHfWsFloats = kHfOffKb2 + 4;
-constexpr int kHfSmemBytes = (kHfD * kHfS + kHfS * kHfU + kHfK0 * 8 * kHfS + kHfS * kHfO0 + kHfS * kHfO1) * 4;
+// shared memory (floats)
+constexpr int kHfAStride = 72;               // expanded activations [input i][basis j][sample s], i-stride padded (bank spread)
+constexpr int kHfHStride = kHfU + 4;         // hidden activations [sample][384], padded
+constexpr int kHfG0 = 8;                     // K split of KAN layer 0 (1536 / 8 = 192 per thread)
+constexpr int kHfG1 = 4;                     // K split of the heads' fc1 (192 / 4 = 48 per thread) and of KAN layer 1
+constexpr int kHfTailFloats = kHfWsFloats - kHfOffWp1;        // Wp1, kb1, Wp2, kb2
+constexpr int kHfW2Floats = kHfOffWp0 - kHfOffW2;             // fc2 weights + biases
+constexpr int kHfSmF = 0;                                     // [192][8] features, transposed
+constexpr int kHfSmA = kHfSmF + kHfD * kHfS;                  // [192][72] expanded KAN activations (layer 1 reuses [64][72])
+constexpr int kHfSmP0 = kHfSmA + kHfK0 * kHfAStride;          // [8][64][8] KAN layer-0 partial sums (layer 1 reuses [4][128])
+constexpr int kHfSmP1 = kHfSmP0 + kHfG0 * kHfO0 * kHfS;       // [4][384][8] fc1 partial sums
+constexpr int kHfSmH = kHfSmP1 + kHfG1 * kHfU * kHfS;         // [8][388] hidden activations
+constexpr int kHfSmW2 = kHfSmH + kHfS * kHfHStride;           // fc2 weights + biases
+constexpr int kHfSmTail = kHfSmW2 + kHfW2Floats;              // Wp1, kb1, Wp2, kb2
+constexpr int kHfSmemBytes = (kHfSmTail + kHfTailFloats) * 4;
+static_assert(kHfOffW2 % 4 == 0 && kHfOffWp1 % 4 == 0 && kHfW2Floats % 4 == 0 && kHfTailFloats % 4 == 0, "16-byte cp.async");
+static_assert(kHfSmW2 % 4 == 0 && kHfSmTail % 4 == 0 && kHfSmH % 4 == 0 && kHfSmA % 4 == 0, "float4 alignment");
 
 struct HeadsFusedParams {          // device pointers, reference parameter layouts
   const float* fc1_w[3]; const float* fc1_b[3];      // cls, ord, unc: [128,192], [128]
@@ -72,120 +92,174 @@ __global__ void heads_fused_pack_kernel(const HeadsFusedParams p, float* __restr
   }
 }
 
-__global__ void __launch_bounds__(kHfThreads)
+__device__ __forceinline__ void hf_cp_async16(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gsrc) : "memory");
+}
+
+__global__ void __launch_bounds__(kHfThreads, 1)
 heads_fused_kernel(const float* __restrict__ feat, const float* __restrict__ ws, Knots kn, int batch,
                    float* __restrict__ cls, float* __restrict__ ord, float* __restrict__ mu, float* __restrict__ log_var,
                    float* __restrict__ kan) {
   extern __shared__ __align__(16) float hsm[];
-  float* sF = hsm;                          // [192][16]   features, transposed: sF[k][s]
-  float* sH = sF + kHfD * kHfS;             // [16][384]   hidden activations of the three heads
-  float* sA = sH + kHfS * kHfU;             // [1536][16]  expanded KAN activations sA[i*8+k][s]
-  float* sK1 = sA + kHfK0 * 8 * kHfS;       // [64][16]    KAN layer-0 output (transposed)
-  float* sK2 = sK1 + kHfS * kHfO0;          // [16][16]    KAN layer-1 output (transposed)
-  const int tid = threadIdx.x;
+  float* sF = hsm + kHfSmF;
+  float* sA = hsm + kHfSmA;
+  float* sP0 = hsm + kHfSmP0;
+  float* sP1 = hsm + kHfSmP1;
+  float* sH = hsm + kHfSmH;
+  float* sW2 = hsm + kHfSmW2;
+  float* sTail = hsm + kHfSmTail;
+  const float* sWp1 = sTail;                                   // [512][16]
+  const float* sKb1 = sTail + (kHfOffKb1 - kHfOffWp1);
+  const float* sWp2 = sTail + (kHfOffWp2 - kHfOffWp1);         // [16][8]
+  const float* sKb2 = sTail + (kHfOffKb2 - kHfOffWp1);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int s0 = blockIdx.x * kHfS;
+
+  // late-layer weights -> shared memory, asynchronously (needed after the second barrier at the earliest)
+  for (int i = tid; i < kHfW2Floats / 4; i += kHfThreads) hf_cp_async16(sW2 + 4 * i, ws + kHfOffW2 + 4 * i);
+  for (int i = tid; i < kHfTailFloats / 4; i += kHfThreads) hf_cp_async16(sTail + 4 * i, ws + kHfOffWp1 + 4 * i);
+  asm volatile("cp.async.commit_group;" ::: "memory");
 
   for (int idx = tid; idx < kHfS * kHfD; idx += kHfThreads) {
     const int s = idx / kHfD, k = idx % kHfD;
     sF[k * kHfS + s] = (s0 + s < batch) ? feat[static_cast<size_t>(s0 + s) * kHfD + k] : 0.0f;
   }
   __syncthreads();
-
-  // ---- hidden layers of the three heads: unit u = head*128 + j; thread owns units tid (and tid + 256 < 384)
-  for (int u = tid; u < kHfU; u += kHfThreads) {
-    float acc[kHfS];
-#pragma unroll
-    for (int s = 0; s < kHfS; ++s) acc[s] = 0.0f;
-    const float* w = ws + kHfOffW1T + u;
-#pragma unroll 4
-    for (int k = 0; k < kHfD; ++k) {
-      const float wk = w[k * kHfU];
-      const float4* f4 = reinterpret_cast<const float4*>(sF + k * kHfS);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 f = f4[q];
-        acc[4 * q + 0] = fmaf(f.x, wk, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(f.y, wk, acc[4 * q + 1]);
-        acc[4 * q + 2] = fmaf(f.z, wk, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(f.w, wk, acc[4 * q + 3]);
-      }
-    }
-    const float b = ws[kHfOffB1 + u];
-#pragma unroll
-    for (int s = 0; s < kHfS; ++s) sH[s * kHfU + u] = fmaxf(acc[s] + b, 0.0f);
-  }
   // ---- expanded KAN activations of layer 0 (same closed form / tanhf as the per-layer kernel)
-  for (int pr = tid; pr < kHfS * kHfK0; pr += kHfThreads) {
-    const int s = pr / kHfK0, i = pr % kHfK0;
+  for (int idx = tid; idx < kHfS * kHfK0; idx += kHfThreads) {
+    const int s = idx & (kHfS - 1), i = idx >> 3;
     float a[kKW], da[kKW], dt;
     kan_expand<false>(sF[i * kHfS + s], kn, a, da, dt);
 #pragma unroll
-    for (int k = 0; k < kKW; ++k) sA[(i * 8 + k) * kHfS + s] = a[k];
+    for (int k = 0; k < kKW; ++k) sA[i * kHfAStride + k * kHfS + s] = a[k];
   }
-  __syncthreads();
-
-  // ---- second layers of the heads: 9 outputs x 16 samples
-  if (tid < 9 * kHfS) {
-    const int o = tid % 9, s = tid / 9;
-    const int head = (o < 4) ? 0 : (o < 7) ? 1 : 2;
-    const float* w = ws + kHfOffW2 + o * kHfH;
-    const float* h = sH + s * kHfU + head * kHfH;
-    float acc = 0.0f;
-#pragma unroll 8
-    for (int j = 0; j < kHfH; ++j) acc = fmaf(h[j], w[j], acc);
-    acc += ws[kHfOffB2 + o];
-    const int sg = s0 + s;
-    if (sg < batch) {
-      if (o < 4) cls[static_cast<size_t>(sg) * 4 + o] = acc;
-      else if (o < 7) ord[static_cast<size_t>(sg) * 3 + (o - 4)] = acc;
-      else if (o == 7) mu[sg] = acc;
-      else log_var[sg] = fminf(fmaxf(acc, -10.0f), 10.0f);
-    }
-  }
-  // ---- KAN layer 0: thread (o = tid % 64, samples 4*(tid/64) .. +3)
+  // ---- fc1 of the three heads: thread = (unit j of every head, quarter kq of the 192 inputs)
   {
-    const int o = tid & 63, sg4 = (tid >> 6) * 4;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    const float* w = ws + kHfOffWp0 + o;
-#pragma unroll 8
-    for (int kk = 0; kk < kHfK0 * 8; ++kk) {
-      const float wk = w[kk * kHfO0];
-      const float4 a = *reinterpret_cast<const float4*>(sA + kk * kHfS + sg4);
-      acc[0] = fmaf(a.x, wk, acc[0]); acc[1] = fmaf(a.y, wk, acc[1]);
-      acc[2] = fmaf(a.z, wk, acc[2]); acc[3] = fmaf(a.w, wk, acc[3]);
-    }
-    const float b = ws[kHfOffKb0 + o];
+    const int j = tid & (kHfH - 1), kq = tid >> 7;
+    float acc[3][kHfS];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) sK1[o * kHfS + sg4 + q] = fmaxf(acc[q] + b, 0.0f);
+    for (int h = 0; h < 3; ++h)
+#pragma unroll
+      for (int s = 0; s < kHfS; ++s) acc[h][s] = 0.0f;
+    const float* w = ws + kHfOffW1T + static_cast<size_t>(kq * (kHfD / kHfG1)) * kHfU + j;
+    const float* f = sF + kq * (kHfD / kHfG1) * kHfS;
+#pragma unroll 8
+    for (int k = 0; k < kHfD / kHfG1; ++k) {
+      const float w0 = __ldg(w + k * kHfU), w1 = __ldg(w + k * kHfU + kHfH), w2 = __ldg(w + k * kHfU + 2 * kHfH);
+      const float4 fa = *reinterpret_cast<const float4*>(f + k * kHfS);
+      const float4 fb = *reinterpret_cast<const float4*>(f + k * kHfS + 4);
+      const float fv[8] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w};
+#pragma unroll
+      for (int s = 0; s < kHfS; ++s) {
+        acc[0][s] = fmaf(fv[s], w0, acc[0][s]);
+        acc[1][s] = fmaf(fv[s], w1, acc[1][s]);
+        acc[2][s] = fmaf(fv[s], w2, acc[2][s]);
+      }
+    }
+#pragma unroll
+    for (int h = 0; h < 3; ++h) {
+      float* dst = sP1 + (kq * kHfU + h * kHfH + j) * kHfS;
+      *reinterpret_cast<float4*>(dst) = make_float4(acc[h][0], acc[h][1], acc[h][2], acc[h][3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[h][4], acc[h][5], acc[h][6], acc[h][7]);
+    }
   }
-  __syncthreads();
-  // ---- KAN layer 1 (64 -> 16): expand, then thread (o = tid % 16, sample tid / 16)
-  for (int pr = tid; pr < kHfS * kHfO0; pr += kHfThreads) {
-    const int s = pr / kHfO0, i = pr % kHfO0;
+  __syncthreads();          // sA complete
+  // ---- KAN layer 0: thread = (output o, eighth g of the 1536 expanded inputs)
+  {
+    const int o = tid & (kHfO0 - 1), g = tid >> 6;
+    constexpr int kIPer = kHfK0 / kHfG0;      // 24 inputs = 192 expanded rows
+    float acc[kHfS];
+#pragma unroll
+    for (int s = 0; s < kHfS; ++s) acc[s] = 0.0f;
+    const float* w = ws + kHfOffWp0 + static_cast<size_t>(g * kIPer * 8) * kHfO0 + o;
+    const float* a = sA + g * kIPer * kHfAStride;
+#pragma unroll 2
+    for (int i = 0; i < kIPer; ++i) {
+      float wv[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) wv[k] = __ldg(w + (i * 8 + k) * kHfO0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float4 aa = *reinterpret_cast<const float4*>(a + i * kHfAStride + k * kHfS);
+        const float4 ab = *reinterpret_cast<const float4*>(a + i * kHfAStride + k * kHfS + 4);
+        acc[0] = fmaf(aa.x, wv[k], acc[0]); acc[1] = fmaf(aa.y, wv[k], acc[1]);
+        acc[2] = fmaf(aa.z, wv[k], acc[2]); acc[3] = fmaf(aa.w, wv[k], acc[3]);
+        acc[4] = fmaf(ab.x, wv[k], acc[4]); acc[5] = fmaf(ab.y, wv[k], acc[5]);
+        acc[6] = fmaf(ab.z, wv[k], acc[6]); acc[7] = fmaf(ab.w, wv[k], acc[7]);
+      }
+    }
+    float* dst = sP0 + (g * kHfO0 + o) * kHfS;
+    *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();          // partial sums + prefetched weights visible; every thread is done reading sA
+  // ---- reduce: hidden activations of the heads (bias, ReLU) ...
+  for (int idx = tid; idx < kHfU * kHfS; idx += kHfThreads) {
+    const int s = idx & (kHfS - 1), u = idx >> 3;
+    float v = __ldg(ws + kHfOffB1 + u);
+#pragma unroll
+    for (int q = 0; q < kHfG1; ++q) v += sP1[(q * kHfU + u) * kHfS + s];
+    sH[s * kHfHStride + u] = fmaxf(v, 0.0f);
+  }
+  // ---- ... and KAN layer-0 outputs (bias, ReLU), expanded straight into the layer-1 activations
+  {
+    const int s = tid & (kHfS - 1), o = tid >> 3;
+    float v = __ldg(ws + kHfOffKb0 + o);
+#pragma unroll
+    for (int g = 0; g < kHfG0; ++g) v += sP0[(g * kHfO0 + o) * kHfS + s];
     float a[kKW], da[kKW], dt;
-    kan_expand<false>(sK1[i * kHfS + s], kn, a, da, dt);
+    kan_expand<false>(fmaxf(v, 0.0f), kn, a, da, dt);
 #pragma unroll
-    for (int k = 0; k < kKW; ++k) sA[(i * 8 + k) * kHfS + s] = a[k];
+    for (int k = 0; k < kKW; ++k) sA[o * kHfAStride + k * kHfS + s] = a[k];
   }
   __syncthreads();
+  // ---- KAN layer 1 (64 -> 16): thread = (output o, sample s, quarter q of the 512 expanded inputs)
   {
-    const int o = tid & 15, s = tid >> 4;
+    const int o = tid & (kHfO1 - 1), s = (tid >> 4) & (kHfS - 1), q = tid >> 7;
     float acc = 0.0f;
-    const float* w = ws + kHfOffWp1 + o;
-#pragma unroll 8
-    for (int kk = 0; kk < kHfO0 * 8; ++kk) acc = fmaf(sA[kk * kHfS + s], w[kk * kHfO1], acc);
-    sK2[o * kHfS + s] = fmaxf(acc + ws[kHfOffKb1 + o], 0.0f);
+#pragma unroll 4
+    for (int i = q * 16; i < q * 16 + 16; ++i)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc = fmaf(sA[i * kHfAStride + k * kHfS + s], sWp1[(i * 8 + k) * kHfO1 + o], acc);
+    sP0[q * 128 + s * kHfO1 + o] = acc;       // sP0 was consumed before the previous barrier
   }
   __syncthreads();
-  // ---- KAN layer 2 (16 -> 1) and 3*sigmoid: one thread per sample
-  if (tid < kHfS) {
-    const int s = tid;
-    float acc = 0.0f;
-    for (int i = 0; i < kHfO1; ++i) {
-      float a[kKW], da[kKW], dt;
-      kan_expand<false>(sK2[i * kHfS + s], kn, a, da, dt);
+  if (warp < 4) {
+    // ---- KAN layer-1 epilogue, layer 2 (16 -> 1) and 3*sigmoid: thread = (sample s, layer-2 input i), 16-lane reduction
+    const int i = tid & (kHfO1 - 1), s = tid >> 4;
+    float v = sKb1[i];
 #pragma unroll
-      for (int k = 0; k < kKW; ++k) acc = fmaf(a[k], ws[kHfOffWp2 + i * 8 + k], acc);
+    for (int q = 0; q < kHfG1; ++q) v += sP0[q * 128 + s * kHfO1 + i];
+    float a[kKW], da[kKW], dt;
+    kan_expand<false>(fmaxf(v, 0.0f), kn, a, da, dt);
+    float acc = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kKW; ++k) acc = fmaf(a[k], sWp2[i * 8 + k], acc);
+#pragma unroll
+    for (int d = 8; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+    if (i == 0 && s0 + s < batch) kan[s0 + s] = 3.0f / (1.0f + expf(-(acc + sKb2[0])));
+  } else if (warp < 13) {
+    // ---- second layers of the heads: warp = one of the 9 outputs, lanes split the 128 hidden units
+    const int o = warp - 4;
+    const int head = (o < 4) ? 0 : (o < 7) ? 1 : 2;
+    const float4 wv = *reinterpret_cast<const float4*>(sW2 + o * kHfH + lane * 4);
+    const float bias = sW2[9 * kHfH + o];
+#pragma unroll
+    for (int s = 0; s < kHfS; ++s) {
+      const float4 hv = *reinterpret_cast<const float4*>(sH + s * kHfHStride + head * kHfH + lane * 4);
+      float acc = fmaf(hv.x, wv.x, fmaf(hv.y, wv.y, fmaf(hv.z, wv.z, hv.w * wv.w)));
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, d);
+      acc += bias;
+      const int sg = s0 + s;
+      if (lane == 0 && sg < batch) {
+        if (o < 4) cls[static_cast<size_t>(sg) * 4 + o] = acc;
+        else if (o < 7) ord[static_cast<size_t>(sg) * 3 + (o - 4)] = acc;
+        else if (o == 7) mu[sg] = acc;
+        else log_var[sg] = fminf(fmaxf(acc, -10.0f), 10.0f);
+      }
     }
-    acc += ws[kHfOffKb2];
-    if (s0 + s < batch) kan[s0 + s] = 3.0f / (1.0f + expf(-acc));
   }
 }
