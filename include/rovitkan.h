@@ -143,6 +143,14 @@ int rvk_gemm_nt(int mode, const void* a_bf16, int64_t lda, const void* b_bf16, i
 int rvk_mlp_fused(const float* x_in_tiled, float* x_out_tiled, const float* gamma2, const float* beta2,
                   const void* w1_bf16, const float* b1, const void* w2_f16, const float* b2, const float* gamma,
                   const float* beta, float eps, void* ln_out_bf16, int m, int cta_group, void* stream);
+/* The same kernel with the attention output projection folded in (timm Block.forward first half: x + proj(attn),
+ * Attention.proj): before the MLP half it computes  x_in += ctx . wproj^T + bproj  on the tensor cores (accumulator in
+ * the TMEM columns that are idle between two row tiles), so the projected residual stream never makes its own round
+ * trip through memory.  ctx bf16 [m,192] (rvk_attention_forward output), wproj bf16 [192,192], bproj fp32 [192]. */
+int rvk_attn_proj_mlp_fused(const float* x_in_tiled, float* x_out_tiled, const void* ctx_bf16, const void* wproj_bf16,
+                            const float* bproj, const float* gamma2, const float* beta2, const void* w1_bf16, const float* b1,
+                            const void* w2_f16, const float* b2, const float* gamma, const float* beta, float eps,
+                            void* ln_out_bf16, int m, int cta_group, void* stream);
 /* Debugging aid: device buffer of 4*512 int64 into which the following rvk_mlp_fused launches log clock64 events
  * of CTA 0 (NULL switches it off, the default). */
 void rvk_debug_set_mlp_trace(void* device_buf);

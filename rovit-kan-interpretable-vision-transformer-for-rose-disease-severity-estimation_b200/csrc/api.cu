@@ -223,18 +223,36 @@ int rvk_gemm_nt(int mode, const void* a_bf16, int64_t lda, const void* b_bf16, i
   a.p.has_res = (aux != nullptr || res_table != nullptr) ? 1 : 0;
   return rvk_gemm_nt_launch(a, S(stream));
 }
-int rvk_mlp_fused(const float* x_in_tiled, float* x_out_tiled, const float* gamma2, const float* beta2,
-                  const void* w1_bf16, const float* b1, const void* w2_f16, const float* b2, const float* gamma,
-                  const float* beta, float eps, void* ln_out_bf16, int m, int cta_group, void* stream) {
+static int mlp_fused_common(const float* x_in_tiled, float* x_out_tiled, const void* ctx_bf16, const void* wproj_bf16,
+                            const float* bproj, const float* gamma2, const float* beta2, const void* w1_bf16, const float* b1,
+                            const void* w2_f16, const float* b2, const float* gamma, const float* beta, float eps,
+                            void* ln_out_bf16, int m, int cta_group, void* stream) {
   if (m < 0) return RVK_ERR_BAD_ARG;
   MlpFusedArgs a;
   a.w1 = w1_bf16; a.w2_f16 = w2_f16; a.ln_out = ln_out_bf16;
+  a.ctx = ctx_bf16; a.wproj = wproj_bf16;
   a.cta_group = cta_group;
   a.p.M = m; a.p.x_in = x_in_tiled; a.p.x_out = x_out_tiled; a.p.gamma2 = gamma2; a.p.beta2 = beta2;
   a.p.b1 = b1; a.p.b2 = b2; a.p.gamma = gamma; a.p.beta = beta; a.p.eps = eps;
+  a.p.bp = bproj;
+  a.p.has_proj = ctx_bf16 != nullptr ? 1 : 0;
   a.p.has_ln = ln_out_bf16 != nullptr ? 1 : 0;
   a.p.trace = g_mlp_trace;
   return rvk_mlp_fused_launch(a, S(stream));
+}
+int rvk_mlp_fused(const float* x_in_tiled, float* x_out_tiled, const float* gamma2, const float* beta2,
+                  const void* w1_bf16, const float* b1, const void* w2_f16, const float* b2, const float* gamma,
+                  const float* beta, float eps, void* ln_out_bf16, int m, int cta_group, void* stream) {
+  return mlp_fused_common(x_in_tiled, x_out_tiled, nullptr, nullptr, nullptr, gamma2, beta2, w1_bf16, b1, w2_f16, b2, gamma,
+                          beta, eps, ln_out_bf16, m, cta_group, stream);
+}
+int rvk_attn_proj_mlp_fused(const float* x_in_tiled, float* x_out_tiled, const void* ctx_bf16, const void* wproj_bf16,
+                            const float* bproj, const float* gamma2, const float* beta2, const void* w1_bf16, const float* b1,
+                            const void* w2_f16, const float* b2, const float* gamma, const float* beta, float eps,
+                            void* ln_out_bf16, int m, int cta_group, void* stream) {
+  if (m > 0 && (ctx_bf16 == nullptr || wproj_bf16 == nullptr || bproj == nullptr)) return RVK_ERR_BAD_ARG;
+  return mlp_fused_common(x_in_tiled, x_out_tiled, ctx_bf16, wproj_bf16, bproj, gamma2, beta2, w1_bf16, b1, w2_f16, b2, gamma,
+                          beta, eps, ln_out_bf16, m, cta_group, stream);
 }
 /* debugging aid (not part of the product path): device buffer of 4*512 int64 that the next rvk_mlp_fused launches log clock events into */
 void rvk_debug_set_mlp_trace(void* buf) { g_mlp_trace = static_cast<long long*>(buf); }

@@ -169,6 +169,13 @@ bool fused_inference() {
   }();
   return on;
 }
+bool fuse_proj() {        // RVK_FUSE_PROJ=0: keep the attention output projection as its own GEMM launch (A/B measurements)
+  static const bool on = [] {
+    const char* e = getenv("RVK_FUSE_PROJ");
+    return !(e != nullptr && e[0] == '0');
+  }();
+  return on;
+}
 int mlp_cta_group() {
   static const int g = [] {
     const char* e = getenv("RVK_MLP_CTA_GROUP");
@@ -244,9 +251,11 @@ int rvk_encoder_forward_impl(const void* const* params, const void* wbuf, const 
         const BlockSaved& B = A.blk[i];
         RVK_TRY(gemm_plain(ln, kD, at(wbuf, W.qkv[i]), kD, b16(B.qkv, kQkv), kQkv, M, kQkv, kD, P(params, bp(i, B_QKVB)), s));
         RVK_TRY(rvk_attention_fwd_launch(b16(B.qkv, kQkv), b16(B.ctx, kD), nullptr, nb, s));
-        // x += proj(ctx); LayerNorm2 is applied on load by the MLP kernel, so no normalised copy is written
-        RVK_TRY(gemm_res_ln(b16(B.ctx, kD), kD, kD, at(wbuf, W.proj[i]), P(params, bp(i, B_PROJB)), x, nullptr, x, nullptr,
-                            nullptr, nullptr, nullptr, nullptr, M, s, true));
+        // x += proj(ctx): folded into the MLP kernel (default) or as its own GEMM; LayerNorm2 is applied on load by the
+        // MLP kernel, so no normalised copy is written
+        if (!fuse_proj())
+          RVK_TRY(gemm_res_ln(b16(B.ctx, kD), kD, kD, at(wbuf, W.proj[i]), P(params, bp(i, B_PROJB)), x, nullptr, x, nullptr,
+                              nullptr, nullptr, nullptr, nullptr, M, s, true));
         const bool last = (i == kDepth - 1);
         MlpFusedArgs m;
         m.w1 = at(wbuf, W.fc1[i]); m.w2_f16 = at(wbuf, W.fc2h[i]);
@@ -258,6 +267,10 @@ int rvk_encoder_forward_impl(const void* const* params, const void* wbuf, const 
         m.p.gamma = last ? nullptr : P(params, bp(i + 1, B_N1W));
         m.p.beta = last ? nullptr : P(params, bp(i + 1, B_N1B));
         m.p.eps = kLnEps; m.p.has_ln = last ? 0 : 1; m.p.trace = nullptr;
+        if (fuse_proj()) {
+          m.ctx = b16(B.ctx, kD); m.wproj = at(wbuf, W.proj[i]);
+          m.p.bp = P(params, bp(i, B_PROJB)); m.p.has_proj = 1;
+        }
         RVK_TRY(rvk_mlp_fused_launch(m, s));
       }
       RVK_TRY(rvk_layernorm_fwd_tiled_launch(x, kTok, P(params, P_NORM_W), P(params, P_NORM_B), kLnEps,

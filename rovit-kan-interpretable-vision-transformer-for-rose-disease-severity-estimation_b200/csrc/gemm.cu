@@ -145,11 +145,17 @@ static int launch_mlp_fused(const MlpFusedArgs& a, cudaStream_t stream) {
     configured = true;
   }
   const MlpFusedParams& p = a.p;
-  CUtensorMap tmW1, tmW2, tmLn;
+  CUtensorMap tmW1, tmW2, tmLn, tmCtx, tmWp;
   RVK_TRY(rvk_make_tmap_2d(&tmW1, a.w1, RVK_BF16, 768, 192, 192, 128 / G, 64));
   RVK_TRY(rvk_make_tmap_2d(&tmW2, a.w2_f16, RVK_BF16 /* 2-byte elements */, 192, 768, 768, 192 / G, 64));
   tmLn = tmW1;
   if (p.has_ln) RVK_TRY(rvk_make_tmap_2d(&tmLn, a.ln_out, RVK_BF16, p.M, 192, 192, 32, 64));
+  tmCtx = tmW1;
+  tmWp = tmW1;
+  if (p.has_proj) {
+    RVK_TRY(rvk_make_tmap_2d(&tmCtx, a.ctx, RVK_BF16, p.M, 192, 192, 128, 64));
+    RVK_TRY(rvk_make_tmap_2d(&tmWp, a.wproj, RVK_BF16, 192, 192, 192, 192 / G, 64));
+  }
   const int tiles = (p.M + 127) / 128;
   const int units = (tiles + G - 1) / G;
   const int max_clusters = kNumSMsB200 / G;
@@ -166,8 +172,8 @@ static int launch_mlp_fused(const MlpFusedArgs& a, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  ScopedTimer timer(stream, 2.0 * p.M * 192.0 * 768.0 * 2.0);
-  RVK_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, tmW1, tmW2, tmLn, p));
+  ScopedTimer timer(stream, 2.0 * p.M * 192.0 * (768.0 * 2.0 + (p.has_proj ? 192.0 : 0.0)));
+  RVK_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, tmW1, tmW2, tmLn, tmCtx, tmWp, p));
   return rvk_launch_check();
 }
 
@@ -178,6 +184,7 @@ int rvk_mlp_fused_launch(const MlpFusedArgs& a, cudaStream_t stream) {
       p.b2 == nullptr || p.gamma2 == nullptr || p.beta2 == nullptr)
     return RVK_ERR_BAD_ARG;
   if (p.has_ln && (a.ln_out == nullptr || p.gamma == nullptr || p.beta == nullptr)) return RVK_ERR_BAD_ARG;
+  if (p.has_proj && (a.ctx == nullptr || a.wproj == nullptr || p.bp == nullptr)) return RVK_ERR_BAD_ARG;
   if (a.cta_group == 1) return launch_mlp_fused<1>(a, stream);
   if (a.cta_group == 2) return launch_mlp_fused<2>(a, stream);
   return RVK_ERR_BAD_ARG;

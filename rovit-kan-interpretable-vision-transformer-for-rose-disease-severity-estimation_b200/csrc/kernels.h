@@ -36,6 +36,8 @@ struct MlpFusedArgs {
   const void* w1 = nullptr;       // bf16 [768,192]
   const void* w2_f16 = nullptr;   // fp16 [192,768] (the hidden activation is kept in fp16)
   void* ln_out = nullptr;         // bf16 [M,192] (p.has_ln)
+  const void* ctx = nullptr;      // bf16 [M,192] attention output  (p.has_proj: x_in += ctx . wproj^T + p.bp first)
+  const void* wproj = nullptr;    // bf16 [192,192]
   int cta_group = 2;
   MlpFusedParams p{};
 };

@@ -46,6 +46,8 @@ struct MlpFusedParams {
   const float* b2;      // [192]
   const float* gamma;   // [192] next LayerNorm (has_ln)
   const float* beta;
+  const float* bp;      // [192] attention output-projection bias (has_proj)
+  int has_proj;         // the kernel also does  x += ctx . Wproj^T + bp  (timm Attention.proj + residual) on load
   float eps;
   int has_ln;           // also write ln_out = LayerNorm(x_out) (bf16 [M,192], through the tmLn tensor map)
   long long* trace;     // debugging: optional [4][512] clock64 event log of CTA 0 (nullptr = off)
@@ -63,7 +65,7 @@ struct MlpSmem {
   static constexpr int kWStages = (G == 2) ? 8 : 4;
   static constexpr int kW1Bytes = 16384 / G;
   static constexpr int kW2Bytes = 24576 / G;
-  static constexpr int kVecBytes = 768 * 2 + 5 * 192 * 4;   // b1 (fp16); b2, gamma2, beta2, gamma, beta (fp32)
+  static constexpr int kVecBytes = 768 * 2 + 6 * 192 * 4;   // b1 (fp16); b2, gamma2, beta2, gamma, beta, bp (fp32)
   static constexpr int kPartBytes = 2 * kMlpTeams * 128 * 8;   // LayerNorm partial (sum, sumsq): [on-load | final][team][row]
   static constexpr int kBarBytes = 512;
   static constexpr int kTotal = 1024 + kABytes + kHBytes + kWStages * kWStage + kVecBytes + kPartBytes + kBarBytes;
@@ -113,7 +115,8 @@ __device__ __forceinline__ __half2 gelu_erf_h2(__half2 x) {
 template <int G>
 __global__ void __launch_bounds__(kMlpThreads, 1)
 mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
-                 const __grid_constant__ CUtensorMap tmLn, const MlpFusedParams p) {
+                 const __grid_constant__ CUtensorMap tmLn, const __grid_constant__ CUtensorMap tmCtx,
+                 const __grid_constant__ CUtensorMap tmWp, const MlpFusedParams p) {
   using L = MlpSmem<G>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment by offset (keeps the shared address space visible to the compiler: LDS/STS, not generic LD/ST)
@@ -127,7 +130,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
   float* sBeta2 = sGamma2 + 192;
   float* sGamma = sBeta2 + 192;
   float* sBeta = sGamma + 192;
-  float2* sPartA = reinterpret_cast<float2*>(sBeta + 192);
+  float* sBp = sBeta + 192;
+  float2* sPartA = reinterpret_cast<float2*>(sBp + 192);
   float2* sPartF = sPartA + kMlpTeams * 128;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sPartF + kMlpTeams * 128);
   uint64_t* a_full = bars;            // leader: A operand of both CTAs written
@@ -137,7 +141,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
   uint64_t* h_empty = bars + 6;       // [2]
   uint64_t* d2_full = bars + 8;
   uint64_t* d2_empty = bars + 9;      // leader
-  uint64_t* w_full = bars + 10;       // [kWStages]
+  uint64_t* ctx_full = bars + 10;     // leader: ctx tiles of both CTAs landed in the A buffer (has_proj)
+  uint64_t* proj_full = bars + 11;    // projection accumulator complete (has_proj)
+  uint64_t* w_full = bars + 12;       // [kWStages]
   uint64_t* w_empty = w_full + L::kWStages;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_empty + L::kWStages);
 
@@ -161,12 +167,15 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
       sBeta2[i] = p.beta2[i];
       sGamma[i] = p.has_ln ? p.gamma[i] : 1.0f;
       sBeta[i] = p.has_ln ? p.beta[i] : 0.0f;
+      sBp[i] = p.has_proj ? p.bp[i] : 0.0f;
     }
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
     tma_prefetch_desc(&tmLn);
+    tma_prefetch_desc(&tmCtx);
+    tma_prefetch_desc(&tmWp);
     mbar_init(a_full, kMlpEpiWarps * G);
     mbar_init(a_empty, 1);
     for (int i = 0; i < L::kWStages; ++i) {
@@ -180,6 +189,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     }
     mbar_init(d2_full, 1);
     mbar_init(d2_empty, kMlpEpiWarps * G);
+    mbar_init(ctx_full, 1);
+    mbar_init(proj_full, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -199,7 +210,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
   };
 
   // Weight panels are consumed in this order (producer and issuer walk the same sequence):
-  //   W1(0) W1(1) | per tile:  c = 0..3: W1(c+2) W2(c);  c = 4: W2(4);  c = 5: W2(5) [then W1(0) W1(1) of the next tile]
+  //   [Wp] W1(0) W1(1) | per tile:  c = 0..3: W1(c+2) W2(c);  c = 4: W2(4);  c = 5: W2(5) [then [Wp] W1(0) W1(1) of the next tile]
   if (warp == 0) {
     // ================================================================= TMA producer (every CTA loads its own share)
     if (lane == 0 && n_my > 0) {
@@ -218,6 +229,19 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
       auto load_w2 = [&](int c) {        // W2 columns [c*128, c*128+128) of all 192 rows: this CTA stages 192/G rows
         for (int kp = 0; kp < 2; ++kp) load_panel(&tmW2, L::kW2Bytes, c * 128 + kp * 64, static_cast<int>(rank) * (192 / G));
       };
+      auto load_wp = [&]() {             // Wproj [192 out, 192 in]: three K panels, this CTA stages 192/G rows of each
+        for (int kp = 0; kp < 3; ++kp) load_panel(&tmWp, L::kW2Bytes, kp * 64, static_cast<int>(rank) * (192 / G));
+      };
+      auto load_ctx = [&](int it) {      // attention output rows of tile `it` into the (free) A buffer
+        mbar_wait(a_empty, (it & 1) ^ 1);
+        if (leader) mbar_arrive_expect_tx(ctx_full, G * L::kABytes);
+        const int m0 = tile_row0(it);
+        for (int kp = 0; kp < 3; ++kp) {
+          if (G == 2) tma_load_2d_pair(sA + kp * 16384, &tmCtx, mapa_u32(smem_u32(ctx_full), 0), kp * 64, m0);
+          else tma_load_2d(sA + kp * 16384, &tmCtx, ctx_full, kp * 64, m0);
+        }
+      };
+      if (p.has_proj) { load_ctx(0); load_wp(); }
       load_w1(0);
       load_w1(1);
       for (int it = 0; it < n_my; ++it) {
@@ -225,7 +249,11 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
           if (c <= 3) load_w1(c + 2);
           load_w2(c);
         }
-        if (it + 1 < n_my) { load_w1(0); load_w1(1); }
+        if (it + 1 < n_my) {
+          if (p.has_proj) { load_ctx(it + 1); load_wp(); }     // (the last fc1 of tile `it` was issued at c = 3)
+          load_w1(0);
+          load_w1(1);
+        }
       }
     }
   } else if (warp == 1) {
@@ -280,6 +308,16 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         commit(&h_empty[b]);
         if (c == 5) commit(d2_full);
       };
+      // attention output projection of tile `it` into the (idle) D1 columns [0,192): A = ctx tile in the A buffer
+      auto proj = [&](int it) {
+        constexpr uint32_t idescp = umma_idesc_bf16(128 * G, 192, 0, 0);
+        mbar_wait(ctx_full, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int kp = 0; kp < 3; ++kp) panel_mmas(tmem_base, a_lo0 + kp * (16384 >> 4), idescp, kp != 0);
+        commit(proj_full);
+      };
+      if (p.has_proj) proj(0);
       mbar_wait(a_full, 0);
       tc_fence_after();
       fc1(0);
@@ -300,6 +338,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
           if (lane == 0) trace(0, 3);
         }
         if (it + 1 < n_my) {
+          if (p.has_proj) proj(it + 1);          // D1 is idle: GELU(5) has drained it, fc1 of the next tile waits for a_full
           mbar_wait(a_full, (it + 1) & 1);
           tc_fence_after();
           fc1(0);
@@ -320,9 +359,9 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     const uint32_t af_l = (G == 2) ? mapa_u32(smem_u32(a_full), 0) : 0u;
 
     // this thread's 48 columns [48*team, 48*team+48) of token row `grow` = float4 slots f = 12*team + i of the tiled stream
-    auto load_row48 = [&](int grow, float (&x)[48]) {
+    auto load_row48_from = [&](const float* xbase, int grow, float (&x)[48]) {
       const bool valid = grow < p.M;
-      const float* src = p.x_in + xt_offset(valid ? grow : 0, 0, 0) + 12 * team * 128;
+      const float* src = xbase + xt_offset(valid ? grow : 0, 0, 0) + 12 * team * 128;
 #pragma unroll
       for (int i = 0; i < 12; ++i) {
         float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -330,6 +369,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         x[i * 4 + 0] = r.x; x[i * 4 + 1] = r.y; x[i * 4 + 2] = r.z; x[i * 4 + 3] = r.w;
       }
     };
+    auto load_row48 = [&](int grow, float (&x)[48]) { load_row48_from(p.x_in, grow, x); };
     auto prefetch_row48 = [&](int grow) {       // one 128-byte line per 8 lanes
       if (grow < p.M && (lane & 7) == 0) {
         const float* xp = p.x_in + xt_offset(grow, 0, 0) + 12 * team * 128;
@@ -367,15 +407,39 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
     // A operand of tile `it`: LayerNorm2 of the token rows, straight into shared memory
     auto produce_a = [&](int it) {
       float x[48];
-      load_row48(tile_row0(it) + row, x);
-      if (tr) trace(1, 30);
-      mbar_wait(a_empty, (it & 1) ^ 1);           // fc1 of the previous tile has read the buffer
-      if (tr) trace(1, 31);
+      const int grow = tile_row0(it) + row;
+      load_row48(grow, x);
+      if (p.has_proj) {
+        // x += ctx . Wproj^T + bp: the accumulator sits in the idle D1 columns; the new row goes back to the token stream
+        // (the final epilogue re-reads it as the MLP residual) and feeds LayerNorm2 below
+        mbar_wait(proj_full, it & 1);
+        tc_fence_after();
+        const uint32_t tP = tmem_base + team * 48 + lane_sel;
+        {
+          float v[32];
+          tmem_ld32(tP, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] += v[i] + sBp[team * 48 + i];
+        }
+        {
+          float v[16];
+          tmem_ld16(tP + 32, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[32 + i] += v[i] + sBp[team * 48 + 32 + i];
+        }
+        tc_fence_before();
+        if (grow < p.M) {
+          float* dstx = p.x_out + xt_offset(grow, 0, 0) + 12 * team * 128;
+#pragma unroll
+          for (int i = 0; i < 12; ++i)
+            *reinterpret_cast<float4*>(dstx + i * 128) = make_float4(x[i * 4], x[i * 4 + 1], x[i * 4 + 2], x[i * 4 + 3]);
+        }
+      } else {
+        mbar_wait(a_empty, (it & 1) ^ 1);         // fc1 of the previous tile has read the buffer
+      }
       float mean, rstd;
       row_stats(sPartA, x, mean, rstd);
-      if (tr) trace(1, 32);
       store_ln48(sA, x, mean, rstd, sGamma2, sBeta2);
-      if (tr) trace(1, 33);
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
@@ -389,7 +453,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
       const int grow = m0 + row;
       const bool valid = grow < p.M;
       float x[48];
-      load_row48(grow, x);                       // residual (L2 hit: the same rows fed produce_a)
+      load_row48_from(p.has_proj ? p.x_out : p.x_in, grow, x);     // residual (L2 hit: the rows produce_a read / wrote)
       if (tr) trace(1, 40);
       mbar_wait(d2_full, it & 1);
       tc_fence_after();

@@ -35,7 +35,7 @@ def gelu(x):
     return 0.5 * x * (1 + torch.erf(x / 2 ** 0.5))
 
 
-def run_case(M, G, has_ln, seed=0, inplace=False):
+def run_case(M, G, has_ln, seed=0, inplace=False, proj=False):
     g = torch.Generator().manual_seed(seed)
     w1 = (torch.randn(768, 192, generator=g) * 0.08).to(DEV).to(torch.bfloat16)
     w2 = (torch.randn(192, 768, generator=g) * 0.05).to(DEV).to(torch.float16)
@@ -49,16 +49,24 @@ def run_case(M, G, has_ln, seed=0, inplace=False):
     xt = to_tiled(x)
     xo = xt if inplace else torch.full_like(xt, float('nan'))
     ln_out = torch.full((M, 192), float('nan'), device=DEV, dtype=torch.bfloat16) if has_ln else None
-    _lib.call('rvk_mlp_fused', xt.data_ptr(), xo.data_ptr(), gamma2.data_ptr(), beta2.data_ptr(), w1.data_ptr(),
-              b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), gamma.data_ptr() if has_ln else 0,
-              beta.data_ptr() if has_ln else 0, 1e-6, ln_out.data_ptr() if has_ln else 0, M, G,
-              torch.cuda.current_stream().cuda_stream)
+    tail = (gamma2.data_ptr(), beta2.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(),
+            gamma.data_ptr() if has_ln else 0, beta.data_ptr() if has_ln else 0, 1e-6, ln_out.data_ptr() if has_ln else 0, M, G,
+            torch.cuda.current_stream().cuda_stream)
+    if proj:
+        # attention output projection folded in: x <- x + ctx . Wp^T + bp before the MLP half (fp32 accumulation of bf16 operands)
+        ctx = torch.randn(M, 192, generator=g).to(DEV).to(torch.bfloat16)
+        wp = (torch.randn(192, 192, generator=g) * 0.08).to(DEV).to(torch.bfloat16)
+        bp = torch.randn(192, generator=g).to(DEV)
+        _lib.call('rvk_attn_proj_mlp_fused', xt.data_ptr(), xo.data_ptr(), ctx.data_ptr(), wp.data_ptr(), bp.data_ptr(), *tail)
+        x = x + ctx.float() @ wp.float().t() + bp
+    else:
+        _lib.call('rvk_mlp_fused', xt.data_ptr(), xo.data_ptr(), *tail)
     torch.cuda.synchronize()
     a = torch.nn.functional.layer_norm(x, (192,), gamma2, beta2, 1e-6).to(torch.bfloat16).float()   # A operand is bf16
     h = gelu(a @ w1.float().t() + b1)      # kept in fp16 on chip (GELU itself evaluated in half2)
     ref = x + h @ w2.float().t() + b2
     got = from_tiled(xo, M)
-    assert_close(got, ref, rtol=2e-3, atol=2e-3, scale_tol=1e-3, what=f'mlp_fused x_out M={M} G={G}')
+    assert_close(got, ref, rtol=2e-3, atol=2e-3, scale_tol=1e-3, what=f'mlp_fused x_out M={M} G={G} proj={proj}')
     if has_ln:
         ref_ln = torch.nn.functional.layer_norm(ref, (192,), gamma, beta, 1e-6)
         assert_close(ln_out.float(), ref_ln, rtol=1e-2, atol=1e-2, what=f'mlp_fused ln_out M={M} G={G}')
@@ -79,3 +87,11 @@ def test_mlp_fused_cta_pair(M):
 def test_mlp_fused_no_layernorm_in_place(G):
     run_case(1000, G, False, seed=7, inplace=True)
     run_case(197 * 40, G, True, seed=8, inplace=True)
+
+
+@pytest.mark.parametrize('G', [1, 2])
+@pytest.mark.parametrize('M', [128, 300, 1000, 197 * 64, 197 * 300 + 5])
+def test_attn_proj_mlp_fused(M, G):
+    """rvk_attn_proj_mlp_fused: x + proj(ctx) computed in the idle TMEM columns, then the MLP half on the new rows."""
+    run_case(M, G, True, seed=M + 11, proj=True)
+    run_case(M, G, M % 2 == 0, seed=M + 12, inplace=True, proj=True)
