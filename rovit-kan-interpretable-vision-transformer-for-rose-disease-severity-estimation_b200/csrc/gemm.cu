@@ -154,7 +154,7 @@ static int launch_mlp_fused(const MlpFusedArgs& a, cudaStream_t stream) {
   tmWp = tmW1;
   if (p.has_proj) {
     RVK_TRY(rvk_make_tmap_2d(&tmCtx, a.ctx, RVK_BF16, p.M, 192, 192, 128, 64));
-    RVK_TRY(rvk_make_tmap_2d(&tmWp, a.wproj, RVK_BF16, 192, 192, 192, 192 / G, 64));
+    RVK_TRY(rvk_make_tmap_2d(&tmWp, a.wproj, RVK_BF16, 192, 192, 192, 32, 64));
   }
   const int tiles = (p.M + 127) / 128;
   const int units = (tiles + G - 1) / G;

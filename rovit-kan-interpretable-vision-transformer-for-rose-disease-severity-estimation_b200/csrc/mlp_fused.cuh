@@ -210,7 +210,7 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
   };
 
   // Weight panels are consumed in this order (producer and issuer walk the same sequence):
-  //   [Wp] W1(0) W1(1) | per tile:  c = 0..3: W1(c+2) W2(c);  c = 4: W2(4);  c = 5: W2(5) [then [Wp] W1(0) W1(1) of the next tile]
+  //   [Wp] W1(0) W1(1) | per tile:  c = 0..3: W1(c+2) W2(c);  c = 4: W2(4) [Wp of the next tile];  c = 5: W2(5) [then W1(0) W1(1) of the next tile]
   if (warp == 0) {
     // ================================================================= TMA producer (every CTA loads its own share)
     if (lane == 0 && n_my > 0) {
@@ -229,8 +229,21 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
       auto load_w2 = [&](int c) {        // W2 columns [c*128, c*128+128) of all 192 rows: this CTA stages 192/G rows
         for (int kp = 0; kp < 2; ++kp) load_panel(&tmW2, L::kW2Bytes, c * 128 + kp * 64, static_cast<int>(rank) * (192 / G));
       };
-      auto load_wp = [&]() {             // Wproj [192 out, 192 in]: three K panels, this CTA stages 192/G rows of each
-        for (int kp = 0; kp < 3; ++kp) load_panel(&tmWp, L::kW2Bytes, kp * 64, static_cast<int>(rank) * (192 / G));
+      // Wproj [192 out, 192 in], three K panels.  The projection runs as TWO accumulators (see the issuer): outputs 0..127
+      // and 128..191, so a stage holds [this CTA's 128/G rows of the first | its 64/G rows of the second], in 32-row boxes
+      auto load_wp = [&]() {
+        constexpr int nA = 128 / G / 32, nB = 64 / G / 32;
+        for (int kp = 0; kp < 3; ++kp) {
+          mbar_wait(&w_empty[ws], wph ^ 1);
+          if (leader) mbar_arrive_expect_tx(&w_full[ws], G * L::kW2Bytes);
+          uint8_t* dst = sW + ws * L::kWStage;
+          for (int j = 0; j < nA + nB; ++j) {
+            const int r0 = (j < nA) ? static_cast<int>(rank) * (128 / G) + j * 32 : 128 + static_cast<int>(rank) * (64 / G) + (j - nA) * 32;
+            if (G == 2) tma_load_2d_pair(dst + j * 4096, &tmWp, mapa_u32(smem_u32(&w_full[ws]), 0), kp * 64, r0);
+            else tma_load_2d(dst + j * 4096, &tmWp, &w_full[ws], kp * 64, r0);
+          }
+          if (++ws == L::kWStages) { ws = 0; wph ^= 1; }
+        }
       };
       auto load_ctx = [&](int it) {      // attention output rows of tile `it` into the (free) A buffer
         mbar_wait(a_empty, (it & 1) ^ 1);
@@ -248,9 +261,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         for (int c = 0; c < 6; ++c) {
           if (c <= 3) load_w1(c + 2);
           load_w2(c);
+          // the A buffer is free once the tile's last fc1 (issued at c = 3) has completed
+          if (c == 4 && p.has_proj && it + 1 < n_my) { load_ctx(it + 1); load_wp(); }
         }
         if (it + 1 < n_my) {
-          if (p.has_proj) { load_ctx(it + 1); load_wp(); }     // (the last fc1 of tile `it` was issued at c = 3)
           load_w1(0);
           load_w1(1);
         }
@@ -308,13 +322,32 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         commit(&h_empty[b]);
         if (c == 5) commit(d2_full);
       };
-      // attention output projection of tile `it` into the (idle) D1 columns [0,192): A = ctx tile in the A buffer
+      // attention output projection of tile `it`, A = ctx tile in the A buffer, as two accumulators so that it can be
+      // issued BEFORE the tile boundary: outputs 0..127 -> D1[0] (idle once GELU of chunk 4 has drained it), outputs
+      // 128..191 -> the 64 TMEM columns 448..511 nobody else uses.  By the time the epilogue warps have finished GELU(5)
+      // the projection is complete, so the next tile's LayerNorm-on-load never waits for the tensor pipe.
       auto proj = [&](int it) {
-        constexpr uint32_t idescp = umma_idesc_bf16(128 * G, 192, 0, 0);
+        constexpr uint32_t idescA = umma_idesc_bf16(128 * G, 128, 0, 0);
+        constexpr uint32_t idescB = umma_idesc_bf16(128 * G, 64, 0, 0);
         mbar_wait(ctx_full, it & 1);
         tc_fence_after();
 #pragma unroll
-        for (int kp = 0; kp < 3; ++kp) panel_mmas(tmem_base, a_lo0 + kp * (16384 >> 4), idescp, kp != 0);
+        for (int kp = 0; kp < 3; ++kp) {
+          mbar_wait(&w_full[ws], wph);
+          tc_fence_after();
+          const uint32_t a_lo = a_lo0 + kp * (16384 >> 4);
+          const uint32_t b_lo = w_lo0 + ws * (L::kWStage >> 4);
+          if (issuer) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16_split<G>(tmem_base, a_lo + 2 * k, b_lo + 2 * k, idescA, (kp | k) != 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_f16_split<G>(tmem_base + 448, a_lo + 2 * k, b_lo + ((128 / G) * 128 >> 4) + 2 * k, idescB, (kp | k) != 0 ? 1u : 0u);
+          }
+          __syncwarp();
+          commit(&w_empty[ws]);
+          if (++ws == L::kWStages) { ws = 0; wph ^= 1; }
+        }
         commit(proj_full);
       };
       if (p.has_proj) proj(0);
@@ -335,10 +368,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
             tc_fence_after();
           }
           fc2(c);
+          if (c == 4 && p.has_proj && it + 1 < n_my) proj(it + 1);
           if (lane == 0) trace(0, 3);
         }
         if (it + 1 < n_my) {
-          if (p.has_proj) proj(it + 1);          // D1 is idle: GELU(5) has drained it, fc1 of the next tile waits for a_full
           mbar_wait(a_full, (it + 1) & 1);
           tc_fence_after();
           fc1(0);
@@ -414,16 +447,18 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         // (the final epilogue re-reads it as the MLP residual) and feeds LayerNorm2 below
         mbar_wait(proj_full, it & 1);
         tc_fence_after();
-        const uint32_t tP = tmem_base + team * 48 + lane_sel;
+        // columns [48*team, 48*team+48) of the projection: outputs 0..127 sit in TMEM columns 0..127, outputs 128..191 in 448..511
+        const uint32_t tP0 = tmem_base + lane_sel + (team < 3 ? team * 48 : 448 + 16);
+        const uint32_t tP1 = tmem_base + lane_sel + (team < 2 ? team * 48 + 32 : team == 2 ? 448 : 448 + 48);
         {
           float v[32];
-          tmem_ld32(tP, v);
+          tmem_ld32(tP0, v);
 #pragma unroll
           for (int i = 0; i < 32; ++i) x[i] += v[i] + sBp[team * 48 + i];
         }
         {
           float v[16];
-          tmem_ld16(tP + 32, v);
+          tmem_ld16(tP1, v);
 #pragma unroll
           for (int i = 0; i < 16; ++i) x[32 + i] += v[i] + sBp[team * 48 + 32 + i];
         }
@@ -520,7 +555,6 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
         const uint32_t n = static_cast<uint32_t>(q >> 1);
         if (tr) trace(1, 10);
         mbar_wait(&d1_full[b], n & 1);
-        mbar_wait(&h_empty[b], (n & 1) ^ 1);
         tc_fence_after();
         if (tr) trace(1, 12);
         {
@@ -528,20 +562,25 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
           tmem_ld32(tmem_base + b * 128 + team * 32 + lane_sel, v);
           const uint4* bb = reinterpret_cast<const uint4*>(sB1 + c * 128 + team * 32);
           uint8_t* panel = sH + b * 32768 + (team >> 1) * 16384;
+          uint32_t o[16];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const uint4 bq = bb[j];                              // 8 fp16 biases
             const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
-            uint32_t o[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               __half2 hx = __floats2half2_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
               hx = __hadd2(hx, *reinterpret_cast<const __half2*>(&bw[e]));
               const __half2 g = gelu_erf_h2(hx);
-              o[e] = *reinterpret_cast<const uint32_t*>(&g);
+              o[j * 4 + e] = *reinterpret_cast<const uint32_t*>(&g);
             }
-            *reinterpret_cast<uint4*>(panel + sw128_offset(row, (team & 1) * 4 + j)) = make_uint4(o[0], o[1], o[2], o[3]);
           }
+          // the hidden-chunk buffer is only needed now: fc2 of chunk c-2 (its last reader) had the whole GELU to finish
+          mbar_wait(&h_empty[b], (n & 1) ^ 1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(panel + sw128_offset(row, (team & 1) * 4 + j)) =
+                make_uint4(o[j * 4], o[j * 4 + 1], o[j * 4 + 2], o[j * 4 + 3]);
         }
         tc_fence_before();
         fence_proxy_async_smem();
