@@ -442,11 +442,13 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
       float x[48];
       const int grow = tile_row0(it) + row;
       load_row48(grow, x);
+      if (tr) trace(1, 30);
       if (p.has_proj) {
         // x += ctx . Wproj^T + bp: the accumulator sits in the idle D1 columns; the new row goes back to the token stream
         // (the final epilogue re-reads it as the MLP residual) and feeds LayerNorm2 below
         mbar_wait(proj_full, it & 1);
         tc_fence_after();
+        if (tr) trace(1, 31);
         // columns [48*team, 48*team+48) of the projection: outputs 0..127 sit in TMEM columns 0..127, outputs 128..191 in 448..511
         const uint32_t tP0 = tmem_base + lane_sel + (team < 3 ? team * 48 : 448 + 16);
         const uint32_t tP1 = tmem_base + lane_sel + (team < 2 ? team * 48 + 32 : team == 2 ? 448 : 448 + 48);
@@ -472,8 +474,10 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
       } else {
         mbar_wait(a_empty, (it & 1) ^ 1);         // fc1 of the previous tile has read the buffer
       }
+      if (tr) trace(1, 32);
       float mean, rstd;
       row_stats(sPartA, x, mean, rstd);
+      if (tr) trace(1, 33);
       store_ln48(sA, x, mean, rstd, sGamma2, sBeta2);
       fence_proxy_async_smem();
       __syncwarp();
