@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the RoViT-KAN hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode infer|train] [--batch B] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode infer|train|kan|sweep] [--batch B] [--impl ours|reference]
 
 Default = BASELINE.json configs[1]: RoViT-KAN inference, batch 1024 per GPU, bf16 tensor-core trunk, all four
 heads (KAN severity enabled), random-init weights, synthetic 224x224 images.  A "step" is one forward pass
@@ -14,8 +14,10 @@ stream, max over ranks.  The 1024-image input (616 MB fp32) and every inter-kern
 126 MB L2, so no L2 flush is needed between iterations ("l2": "inputs larger than L2").
 
 One JSON line is printed by rank 0; see the task contract for the keys.  `roofline` describes the dominant
-kernel (the tcgen05 GEMM family: 49 launches per forward); its per-launch device time is measured
-in-situ with CUDA events by librovitkan (rvk_gemm_timing_*) in K extra steps after the timed region.
+kernel (inference: mlp_fused_kernel, one launch per block, ~50 % of the step; training: the tcgen05 GEMM family); its
+per-launch device time is measured in-situ with CUDA events on the launch stream by librovitkan (rvk_gemm_timing_*)
+in K extra steps after the timed region; `traffic` (DRAM bytes per launch) comes from the committed ncu --set full
+capture of the same kernel (profiles/roofline_traffic.json).
 `cpu_baseline` / `--impl reference` time the reference's CPU algorithm (oracle port incl. the reference's
 per-(input,output) Python loop in the KAN, models/kan.py:85-89) on the host cores, batch 32 per step.
 """
@@ -281,6 +283,30 @@ def run_ours(args, rank, local_rank, world):
     pk = peaks()
     gemm_tflops = (t_fl.value / (t_ms.value * 1e-3) / 1e12) if t_ms.value > 0 else 0.0
     flop_img = TRAIN_FLOP_PER_IMG if train else FWD_FLOP_PER_IMG
+    # dominant kernel: the fused (proj +) MLP kernel in inference (~50 % of the step), the dgrad/wgrad GEMM family in training
+    kinds = {}
+    for kind, name in ((0, 'gemm_nt_kernel'), (1, 'gemm_tn_kernel'), (2, 'mlp_fused_kernel')):
+        k_ms, k_fl = ctypes.c_double(0), ctypes.c_double(0)
+        n = lib.rvk_gemm_timing_kind(kind, ctypes.byref(k_ms), ctypes.byref(k_fl))
+        if n > 0 and k_ms.value > 0:
+            kinds[name] = {'launches': int(n), 'us_per_launch': k_ms.value * 1e3 / n, 'gflop_per_launch': k_fl.value / n / 1e9,
+                           'tflops': k_fl.value / (k_ms.value * 1e-3) / 1e12, 'ms_per_step': k_ms.value / K}
+    if not train and 'mlp_fused_kernel' in kinds:
+        dom = kinds['mlp_fused_kernel']
+        dom_name = ('mlp_fused_kernel<2> (attention out-projection + LayerNorm2 + fc1 + GELU + fc2 + residual + LayerNorm1, '
+                    'one launch per block; algorithmic FLOPs 2*M*192*(192 + 2*768) per launch, M = batch*197)')
+        dom_tflops = dom['tflops']
+    else:
+        dom, dom_name, dom_tflops = None, 'gemm_nt_kernel / gemm_tn_kernel / mlp_fused_kernel (tcgen05, all launches)', gemm_tflops
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')) as f:
+            tj = json.load(f)
+        ent = tj.get('train' if train else 'infer')
+        if ent and ent.get('batch_per_gpu') == batch:
+            traffic, traffic_src = ent['dram_bytes_per_launch'], ent['source']
+    except (OSError, ValueError, KeyError):
+        pass
     line = {
         'metric': 'images/sec (224^2, device-timed) RoViT-KAN ' + ('train step' if train else 'inference forward'),
         'value': value, 'unit': 'images/sec', 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_total / K,
@@ -295,10 +321,17 @@ def run_ours(args, rank, local_rank, world):
         'gpu_launches': int(launches),
         'clocks': clocks,
         'e2e_bf16_input': e2e_bf16,
-        'roofline': {'bound': 'tensor', 'achieved': gemm_tflops, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
-                     'frac': gemm_tflops / pk['tflops_sustained'], 'traffic': None,
-                     'kernel': 'gemm_nt_kernel / gemm_tn_kernel (tcgen05, all launches)', 'launches_timed': int(n_gemm),
-                     'gemm_ms_per_step': t_ms.value / K, 'peak_source': pk['source'] + ' sustained bf16',
+        'roofline': {'bound': 'tensor', 'achieved': dom_tflops, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
+                     'frac': dom_tflops / pk['tflops_sustained'], 'traffic': traffic, 'traffic_source': traffic_src,
+                     'kernel': dom_name,
+                     'us_per_launch': dom['us_per_launch'] if dom else None,
+                     'gflop_per_launch': dom['gflop_per_launch'] if dom else None,
+                     'share_of_step': (dom['ms_per_step'] / (ms_total / K)) if dom else None,
+                     'launches_timed': int(dom['launches'] if dom else n_gemm),
+                     'peak_source': pk['source'] + ' sustained bf16',
+                     'kernels': kinds,
+                     'all_tcgen05_gemms': {'tflops': gemm_tflops, 'frac': gemm_tflops / pk['tflops_sustained'],
+                                           'ms_per_step': t_ms.value / K, 'launches_timed': int(n_gemm)},
                      'whole_step_tflops': value / world * flop_img / 1e12,
                      'whole_step_frac': value / world * flop_img / 1e12 / pk['tflops_sustained']},
     }
@@ -382,13 +415,65 @@ def run_kan(args, rank, local_rank, world):
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------ throughput sweep
+def run_sweep(args, rank, local_rank, world):
+    """BASELINE.json configs[4]: forward throughput of DeiT-Tiny backbone + heads + KAN at batch 64..8192 per GPU, each
+    rank on its own shard (no collective), against the tensor roofline (2.507 GFLOP per image)."""
+    import torch
+    import torch.distributed as dist
+    from rovitkan_b200.models import RoViTKAN
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    torch.manual_seed(0)
+    model = RoViTKAN(pretrained=False).to(dev).eval()
+    K, W = args.steps, max(3, args.warmup)
+    pk = peaks()
+    rows = []
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > L2: small batches would otherwise stay L2-resident
+    for batch in (64, 128, 148, 256, 296, 512, 1024, 2048, 4096, 8192):
+        g = torch.Generator(device=dev).manual_seed(1000 + rank)
+        images = torch.randn(batch, 3, 224, 224, generator=g, device=dev)
+        with torch.no_grad():
+            for _ in range(W):
+                model(images)
+            tot = 0.0
+            for _ in range(K):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                e0.record()
+                model(images)
+                e1.record()
+                torch.cuda.synchronize()
+                tot += e0.elapsed_time(e1)
+        ms = torch.tensor([tot / K], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ips = batch * world / (float(ms) / 1e3)
+        rows.append({'batch_per_gpu': batch, 'ms_per_step': float(ms), 'images_per_sec': ips,
+                     'tensor_roofline_frac': ips / world * FWD_FLOP_PER_IMG / 1e12 / pk['tflops_sustained']})
+        del images
+    if rank == 0:
+        print(json.dumps({'metric': 'images/sec (224^2, device-timed) RoViT-KAN inference forward, batch sweep', 'unit': 'images/sec',
+                          'n_gpus': world, 'steps': K, 'warmup': W, 'higher_is_better': True, 'scaling': 'weak', 'dtype': 'bf16',
+                          'data': 'synthetic', 'config': {'workload': 'encoder-throughput sweep, batch 64-8192 per GPU', 'parallelism': f'dp{world}',
+                                                          'l2': 'L2 flushed (256 MB memset) before every timed step'},
+                          'peak_tflops': pk['tflops_sustained'], 'sweep': rows}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--mode', default='infer', choices=['infer', 'train', 'kan'])
+    ap.add_argument('--mode', default='infer', choices=['infer', 'train', 'kan', 'sweep'])
     ap.add_argument('--batch', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-steps', type=int, default=40, help='batch-32 reference forwards timed for cpu_baseline (~10-20 s)')
@@ -401,6 +486,8 @@ def main():
     elif args.mode == 'kan':
         if rank == 0:
             run_kan(args, rank, local_rank, world)
+    elif args.mode == 'sweep':
+        run_sweep(args, rank, local_rank, world)
     else:
         run_ours(args, rank, local_rank, world)
 

@@ -31,10 +31,12 @@ int rvk_device_check(void);                  /* 0 iff the current device is comp
  * rvk_launch_count: kernels this library has launched in this process so far.
  * rvk_gemm_timing_enable(1): bracket every tensor-core GEMM launch with CUDA events on its own stream;
  * rvk_gemm_timing_collect (after a stream sync) returns the launch count and sums their device time and
- * algorithmic FLOPs (2*M*N*K) since the previous collect. */
+ * algorithmic FLOPs (2*M*N*K) since the previous collect; rvk_gemm_timing_kind then gives the same three numbers
+ * of that collect for one kernel: kind 0 = gemm_nt_kernel, 1 = gemm_tn_kernel, 2 = mlp_fused_kernel. */
 int64_t rvk_launch_count(void);
 void rvk_gemm_timing_enable(int on);
 int rvk_gemm_timing_collect(double* total_ms_host, double* total_flops_host);
+int rvk_gemm_timing_kind(int kind, double* ms_host, double* flops_host);
 
 /* ---- KAN severity path ----------------------------------------------------------------------------
  * Replaces KANLayer.forward (models/kan.py:70-95) incl. BSplineBasis.compute_basis (:10-44), and the
@@ -169,7 +171,7 @@ int rvk_layernorm_forward(const float* x, int64_t x_row_stride, const float* gam
 int rvk_layernorm_backward(const void* g, int g_is_bf16, int64_t g_row_stride, const float* x, int64_t x_row_stride,
                            const float* mean, const float* rstd, const float* gamma, const float* dx_in,
                            float* dx_out, int64_t dx_row_stride, void* dx_out_bf16, float* dgamma, float* dbeta,
-                           int rows, void* stream);
+                           float* dcolsum, int rows, void* stream);
 int rvk_im2col(const float* images, void* patches_bf16, int batch, void* stream);
 int rvk_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
 

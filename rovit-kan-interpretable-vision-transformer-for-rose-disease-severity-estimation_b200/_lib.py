@@ -23,6 +23,7 @@ SIGNATURES = {
     'rvk_launch_count': (_L, []),
     'rvk_gemm_timing_enable': (None, [_I]),
     'rvk_gemm_timing_collect': (_I, [_P, _P]),
+    'rvk_gemm_timing_kind': (_I, [_I, _P, _P]),
     'rvk_kan_layer_workspace_floats': (_L, [_I, _I, _I]),
     'rvk_kan_basis': (_I, [_P, _P, _I, _L, _P, _P]),
     'rvk_kan_layer_forward': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
@@ -49,7 +50,7 @@ SIGNATURES = {
     'rvk_attention_forward': (_I, [_P, _P, _P, _I, _P]),
     'rvk_attention_backward': (_I, [_P, _P, _P, _P, _P, _I, _P]),
     'rvk_layernorm_forward': (_I, [_P, _L, _P, _P, _F, _P, _I, _L, _P, _P, _I, _P]),
-    'rvk_layernorm_backward': (_I, [_P, _I, _L, _P, _L, _P, _P, _P, _P, _P, _L, _P, _P, _P, _I, _P]),
+    'rvk_layernorm_backward': (_I, [_P, _I, _L, _P, _L, _P, _P, _P, _P, _P, _L, _P, _P, _P, _P, _I, _P]),
     'rvk_im2col': (_I, [_P, _P, _I, _P]),
     'rvk_cast_bf16': (_I, [_P, _P, _L, _P]),
 }

@@ -10,6 +10,7 @@ const char* rvk_last_error_cstr();
 long long rvk_launch_count_impl();
 void rvk_gemm_timing_enable_impl(int on);
 int rvk_gemm_timing_collect_impl(double* total_ms, double* total_flops);
+int rvk_gemm_timing_kind_impl(int kind, double* ms, double* flops);
 
 namespace {
 inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
@@ -59,6 +60,7 @@ int rvk_device_check(void) {
 
 int64_t rvk_launch_count(void) { return rvk_launch_count_impl(); }
 void rvk_gemm_timing_enable(int on) { rvk_gemm_timing_enable_impl(on); }
+int rvk_gemm_timing_kind(int kind, double* ms_host, double* flops_host) { return rvk_gemm_timing_kind_impl(kind, ms_host, flops_host); }
 int rvk_gemm_timing_collect(double* total_ms_host, double* total_flops_host) {
   return rvk_gemm_timing_collect_impl(total_ms_host, total_flops_host);
 }
@@ -280,14 +282,14 @@ int rvk_layernorm_forward(const float* x, int64_t x_row_stride, const float* gam
 }
 int rvk_layernorm_backward(const void* g, int g_is_bf16, int64_t g_row_stride, const float* x, int64_t x_row_stride,
                            const float* mean, const float* rstd, const float* gamma, const float* dx_in, float* dx_out,
-                           int64_t dx_row_stride, void* dx_out_bf16, float* dgamma, float* dbeta, int rows,
-                           void* stream) {
+                           int64_t dx_row_stride, void* dx_out_bf16, float* dgamma, float* dbeta, float* dcolsum,
+                           int rows, void* stream) {
   if (rows < 0 || (rows > 0 && (g == nullptr || x == nullptr || mean == nullptr || rstd == nullptr || gamma == nullptr ||
                                 dx_out == nullptr)))
     return RVK_ERR_BAD_ARG;
   if ((dgamma == nullptr) != (dbeta == nullptr)) return RVK_ERR_BAD_ARG;
   return rvk_layernorm_bwd_launch(g, g_is_bf16, g_row_stride, x, x_row_stride, mean, rstd, gamma, dx_in, dx_out,
-                                  dx_row_stride, dx_out_bf16, dgamma, dbeta, rows, S(stream));
+                                  dx_row_stride, dx_out_bf16, dgamma, dbeta, dcolsum, rows, S(stream));
 }
 int rvk_im2col(const float* images, void* patches_bf16, int batch, void* stream) {
   if (batch < 0 || (batch > 0 && (images == nullptr || patches_bf16 == nullptr))) return RVK_ERR_BAD_ARG;

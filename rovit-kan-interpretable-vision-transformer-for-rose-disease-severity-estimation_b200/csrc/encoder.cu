@@ -350,13 +350,14 @@ int rvk_encoder_backward_impl(const void* const* params, const void* wbuf, void*
     RVK_TRY(rvk_layernorm_bwd_launch(dfeatures + size_t(b0) * kD, 0, kD, f32(A.x_final, kD), int64_t(kTok) * kD,
                                      reinterpret_cast<float*>(at(workspace, A.mean_f)) + b0,
                                      reinterpret_cast<float*>(at(workspace, A.rstd_f)) + b0, P(params, P_NORM_W),
-                                     nullptr, dx, int64_t(kTok) * kD, dxb, G(grads, P_NORM_W), G(grads, P_NORM_B), nb, s));
+                                     nullptr, dx, int64_t(kTok) * kD, dxb, G(grads, P_NORM_W), G(grads, P_NORM_B),
+                                     G(grads, bp(kDepth - 1, B_FC2B)), nb, s));
 
     for (int i = kDepth - 1; i >= 0; --i) {
       const BlockSaved& B = A.blk[i];
       // ---- MLP: x_next = x_mid + fc2(gelu(fc1(ln2)))
       RVK_TRY(rvk_gemm_tn_launch(dxb, kD, b16(B.h, kMlp), kMlp, G(grads, bp(i, B_FC2W)), kMlp, M, kD, kMlp, 1.0f, s));
-      RVK_TRY(rvk_colsum_launch(dx, 0, kD, M, kD, G(grads, bp(i, B_FC2B)), 1.0f, s));
+      // (fc2 bias gradient = column sums of dx: accumulated by the LayerNorm backward that wrote dx)
       {   // dz = (dx * W2) o gelu'(z)
         GemmNtArgs a;
         a.mode = EPI_DGELU;
@@ -371,10 +372,9 @@ int rvk_encoder_backward_impl(const void* const* params, const void* wbuf, void*
       RVK_TRY(gemm_plain(dz, kMlp, at(wbuf, W.fc1T[i]), kMlp, g, kD, M, kD, kMlp, nullptr, s));
       RVK_TRY(rvk_layernorm_bwd_launch(g, 1, kD, f32(B.x_mid, kD), kD, stat(B.mean2), stat(B.rstd2),
                                        P(params, bp(i, B_N2W)), dx, dx, kD, dxb, G(grads, bp(i, B_N2W)),
-                                       G(grads, bp(i, B_N2B)), M, s));
+                                       G(grads, bp(i, B_N2B)), G(grads, bp(i, B_PROJB)), M, s));
       // ---- attention: x_mid = x_in + proj(attn(qkv(ln1)))
       RVK_TRY(rvk_gemm_tn_launch(dxb, kD, b16(B.ctx, kD), kD, G(grads, bp(i, B_PROJW)), kD, M, kD, kD, 1.0f, s));
-      RVK_TRY(rvk_colsum_launch(dx, 0, kD, M, kD, G(grads, bp(i, B_PROJB)), 1.0f, s));
       RVK_TRY(gemm_plain(dxb, kD, at(wbuf, W.projT[i]), kD, dctx, kD, M, kD, kD, nullptr, s));
       RVK_TRY(rvk_attention_bwd_launch(b16(B.qkv, kQkv), b16(B.ctx, kD), dctx,
                                        reinterpret_cast<float*>(at(workspace, B.lse)) + size_t(b0) * 3 * kTok, dqkv, nb, s));
@@ -383,7 +383,7 @@ int rvk_encoder_backward_impl(const void* const* params, const void* wbuf, void*
       RVK_TRY(gemm_plain(dqkv, kQkv, at(wbuf, W.qkvT[i]), kQkv, g, kD, M, kD, kQkv, nullptr, s));
       RVK_TRY(rvk_layernorm_bwd_launch(g, 1, kD, f32(B.x_in, kD), kD, stat(B.mean1), stat(B.rstd1),
                                        P(params, bp(i, B_N1W)), dx, dx, kD, dxb, G(grads, bp(i, B_N1W)),
-                                       G(grads, bp(i, B_N1B)), M, s));
+                                       G(grads, bp(i, B_N1B)), i > 0 ? G(grads, bp(i - 1, B_FC2B)) : nullptr, M, s));
     }
     // ---- patch embedding, class token, position embedding
     RVK_TRY(rvk_gemm_tn_launch(dxb, kD, b16(A.patches, kPatchK), kPatchK, G(grads, P_PATCH_W), kPatchK, M, kD, kPatchK,

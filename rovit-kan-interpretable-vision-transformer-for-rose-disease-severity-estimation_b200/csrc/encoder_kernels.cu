@@ -123,59 +123,109 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, long long xs, 
 }
 
 // ------------------------------------------------------------------ LayerNorm backward
-// dx = rstd * (g*gamma - mean(g*gamma) - xhat * mean(g*gamma*xhat)); dgamma += g*xhat; dbeta += g
+// dx = rstd * (g*gamma - mean(g*gamma) - xhat * mean(g*gamma*xhat)) (+ dx_in); dgamma += g*xhat; dbeta += g;
+// dcolsum += column sums of the dx written (the bias gradient of the Linear layer whose output gradient dx is: fc2 / proj
+// bias -- saves a separate pass over dx).
+// A streaming kernel: 16 lanes per row, 16-byte accesses (lane l owns columns 4l + 64j .. +3, j = 0..2), two rows per warp
+// per iteration, all loads of a row issued before the first reduction.
 template <bool G_BF16>
-__global__ void layernorm_bwd_kernel(const void* __restrict__ g, long long gs, const float* __restrict__ x,
-                                     long long xs, const float* __restrict__ mean, const float* __restrict__ rstd,
-                                     const float* __restrict__ gamma, const float* dx_in,
-                                     float* dx_out, long long dxs, __nv_bfloat16* __restrict__ dx_bf16,
-                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int rows) {
-  __shared__ float s_dg[kD], s_db[kD];
-  for (int i = threadIdx.x; i < kD; i += blockDim.x) { s_dg[i] = 0.0f; s_db[i] = 0.0f; }
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const void* __restrict__ g, long long gs, const float* __restrict__ x, long long xs,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
+                     const float* dx_in, float* dx_out, long long dxs, __nv_bfloat16* __restrict__ dx_bf16,
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcolsum, int rows) {
+  __shared__ float s_acc[3][kD];
+  for (int i = threadIdx.x; i < 3 * kD; i += blockDim.x) (&s_acc[0][0])[i] = 0.0f;
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  float gam[6], dg[6], db[6];
+  const int hl = threadIdx.x & 15;                                   // lane within the half-warp that shares a row
+  const int half = threadIdx.x >> 4;                                 // row slot within the block
+  const int slots = blockDim.x >> 4;
+  float4 gam[3];
+  float dg[12], db[12], ds[12];
 #pragma unroll
-  for (int i = 0; i < 6; ++i) { gam[i] = gamma[lane + 32 * i]; dg[i] = 0.0f; db[i] = 0.0f; }
-  for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_block) {
-    const float mu = mean[r], rs = rstd[r];
-    float gv[6], xh[6];
+  for (int j = 0; j < 3; ++j) gam[j] = *reinterpret_cast<const float4*>(gamma + 4 * hl + 64 * j);
+#pragma unroll
+  for (int i = 0; i < 12; ++i) { dg[i] = 0.0f; db[i] = 0.0f; ds[i] = 0.0f; }
+  const int n_iter = (rows + gridDim.x * slots - 1) / (gridDim.x * slots);      // uniform trip count: shuffles stay converged
+  for (int itn = 0; itn < n_iter; ++itn) {
+    const int r = (itn * gridDim.x + blockIdx.x) * slots + half;
+    const bool live = r < rows;
+    const size_t rr = live ? static_cast<size_t>(r) : 0;
+    float gv[12], xh[12], din[12];
+    const float mu = mean[rr], rs = rstd[rr];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const int c = 4 * hl + 64 * j;
+      if (G_BF16) {
+        const uint2 w = *reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(g) + rr * gs + c);
+        gv[4 * j + 0] = __uint_as_float(w.x << 16); gv[4 * j + 1] = __uint_as_float(w.x & 0xffff0000u);
+        gv[4 * j + 2] = __uint_as_float(w.y << 16); gv[4 * j + 3] = __uint_as_float(w.y & 0xffff0000u);
+      } else {
+        const float4 w = *reinterpret_cast<const float4*>(static_cast<const float*>(g) + rr * gs + c);
+        gv[4 * j + 0] = w.x; gv[4 * j + 1] = w.y; gv[4 * j + 2] = w.z; gv[4 * j + 3] = w.w;
+      }
+      const float4 xv = *reinterpret_cast<const float4*>(x + rr * xs + c);
+      xh[4 * j + 0] = xv.x; xh[4 * j + 1] = xv.y; xh[4 * j + 2] = xv.z; xh[4 * j + 3] = xv.w;
+      float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (dx_in != nullptr) dv = *reinterpret_cast<const float4*>(dx_in + rr * dxs + c);
+      din[4 * j + 0] = dv.x; din[4 * j + 1] = dv.y; din[4 * j + 2] = dv.z; din[4 * j + 3] = dv.w;
+    }
     float c1 = 0.0f, c2 = 0.0f;
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const int c = lane + 32 * i;
-      gv[i] = G_BF16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(g)[static_cast<size_t>(r) * gs + c])
-                     : static_cast<const float*>(g)[static_cast<size_t>(r) * gs + c];
-      xh[i] = (x[static_cast<size_t>(r) * xs + c] - mu) * rs;
-      const float gg = gv[i] * gam[i];
-      c1 += gg;
-      c2 = fmaf(gg, xh[i], c2);
-      dg[i] = fmaf(gv[i], xh[i], dg[i]);
-      db[i] += gv[i];
-    }
-    c1 = warp_sum(c1) * (1.0f / kD);
-    c2 = warp_sum(c2) * (1.0f / kD);
+    for (int j = 0; j < 3; ++j) {
+      const float gm[4] = {gam[j].x, gam[j].y, gam[j].z, gam[j].w};
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const int c = lane + 32 * i;
-      float d = rs * (gv[i] * gam[i] - c1 - xh[i] * c2);
-      if (dx_in != nullptr) d += dx_in[static_cast<size_t>(r) * dxs + c];
-      dx_out[static_cast<size_t>(r) * dxs + c] = d;
-      if (dx_bf16 != nullptr) dx_bf16[static_cast<size_t>(r) * dxs + c] = __float2bfloat16(d);
+      for (int e = 0; e < 4; ++e) {
+        const int i = 4 * j + e;
+        if (!live) gv[i] = 0.0f;
+        xh[i] = (xh[i] - mu) * rs;
+        const float gg = gv[i] * gm[e];
+        c1 += gg;
+        c2 = fmaf(gg, xh[i], c2);
+        dg[i] = fmaf(gv[i], xh[i], dg[i]);
+        db[i] += gv[i];
+      }
+    }
+#pragma unroll
+    for (int d = 8; d >= 1; d >>= 1) {
+      c1 += __shfl_xor_sync(0xffffffffu, c1, d);
+      c2 += __shfl_xor_sync(0xffffffffu, c2, d);
+    }
+    c1 *= (1.0f / kD);
+    c2 *= (1.0f / kD);
+    if (live) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        const int c = 4 * hl + 64 * j;
+        const float gm[4] = {gam[j].x, gam[j].y, gam[j].z, gam[j].w};
+        float d[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = 4 * j + e;
+          d[e] = rs * (gv[i] * gm[e] - c1 - xh[i] * c2) + din[i];
+          ds[i] += d[e];
+        }
+        *reinterpret_cast<float4*>(dx_out + rr * dxs + c) = make_float4(d[0], d[1], d[2], d[3]);
+        if (dx_bf16 != nullptr) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(d[0], d[1]), hi = __floats2bfloat162_rn(d[2], d[3]);
+          *reinterpret_cast<uint2*>(dx_bf16 + rr * dxs + c) =
+              make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        }
+      }
     }
   }
-  if (dgamma != nullptr) {
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      atomicAdd(&s_dg[lane + 32 * i], dg[i]);
-      atomicAdd(&s_db[lane + 32 * i], db[i]);
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int c = 4 * hl + 64 * j + e, i = 4 * j + e;
+      if (dgamma != nullptr) { atomicAdd(&s_acc[0][c], dg[i]); atomicAdd(&s_acc[1][c], db[i]); }
+      if (dcolsum != nullptr) atomicAdd(&s_acc[2][c], ds[i]);
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < kD; i += blockDim.x) {
-      atomicAdd(&dgamma[i], s_dg[i]);
-      atomicAdd(&dbeta[i], s_db[i]);
-    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kD; i += blockDim.x) {
+    if (dgamma != nullptr) { atomicAdd(&dgamma[i], s_acc[0][i]); atomicAdd(&dbeta[i], s_acc[1][i]); }
+    if (dcolsum != nullptr) atomicAdd(&dcolsum[i], s_acc[2][i]);
   }
 }
 
@@ -306,16 +356,20 @@ int rvk_layernorm_fwd_tiled_launch(const float* x_tiled, int64_t token_row_strid
 int rvk_layernorm_bwd_launch(const void* g, int g_is_bf16, int64_t g_row_stride, const float* x, int64_t x_row_stride,
                              const float* mean, const float* rstd, const float* gamma, const float* dx_in,
                              float* dx_out, int64_t dx_row_stride, void* dx_out_bf16, float* dgamma, float* dbeta,
-                             int rows, cudaStream_t stream) {
+                             float* dcolsum, int rows, cudaStream_t stream) {
   if (rows <= 0) return RVK_OK;
-  const int blocks = min((rows + 7) / 8, kNumSMsB200 * 4);
+  if ((g_row_stride | x_row_stride | dx_row_stride) % 4 != 0 ||
+      ((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx_in) |
+        reinterpret_cast<uintptr_t>(dx_out) | reinterpret_cast<uintptr_t>(dx_out_bf16) | reinterpret_cast<uintptr_t>(gamma)) & 15) != 0)
+    return RVK_ERR_UNSUPPORTED_SHAPE;
+  const int blocks = min((rows + 15) / 16, kNumSMsB200 * 6);
   auto* dxb = static_cast<__nv_bfloat16*>(dx_out_bf16);
   if (g_is_bf16)
     layernorm_bwd_kernel<true><<<blocks, 256, 0, stream>>>(g, g_row_stride, x, x_row_stride, mean, rstd, gamma, dx_in,
-                                                           dx_out, dx_row_stride, dxb, dgamma, dbeta, rows);
+                                                           dx_out, dx_row_stride, dxb, dgamma, dbeta, dcolsum, rows);
   else
     layernorm_bwd_kernel<false><<<blocks, 256, 0, stream>>>(g, g_row_stride, x, x_row_stride, mean, rstd, gamma, dx_in,
-                                                            dx_out, dx_row_stride, dxb, dgamma, dbeta, rows);
+                                                            dx_out, dx_row_stride, dxb, dgamma, dbeta, dcolsum, rows);
   return rvk_launch_check();
 }
 

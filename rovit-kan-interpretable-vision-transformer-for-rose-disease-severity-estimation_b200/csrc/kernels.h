@@ -65,7 +65,7 @@ int rvk_layernorm_fwd_tiled_launch(const float* x_tiled, int64_t token_row_strid
 int rvk_layernorm_bwd_launch(const void* g, int g_is_bf16, int64_t g_row_stride, const float* x, int64_t x_row_stride,
                              const float* mean, const float* rstd, const float* gamma, const float* dx_in,
                              float* dx_out, int64_t dx_row_stride, void* dx_out_bf16, float* dgamma, float* dbeta,
-                             int rows, cudaStream_t stream);
+                             float* dcolsum, int rows, cudaStream_t stream);
 int rvk_colsum_launch(const void* src, int src_is_bf16, int64_t ld, int rows, int cols, float* out, float scale,
                       cudaStream_t stream);
 int rvk_token_grad_reduce_launch(const float* dx0, int batch, float* dpos, float* dcls, float* dpatch_bias,

@@ -92,7 +92,7 @@ def test_layernorm_forward_strided_cls_rows():
                  what='cls-row ln')
 
 
-@pytest.mark.parametrize('rows,g_bf16', [(3, False), (4000, True)])
+@pytest.mark.parametrize('rows,g_bf16', [(3, False), (17, True), (4000, True), (50432, False)])
 def test_layernorm_backward(rows, g_bf16):
     x = (torch.randn(rows, 192, device=DEV) * 2).requires_grad_(True)
     gamma = torch.randn(192, device=DEV, requires_grad=True)
@@ -108,9 +108,11 @@ def test_layernorm_backward(rows, g_bf16):
     dx = dx_in.clone()
     dxb = torch.zeros(rows, 192, device=DEV, dtype=torch.bfloat16)
     dgamma, dbeta = torch.zeros(192, device=DEV), torch.zeros(192, device=DEV)
+    dcol = torch.full((192,), 0.5, device=DEV)          # accumulates: column sums of the dx written (fused bias gradient)
     _lib.call('rvk_layernorm_backward', _p(g), int(g_bf16), 192, _p(x.detach()), 192, _p(mean), _p(rstd),
-              _p(gamma.detach()), _p(dx), _p(dx), 192, _p(dxb), _p(dgamma), _p(dbeta), rows, _s())
+              _p(gamma.detach()), _p(dx), _p(dx), 192, _p(dxb), _p(dgamma), _p(dbeta), _p(dcol), rows, _s())
     torch.cuda.synchronize()
+    assert_close(dcol, 0.5 + dx.sum(0), rtol=1e-3, atol=1e-3, scale_tol=1e-4, what='fused column sum of dx')
     assert_close(dx, dx_in + x.grad, rtol=1e-4, atol=1e-4, what='dx')
     assert_close(dxb.float(), dx, rtol=8e-3, atol=1e-3, what='dx bf16 copy')
     assert_close(dgamma, gamma.grad, rtol=1e-3, atol=1e-3, scale_tol=1e-4, what='dgamma')
