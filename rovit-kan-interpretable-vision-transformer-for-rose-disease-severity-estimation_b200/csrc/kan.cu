@@ -361,6 +361,9 @@ bool kan_tc_disabled() {
   static const bool off = [] { const char* e = getenv("RVK_KAN_SIMT"); return e != nullptr && e[0] == '1'; }();
   return off;
 }
+bool kan_use_tc(int batch, int n_in, int n_out) {
+  return batch >= kKanTcMinBatch && n_in % 8 == 0 && n_out <= 64 && n_in >= 64 && !kan_tc_disabled();
+}
 
 #include "kan_tc.cuh"
 #include "heads_fused.cuh"
@@ -373,7 +376,8 @@ int64_t rvk_kan_workspace_floats(int n_in, int n_out, int with_backward) {
   const int64_t wp = in_pad * 8 * out_pad;
   // + one wp-sized block for the bf16 hi / lo split of the packed weights (tensor-core path, large batches)
   // (+ 64 floats: interval thresholds of the tensor-core path)
-  return (with_backward ? 3 * wp : wp) + wp + 64;
+  // (+ with backward: a second split in packed-row-major order, the B operand of the tensor-core dx kernel)
+  return (with_backward ? 3 * wp : wp) + wp + 64 + (with_backward ? wp : 0);
 }
 
 int rvk_kan_basis_launch(const float* t, const float* knots_host, float* out, int64_t n, cudaStream_t stream) {
@@ -397,13 +401,19 @@ int rvk_kan_layer_fwd_launch(const KanLayerDesc& L, const float* x, float* y, in
   const int pack_blocks = static_cast<int>((wp + 255) / 256 < 1184 ? (wp + 255) / 256 : 1184);
   kan_pack_kernel<<<pack_blocks, 256, 0, stream>>>(L.spline, L.lin_w, L.in_features, L.out_features, in_pad, out_pad, Wp, WpT);
   RVK_TRY(rvk_launch_check());
-  if (batch >= kKanTcMinBatch && L.in_features % 8 == 0 && L.out_features <= 64 && L.in_features >= 64 && !kan_tc_disabled()) {
+  if (kan_use_tc(batch, L.in_features, L.out_features)) {
     // tensor-core path: operands split hi + lo in bf16, activations generated on the fly (kan_tc.cuh)
     const int kp = in_pad * 8;
     auto* w_hi = reinterpret_cast<__nv_bfloat16*>(workspace + (with_backward ? 3 : 1) * wp);
     auto* w_lo = w_hi + static_cast<size_t>(64) * kp;
     kan_split_weights_kernel<<<pack_blocks, 256, 0, stream>>>(L.spline, L.lin_w, L.in_features, L.out_features, kp, w_hi, w_lo);
     RVK_TRY(rvk_launch_check());
+    if (with_backward) {      // packed-row-major split for the tensor-core dx kernel (after the 64 threshold floats)
+      auto* w2_hi = reinterpret_cast<__nv_bfloat16*>(workspace + 4 * wp + 64);
+      kan_split_weights_rows_kernel<<<pack_blocks, 256, 0, stream>>>(L.spline, L.lin_w, L.in_features, L.out_features, kp, w2_hi,
+                                                                    w2_hi + static_cast<size_t>(64) * kp);
+      RVK_TRY(rvk_launch_check());
+    }
     static bool configured = false;
     if (!configured) {
       RVK_CUDA_TRY(cudaFuncSetAttribute(kan_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
@@ -456,16 +466,61 @@ int rvk_kan_layer_bwd_launch(const KanLayerDesc& L, const float* x, const float*
     if (splits > sub_tiles) splits = sub_tiles;
     const int sps = ((sub_tiles + splits - 1) / splits) * kTS;
     splits = (batch + sps - 1) / sps;
-    dim3 grid(in_pad / kIC, out_pad / kTO, splits);
-    kan_bwd_w_kernel<<<grid, 256, 0, stream>>>(x, y, gy, act, kn, dWp, dlin_b, batch, L.in_features, L.out_features,
-                                               out_pad, sps);
+    if (kan_use_tc(batch, L.in_features, L.out_features) && L.in_features % 64 == 0) {
+      // tensor-core weight gradient (kan_tc.cuh): grid = (batch slices) x (groups of 64 inputs)
+      static bool configured = false;
+      if (!configured) {
+        RVK_CUDA_TRY(cudaFuncSetAttribute(kan_bwd_w_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcWgSmemBytes));
+        configured = true;
+      }
+      KanTcTables tb;
+      tb.xthr = workspace + 4 * wp;          // written by the forward launch
+      for (int j = 0; j < 8; ++j) {
+        tb.knot[j] = L.knots_host[j];
+        tb.inv_h[j] = 1.0f / (L.knots_host[j + 1] - L.knots_host[j]);
+      }
+      const int groups = L.in_features / 64;
+      const int tiles128 = (batch + 127) / 128;
+      int slices = kNumSMsB200 / groups;
+      if (slices > tiles128) slices = tiles128;
+      kan_bwd_w_tc_kernel<<<dim3(slices, groups), kTcThreads, kTcWgSmemBytes, stream>>>(x, y, gy, tb, dWp, dlin_b, act, batch,
+                                                                                        L.in_features, L.out_features);
+    } else {
+      dim3 grid(in_pad / kIC, out_pad / kTO, splits);
+      kan_bwd_w_kernel<<<grid, 256, 0, stream>>>(x, y, gy, act, kn, dWp, dlin_b, batch, L.in_features, L.out_features,
+                                                 out_pad, sps);
+    }
     RVK_TRY(rvk_launch_check());
     const int64_t tot = static_cast<int64_t>(L.in_features) * L.out_features * 8;
     const int ub = static_cast<int>((tot + 255) / 256 < 1184 ? (tot + 255) / 256 : 1184);
     kan_unpack_grad_kernel<<<ub, 256, 0, stream>>>(dWp, L.in_features, L.out_features, out_pad, dspline, dlin_w);
     RVK_TRY(rvk_launch_check());
   }
-  if (dx != nullptr) {
+  if (dx != nullptr && kan_use_tc(batch, L.in_features, L.out_features)) {
+    // tensor-core dx (kan_tc.cuh); split weights and thresholds were written by the forward launch into the workspace
+    const int kp = in_pad * 8;
+    auto* w2_hi = reinterpret_cast<__nv_bfloat16*>(workspace + 4 * wp + 64);
+    auto* w2_lo = w2_hi + static_cast<size_t>(64) * kp;
+    static bool configured = false;
+    if (!configured) {
+      RVK_CUDA_TRY(cudaFuncSetAttribute(kan_bwd_x_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcBxSmemBytes));
+      configured = true;
+    }
+    CUtensorMap tmWhi, tmWlo;
+    RVK_TRY(rvk_make_tmap_2d(&tmWhi, w2_hi, RVK_BF16, kp, 64, 64, 64, 64));
+    RVK_TRY(rvk_make_tmap_2d(&tmWlo, w2_lo, RVK_BF16, kp, 64, 64, 64, 64));
+    KanTcTables tb;
+    tb.xthr = workspace + 4 * wp;            // = the 16 floats after the forward's split weights
+    for (int j = 0; j < 8; ++j) {
+      tb.knot[j] = L.knots_host[j];
+      tb.inv_h[j] = 1.0f / (L.knots_host[j + 1] - L.knots_host[j]);
+    }
+    const int tiles = (batch + 127) / 128;
+    const int grid = tiles < kNumSMsB200 ? tiles : kNumSMsB200;
+    kan_bwd_x_tc_kernel<<<grid, kTcThreads, kTcBxSmemBytes, stream>>>(tmWhi, tmWlo, x, y, gy, tb, dx, act, batch, L.in_features,
+                                                                     L.out_features, L.in_features / 8);
+    RVK_TRY(rvk_launch_check());
+  } else if (dx != nullptr) {
     kan_bwd_x_kernel<<<(batch + kTS - 1) / kTS, 256, 0, stream>>>(x, y, gy, act, kn, WpT, dx, batch, L.in_features,
                                                                    L.out_features, in_pad, out_pad);
     RVK_TRY(rvk_launch_check());

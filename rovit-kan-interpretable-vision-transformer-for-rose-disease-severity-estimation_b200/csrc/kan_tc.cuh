@@ -67,6 +67,45 @@ __global__ void kan_split_weights_kernel(const float* __restrict__ spline, const
   }
 }
 
+// The 8 packed activations [N_0(tanh x) .. N_6(tanh x), x] of one (sample, input), split hi + lo in bf16, written as one
+// 16-byte K chunk each at byte offset `off` of the hi / lo operand tiles.
+__device__ __forceinline__ void kan_tc_expand_store(float xe, uint32_t off, uint8_t* ahi, uint8_t* alo, const float* sXthr,
+                                                    const float* sKnot, const float* sInvH) {
+  // tanh (branch-free, MUFU): values only; the interval comes from x-space thresholds
+  const float ex = ex2_approx(fabsf(xe) * 2.8853900817779268f);
+  float rc;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(ex + 1.0f));
+  const float tt = copysignf(fmaf(-2.0f, rc, 1.0f), xe);
+  int j = static_cast<int>((tt + 1.0f) * 5.0f);
+  j = min(max(j, 0), 7);
+  if (xe < sXthr[j]) --j;
+  else if (xe >= sXthr[j + 1]) ++j;           // j = #{m >= 1 : x >= xthr[m]}, capped at 8 (>= 7: dead zone)
+  // slot 7 = raw x (hi / lo); slots 0..6 zero unless overwritten below
+  const __nv_bfloat16 xh = __float2bfloat16(xe);
+  const __nv_bfloat16 xl = __float2bfloat16(xe - __bfloat162float(xh));
+  *reinterpret_cast<uint4*>(ahi + off) = make_uint4(0u, 0u, 0u, static_cast<uint32_t>(__bfloat16_as_ushort(xh)) << 16);
+  *reinterpret_cast<uint4*>(alo + off) = make_uint4(0u, 0u, 0u, static_cast<uint32_t>(__bfloat16_as_ushort(xl)) << 16);
+  if (j < 7) {
+    const float u = (tt - sKnot[j]) * sInvH[j];
+    const float u2 = u * u, u3 = u2 * u, om = 1.0f - u;
+    float v[4];
+    v[0] = u3 * (1.0f / 6.0f);                                            // slot j
+    v[1] = (1.0f + 3.0f * u + 3.0f * u2 - 3.0f * u3) * (1.0f / 6.0f);     // slot j-1
+    v[2] = (4.0f - 6.0f * u2 + 3.0f * u3) * (1.0f / 6.0f);                // slot j-2
+    v[3] = om * om * om * (1.0f / 6.0f);                                  // slot j-3
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int slot = j - m;
+      if (slot >= 0) {
+        const __nv_bfloat16 h = __float2bfloat16(v[m]);
+        const __nv_bfloat16 l = __float2bfloat16(v[m] - __bfloat162float(h));
+        *reinterpret_cast<__nv_bfloat16*>(ahi + off + slot * 2) = h;
+        *reinterpret_cast<__nv_bfloat16*>(alo + off + slot * 2) = l;
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1)
 kan_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
                   const float* __restrict__ x, const float* __restrict__ bias, const KanTcTables tb, float* __restrict__ y,
@@ -206,41 +245,7 @@ kan_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_consta
         uint8_t* alo = ahi + 16384;
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          const float xe = e == 0 ? xv.x : xv.y;
-          // tanh (branch-free, MUFU): values only; the interval comes from x-space thresholds
-          const float ex = ex2_approx(fabsf(xe) * 2.8853900817779268f);
-          float rc;
-          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(ex + 1.0f));
-          const float tt = copysignf(fmaf(-2.0f, rc, 1.0f), xe);
-          int j = static_cast<int>((tt + 1.0f) * 5.0f);
-          j = min(max(j, 0), 7);
-          if (xe < sXthr[j]) --j;
-          else if (xe >= sXthr[j + 1]) ++j;           // j = #{m >= 1 : x >= xthr[m]}, capped at 8 (>= 7: dead zone)
-          const uint32_t off = sw128_offset(srow, 2 * ip + e);   // input (2*ip+e) of the chunk = one 16-byte K chunk
-          // slot 7 = raw x (hi / lo); slots 0..6 zero unless overwritten below
-          const __nv_bfloat16 xh = __float2bfloat16(xe);
-          const __nv_bfloat16 xl = __float2bfloat16(xe - __bfloat162float(xh));
-          *reinterpret_cast<uint4*>(ahi + off) = make_uint4(0u, 0u, 0u, static_cast<uint32_t>(__bfloat16_as_ushort(xh)) << 16);
-          *reinterpret_cast<uint4*>(alo + off) = make_uint4(0u, 0u, 0u, static_cast<uint32_t>(__bfloat16_as_ushort(xl)) << 16);
-          if (j < 7) {
-            const float u = (tt - sKnot[j]) * sInvH[j];
-            const float u2 = u * u, u3 = u2 * u, om = 1.0f - u;
-            float v[4];
-            v[0] = u3 * (1.0f / 6.0f);                                            // slot j
-            v[1] = (1.0f + 3.0f * u + 3.0f * u2 - 3.0f * u3) * (1.0f / 6.0f);     // slot j-1
-            v[2] = (4.0f - 6.0f * u2 + 3.0f * u3) * (1.0f / 6.0f);                // slot j-2
-            v[3] = om * om * om * (1.0f / 6.0f);                                  // slot j-3
-#pragma unroll
-            for (int m = 0; m < 4; ++m) {
-              const int slot = j - m;
-              if (slot >= 0) {
-                const __nv_bfloat16 h = __float2bfloat16(v[m]);
-                const __nv_bfloat16 l = __float2bfloat16(v[m] - __bfloat162float(h));
-                *reinterpret_cast<__nv_bfloat16*>(ahi + off + slot * 2) = h;
-                *reinterpret_cast<__nv_bfloat16*>(alo + off + slot * 2) = l;
-              }
-            }
-          }
+          kan_tc_expand_store(e == 0 ? xv.x : xv.y, sw128_offset(srow, 2 * ip + e), ahi, alo, sXthr, sKnot, sInvH);
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -293,4 +298,482 @@ kan_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_consta
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, 128);
+}
+
+// =====================================================================================================================
+// Tensor-core backward w.r.t. the layer input:
+//     T[b, i*8+k] = sum_o g[b,o] * Wp[i*8+k, o],   g = gy * act'(y)         GEMM [B x out] x [out x 8*in], split hi + lo
+//     dx[b, i]    = T[b, i*8+7] + (1 - t^2) * sum_k N'_k(t) * T[b, i*8+k],   t = tanh x[b,i]
+// Per 128-sample tile the sixteen worker warps build the K-major swizzled operand tile of g (hi | lo) once; the issuer
+// then walks the input chunks (8 inputs = 64 packed rows of Wp = one UMMA N tile) with two TMEM accumulators, and the
+// workers contract each finished 128 x 64 block of T against the basis derivatives straight out of TMEM (thread = one
+// sample row x two inputs), so T never exists in memory either.  Wp2 hi / lo: bf16 [8*in_pad][64] (packed row major).
+__device__ __forceinline__ void kan_tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+constexpr int kTcGBufBytes = 2 * 16384;             // g_hi | g_lo, each [128 x 64] bf16
+constexpr int kTcBxSmemBytes = 1024 + 2 * kTcGBufBytes + kTcWStages * kTcWStageBytes + 32 * 4 + 256;
+
+// Wp (fp32 [kp][out_pad=64]) -> bf16 hi / lo, row-major [kp][64] each
+__global__ void kan_split_weights_rows_kernel(const float* __restrict__ spline, const float* __restrict__ lin_w, int n_in,
+                                              int n_out, int kp, __nv_bfloat16* __restrict__ w_hi,
+                                              __nv_bfloat16* __restrict__ w_lo) {
+  const long long total = 64LL * kp;
+  for (long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int kk = static_cast<int>(idx >> 6), o = static_cast<int>(idx & 63);
+    const int i = kk >> 3, k = kk & 7;
+    float v = 0.0f;
+    if (i < n_in && o < n_out)
+      v = (k < 7) ? spline[(static_cast<size_t>(i) * n_out + o) * 7 + k] : lin_w[static_cast<size_t>(o) * n_in + i];
+    const __nv_bfloat16 hi = __float2bfloat16(v);
+    w_hi[idx] = hi;
+    w_lo[idx] = __float2bfloat16(v - __bfloat162float(hi));
+  }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+kan_bwd_x_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo,
+                    const float* __restrict__ x, const float* __restrict__ yv, const float* __restrict__ gy, const KanTcTables tb,
+                    float* __restrict__ dx, int act, int batch, int n_in, int n_out, int num_chunks) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sG = smem;
+  uint8_t* sW = sG + 2 * kTcGBufBytes;
+  float* sXthr = reinterpret_cast<float*>(sW + kTcWStages * kTcWStageBytes);     // [12]
+  float* sKnot = sXthr + 12;     // [8]
+  float* sInvH = sKnot + 8;      // [8]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sInvH + 8 + 4);
+  uint64_t* g_full = bars;                       // [2]
+  uint64_t* g_empty = g_full + 2;                // [2]
+  uint64_t* w_full = g_empty + 2;                // [4]
+  uint64_t* w_empty = w_full + kTcWStages;       // [4]
+  uint64_t* d_full = w_empty + kTcWStages;       // [2]
+  uint64_t* d_empty = d_full + 2;                // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(d_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = (batch + 127) / 128;
+
+  if (threadIdx.x < 9) sXthr[threadIdx.x] = tb.xthr[threadIdx.x];
+  if (threadIdx.x < 8) { sKnot[threadIdx.x] = tb.knot[threadIdx.x]; sInvH[threadIdx.x] = tb.inv_h[threadIdx.x]; }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmWhi);
+    tma_prefetch_desc(&tmWlo);
+    for (int i = 0; i < 2; ++i) { mbar_init(&g_full[i], 16); mbar_init(&g_empty[i], 1); }
+    for (int i = 0; i < kTcWStages; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 16); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ================================================================= weight producer: Wp rows [c*64, c*64+64), hi | lo
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        for (int c = 0; c < num_chunks; ++c) {
+          mbar_wait(&w_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&w_full[s], kTcWStageBytes);
+          tma_load_2d(sW + s * kTcWStageBytes, &tmWhi, &w_full[s], 0, c * 64);
+          tma_load_2d(sW + s * kTcWStageBytes + 8192, &tmWlo, &w_full[s], 0, c * 64);
+          if (++s == kTcWStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================= UMMA issuer
+    constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+    const bool issuer = elect_one();
+    const uint32_t g_lo0 = umma_desc_lo(smem_u32(sG)), w_lo0 = umma_desc_lo(smem_u32(sW));
+    int sw = 0, acc = 0, it = 0;
+    uint32_t phw = 0, acc_ph = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      const int gb = it & 1;
+      mbar_wait(&g_full[gb], (it >> 1) & 1);
+      const uint32_t ghi = g_lo0 + gb * (kTcGBufBytes >> 4), glo = ghi + (16384 >> 4);
+      for (int c = 0; c < num_chunks; ++c) {
+        mbar_wait(&w_full[sw], phw);
+        mbar_wait(&d_empty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d = tmem_base + acc * 64;
+        const uint32_t whi = w_lo0 + sw * (kTcWStageBytes >> 4), wlo = whi + (8192 >> 4);
+        if (issuer) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_split<1>(d, ghi + 2 * k, whi + 2 * k, idesc, k != 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_split<1>(d, ghi + 2 * k, wlo + 2 * k, idesc, 1u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_split<1>(d, glo + 2 * k, whi + 2 * k, idesc, 1u);
+          umma_commit(&w_empty[sw]);
+          umma_commit(&d_full[acc]);
+          if (c == num_chunks - 1) umma_commit(&g_empty[gb]);
+        }
+        __syncwarp();
+        if (++sw == kTcWStages) { sw = 0; phw ^= 1; }
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+      }
+    }
+  } else {
+    // ================================================================= workers: g tile builder + derivative contraction
+    const int pw = warp - 2;                              // 0..15
+    const int pt = pw * 32 + lane;                        // 0..511
+    const int srow = pt >> 2, gq = pt & 3;                // g tile: sample row, 16-column quarter
+    const int quad = warp & 3, cg = pw >> 2;              // T blocks: TMEM lane quadrant (= warp % 4), inputs 2cg, 2cg+1 of a chunk
+    const int erow = quad * 32 + lane;
+    const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
+    int acc = 0, it = 0;
+    uint32_t acc_ph = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++it) {
+      // ---- g = gy * act'(y) -> hi | lo operand tile
+      {
+        const int gb = it & 1;
+        const int sg = t * 128 + srow;
+        float g[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) g[i] = 0.0f;
+        if (sg < batch) {
+          const size_t off = static_cast<size_t>(sg) * n_out + gq * 16;
+          if (n_out == 64) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 a = *reinterpret_cast<const float4*>(gy + off + 4 * q);
+              const float4 b = *reinterpret_cast<const float4*>(yv + off + 4 * q);
+              g[4 * q + 0] = a.x * act_grad(act, b.x); g[4 * q + 1] = a.y * act_grad(act, b.y);
+              g[4 * q + 2] = a.z * act_grad(act, b.z); g[4 * q + 3] = a.w * act_grad(act, b.w);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (gq * 16 + i < n_out) g[i] = gy[off + i] * act_grad(act, yv[off + i]);
+          }
+        }
+        mbar_wait(&g_empty[gb], ((it >> 1) & 1) ^ 1);
+        uint8_t* ghi = sG + gb * kTcGBufBytes;
+        uint8_t* glo = ghi + 16384;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t wh[4], wl[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = g[h * 8 + 2 * e], b = g[h * 8 + 2 * e + 1];
+            const __nv_bfloat16 ah = __float2bfloat16(a), bh = __float2bfloat16(b);
+            const __nv_bfloat16 al = __float2bfloat16(a - __bfloat162float(ah)), bl = __float2bfloat16(b - __bfloat162float(bh));
+            wh[e] = static_cast<uint32_t>(__bfloat16_as_ushort(ah)) | (static_cast<uint32_t>(__bfloat16_as_ushort(bh)) << 16);
+            wl[e] = static_cast<uint32_t>(__bfloat16_as_ushort(al)) | (static_cast<uint32_t>(__bfloat16_as_ushort(bl)) << 16);
+          }
+          const uint32_t off = sw128_offset(srow, gq * 2 + h);
+          *reinterpret_cast<uint4*>(ghi + off) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+          *reinterpret_cast<uint4*>(glo + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&g_full[gb]);
+      }
+      // ---- per chunk: T block out of TMEM, contracted with the basis derivatives
+      const int eg = t * 128 + erow;
+      const bool live = eg < batch;
+      const float* xr = x + static_cast<size_t>(live ? eg : 0) * n_in + 2 * cg;
+      float* dxr = dx + static_cast<size_t>(live ? eg : 0) * n_in + 2 * cg;
+      {   // next tile's x rows -> L2
+        const long long tn = static_cast<long long>(t) + gridDim.x;
+        if (tn < num_tiles) {
+          const char* base = reinterpret_cast<const char*>(x) + tn * 128 * static_cast<long long>(n_in) * 4;
+          const long long bytes = min(128LL, static_cast<long long>(batch) - tn * 128) * n_in * 4;
+          for (long long o = static_cast<long long>(pt) * 128; o < bytes; o += 512 * 128) prefetch_l2(base + o);
+        }
+      }
+      float2 xnext = live ? *reinterpret_cast<const float2*>(xr) : make_float2(0.f, 0.f);
+#pragma unroll 1
+      for (int c = 0; c < num_chunks; ++c) {
+        const float2 xv = xnext;
+        if (live && c + 1 < num_chunks) xnext = *reinterpret_cast<const float2*>(xr + (c + 1) * 8);
+        mbar_wait(&d_full[acc], acc_ph);
+        tc_fence_after();
+        float T[16];
+        kan_tmem_ld16(tmem_base + acc * 64 + cg * 16 + lane_sel, T);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&d_empty[acc]);
+        if (++acc == 2) { acc = 0; acc_ph ^= 1; }
+        float out[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const float xe = e == 0 ? xv.x : xv.y;
+          const float ex = ex2_approx(fabsf(xe) * 2.8853900817779268f);
+          float rc;
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(ex + 1.0f));
+          const float tt = copysignf(fmaf(-2.0f, rc, 1.0f), xe);
+          const float dt = 4.0f * rc * (1.0f - rc);                 // 1 - tanh^2, without cancellation
+          int j = static_cast<int>((tt + 1.0f) * 5.0f);
+          j = min(max(j, 0), 7);
+          if (xe < sXthr[j]) --j;
+          else if (xe >= sXthr[j + 1]) ++j;
+          float sp = 0.0f;
+          if (j < 7) {
+            const float ih = sInvH[j];
+            const float u = (tt - sKnot[j]) * ih;
+            const float u2 = u * u, om = 1.0f - u;
+            float d[4];
+            d[0] = 0.5f * u2 * ih;                                               // slot j
+            d[1] = (3.0f + 6.0f * u - 9.0f * u2) * (1.0f / 6.0f) * ih;           // slot j-1
+            d[2] = (-12.0f * u + 9.0f * u2) * (1.0f / 6.0f) * ih;                // slot j-2
+            d[3] = -0.5f * om * om * ih;                                         // slot j-3
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+              const int slot = j - m;
+#pragma unroll
+              for (int k = 0; k < 7; ++k)
+                if (slot == k) sp = fmaf(T[e * 8 + k], d[m], sp);
+            }
+          }
+          out[e] = fmaf(dt, sp, T[e * 8 + 7]);
+        }
+        if (live) *reinterpret_cast<float2*>(dxr + c * 8) = make_float2(out[0], out[1]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 128);
+}
+
+// =====================================================================================================================
+// Tensor-core weight gradient:
+//     dWp[i*8+k, o] += sum_b A[b, i*8+k] * g[b, o],   dlin_b[o] += sum_b g[b, o],      g = gy * act'(y)
+// a GEMM whose reduction index is the SAMPLE: both operands are MN-major UMMA operands (gemm_tn.cuh), and the tiles the
+// forward kernel generates -- [128 samples x 64 packed rows], 128-byte rows, 8-row swizzle atoms -- are exactly the
+// canonical MN-major atom stack, so the same expansion code feeds this kernel.  A CTA owns a group of 64 inputs (four
+// M = 128 blocks of packed rows = four TMEM accumulators that live for the whole kernel) and every (grid.x)-th 128-sample
+// tile; per tile it expands its 64 inputs (two chunks = one M block per stage, hi | lo) and the g tile (hi | lo), and
+// the issuer adds  A_hi g_hi + A_hi g_lo + A_lo g_hi  over the 8 K steps of 16 samples.  At the end the accumulators
+// are added into the fp32 packed gradient with red.global.add (split over the batch).
+constexpr int kTcWgAStageBytes = 4 * 16384;           // [hi | lo] x two 64-row panels of [128 samples x 64] bf16
+constexpr int kTcWgSmemBytes = 1024 + 2 * kTcWgAStageBytes + 2 * kTcGBufBytes + 64 * 4 + 32 * 4 + 256;
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+kan_bwd_w_tc_kernel(const float* __restrict__ x, const float* __restrict__ yv, const float* __restrict__ gy, const KanTcTables tb,
+                    float* __restrict__ dWp, float* __restrict__ dlin_b, int act, int batch, int n_in, int n_out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sG = sA + 2 * kTcWgAStageBytes;
+  float* sDb = reinterpret_cast<float*>(sG + 2 * kTcGBufBytes);     // [64]
+  float* sXthr = sDb + 64;       // [12]
+  float* sKnot = sXthr + 12;     // [8]
+  float* sInvH = sKnot + 8;      // [8]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sInvH + 8 + 4);
+  uint64_t* a_full = bars;                       // [2]
+  uint64_t* a_empty = a_full + 2;                // [2]
+  uint64_t* g_full = a_empty + 2;                // [2]
+  uint64_t* g_empty = g_full + 2;                // [2]
+  uint64_t* acc_full = g_empty + 2;              // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = (batch + 127) / 128;
+  const int group = blockIdx.y;                  // inputs [64*group, 64*group + 64)
+  const int n_my = (blockIdx.x < num_tiles) ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (threadIdx.x < 64) sDb[threadIdx.x] = 0.0f;
+  if (threadIdx.x < 9) sXthr[threadIdx.x] = tb.xthr[threadIdx.x];
+  if (threadIdx.x < 8) { sKnot[threadIdx.x] = tb.knot[threadIdx.x]; sInvH[threadIdx.x] = tb.inv_h[threadIdx.x]; }
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&a_full[i], 16); mbar_init(&a_empty[i], 1);
+      mbar_init(&g_full[i], 16); mbar_init(&g_empty[i], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 1) {
+    // ================================================================= UMMA issuer (both operands MN-major)
+    if (lane == 0 && n_my > 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 1, 1);
+      int sa = 0;
+      uint32_t pha = 0;
+      for (int it = 0; it < n_my; ++it) {
+        const int gb = it & 1;
+        mbar_wait(&g_full[gb], (it >> 1) & 1);
+        const uint32_t g_hi = smem_u32(sG + gb * kTcGBufBytes), g_lo = g_hi + 16384;
+        for (int pr = 0; pr < 4; ++pr) {
+          mbar_wait(&a_full[sa], pha);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(sA + sa * kTcWgAStageBytes), a_lo = a_hi + 32768;
+          const uint32_t d = tmem_base + pr * 64;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {           // 16 samples per UMMA = two 8-row swizzle atoms
+            const uint64_t ah = umma_smem_desc(a_hi + k * 2048, 16384, 1024);
+            const uint64_t al = umma_smem_desc(a_lo + k * 2048, 16384, 1024);
+            const uint64_t gh = umma_smem_desc(g_hi + k * 2048, 16384, 1024);
+            const uint64_t gl = umma_smem_desc(g_lo + k * 2048, 16384, 1024);
+            umma_bf16(d, ah, gh, idesc, (it | k) != 0 ? 1u : 0u);
+            umma_bf16(d, ah, gl, idesc, 1u);
+            umma_bf16(d, al, gh, idesc, 1u);
+          }
+          umma_commit(&a_empty[sa]);
+          if (pr == 3) umma_commit(&g_empty[gb]);
+          if (++sa == 2) { sa = 0; pha ^= 1; }
+        }
+      }
+      umma_commit(acc_full);
+    }
+  } else if (warp >= 2) {
+    // ================================================================= workers: operand generation, final reduction
+    const int pw = warp - 2;                              // 0..15
+    const int pt = pw * 32 + lane;                        // 0..511
+    const int srow = pt >> 2, ip = pt & 3;                // sample row; A: inputs 2ip, 2ip+1 of a chunk; g: 16-column quarter ip
+    int sa = 0;
+    uint32_t pha = 0;
+    float db[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) db[i] = 0.0f;
+    for (int it = 0; it < n_my; ++it) {
+      const int t = blockIdx.x + it * gridDim.x;
+      const int sg = t * 128 + srow;
+      const bool live = sg < batch;
+      // ---- g tile (hi | lo), and this thread's share of the bias gradient
+      {
+        const int gb = it & 1;
+        float g[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) g[i] = 0.0f;
+        if (live) {
+          const size_t off = static_cast<size_t>(sg) * n_out + ip * 16;
+          if (n_out == 64) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 a = *reinterpret_cast<const float4*>(gy + off + 4 * q);
+              const float4 b = *reinterpret_cast<const float4*>(yv + off + 4 * q);
+              g[4 * q + 0] = a.x * act_grad(act, b.x); g[4 * q + 1] = a.y * act_grad(act, b.y);
+              g[4 * q + 2] = a.z * act_grad(act, b.z); g[4 * q + 3] = a.w * act_grad(act, b.w);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (ip * 16 + i < n_out) g[i] = gy[off + i] * act_grad(act, yv[off + i]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) db[i] += g[i];
+        mbar_wait(&g_empty[gb], ((it >> 1) & 1) ^ 1);
+        uint8_t* ghi = sG + gb * kTcGBufBytes;
+        uint8_t* glo = ghi + 16384;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t wh[4], wl[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float a = g[h * 8 + 2 * e], b = g[h * 8 + 2 * e + 1];
+            const __nv_bfloat16 ah = __float2bfloat16(a), bh = __float2bfloat16(b);
+            const __nv_bfloat16 al = __float2bfloat16(a - __bfloat162float(ah)), bl = __float2bfloat16(b - __bfloat162float(bh));
+            wh[e] = static_cast<uint32_t>(__bfloat16_as_ushort(ah)) | (static_cast<uint32_t>(__bfloat16_as_ushort(bh)) << 16);
+            wl[e] = static_cast<uint32_t>(__bfloat16_as_ushort(al)) | (static_cast<uint32_t>(__bfloat16_as_ushort(bl)) << 16);
+          }
+          const uint32_t off = sw128_offset(srow, ip * 2 + h);
+          *reinterpret_cast<uint4*>(ghi + off) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+          *reinterpret_cast<uint4*>(glo + off) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&g_full[gb]);
+      }
+      // ---- expanded activations of this CTA's 64 inputs: four stages of two chunks
+      const float* xr = x + static_cast<size_t>(live ? sg : 0) * n_in + group * 64 + 2 * ip;
+      {   // next tile's x rows (this group's 256-byte slice of each) -> L2
+        const int tn = t + gridDim.x;
+        if (tn < num_tiles && ip == 0 && tn * 128 + srow < batch)
+          prefetch_l2(x + static_cast<size_t>(tn * 128 + srow) * n_in + group * 64);
+      }
+      float2 xnext = live ? *reinterpret_cast<const float2*>(xr) : make_float2(0.f, 0.f);
+#pragma unroll 1
+      for (int pr = 0; pr < 4; ++pr) {
+        mbar_wait(&a_empty[sa], pha ^ 1);
+        uint8_t* stage = sA + sa * kTcWgAStageBytes;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const float2 xv = xnext;
+          const int cn = pr * 2 + h + 1;
+          if (live && cn < 8) xnext = *reinterpret_cast<const float2*>(xr + cn * 8);
+          uint8_t* ahi = stage + h * 16384;
+          uint8_t* alo = ahi + 32768;
+          if (live) {
+            kan_tc_expand_store(xv.x, sw128_offset(srow, 2 * ip), ahi, alo, sXthr, sKnot, sInvH);
+            kan_tc_expand_store(xv.y, sw128_offset(srow, 2 * ip + 1), ahi, alo, sXthr, sKnot, sInvH);
+          } else {                                  // rows past the batch must not contribute (raw-x slot of x = 0 is 0 anyway,
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);   // but the spline slots of tanh(0) are not)
+            *reinterpret_cast<uint4*>(ahi + sw128_offset(srow, 2 * ip)) = z;
+            *reinterpret_cast<uint4*>(alo + sw128_offset(srow, 2 * ip)) = z;
+            *reinterpret_cast<uint4*>(ahi + sw128_offset(srow, 2 * ip + 1)) = z;
+            *reinterpret_cast<uint4*>(alo + sw128_offset(srow, 2 * ip + 1)) = z;
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[sa]);
+        if (++sa == 2) { sa = 0; pha ^= 1; }
+      }
+    }
+    // ---- bias gradient: columns ip*16 .. +15, summed over this thread's rows -> shared -> global (group 0 only)
+    if (group == 0 && dlin_b != nullptr) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float v = db[i];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        if (lane < 4) atomicAdd(&sDb[ip * 16 + i], v);
+      }
+    }
+    // ---- accumulators -> fp32 packed gradient (split over the batch: red.global.add)
+    if (n_my > 0) {
+      const int quad = warp & 3, cg = pw >> 2;
+      const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
+      mbar_wait(acc_full, 0);
+      tc_fence_after();
+#pragma unroll 1
+      for (int pr = 0; pr < 4; ++pr) {
+        float v[16];
+        kan_tmem_ld16(tmem_base + pr * 64 + cg * 16 + lane_sel, v);
+        float* dst = dWp + (static_cast<size_t>(group) * 512 + pr * 128 + quad * 32 + lane) * 64 + cg * 16;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) atomicAdd(dst + i, v[i]);
+      }
+    }
+    named_bar_sync(1, 16 * 32);
+    if (group == 0 && dlin_b != nullptr && pt < n_out) atomicAdd(&dlin_b[pt], sDb[pt]);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
 }
