@@ -407,9 +407,13 @@ def run_kan(args, rank, local_rank, world):
                    'l2': 'L2 flushed (256 MB memset) between timed iterations'},
         'gpu_launches': int(r['fwd_bwd']['launches']) * K,
         'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': gbs / pk['hbm_gbs'],
-                     'traffic': None, 'kernel': 'kan_fwd_kernel + kan_bwd_w_kernel + kan_bwd_x_kernel (fp32 FMA)',
-                     'note': 'algorithmic 152 MB / 38.7 GFLOP per fwd+bwd: 255 FLOP/B, i.e. bound by the fp32 FMA pipe '
-                             '(%.1f TFLOP/s achieved), not by HBM' % (alg_flops / (ms * 1e-3) / 1e12)},
+                     'traffic': None,
+                     'kernel': 'kan_fwd_tc_kernel + kan_bwd_x_tc_kernel + kan_bwd_w_tc_kernel (tcgen05, operands generated on the fly, '
+                               'hi+lo bf16 split = 3 MMAs per product) for 192->64; fp32 CUDA-core kernels for 64->1',
+                     'note': 'algorithmic 152 MB / 38.7 GFLOP per fwd+bwd (%.1f TFLOP/s dense-equivalent achieved): the three kernels '
+                             'are bound by the CUDA-core generation of the expanded activations (tanh, interval search, four cubics, '
+                             'hi/lo split: ~100 instructions per (sample, input), done once per kernel), not by HBM or the tensor pipe'
+                             % (alg_flops / (ms * 1e-3) / 1e12)},
         'detail': out,
     }
     print(json.dumps(line), flush=True)
