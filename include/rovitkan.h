@@ -157,9 +157,11 @@ int rvk_attn_proj_mlp_fused(const float* x_in_tiled, float* x_out_tiled, const v
  * of CTA 0 (NULL switches it off, the default). */
 void rvk_debug_set_mlp_trace(void* device_buf);
 void rvk_debug_set_attn_trace(void* device_buf);   /* same for rvk_attention_forward */
-/* C[P,Q] (fp32) += scale * A[M,P]^T B[M,Q], bf16 operands (weight gradients). */
+/* C[P,Q] (fp32) += scale * A[M,P]^T B[M,Q], bf16 operands (weight gradients).  a_colsum (optional, fp32 [P], needs
+ * Q <= 192): += scale * sum_m A[m,p] -- the bias gradient of the same Linear layer, computed by the same kernel through a
+ * constant column of ones appended to B. */
 int rvk_gemm_tn(const void* a_bf16, int64_t lda, const void* b_bf16, int64_t ldb, float* c, int64_t ldc, int m,
-                int p, int q, float scale, void* stream);
+                int p, int q, float scale, float* a_colsum, void* stream);
 /* softmax(q k^T / 8) v per (image, head); qkv bf16 [batch*197,576], ctx bf16 [batch*197,192], lse fp32
  * [batch,3,197] (log2 domain) or NULL. */
 int rvk_attention_forward(const void* qkv, void* ctx, float* lse, int batch, void* stream);

@@ -46,7 +46,7 @@ SIGNATURES = {
     'rvk_attn_proj_mlp_fused': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _I, _I, _P]),
     'rvk_debug_set_mlp_trace': (None, [_P]),
     'rvk_debug_set_attn_trace': (None, [_P]),
-    'rvk_gemm_tn': (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _F, _P]),
+    'rvk_gemm_tn': (_I, [_P, _L, _P, _L, _P, _L, _I, _I, _I, _F, _P, _P]),
     'rvk_attention_forward': (_I, [_P, _P, _P, _I, _P]),
     'rvk_attention_backward': (_I, [_P, _P, _P, _P, _P, _I, _P]),
     'rvk_layernorm_forward': (_I, [_P, _L, _P, _P, _F, _P, _I, _L, _P, _P, _I, _P]),

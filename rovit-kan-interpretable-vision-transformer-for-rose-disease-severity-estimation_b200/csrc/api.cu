@@ -260,9 +260,9 @@ int rvk_attn_proj_mlp_fused(const float* x_in_tiled, float* x_out_tiled, const v
 void rvk_debug_set_mlp_trace(void* buf) { g_mlp_trace = static_cast<long long*>(buf); }
 void rvk_debug_set_attn_trace(void* buf) { rvk_debug_set_attn_trace_impl(buf); }
 int rvk_gemm_tn(const void* a_bf16, int64_t lda, const void* b_bf16, int64_t ldb, float* c, int64_t ldc, int m, int p,
-                int q, float scale, void* stream) {
+                int q, float scale, float* a_colsum, void* stream) {
   if (m < 0) return RVK_ERR_BAD_ARG;
-  return rvk_gemm_tn_launch(a_bf16, lda, b_bf16, ldb, c, ldc, m, p, q, scale, S(stream));
+  return rvk_gemm_tn_launch(a_bf16, lda, b_bf16, ldb, c, ldc, m, p, q, scale, a_colsum, S(stream));
 }
 int rvk_attention_forward(const void* qkv, void* ctx, float* lse, int batch, void* stream) {
   if (batch < 0 || (batch > 0 && (qkv == nullptr || ctx == nullptr))) return RVK_ERR_BAD_ARG;

@@ -356,7 +356,7 @@ int rvk_encoder_backward_impl(const void* const* params, const void* wbuf, void*
     for (int i = kDepth - 1; i >= 0; --i) {
       const BlockSaved& B = A.blk[i];
       // ---- MLP: x_next = x_mid + fc2(gelu(fc1(ln2)))
-      RVK_TRY(rvk_gemm_tn_launch(dxb, kD, b16(B.h, kMlp), kMlp, G(grads, bp(i, B_FC2W)), kMlp, M, kD, kMlp, 1.0f, s));
+      RVK_TRY(rvk_gemm_tn_launch(dxb, kD, b16(B.h, kMlp), kMlp, G(grads, bp(i, B_FC2W)), kMlp, M, kD, kMlp, 1.0f, nullptr, s));
       // (fc2 bias gradient = column sums of dx: accumulated by the LayerNorm backward that wrote dx)
       {   // dz = (dx * W2) o gelu'(z)
         GemmNtArgs a;
@@ -367,19 +367,20 @@ int rvk_encoder_backward_impl(const void* const* params, const void* wbuf, void*
         a.p.M = M; a.p.N = kMlp; a.p.K = kD;
         RVK_TRY(rvk_gemm_nt_launch(a, s));
       }
-      RVK_TRY(rvk_gemm_tn_launch(dz, kMlp, b16(B.ln2, kD), kD, G(grads, bp(i, B_FC1W)), kD, M, kMlp, kD, 1.0f, s));
-      RVK_TRY(rvk_colsum_launch(dz, 1, kMlp, M, kMlp, G(grads, bp(i, B_FC1B)), 1.0f, s));
+      // (fc1 bias gradient = column sums of dz: the ones column of the same GEMM)
+      RVK_TRY(rvk_gemm_tn_launch(dz, kMlp, b16(B.ln2, kD), kD, G(grads, bp(i, B_FC1W)), kD, M, kMlp, kD, 1.0f,
+                                 G(grads, bp(i, B_FC1B)), s));
       RVK_TRY(gemm_plain(dz, kMlp, at(wbuf, W.fc1T[i]), kMlp, g, kD, M, kD, kMlp, nullptr, s));
       RVK_TRY(rvk_layernorm_bwd_launch(g, 1, kD, f32(B.x_mid, kD), kD, stat(B.mean2), stat(B.rstd2),
                                        P(params, bp(i, B_N2W)), dx, dx, kD, dxb, G(grads, bp(i, B_N2W)),
                                        G(grads, bp(i, B_N2B)), G(grads, bp(i, B_PROJB)), M, s));
       // ---- attention: x_mid = x_in + proj(attn(qkv(ln1)))
-      RVK_TRY(rvk_gemm_tn_launch(dxb, kD, b16(B.ctx, kD), kD, G(grads, bp(i, B_PROJW)), kD, M, kD, kD, 1.0f, s));
+      RVK_TRY(rvk_gemm_tn_launch(dxb, kD, b16(B.ctx, kD), kD, G(grads, bp(i, B_PROJW)), kD, M, kD, kD, 1.0f, nullptr, s));
       RVK_TRY(gemm_plain(dxb, kD, at(wbuf, W.projT[i]), kD, dctx, kD, M, kD, kD, nullptr, s));
       RVK_TRY(rvk_attention_bwd_launch(b16(B.qkv, kQkv), b16(B.ctx, kD), dctx,
                                        reinterpret_cast<float*>(at(workspace, B.lse)) + size_t(b0) * 3 * kTok, dqkv, nb, s));
-      RVK_TRY(rvk_gemm_tn_launch(dqkv, kQkv, b16(B.ln1, kD), kD, G(grads, bp(i, B_QKVW)), kD, M, kQkv, kD, 1.0f, s));
-      RVK_TRY(rvk_colsum_launch(dqkv, 1, kQkv, M, kQkv, G(grads, bp(i, B_QKVB)), 1.0f, s));
+      RVK_TRY(rvk_gemm_tn_launch(dqkv, kQkv, b16(B.ln1, kD), kD, G(grads, bp(i, B_QKVW)), kD, M, kQkv, kD, 1.0f,
+                                 G(grads, bp(i, B_QKVB)), s));
       RVK_TRY(gemm_plain(dqkv, kQkv, at(wbuf, W.qkvT[i]), kQkv, g, kD, M, kD, kQkv, nullptr, s));
       RVK_TRY(rvk_layernorm_bwd_launch(g, 1, kD, f32(B.x_in, kD), kD, stat(B.mean1), stat(B.rstd1),
                                        P(params, bp(i, B_N1W)), dx, dx, kD, dxb, G(grads, bp(i, B_N1W)),
@@ -387,7 +388,7 @@ int rvk_encoder_backward_impl(const void* const* params, const void* wbuf, void*
     }
     // ---- patch embedding, class token, position embedding
     RVK_TRY(rvk_gemm_tn_launch(dxb, kD, b16(A.patches, kPatchK), kPatchK, G(grads, P_PATCH_W), kPatchK, M, kD, kPatchK,
-                               1.0f, s));
+                               1.0f, nullptr, s));
     RVK_TRY(rvk_token_grad_reduce_launch(dx, nb, G(grads, P_POS), G(grads, P_CLS), G(grads, P_PATCH_B), s));
   }
   return RVK_OK;

@@ -107,8 +107,9 @@ int rvk_gemm_nt_launch(const GemmNtArgs& a, cudaStream_t stream) {
 }
 
 int rvk_gemm_tn_launch(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int M, int P,
-                       int Q, float scale, cudaStream_t stream) {
+                       int Q, float scale, float* a_colsum, cudaStream_t stream) {
   if (M <= 0 || P <= 0 || Q <= 0) return RVK_OK;
+  if (a_colsum != nullptr && Q > kBQ) return RVK_ERR_UNSUPPORTED_SHAPE;    // the ones column rides on a single Q tile
   if (A == nullptr || B == nullptr || C == nullptr) return RVK_ERR_BAD_ARG;
   if (P % 64 != 0 || Q % 64 != 0) return RVK_ERR_UNSUPPORTED_SHAPE;
   using L = GemmTnSmem<kBQ, kTnStages>;
@@ -132,6 +133,7 @@ int rvk_gemm_tn_launch(const void* A, int64_t lda, const void* B, int64_t ldb, f
   p.chunks_per_split = (total_chunks + splits - 1) / splits;
   p.C = C;
   p.scale = scale;
+  p.colsum = a_colsum;
   splits = (total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
   ScopedTimer timer(stream, 2.0 * M * P * Q, kKindTn);
   kernel<<<dim3(tiles, splits), kTnThreads, L::kTotal, stream>>>(tmA, tmB, p);

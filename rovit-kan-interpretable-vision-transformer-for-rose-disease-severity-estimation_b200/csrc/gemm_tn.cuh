@@ -6,6 +6,11 @@
 // per 1024 B swizzle atom).  Descriptor strides: LBO = distance between 64-column boxes (8 KB),
 // SBO = distance between 8-row groups (1 KB).
 //
+// Bias gradients for free: when the launcher passes `colsum` (and Q fits one tile), a constant panel of ONES is appended
+// to the B operand of every stage and the UMMA runs with N = BQ + 16: accumulator column BQ then holds sum_m A[m, p],
+// the column sums of A = the bias gradient of the Linear layer whose output gradient A is.  8 % more tensor work instead
+// of a separate pass over A.
+//
 // Grid = (P tiles of 128) x (Q tiles of BQ) x splits over M; every CTA reduces its M-range into one
 // TMEM accumulator and adds it into the fp32 gradient with coalesced red.global.add (split-K).
 // Warp roles (192 threads): w0 TMA producer, w1 UMMA issuer + TMEM owner, w2..w5 epilogue.
@@ -19,6 +24,7 @@ struct GemmTnParams {
   int chunks_per_split;   // in units of 64 rows of M
   float* C;
   float scale;
+  float* colsum;          // optional [P]: += scale * sum_m A[m, p]  (requires Q <= BQ)
 };
 
 constexpr int kTnThreads = 192;
@@ -27,7 +33,9 @@ template <int BQ, int STAGES>
 struct GemmTnSmem {
   static constexpr int kABytes = 2 * 64 * 128;          // two [64 x 64] bf16 boxes
   static constexpr int kBBytes = (BQ / 64) * 64 * 128;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kOnesBytes = 64 * 128;           // constant [64 x 64] panel of 1.0 right after the B boxes (colsum)
+  static constexpr int kStageBytes = kABytes + kBBytes + kOnesBytes;
+  static constexpr int kTxBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = 128 * 33 * 4;
   static constexpr int kTotal = 1024 + STAGES * kStageBytes + kStagingBytes + 256;
 };
@@ -73,6 +81,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tmem_alloc(tmem_ptr, 256);
     tmem_relinquish();
   }
+  if (p.colsum != nullptr) {      // the ones panels are never touched by TMA: written once
+    for (int i = threadIdx.x; i < STAGES * (L::kOnesBytes / 16); i += blockDim.x) {
+      const int st = i / (L::kOnesBytes / 16), o = i % (L::kOnesBytes / 16);
+      *reinterpret_cast<uint4*>(sOperands + st * L::kStageBytes + L::kABytes + L::kBBytes + o * 16) =
+          make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    }
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -85,7 +101,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t ph = 0;
         for (int c = c_begin; c < c_end; ++c) {
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full[s], L::kStageBytes);
+          mbar_arrive_expect_tx(&full[s], L::kTxBytes);
           uint8_t* a = sOperands + s * L::kStageBytes;
           tma_load_2d(a, &tmA, &full[s], p0, c * 64);
           tma_load_2d(a + 8192, &tmA, &full[s], p0 + 64, c * 64);
@@ -97,7 +113,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     } else if (warp == 1) {
       if (lane == 0) {
-        constexpr uint32_t idesc = umma_idesc_bf16(128, BQ, 1, 1);
+        const uint32_t idesc = (p.colsum != nullptr) ? umma_idesc_bf16(128, BQ + 16, 1, 1) : umma_idesc_bf16(128, BQ, 1, 1);
         int s = 0;
         uint32_t ph = 0;
         for (int c = 0; c < n_chunks; ++c) {
@@ -138,6 +154,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             atomicAdd(p.C + static_cast<size_t>(gp) * p.ldc + gq, sStage[rr * 33 + lane] * p.scale);
         }
         named_bar_sync(1, 128);
+      }
+      if (p.colsum != nullptr) {
+        float v[32];
+        tmem_ld32(tacc + BQ, v);             // column BQ = A^T . 1  (columns beyond BQ + 16 are unused TMEM)
+        const int gp = p0 + row;
+        if (gp < p.P) atomicAdd(p.colsum + gp, v[0] * p.scale);
       }
     }
   }

@@ -26,9 +26,10 @@ struct GemmNtArgs {
 };
 int rvk_gemm_nt_launch(const GemmNtArgs& a, cudaStream_t stream);
 
-// C[P,Q] (fp32, ldc) += scale * A[M,P]^T B[M,Q]; A, B bf16 row-major
+// C[P,Q] (fp32, ldc) += scale * A[M,P]^T B[M,Q]; A, B bf16 row-major; optional a_colsum[P] += scale * column sums of A
+// (the bias gradient when A is an output gradient; needs Q <= 192)
 int rvk_gemm_tn_launch(const void* A, int64_t lda, const void* B, int64_t ldb, float* C, int64_t ldc, int M, int P,
-                       int Q, float scale, cudaStream_t stream);
+                       int Q, float scale, float* a_colsum, cudaStream_t stream);
 
 // fused MLP block of the inference path: x_out = x_in + fc2(gelu(fc1(LayerNorm2(x_in)))) (+ LayerNorm -> ln_out); the
 // fp32 token stream x uses the tiled layout of common.cuh (xt_offset).  cta_group: 2 = CTA pairs (default), 1 = single CTAs.

@@ -152,9 +152,14 @@ def test_gemm_tn_weight_gradient(M, P, Q):
     A, B = _rand_bf16(M, P, seed=16), _rand_bf16(M, Q, seed=17)
     C = torch.randn(P, Q, device=DEV)
     ref = C.double() + 0.5 * (A.double().t() @ B.double())
-    _lib.call('rvk_gemm_tn', _p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0), M, P, Q, 0.5, _s())
+    fused_bias = Q <= 192                       # bias gradient (column sums of A) through the ones column of the same GEMM
+    cs = torch.full((P,), 0.25, device=DEV)
+    _lib.call('rvk_gemm_tn', _p(A), A.stride(0), _p(B), B.stride(0), _p(C), C.stride(0), M, P, Q, 0.5,
+              _p(cs) if fused_bias else 0, _s())
     torch.cuda.synchronize()
     assert_close(C, ref.float(), rtol=1e-4, atol=1e-4, scale_tol=2e-5, what=f'wgrad {M}x{P}x{Q}')
+    if fused_bias:
+        assert_close(cs, (0.25 + 0.5 * A.double().sum(0)).float(), rtol=1e-4, atol=1e-3, scale_tol=2e-5, what='fused column sums of A')
 
 
 def test_gemm_rejects_bad_shapes():
