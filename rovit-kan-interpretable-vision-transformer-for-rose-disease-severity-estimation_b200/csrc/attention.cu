@@ -9,6 +9,8 @@
 //   with delta[q] = sum_d dO[q,d] * O[q,d].
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace {
 
 constexpr int kTok = 197;
@@ -295,11 +297,16 @@ attn_bwd_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __re
 }  // namespace
 
 // ------------------------------------------------------------------------------------------- launchers
+int rvk_attention_bwd_tc_launch(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv, int batch,
+                                cudaStream_t stream);      // attention_tc.cu
 constexpr int kAttnBwdSmem = 4 * kPad * 128 + kAttnWarps * 2048 + 2 * kPad * 4;
 
 int rvk_attention_bwd_launch(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
                              int batch, cudaStream_t stream) {
   if (batch <= 0) return RVK_OK;
+  // default: the tcgen05 kernel (attention_tc.cu); RVK_ATTN_BWD_SIMT=1 keeps this file's mma.sync kernel (A/B measurements)
+  static const bool simt = [] { const char* e = getenv("RVK_ATTN_BWD_SIMT"); return e != nullptr && e[0] == '1'; }();
+  if (!simt) return rvk_attention_bwd_tc_launch(qkv, ctx, dctx, lse, dqkv, batch, stream);
   static bool configured = false;
   if (!configured) {
     RVK_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdSmem));

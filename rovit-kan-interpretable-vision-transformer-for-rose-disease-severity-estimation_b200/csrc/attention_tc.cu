@@ -21,6 +21,8 @@
 #include "kernels.h"
 #include "tma_host.h"
 
+#include <type_traits>
+
 namespace {
 
 constexpr int kTok = 197, kHeads = 3, kHd = 64;
@@ -315,6 +317,273 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == kSmWarps + 1) tmem_dealloc(tmem_base, 512);
 }
 
+
+// =====================================================================================================================
+// Attention BACKWARD on tcgen05 (recompute from the saved log-sum-exp; no atomics, no stored probabilities).
+// Per (image, head) four work units, each one 128-row tile with the same two-GEMMs -> elementwise -> GEMM(s) shape as
+// the forward:
+//   phase K, key tile kt:    S^T = K_kt Q^T, dP^T = V_kt dO^T            (UMMA 128 x 208 x 64 each, TMEM columns [0,208) / [208,416))
+//                            P^T = exp2(S^T c - lse[q]),  dS^T = P^T o (dP^T - delta[q])      (sixteen warps, bf16 back into TMEM)
+//                            dV_kt = P^T dO,  dK_kt = scale dS^T Q       (A operand in TMEM, B = dO / Q tile read MN-major)
+//   phase Q, query tile qt:  S = Q_qt K^T, dP = dO_qt V^T;  dS = P o (dP - delta[row]);  dQ_qt = scale dS K
+// with delta[q] = sum_d dO[q,d] O[q,d].  A warp (quad, cg) owns 32 rows and a column slice that is a whole number of
+// UMMA K steps (64 / 48 / 48 / 48 columns); it walks its slice in pieces of 32 or 16 columns and writes the packed
+// bf16 results of a piece (P pairs, then dS pairs) over the very S columns it has just read, so no warp ever
+// overwrites scores another warp still needs and the whole dP region is free for the 64-column output tiles.  The issuer
+// pairs each 16-row K step of the B tile with the TMEM columns where that piece put it (kBwdPCol / kBwdDsCol).
+// Q, K, V, dO tiles are 256 rows (rows >= 197 zero-filled by TMA) so that each serves as M tile, N = 208 operand and
+// MN-major B operand alike.  One unit in flight (the regions are single-buffered): tensor pipe and softmax warps alternate.
+constexpr int kBwdTileBytes = 256 * 128;
+constexpr int kBwdSmemBytes = 1024 + 4 * kBwdTileBytes + 2 * 256 * 4 + 256;
+// TMEM column (relative to the S region) of the packed pairs of K step j (rows 16j .. 16j+15 of the B tile)
+__device__ constexpr int kBwdPCol[13] = {0, 8, 32, 40, 64, 72, 96, 112, 120, 144, 160, 168, 192};            // P (phase K), dS (phase Q)
+__device__ constexpr int kBwdDsCol[13] = {16, 24, 48, 56, 80, 88, 104, 128, 136, 152, 176, 184, 200};        // dS (phase K)
+
+__global__ void __launch_bounds__(kThreads, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
+                   const __nv_bfloat16* __restrict__ ctx, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv,
+                   int num_items) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + kBwdTileBytes;
+  uint8_t* sV = sK + kBwdTileBytes;
+  uint8_t* sDO = sV + kBwdTileBytes;
+  float* sLse = reinterpret_cast<float*>(sDO + kBwdTileBytes);     // [256] (+inf beyond 197: P = 0 there)
+  float* sDelta = sLse + 256;                                      // [256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
+  uint64_t* tiles_full = bars;
+  uint64_t* tiles_empty = bars + 1;
+  uint64_t* s_full = bars + 2;
+  uint64_t* p_full = bars + 3;
+  uint64_t* o_full = bars + 4;
+  uint64_t* d_read = bars + 5;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
+  if (warp == kSmWarps && lane == 0) {
+    tma_prefetch_desc(&tmQKV);
+    tma_prefetch_desc(&tmDO);
+    mbar_init(tiles_full, 1);
+    mbar_init(tiles_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, kSmWarps);
+    mbar_init(o_full, 1);
+    mbar_init(d_read, kSmWarps);
+    fence_mbar_init();
+  }
+  if (warp == kSmWarps + 1) {
+    tmem_alloc(tmem_ptr, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  constexpr uint32_t kRegB = 208;          // dP region; after the elementwise pass: output tiles at [208,272) and [272,336)
+
+  if (warp == kSmWarps) {
+    // ================================================================= TMA producer
+    if (lane == 0) {
+      for (int ii = 0; ii < n_items; ++ii) {
+        const int item = blockIdx.x + ii * gridDim.x;
+        const int b = item / kHeads, h = item % kHeads;
+        mbar_wait(tiles_empty, (ii & 1) ^ 1);
+        mbar_arrive_expect_tx(tiles_full, 4 * kBwdTileBytes);
+        tma_load_3d(sQ, &tmQKV, tiles_full, h * kHd, 0, b);
+        tma_load_3d(sK, &tmQKV, tiles_full, 192 + h * kHd, 0, b);
+        tma_load_3d(sV, &tmQKV, tiles_full, 384 + h * kHd, 0, b);
+        tma_load_3d(sDO, &tmDO, tiles_full, h * kHd, 0, b);
+      }
+    }
+  } else if (warp == kSmWarps + 1) {
+    // ================================================================= UMMA issuer (whole warp; one elected lane issues)
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, kKeysPad, 0, 0);   // [128 x 208] = A_tile B^T, both K-major
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, kHd, 0, 1);        // [128 x 64] = A(TMEM) B, B MN-major
+    const bool issuer = elect_one();
+    const uint32_t q_lo = umma_desc_lo(smem_u32(sQ)), k_lo = umma_desc_lo(smem_u32(sK));
+    const uint32_t v_lo = umma_desc_lo(smem_u32(sV)), do_lo = umma_desc_lo(smem_u32(sDO));
+    const uint32_t q_mn = umma_desc_lo(smem_u32(sQ), 8192), k_mn = umma_desc_lo(smem_u32(sK), 8192);
+    const uint32_t do_mn = umma_desc_lo(smem_u32(sDO), 8192);
+    for (int ii = 0; ii < n_items; ++ii) {
+      mbar_wait(tiles_full, ii & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int u = 0; u < 4; ++u) {
+        const int n = ii * 4 + u;
+        const int t = u & 1;                        // row tile
+        const bool phase_k = u < 2;
+        if (n > 0) {
+          mbar_wait(d_read, (n - 1) & 1);           // previous unit's output tiles are in registers: both regions are free
+          tc_fence_after();
+        }
+        if (issuer) {
+          const uint32_t a1 = (phase_k ? k_lo : q_lo) + t * (16384 >> 4), b1 = phase_k ? q_lo : k_lo;
+          const uint32_t a2 = (phase_k ? v_lo : do_lo) + t * (16384 >> 4), b2 = phase_k ? do_lo : v_lo;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_split<1>(tmem_base, a1 + 2 * k, b1 + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_split<1>(tmem_base + kRegB, a2 + 2 * k, b2 + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+          umma_commit(s_full);
+        }
+        __syncwarp();
+        mbar_wait(p_full, n & 1);
+        tc_fence_after();
+        if (issuer) {
+          if (phase_k) {
+#pragma unroll
+            for (int j = 0; j < 13; ++j)          // dV = P^T dO
+              umma_ts_bf16(tmem_base + kRegB, tmem_base + kBwdPCol[j], do_mn + j * (2048 >> 4), idesc_o, j != 0 ? 1u : 0u);
+#pragma unroll
+            for (int j = 0; j < 13; ++j)          // dK = dS^T Q
+              umma_ts_bf16(tmem_base + kRegB + 64, tmem_base + kBwdDsCol[j], q_mn + j * (2048 >> 4), idesc_o, j != 0 ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 13; ++j)          // dQ = dS K
+              umma_ts_bf16(tmem_base + kRegB, tmem_base + kBwdPCol[j], k_mn + j * (2048 >> 4), idesc_o, j != 0 ? 1u : 0u);
+          }
+          umma_commit(o_full);
+          if (u == 3) umma_commit(tiles_empty);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================================================================= elementwise + epilogue warps
+    const int quad = warp & 3, cg = warp >> 2;
+    const int row = quad * 32 + lane;
+    const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
+    const int a0 = (cg == 0) ? 0 : 16 + 48 * cg;      // slice start: 0, 64, 112, 160
+    const int w1 = (cg == 0) ? 32 : 16;               // width of the slice's second piece (the first is 32 wide)
+    const uint32_t tS = tmem_base + lane_sel, tB = tmem_base + kRegB + lane_sel;
+    const int tid = warp * 32 + lane;                 // 0..511
+    for (int ii = 0; ii < n_items; ++ii) {
+      const int item = blockIdx.x + ii * gridDim.x;
+      const int b = item / kHeads, h = item % kHeads;
+      mbar_wait(tiles_full, ii & 1);
+      // ---- delta[q] = dO[q,:] . O[q,:] and lse[q] -> shared (two threads per row)
+      {
+        const int r = tid >> 1, half = tid & 1;
+        float acc = 0.0f;
+        if (r < kTok) {
+          const uint4* op = reinterpret_cast<const uint4*>(ctx + (static_cast<size_t>(b) * kTok + r) * 192 + h * kHd + half * 32);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const uint4 o4 = op[c];
+            const uint4 d4 = *reinterpret_cast<const uint4*>(sDO + sw128_offset(r, half * 4 + c));
+            const uint32_t ow[4] = {o4.x, o4.y, o4.z, o4.w}, dw[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 of = unpack_bf16x2(ow[e]), df = unpack_bf16x2(dw[e]);
+              acc = fmaf(of.x, df.x, acc);
+              acc = fmaf(of.y, df.y, acc);
+            }
+          }
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (half == 0) {
+          sDelta[r] = acc;
+          sLse[r] = (r < kTok) ? lse[static_cast<size_t>(item) * kTok + r] : INFINITY;
+        }
+      }
+      named_bar_sync(1, kSmWarps * 32);
+
+#pragma unroll 1
+      for (int u = 0; u < 4; ++u) {
+        const int n = ii * 4 + u;
+        const int t = u & 1;
+        const bool phase_k = u < 2;
+        const int grow = t * 128 + row;                        // key (phase K) / query (phase Q) index of this thread's row
+        const bool warp_live = (t * 128 + quad * 32) < kTok;   // uniform over the warp
+        mbar_wait(s_full, n & 1);
+        tc_fence_after();
+        if (warp_live) {
+          const float lse_r = sLse[grow], delta_r = sDelta[grow];     // phase Q: this row's statistics
+          // P / dS of columns [a, a+W) from S and dP of the same columns; packed results go back over S[a, a+W)
+          auto piece = [&](int a, auto wtag) {
+            constexpr int W = decltype(wtag)::value;
+            float sv[W], dv[W];
+            if (W == 32) {
+              tmem_ld32(tS + a, *reinterpret_cast<float(*)[32]>(&sv[0]));
+              tmem_ld32(tB + a, *reinterpret_cast<float(*)[32]>(&dv[0]));
+            } else {
+              tmem_ld16f(tS + a, sv);
+              tmem_ld16f(tB + a, dv);
+            }
+            uint32_t pw[W / 2], dw[W / 2];
+#pragma unroll
+            for (int e = 0; e < W / 2; ++e) {
+              float l0, l1, d0, d1;
+              if (phase_k) {
+                const float2 l2 = *reinterpret_cast<const float2*>(&sLse[a + 2 * e]);
+                const float2 d2 = *reinterpret_cast<const float2*>(&sDelta[a + 2 * e]);
+                l0 = l2.x; l1 = l2.y; d0 = d2.x; d1 = d2.y;
+              } else {
+                l0 = l1 = lse_r; d0 = d1 = delta_r;
+              }
+              const float p0 = ex2_approx(fmaf(sv[2 * e], kScaleLog2e, -l0));
+              const float p1 = ex2_approx(fmaf(sv[2 * e + 1], kScaleLog2e, -l1));
+              float s0 = p0 * (dv[2 * e] - d0), s1 = p1 * (dv[2 * e + 1] - d1);
+              if (!phase_k) {                                 // padded keys: K rows are zero, P is not
+                if (a + 2 * e >= kTok) s0 = 0.0f;
+                if (a + 2 * e + 1 >= kTok) s1 = 0.0f;
+              }
+              pw[e] = pack_bf16x2(p0, p1);
+              dw[e] = pack_bf16x2(s0, s1);
+            }
+            if (phase_k) {
+              if (W == 32) { tmem_st16(tS + a, pw); tmem_st16(tS + a + 16, dw); }
+              else { tmem_st8(tS + a, pw); tmem_st8(tS + a + 8, dw); }
+            } else {
+              if (W == 32) tmem_st16(tS + a, dw); else tmem_st8(tS + a, dw);
+            }
+          };
+          piece(a0, std::integral_constant<int, 32>{});
+          if (cg == 0) piece(a0 + 32, std::integral_constant<int, 32>{});
+          else piece(a0 + 32, std::integral_constant<int, 16>{});
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+
+        // ---- output tiles of this unit
+        mbar_wait(o_full, n & 1);
+        tc_fence_after();
+        float o0[16], o1[16];
+        if (warp_live) {
+          tmem_ld16f(tmem_base + kRegB + cg * 16 + lane_sel, o0);
+          if (phase_k) tmem_ld16f(tmem_base + kRegB + 64 + cg * 16 + lane_sel, o1);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(d_read);
+        if (warp_live && grow < kTok) {
+          __nv_bfloat16* base = dqkv + (static_cast<size_t>(b) * kTok + grow) * 576 + h * kHd + cg * 16;
+          auto store16 = [&](__nv_bfloat16* dst, const float* v, float sc) {
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              d4[j] = make_uint4(pack_bf16x2(v[j * 8 + 0] * sc, v[j * 8 + 1] * sc), pack_bf16x2(v[j * 8 + 2] * sc, v[j * 8 + 3] * sc),
+                                 pack_bf16x2(v[j * 8 + 4] * sc, v[j * 8 + 5] * sc), pack_bf16x2(v[j * 8 + 6] * sc, v[j * 8 + 7] * sc));
+          };
+          if (phase_k) {
+            store16(base + 384, o0, 1.0f);          // dV
+            store16(base + 192, o1, 0.125f);        // dK
+          } else {
+            store16(base, o0, 0.125f);              // dQ
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kSmWarps + 1) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace
 
 static long long* g_attn_trace = nullptr;
@@ -333,5 +602,23 @@ int rvk_attention_fwd_launch(const void* qkv, void* ctx, float* lse, int batch, 
   const int items = batch * kHeads;
   const int grid = items < kNumSMsB200 ? items : kNumSMsB200;
   attn_fwd_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmQ, tmKV, static_cast<__nv_bfloat16*>(ctx), lse, items, g_attn_trace);
+  return rvk_launch_check();
+}
+
+int rvk_attention_bwd_tc_launch(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv, int batch,
+                                cudaStream_t stream) {
+  if (batch <= 0) return RVK_OK;
+  static bool configured = false;
+  if (!configured) {
+    RVK_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes));
+    configured = true;
+  }
+  CUtensorMap tmQKV, tmDO;
+  RVK_TRY(rvk_make_tmap_3d(&tmQKV, qkv, RVK_BF16, 576, kTok, batch, 576, int64_t(kTok) * 576, 64, 256));
+  RVK_TRY(rvk_make_tmap_3d(&tmDO, dctx, RVK_BF16, 192, kTok, batch, 192, int64_t(kTok) * 192, 64, 256));
+  const int items = batch * kHeads;
+  const int grid = items < kNumSMsB200 ? items : kNumSMsB200;
+  attn_bwd_tc_kernel<<<grid, kThreads, kBwdSmemBytes, stream>>>(tmQKV, tmDO, static_cast<const __nv_bfloat16*>(ctx), lse,
+                                                               static_cast<__nv_bfloat16*>(dqkv), items);
   return rvk_launch_check();
 }

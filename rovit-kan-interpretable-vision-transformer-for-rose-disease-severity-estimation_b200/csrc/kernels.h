@@ -48,6 +48,8 @@ int rvk_mlp_fused_launch(const MlpFusedArgs& a, cudaStream_t stream);
 int rvk_attention_fwd_launch(const void* qkv, void* ctx, float* lse, int batch, cudaStream_t stream);
 int rvk_attention_bwd_launch(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
                              int batch, cudaStream_t stream);
+int rvk_attention_bwd_tc_launch(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
+                                int batch, cudaStream_t stream);
 
 // ---- token-stream kernels (encoder_kernels.cu) -----------------------------------------------------
 int rvk_im2col_launch(const void* images, int images_bf16, void* patches_bf16, int batch, cudaStream_t stream);
