@@ -71,6 +71,33 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* w) {
 __device__ __forceinline__ void tmem_st2(uint32_t taddr, uint32_t w0, uint32_t w1) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(w0), "r"(w1) : "memory");
 }
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
 // D[tmem] (+)= A[tmem, K-major bf16 pairs] * B[smem desc]
 __device__ __forceinline__ void umma_ts_bf16(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -319,25 +346,27 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
 
 // =====================================================================================================================
-// Attention BACKWARD on tcgen05 (recompute from the saved log-sum-exp; no atomics, no stored probabilities).
-// Per (image, head) four work units, each one 128-row tile with the same two-GEMMs -> elementwise -> GEMM(s) shape as
-// the forward:
-//   phase K, key tile kt:    S^T = K_kt Q^T, dP^T = V_kt dO^T            (UMMA 128 x 208 x 64 each, TMEM columns [0,208) / [208,416))
-//                            P^T = exp2(S^T c - lse[q]),  dS^T = P^T o (dP^T - delta[q])      (sixteen warps, bf16 back into TMEM)
-//                            dV_kt = P^T dO,  dK_kt = scale dS^T Q       (A operand in TMEM, B = dO / Q tile read MN-major)
-//   phase Q, query tile qt:  S = Q_qt K^T, dP = dO_qt V^T;  dS = P o (dP - delta[row]);  dQ_qt = scale dS K
-// with delta[q] = sum_d dO[q,d] O[q,d].  A warp (quad, cg) owns 32 rows and a column slice that is a whole number of
-// UMMA K steps (64 / 48 / 48 / 48 columns); it walks its slice in pieces of 32 or 16 columns and writes the packed
-// bf16 results of a piece (P pairs, then dS pairs) over the very S columns it has just read, so no warp ever
-// overwrites scores another warp still needs and the whole dP region is free for the 64-column output tiles.  The issuer
-// pairs each 16-row K step of the B tile with the TMEM columns where that piece put it (kBwdPCol / kBwdDsCol).
-// Q, K, V, dO tiles are 256 rows (rows >= 197 zero-filled by TMA) so that each serves as M tile, N = 208 operand and
-// MN-major B operand alike.  One unit in flight (the regions are single-buffered): tensor pipe and softmax warps alternate.
+// Attention BACKWARD on tcgen05 (recompute from the saved log-sum-exp; no atomics, no stored probabilities, every
+// (key, query) pair visited ONCE).  Per (image, head) four work units (key tile kt) x (query tile qt), rows = keys:
+//     S^T = K_kt Q_qt^T,  dP^T = V_kt dO_qt^T         UMMA 128 x Nq x 64, Nq = 128 (qt = 0) or 80 (qt = 1: queries 128..207)
+//     P^T = exp2(S^T c - lse[q]),  dS^T = P^T o (dP^T - delta[q])               sixteen warps, one 32- or 16-column piece each
+//     dV_kt += P^T dO_qt,  dK_kt += dS^T Q_qt         A operand (bf16 pairs) in TMEM, B = dO / Q tile read MN-major
+//     dQ_qt += dS K_kt                                 A = dS^T tile in SHARED memory read MN-major (M = queries), B = K tile MN-major
+// with delta[q] = sum_d dO[q,d] O[q,d].  TMEM: S^T [0,128), dP^T [128,256), dV [256,320), dK [320,384), dQ_0 [384,448),
+// dQ_1 [448,512) -- all 512 columns.  A warp (quad, cg) owns 32 key rows and a column slice that is a whole number of
+// UMMA K steps; it writes the packed P pairs and dS pairs over the very S columns it has just read (no warp ever
+// overwrites scores another warp still needs) and the dS values a second time into the swizzled shared-memory tile for
+// the dQ product.  Q, K, V, dO tiles are 256 rows (rows >= 197 zero-filled by TMA) so that each serves as M tile,
+// N operand and MN-major B operand alike.  One unit in flight: tensor pipe and elementwise warps alternate.
 constexpr int kBwdTileBytes = 256 * 128;
-constexpr int kBwdSmemBytes = 1024 + 4 * kBwdTileBytes + 2 * 256 * 4 + 256;
-// TMEM column (relative to the S region) of the packed pairs of K step j (rows 16j .. 16j+15 of the B tile)
-__device__ constexpr int kBwdPCol[13] = {0, 8, 32, 40, 64, 72, 96, 112, 120, 144, 160, 168, 192};            // P (phase K), dS (phase Q)
-__device__ constexpr int kBwdDsCol[13] = {16, 24, 48, 56, 80, 88, 104, 128, 136, 152, 176, 184, 200};        // dS (phase K)
+constexpr int kBwdDsBytes = 2 * 16384;          // dS^T tile: two 64-query panels of [128 key rows x 128 B]
+constexpr int kBwdSmemBytes = 1024 + 4 * kBwdTileBytes + kBwdDsBytes + 2 * 256 * 4 + 256;
+// slice of column group cg: qt = 0: 32 columns at 32*cg;  qt = 1: cg 0 -> [0,32), cg 1..3 -> 16 columns at 16 + 16*cg.
+// K step j (queries 16j .. 16j+15 of the tile) -> TMEM column of its P pairs; its dS pairs sit half a slice further
+__device__ constexpr int kBwdPCol0[8] = {0, 8, 32, 40, 64, 72, 96, 104};
+__device__ constexpr int kBwdDsCol0[8] = {16, 24, 48, 56, 80, 88, 112, 120};
+__device__ constexpr int kBwdPCol1[5] = {0, 8, 32, 48, 64};
+__device__ constexpr int kBwdDsCol1[5] = {16, 24, 40, 56, 72};
 
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
@@ -349,16 +378,18 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   uint8_t* sK = sQ + kBwdTileBytes;
   uint8_t* sV = sK + kBwdTileBytes;
   uint8_t* sDO = sV + kBwdTileBytes;
-  float* sLse = reinterpret_cast<float*>(sDO + kBwdTileBytes);     // [256] (+inf beyond 197: P = 0 there)
+  uint8_t* sDS = sDO + kBwdTileBytes;
+  float* sLse = reinterpret_cast<float*>(sDS + kBwdDsBytes);       // [256] (+inf beyond 197: P = 0 there)
   float* sDelta = sLse + 256;                                      // [256]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
   uint64_t* tiles_full = bars;
   uint64_t* tiles_empty = bars + 1;
   uint64_t* s_full = bars + 2;
   uint64_t* p_full = bars + 3;
-  uint64_t* o_full = bars + 4;
-  uint64_t* d_read = bars + 5;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* o_full = bars + 4;       // the unit's three products have completed: S / dP regions and the dS tile are free
+  uint64_t* kv_read = bars + 5;      // dV / dK of a key tile are in registers
+  uint64_t* q_read = bars + 6;       // dQ of the item is in registers
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
@@ -370,7 +401,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     mbar_init(s_full, 1);
     mbar_init(p_full, kSmWarps);
     mbar_init(o_full, 1);
-    mbar_init(d_read, kSmWarps);
+    mbar_init(kv_read, kSmWarps);
+    mbar_init(q_read, kSmWarps);
     fence_mbar_init();
   }
   if (warp == kSmWarps + 1) {
@@ -381,7 +413,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  constexpr uint32_t kRegB = 208;          // dP region; after the elementwise pass: output tiles at [208,272) and [272,336)
+  constexpr uint32_t kColDP = 128, kColDV = 256, kColDK = 320, kColDQ = 384;
 
   if (warp == kSmWarps) {
     // ================================================================= TMA producer
@@ -399,49 +431,63 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     }
   } else if (warp == kSmWarps + 1) {
     // ================================================================= UMMA issuer (whole warp; one elected lane issues)
-    constexpr uint32_t idesc_s = umma_idesc_bf16(128, kKeysPad, 0, 0);   // [128 x 208] = A_tile B^T, both K-major
+    constexpr uint32_t idesc_s0 = umma_idesc_bf16(128, 128, 0, 0);       // [128 x Nq] = A_tile B^T, both K-major
+    constexpr uint32_t idesc_s1 = umma_idesc_bf16(128, 80, 0, 0);
     constexpr uint32_t idesc_o = umma_idesc_bf16(128, kHd, 0, 1);        // [128 x 64] = A(TMEM) B, B MN-major
+    constexpr uint32_t idesc_q = umma_idesc_bf16(128, kHd, 1, 1);        // [128 x 64] = A^T B, both MN-major (dQ)
     const bool issuer = elect_one();
     const uint32_t q_lo = umma_desc_lo(smem_u32(sQ)), k_lo = umma_desc_lo(smem_u32(sK));
     const uint32_t v_lo = umma_desc_lo(smem_u32(sV)), do_lo = umma_desc_lo(smem_u32(sDO));
     const uint32_t q_mn = umma_desc_lo(smem_u32(sQ), 8192), k_mn = umma_desc_lo(smem_u32(sK), 8192);
     const uint32_t do_mn = umma_desc_lo(smem_u32(sDO), 8192);
+    const uint32_t ds_mn = umma_desc_lo(smem_u32(sDS), 16384);           // two 64-query panels, 16 KB apart
     for (int ii = 0; ii < n_items; ++ii) {
       mbar_wait(tiles_full, ii & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int u = 0; u < 4; ++u) {
         const int n = ii * 4 + u;
-        const int t = u & 1;                        // row tile
-        const bool phase_k = u < 2;
+        const int kt = u >> 1, qt = u & 1;
         if (n > 0) {
-          mbar_wait(d_read, (n - 1) & 1);           // previous unit's output tiles are in registers: both regions are free
+          mbar_wait(o_full, (n - 1) & 1);             // S / dP regions and the dS tile are no longer read by the tensor pipe
           tc_fence_after();
         }
         if (issuer) {
-          const uint32_t a1 = (phase_k ? k_lo : q_lo) + t * (16384 >> 4), b1 = phase_k ? q_lo : k_lo;
-          const uint32_t a2 = (phase_k ? v_lo : do_lo) + t * (16384 >> 4), b2 = phase_k ? do_lo : v_lo;
+          const uint32_t idesc_s = qt == 0 ? idesc_s0 : idesc_s1;
+          const uint32_t ak = k_lo + kt * (16384 >> 4), av = v_lo + kt * (16384 >> 4);
+          const uint32_t bq = q_lo + qt * (16384 >> 4), bd = do_lo + qt * (16384 >> 4);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_split<1>(tmem_base, a1 + 2 * k, b1 + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_f16_split<1>(tmem_base, ak + 2 * k, bq + 2 * k, idesc_s, k != 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_split<1>(tmem_base + kRegB, a2 + 2 * k, b2 + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) umma_f16_split<1>(tmem_base + kColDP, av + 2 * k, bd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
           umma_commit(s_full);
         }
         __syncwarp();
+        // the accumulators this unit starts must have been read out by the epilogue of the previous key tile / item
+        if (qt == 0 && n >= 2) { mbar_wait(kv_read, ((n >> 1) - 1) & 1); }
+        if (u == 0 && ii > 0) { mbar_wait(q_read, (ii - 1) & 1); }
         mbar_wait(p_full, n & 1);
         tc_fence_after();
         if (issuer) {
-          if (phase_k) {
+          const int nj = qt == 0 ? 8 : 5;
+          const uint32_t row0 = static_cast<uint32_t>(qt * 128) * (128 >> 4);     // B tiles: first query row of the tile
 #pragma unroll
-            for (int j = 0; j < 13; ++j)          // dV = P^T dO
-              umma_ts_bf16(tmem_base + kRegB, tmem_base + kBwdPCol[j], do_mn + j * (2048 >> 4), idesc_o, j != 0 ? 1u : 0u);
+          for (int j = 0; j < 8; ++j) {           // dV += P^T dO
+            if (j < nj)
+              umma_ts_bf16(tmem_base + kColDV, tmem_base + (qt == 0 ? kBwdPCol0[j] : kBwdPCol1[j < 5 ? j : 0]),
+                           do_mn + row0 + j * (2048 >> 4), idesc_o, (qt | j) != 0 ? 1u : 0u);
+          }
 #pragma unroll
-            for (int j = 0; j < 13; ++j)          // dK = dS^T Q
-              umma_ts_bf16(tmem_base + kRegB + 64, tmem_base + kBwdDsCol[j], q_mn + j * (2048 >> 4), idesc_o, j != 0 ? 1u : 0u);
-          } else {
+          for (int j = 0; j < 8; ++j) {           // dK += dS^T Q
+            if (j < nj)
+              umma_ts_bf16(tmem_base + kColDK, tmem_base + (qt == 0 ? kBwdDsCol0[j] : kBwdDsCol1[j < 5 ? j : 0]),
+                           q_mn + row0 + j * (2048 >> 4), idesc_o, (qt | j) != 0 ? 1u : 0u);
+          }
 #pragma unroll
-            for (int j = 0; j < 13; ++j)          // dQ = dS K
-              umma_ts_bf16(tmem_base + kRegB, tmem_base + kBwdPCol[j], k_mn + j * (2048 >> 4), idesc_o, j != 0 ? 1u : 0u);
+          for (int k = 0; k < 8; ++k) {           // dQ_qt += dS K_kt: 16 key rows per step
+            const uint64_t ad = (static_cast<uint64_t>(kUmmaDescHiSw128) << 32) | (ds_mn + k * (2048 >> 4));
+            const uint64_t bd2 = (static_cast<uint64_t>(kUmmaDescHiSw128) << 32) | (k_mn + (kt * 128 * 128 >> 4) + k * (2048 >> 4));
+            umma_bf16(tmem_base + kColDQ + qt * 64, ad, bd2, idesc_q, (kt | k) != 0 ? 1u : 0u);
           }
           umma_commit(o_full);
           if (u == 3) umma_commit(tiles_empty);
@@ -449,15 +495,21 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         __syncwarp();
       }
     }
+    if (n_items > 0) mbar_wait(o_full, (n_items * 4 - 1) & 1);
   } else {
     // ================================================================= elementwise + epilogue warps
     const int quad = warp & 3, cg = warp >> 2;
     const int row = quad * 32 + lane;
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
-    const int a0 = (cg == 0) ? 0 : 16 + 48 * cg;      // slice start: 0, 64, 112, 160
-    const int w1 = (cg == 0) ? 32 : 16;               // width of the slice's second piece (the first is 32 wide)
-    const uint32_t tS = tmem_base + lane_sel, tB = tmem_base + kRegB + lane_sel;
+    const uint32_t tS = tmem_base + lane_sel, tB = tmem_base + kColDP + lane_sel;
     const int tid = warp * 32 + lane;                 // 0..511
+    auto store16 = [&](__nv_bfloat16* dst, const float* v, float sc) {
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        d4[j] = make_uint4(pack_bf16x2(v[j * 8 + 0] * sc, v[j * 8 + 1] * sc), pack_bf16x2(v[j * 8 + 2] * sc, v[j * 8 + 3] * sc),
+                           pack_bf16x2(v[j * 8 + 4] * sc, v[j * 8 + 5] * sc), pack_bf16x2(v[j * 8 + 6] * sc, v[j * 8 + 7] * sc));
+    };
     for (int ii = 0; ii < n_items; ++ii) {
       const int item = blockIdx.x + ii * gridDim.x;
       const int b = item / kHeads, h = item % kHeads;
@@ -492,87 +544,97 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 #pragma unroll 1
       for (int u = 0; u < 4; ++u) {
         const int n = ii * 4 + u;
-        const int t = u & 1;
-        const bool phase_k = u < 2;
-        const int grow = t * 128 + row;                        // key (phase K) / query (phase Q) index of this thread's row
-        const bool warp_live = (t * 128 + quad * 32) < kTok;   // uniform over the warp
+        const int kt = u >> 1, qt = u & 1;
+        const int key = kt * 128 + row;
+        const bool warp_live = (kt * 128 + quad * 32) < kTok;   // uniform over the warp: some key row of the warp is real
+        // this warp's query columns of the unit: [a, a + W) of the tile
+        const int a = (qt == 0) ? 32 * cg : (cg == 0 ? 0 : 16 + 16 * cg);
+        const bool wide = (qt == 0) || (cg == 0);
         mbar_wait(s_full, n & 1);
         tc_fence_after();
         if (warp_live) {
-          const float lse_r = sLse[grow], delta_r = sDelta[grow];     // phase Q: this row's statistics
-          // P / dS of columns [a, a+W) from S and dP of the same columns; packed results go back over S[a, a+W)
-          auto piece = [&](int a, auto wtag) {
+          // P / dS of columns [a, a+W): packed P pairs over S[a, a+W/2), dS pairs over S[a+W/2, a+W), dS also into the smem tile
+          auto piece = [&](auto wtag) {
             constexpr int W = decltype(wtag)::value;
             float sv[W], dv[W];
             if (W == 32) {
-              tmem_ld32(tS + a, *reinterpret_cast<float(*)[32]>(&sv[0]));
-              tmem_ld32(tB + a, *reinterpret_cast<float(*)[32]>(&dv[0]));
+              tmem_ld32_nowait(tS + a, *reinterpret_cast<float(*)[32]>(&sv[0]));
+              tmem_ld32_nowait(tB + a, *reinterpret_cast<float(*)[32]>(&dv[0]));
             } else {
-              tmem_ld16f(tS + a, sv);
-              tmem_ld16f(tB + a, dv);
+              tmem_ld16_nowait(tS + a, sv);
+              tmem_ld16_nowait(tB + a, dv);
             }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             uint32_t pw[W / 2], dw[W / 2];
+            const int q0 = qt * 128 + a;
 #pragma unroll
-            for (int e = 0; e < W / 2; ++e) {
-              float l0, l1, d0, d1;
-              if (phase_k) {
-                const float2 l2 = *reinterpret_cast<const float2*>(&sLse[a + 2 * e]);
-                const float2 d2 = *reinterpret_cast<const float2*>(&sDelta[a + 2 * e]);
-                l0 = l2.x; l1 = l2.y; d0 = d2.x; d1 = d2.y;
-              } else {
-                l0 = l1 = lse_r; d0 = d1 = delta_r;
-              }
-              const float p0 = ex2_approx(fmaf(sv[2 * e], kScaleLog2e, -l0));
-              const float p1 = ex2_approx(fmaf(sv[2 * e + 1], kScaleLog2e, -l1));
-              float s0 = p0 * (dv[2 * e] - d0), s1 = p1 * (dv[2 * e + 1] - d1);
-              if (!phase_k) {                                 // padded keys: K rows are zero, P is not
-                if (a + 2 * e >= kTok) s0 = 0.0f;
-                if (a + 2 * e + 1 >= kTok) s1 = 0.0f;
-              }
-              pw[e] = pack_bf16x2(p0, p1);
-              dw[e] = pack_bf16x2(s0, s1);
+            for (int e = 0; e < W / 4; ++e) {
+              const float4 l4 = *reinterpret_cast<const float4*>(&sLse[q0 + 4 * e]);
+              const float4 d4 = *reinterpret_cast<const float4*>(&sDelta[q0 + 4 * e]);
+              const float p0 = ex2_approx(fmaf(sv[4 * e + 0], kScaleLog2e, -l4.x));
+              const float p1 = ex2_approx(fmaf(sv[4 * e + 1], kScaleLog2e, -l4.y));
+              const float p2 = ex2_approx(fmaf(sv[4 * e + 2], kScaleLog2e, -l4.z));
+              const float p3 = ex2_approx(fmaf(sv[4 * e + 3], kScaleLog2e, -l4.w));
+              pw[2 * e] = pack_bf16x2(p0, p1);
+              pw[2 * e + 1] = pack_bf16x2(p2, p3);
+              dw[2 * e] = pack_bf16x2(p0 * (dv[4 * e + 0] - d4.x), p1 * (dv[4 * e + 1] - d4.y));
+              dw[2 * e + 1] = pack_bf16x2(p2 * (dv[4 * e + 2] - d4.z), p3 * (dv[4 * e + 3] - d4.w));
             }
-            if (phase_k) {
-              if (W == 32) { tmem_st16(tS + a, pw); tmem_st16(tS + a + 16, dw); }
-              else { tmem_st8(tS + a, pw); tmem_st8(tS + a + 8, dw); }
-            } else {
-              if (W == 32) tmem_st16(tS + a, dw); else tmem_st8(tS + a, dw);
+            if (W == 32) { tmem_st16(tS + a, pw); tmem_st16(tS + a + 16, dw); }
+            else { tmem_st8(tS + a, pw); tmem_st8(tS + a + 8, dw); }
+            // dS^T tile for the dQ product: row = key, 16-byte chunks of 8 queries, panel = 64 queries
+#pragma unroll
+            for (int c = 0; c < W / 8; ++c) {
+              const int qc = a + 8 * c;                 // first query (within the tile) of this chunk
+              *reinterpret_cast<uint4*>(sDS + (qc >> 6) * 16384 + sw128_offset(row, (qc >> 3) & 7)) =
+                  make_uint4(dw[4 * c], dw[4 * c + 1], dw[4 * c + 2], dw[4 * c + 3]);
             }
           };
-          piece(a0, std::integral_constant<int, 32>{});
-          if (cg == 0) piece(a0 + 32, std::integral_constant<int, 32>{});
-          else piece(a0 + 32, std::integral_constant<int, 16>{});
+          if (wide) piece(std::integral_constant<int, 32>{});
+          else piece(std::integral_constant<int, 16>{});
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        } else {
+          // no real key in these 32 rows: their dS rows must still be finite zeros for the dQ product (K rows are zero, 0 * NaN is not)
+          const int W = wide ? 32 : 16;
+          for (int c = 0; c < W / 8; ++c) {
+            const int qc = a + 8 * c;
+            *reinterpret_cast<uint4*>(sDS + (qc >> 6) * 16384 + sw128_offset(row, (qc >> 3) & 7)) = make_uint4(0u, 0u, 0u, 0u);
+          }
         }
+        fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(p_full);
 
-        // ---- output tiles of this unit
-        mbar_wait(o_full, n & 1);
-        tc_fence_after();
-        float o0[16], o1[16];
-        if (warp_live) {
-          tmem_ld16f(tmem_base + kRegB + cg * 16 + lane_sel, o0);
-          if (phase_k) tmem_ld16f(tmem_base + kRegB + 64 + cg * 16 + lane_sel, o1);
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(d_read);
-        if (warp_live && grow < kTok) {
-          __nv_bfloat16* base = dqkv + (static_cast<size_t>(b) * kTok + grow) * 576 + h * kHd + cg * 16;
-          auto store16 = [&](__nv_bfloat16* dst, const float* v, float sc) {
-            uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-              d4[j] = make_uint4(pack_bf16x2(v[j * 8 + 0] * sc, v[j * 8 + 1] * sc), pack_bf16x2(v[j * 8 + 2] * sc, v[j * 8 + 3] * sc),
-                                 pack_bf16x2(v[j * 8 + 4] * sc, v[j * 8 + 5] * sc), pack_bf16x2(v[j * 8 + 6] * sc, v[j * 8 + 7] * sc));
-          };
-          if (phase_k) {
-            store16(base + 384, o0, 1.0f);          // dV
-            store16(base + 192, o1, 0.125f);        // dK
-          } else {
-            store16(base, o0, 0.125f);              // dQ
+        // ---- finished accumulators
+        if (qt == 1) {
+          mbar_wait(o_full, n & 1);
+          tc_fence_after();
+          // dV, dK of key tile kt
+          float o0[16];
+          if (warp_live) tmem_ld16f(tmem_base + kColDV + cg * 16 + lane_sel, o0);
+          __nv_bfloat16* base = dqkv + (static_cast<size_t>(b) * kTok + (key < kTok ? key : 0)) * 576 + h * kHd + cg * 16;
+          if (warp_live && key < kTok) store16(base + 384, o0, 1.0f);
+          if (warp_live) tmem_ld16f(tmem_base + kColDK + cg * 16 + lane_sel, o0);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(kv_read);
+          if (warp_live && key < kTok) store16(base + 192, o0, 0.125f);
+          if (kt == 1) {
+            // dQ of both query tiles (rows = queries now)
+#pragma unroll 1
+            for (int t2 = 0; t2 < 2; ++t2) {
+              const int q = t2 * 128 + row;
+              const bool live_q = (t2 * 128 + quad * 32) < kTok;
+              if (live_q) tmem_ld16f(tmem_base + kColDQ + t2 * 64 + cg * 16 + lane_sel, o0);
+              if (t2 == 1) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(q_read);
+              }
+              if (live_q && q < kTok)
+                store16(dqkv + (static_cast<size_t>(b) * kTok + q) * 576 + h * kHd + cg * 16, o0, 0.125f);
+            }
           }
         }
       }

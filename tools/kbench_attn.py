@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""Micro-benchmark (and optional clock trace) of the attention forward kernel.  usage: kbench_attn.py [images=1024]"""
+"""Micro-benchmark (and optional clock trace) of the attention forward kernel, or of the backward kernel.
+usage: kbench_attn.py [images=1024] [bwd]   (RVK_ATTN_BWD_SIMT=1: the mma.sync backward)"""
 import os
 import sys
 
@@ -13,10 +14,19 @@ M = images * 197
 qkv = (torch.randn(M, 576, device='cuda') * 1.0).to(torch.bfloat16)
 ctx = torch.empty(M, 192, device='cuda', dtype=torch.bfloat16)
 s = torch.cuda.current_stream().cuda_stream
+bwd = len(sys.argv) > 2 and sys.argv[2] == 'bwd'
+if bwd:
+    lse = torch.zeros(images, 3, 197, device='cuda')
+    dctx = torch.randn(M, 192, device='cuda').to(torch.bfloat16)
+    dqkv = torch.empty(M, 576, device='cuda', dtype=torch.bfloat16)
+    _lib.call('rvk_attention_forward', qkv.data_ptr(), ctx.data_ptr(), lse.data_ptr(), images, s)
 
 
 def run():
-    _lib.call('rvk_attention_forward', qkv.data_ptr(), ctx.data_ptr(), 0, images, s)
+    if bwd:
+        _lib.call('rvk_attention_backward', qkv.data_ptr(), ctx.data_ptr(), dctx.data_ptr(), lse.data_ptr(), dqkv.data_ptr(), images, s)
+    else:
+        _lib.call('rvk_attention_forward', qkv.data_ptr(), ctx.data_ptr(), 0, images, s)
 
 
 for _ in range(3):
@@ -29,6 +39,9 @@ for _ in range(10):
 e1.record()
 torch.cuda.synchronize()
 us = e0.elapsed_time(e1) * 100
+if bwd:
+    print(f'attention bwd {images} images: {us:.1f} us/launch  {images * 3 * 10 * 197 * 197 * 64 / us / 1e6:.1f} TFLOP/s (5 algorithmic GEMMs)')
+    sys.exit(0)
 print(f'attention fwd {images} images: {us:.1f} us/launch  {images * 3 * 4 * 197 * 197 * 64 / us / 1e6:.1f} TFLOP/s')
 if os.environ.get('ATTN_TRACE'):
     tr = torch.zeros(4 * 512, dtype=torch.int64, device='cuda')
