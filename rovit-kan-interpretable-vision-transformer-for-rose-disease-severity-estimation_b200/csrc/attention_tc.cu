@@ -350,28 +350,28 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // (key, query) pair visited ONCE).  Per (image, head) four work units (key tile kt) x (query tile qt), rows = keys:
 //     S^T = K_kt Q_qt^T,  dP^T = V_kt dO_qt^T         UMMA 128 x Nq x 64, Nq = 128 (qt = 0) or 80 (qt = 1: queries 128..207)
 //     P^T = exp2(S^T c - lse[q]),  dS^T = P^T o (dP^T - delta[q])               sixteen warps, one 32- or 16-column piece each
-//     dV_kt += P^T dO_qt,  dK_kt += dS^T Q_qt         A operand (bf16 pairs) in TMEM, B = dO / Q tile read MN-major
-//     dQ_qt += dS K_kt                                 A = dS^T tile in SHARED memory read MN-major (M = queries), B = K tile MN-major
+//     dV_kt += P^T dO_qt                               A operand (bf16 pairs) in TMEM, B = dO tile read MN-major
+//     dK_kt += dS^T Q_qt,  dQ_qt += dS K_kt            A = the dS^T tile in SHARED memory, read K-major (M = keys) for dK and
+//                                                      MN-major (M = queries) for dQ; B = Q / K tile read MN-major
 // with delta[q] = sum_d dO[q,d] O[q,d].  TMEM: S^T [0,128), dP^T [128,256), dV [256,320), dK [320,384), dQ_0 [384,448),
 // dQ_1 [448,512) -- all 512 columns.  A warp (quad, cg) owns 32 key rows and a column slice that is a whole number of
-// UMMA K steps; it writes the packed P pairs and dS pairs over the very S columns it has just read (no warp ever
-// overwrites scores another warp still needs) and the dS values a second time into the swizzled shared-memory tile for
-// the dQ product.  Q, K, V, dO tiles are 256 rows (rows >= 197 zero-filled by TMA) so that each serves as M tile,
-// N operand and MN-major B operand alike.  One unit in flight: tensor pipe and elementwise warps alternate.
+// UMMA K steps; it writes the packed P pairs over the very dP columns it has just read (no warp ever overwrites values
+// another warp still needs) and the dS values into a swizzled shared-memory tile (double-buffered).  With no operand
+// left in the S region, S^T of the NEXT unit is issued right behind dV, and dK / dQ of this unit run while the
+// elementwise warps already work on the next one.  Q, K, V, dO tiles are 256 rows (rows >= 197 zero-filled by TMA) so that each serves as M tile,
+// N operand and MN-major B operand alike.
 constexpr int kBwdTileBytes = 256 * 128;
 constexpr int kBwdDsBytes = 2 * 16384;          // dS^T tile: two 64-query panels of [128 key rows x 128 B]
-constexpr int kBwdSmemBytes = 1024 + 4 * kBwdTileBytes + kBwdDsBytes + 2 * 256 * 4 + 256;
+constexpr int kBwdSmemBytes = 1024 + 4 * kBwdTileBytes + 2 * kBwdDsBytes + 4 * 256 * 4 + 256;
 // slice of column group cg: qt = 0: 32 columns at 32*cg;  qt = 1: cg 0 -> [0,32), cg 1..3 -> 16 columns at 16 + 16*cg.
-// K step j (queries 16j .. 16j+15 of the tile) -> TMEM column of its P pairs; its dS pairs sit half a slice further
+// K step j (queries 16j .. 16j+15 of the tile) -> column (inside the dP region) of its packed P pairs
 __device__ constexpr int kBwdPCol0[8] = {0, 8, 32, 40, 64, 72, 96, 104};
-__device__ constexpr int kBwdDsCol0[8] = {16, 24, 48, 56, 80, 88, 112, 120};
 __device__ constexpr int kBwdPCol1[5] = {0, 8, 32, 48, 64};
-__device__ constexpr int kBwdDsCol1[5] = {16, 24, 40, 56, 72};
 
 __global__ void __launch_bounds__(kThreads, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO,
-                   const __nv_bfloat16* __restrict__ ctx, const float* __restrict__ lse, __nv_bfloat16* __restrict__ dqkv,
-                   int num_items) {
+                   const __nv_bfloat16* __restrict__ ctx, const __nv_bfloat16* __restrict__ dctx, const float* __restrict__ lse,
+                   __nv_bfloat16* __restrict__ dqkv, int num_items) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;
@@ -379,14 +379,14 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   uint8_t* sV = sK + kBwdTileBytes;
   uint8_t* sDO = sV + kBwdTileBytes;
   uint8_t* sDS = sDO + kBwdTileBytes;
-  float* sLse = reinterpret_cast<float*>(sDS + kBwdDsBytes);       // [256] (+inf beyond 197: P = 0 there)
-  float* sDelta = sLse + 256;                                      // [256]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 256);
+  float* sLse = reinterpret_cast<float*>(sDS + 2 * kBwdDsBytes);   // [2][256] per item parity (+inf beyond 197: P = 0 there)
+  float* sDelta = sLse + 512;                                      // [2][256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 512);
   uint64_t* tiles_full = bars;
   uint64_t* tiles_empty = bars + 1;
   uint64_t* s_full = bars + 2;
   uint64_t* p_full = bars + 3;
-  uint64_t* o_full = bars + 4;       // the unit's three products have completed: S / dP regions and the dS tile are free
+  uint64_t* o_full = bars + 4;       // the unit's three products have completed (accumulators, dS buffer)
   uint64_t* kv_read = bars + 5;      // dV / dK of a key tile are in registers
   uint64_t* q_read = bars + 6;       // dQ of the item is in registers
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
@@ -433,69 +433,87 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     // ================================================================= UMMA issuer (whole warp; one elected lane issues)
     constexpr uint32_t idesc_s0 = umma_idesc_bf16(128, 128, 0, 0);       // [128 x Nq] = A_tile B^T, both K-major
     constexpr uint32_t idesc_s1 = umma_idesc_bf16(128, 80, 0, 0);
-    constexpr uint32_t idesc_o = umma_idesc_bf16(128, kHd, 0, 1);        // [128 x 64] = A(TMEM) B, B MN-major
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, kHd, 0, 1);        // [128 x 64] = A B, A K-major (TMEM or smem), B MN-major
     constexpr uint32_t idesc_q = umma_idesc_bf16(128, kHd, 1, 1);        // [128 x 64] = A^T B, both MN-major (dQ)
     const bool issuer = elect_one();
     const uint32_t q_lo = umma_desc_lo(smem_u32(sQ)), k_lo = umma_desc_lo(smem_u32(sK));
     const uint32_t v_lo = umma_desc_lo(smem_u32(sV)), do_lo = umma_desc_lo(smem_u32(sDO));
     const uint32_t q_mn = umma_desc_lo(smem_u32(sQ), 8192), k_mn = umma_desc_lo(smem_u32(sK), 8192);
     const uint32_t do_mn = umma_desc_lo(smem_u32(sDO), 8192);
-    const uint32_t ds_mn = umma_desc_lo(smem_u32(sDS), 16384);           // two 64-query panels, 16 KB apart
-    for (int ii = 0; ii < n_items; ++ii) {
-      mbar_wait(tiles_full, ii & 1);
+    const uint32_t ds_k0 = umma_desc_lo(smem_u32(sDS));                  // K-major view (dK): rows = keys
+    const uint32_t ds_mn0 = umma_desc_lo(smem_u32(sDS), 16384);          // MN-major view (dQ): two 64-query panels, 16 KB apart
+    const int total = n_items * 4;
+    // S^T and dP^T of unit (kt, qt)
+    auto issue_s = [&](int kt, int qt) {
+      const uint32_t idesc_s = qt == 0 ? idesc_s0 : idesc_s1;
+      const uint32_t ak = k_lo + kt * (16384 >> 4), bq = q_lo + qt * (16384 >> 4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_f16_split<1>(tmem_base, ak + 2 * k, bq + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+    };
+    auto issue_dp = [&](int kt, int qt) {
+      const uint32_t idesc_s = qt == 0 ? idesc_s0 : idesc_s1;
+      const uint32_t av = v_lo + kt * (16384 >> 4), bd = do_lo + qt * (16384 >> 4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_f16_split<1>(tmem_base + kColDP, av + 2 * k, bd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+    };
+    if (n_items > 0) {
+      mbar_wait(tiles_full, 0);
       tc_fence_after();
+      if (issuer) { issue_s(0, 0); issue_dp(0, 0); umma_commit(s_full); }
+      __syncwarp();
+    }
 #pragma unroll 1
-      for (int u = 0; u < 4; ++u) {
-        const int n = ii * 4 + u;
-        const int kt = u >> 1, qt = u & 1;
-        if (n > 0) {
-          mbar_wait(o_full, (n - 1) & 1);             // S / dP regions and the dS tile are no longer read by the tensor pipe
-          tc_fence_after();
+    for (int n = 0; n < total; ++n) {
+      const int ii = n >> 2, u = n & 3;
+      const int kt = u >> 1, qt = u & 1;
+      const int nj = qt == 0 ? 8 : 5;
+      const uint32_t row0 = static_cast<uint32_t>(qt * 128) * (128 >> 4);     // B tiles: first query row of the tile
+      const uint32_t dsb = static_cast<uint32_t>(n & 1) * (kBwdDsBytes >> 4);
+      // the accumulators this unit starts must have been read out by the epilogue of the previous key tile / item
+      if (qt == 0 && n >= 2) { mbar_wait(kv_read, ((n >> 1) - 1) & 1); }
+      if (u == 0 && ii > 0) { mbar_wait(q_read, (ii - 1) & 1); }
+      mbar_wait(p_full, n & 1);
+      tc_fence_after();
+      const bool same_item = u < 3;             // the next unit works on the tiles that are already in shared memory
+      if (issuer) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {           // dV += P^T dO   (P pairs sit in the dP region)
+          if (j < nj)
+            umma_ts_bf16(tmem_base + kColDV, tmem_base + kColDP + (qt == 0 ? kBwdPCol0[j] : kBwdPCol1[j < 5 ? j : 0]),
+                         do_mn + row0 + j * (2048 >> 4), idesc_o, (qt | j) != 0 ? 1u : 0u);
         }
-        if (issuer) {
-          const uint32_t idesc_s = qt == 0 ? idesc_s0 : idesc_s1;
-          const uint32_t ak = k_lo + kt * (16384 >> 4), av = v_lo + kt * (16384 >> 4);
-          const uint32_t bq = q_lo + qt * (16384 >> 4), bd = do_lo + qt * (16384 >> 4);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_split<1>(tmem_base, ak + 2 * k, bq + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_split<1>(tmem_base + kColDP, av + 2 * k, bd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        if (same_item) {
+          // next unit's S^T / dP^T right behind dV: tcgen05.mma instructions of one thread execute in issue order
+          // (pipelined), so dP^T cannot overwrite the P pairs before dV has read them; the S region holds no operand
+          issue_s((u + 1) >> 1, (u + 1) & 1);
+          issue_dp((u + 1) >> 1, (u + 1) & 1);
           umma_commit(s_full);
         }
-        __syncwarp();
-        // the accumulators this unit starts must have been read out by the epilogue of the previous key tile / item
-        if (qt == 0 && n >= 2) { mbar_wait(kv_read, ((n >> 1) - 1) & 1); }
-        if (u == 0 && ii > 0) { mbar_wait(q_read, (ii - 1) & 1); }
-        mbar_wait(p_full, n & 1);
-        tc_fence_after();
-        if (issuer) {
-          const int nj = qt == 0 ? 8 : 5;
-          const uint32_t row0 = static_cast<uint32_t>(qt * 128) * (128 >> 4);     // B tiles: first query row of the tile
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {           // dV += P^T dO
-            if (j < nj)
-              umma_ts_bf16(tmem_base + kColDV, tmem_base + (qt == 0 ? kBwdPCol0[j] : kBwdPCol1[j < 5 ? j : 0]),
-                           do_mn + row0 + j * (2048 >> 4), idesc_o, (qt | j) != 0 ? 1u : 0u);
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {           // dK += dS^T Q
-            if (j < nj)
-              umma_ts_bf16(tmem_base + kColDK, tmem_base + (qt == 0 ? kBwdDsCol0[j] : kBwdDsCol1[j < 5 ? j : 0]),
-                           q_mn + row0 + j * (2048 >> 4), idesc_o, (qt | j) != 0 ? 1u : 0u);
-          }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {           // dQ_qt += dS K_kt: 16 key rows per step
-            const uint64_t ad = (static_cast<uint64_t>(kUmmaDescHiSw128) << 32) | (ds_mn + k * (2048 >> 4));
-            const uint64_t bd2 = (static_cast<uint64_t>(kUmmaDescHiSw128) << 32) | (k_mn + (kt * 128 * 128 >> 4) + k * (2048 >> 4));
-            umma_bf16(tmem_base + kColDQ + qt * 64, ad, bd2, idesc_q, (kt | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(o_full);
-          if (u == 3) umma_commit(tiles_empty);
+        for (int j = 0; j < 8; ++j) {           // dK += dS^T Q   (dS^T tile K-major: 16 queries = 32 bytes of a row, 64 per panel)
+          if (j < nj)
+            umma_f16_split<1>(tmem_base + kColDK, ds_k0 + dsb + (j >> 2) * (16384 >> 4) + (j & 3) * 2, q_mn + row0 + j * (2048 >> 4),
+                              idesc_o, (qt | j) != 0 ? 1u : 0u);
         }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {           // dQ_qt += dS K_kt: 16 key rows per step
+          const uint64_t ad = (static_cast<uint64_t>(kUmmaDescHiSw128) << 32) | (ds_mn0 + dsb + k * (2048 >> 4));
+          const uint64_t bd2 = (static_cast<uint64_t>(kUmmaDescHiSw128) << 32) | (k_mn + (kt * 128 * 128 >> 4) + k * (2048 >> 4));
+          umma_bf16(tmem_base + kColDQ + qt * 64, ad, bd2, idesc_q, (kt | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(o_full);
+        if (u == 3) umma_commit(tiles_empty);
+      }
+      __syncwarp();
+      if (!same_item && ii + 1 < n_items) {
+        // next item: its tiles replace the ones the products above still read (tiles_full implies they have completed)
+        mbar_wait(tiles_full, (ii + 1) & 1);
+        tc_fence_after();
+        if (issuer) { issue_s(0, 0); issue_dp(0, 0); umma_commit(s_full); }
         __syncwarp();
       }
     }
-    if (n_items > 0) mbar_wait(o_full, (n_items * 4 - 1) & 1);
+    if (total > 0) mbar_wait(o_full, (total - 1) & 1);
   } else {
     // ================================================================= elementwise + epilogue warps
     const int quad = warp & 3, cg = warp >> 2;
@@ -510,134 +528,153 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         d4[j] = make_uint4(pack_bf16x2(v[j * 8 + 0] * sc, v[j * 8 + 1] * sc), pack_bf16x2(v[j * 8 + 2] * sc, v[j * 8 + 3] * sc),
                            pack_bf16x2(v[j * 8 + 4] * sc, v[j * 8 + 5] * sc), pack_bf16x2(v[j * 8 + 6] * sc, v[j * 8 + 7] * sc));
     };
-    for (int ii = 0; ii < n_items; ++ii) {
+    // delta[q] = dO[q,:] . O[q,:] and lse[q] of item `ii` -> shared buffer ii & 1 (two threads per row, straight from global
+    // memory: independent of the tile loads, so it runs while the tensor pipe still works on the previous item)
+    auto prepass = [&](int ii) {
       const int item = blockIdx.x + ii * gridDim.x;
       const int b = item / kHeads, h = item % kHeads;
-      mbar_wait(tiles_full, ii & 1);
-      // ---- delta[q] = dO[q,:] . O[q,:] and lse[q] -> shared (two threads per row)
-      {
-        const int r = tid >> 1, half = tid & 1;
-        float acc = 0.0f;
-        if (r < kTok) {
-          const uint4* op = reinterpret_cast<const uint4*>(ctx + (static_cast<size_t>(b) * kTok + r) * 192 + h * kHd + half * 32);
+      const int r = tid >> 1, half = tid & 1;
+      float acc = 0.0f;
+      if (r < kTok) {
+        const size_t off = (static_cast<size_t>(b) * kTok + r) * 192 + h * kHd + half * 32;
+        const uint4* op = reinterpret_cast<const uint4*>(ctx + off);
+        const uint4* dp = reinterpret_cast<const uint4*>(dctx + off);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint4 o4 = op[c];
-            const uint4 d4 = *reinterpret_cast<const uint4*>(sDO + sw128_offset(r, half * 4 + c));
-            const uint32_t ow[4] = {o4.x, o4.y, o4.z, o4.w}, dw[4] = {d4.x, d4.y, d4.z, d4.w};
+        for (int c = 0; c < 4; ++c) {
+          const uint4 o4 = op[c], d4 = dp[c];
+          const uint32_t ow[4] = {o4.x, o4.y, o4.z, o4.w}, dw[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 of = unpack_bf16x2(ow[e]), df = unpack_bf16x2(dw[e]);
-              acc = fmaf(of.x, df.x, acc);
-              acc = fmaf(of.y, df.y, acc);
-            }
+          for (int e = 0; e < 4; ++e) {
+            const float2 of = unpack_bf16x2(ow[e]), df = unpack_bf16x2(dw[e]);
+            acc = fmaf(of.x, df.x, acc);
+            acc = fmaf(of.y, df.y, acc);
           }
         }
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        if (half == 0) {
-          sDelta[r] = acc;
-          sLse[r] = (r < kTok) ? lse[static_cast<size_t>(item) * kTok + r] : INFINITY;
+      }
+      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+      if (half == 0) {
+        sDelta[(ii & 1) * 256 + r] = acc;
+        sLse[(ii & 1) * 256 + r] = (r < kTok) ? lse[static_cast<size_t>(item) * kTok + r] : INFINITY;
+      }
+    };
+    // accumulators of the key tile that unit m (qt = 1) completed: dV, dK; after the item's last unit also dQ of both query tiles
+    auto epilogue = [&](int m) {
+      const int ii = m >> 2, kt = (m & 3) >> 1;
+      const int item = blockIdx.x + ii * gridDim.x;
+      const int b = item / kHeads, h = item % kHeads;
+      const int key = kt * 128 + row;
+      const bool warp_live = (kt * 128 + quad * 32) < kTok;
+      tc_fence_after();
+      float o0[16];
+      if (warp_live) tmem_ld16f(tmem_base + kColDV + cg * 16 + lane_sel, o0);
+      __nv_bfloat16* base = dqkv + (static_cast<size_t>(b) * kTok + (key < kTok ? key : 0)) * 576 + h * kHd + cg * 16;
+      if (warp_live && key < kTok) store16(base + 384, o0, 1.0f);
+      if (warp_live) tmem_ld16f(tmem_base + kColDK + cg * 16 + lane_sel, o0);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(kv_read);
+      if (warp_live && key < kTok) store16(base + 192, o0, 0.125f);
+      if (kt == 1) {
+        // dQ of both query tiles (rows = queries now)
+#pragma unroll 1
+        for (int t2 = 0; t2 < 2; ++t2) {
+          const int q = t2 * 128 + row;
+          const bool live_q = (t2 * 128 + quad * 32) < kTok;
+          if (live_q) tmem_ld16f(tmem_base + kColDQ + t2 * 64 + cg * 16 + lane_sel, o0);
+          if (t2 == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(q_read);
+          }
+          if (live_q && q < kTok)
+            store16(dqkv + (static_cast<size_t>(b) * kTok + q) * 576 + h * kHd + cg * 16, o0, 0.125f);
         }
       }
+    };
+
+    const int total = n_items * 4;
+    if (n_items > 0) {
+      prepass(0);
       named_bar_sync(1, kSmWarps * 32);
-
+    }
 #pragma unroll 1
-      for (int u = 0; u < 4; ++u) {
-        const int n = ii * 4 + u;
-        const int kt = u >> 1, qt = u & 1;
-        const int key = kt * 128 + row;
-        const bool warp_live = (kt * 128 + quad * 32) < kTok;   // uniform over the warp: some key row of the warp is real
-        // this warp's query columns of the unit: [a, a + W) of the tile
-        const int a = (qt == 0) ? 32 * cg : (cg == 0 ? 0 : 16 + 16 * cg);
-        const bool wide = (qt == 0) || (cg == 0);
-        mbar_wait(s_full, n & 1);
-        tc_fence_after();
-        if (warp_live) {
-          // P / dS of columns [a, a+W): packed P pairs over S[a, a+W/2), dS pairs over S[a+W/2, a+W), dS also into the smem tile
-          auto piece = [&](auto wtag) {
-            constexpr int W = decltype(wtag)::value;
-            float sv[W], dv[W];
-            if (W == 32) {
-              tmem_ld32_nowait(tS + a, *reinterpret_cast<float(*)[32]>(&sv[0]));
-              tmem_ld32_nowait(tB + a, *reinterpret_cast<float(*)[32]>(&dv[0]));
-            } else {
-              tmem_ld16_nowait(tS + a, sv);
-              tmem_ld16_nowait(tB + a, dv);
-            }
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            uint32_t pw[W / 2], dw[W / 2];
-            const int q0 = qt * 128 + a;
+    for (int n = 0; n < total; ++n) {
+      const int ii = n >> 2, u = n & 3;
+      const int kt = u >> 1, qt = u & 1;
+      const bool warp_live = (kt * 128 + quad * 32) < kTok;   // uniform over the warp: some key row of the warp is real
+      // this warp's query columns of the unit: [a, a + W) of the tile
+      const int a = (qt == 0) ? 32 * cg : (cg == 0 ? 0 : 16 + 16 * cg);
+      const bool wide = (qt == 0) || (cg == 0);
+      uint8_t* ds_buf = sDS + (n & 1) * kBwdDsBytes;
+      const float* lse_b = sLse + (ii & 1) * 256;
+      const float* delta_b = sDelta + (ii & 1) * 256;
+      mbar_wait(s_full, n & 1);     // (also: every earlier product but dK / dQ of unit n-1 has completed -> this dS buffer is free)
+      tc_fence_after();
+      if (warp_live) {
+        // P / dS of columns [a, a+W): packed P pairs over dP[a, a+W/2) (columns this warp has just read), dS into the smem tile
+        auto piece = [&](auto wtag) {
+          constexpr int W = decltype(wtag)::value;
+          float sv[W], dv[W];
+          if (W == 32) {
+            tmem_ld32_nowait(tS + a, *reinterpret_cast<float(*)[32]>(&sv[0]));
+            tmem_ld32_nowait(tB + a, *reinterpret_cast<float(*)[32]>(&dv[0]));
+          } else {
+            tmem_ld16_nowait(tS + a, sv);
+            tmem_ld16_nowait(tB + a, dv);
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          uint32_t pw[W / 2], dw[W / 2];
+          const int q0 = qt * 128 + a;
 #pragma unroll
-            for (int e = 0; e < W / 4; ++e) {
-              const float4 l4 = *reinterpret_cast<const float4*>(&sLse[q0 + 4 * e]);
-              const float4 d4 = *reinterpret_cast<const float4*>(&sDelta[q0 + 4 * e]);
-              const float p0 = ex2_approx(fmaf(sv[4 * e + 0], kScaleLog2e, -l4.x));
-              const float p1 = ex2_approx(fmaf(sv[4 * e + 1], kScaleLog2e, -l4.y));
-              const float p2 = ex2_approx(fmaf(sv[4 * e + 2], kScaleLog2e, -l4.z));
-              const float p3 = ex2_approx(fmaf(sv[4 * e + 3], kScaleLog2e, -l4.w));
-              pw[2 * e] = pack_bf16x2(p0, p1);
-              pw[2 * e + 1] = pack_bf16x2(p2, p3);
-              dw[2 * e] = pack_bf16x2(p0 * (dv[4 * e + 0] - d4.x), p1 * (dv[4 * e + 1] - d4.y));
-              dw[2 * e + 1] = pack_bf16x2(p2 * (dv[4 * e + 2] - d4.z), p3 * (dv[4 * e + 3] - d4.w));
-            }
-            if (W == 32) { tmem_st16(tS + a, pw); tmem_st16(tS + a + 16, dw); }
-            else { tmem_st8(tS + a, pw); tmem_st8(tS + a + 8, dw); }
-            // dS^T tile for the dQ product: row = key, 16-byte chunks of 8 queries, panel = 64 queries
+          for (int e = 0; e < W / 4; ++e) {
+            const float4 l4 = *reinterpret_cast<const float4*>(&lse_b[q0 + 4 * e]);
+            const float4 d4 = *reinterpret_cast<const float4*>(&delta_b[q0 + 4 * e]);
+            const float p0 = ex2_approx(fmaf(sv[4 * e + 0], kScaleLog2e, -l4.x));
+            const float p1 = ex2_approx(fmaf(sv[4 * e + 1], kScaleLog2e, -l4.y));
+            const float p2 = ex2_approx(fmaf(sv[4 * e + 2], kScaleLog2e, -l4.z));
+            const float p3 = ex2_approx(fmaf(sv[4 * e + 3], kScaleLog2e, -l4.w));
+            pw[2 * e] = pack_bf16x2(p0, p1);
+            pw[2 * e + 1] = pack_bf16x2(p2, p3);
+            dw[2 * e] = pack_bf16x2(p0 * (dv[4 * e + 0] - d4.x), p1 * (dv[4 * e + 1] - d4.y));
+            dw[2 * e + 1] = pack_bf16x2(p2 * (dv[4 * e + 2] - d4.z), p3 * (dv[4 * e + 3] - d4.w));
+          }
+          if (W == 32) tmem_st16(tB + a, pw); else tmem_st8(tB + a, pw);
+          // dS^T tile (this unit's buffer): row = key, 16-byte chunks of 8 queries, panel = 64 queries
 #pragma unroll
-            for (int c = 0; c < W / 8; ++c) {
-              const int qc = a + 8 * c;                 // first query (within the tile) of this chunk
-              *reinterpret_cast<uint4*>(sDS + (qc >> 6) * 16384 + sw128_offset(row, (qc >> 3) & 7)) =
-                  make_uint4(dw[4 * c], dw[4 * c + 1], dw[4 * c + 2], dw[4 * c + 3]);
-            }
-          };
-          if (wide) piece(std::integral_constant<int, 32>{});
-          else piece(std::integral_constant<int, 16>{});
-          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-        } else {
-          // no real key in these 32 rows: their dS rows must still be finite zeros for the dQ product (K rows are zero, 0 * NaN is not)
-          const int W = wide ? 32 : 16;
           for (int c = 0; c < W / 8; ++c) {
-            const int qc = a + 8 * c;
-            *reinterpret_cast<uint4*>(sDS + (qc >> 6) * 16384 + sw128_offset(row, (qc >> 3) & 7)) = make_uint4(0u, 0u, 0u, 0u);
+            const int qc = a + 8 * c;                 // first query (within the tile) of this chunk
+            *reinterpret_cast<uint4*>(ds_buf + (qc >> 6) * 16384 + sw128_offset(row, (qc >> 3) & 7)) =
+                make_uint4(dw[4 * c], dw[4 * c + 1], dw[4 * c + 2], dw[4 * c + 3]);
           }
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
-
-        // ---- finished accumulators
-        if (qt == 1) {
-          mbar_wait(o_full, n & 1);
-          tc_fence_after();
-          // dV, dK of key tile kt
-          float o0[16];
-          if (warp_live) tmem_ld16f(tmem_base + kColDV + cg * 16 + lane_sel, o0);
-          __nv_bfloat16* base = dqkv + (static_cast<size_t>(b) * kTok + (key < kTok ? key : 0)) * 576 + h * kHd + cg * 16;
-          if (warp_live && key < kTok) store16(base + 384, o0, 1.0f);
-          if (warp_live) tmem_ld16f(tmem_base + kColDK + cg * 16 + lane_sel, o0);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(kv_read);
-          if (warp_live && key < kTok) store16(base + 192, o0, 0.125f);
-          if (kt == 1) {
-            // dQ of both query tiles (rows = queries now)
-#pragma unroll 1
-            for (int t2 = 0; t2 < 2; ++t2) {
-              const int q = t2 * 128 + row;
-              const bool live_q = (t2 * 128 + quad * 32) < kTok;
-              if (live_q) tmem_ld16f(tmem_base + kColDQ + t2 * 64 + cg * 16 + lane_sel, o0);
-              if (t2 == 1) {
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(q_read);
-              }
-              if (live_q && q < kTok)
-                store16(dqkv + (static_cast<size_t>(b) * kTok + q) * 576 + h * kHd + cg * 16, o0, 0.125f);
-            }
-          }
+        };
+        if (wide) piece(std::integral_constant<int, 32>{});
+        else piece(std::integral_constant<int, 16>{});
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      } else {
+        // no real key in these 32 rows: their dS rows must still be finite zeros for the dQ product (K rows are zero, 0 * NaN is not)
+        const int W = wide ? 32 : 16;
+        for (int c = 0; c < W / 8; ++c) {
+          const int qc = a + 8 * c;
+          *reinterpret_cast<uint4*>(ds_buf + (qc >> 6) * 16384 + sw128_offset(row, (qc >> 3) & 7)) = make_uint4(0u, 0u, 0u, 0u);
         }
       }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      // consume o_full phase by phase (a parity wait must never skip one): dK / dQ of the previous unit ran while this unit was
+      // processed and have long finished; the barrier cannot be further than phase n before this warp arrives below
+      if (n > 0) mbar_wait(o_full, (n - 1) & 1);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      // the key tile the PREVIOUS unit completed is stored now, while the tensor pipe works on this unit's products
+      if (n > 0 && qt == 0) epilogue(n - 1);
+      if (u == 3 && ii + 1 < n_items) {
+        prepass(ii + 1);
+        named_bar_sync(1, kSmWarps * 32);
+      }
+    }
+    if (total > 0) {
+      mbar_wait(o_full, (total - 1) & 1);
+      epilogue(total - 1);
     }
   }
 
@@ -680,7 +717,8 @@ int rvk_attention_bwd_tc_launch(const void* qkv, const void* ctx, const void* dc
   RVK_TRY(rvk_make_tmap_3d(&tmDO, dctx, RVK_BF16, 192, kTok, batch, 192, int64_t(kTok) * 192, 64, 256));
   const int items = batch * kHeads;
   const int grid = items < kNumSMsB200 ? items : kNumSMsB200;
-  attn_bwd_tc_kernel<<<grid, kThreads, kBwdSmemBytes, stream>>>(tmQKV, tmDO, static_cast<const __nv_bfloat16*>(ctx), lse,
+  attn_bwd_tc_kernel<<<grid, kThreads, kBwdSmemBytes, stream>>>(tmQKV, tmDO, static_cast<const __nv_bfloat16*>(ctx),
+                                                               static_cast<const __nv_bfloat16*>(dctx), lse,
                                                                static_cast<__nv_bfloat16*>(dqkv), items);
   return rvk_launch_check();
 }
