@@ -443,64 +443,76 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     const uint32_t ds_k0 = umma_desc_lo(smem_u32(sDS));                  // K-major view (dK): rows = keys
     const uint32_t ds_mn0 = umma_desc_lo(smem_u32(sDS), 16384);          // MN-major view (dQ): two 64-query panels, 16 KB apart
     const int total = n_items * 4;
-    // S^T and dP^T of unit (kt, qt)
-    auto issue_s = [&](int kt, int qt) {
-      const uint32_t idesc_s = qt == 0 ? idesc_s0 : idesc_s1;
-      const uint32_t ak = k_lo + kt * (16384 >> 4), bq = q_lo + qt * (16384 >> 4);
+    // Everything an MMA needs is computed here in warp-uniform code (uniform datapath); the elected lane only executes the
+    // tcgen05 instructions.  With the address arithmetic inside the divergent region every MMA costs ~20 dependent
+    // instructions of the single issuing thread (fused MLP kernel).
+    auto issue_s_dp = [&](uint32_t ak, uint32_t bq, uint32_t av, uint32_t bd, uint32_t idesc_s) {
+      if (issuer) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_f16_split<1>(tmem_base, ak + 2 * k, bq + 2 * k, idesc_s, k != 0 ? 1u : 0u);
-    };
-    auto issue_dp = [&](int kt, int qt) {
-      const uint32_t idesc_s = qt == 0 ? idesc_s0 : idesc_s1;
-      const uint32_t av = v_lo + kt * (16384 >> 4), bd = do_lo + qt * (16384 >> 4);
+        for (int k = 0; k < 4; ++k) umma_f16_split<1>(tmem_base, ak + 2 * k, bq + 2 * k, idesc_s, k != 0 ? 1u : 0u);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) umma_f16_split<1>(tmem_base + kColDP, av + 2 * k, bd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) umma_f16_split<1>(tmem_base + kColDP, av + 2 * k, bd + 2 * k, idesc_s, k != 0 ? 1u : 0u);
+        umma_commit(s_full);
+      }
+      __syncwarp();
     };
     if (n_items > 0) {
       mbar_wait(tiles_full, 0);
       tc_fence_after();
-      if (issuer) { issue_s(0, 0); issue_dp(0, 0); umma_commit(s_full); }
-      __syncwarp();
+      issue_s_dp(k_lo, q_lo, v_lo, do_lo, idesc_s0);
     }
 #pragma unroll 1
     for (int n = 0; n < total; ++n) {
       const int ii = n >> 2, u = n & 3;
       const int kt = u >> 1, qt = u & 1;
-      const int nj = qt == 0 ? 8 : 5;
       const uint32_t row0 = static_cast<uint32_t>(qt * 128) * (128 >> 4);     // B tiles: first query row of the tile
       const uint32_t dsb = static_cast<uint32_t>(n & 1) * (kBwdDsBytes >> 4);
+      const uint32_t d_dv = tmem_base + kColDV, d_dk = tmem_base + kColDK, d_dq = tmem_base + kColDQ + qt * 64;
+      const uint32_t p_base = tmem_base + kColDP;
+      const uint32_t do_b = do_mn + row0, q_b = q_mn + row0, k_b = k_mn + kt * (128 * 128 >> 4);
+      const uint32_t ds_k = ds_k0 + dsb, ds_m = ds_mn0 + dsb;
+      const uint32_t first_kv = qt != 0 ? 1u : 0u, first_q = kt != 0 ? 1u : 0u;   // accumulate flag of a product's first MMA
+      const bool same_item = u < 3;             // the next unit works on the tiles that are already in shared memory
+      const int kt1 = (u + 1) >> 1, qt1 = (u + 1) & 1;
+      const uint32_t ak1 = k_lo + kt1 * (16384 >> 4), bq1 = q_lo + qt1 * (16384 >> 4);
+      const uint32_t av1 = v_lo + kt1 * (16384 >> 4), bd1 = do_lo + qt1 * (16384 >> 4);
+      const uint32_t idesc_s1n = qt1 == 0 ? idesc_s0 : idesc_s1;
       // the accumulators this unit starts must have been read out by the epilogue of the previous key tile / item
       if (qt == 0 && n >= 2) { mbar_wait(kv_read, ((n >> 1) - 1) & 1); }
       if (u == 0 && ii > 0) { mbar_wait(q_read, (ii - 1) & 1); }
       mbar_wait(p_full, n & 1);
       tc_fence_after();
-      const bool same_item = u < 3;             // the next unit works on the tiles that are already in shared memory
       if (issuer) {
+        // dV += P^T dO   (P pairs sit in the dP region)
+        if (qt == 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {           // dV += P^T dO   (P pairs sit in the dP region)
-          if (j < nj)
-            umma_ts_bf16(tmem_base + kColDV, tmem_base + kColDP + (qt == 0 ? kBwdPCol0[j] : kBwdPCol1[j < 5 ? j : 0]),
-                         do_mn + row0 + j * (2048 >> 4), idesc_o, (qt | j) != 0 ? 1u : 0u);
+          for (int j = 0; j < 8; ++j) umma_ts_bf16(d_dv, p_base + kBwdPCol0[j], do_b + j * (2048 >> 4), idesc_o, j != 0 ? 1u : first_kv);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 5; ++j) umma_ts_bf16(d_dv, p_base + kBwdPCol1[j], do_b + j * (2048 >> 4), idesc_o, j != 0 ? 1u : first_kv);
         }
         if (same_item) {
           // next unit's S^T / dP^T right behind dV: tcgen05.mma instructions of one thread execute in issue order
           // (pipelined), so dP^T cannot overwrite the P pairs before dV has read them; the S region holds no operand
-          issue_s((u + 1) >> 1, (u + 1) & 1);
-          issue_dp((u + 1) >> 1, (u + 1) & 1);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_split<1>(tmem_base, ak1 + 2 * k, bq1 + 2 * k, idesc_s1n, k != 0 ? 1u : 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_split<1>(p_base, av1 + 2 * k, bd1 + 2 * k, idesc_s1n, k != 0 ? 1u : 0u);
           umma_commit(s_full);
         }
+        // dK += dS^T Q   (dS^T tile K-major: 16 queries = 32 bytes of a row, 64 per panel)
+        if (qt == 0) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {           // dK += dS^T Q   (dS^T tile K-major: 16 queries = 32 bytes of a row, 64 per panel)
-          if (j < nj)
-            umma_f16_split<1>(tmem_base + kColDK, ds_k0 + dsb + (j >> 2) * (16384 >> 4) + (j & 3) * 2, q_mn + row0 + j * (2048 >> 4),
-                              idesc_o, (qt | j) != 0 ? 1u : 0u);
-        }
+          for (int j = 0; j < 8; ++j)
+            umma_f16_split<1>(d_dk, ds_k + (j >> 2) * (16384 >> 4) + (j & 3) * 2, q_b + j * (2048 >> 4), idesc_o, j != 0 ? 1u : first_kv);
+        } else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {           // dQ_qt += dS K_kt: 16 key rows per step
-          const uint64_t ad = (static_cast<uint64_t>(kUmmaDescHiSw128) << 32) | (ds_mn0 + dsb + k * (2048 >> 4));
-          const uint64_t bd2 = (static_cast<uint64_t>(kUmmaDescHiSw128) << 32) | (k_mn + (kt * 128 * 128 >> 4) + k * (2048 >> 4));
-          umma_bf16(tmem_base + kColDQ + qt * 64, ad, bd2, idesc_q, (kt | k) != 0 ? 1u : 0u);
+          for (int j = 0; j < 5; ++j)
+            umma_f16_split<1>(d_dk, ds_k + (j >> 2) * (16384 >> 4) + (j & 3) * 2, q_b + j * (2048 >> 4), idesc_o, j != 0 ? 1u : first_kv);
         }
+        // dQ_qt += dS K_kt: both operands MN-major, 16 key rows per step
+#pragma unroll
+        for (int k = 0; k < 8; ++k) umma_f16_split<1>(d_dq, ds_m + k * (2048 >> 4), k_b + k * (2048 >> 4), idesc_q, k != 0 ? 1u : first_q);
         umma_commit(o_full);
         if (u == 3) umma_commit(tiles_empty);
       }
@@ -509,8 +521,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
         // next item: its tiles replace the ones the products above still read (tiles_full implies they have completed)
         mbar_wait(tiles_full, (ii + 1) & 1);
         tc_fence_after();
-        if (issuer) { issue_s(0, 0); issue_dp(0, 0); umma_commit(s_full); }
-        __syncwarp();
+        issue_s_dp(k_lo, q_lo, v_lo, do_lo, idesc_s0);
       }
     }
     if (total > 0) mbar_wait(o_full, (total - 1) & 1);
