@@ -110,16 +110,67 @@ def cpu_reference(steps, warmup, batch=32, quiet=False):
                       f'loop) after {warmup} warm-up; {dt:.1f} s of CPU work', 'ms_per_step': dt / steps * 1e3}
 
 
+def cpu_reference_train(steps, warmup, batch=8):
+    """Reference train step (forward + joint loss + backward through torch autograd, no optimizer) on the host cores."""
+    import torch
+    from oracle import losses as olosses
+    from oracle import model as omodel
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'knots' not in k else v)
+          for k, v in omodel.random_state_dict(0).items()}
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(batch, 3, 224, 224, generator=g)
+    y = torch.randint(0, 4, (batch,), generator=g)
+
+    def step():
+        for v in sd.values():
+            if v.requires_grad:
+                v.grad = None
+        olosses.joint(omodel.forward(sd, x, stage=4, kan_loop=True), y, y, 4)['total_loss'].backward()
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return {'value': batch * steps / dt, 'unit': 'images/sec', 'cores': cores, 'kind': 'port',
+            'sample': f'{steps} stage-4 train steps (forward + joint loss + backward, fp32, KAN via the reference\'s per-(input,output) '
+                      f'loop) of batch {batch} after {warmup} warm-up; {dt:.1f} s of CPU work', 'ms_per_step': dt / steps * 1e3}
+
+
+def workload_config(train, batch, world):
+    """The `config` object both arms print (the reference arm times a bounded sample of the same workload)."""
+    return {'workload': ('RoViT-KAN curriculum stage-4 training step (all losses, AdamW), batch %d/GPU' % batch) if train
+            else 'RoViT-KAN inference, batch %d per GPU, bf16 tensor-core trunk, all four heads (KAN severity enabled)' % batch,
+            'batch_per_gpu': batch, 'global_batch': batch * world, 'image': '3x224x224', 'chunk_images': min(batch, 2048),
+            'parallelism': f'dp{world}', 'l2': 'inputs larger than L2 (616 MB per batch), no flush needed',
+            'weights': 'random init (timm init laws), seed 0'}
+
+
+def metric_name(train):
+    return 'images/sec (224^2, device-timed) RoViT-KAN ' + ('train step' if train else 'inference forward')
+
+
 def run_reference(args, rank, world):
+    """The reference's own CPU implementation of the path (oracle port: the reference is a Python project whose trunk lives in
+    the absent `timm`), all host threads, on a bounded sample of OUR arm's workload; same metric / unit / config keys."""
     if rank != 0:
         return
-    steps, warmup = max(1, args.steps), max(1, min(args.warmup, 2))
-    r = cpu_reference(steps, warmup)
-    line = {'impl': 'reference', 'metric': 'images/sec (224^2) RoViT-KAN eval forward, reference CPU path', 'value': r['value'],
+    train = args.mode == 'train'
+    if train:
+        steps, warmup = max(1, min(args.steps, 3)), 1
+        r = cpu_reference_train(steps, warmup)
+    else:
+        steps, warmup = max(1, args.steps), max(1, min(args.warmup, 2))
+        r = cpu_reference(steps, warmup)
+    batch = args.batch or (256 if train else 1024)
+    cfg = workload_config(train, batch, max(1, args.gpus))
+    cfg['reference_sample'] = r['sample']
+    line = {'impl': 'reference', 'metric': metric_name(train), 'value': r['value'],
             'unit': 'images/sec', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': r['ms_per_step'],
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
-            'config': {'workload': 'RoViT-KAN eval forward, all four heads, batch 32 per step on host cores (bounded '
-                                   'sample of the inference workload)', 'batch': 32},
+            'config': cfg,
             'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
             'e2e': {'value': r['value'], 'unit': 'images/sec', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
@@ -308,14 +359,10 @@ def run_ours(args, rank, local_rank, world):
     except (OSError, ValueError, KeyError):
         pass
     line = {
-        'metric': 'images/sec (224^2, device-timed) RoViT-KAN ' + ('train step' if train else 'inference forward'),
+        'metric': metric_name(train),
         'value': value, 'unit': 'images/sec', 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_total / K,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-        'config': {'workload': ('RoViT-KAN curriculum stage-4 training step (all losses, AdamW), batch %d/GPU' % batch) if train
-                   else 'RoViT-KAN inference, batch %d per GPU, bf16 tensor-core trunk, all four heads (KAN severity enabled)' % batch,
-                   'batch_per_gpu': batch, 'global_batch': batch * world, 'image': '3x224x224', 'chunk_images': min(batch, 2048),
-                   'parallelism': f'dp{world}', 'l2': 'inputs larger than L2 (616 MB per batch), no flush needed',
-                   'weights': 'random init (timm init laws), seed 0'},
+        'config': workload_config(train, batch, world),
         'e2e': {'value': e2e_value, 'unit': 'images/sec', 'h2d_bytes_per_step': host_images.numel() * 4,
                 'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / K},
         'gpu_launches': int(launches),
