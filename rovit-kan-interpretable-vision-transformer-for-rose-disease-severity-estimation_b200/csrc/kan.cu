@@ -297,7 +297,8 @@ kan_bwd_x_kernel(const float* __restrict__ x, const float* __restrict__ yv, cons
   const int s0 = blockIdx.x * kTS;
   const int ldT = in_pad * kKW;
 
-  for (int i0 = 0; i0 < n_in; i0 += kDxIC) {
+  {
+    const int i0 = blockIdx.y * kDxIC;          // one 16-input chunk per CTA: small batches still fill the machine
     float acc[4][kKW];
 #pragma unroll
     for (int a = 0; a < 4; ++a)
@@ -521,8 +522,8 @@ int rvk_kan_layer_bwd_launch(const KanLayerDesc& L, const float* x, const float*
                                                                      L.out_features, L.in_features / 8);
     RVK_TRY(rvk_launch_check());
   } else if (dx != nullptr) {
-    kan_bwd_x_kernel<<<(batch + kTS - 1) / kTS, 256, 0, stream>>>(x, y, gy, act, kn, WpT, dx, batch, L.in_features,
-                                                                   L.out_features, in_pad, out_pad);
+    kan_bwd_x_kernel<<<dim3((batch + kTS - 1) / kTS, (L.in_features + kDxIC - 1) / kDxIC), 256, 0, stream>>>(
+        x, y, gy, act, kn, WpT, dx, batch, L.in_features, L.out_features, in_pad, out_pad);
     RVK_TRY(rvk_launch_check());
   }
   return RVK_OK;
