@@ -3,6 +3,7 @@
 #include "mlp_fused.cuh"
 #include "tma_host.h"
 
+#include <cstdlib>
 #include <vector>
 
 namespace {
@@ -124,7 +125,11 @@ int rvk_gemm_tn_launch(const void* A, int64_t lda, const void* B, int64_t ldb, f
   RVK_TRY(rvk_make_tmap_2d(&tmB, B, RVK_BF16, M, Q, ldb, 64, 64));
   const int tiles = ((P + 127) / 128) * ((Q + kBQ - 1) / kBQ);
   const int total_chunks = (M + 63) / 64;
-  int splits = (2 * kNumSMsB200 + tiles - 1) / tiles;
+  // one CTA per SM and launch: a CTA pays ~7 us of fixed cost (TMEM allocation, pipeline fill, the red.global.add epilogue of its
+  // 128 x 192 tile), so a single full wave beats two half-length ones (measured: 31.4k vs 30.2k img/s on the train step).
+  // RVK_TN_WAVES=2..4 restores finer splits for A/B measurements.
+  static const int waves = [] { const char* e = getenv("RVK_TN_WAVES"); return (e != nullptr && e[0] >= '1' && e[0] <= '4') ? e[0] - '0' : 1; }();
+  int splits = waves * kNumSMsB200 / tiles;
   if (splits > total_chunks) splits = total_chunks;
   if (splits < 1) splits = 1;
   GemmTnParams p;
