@@ -47,7 +47,7 @@ def test_attention_forward(batch):
     assert_close(lse, lse_ref, rtol=1e-4, atol=1e-3, what='lse')
 
 
-@pytest.mark.parametrize('batch', [1, 5])
+@pytest.mark.parametrize('batch', [1, 5, 60])      # 60 images = 180 (image, head) items: CTAs that walk more than one item
 def test_attention_backward(batch):
     g = torch.Generator().manual_seed(1)
     qkv = (torch.randn(batch * TOK, 576, generator=g)).to(DEV).to(torch.bfloat16)
@@ -64,6 +64,31 @@ def test_attention_backward(batch):
     ref_ctx = (p @ v).transpose(1, 2).reshape(batch * TOK, 192)
     ref_ctx.backward(dctx.float())
     assert_close(dqkv.float(), x.grad, rtol=2e-2, atol=2e-2, scale_tol=5e-3, what='dqkv')
+
+
+def test_attention_backward_properties_at_training_batch():
+    """Size-independent properties at BASELINE configs[3]'s 256 images per GPU: an image's gradient does not depend on the batch it
+    travels in (bitwise: items are independent), and the backward is linear in the upstream gradient."""
+    batch = 256
+    g = torch.Generator().manual_seed(2)
+    qkv = (torch.randn(batch * TOK, 576, generator=g)).to(DEV).to(torch.bfloat16)
+    dctx = (torch.randn(batch * TOK, 192, generator=g)).to(DEV).to(torch.bfloat16)
+
+    def run(qkv_, dctx_, n):
+        ctx = torch.zeros(n * TOK, 192, device=DEV, dtype=torch.bfloat16)
+        lse = torch.zeros(n, 3, TOK, device=DEV)
+        _lib.call('rvk_attention_forward', _p(qkv_), _p(ctx), _p(lse), n, _s())
+        out = torch.full((n * TOK, 576), float('nan'), device=DEV, dtype=torch.bfloat16)
+        _lib.call('rvk_attention_backward', _p(qkv_), _p(ctx), _p(dctx_), _p(lse), _p(out), n, _s())
+        torch.cuda.synchronize()
+        return out
+    full = run(qkv, dctx, batch)
+    assert bool(torch.isfinite(full.float()).all())
+    for img in (0, 147, 255):
+        one = run(qkv[img * TOK:(img + 1) * TOK].contiguous(), dctx[img * TOK:(img + 1) * TOK].contiguous(), 1)
+        assert torch.equal(one, full[img * TOK:(img + 1) * TOK]), f'image {img}: gradient depends on the batch'
+    twice = run(qkv, (dctx.float() * 2).to(torch.bfloat16), batch)          # exact in bf16: a power of two
+    assert_close(twice.float(), 2 * full.float(), rtol=1e-2, atol=1e-3, what='linearity in dctx')
 
 
 @pytest.mark.parametrize('rows,bf16', [(1, True), (37, False), (5000, True)])

@@ -178,6 +178,23 @@ def test_kan_dead_zone_property():
     assert_close(y, ref.float(), rtol=1e-4, atol=1e-4, what='dead-zone == linear branch')
 
 
+def test_kan_dead_zone_backward_property():
+    """Same property for the tensor-core backward at batch 65536: in the dead zone the spline weights receive exactly zero
+    gradient and dx, dWl, db are those of the linear branch alone."""
+    from rovitkan_b200 import ops
+    torch.manual_seed(8)
+    layer = KANLayer(192, 64).to(DEV)
+    x = (torch.rand(65536, 192, device=DEV) * 3 + 0.45).requires_grad_(True)
+    gy = torch.randn(65536, 64, device=DEV)
+    y = ops.KanLayerFn.apply(x, layer.spline_weights, layer.linear.weight, layer.linear.bias, layer.knots_host(), 0)
+    y.backward(gy)
+    assert float(layer.spline_weights.grad.abs().max()) == 0.0
+    assert_close(x.grad, (gy.double() @ layer.linear.weight.double()).float(), rtol=1e-3, atol=1e-4, what='dx == g . Wl')
+    assert_close(layer.linear.weight.grad, (gy.double().t() @ x.detach().double()).float(), rtol=1e-3, atol=1e-2, scale_tol=1e-4,
+                 what='dWl == g^T x')
+    assert_close(layer.linear.bias.grad, gy.double().sum(0).float(), rtol=1e-3, atol=1e-2, what='db == colsum g')
+
+
 def test_heads_match_reference():
     g = load_golden('heads.npz')
     ch, oh, uh = (ClassificationHead(192, 128, 4, dropout=0.0).to(DEV), OrdinalHead(192, 128, 4, dropout=0.0).to(DEV),

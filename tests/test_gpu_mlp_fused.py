@@ -95,3 +95,35 @@ def test_attn_proj_mlp_fused(M, G):
     """rvk_attn_proj_mlp_fused: x + proj(ctx) computed in the idle TMEM columns, then the MLP half on the new rows."""
     run_case(M, G, True, seed=M + 11, proj=True)
     run_case(M, G, M % 2 == 0, seed=M + 12, inplace=True, proj=True)
+
+
+def test_attn_proj_mlp_fused_equals_two_launches_at_benchmark_size():
+    """BASELINE configs[1] size (1024 images = 201 728 token rows): folding the attention output projection into the MLP kernel
+    must give what the separate projection GEMM followed by rvk_mlp_fused gives (same bf16 operands, fp32 accumulation; the
+    only difference is the order of two fp32 additions per element)."""
+    M = 1024 * 197
+    g = torch.Generator().manual_seed(99)
+    mk = lambda *sh, sc=1.0: (torch.randn(*sh, generator=g) * sc).to(DEV)
+    w1, w2 = mk(768, 192, sc=0.08).to(torch.bfloat16), mk(192, 768, sc=0.05).to(torch.float16)
+    b1, b2, bp = mk(768, sc=0.5), mk(192), mk(192)
+    gamma2, beta2, gamma, beta = 1 + mk(192, sc=0.2), mk(192, sc=0.3), 1 + mk(192, sc=0.2), mk(192, sc=0.3)
+    wp = mk(192, 192, sc=0.08).to(torch.bfloat16)
+    x = to_tiled(mk(M, 192, sc=2.0) + 0.5)
+    ctx = mk(M, 192).to(torch.bfloat16)
+    s = torch.cuda.current_stream().cuda_stream
+    tail = (gamma2.data_ptr(), beta2.data_ptr(), w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), gamma.data_ptr(),
+            beta.data_ptr(), 1e-6)
+    xa, lna = x.clone(), torch.empty(M, 192, device=DEV, dtype=torch.bfloat16)
+    _lib.call('rvk_attn_proj_mlp_fused', xa.data_ptr(), xa.data_ptr(), ctx.data_ptr(), wp.data_ptr(), bp.data_ptr(), *tail,
+              lna.data_ptr(), M, 2, s)
+    # two launches: x += ctx . Wp^T + bp through the fp32 GEMM epilogue (row-major round trip), then the MLP kernel
+    xr = from_tiled(x, M).contiguous()
+    t = torch.empty(M, 192, device=DEV)
+    _lib.call('rvk_gemm_nt', 3, ctx.data_ptr(), 192, wp.data_ptr(), 192, t.data_ptr(), 192, 0, 0, 0, 0, M, 192, 192, bp.data_ptr(),
+              0, 0, 0, 0, 1e-6, 0, 0, s)
+    xb = to_tiled(xr + t)
+    lnb = torch.empty(M, 192, device=DEV, dtype=torch.bfloat16)
+    _lib.call('rvk_mlp_fused', xb.data_ptr(), xb.data_ptr(), *tail, lnb.data_ptr(), M, 2, s)
+    torch.cuda.synchronize()
+    assert_close(from_tiled(xa, M), from_tiled(xb, M), rtol=2e-3, atol=2e-3, scale_tol=1e-3, what='fused vs two launches (x)')
+    assert float((lna.float() - lnb.float()).abs().mean()) < 2e-3
