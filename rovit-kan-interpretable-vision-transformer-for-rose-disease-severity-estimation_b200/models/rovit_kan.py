@@ -17,6 +17,11 @@ from .heads import ClassificationHead, OrdinalHead, UncertaintyHead
 from .kan import KANSeverityModule
 
 
+def _serial_heads() -> bool:
+    import os
+    return os.environ.get('RVK_SERIAL_HEADS', '0') == '1'
+
+
 class RoViTKAN(nn.Module):
     def __init__(self, config_or_embed_dim=None, hidden_dim: int = 128, num_classes: int = 4,
                  kan_layers: list = None, kan_num_knots: int = 5, kan_degree: int = 3, dropout: float = 0.3,
@@ -86,15 +91,53 @@ class RoViTKAN(nn.Module):
                 cls, ordl, mu, lv, kan = ops.heads_fused(self._tail_state, features, ps, self.kan_module.kan_layers[0].knots_host())
                 return {'cls_logits': cls, 'features': features, 'ordinal_logits': ordl, 'mu': mu, 'log_var': lv,
                         'kan_severity': kan}
-        out = {'cls_logits': self.classification_head(features), 'features': features,
-               'ordinal_logits': None, 'mu': None, 'log_var': None, 'kan_severity': None}
+        out = {'cls_logits': None, 'features': features, 'ordinal_logits': None, 'mu': None, 'log_var': None, 'kan_severity': None}
+        branches = [('cls', self.classification_head)]
         if stage >= 2:
-            out['ordinal_logits'] = self.ordinal_head(features)
+            branches.append(('ord', self.ordinal_head))
         if stage >= 3:
-            out['mu'], out['log_var'] = self.uncertainty_head(features)
+            branches.append(('unc', self.uncertainty_head))
         if stage >= 4:
-            out['kan_severity'] = self.kan_module(features)
+            branches.append(('kan', self.kan_module))
+        res = self._run_branches(features, branches)
+        out['cls_logits'] = res['cls']
+        if 'ord' in res:
+            out['ordinal_logits'] = res['ord']
+        if 'unc' in res:
+            out['mu'], out['log_var'] = res['unc']
+        if 'kan' in res:
+            out['kan_severity'] = res['kan']
         return out
+
+    def _run_branches(self, features, branches):
+        """The heads are independent given the features, and at training batch sizes each of them is a chain of small,
+        latency-bound kernels: run every branch on its own CUDA stream (fork after the trunk, join before the loss).  autograd
+        replays each branch's backward on the stream its forward ran on, so the backward chains overlap the same way.
+        RVK_SERIAL_HEADS=1 keeps everything on the current stream."""
+        if len(branches) == 1 or not features.is_cuda or _serial_heads():
+            return {name: fn(features) for name, fn in branches}
+        cur = torch.cuda.current_stream(features.device)
+        streams = getattr(self, '_branch_streams', None)
+        if streams is None or len(streams) < len(branches) - 1 or streams[0].device != features.device:
+            streams = [torch.cuda.Stream(device=features.device) for _ in range(3)]
+            self._branch_streams = streams
+        fork = torch.cuda.Event()
+        fork.record(cur)
+        res = {}
+        name0, fn0 = branches[-1]                  # the longest chain (KAN stack in stage 4) stays on the current stream
+        for i, (name, fn) in enumerate(branches[:-1]):
+            s = streams[i]
+            s.wait_event(fork)
+            with torch.cuda.stream(s):
+                res[name] = fn(features)
+            features.record_stream(s)
+        res[name0] = fn0(features)
+        for i in range(len(branches) - 1):
+            cur.wait_stream(streams[i])
+        for name, _ in branches[:-1]:              # produced on a side stream, consumed (loss) on the current one
+            for t in (res[name] if isinstance(res[name], tuple) else (res[name],)):
+                t.record_stream(cur)
+        return res
 
     def predict(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
         self.eval()
