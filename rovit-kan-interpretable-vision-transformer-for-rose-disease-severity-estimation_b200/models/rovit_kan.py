@@ -121,6 +121,11 @@ class RoViTKAN(nn.Module):
         if streams is None or len(streams) < len(branches) - 1 or streams[0].device != features.device:
             streams = [torch.cuda.Stream(device=features.device) for _ in range(3)]
             self._branch_streams = streams
+            # the head parameters' AccumulateGrad nodes live on the default stream while their gradients are produced on the
+            # branch streams: intentional (autograd synchronises them), so silence the advisory warning about it
+            quiet = getattr(torch.autograd.graph, 'set_warn_on_accumulate_grad_stream_mismatch', None)
+            if quiet is not None:
+                quiet(False)
         fork = torch.cuda.Event()
         fork.record(cur)
         res = {}
