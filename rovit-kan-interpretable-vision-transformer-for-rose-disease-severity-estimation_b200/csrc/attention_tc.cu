@@ -156,6 +156,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  griddep_wait();                    // (programmatic dependent launch: the setup above overlapped the previous kernel's tail)
+  griddep_launch_dependents();
   // debugging: clock64 event log of CTA 0 (role 0 = UMMA issuer, 1 = softmax warp 0); entry = (tag << 48) | clock
   int trace_n = 0;
   auto trace = [&](int role, int tag) {
@@ -711,7 +713,17 @@ int rvk_attention_fwd_launch(const void* qkv, void* ctx, float* lse, int batch, 
   RVK_TRY(rvk_make_tmap_3d(&tmKV, qkv, RVK_BF16, 576, kTok, batch, 576, int64_t(kTok) * 576, 64, kKeysPad));
   const int items = batch * kHeads;
   const int grid = items < kNumSMsB200 ? items : kNumSMsB200;
-  attn_fwd_tc_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmQ, tmKV, static_cast<__nv_bfloat16*>(ctx), lse, items, g_attn_trace);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = rvk_pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RVK_CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_fwd_tc_kernel, tmQ, tmKV, static_cast<__nv_bfloat16*>(ctx), lse, items, g_attn_trace));
   return rvk_launch_check();
 }
 

@@ -80,11 +80,26 @@ int launch_nt(const GemmNtArgs& a, cudaStream_t stream) {
   const int tiles = ((p.M + 127) / 128) * (p.N / kBN);
   const int grid = tiles < kNumSMsB200 ? tiles : kNumSMsB200;
   ScopedTimer timer(stream, 2.0 * p.M * p.N * p.K, kKindNt);
-  kernel<<<grid, kGemmThreads, L::kTotal, stream>>>(tmA, tmB, tmOut, tmOut2, tmAux, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = rvk_pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RVK_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, tmOut, tmOut2, tmAux, p));
   return rvk_launch_check();
 }
 
 }  // namespace
+
+bool rvk_pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("RVK_PDL"); return !(e != nullptr && e[0] == '0'); }();
+  return on;
+}
 
 int rvk_gemm_nt_launch(const GemmNtArgs& a, cudaStream_t stream) {
   const GemmNtParams& p = a.p;
@@ -176,13 +191,15 @@ static int launch_mlp_fused(const MlpFusedArgs& a, cudaStream_t stream) {
   cfg.blockDim = dim3(kMlpThreads);
   cfg.dynamicSmemBytes = L::kTotal;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = G;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = rvk_pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   ScopedTimer timer(stream, 2.0 * p.M * 192.0 * (768.0 * 2.0 + (p.has_proj ? 192.0 : 0.0)), kKindMlp);
   RVK_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, tmW1, tmW2, tmLn, tmCtx, tmWp, p));
   return rvk_launch_check();

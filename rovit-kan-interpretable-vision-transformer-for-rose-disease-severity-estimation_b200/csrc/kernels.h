@@ -44,6 +44,9 @@ struct MlpFusedArgs {
 };
 int rvk_mlp_fused_launch(const MlpFusedArgs& a, cudaStream_t stream);
 
+// programmatic dependent launch of the big trunk kernels (gemm_nt, attention forward, fused MLP); RVK_PDL=0 switches it off
+bool rvk_pdl_enabled();
+
 // ---- attention -----------------------------------------------------------------------------------
 int rvk_attention_fwd_launch(const void* qkv, void* ctx, float* lse, int batch, cudaStream_t stream);
 int rvk_attention_bwd_launch(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,

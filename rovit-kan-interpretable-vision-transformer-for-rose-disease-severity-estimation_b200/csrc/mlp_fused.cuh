@@ -201,6 +201,8 @@ mlp_fused_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant
   if (G == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  griddep_wait();                    // the setup above overlapped the previous kernel's tail; its outputs are needed from here on
+  griddep_launch_dependents();
   // event log: role 0 = UMMA issuer, 1 = epilogue warp 3; entry = (tag << 48) | clock
   int trace_n = 0;
   auto trace = [&](int role, int tag) {
