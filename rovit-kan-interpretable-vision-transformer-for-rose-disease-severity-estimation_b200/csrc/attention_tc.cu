@@ -416,6 +416,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   constexpr uint32_t kColDP = 128, kColDV = 256, kColDK = 320, kColDQ = 384;
+  griddep_wait();                    // (programmatic dependent launch: the setup above overlapped the previous kernel's tail)
+  griddep_launch_dependents();
 
   if (warp == kSmWarps) {
     // ================================================================= TMA producer
@@ -740,8 +742,17 @@ int rvk_attention_bwd_tc_launch(const void* qkv, const void* ctx, const void* dc
   RVK_TRY(rvk_make_tmap_3d(&tmDO, dctx, RVK_BF16, 192, kTok, batch, 192, int64_t(kTok) * 192, 64, 256));
   const int items = batch * kHeads;
   const int grid = items < kNumSMsB200 ? items : kNumSMsB200;
-  attn_bwd_tc_kernel<<<grid, kThreads, kBwdSmemBytes, stream>>>(tmQKV, tmDO, static_cast<const __nv_bfloat16*>(ctx),
-                                                               static_cast<const __nv_bfloat16*>(dctx), lse,
-                                                               static_cast<__nv_bfloat16*>(dqkv), items);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kBwdSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = rvk_pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RVK_CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_bwd_tc_kernel, tmQKV, tmDO, static_cast<const __nv_bfloat16*>(ctx),
+                                  static_cast<const __nv_bfloat16*>(dctx), lse, static_cast<__nv_bfloat16*>(dqkv), items));
   return rvk_launch_check();
 }

@@ -137,6 +137,8 @@ layernorm_bwd_kernel(const void* __restrict__ g, long long gs, const float* __re
   __shared__ float s_acc[3][kD];
   for (int i = threadIdx.x; i < 3 * kD; i += blockDim.x) (&s_acc[0][0])[i] = 0.0f;
   __syncthreads();
+  griddep_wait();                    // (programmatic dependent launch)
+  griddep_launch_dependents();
   const int hl = threadIdx.x & 15;                                   // lane within the half-warp that shares a row
   const int half = threadIdx.x >> 4;                                 // row slot within the block
   const int slots = blockDim.x >> 4;
@@ -364,12 +366,22 @@ int rvk_layernorm_bwd_launch(const void* g, int g_is_bf16, int64_t g_row_stride,
     return RVK_ERR_UNSUPPORTED_SHAPE;
   const int blocks = min((rows + 15) / 16, kNumSMsB200 * 6);
   auto* dxb = static_cast<__nv_bfloat16*>(dx_out_bf16);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(256);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = rvk_pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const long long gs = g_row_stride, xs = x_row_stride, dxs = dx_row_stride;
   if (g_is_bf16)
-    layernorm_bwd_kernel<true><<<blocks, 256, 0, stream>>>(g, g_row_stride, x, x_row_stride, mean, rstd, gamma, dx_in,
-                                                           dx_out, dx_row_stride, dxb, dgamma, dbeta, dcolsum, rows);
+    RVK_CUDA_TRY(cudaLaunchKernelEx(&cfg, layernorm_bwd_kernel<true>, g, gs, x, xs, mean, rstd, gamma, dx_in, dx_out, dxs, dxb, dgamma,
+                                    dbeta, dcolsum, rows));
   else
-    layernorm_bwd_kernel<false><<<blocks, 256, 0, stream>>>(g, g_row_stride, x, x_row_stride, mean, rstd, gamma, dx_in,
-                                                            dx_out, dx_row_stride, dxb, dgamma, dbeta, dcolsum, rows);
+    RVK_CUDA_TRY(cudaLaunchKernelEx(&cfg, layernorm_bwd_kernel<false>, g, gs, x, xs, mean, rstd, gamma, dx_in, dx_out, dxs, dxb, dgamma,
+                                    dbeta, dcolsum, rows));
   return rvk_launch_check();
 }
 

@@ -156,7 +156,17 @@ int rvk_gemm_tn_launch(const void* A, int64_t lda, const void* B, int64_t ldb, f
   p.colsum = a_colsum;
   splits = (total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
   ScopedTimer timer(stream, 2.0 * M * P * Q, kKindTn);
-  kernel<<<dim3(tiles, splits), kTnThreads, L::kTotal, stream>>>(tmA, tmB, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(tiles, splits);
+  cfg.blockDim = dim3(kTnThreads);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = rvk_pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RVK_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, p));
   return rvk_launch_check();
 }
 

@@ -93,6 +93,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  griddep_wait();                    // (programmatic dependent launch: the setup above overlapped the previous kernel's tail)
+  griddep_launch_dependents();
 
   if (n_chunks > 0) {
     if (warp == 0) {
