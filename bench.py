@@ -383,7 +383,7 @@ def run_ours(args, rank, local_rank, world):
                      'whole_step_frac': value / world * flop_img / 1e12 / pk['tflops_sustained']},
     }
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference(steps=args.cpu_steps, warmup=1)
+        r = cpu_reference_train(steps=3, warmup=1) if train else cpu_reference(steps=args.cpu_steps, warmup=1)
         line['cpu_baseline'] = {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
     print(json.dumps(line), flush=True)
     if world > 1:
