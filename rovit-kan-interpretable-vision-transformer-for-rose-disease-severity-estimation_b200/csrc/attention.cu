@@ -307,11 +307,7 @@ int rvk_attention_bwd_launch(const void* qkv, const void* ctx, const void* dctx,
   // default: the tcgen05 kernel (attention_tc.cu); RVK_ATTN_BWD_SIMT=1 keeps this file's mma.sync kernel (A/B measurements)
   static const bool simt = [] { const char* e = getenv("RVK_ATTN_BWD_SIMT"); return e != nullptr && e[0] == '1'; }();
   if (!simt) return rvk_attention_bwd_tc_launch(qkv, ctx, dctx, lse, dqkv, batch, stream);
-  static bool configured = false;
-  if (!configured) {
-    RVK_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnBwdSmem));
-    configured = true;
-  }
+  RVK_SET_MAX_SMEM(attn_bwd_kernel, kAttnBwdSmem);
   attn_bwd_kernel<<<batch * kHeads, kAttnThreads, kAttnBwdSmem, stream>>>(
       static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(ctx),
       static_cast<const __nv_bfloat16*>(dctx), lse, static_cast<__nv_bfloat16*>(dqkv));

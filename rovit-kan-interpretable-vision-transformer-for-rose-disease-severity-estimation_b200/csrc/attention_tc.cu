@@ -705,11 +705,7 @@ void rvk_debug_set_attn_trace_impl(void* buf) { g_attn_trace = static_cast<long 
 
 int rvk_attention_fwd_launch(const void* qkv, void* ctx, float* lse, int batch, cudaStream_t stream) {
   if (batch <= 0) return RVK_OK;
-  static bool configured = false;
-  if (!configured) {
-    RVK_CUDA_TRY(cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    configured = true;
-  }
+  RVK_SET_MAX_SMEM(attn_fwd_tc_kernel, kSmemBytes);
   CUtensorMap tmQ, tmKV;
   RVK_TRY(rvk_make_tmap_3d(&tmQ, qkv, RVK_BF16, 576, kTok, batch, 576, int64_t(kTok) * 576, 64, 256));
   RVK_TRY(rvk_make_tmap_3d(&tmKV, qkv, RVK_BF16, 576, kTok, batch, 576, int64_t(kTok) * 576, 64, kKeysPad));
@@ -732,11 +728,7 @@ int rvk_attention_fwd_launch(const void* qkv, void* ctx, float* lse, int batch, 
 int rvk_attention_bwd_tc_launch(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv, int batch,
                                 cudaStream_t stream) {
   if (batch <= 0) return RVK_OK;
-  static bool configured = false;
-  if (!configured) {
-    RVK_CUDA_TRY(cudaFuncSetAttribute(attn_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes));
-    configured = true;
-  }
+  RVK_SET_MAX_SMEM(attn_bwd_tc_kernel, kBwdSmemBytes);
   CUtensorMap tmQKV, tmDO;
   RVK_TRY(rvk_make_tmap_3d(&tmQKV, qkv, RVK_BF16, 576, kTok, batch, 576, int64_t(kTok) * 576, 64, 256));
   RVK_TRY(rvk_make_tmap_3d(&tmDO, dctx, RVK_BF16, 192, kTok, batch, 192, int64_t(kTok) * 192, 64, 256));

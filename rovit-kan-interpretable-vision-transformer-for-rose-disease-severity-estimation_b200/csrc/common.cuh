@@ -31,6 +31,19 @@ enum RvkStatus : int {
     }                                                        \
   } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a per-DEVICE setting: do it once per device and kernel, not once per process
+// (a process may drive more than one GPU even though the benchmark uses one process per GPU)
+#define RVK_SET_MAX_SMEM(kernel, bytes)                                                                        \
+  do {                                                                                                         \
+    static bool rvk_done_[64] = {};                                                                            \
+    int rvk_dev_ = 0;                                                                                          \
+    RVK_CUDA_TRY(cudaGetDevice(&rvk_dev_));                                                                    \
+    if (rvk_dev_ < 0 || rvk_dev_ >= 64 || !rvk_done_[rvk_dev_]) {                                              \
+      RVK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));          \
+      if (rvk_dev_ >= 0 && rvk_dev_ < 64) rvk_done_[rvk_dev_] = true;                                          \
+    }                                                                                                          \
+  } while (0)
+
 #define RVK_TRY(expr)                 \
   do {                                \
     int _s = (expr);                  \

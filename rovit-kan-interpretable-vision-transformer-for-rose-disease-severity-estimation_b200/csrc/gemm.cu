@@ -51,11 +51,7 @@ template <int MODE>
 int launch_nt(const GemmNtArgs& a, cudaStream_t stream) {
   using L = GemmNtSmem<kBN, kNtStages>;
   auto kernel = gemm_nt_kernel<kBN, MODE, kNtStages>;
-  static bool configured = false;
-  if (!configured) {
-    RVK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    configured = true;
-  }
+  RVK_SET_MAX_SMEM(kernel, L::kTotal);
   const GemmNtParams& p = a.p;
   CUtensorMap tmA, tmB, tmOut, tmOut2, tmAux;
   RVK_TRY(rvk_make_tmap_2d(&tmA, a.A, RVK_BF16, p.M, p.K, a.lda, 128, 64));
@@ -130,11 +126,7 @@ int rvk_gemm_tn_launch(const void* A, int64_t lda, const void* B, int64_t ldb, f
   if (P % 64 != 0 || Q % 64 != 0) return RVK_ERR_UNSUPPORTED_SHAPE;
   using L = GemmTnSmem<kBQ, kTnStages>;
   auto kernel = gemm_tn_kernel<kBQ, kTnStages>;
-  static bool configured = false;
-  if (!configured) {
-    RVK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    configured = true;
-  }
+  RVK_SET_MAX_SMEM(kernel, L::kTotal);
   CUtensorMap tmA, tmB;
   RVK_TRY(rvk_make_tmap_2d(&tmA, A, RVK_BF16, M, P, lda, 64, 64));
   RVK_TRY(rvk_make_tmap_2d(&tmB, B, RVK_BF16, M, Q, ldb, 64, 64));
@@ -175,11 +167,7 @@ template <int G>
 static int launch_mlp_fused(const MlpFusedArgs& a, cudaStream_t stream) {
   using L = MlpSmem<G>;
   auto kernel = mlp_fused_kernel<G>;
-  static bool configured = false;
-  if (!configured) {
-    RVK_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
-    configured = true;
-  }
+  RVK_SET_MAX_SMEM(kernel, L::kTotal);
   const MlpFusedParams& p = a.p;
   CUtensorMap tmW1, tmW2, tmLn, tmCtx, tmWp;
   RVK_TRY(rvk_make_tmap_2d(&tmW1, a.w1, RVK_BF16, 768, 192, 192, 128 / G, 64));

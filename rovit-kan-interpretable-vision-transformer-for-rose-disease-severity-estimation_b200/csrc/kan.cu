@@ -415,11 +415,7 @@ int rvk_kan_layer_fwd_launch(const KanLayerDesc& L, const float* x, float* y, in
                                                                     w2_hi + static_cast<size_t>(64) * kp);
       RVK_TRY(rvk_launch_check());
     }
-    static bool configured = false;
-    if (!configured) {
-      RVK_CUDA_TRY(cudaFuncSetAttribute(kan_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
-      configured = true;
-    }
+    RVK_SET_MAX_SMEM(kan_fwd_tc_kernel, kTcSmemBytes);
     CUtensorMap tmWhi, tmWlo;
     RVK_TRY(rvk_make_tmap_2d(&tmWhi, w_hi, RVK_BF16, 64, kp, kp, 64, 64));
     RVK_TRY(rvk_make_tmap_2d(&tmWlo, w_lo, RVK_BF16, 64, kp, kp, 64, 64));
@@ -469,11 +465,7 @@ int rvk_kan_layer_bwd_launch(const KanLayerDesc& L, const float* x, const float*
     splits = (batch + sps - 1) / sps;
     if (kan_use_tc(batch, L.in_features, L.out_features) && L.in_features % 64 == 0) {
       // tensor-core weight gradient (kan_tc.cuh): grid = (batch slices) x (groups of 64 inputs)
-      static bool configured = false;
-      if (!configured) {
-        RVK_CUDA_TRY(cudaFuncSetAttribute(kan_bwd_w_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcWgSmemBytes));
-        configured = true;
-      }
+      RVK_SET_MAX_SMEM(kan_bwd_w_tc_kernel, kTcWgSmemBytes);
       KanTcTables tb;
       tb.xthr = workspace + 4 * wp;          // written by the forward launch
       for (int j = 0; j < 8; ++j) {
@@ -502,11 +494,7 @@ int rvk_kan_layer_bwd_launch(const KanLayerDesc& L, const float* x, const float*
     const int kp = in_pad * 8;
     auto* w2_hi = reinterpret_cast<__nv_bfloat16*>(workspace + 4 * wp + 64);
     auto* w2_lo = w2_hi + static_cast<size_t>(64) * kp;
-    static bool configured = false;
-    if (!configured) {
-      RVK_CUDA_TRY(cudaFuncSetAttribute(kan_bwd_x_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcBxSmemBytes));
-      configured = true;
-    }
+    RVK_SET_MAX_SMEM(kan_bwd_x_tc_kernel, kTcBxSmemBytes);
     CUtensorMap tmWhi, tmWlo;
     RVK_TRY(rvk_make_tmap_2d(&tmWhi, w2_hi, RVK_BF16, kp, 64, 64, 64, 64));
     RVK_TRY(rvk_make_tmap_2d(&tmWlo, w2_lo, RVK_BF16, kp, 64, 64, 64, 64));
@@ -554,11 +542,7 @@ int rvk_heads_fused_launch(const float* features, const float* ws, const float* 
   if (features == nullptr || ws == nullptr || knots_host == nullptr || cls == nullptr || ord == nullptr || mu == nullptr ||
       log_var == nullptr || kan == nullptr)
     return RVK_ERR_BAD_ARG;
-  static bool configured = false;
-  if (!configured) {
-    RVK_CUDA_TRY(cudaFuncSetAttribute(heads_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kHfSmemBytes));
-    configured = true;
-  }
+  RVK_SET_MAX_SMEM(heads_fused_kernel, kHfSmemBytes);
   Knots kn;
   for (int i = 0; i < kKnots; ++i) kn.k[i] = knots_host[i];
   heads_fused_kernel<<<(batch + kHfS - 1) / kHfS, kHfThreads, kHfSmemBytes, stream>>>(features, ws, kn, batch, cls, ord, mu,

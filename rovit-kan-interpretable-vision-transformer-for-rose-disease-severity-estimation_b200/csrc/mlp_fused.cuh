@@ -1,21 +1,27 @@
-// Fused transformer MLP block on tcgen05 / TMEM, sm_100a (inference path of the DeiT-Tiny trunk):
+// Fused transformer block tail on tcgen05 / TMEM, sm_100a (inference path of the DeiT-Tiny trunk): the attention output
+// projection and the whole MLP half in ONE launch per block,
 //
+//     x     = x + ctx . Wproj^T + bp                              (has_proj; timm Attention.proj + first residual)
 //     a     = LayerNorm2(x) * gamma2 + beta2                      (computed ON LOAD, never written to HBM)
 //     x_out = x + fc2( gelu( fc1(a) + b1 ) ) + b2 ;     ln_out = LayerNorm1'(x_out) * gamma1 + beta1  (next block)
 //
-// (timm Block.forward second half: x + mlp(norm2(x)), followed by the NEXT block's norm1; restated in
-// oracle/vit.py::_Block.)  Neither the normalised input nor the 768-wide hidden activation touches HBM: per 128-row
-// tile the epilogue warps read the fp32 token rows, normalise them into the K-major swizzled A operand in shared
-// memory, and the hidden dimension is walked in six chunks of 128 columns,
+// (timm Block.forward: x + attn(norm1(x)) [the projection part], x + mlp(norm2(x)), followed by the NEXT block's norm1;
+// restated in oracle/vit.py::_Block.)  Neither the normalised input nor the 768-wide hidden activation touches HBM: per
+// 128-row tile the epilogue warps read the fp32 token rows, add the projection out of TMEM, normalise the rows into the
+// K-major swizzled A operand in shared memory, and the hidden dimension is walked in six chunks of 128 columns,
 //     D1[c&1] = a . W1[c]^T          UMMA  M=128*G  N=128  K=192   bf16 x bf16  (TMEM columns   0..255, two buffers)
 //     H[c&1]  = f16(gelu(D1 + b1))   epilogue warps: tcgen05.ld -> registers -> K-major swizzled smem operand
 //     D2     += H[c&1] . W2[:,c]^T   UMMA  M=128*G  N=192  K=128   f16 x f16    (TMEM columns 256..447)
 // and the final epilogue adds bias + residual, writes the fp32 token stream and (through the then idle H buffers
 // and TMA) the LayerNorm'ed bf16 operand of the next block's qkv GEMM.
-// HBM traffic per row: 768 B (x in) + 768 B (x out) + 384 B (ln out); the unfused fc1 / fc2 pair moved 5.4 KB.
+// The projection of the NEXT tile (A = its ctx tile, TMA-loaded into the A buffer as soon as the tile's last fc1 has read
+// it; B = Wproj panels from the weight ring) runs as two accumulators -- outputs 0..127 in D1[0] once GELU of chunk 4
+// has drained it, outputs 128..191 in the 64 spare TMEM columns 448..511 -- so it is issued before the tile boundary.
+// HBM traffic per row: 768 B (x in) + 384 B (ctx in) + 768 B (x out) + 384 B (ln out) [+ 768 B + 768 B through L2 for the
+// projected rows]; the unfused proj / fc1 / fc2 GEMMs moved 7.7 KB.
 //
-// The kernel is bound by the epilogue warps, not by the tensor pipe (ncu + clock traces: profiles/), so GELU runs
-// as packed half2 arithmetic (two elements per instruction) and the hidden activation is kept in fp16 (11-bit
+// The kernel is bound by the epilogue warps, not by the tensor pipe (ncu + clock traces: profiles/), so GELU
+// runs as packed half2 arithmetic (two elements per instruction) and the hidden activation is kept in fp16 (11-bit
 // significand: one rounding of 2^-11 instead of bf16's 2^-9; the fp16 polynomial evaluation costs about that
 // difference back, see gelu_erf_h2).  fc2 therefore takes an fp16 copy of W2.
 //
@@ -23,13 +29,14 @@
 // its own 128 rows of A / H and only HALF of every weight panel, so the weight stream out of L2 and the shared
 // memory operand reads per SM are halved against G = 1 (kept as a single-CTA variant for testing).
 //
-// Warp roles (608 threads): w0 TMA producer (ring of weight panels), w1 UMMA issuer (leader CTA only) + TMEM
+// Warp roles (608 threads): w0 TMA producer (ring of weight panels, ctx tiles), w1 UMMA issuer (leader CTA only) + TMEM
 // owner, w2 idle, w3..w18 sixteen epilogue warps = four teams x four TMEM lane quadrants (one token row per
 // thread).  Team t owns columns [32t, 32t+32) of every hidden chunk and columns [48t, 48t+48) of the token row in
 // the LayerNorm-on-load and in the final epilogue, so all teams carry the same load in every phase.  The fp32
 // token stream uses the tiled layout of common.cuh (xt_offset): coalesced 512-byte global accesses straight
 // from/to registers.  Per tile the epilogue warps run  GELU x6 -> A operand of the NEXT tile -> final epilogue,
-// so the tensor pipe already works on the next tile's fc1 while the final epilogue drains D2.
+// so the tensor pipe already works on the next tile's fc1 while the final epilogue drains D2.  Launched with
+// programmatic stream serialization: everything before griddep_wait() overlaps the previous kernel's tail.
 #pragma once
 
 #include <cuda_fp16.h>
