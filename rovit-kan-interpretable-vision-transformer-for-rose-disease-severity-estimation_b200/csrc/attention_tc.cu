@@ -384,27 +384,31 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
   float* sLse = reinterpret_cast<float*>(sDS + 2 * kBwdDsBytes);   // [2][256] per item parity (+inf beyond 197: P = 0 there)
   float* sDelta = sLse + 512;                                      // [2][256]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sDelta + 512);
-  uint64_t* tiles_full = bars;
-  uint64_t* tiles_empty = bars + 1;
-  uint64_t* s_full = bars + 2;
-  uint64_t* p_full = bars + 3;
-  uint64_t* o_full = bars + 4;       // the unit's three products have completed (accumulators, dS buffer)
-  uint64_t* kv_read = bars + 5;      // dV / dK of a key tile are in registers
-  uint64_t* q_read = bars + 6;       // dQ of the item is in registers
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 7);
+  // The four tiles are loaded as HALVES, grouped by the units that read them, so that the next item's halves arrive while this
+  // item is still being processed: A = {K, V rows 0..127} (units 0, 1), B = {K, V rows 128..255} (units 2, 3),
+  // C = {Q, dO rows 0..127} (units 0, 2), D = {Q, dO rows 128..255} (units 1, 3)
+  uint64_t* grp_full = bars;         // [4]
+  uint64_t* s_full = bars + 4;
+  uint64_t* p_full = bars + 5;
+  uint64_t* o_full = bars + 6;       // the unit's three products have completed (accumulators, dS buffer, and its tile halves)
+  uint64_t* kv_read = bars + 7;      // dV / dK of a key tile are in registers
+  uint64_t* q_read = bars + 8;       // dQ of the item is in registers
+  uint64_t* unit_done = bars + 9;    // [4] unit u of the item has completed (same event as o_full, but one barrier per u, so the
+                                     // producer's parity wait stays valid even if it ever lagged more than one unit behind)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = (num_items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   if (warp == kSmWarps && lane == 0) {
     tma_prefetch_desc(&tmQKV);
     tma_prefetch_desc(&tmDO);
-    mbar_init(tiles_full, 1);
-    mbar_init(tiles_empty, 1);
+    for (int i = 0; i < 4; ++i) mbar_init(&grp_full[i], 1);
     mbar_init(s_full, 1);
     mbar_init(p_full, kSmWarps);
     mbar_init(o_full, 1);
     mbar_init(kv_read, kSmWarps);
     mbar_init(q_read, kSmWarps);
+    for (int i = 0; i < 4; ++i) mbar_init(&unit_done[i], 1);
     fence_mbar_init();
   }
   if (warp == kSmWarps + 1) {
@@ -421,16 +425,30 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 
   if (warp == kSmWarps) {
     // ================================================================= TMA producer
-    if (lane == 0) {
-      for (int ii = 0; ii < n_items; ++ii) {
+    if (lane == 0 && n_items > 0) {
+      auto load_grp = [&](int grp, int ii) {
         const int item = blockIdx.x + ii * gridDim.x;
         const int b = item / kHeads, h = item % kHeads;
-        mbar_wait(tiles_empty, (ii & 1) ^ 1);
-        mbar_arrive_expect_tx(tiles_full, 4 * kBwdTileBytes);
-        tma_load_3d(sQ, &tmQKV, tiles_full, h * kHd, 0, b);
-        tma_load_3d(sK, &tmQKV, tiles_full, 192 + h * kHd, 0, b);
-        tma_load_3d(sV, &tmQKV, tiles_full, 384 + h * kHd, 0, b);
-        tma_load_3d(sDO, &tmDO, tiles_full, h * kHd, 0, b);
+        const int r0 = (grp & 1) * 128;
+        mbar_arrive_expect_tx(&grp_full[grp], 2 * 16384);
+        if (grp < 2) {
+          tma_load_3d(sK + r0 * 128, &tmQKV, &grp_full[grp], 192 + h * kHd, r0, b);
+          tma_load_3d(sV + r0 * 128, &tmQKV, &grp_full[grp], 384 + h * kHd, r0, b);
+        } else {
+          tma_load_3d(sQ + r0 * 128, &tmQKV, &grp_full[grp], h * kHd, r0, b);
+          tma_load_3d(sDO + r0 * 128, &tmDO, &grp_full[grp], h * kHd, r0, b);
+        }
+      };
+      load_grp(0, 0); load_grp(2, 0); load_grp(3, 0); load_grp(1, 0);
+      const int total = n_items * 4;
+      for (int n = 0; n < total; ++n) {
+        const int ii = n >> 2, u = n & 3;
+        mbar_wait(&unit_done[u], ii & 1);  // unit n's products have completed: the halves only it (and earlier units) read are free
+        if (ii + 1 < n_items) {
+          if (u == 1) load_grp(0, ii + 1);
+          else if (u == 2) load_grp(2, ii + 1);
+          else if (u == 3) { load_grp(1, ii + 1); load_grp(3, ii + 1); }
+        }
       }
     }
   } else if (warp == kSmWarps + 1) {
@@ -461,7 +479,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
       __syncwarp();
     };
     if (n_items > 0) {
-      mbar_wait(tiles_full, 0);
+      mbar_wait(&grp_full[0], 0);
+      mbar_wait(&grp_full[2], 0);
       tc_fence_after();
       issue_s_dp(k_lo, q_lo, v_lo, do_lo, idesc_s0);
     }
@@ -495,6 +514,15 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 #pragma unroll
           for (int j = 0; j < 5; ++j) umma_ts_bf16(d_dv, p_base + kBwdPCol1[j], do_b + j * (2048 >> 4), idesc_o, j != 0 ? 1u : first_kv);
         }
+      }
+      __syncwarp();
+      if (same_item) {
+        // the next unit's tile halves (loaded long ago): unit 1 adds D = {Q, dO rows 128..}, unit 2 adds B = {K, V rows 128..}
+        if (u == 0) mbar_wait(&grp_full[3], ii & 1);
+        else if (u == 1) mbar_wait(&grp_full[1], ii & 1);
+        tc_fence_after();
+      }
+      if (issuer) {
         if (same_item) {
           // next unit's S^T / dP^T right behind dV: tcgen05.mma instructions of one thread execute in issue order
           // (pipelined), so dP^T cannot overwrite the P pairs before dV has read them; the S region holds no operand
@@ -518,12 +546,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 #pragma unroll
         for (int k = 0; k < 8; ++k) umma_f16_split<1>(d_dq, ds_m + k * (2048 >> 4), k_b + k * (2048 >> 4), idesc_q, k != 0 ? 1u : first_q);
         umma_commit(o_full);
-        if (u == 3) umma_commit(tiles_empty);
+        umma_commit(&unit_done[u]);
       }
       __syncwarp();
       if (!same_item && ii + 1 < n_items) {
-        // next item: its tiles replace the ones the products above still read (tiles_full implies they have completed)
-        mbar_wait(tiles_full, (ii + 1) & 1);
+        // next item: halves A and C of its tiles have been in shared memory since units 1 and 2 of this item finished
+        mbar_wait(&grp_full[0], (ii + 1) & 1);
+        mbar_wait(&grp_full[2], (ii + 1) & 1);
         tc_fence_after();
         issue_s_dp(k_lo, q_lo, v_lo, do_lo, idesc_s0);
       }
@@ -730,8 +759,8 @@ int rvk_attention_bwd_tc_launch(const void* qkv, const void* ctx, const void* dc
   if (batch <= 0) return RVK_OK;
   RVK_SET_MAX_SMEM(attn_bwd_tc_kernel, kBwdSmemBytes);
   CUtensorMap tmQKV, tmDO;
-  RVK_TRY(rvk_make_tmap_3d(&tmQKV, qkv, RVK_BF16, 576, kTok, batch, 576, int64_t(kTok) * 576, 64, 256));
-  RVK_TRY(rvk_make_tmap_3d(&tmDO, dctx, RVK_BF16, 192, kTok, batch, 192, int64_t(kTok) * 192, 64, 256));
+  RVK_TRY(rvk_make_tmap_3d(&tmQKV, qkv, RVK_BF16, 576, kTok, batch, 576, int64_t(kTok) * 576, 64, 128));
+  RVK_TRY(rvk_make_tmap_3d(&tmDO, dctx, RVK_BF16, 192, kTok, batch, 192, int64_t(kTok) * 192, 64, 128));
   const int items = batch * kHeads;
   const int grid = items < kNumSMsB200 ? items : kNumSMsB200;
   cudaLaunchConfig_t cfg = {};
