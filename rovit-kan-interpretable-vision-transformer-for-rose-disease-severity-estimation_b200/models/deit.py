@@ -16,7 +16,7 @@ import warnings
 import torch
 import torch.nn as nn
 
-from ._bootstrap import ops as _ops
+from .._bootstrap import ops as _ops
 
 EMBED, HEADS, DEPTH, MLP, PATCH, TOKENS = 192, 3, 12, 768, 16, 197
 

@@ -11,7 +11,7 @@ from typing import Tuple
 import torch
 import torch.nn as nn
 
-from ._bootstrap import ops as _ops
+from .._bootstrap import ops as _ops
 
 
 def _linear(x, lin: nn.Linear, relu: bool = False, drop_p: float = 0.0, clamp=None):

@@ -12,7 +12,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from ._bootstrap import ops as _ops
+from .._bootstrap import ops as _ops
 
 _DEGREE = 3
 

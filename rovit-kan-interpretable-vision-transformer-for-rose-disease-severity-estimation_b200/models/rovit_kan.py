@@ -11,7 +11,7 @@ from typing import Dict
 import torch
 import torch.nn as nn
 
-from ._bootstrap import ops as _ops
+from .._bootstrap import ops as _ops
 from .backbone import DeiTTinyBackbone
 from .heads import ClassificationHead, OrdinalHead, UncertaintyHead
 from .kan import KANSeverityModule

@@ -11,7 +11,7 @@ from typing import Dict, Optional
 import torch
 import torch.nn as nn
 
-from ._bootstrap import ops as _ops
+from .._bootstrap import ops as _ops
 
 
 def _check_reduction(reduction: str):
