@@ -1,25 +1,31 @@
 #!/usr/bin/env python
 """Benchmark of the RoViT-KAN hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode infer|train|kan|sweep] [--batch B] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode all|infer|train|kan|sweep] [--batch B] [--impl ours|reference]
 
-Default = BASELINE.json configs[1]: RoViT-KAN inference, batch 1024 per GPU, bf16 tensor-core trunk, all four
-heads (KAN severity enabled), random-init weights, synthetic 224x224 images.  A "step" is one forward pass
-of the whole model over one batch.  With --gpus N > 1 (launched by torch.distributed.run) every rank runs its
-own batch: the path is data parallel with no data-path collective in inference ("scaling": "weak"); in
---mode train ranks all-reduce the flat gradient once per step over NCCL.
+Default (`--mode all`) prints ONE JSON line whose headline (`metric`, `value`, `e2e`, `roofline`, ...) is BASELINE.json
+configs[1] -- RoViT-KAN inference, batch 1024 per GPU, bf16 tensor-core trunk, all four heads (KAN severity enabled),
+random-init weights, synthetic 224x224 images -- and which carries the other BASELINE configs as sub-objects measured in the
+same process at the same N:
+    "train"  configs[3]  stage-4 training step (all losses, AdamW with the reference's two LR groups), batch 256 per GPU,
+                         gradient all-reduce over NCCL when N > 1; phases, per-kernel rooflines, CutMix and frozen-backbone variants
+    "kan"    configs[2]  KANSeverityModule([192,64,1]) (and the production [192,64,16,1]), batch 65536, forward + backward
+    "sweep"  configs[4]  forward throughput at batch 64..8192 per GPU against the tensor roofline
+    "gpu_eager_baseline" the oracle restatement of the reference (PyTorch eager: cuBLAS / SDPA kernels) on the same B200
+`--mode infer|train|kan|sweep` runs one of them alone as its own headline line.
 
-Timing: W untimed steps, then K steps bracketed by barrier + cuda synchronize, CUDA events on the launch
-stream, max over ranks.  The 1024-image input (616 MB fp32) and every inter-kernel tensor set exceed the
-126 MB L2, so no L2 flush is needed between iterations ("l2": "inputs larger than L2").
+A "step" is one pass of the path over one batch.  With --gpus N > 1 (launched by torch.distributed.run) every rank runs
+its own batch: pure data parallel, "scaling": "weak"; the only collective is the gradient all-reduce of the train step.
 
-One JSON line is printed by rank 0; see the task contract for the keys.  `roofline` describes the dominant
-kernel (inference: mlp_fused_kernel, one launch per block, ~50 % of the step; training: the tcgen05 GEMM family); its
-per-launch device time is measured in-situ with CUDA events on the launch stream by librovitkan (rvk_gemm_timing_*)
-in K extra steps after the timed region; `traffic` (DRAM bytes per launch) comes from the committed ncu --set full
-capture of the same kernel (profiles/roofline_traffic.json).
-`cpu_baseline` / `--impl reference` time the reference's CPU algorithm (oracle port incl. the reference's
-per-(input,output) Python loop in the KAN, models/kan.py:85-89) on the host cores, batch 32 per step.
+Timing: W untimed steps, then K steps bracketed by barrier + cuda synchronize, CUDA events on the launch stream, max over
+ranks.  The 1024-image input (616 MB fp32) and every inter-kernel tensor set exceed the 126 MB L2, so the inference and
+train steps need no L2 flush ("l2" in `config`); the KAN microbenchmark and the sweep flush L2 between timed iterations.
+
+Per-kernel numbers (`roofline.kernels`, `train.kernels`, `kan.kernels`): device time of every launch of a kernel family,
+CUDA events on the launch stream inside librovitkan (rvk_timing_*), measured in K extra steps after the timed region;
+`traffic` (DRAM bytes per launch) comes from the committed ncu --set full captures (profiles/roofline_traffic.json).
+`cpu_baseline` / `--impl reference`: the reference's CPU algorithm (oracle port incl. the reference's per-(input,output)
+Python loop in the KAN, models/kan.py:85-89) on the host cores.
 """
 
 import argparse
@@ -36,6 +42,11 @@ sys.path.insert(0, ROOT)
 
 FWD_FLOP_PER_IMG = 2.507e9          # 1253.7 M MAC per image, forward
 TRAIN_FLOP_PER_IMG = 7.52e9
+KAN_BYTES_PER_SAMPLE = 152.0e6 / 65536      # [192,64,1] fwd+bwd algorithmic bytes
+KAN_FLOP_PER_SAMPLE = 38.7e9 / 65536
+SWEEP_BATCHES = (64, 128, 148, 256, 296, 512, 1024, 2048, 4096, 8192)
+# which roofline bounds each kernel family (rvk_timing_kind_name): tensor pipe for the tcgen05 kernels, HBM otherwise
+TENSOR_BOUND = {'gemm_nt_kernel', 'gemm_tn_kernel', 'mlp_fused_kernel', 'attn_fwd_tc_kernel', 'attn_bwd_tc_kernel'}
 
 
 def peaks():
@@ -89,9 +100,9 @@ class ClockSampler:
                 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
-# ------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_reference(steps, warmup, batch=32, quiet=False):
-    """Reference algorithm on the host cores: oracle port with the reference's KAN double loop."""
+# ------------------------------------------------------------------------------------------ CPU reference legs
+def cpu_reference(steps, warmup, batch=32):
+    """Reference algorithm on the host cores: oracle port with the reference's KAN double loop; eval forwards."""
     import torch
     from oracle import model as omodel
     cores = os.cpu_count() or 1
@@ -105,13 +116,14 @@ def cpu_reference(steps, warmup, batch=32, quiet=False):
         for _ in range(steps):
             omodel.forward(sd, x, stage=4, kan_loop=True)
         dt = time.perf_counter() - t0
-    return {'value': batch * steps / dt, 'unit': 'images/sec', 'cores': cores, 'kind': 'port',
+    return {'value': batch * steps / dt, 'unit': 'images/sec', 'cores': cores, 'kind': 'port', 'batch': batch,
             'sample': f'{steps} eval forwards of batch {batch} (fp32, stage 4, KAN via the reference\'s per-(input,output) '
                       f'loop) after {warmup} warm-up; {dt:.1f} s of CPU work', 'ms_per_step': dt / steps * 1e3}
 
 
-def cpu_reference_train(steps, warmup, batch=8):
-    """Reference train step (forward + joint loss + backward through torch autograd, no optimizer) on the host cores."""
+def cpu_reference_train(steps, warmup, batch=32):
+    """Reference train step (forward + joint loss + backward through torch autograd, no optimizer) on the host cores,
+    batch 32 = the reference's own training batch (configs/config.py:33)."""
     import torch
     from oracle import losses as olosses
     from oracle import model as omodel
@@ -134,9 +146,32 @@ def cpu_reference_train(steps, warmup, batch=8):
     for _ in range(steps):
         step()
     dt = time.perf_counter() - t0
-    return {'value': batch * steps / dt, 'unit': 'images/sec', 'cores': cores, 'kind': 'port',
+    return {'value': batch * steps / dt, 'unit': 'images/sec', 'cores': cores, 'kind': 'port', 'batch': batch,
             'sample': f'{steps} stage-4 train steps (forward + joint loss + backward, fp32, KAN via the reference\'s per-(input,output) '
                       f'loop) of batch {batch} after {warmup} warm-up; {dt:.1f} s of CPU work', 'ms_per_step': dt / steps * 1e3}
+
+
+def cpu_reference_kan(batches=(32,), dims=(192, 64, 1)):
+    """Reference KANSeverityModule forward + backward (per-(input,output) loop port, autograd) on the host cores."""
+    import torch
+    from oracle import kan as okan
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    out = []
+    for b in batches:
+        g = torch.Generator().manual_seed(0)
+        layers = [tuple(p.requires_grad_(True) for p in l) for l in okan.init_layers(list(dims), generator=g)]
+        x = torch.randn(b, dims[0], generator=g).requires_grad_(True)
+        gy = torch.randn(b, 1, generator=g)
+        t0 = time.perf_counter()
+        y = okan.severity_forward(x, layers, okan.make_knots(), loop=True)
+        t1 = time.perf_counter()
+        y.backward(gy)
+        t2 = time.perf_counter()
+        out.append({'batch': b, 'fwd_ms': (t1 - t0) * 1e3, 'fwd_bwd_ms': (t2 - t0) * 1e3, 'samples_per_sec': b / (t2 - t0)})
+    return {'kind': 'port', 'cores': cores, 'unit': 'samples/sec', 'value': out[0]['samples_per_sec'], 'runs': out,
+            'sample': f'KANSeverityModule({list(dims)}) forward + backward through the reference\'s per-(input,output) loop, one '
+                      f'run each at batch {list(batches)} (loop cost is per batch, not per sample)'}
 
 
 def workload_config(train, batch, world):
@@ -154,114 +189,136 @@ def metric_name(train):
 
 def run_reference(args, rank, world):
     """The reference's own CPU implementation of the path (oracle port: the reference is a Python project whose trunk lives in
-    the absent `timm`), all host threads, on a bounded sample of OUR arm's workload; same metric / unit / config keys."""
+    the absent `timm`), all host threads, on a bounded sample of OUR arm's workload; same metric / unit / config / steps /
+    warm-up as our arm.  One step = one batch-32 forward (1/32 of the batch-1024 step; BASELINE configs[0]); because the
+    reference's KAN loop costs per BATCH, one full batch-1024 forward is timed too and reported as `same_batch`."""
     if rank != 0:
         return
     train = args.mode == 'train'
+    K, W = args.steps, max(3, args.warmup)
+    batch = args.batch or (256 if train else 1024)
+    line = {'impl': 'reference', 'metric': metric_name(train), 'unit': 'images/sec', 'n_gpus': args.gpus,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
+            'config': workload_config(train, batch, max(1, args.gpus)), 'gpu_launches': 0}
     if train:
-        steps, warmup = max(1, min(args.steps, 3)), 1
+        steps, warmup = max(1, min(K, 2)), 1
         r = cpu_reference_train(steps, warmup)
     else:
-        steps, warmup = max(1, args.steps), max(1, min(args.warmup, 2))
+        steps, warmup = K, W
         r = cpu_reference(steps, warmup)
-    batch = args.batch or (256 if train else 1024)
-    cfg = workload_config(train, batch, max(1, args.gpus))
-    cfg['reference_sample'] = r['sample']
-    line = {'impl': 'reference', 'metric': metric_name(train), 'value': r['value'],
-            'unit': 'images/sec', 'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup, 'ms_per_step': r['ms_per_step'],
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
-            'config': cfg,
-            'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
-            'e2e': {'value': r['value'], 'unit': 'images/sec', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-            'gpu_launches': 0}
+        full = cpu_reference(1, 0, batch=batch)
+        line['same_batch'] = {'batch': batch, 'value': full['value'], 'unit': 'images/sec', 'ms_per_step': full['ms_per_step'],
+                              'sample': full['sample']}
+        if args.mode == 'all' and args.gpus == 1 and not args.no_subs:
+            t = cpu_reference_train(1, 1)
+            line['train'] = {'value': t['value'], 'unit': 'images/sec', 'ms_per_step': t['ms_per_step'], 'sample': t['sample']}
+            line['kan'] = cpu_reference_kan()
+    line.update({'value': r['value'], 'steps': steps, 'warmup': warmup, 'ms_per_step': r['ms_per_step'],
+                 'reference_sample': r['sample'],
+                 'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
+                 'e2e': {'value': r['value'], 'unit': 'images/sec', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}})
     print(json.dumps(line), flush=True)
 
 
-# ------------------------------------------------------------------------------------------ our arm
-def run_ours(args, rank, local_rank, world):
-    import torch
-    import torch.distributed as dist
-    from rovitkan_b200 import _lib
-    from rovitkan_b200.models import RoViTKAN
-    from rovitkan_b200.training.losses import JointLoss
+# ------------------------------------------------------------------------------------------ our arm: shared plumbing
+class Ctx:
+    def __init__(self, rank, local_rank, world):
+        import torch
+        import torch.distributed as dist
+        from rovitkan_b200 import _lib
+        assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+        self.torch, self.dist = torch, dist
+        self.rank, self.local_rank, self.world = rank, local_rank, world
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device('cuda', local_rank)
+        if world > 1 and not dist.is_initialized():
+            dist.init_process_group('nccl', device_id=self.dev)
+        self.lib = _lib.load()
+        self.pk = peaks()
+        self._flush = None
 
-    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
-    torch.cuda.set_device(local_rank)
-    dev = torch.device('cuda', local_rank)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-    lib = _lib.load()
-    train = args.mode == 'train'
-    batch = args.batch or (256 if train else 1024)
-    K, W = args.steps, max(3, args.warmup)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    torch.manual_seed(0)
-    model = RoViTKAN(pretrained=False).to(dev)
-    g = torch.Generator().manual_seed(1000 + rank)
-    host_images = torch.randn(batch, 3, 224, 224, generator=g).pin_memory()
-    labels = torch.randint(0, 4, (batch,), generator=g)
-    images = host_images.to(dev)
-    yd = labels.to(dev)
+    def max_over_ranks(self, ms):
+        if self.world == 1:
+            return float(ms)
+        t = self.torch.tensor([float(ms)], device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t)
 
-    if train:
-        model.train()
-        loss_fn = JointLoss(focal_alpha=torch.ones(4))
-        opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-4, fused=True)
-        params = [p for p in model.parameters()]
-
-        def step(x):
-            out = model(x)
-            loss = loss_fn(out, yd, yd, 4)['total_loss']
-            opt.zero_grad(set_to_none=True)
-            loss.backward()
-            if world > 1:
-                from rovitkan_b200.dist import all_reduce_gradients
-                all_reduce_gradients(params, world)
-            torch.nn.utils.clip_grad_norm_(params, 1.0)
-            opt.step()
-            return loss
-    else:
-        model.eval()
-
-        def step(x):
-            with torch.no_grad():
-                return model(x)['kan_severity']
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, n):
-        barrier()
+    def timed(self, fn, n):
+        """n calls of fn() between barrier + synchronize, CUDA events on the launch stream, max over ranks -> ms total."""
+        torch = self.torch
+        self.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(n):
             fn()
         e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms)
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1))
 
-    for _ in range(W):
-        step(images)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    l0 = lib.rvk_launch_count()
-    ms_total = timed(lambda: step(images), K)
-    launches = lib.rvk_launch_count() - l0
-    clocks = sampler.stop() if rank == 0 else None
-    value = batch * world * K / (ms_total / 1e3)
+    def timed_run(self, fn, n):
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn(n)
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1))
 
-    # end-to-end through the public API: every step copies ITS batch from pinned host memory to the device and
-    # reads its result back to the host, all inside the timed region.  The copy of step i+1 runs on a second
-    # stream while step i computes (double-buffered), as a serving loop would do it.
-    copy_stream = torch.cuda.Stream(device=dev)
+    def flush_l2(self):
+        if self._flush is None:
+            self._flush = self.torch.empty(256 << 20, dtype=self.torch.uint8, device=self.dev)
+        self._flush.zero_()
 
-    def make_e2e(host_batch):
+    def kernel_table(self, fn, n, step_ms):
+        """Device time of every kernel family of librovitkan over n more calls of fn(): CUDA events around each launch
+        on its own stream (this serialises programmatic dependent launches, so the sum can exceed the step time)."""
+        lib, pk = self.lib, self.pk
+        lib.rvk_timing_enable(1)
+        self.torch.cuda.synchronize()
+        for _ in range(n):
+            fn()
+        self.torch.cuda.synchronize()
+        lib.rvk_timing_collect()
+        lib.rvk_timing_enable(0)
+        table, kind = {}, 0
+        while True:
+            name = lib.rvk_timing_kind_name(kind)
+            if name is None:
+                break
+            ms, fl, by = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_double(0)
+            cnt = lib.rvk_timing_kind(kind, ctypes.byref(ms), ctypes.byref(fl), ctypes.byref(by))
+            kind += 1
+            if cnt <= 0 or ms.value <= 0:
+                continue
+            name = name.decode()
+            e = {'launches': int(cnt), 'launches_per_step': cnt / n, 'us_per_launch': ms.value * 1e3 / cnt,
+                 'ms_per_step': ms.value / n, 'share_of_step': ms.value / n / step_ms}
+            if fl.value > 0:
+                e['gflop_per_launch'] = fl.value / cnt / 1e9
+                e['tflops'] = fl.value / (ms.value * 1e-3) / 1e12
+                e['frac_tensor'] = e['tflops'] / pk['tflops_sustained']
+            if by.value > 0:
+                e['mb_per_launch'] = by.value / cnt / 1e6
+                e['gbs'] = by.value / (ms.value * 1e-3) / 1e9
+                e['frac_hbm'] = e['gbs'] / pk['hbm_gbs']
+            e['bound'] = 'tensor' if name in TENSOR_BOUND else 'hbm'
+            e['frac'] = e.get('frac_tensor' if e['bound'] == 'tensor' else 'frac_hbm')
+            table[name] = e
+        return table
+
+    def make_e2e(self, step, host_batch):
+        """End-to-end loop through the public nn.Module call: every step copies ITS batch from pinned host memory to the
+        device and reads its result back to the host, all inside the timed region.  The copy of step i+1 runs on a second
+        stream while step i computes (double-buffered), as a serving / training input loop would do it."""
+        torch, dev = self.torch, self.dev
+        copy_stream = torch.cuda.Stream(device=dev)
         bufs = [torch.empty(host_batch.shape, dtype=host_batch.dtype, device=dev) for _ in range(2)]
         ready = [torch.cuda.Event() for _ in range(2)]
         consumed = [torch.cuda.Event() for _ in range(2)]
@@ -288,129 +345,224 @@ def run_ours(args, rank, local_rank, world):
             return last
         return e2e_run
 
-    e2e_run = make_e2e(host_images)
+    def e2e(self, step, host_batch, K, batch, d2h_bytes):
+        run = self.make_e2e(step, host_batch)
+        run(2)
+        ms = self.timed_run(run, K)
+        return {'value': batch * self.world * K / (ms / 1e3), 'unit': 'images/sec',
+                'h2d_bytes_per_step': host_batch.numel() * host_batch.element_size(), 'd2h_bytes_per_step': d2h_bytes,
+                'ms_per_step': ms / K, 'input_dtype': str(host_batch.dtype).replace('torch.', '')}
 
-    def timed_run(fn, n):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        fn(n)
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms)
 
-    e2e_run(2)
-    ms_e2e = timed_run(e2e_run, K)
-    e2e_value = batch * world * K / (ms_e2e / 1e3)
-    # serving variant: the host batch is already bf16 (the trunk rounds pixels to bf16 first, so the results are
-    # bit-identical); halves the PCIe bytes that bound the fp32 end-to-end number
-    e2e_bf16 = None
-    if not train:
-        host_bf16 = host_images.to(torch.bfloat16).pin_memory()
-        run_bf16 = make_e2e(host_bf16)
-        run_bf16(2)
-        ms_b = timed_run(run_bf16, K)
-        e2e_bf16 = {'value': batch * world * K / (ms_b / 1e3), 'unit': 'images/sec', 'h2d_bytes_per_step': host_bf16.numel() * 2,
-                    'd2h_bytes_per_step': batch * 4, 'ms_per_step': ms_b / K}
-    d2h = 4 if train else batch * 4
-
-    # in-situ device time of the dominant kernel family (tcgen05 GEMMs), K more steps
-    lib.rvk_gemm_timing_enable(1)
-    torch.cuda.synchronize()
-    for _ in range(K):
-        step(images)
-    torch.cuda.synchronize()
-    t_ms, t_fl = ctypes.c_double(0), ctypes.c_double(0)
-    n_gemm = lib.rvk_gemm_timing_collect(ctypes.byref(t_ms), ctypes.byref(t_fl))
-    lib.rvk_gemm_timing_enable(0)
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    pk = peaks()
-    gemm_tflops = (t_fl.value / (t_ms.value * 1e-3) / 1e12) if t_ms.value > 0 else 0.0
-    flop_img = TRAIN_FLOP_PER_IMG if train else FWD_FLOP_PER_IMG
-    # dominant kernel: the fused (proj +) MLP kernel in inference (~50 % of the step), the dgrad/wgrad GEMM family in training
-    kinds = {}
-    for kind, name in ((0, 'gemm_nt_kernel'), (1, 'gemm_tn_kernel'), (2, 'mlp_fused_kernel')):
-        k_ms, k_fl = ctypes.c_double(0), ctypes.c_double(0)
-        n = lib.rvk_gemm_timing_kind(kind, ctypes.byref(k_ms), ctypes.byref(k_fl))
-        if n > 0 and k_ms.value > 0:
-            kinds[name] = {'launches': int(n), 'us_per_launch': k_ms.value * 1e3 / n, 'gflop_per_launch': k_fl.value / n / 1e9,
-                           'tflops': k_fl.value / (k_ms.value * 1e-3) / 1e12, 'ms_per_step': k_ms.value / K}
-    if not train and 'mlp_fused_kernel' in kinds:
-        dom = kinds['mlp_fused_kernel']
-        dom_name = ('mlp_fused_kernel<2> (attention out-projection + LayerNorm2 + fc1 + GELU + fc2 + residual + LayerNorm1, '
-                    'one launch per block; algorithmic FLOPs 2*M*192*(192 + 2*768) per launch, M = batch*197)')
-        dom_tflops = dom['tflops']
-    else:
-        dom, dom_name, dom_tflops = None, 'gemm_nt_kernel / gemm_tn_kernel / mlp_fused_kernel (tcgen05, all launches)', gemm_tflops
-    traffic, traffic_src = None, None
+def traffic_entry(key, batch):
     try:
         with open(os.path.join(ROOT, 'profiles', 'roofline_traffic.json')) as f:
-            tj = json.load(f)
-        ent = tj.get('train' if train else 'infer')
+            ent = json.load(f).get(key)
         if ent and ent.get('batch_per_gpu') == batch:
-            traffic, traffic_src = ent['dram_bytes_per_launch'], ent['source']
+            return ent['dram_bytes_per_launch'], ent['source']
     except (OSError, ValueError, KeyError):
         pass
-    line = {
-        'metric': metric_name(train),
-        'value': value, 'unit': 'images/sec', 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_total / K,
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
-        'config': workload_config(train, batch, world),
-        'e2e': {'value': e2e_value, 'unit': 'images/sec', 'h2d_bytes_per_step': host_images.numel() * 4,
-                'd2h_bytes_per_step': d2h, 'ms_per_step': ms_e2e / K},
-        'gpu_launches': int(launches),
-        'clocks': clocks,
-        'e2e_bf16_input': e2e_bf16,
-        'roofline': {'bound': 'tensor', 'achieved': dom_tflops, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
-                     'frac': dom_tflops / pk['tflops_sustained'], 'traffic': traffic, 'traffic_source': traffic_src,
-                     'kernel': dom_name,
-                     'us_per_launch': dom['us_per_launch'] if dom else None,
-                     'gflop_per_launch': dom['gflop_per_launch'] if dom else None,
-                     'share_of_step': (dom['ms_per_step'] / (ms_total / K)) if dom else None,
-                     'launches_timed': int(dom['launches'] if dom else n_gemm),
-                     'peak_source': pk['source'] + ' sustained bf16',
-                     'kernels': kinds,
-                     'all_tcgen05_gemms': {'tflops': gemm_tflops, 'frac': gemm_tflops / pk['tflops_sustained'],
-                                           'ms_per_step': t_ms.value / K, 'launches_timed': int(n_gemm)},
-                     'whole_step_tflops': value / world * flop_img / 1e12,
-                     'whole_step_frac': value / world * flop_img / 1e12 / pk['tflops_sustained']},
-    }
-    if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_train(steps=3, warmup=1) if train else cpu_reference(steps=args.cpu_steps, warmup=1)
-        line['cpu_baseline'] = {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
-    print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    return None, None
 
 
+# ------------------------------------------------------------------------------------------ configs[1]: inference
+def bench_infer(ctx, K, W, batch, with_e2e=True):
+    torch = ctx.torch
+    from rovitkan_b200.models import RoViTKAN
+    torch.manual_seed(0)
+    model = RoViTKAN(pretrained=False).to(ctx.dev).eval()
+    g = torch.Generator().manual_seed(1000 + ctx.rank)
+    host_images = torch.randn(batch, 3, 224, 224, generator=g).pin_memory()
+    images = host_images.to(ctx.dev)
 
-# ------------------------------------------------------------------------------------------ KAN microbenchmark
-def run_kan(args, rank, local_rank, world):
-    """BASELINE.json configs[2]: KANSeverityModule([192,64,1]) (and the production [192,64,16,1]), grid=5 k=3, batch
-    65536, forward + backward (dx, dW, dWl, db of every layer).  Algorithmic bytes / FLOPs per fwd+bwd from
-    SURVEY.md section 8(d): 152 MB, 38.7 GFLOP for the [192,64,1] stack."""
+    def step(x):
+        with torch.no_grad():
+            return model(x)['kan_severity']
+    for _ in range(W):
+        step(images)
+    sampler = ClockSampler(ctx.local_rank)
+    if ctx.rank == 0:
+        sampler.start()
+    l0 = ctx.lib.rvk_launch_count()
+    ms_total = ctx.timed(lambda: step(images), K)
+    launches = ctx.lib.rvk_launch_count() - l0
+    clocks = sampler.stop() if ctx.rank == 0 else None
+    value = batch * ctx.world * K / (ms_total / 1e3)
+    step_ms = ms_total / K
+    res = {'value': value, 'ms_per_step': step_ms, 'gpu_launches': int(launches), 'clocks': clocks, 'batch': batch}
+    if with_e2e:
+        res['e2e'] = ctx.e2e(step, host_images, K, batch, batch * 4)
+        # serving variants: the host batch already bf16 (bit-identical results: the trunk rounds pixels to bf16 first) or
+        # uint8 pixels as an image decoder produces them (ToTensor + Normalize folded into the patch gather)
+        res['e2e_bf16_input'] = ctx.e2e(step, host_images.to(torch.bfloat16).pin_memory(), K, batch, batch * 4)
+        host_u8 = torch.randint(0, 256, (batch, 3, 224, 224), dtype=torch.uint8, generator=g).pin_memory()
+        res['e2e_uint8_input'] = ctx.e2e(step, host_u8, K, batch, batch * 4)
+    kernels = ctx.kernel_table(lambda: step(images), K, step_ms)
+    res['kernels'] = kernels
+    pk = ctx.pk
+    dom = kernels.get('mlp_fused_kernel')
+    traffic, traffic_src = traffic_entry('infer', batch)
+    tc = [e for n, e in kernels.items() if n in TENSOR_BOUND]
+    tc_ms = sum(e['ms_per_step'] for e in tc)
+    tc_fl = sum(e['gflop_per_launch'] * e['launches_per_step'] for e in tc) * 1e9
+    res['roofline'] = {
+        'bound': 'tensor', 'achieved': dom['tflops'] if dom else None, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
+        'frac': dom['frac_tensor'] if dom else None, 'traffic': traffic, 'traffic_source': traffic_src,
+        'kernel': ('mlp_fused_kernel<2> (attention out-projection + LayerNorm2 + fc1 + GELU + fc2 + residual + LayerNorm1, '
+                   'one launch per block; algorithmic FLOPs 2*M*192*(192 + 2*768) per launch, M = batch*197)'),
+        'us_per_launch': dom['us_per_launch'] if dom else None, 'gflop_per_launch': dom['gflop_per_launch'] if dom else None,
+        'share_of_step': dom['share_of_step'] if dom else None, 'launches_timed': dom['launches'] if dom else 0,
+        'peak_source': pk['source'] + ' sustained bf16', 'kernels': kernels,
+        'all_tcgen05_kernels': {'tflops': tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else None, 'ms_per_step': tc_ms,
+                                'frac': tc_fl / (tc_ms * 1e-3) / 1e12 / pk['tflops_sustained'] if tc_ms > 0 else None},
+        'whole_step_tflops': value / ctx.world * FWD_FLOP_PER_IMG / 1e12,
+        'whole_step_frac': value / ctx.world * FWD_FLOP_PER_IMG / 1e12 / pk['tflops_sustained']}
+    del model, images, host_images
+    torch.cuda.empty_cache()
+    return res
+
+
+# ------------------------------------------------------------------------------------------ configs[3]: train step
+def build_optimizer(model, fused_tail=True):
+    """The reference's optimizer (training/optimizer.py:7-32): AdamW, backbone parameters at lr/10, weight decay 1e-4."""
     import torch
-    from rovitkan_b200 import _lib
+    backbone = [p for n, p in model.named_parameters() if 'backbone' in n and p.requires_grad]
+    heads = [p for n, p in model.named_parameters() if 'backbone' not in n and p.requires_grad]
+    groups = [{'params': backbone, 'lr': 1e-5}, {'params': heads, 'lr': 1e-4}]
+    groups = [g for g in groups if g['params']]
+    if fused_tail:
+        try:
+            from rovitkan_b200.training.optim import FusedAdamW
+            return FusedAdamW(groups, weight_decay=1e-4, max_grad_norm=1.0), True
+        except ImportError:
+            pass
+    return torch.optim.AdamW(groups, weight_decay=1e-4, fused=True), False
+
+
+def bench_train(ctx, K, W, batch, with_variants=True):
+    torch, dist = ctx.torch, ctx.dist
+    from rovitkan_b200.dist import all_reduce_gradients
+    from rovitkan_b200.models import RoViTKAN
+    from rovitkan_b200.training.losses import JointLoss
+    torch.manual_seed(0)
+    model = RoViTKAN(pretrained=False).to(ctx.dev).train()
+    g = torch.Generator().manual_seed(2000 + ctx.rank)
+    host_images = torch.randn(batch, 3, 224, 224, generator=g).pin_memory()
+    yd = torch.randint(0, 4, (batch,), generator=g).to(ctx.dev)
+    yb = yd.flip(0)
+    images = host_images.to(ctx.dev)
+    loss_fn = JointLoss(focal_alpha=torch.ones(4))
+    opt, fused_tail = build_optimizer(model, not os.environ.get('RVK_TORCH_OPTIMIZER'))
+    params = [p for p in model.parameters()]
+    ev = {}
+
+    def mark(name):
+        if ev.get('on'):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            ev.setdefault('marks', []).append((name, e))
+
+    def step(x, cutmix=False):
+        mark('start')
+        out = model(x)
+        if cutmix:        # trainer.py:104-111: both label sets through the loss, blended by lam
+            la, lb = loss_fn(out, yd, yd, 4), loss_fn(out, yb, yd, 4)
+            loss = 0.7 * la['total_loss'] + 0.3 * lb['total_loss']
+        else:
+            loss = loss_fn(out, yd, yd, 4)['total_loss']
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        mark('backward_done')
+        if ctx.world > 1:
+            ev['collectives'] = all_reduce_gradients(params, ctx.world)
+        mark('allreduce_done')
+        if fused_tail:
+            opt.step()                        # unscale + global-norm clip + AdamW + weight shadows in one pass
+        else:
+            torch.nn.utils.clip_grad_norm_([p for p in params if p.grad is not None], 1.0)
+            opt.step()
+        mark('optimizer_done')
+        return loss
+
+    for _ in range(W):
+        step(images)
+    l0 = ctx.lib.rvk_launch_count()
+    ms_total = ctx.timed(lambda: step(images), K)
+    launches = ctx.lib.rvk_launch_count() - l0
+    step_ms = ms_total / K
+    value = batch * ctx.world * K / (ms_total / 1e3)
+    res = {'metric': metric_name(True), 'value': value, 'unit': 'images/sec', 'ms_per_step': step_ms, 'steps': K, 'warmup': W,
+           'batch_per_gpu': batch, 'global_batch': batch * ctx.world, 'gpu_launches': int(launches),
+           'optimizer': 'FusedAdamW (rvk_optimizer_*: unscale + inf check + global-norm clip + AdamW + bf16 weight shadows)'
+           if fused_tail else 'torch.optim.AdamW(fused=True) + clip_grad_norm_',
+           'config': workload_config(True, batch, ctx.world)}
+    # phases (device time between events on the launch stream, max over ranks)
+    ev['on'] = True
+    ctx.barrier()
+    for _ in range(K):
+        step(images)
+    ctx.barrier()
+    ev['on'] = False
+    marks = ev.pop('marks')
+    ph = {'forward_backward': 0.0, 'allreduce_exposed': 0.0, 'clip_optimizer': 0.0}
+    for i in range(0, len(marks), 4):
+        (_, a), (_, b), (_, c), (_, d) = marks[i:i + 4]
+        ph['forward_backward'] += a.elapsed_time(b)
+        ph['allreduce_exposed'] += b.elapsed_time(c)
+        ph['clip_optimizer'] += c.elapsed_time(d)
+    res['phases_ms'] = {k: ctx.max_over_ranks(v / K) for k, v in ph.items()}
+    res['allreduce'] = {'ms_exposed': res['phases_ms']['allreduce_exposed'], 'bytes': sum(p.numel() for p in params) * 4,
+                        'collectives_per_step': ev.get('collectives', 0)}
+    if with_variants:
+        for _ in range(2):
+            step(images, cutmix=True)
+        ms_c = ctx.timed(lambda: step(images, cutmix=True), K)
+        res['cutmix'] = {'value': batch * ctx.world * K / (ms_c / 1e3), 'ms_per_step': ms_c / K,
+                         'note': 'two JointLoss evaluations (labels_a, labels_b) blended with lam = 0.7, trainer.py:104-111'}
+        res['e2e'] = ctx.e2e(step, host_images, K, batch, 4)
+    kernels = ctx.kernel_table(lambda: step(images), K, step_ms)
+    res['kernels'] = kernels
+    pk = ctx.pk
+    tc = [e for n, e in kernels.items() if n in TENSOR_BOUND]
+    tc_ms = sum(e['ms_per_step'] for e in tc)
+    tc_fl = sum(e['gflop_per_launch'] * e['launches_per_step'] for e in tc) * 1e9
+    traffic, traffic_src = traffic_entry('train', batch)
+    res['roofline'] = {'bound': 'tensor', 'achieved': tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else None,
+                       'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
+                       'frac': tc_fl / (tc_ms * 1e-3) / 1e12 / pk['tflops_sustained'] if tc_ms > 0 else None,
+                       'kernel': 'all tcgen05 kernels of the step (gemm_nt / gemm_tn / attention forward + backward); per kernel: `kernels`',
+                       'ms_per_step': tc_ms, 'traffic': traffic, 'traffic_source': traffic_src,
+                       'whole_step_tflops': value / ctx.world * TRAIN_FLOP_PER_IMG / 1e12,
+                       'whole_step_frac': value / ctx.world * TRAIN_FLOP_PER_IMG / 1e12 / pk['tflops_sustained']}
+    if with_variants:
+        # epochs 1-5 of the reference schedule (trainer.py:244-246): backbone frozen, only the 181 978 head parameters train
+        model.freeze_backbone()
+        for p in params:
+            p.grad = None
+        opt, fused_tail = build_optimizer(model, fused_tail)
+        params = [p for p in model.parameters()]
+        for _ in range(3):
+            step(images)
+        ms_f = ctx.timed(lambda: step(images), K)
+        res['frozen_backbone'] = {'value': batch * ctx.world * K / (ms_f / 1e3), 'ms_per_step': ms_f / K,
+                                  'trainable_params': sum(p.numel() for p in params if p.requires_grad)}
+    del model, opt, images, host_images
+    torch.cuda.empty_cache()
+    return res
+
+
+# ------------------------------------------------------------------------------------------ configs[2]: KAN microbenchmark
+def bench_kan(ctx, K, W, batch):
+    """KANSeverityModule([192,64,1]) (and the production [192,64,16,1]), grid=5 k=3, forward + backward (dx, dW, dWl, db of
+    every layer).  Algorithmic bytes / FLOPs per fwd+bwd from SURVEY.md section 8(d): 152 MB, 38.7 GFLOP at batch 65536."""
+    torch = ctx.torch
     from rovitkan_b200.models.kan import KANSeverityModule
-    torch.cuda.set_device(local_rank)
-    dev = torch.device('cuda', local_rank)
-    lib = _lib.load()
-    batch = args.batch or 65536
-    K, W = args.steps, max(3, args.warmup)
-    out = {}
+    out, kernels = {}, None
     for name, dims in (('192-64-1', [192, 64, 1]), ('192-64-16-1', [192, 64, 16, 1])):
         torch.manual_seed(0)
-        m = KANSeverityModule(dims).to(dev)
-        x = torch.randn(batch, 192, generator=torch.Generator().manual_seed(0)).to(dev).requires_grad_(True)
-        gy = torch.randn(batch, 1, generator=torch.Generator().manual_seed(1)).to(dev)
-        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        m = KANSeverityModule(dims).to(ctx.dev)
+        x = torch.randn(batch, 192, generator=torch.Generator().manual_seed(0)).to(ctx.dev).requires_grad_(True)
+        gy = torch.randn(batch, 1, generator=torch.Generator().manual_seed(1)).to(ctx.dev)
 
         def fwd():
             with torch.no_grad():
@@ -428,94 +580,201 @@ def run_kan(args, rank, local_rank, world):
                 fn()
             torch.cuda.synchronize()
             tot = 0.0
-            l0 = lib.rvk_launch_count()
+            l0 = ctx.lib.rvk_launch_count()
             for _ in range(K):
-                flush.zero_()                      # L2 flush between timed iterations (x is 50 MB < 126 MB L2)
+                ctx.flush_l2()                      # x is 50 MB < 126 MB L2
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
                 fn()
                 e1.record()
                 torch.cuda.synchronize()
                 tot += e0.elapsed_time(e1)
-            res[tag] = {'ms': tot / K, 'launches': (lib.rvk_launch_count() - l0) // K}
+            res[tag] = {'ms': ctx.max_over_ranks(tot / K), 'launches': (ctx.lib.rvk_launch_count() - l0) // K}
         out[name] = res
-    if rank != 0:
-        return
-    pk = peaks()
+        if name == '192-64-1':
+            kernels = ctx.kernel_table(fwdbwd, K, res['fwd_bwd']['ms'])
+        del m, x, gy
+    pk = ctx.pk
     r = out['192-64-1']
     ms = r['fwd_bwd']['ms']
-    alg_bytes, alg_flops = 152.0e6 * batch / 65536, 38.7e9 * batch / 65536
-    gbs = alg_bytes / (ms * 1e-3) / 1e9
-    line = {
-        'metric': 'samples/sec KANSeverityModule([192,64,1]) forward+backward', 'value': batch / (ms * 1e-3), 'unit': 'samples/sec',
-        'n_gpus': 1, 'steps': K, 'warmup': W, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'KANLayer microbench: 192->64->1 spline head, grid=5 k=3, batch %d fwd+bwd' % batch,
-                   'l2': 'L2 flushed (256 MB memset) between timed iterations'},
-        'gpu_launches': int(r['fwd_bwd']['launches']) * K,
-        'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': gbs / pk['hbm_gbs'],
-                     'traffic': None,
-                     'kernel': 'kan_fwd_tc_kernel + kan_bwd_x_tc_kernel + kan_bwd_w_tc_kernel (tcgen05, operands generated on the fly, '
-                               'hi+lo bf16 split = 3 MMAs per product) for 192->64; fp32 CUDA-core kernels for 64->1',
-                     'note': 'algorithmic 152 MB / 38.7 GFLOP per fwd+bwd (%.1f TFLOP/s dense-equivalent achieved): the three kernels '
-                             'are bound by the CUDA-core generation of the expanded activations (tanh, interval search, four cubics, '
-                             'hi/lo split: ~100 instructions per (sample, input), done once per kernel), not by HBM or the tensor pipe'
-                             % (alg_flops / (ms * 1e-3) / 1e12)},
-        'detail': out,
-    }
-    print(json.dumps(line), flush=True)
+    gbs = KAN_BYTES_PER_SAMPLE * batch / (ms * 1e-3) / 1e9
+    traffic, traffic_src = traffic_entry('kan', batch)
+    return {'metric': 'samples/sec KANSeverityModule([192,64,1]) forward+backward', 'value': batch * ctx.world / (ms * 1e-3),
+            'unit': 'samples/sec', 'ms_per_step': ms, 'fwd_ms': r['fwd']['ms'], 'steps': K, 'warmup': W, 'batch_per_gpu': batch,
+            'dtype': 'f32', 'gpu_launches': int(r['fwd_bwd']['launches']) * K,
+            'config': {'workload': 'KANLayer microbench: 192->64->1 spline head, grid=5 k=3, batch %d fwd+bwd' % batch,
+                       'l2': 'L2 flushed (256 MB memset) between timed iterations'},
+            'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': gbs / pk['hbm_gbs'],
+                         'traffic': traffic, 'traffic_source': traffic_src,
+                         'kernel': 'whole fwd+bwd of the [192,64,1] stack (algorithmic 152 MB / 38.7 GFLOP at batch 65536); per kernel family: `kernels`',
+                         'dense_equivalent_tflops': KAN_FLOP_PER_SAMPLE * batch / (ms * 1e-3) / 1e12},
+            'kernels': kernels, 'detail': out}
 
 
-# ------------------------------------------------------------------------------------------ throughput sweep
-def run_sweep(args, rank, local_rank, world):
-    """BASELINE.json configs[4]: forward throughput of DeiT-Tiny backbone + heads + KAN at batch 64..8192 per GPU, each
-    rank on its own shard (no collective), against the tensor roofline (2.507 GFLOP per image)."""
-    import torch
-    import torch.distributed as dist
+# ------------------------------------------------------------------------------------------ configs[4]: throughput sweep
+def bench_sweep(ctx, K, W):
+    """Forward throughput of DeiT-Tiny backbone + heads + KAN at batch 64..8192 per GPU, each rank on its own shard (no
+    collective), against the tensor roofline (2.507 GFLOP per image); L2 flushed before every timed step."""
+    torch, dist = ctx.torch, ctx.dist
     from rovitkan_b200.models import RoViTKAN
-    torch.cuda.set_device(local_rank)
-    dev = torch.device('cuda', local_rank)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
     torch.manual_seed(0)
-    model = RoViTKAN(pretrained=False).to(dev).eval()
-    K, W = args.steps, max(3, args.warmup)
-    pk = peaks()
+    model = RoViTKAN(pretrained=False).to(ctx.dev).eval()
     rows = []
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > L2: small batches would otherwise stay L2-resident
-    for batch in (64, 128, 148, 256, 296, 512, 1024, 2048, 4096, 8192):
-        g = torch.Generator(device=dev).manual_seed(1000 + rank)
-        images = torch.randn(batch, 3, 224, 224, generator=g, device=dev)
+    for batch in SWEEP_BATCHES:
+        g = torch.Generator(device=ctx.dev).manual_seed(1000 + ctx.rank)
+        images = torch.randn(batch, 3, 224, 224, generator=g, device=ctx.dev)
         with torch.no_grad():
             for _ in range(W):
                 model(images)
             tot = 0.0
             for _ in range(K):
-                flush.zero_()
+                ctx.flush_l2()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                if world > 1:
-                    dist.barrier()
-                torch.cuda.synchronize()
+                ctx.barrier()
                 e0.record()
                 model(images)
                 e1.record()
                 torch.cuda.synchronize()
                 tot += e0.elapsed_time(e1)
-        ms = torch.tensor([tot / K], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        ips = batch * world / (float(ms) / 1e3)
-        rows.append({'batch_per_gpu': batch, 'ms_per_step': float(ms), 'images_per_sec': ips,
-                     'tensor_roofline_frac': ips / world * FWD_FLOP_PER_IMG / 1e12 / pk['tflops_sustained']})
+        ms = ctx.max_over_ranks(tot / K)
+        ips = batch * ctx.world / (ms / 1e3)
+        rows.append({'batch_per_gpu': batch, 'ms_per_step': ms, 'images_per_sec': ips,
+                     'tensor_roofline_frac': ips / ctx.world * FWD_FLOP_PER_IMG / 1e12 / ctx.pk['tflops_sustained']})
         del images
+    del model
+    torch.cuda.empty_cache()
+    best = max(rows, key=lambda r: r['images_per_sec'])
+    return {'metric': 'images/sec (224^2, device-timed) RoViT-KAN inference forward, batch sweep', 'unit': 'images/sec',
+            'steps': K, 'warmup': W, 'value': best['images_per_sec'], 'best_batch_per_gpu': best['batch_per_gpu'],
+            'config': {'workload': 'encoder-throughput sweep, batch 64-8192 per GPU', 'parallelism': f'dp{ctx.world}',
+                       'l2': 'L2 flushed (256 MB memset) before every timed step'},
+            'peak_tflops': ctx.pk['tflops_sustained'], 'rows': rows}
+
+
+# ------------------------------------------------------------------------------------------ PyTorch eager on the same GPU
+def gpu_eager_baseline(ctx, batch_infer=1024, batch_train=256, steps=5):
+    """The "existing Blackwell kernels" bar (SURVEY.md section 2 / BASELINE.md section 3): the oracle restatement of the
+    reference modules run by PyTorch eager on this B200 (cuBLAS / SDPA / ATen kernels; the KAN contraction vectorised as an
+    einsum -- the reference's own Python loop would take ~0.4 s per batch), fp32 with TF32 off and bf16 autocast."""
+    torch = ctx.torch
+    from oracle import losses as olosses
+    from oracle import model as omodel
+    from oracle import vit as ovit
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sd = {k: v.to(ctx.dev) for k, v in omodel.random_state_dict(0).items()}
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(batch_infer, 3, 224, 224, generator=g).to(ctx.dev)
+    out = {'note': 'oracle/vit.py + vectorised KAN + heads through PyTorch eager on the same GPU, CUDA-event timed', 'steps': steps}
+
+    def fwd(autocast):
+        with torch.no_grad():
+            if autocast:
+                with torch.autocast('cuda', dtype=torch.bfloat16):
+                    f = ovit.forward_functional(sd, x, prefix='backbone.model.').float()
+            else:
+                f = ovit.forward_functional(sd, x, prefix='backbone.model.')
+            return omodel.heads_forward(sd, f, 4)['kan_severity']
+
+    def time_it(fn, n):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+    for tag, ac in (('infer_fp32_no_tf32', False), ('infer_bf16_autocast', True)):
+        ms = time_it(lambda: fwd(ac), steps)
+        out[tag] = {'batch': batch_infer, 'ms_per_step': ms, 'images_per_sec': batch_infer / (ms / 1e3)}
+    del x
+    sdt = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'knots' not in k else v) for k, v in sd.items()}
+    xt = torch.randn(batch_train, 3, 224, 224, generator=g).to(ctx.dev)
+    y = torch.randint(0, 4, (batch_train,), generator=g).to(ctx.dev)
+
+    def train_step():
+        for v in sdt.values():
+            if v.requires_grad:
+                v.grad = None
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            f = ovit.forward_functional(sdt, xt, prefix='backbone.model.').float()
+        olosses.joint(omodel.heads_forward(sdt, f, 4), y, y, 4)['total_loss'].backward()
+    ms = time_it(train_step, steps)
+    out['train_bf16_autocast_fwd_bwd'] = {'batch': batch_train, 'ms_per_step': ms, 'images_per_sec': batch_train / (ms / 1e3),
+                                          'note': 'forward + joint loss + backward, no optimizer'}
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+    del sd, sdt, xt
+    torch.cuda.empty_cache()
+    return out
+
+
+# ------------------------------------------------------------------------------------------ drivers
+def headline(ctx, args, res, train):
+    K, W = args.steps, max(3, args.warmup)
+    batch = res['batch'] if not train else res['batch_per_gpu']
+    line = {'metric': metric_name(train), 'value': res['value'], 'unit': 'images/sec', 'n_gpus': ctx.world, 'steps': K,
+            'warmup': W, 'ms_per_step': res['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'bf16', 'data': 'synthetic', 'config': workload_config(train, batch, ctx.world), 'e2e': res.get('e2e'),
+            'gpu_launches': res['gpu_launches'], 'clocks': res.get('clocks'), 'roofline': res['roofline']}
+    for k in ('e2e_bf16_input', 'e2e_uint8_input', 'phases_ms', 'allreduce', 'cutmix', 'frozen_backbone', 'optimizer'):
+        if k in res:
+            line[k] = res[k]
+    if train:
+        line['kernels'] = res['kernels']
+    return line
+
+
+def run_ours(args, rank, local_rank, world):
+    ctx = Ctx(rank, local_rank, world)
+    K, W = args.steps, max(3, args.warmup)
+    mode = args.mode
+    line = None
+    if mode in ('all', 'infer'):
+        res = bench_infer(ctx, K, W, args.batch or 1024)
+        line = headline(ctx, args, res, False)
+        if mode == 'all' and not args.no_subs:
+            Ks = max(5, min(K, 20))
+            line['train'] = bench_train(ctx, Ks, W, 256)
+            line['kan'] = bench_kan(ctx, Ks, W, 65536)
+            line['sweep'] = bench_sweep(ctx, max(3, min(K, 8)), 3)
+            if rank == 0 and world == 1:
+                try:
+                    line['gpu_eager_baseline'] = gpu_eager_baseline(ctx)
+                    fast = line['gpu_eager_baseline']['infer_bf16_autocast']['images_per_sec']
+                    line['gpu_eager_baseline']['ours_over_eager_bf16_infer'] = line['value'] / fast
+                    line['gpu_eager_baseline']['ours_over_eager_bf16_train'] = (
+                        line['train']['value'] / line['gpu_eager_baseline']['train_bf16_autocast_fwd_bwd']['images_per_sec'])
+                except Exception as e:      # a baseline leg must never take the measurement down
+                    line['gpu_eager_baseline'] = {'error': repr(e)}
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference(steps=args.cpu_steps, warmup=1)
+            line['cpu_baseline'] = {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+            if mode == 'all' and not args.no_subs:
+                t = cpu_reference_train(steps=1, warmup=1)
+                line['train']['cpu_baseline'] = {k: t[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+                line['kan']['cpu_baseline'] = cpu_reference_kan()
+    elif mode == 'train':
+        res = bench_train(ctx, K, W, args.batch or 256)
+        line = headline(ctx, args, res, True)
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            t = cpu_reference_train(steps=2, warmup=1)
+            line['cpu_baseline'] = {k: t[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')}
+    elif mode == 'kan':
+        res = bench_kan(ctx, K, W, args.batch or 65536)
+        line = dict(res, n_gpus=world, higher_is_better=True, scaling='weak', vs_baseline=None, data='synthetic')
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            line['cpu_baseline'] = cpu_reference_kan(batches=(32, 1024, 4096))
+    elif mode == 'sweep':
+        res = bench_sweep(ctx, K, W)
+        line = dict(res, n_gpus=world, higher_is_better=True, scaling='weak', vs_baseline=None, dtype='bf16', data='synthetic')
     if rank == 0:
-        print(json.dumps({'metric': 'images/sec (224^2, device-timed) RoViT-KAN inference forward, batch sweep', 'unit': 'images/sec',
-                          'n_gpus': world, 'steps': K, 'warmup': W, 'higher_is_better': True, 'scaling': 'weak', 'dtype': 'bf16',
-                          'data': 'synthetic', 'config': {'workload': 'encoder-throughput sweep, batch 64-8192 per GPU', 'parallelism': f'dp{world}',
-                                                          'l2': 'L2 flushed (256 MB memset) before every timed step'},
-                          'peak_tflops': pk['tflops_sustained'], 'sweep': rows}), flush=True)
+        print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        ctx.dist.destroy_process_group()
 
 
 def main():
@@ -524,9 +783,10 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--mode', default='infer', choices=['infer', 'train', 'kan', 'sweep'])
+    ap.add_argument('--mode', default='all', choices=['all', 'infer', 'train', 'kan', 'sweep'])
     ap.add_argument('--batch', type=int, default=0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-subs', action='store_true', help='mode all: skip the train / kan / sweep / eager sub-benchmarks')
     ap.add_argument('--cpu-steps', type=int, default=40, help='batch-32 reference forwards timed for cpu_baseline (~10-20 s)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
@@ -534,11 +794,6 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     if args.impl == 'reference':
         run_reference(args, rank, world)
-    elif args.mode == 'kan':
-        if rank == 0:
-            run_kan(args, rank, local_rank, world)
-    elif args.mode == 'sweep':
-        run_sweep(args, rank, local_rank, world)
     else:
         run_ours(args, rank, local_rank, world)
 

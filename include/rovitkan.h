@@ -37,6 +37,13 @@ int64_t rvk_launch_count(void);
 void rvk_gemm_timing_enable(int on);
 int rvk_gemm_timing_collect(double* total_ms_host, double* total_flops_host);
 int rvk_gemm_timing_kind(int kind, double* ms_host, double* flops_host);
+/* The same for every kernel family of the path: rvk_timing_collect (after a device sync) returns the number of timed launches
+ * since the previous collect; rvk_timing_kind gives launches (return value), summed device ms, algorithmic FLOPs and algorithmic
+ * HBM bytes of one family; rvk_timing_kind_name its kernel name (NULL past the last kind). */
+void rvk_timing_enable(int on);
+int rvk_timing_collect(void);
+int rvk_timing_kind(int kind, double* ms_host, double* flops_host, double* bytes_host);
+const char* rvk_timing_kind_name(int kind);
 
 /* ---- KAN severity path ----------------------------------------------------------------------------
  * Replaces KANLayer.forward (models/kan.py:70-95) incl. BSplineBasis.compute_basis (:10-44), and the
@@ -77,10 +84,12 @@ int rvk_linear_backward(const float* x, const float* w, const float* y, const fl
 /* ---- joint loss -----------------------------------------------------------------------------------
  * Replaces JointLoss.forward (training/losses.py:139-181) = FocalLoss (:15-38) + OrdinalBCELoss (:48-72)
  * + UncertaintyLoss (:80-101) + KANRegressionLoss (:109-114).  NULL outputs are the stage-gated heads.
- * out5 = {cls, ord, unc, kan, total}; d_* receive the LOCAL gradients d(term)/d(head output). */
+ * out5 = {cls, ord, unc, kan, total}; d_* receive the LOCAL gradients d(term)/d(head output).
+ * severity_targets are fp32 (the reference casts them with .float(), losses.py:92,112; ordinal targets are
+ * [severity > k]); a class target outside [0, num_classes) makes cls/total NaN and contributes no gradient. */
 int rvk_joint_loss_forward(const float* cls_logits, int num_classes, const float* ord_logits, const float* mu,
                            const float* log_var, const float* kan, const int64_t* class_targets,
-                           const int64_t* severity_targets, const float* alpha, float gamma, float lambda_ord,
+                           const float* severity_targets, const float* alpha, float gamma, float lambda_ord,
                            float mu_unc, float nu_kan, int batch, float* sums_ws4, float* out5, float* d_cls,
                            float* d_ord, float* d_mu, float* d_lv, float* d_kan, void* stream);
 /* dst = local * (upstream5[term] + w_total * upstream5[4]); upstream5 lives on the device (no host sync). */
@@ -111,6 +120,12 @@ int rvk_encoder_forward(const void* const* params_host, const void* wbuf, const 
  * to rvk_encoder_forward on the fp32 images these were rounded from (the trunk rounds pixels to bf16 first). */
 int rvk_encoder_forward_bf16(const void* const* params_host, const void* wbuf, const void* images_bf16, int batch,
                              int training, int chunk_images, void* workspace, float* features, void* stream);
+/* Same with uint8 NCHW pixels (what an image decoder produces: a quarter of the fp32 host->device bytes).  The
+ * reference's transform ToTensor + Normalize(mean, std) is folded into the patch gather: pixel * scale[c] + shift[c]
+ * with scale = 1 / (255 * std[c]), shift = -mean[c] / std[c] (host arrays of 3). */
+int rvk_encoder_forward_u8(const void* const* params_host, const void* wbuf, const uint8_t* images_u8,
+                           const float* scale3_host, const float* shift3_host, int batch, int training,
+                           int chunk_images, void* workspace, float* features, void* stream);
 int rvk_encoder_backward(const void* const* params_host, const void* wbuf, void* workspace,
                          const float* dfeatures, int batch, int chunk_images, void* const* grads_host,
                          void* stream);

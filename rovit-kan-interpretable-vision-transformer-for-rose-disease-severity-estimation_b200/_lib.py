@@ -24,6 +24,10 @@ SIGNATURES = {
     'rvk_gemm_timing_enable': (None, [_I]),
     'rvk_gemm_timing_collect': (_I, [_P, _P]),
     'rvk_gemm_timing_kind': (_I, [_I, _P, _P]),
+    'rvk_timing_enable': (None, [_I]),
+    'rvk_timing_collect': (_I, []),
+    'rvk_timing_kind': (_I, [_I, _P, _P, _P]),
+    'rvk_timing_kind_name': (C.c_char_p, [_I]),
     'rvk_kan_layer_workspace_floats': (_L, [_I, _I, _I]),
     'rvk_kan_basis': (_I, [_P, _P, _I, _L, _P, _P]),
     'rvk_kan_layer_forward': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _I, _P]),
@@ -40,6 +44,7 @@ SIGNATURES = {
     'rvk_encoder_prepare_weights': (_I, [_P, _P, _I, _P]),
     'rvk_encoder_forward': (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     'rvk_encoder_forward_bf16': (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    'rvk_encoder_forward_u8': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     'rvk_encoder_backward': (_I, [_P, _P, _P, _P, _I, _I, _P, _P]),
     'rvk_gemm_nt': (_I, [_I, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _P, _P, _I, _F, _P, _P, _P]),
     'rvk_mlp_fused': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _I, _I, _P]),

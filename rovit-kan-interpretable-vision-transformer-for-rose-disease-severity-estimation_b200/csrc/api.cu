@@ -8,9 +8,10 @@
 
 const char* rvk_last_error_cstr();
 long long rvk_launch_count_impl();
-void rvk_gemm_timing_enable_impl(int on);
-int rvk_gemm_timing_collect_impl(double* total_ms, double* total_flops);
-int rvk_gemm_timing_kind_impl(int kind, double* ms, double* flops);
+void rvk_timing_enable_impl(int on);
+int rvk_timing_collect_impl();
+int rvk_timing_kind_impl(int kind, double* ms, double* flops, double* bytes);
+const char* rvk_timing_kind_name_impl(int kind);
 
 namespace {
 inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
@@ -59,10 +60,29 @@ int rvk_device_check(void) {
 }
 
 int64_t rvk_launch_count(void) { return rvk_launch_count_impl(); }
-void rvk_gemm_timing_enable(int on) { rvk_gemm_timing_enable_impl(on); }
-int rvk_gemm_timing_kind(int kind, double* ms_host, double* flops_host) { return rvk_gemm_timing_kind_impl(kind, ms_host, flops_host); }
+void rvk_timing_enable(int on) { rvk_timing_enable_impl(on); }
+int rvk_timing_collect(void) { return rvk_timing_collect_impl(); }
+int rvk_timing_kind(int kind, double* ms_host, double* flops_host, double* bytes_host) {
+  return rvk_timing_kind_impl(kind, ms_host, flops_host, bytes_host);
+}
+const char* rvk_timing_kind_name(int kind) { return rvk_timing_kind_name_impl(kind); }
+// round-1 names: the three tcgen05 GEMM kernels only (kinds 0..2)
+void rvk_gemm_timing_enable(int on) { rvk_timing_enable_impl(on); }
+int rvk_gemm_timing_kind(int kind, double* ms_host, double* flops_host) {
+  return (kind >= 0 && kind <= 2) ? rvk_timing_kind_impl(kind, ms_host, flops_host, nullptr) : -1;
+}
 int rvk_gemm_timing_collect(double* total_ms_host, double* total_flops_host) {
-  return rvk_gemm_timing_collect_impl(total_ms_host, total_flops_host);
+  rvk_timing_collect_impl();
+  double ms = 0.0, fl = 0.0;
+  int n = 0;
+  for (int k = 0; k <= 2; ++k) {
+    double m = 0.0, f = 0.0;
+    n += rvk_timing_kind_impl(k, &m, &f, nullptr);
+    ms += m; fl += f;
+  }
+  if (total_ms_host) *total_ms_host = ms;
+  if (total_flops_host) *total_flops_host = fl;
+  return n;
 }
 
 // ---- KAN
@@ -163,7 +183,7 @@ int rvk_heads_fused(const float* features, const float* ws, const float* knots_h
 // ---- loss
 int rvk_joint_loss_forward(const float* cls_logits, int num_classes, const float* ord_logits, const float* mu,
                            const float* log_var, const float* kan, const int64_t* class_targets,
-                           const int64_t* severity_targets, const float* alpha, float gamma, float lambda_ord,
+                           const float* severity_targets, const float* alpha, float gamma, float lambda_ord,
                            float mu_unc, float nu_kan, int batch, float* sums_ws4, float* out5, float* d_cls,
                            float* d_ord, float* d_mu, float* d_lv, float* d_kan, void* stream) {
   JointLossArgs a;
@@ -193,12 +213,20 @@ int rvk_encoder_prepare_weights(const void* const* params_host, void* wbuf, int 
 int rvk_encoder_forward(const void* const* params_host, const void* wbuf, const float* images, int batch, int training,
                         int chunk_images, void* workspace, float* features, void* stream) {
   if (batch < 0) return RVK_ERR_BAD_ARG;
-  return rvk_encoder_forward_impl(params_host, wbuf, images, 0, batch, training, chunk_images, workspace, features, S(stream));
+  return rvk_encoder_forward_impl(params_host, wbuf, images, 0, nullptr, batch, training, chunk_images, workspace, features, S(stream));
 }
 int rvk_encoder_forward_bf16(const void* const* params_host, const void* wbuf, const void* images_bf16, int batch,
                              int training, int chunk_images, void* workspace, float* features, void* stream) {
   if (batch < 0) return RVK_ERR_BAD_ARG;
-  return rvk_encoder_forward_impl(params_host, wbuf, images_bf16, 1, batch, training, chunk_images, workspace, features,
+  return rvk_encoder_forward_impl(params_host, wbuf, images_bf16, 1, nullptr, batch, training, chunk_images, workspace, features,
+                                  S(stream));
+}
+int rvk_encoder_forward_u8(const void* const* params_host, const void* wbuf, const uint8_t* images_u8, const float* scale3_host,
+                           const float* shift3_host, int batch, int training, int chunk_images, void* workspace,
+                           float* features, void* stream) {
+  if (batch < 0 || scale3_host == nullptr || shift3_host == nullptr) return RVK_ERR_BAD_ARG;
+  const float norm6[6] = {scale3_host[0], scale3_host[1], scale3_host[2], shift3_host[0], shift3_host[1], shift3_host[2]};
+  return rvk_encoder_forward_impl(params_host, wbuf, images_u8, 2, norm6, batch, training, chunk_images, workspace, features,
                                   S(stream));
 }
 int rvk_encoder_backward(const void* const* params_host, const void* wbuf, void* workspace, const float* dfeatures,
@@ -293,7 +321,7 @@ int rvk_layernorm_backward(const void* g, int g_is_bf16, int64_t g_row_stride, c
 }
 int rvk_im2col(const float* images, void* patches_bf16, int batch, void* stream) {
   if (batch < 0 || (batch > 0 && (images == nullptr || patches_bf16 == nullptr))) return RVK_ERR_BAD_ARG;
-  return rvk_im2col_launch(images, 0, patches_bf16, batch, S(stream));
+  return rvk_im2col_launch(images, 0, patches_bf16, batch, nullptr, S(stream));
 }
 int rvk_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream) {
   if (n < 0 || (n > 0 && (src == nullptr || dst_bf16 == nullptr))) return RVK_ERR_BAD_ARG;

@@ -750,6 +750,8 @@ int rvk_attention_fwd_launch(const void* qkv, void* ctx, float* lse, int batch, 
   attr[0].val.programmaticStreamSerializationAllowed = rvk_pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // algorithmic: QK^T and PV over 197x197x64 per (image, head); qkv read once, ctx written once
+  RvkScopedTimer timer(stream, 4.0 * items * 197.0 * 197.0 * 64.0, double(batch) * 197.0 * (576.0 + 192.0) * 2.0, RVK_T_ATTN_FWD);
   RVK_CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_fwd_tc_kernel, tmQ, tmKV, static_cast<__nv_bfloat16*>(ctx), lse, items, g_attn_trace));
   return rvk_launch_check();
 }
@@ -773,6 +775,8 @@ int rvk_attention_bwd_tc_launch(const void* qkv, const void* ctx, const void* dc
   attr[0].val.programmaticStreamSerializationAllowed = rvk_pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  // algorithmic: S, dP, dV, dK, dQ = five 197x197x64 products per (image, head); qkv + dctx + ctx read, dqkv written
+  RvkScopedTimer timer(stream, 10.0 * items * 197.0 * 197.0 * 64.0, double(batch) * 197.0 * (576.0 * 2 + 192.0 * 2) * 2.0, RVK_T_ATTN_BWD);
   RVK_CUDA_TRY(cudaLaunchKernelEx(&cfg, attn_bwd_tc_kernel, tmQKV, tmDO, static_cast<const __nv_bfloat16*>(ctx),
                                   static_cast<const __nv_bfloat16*>(dctx), lse, static_cast<__nv_bfloat16*>(dqkv), items));
   return rvk_launch_check();

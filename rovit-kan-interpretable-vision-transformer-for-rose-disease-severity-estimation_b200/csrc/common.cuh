@@ -53,6 +53,23 @@ enum RvkStatus : int {
 void rvk_set_last_cuda_error(int code, const char* what);
 void rvk_count_launch();   // every kernel launch of this library is counted (bench.py reports it)
 
+// ---- optional in-situ timing of kernel launches (bench.py roofline): CUDA events on the launch stream around one launch
+enum RvkTimedKind {
+  RVK_T_GEMM_NT = 0, RVK_T_GEMM_TN = 1, RVK_T_MLP_FUSED = 2, RVK_T_ATTN_FWD = 3, RVK_T_ATTN_BWD = 4, RVK_T_LN_BWD = 5,
+  RVK_T_KAN_FWD = 6, RVK_T_KAN_BWD = 7, RVK_T_HEADS_FUSED = 8, RVK_T_IM2COL = 9, RVK_T_OPTIMIZER = 10, RVK_T_HEADS_TRAIN = 11,
+  RVK_T_COUNT = 12
+};
+void* rvk_timer_begin(cudaStream_t s, double flops, double bytes, int kind);   // nullptr when timing is off
+void rvk_timer_end(void* handle, cudaStream_t s);
+struct RvkScopedTimer {
+  cudaStream_t s;
+  void* h;
+  RvkScopedTimer(cudaStream_t stream, double flops, double bytes, int kind) : s(stream), h(rvk_timer_begin(stream, flops, bytes, kind)) {}
+  ~RvkScopedTimer() { if (h != nullptr) rvk_timer_end(h, s); }
+  RvkScopedTimer(const RvkScopedTimer&) = delete;
+  RvkScopedTimer& operator=(const RvkScopedTimer&) = delete;
+};
+
 static inline int rvk_launch_check() {
   rvk_count_launch();
   cudaError_t e = cudaGetLastError();

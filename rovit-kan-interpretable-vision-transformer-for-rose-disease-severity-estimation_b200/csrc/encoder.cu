@@ -216,7 +216,7 @@ int rvk_encoder_prepare_weights_impl(const void* const* params, void* wbuf, int 
                                 reinterpret_cast<float*>(at(wbuf, W.table)), s);
 }
 
-int rvk_encoder_forward_impl(const void* const* params, const void* wbuf, const void* images, int images_bf16, int batch, int training,
+int rvk_encoder_forward_impl(const void* const* params, const void* wbuf, const void* images, int image_fmt, const float* norm6_host, int batch, int training,
                              int chunk_images, void* workspace, float* features, cudaStream_t s) {
   if (batch <= 0) return RVK_OK;
   if (params == nullptr || wbuf == nullptr || images == nullptr || workspace == nullptr || features == nullptr)
@@ -239,8 +239,8 @@ int rvk_encoder_forward_impl(const void* const* params, const void* wbuf, const 
     auto stat = [&](size_t off) { return train ? reinterpret_cast<float*>(at(workspace, off)) + r0 : nullptr; };
 
     uint8_t* patches = b16(A.patches, kPatchK);
-    RVK_TRY(rvk_im2col_launch(static_cast<const uint8_t*>(images) + static_cast<size_t>(b0) * 3 * 224 * 224 * (images_bf16 ? 2 : 4),
-                              images_bf16, patches, nb, s));
+    RVK_TRY(rvk_im2col_launch(static_cast<const uint8_t*>(images) + static_cast<size_t>(b0) * 3 * 224 * 224 * (image_fmt == 0 ? 4 : (image_fmt == 1 ? 2 : 1)),
+                              image_fmt, patches, nb, norm6_host, s));
     if (!train && fused_inference()) {
       // ---- inference: tiled fp32 token stream (updated in place), fused MLP block
       float* x = f32(A.blk[0].x_in, kD);

@@ -19,8 +19,11 @@ constexpr int kPatchK = 768;
 // through the additive token table, so the patch GEMM can emit the [B*197,192] stream directly.
 // IN_BF16: the images are already bf16 (a serving path that halves the host->device copy; bit-identical result, the
 // fp32 path rounds the pixels to bf16 here anyway)
-template <bool IN_BF16>
-__global__ void im2col_kernel(const void* __restrict__ img_v, __nv_bfloat16* __restrict__ out, int batch) {
+// FMT 2: uint8 NCHW pixels (what an image decoder produces: a quarter of the host->device bytes); the per-channel
+// normalisation (pixel / 255 - mean) / std is applied here as pixel * scale[c] + shift[c]
+struct PixelNorm { float scale[3]; float shift[3]; };
+template <int FMT>
+__global__ void im2col_kernel(const void* __restrict__ img_v, __nv_bfloat16* __restrict__ out, int batch, PixelNorm nrm) {
   const int lane = threadIdx.x & 31;
   const long long w = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long total = static_cast<long long>(batch) * kTok * 3;
@@ -33,8 +36,14 @@ __global__ void im2col_kernel(const void* __restrict__ img_v, __nv_bfloat16* __r
   if (tok > 0) {
     const int p = tok - 1, py = p / 14, px = p % 14;
     const size_t off = ((static_cast<size_t>(b) * 3 + c) * 224 + (py * 16 + ky)) * 224 + px * 16 + half * 8;
-    if (IN_BF16) {
+    if (FMT == 1) {
       v = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(img_v) + off);
+    } else if (FMT == 2) {
+      const uint2 q = *reinterpret_cast<const uint2*>(static_cast<const uint8_t*>(img_v) + off);
+      const float sc = nrm.scale[c], sh = nrm.shift[c];
+      auto px = [&](uint32_t word, int byte) { return fmaf(static_cast<float>((word >> (8 * byte)) & 0xffu), sc, sh); };
+      v = make_uint4(pack_bf16x2(px(q.x, 0), px(q.x, 1)), pack_bf16x2(px(q.x, 2), px(q.x, 3)),
+                     pack_bf16x2(px(q.y, 0), px(q.y, 1)), pack_bf16x2(px(q.y, 2), px(q.y, 3)));
     } else {
       const float* src = static_cast<const float*>(img_v) + off;
       const float4 a = *reinterpret_cast<const float4*>(src);
@@ -296,15 +305,21 @@ __global__ void token_grad_reduce_kernel(const float* __restrict__ dx0, int batc
 
 }  // namespace
 
-int rvk_im2col_launch(const void* images, int images_bf16, void* patches_bf16, int batch, cudaStream_t stream) {
+int rvk_im2col_launch(const void* images, int fmt, void* patches_bf16, int batch, const float* norm6_host, cudaStream_t stream) {
   if (batch <= 0) return RVK_OK;
   const long long warps = static_cast<long long>(batch) * kTok * 3;
   const int threads = 256;
   const long long blocks = (warps * 32 + threads - 1) / threads;
-  if (images_bf16)
-    im2col_kernel<true><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(images, static_cast<__nv_bfloat16*>(patches_bf16), batch);
-  else
-    im2col_kernel<false><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(images, static_cast<__nv_bfloat16*>(patches_bf16), batch);
+  if (fmt < 0 || fmt > 2 || (fmt == 2 && norm6_host == nullptr)) return RVK_ERR_BAD_ARG;
+  const int px_bytes = fmt == 0 ? 4 : (fmt == 1 ? 2 : 1);
+  RvkScopedTimer timer(stream, 0.0, double(batch) * (3.0 * 224 * 224 * px_bytes + 197.0 * 768 * 2), RVK_T_IM2COL);
+  PixelNorm nrm{};
+  if (fmt == 2)
+    for (int i = 0; i < 3; ++i) { nrm.scale[i] = norm6_host[i]; nrm.shift[i] = norm6_host[3 + i]; }
+  auto* out = static_cast<__nv_bfloat16*>(patches_bf16);
+  if (fmt == 1) im2col_kernel<1><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(images, out, batch, nrm);
+  else if (fmt == 2) im2col_kernel<2><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(images, out, batch, nrm);
+  else im2col_kernel<0><<<static_cast<unsigned>(blocks), threads, 0, stream>>>(images, out, batch, nrm);
   return rvk_launch_check();
 }
 
@@ -376,6 +391,9 @@ int rvk_layernorm_bwd_launch(const void* g, int g_is_bf16, int64_t g_row_stride,
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const long long gs = g_row_stride, xs = x_row_stride, dxs = dx_row_stride;
+  // algorithmic bytes per row of 192: g (bf16 or fp32) + x fp32 + dx_in fp32 (if any) read; dx fp32 + dx bf16 written
+  RvkScopedTimer timer(stream, 0.0, double(rows) * 192.0 * ((g_is_bf16 ? 2.0 : 4.0) + 4.0 + (dx_in ? 4.0 : 0.0) + 4.0 + (dxb ? 2.0 : 0.0)),
+                       RVK_T_LN_BWD);
   if (g_is_bf16)
     RVK_CUDA_TRY(cudaLaunchKernelEx(&cfg, layernorm_bwd_kernel<true>, g, gs, x, xs, mean, rstd, gamma, dx_in, dx_out, dxs, dxb, dgamma,
                                     dbeta, dcolsum, rows));

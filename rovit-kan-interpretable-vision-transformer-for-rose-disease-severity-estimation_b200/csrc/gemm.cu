@@ -8,40 +8,6 @@
 
 namespace {
 
-// ---- optional in-situ timing of the tensor-core GEMM launches (bench.py roofline) -------------------
-struct TimedLaunch { cudaEvent_t beg, end; double flops; int kind; };
-enum { kKindNt = 0, kKindTn = 1, kKindMlp = 2, kNumKinds = 3 };
-double g_kind_ms[kNumKinds], g_kind_flops[kNumKinds];
-int g_kind_n[kNumKinds];
-bool g_timing = false;
-std::vector<TimedLaunch> g_timed;
-std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_event_pool;
-
-struct ScopedTimer {
-  cudaStream_t s;
-  bool on;
-  TimedLaunch t{};
-  ScopedTimer(cudaStream_t stream, double flops, int kind) : s(stream), on(g_timing) {
-    if (!on) return;
-    if (g_event_pool.empty()) {
-      cudaEventCreate(&t.beg);
-      cudaEventCreate(&t.end);
-    } else {
-      t.beg = g_event_pool.back().first;
-      t.end = g_event_pool.back().second;
-      g_event_pool.pop_back();
-    }
-    t.flops = flops;
-    t.kind = kind;
-    cudaEventRecord(t.beg, s);
-  }
-  ~ScopedTimer() {
-    if (!on) return;
-    cudaEventRecord(t.end, s);
-    g_timed.push_back(t);
-  }
-};
-
 constexpr int kBN = 192;       // every N on this path (192, 576, 768) is a multiple of 192
 constexpr int kNtStages = 3;
 constexpr int kBQ = 192;
@@ -75,7 +41,7 @@ int launch_nt(const GemmNtArgs& a, cudaStream_t stream) {
   }
   const int tiles = ((p.M + 127) / 128) * (p.N / kBN);
   const int grid = tiles < kNumSMsB200 ? tiles : kNumSMsB200;
-  ScopedTimer timer(stream, 2.0 * p.M * p.N * p.K, kKindNt);
+  RvkScopedTimer timer(stream, 2.0 * p.M * p.N * p.K, 0.0, RVK_T_GEMM_NT);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kGemmThreads);
@@ -147,7 +113,7 @@ int rvk_gemm_tn_launch(const void* A, int64_t lda, const void* B, int64_t ldb, f
   p.scale = scale;
   p.colsum = a_colsum;
   splits = (total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
-  ScopedTimer timer(stream, 2.0 * M * P * Q, kKindTn);
+  RvkScopedTimer timer(stream, 2.0 * M * P * Q, 0.0, RVK_T_GEMM_TN);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(tiles, splits);
   cfg.blockDim = dim3(kTnThreads);
@@ -198,7 +164,7 @@ static int launch_mlp_fused(const MlpFusedArgs& a, cudaStream_t stream) {
   attr[1].val.programmaticStreamSerializationAllowed = rvk_pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  ScopedTimer timer(stream, 2.0 * p.M * 192.0 * (768.0 * 2.0 + (p.has_proj ? 192.0 : 0.0)), kKindMlp);
+  RvkScopedTimer timer(stream, 2.0 * p.M * 192.0 * (768.0 * 2.0 + (p.has_proj ? 192.0 : 0.0)), 0.0, RVK_T_MLP_FUSED);
   RVK_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, tmW1, tmW2, tmLn, tmCtx, tmWp, p));
   return rvk_launch_check();
 }
@@ -214,34 +180,4 @@ int rvk_mlp_fused_launch(const MlpFusedArgs& a, cudaStream_t stream) {
   if (a.cta_group == 1) return launch_mlp_fused<1>(a, stream);
   if (a.cta_group == 2) return launch_mlp_fused<2>(a, stream);
   return RVK_ERR_BAD_ARG;
-}
-
-void rvk_gemm_timing_enable_impl(int on) { g_timing = on != 0; }
-
-// Sums the device time of every GEMM launch recorded since the last collect (caller must have
-// synchronised the stream).  Returns the number of launches.
-int rvk_gemm_timing_collect_impl(double* total_ms, double* total_flops) {
-  double ms = 0.0, fl = 0.0;
-  int n = 0;
-  for (int k = 0; k < kNumKinds; ++k) { g_kind_ms[k] = 0.0; g_kind_flops[k] = 0.0; g_kind_n[k] = 0; }
-  for (auto& t : g_timed) {
-    float e = 0.0f;
-    if (cudaEventElapsedTime(&e, t.beg, t.end) == cudaSuccess) {
-      ms += e; fl += t.flops; ++n;
-      g_kind_ms[t.kind] += e; g_kind_flops[t.kind] += t.flops; ++g_kind_n[t.kind];
-    }
-    g_event_pool.emplace_back(t.beg, t.end);
-  }
-  g_timed.clear();
-  if (total_ms) *total_ms = ms;
-  if (total_flops) *total_flops = fl;
-  return n;
-}
-
-// per-kernel breakdown of the last collect: kind 0 = gemm_nt_kernel, 1 = gemm_tn_kernel, 2 = mlp_fused_kernel
-int rvk_gemm_timing_kind_impl(int kind, double* ms, double* flops) {
-  if (kind < 0 || kind >= kNumKinds) return -1;
-  if (ms) *ms = g_kind_ms[kind];
-  if (flops) *flops = g_kind_flops[kind];
-  return g_kind_n[kind];
 }

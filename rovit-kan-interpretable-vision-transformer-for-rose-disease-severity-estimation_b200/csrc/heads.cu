@@ -159,7 +159,7 @@ struct LossParams {
   const float* ord_logits;                     // [B, C-1] or null
   const float* mu; const float* log_var;       // [B] or null
   const float* kan;                            // [B] or null
-  const long long* class_t; const long long* sev_t;
+  const long long* class_t; const float* sev_t;   // severities are fp32: the reference casts them with .float() (losses.py:92,112)
   const float* alpha;                          // [C] or null
   float gamma;
   int batch;
@@ -175,7 +175,11 @@ __global__ void __launch_bounds__(256) joint_loss_kernel(const LossParams p) {
     const int C = p.num_classes;
     {   // focal cross-entropy (losses.py:15-38)
       const float* z = p.cls_logits + static_cast<size_t>(b) * C;
-      const int t = static_cast<int>(p.class_t[b]);
+      const long long t_raw = p.class_t[b];
+      // an out-of-range label (torch raises a device-side assert in gather, losses.py:27): never index with it; the
+      // sample contributes NaN to the loss (loud) and a zero gradient
+      const bool t_ok = t_raw >= 0 && t_raw < C;
+      const int t = t_ok ? static_cast<int>(t_raw) : 0;
       float mx = z[0];
       for (int j = 1; j < C; ++j) mx = fmaxf(mx, z[j]);
       float se = 0.0f;
@@ -184,25 +188,25 @@ __global__ void __launch_bounds__(256) joint_loss_kernel(const LossParams p) {
       const float ce = lse - z[t];
       const float pt = expf(z[t] - lse);
       const float a = (p.alpha != nullptr) ? p.alpha[t] : 1.0f;
-      const float om = 1.0f - pt;
+      const float om = fmaxf(1.0f - pt, 0.0f);        // rounding can push pt above 1: powf(negative, non-integer) is NaN
       const float f = (p.gamma == 2.0f) ? om * om : powf(om, p.gamma);
-      l_cls = a * f * ce * inv_b;
+      l_cls = t_ok ? a * f * ce * inv_b : __int_as_float(0x7fc00000);
       if (p.d_cls != nullptr) {
         const float fm1 = (p.gamma == 2.0f) ? om : ((om > 0.0f) ? powf(om, p.gamma - 1.0f) : 0.0f);
-        const float coef = a * (p.gamma * fm1 * pt * ce + f) * inv_b;
+        const float coef = t_ok ? a * (p.gamma * fm1 * pt * ce + f) * inv_b : 0.0f;
         for (int j = 0; j < C; ++j) {
           const float pj = expf(z[j] - lse);
           p.d_cls[static_cast<size_t>(b) * C + j] = coef * (pj - (j == t ? 1.0f : 0.0f));
         }
       }
     }
-    const float y = static_cast<float>(p.sev_t[b]);
+    const float y = p.sev_t[b];
     if (p.ord_logits != nullptr) {   // BCE-with-logits on [y > k] (losses.py:48-72)
       const int K = C - 1;
       const float inv = inv_b / static_cast<float>(K);
       for (int k = 0; k < K; ++k) {
         const float z = p.ord_logits[static_cast<size_t>(b) * K + k];
-        const float t = (p.sev_t[b] > k) ? 1.0f : 0.0f;
+        const float t = (y > static_cast<float>(k)) ? 1.0f : 0.0f;
         l_ord += (fmaxf(z, 0.0f) - z * t + log1pf(expf(-fabsf(z)))) * inv;
         if (p.d_ord != nullptr) p.d_ord[static_cast<size_t>(b) * K + k] = (1.0f / (1.0f + expf(-z)) - t) * inv;
       }
@@ -307,7 +311,7 @@ int rvk_joint_loss_launch(const JointLossArgs& a, cudaStream_t stream) {
   p.cls_logits = a.cls_logits; p.num_classes = a.num_classes;
   p.ord_logits = a.ord_logits; p.mu = a.mu; p.log_var = a.log_var; p.kan = a.kan;
   p.class_t = reinterpret_cast<const long long*>(a.class_t);
-  p.sev_t = reinterpret_cast<const long long*>(a.sev_t);
+  p.sev_t = static_cast<const float*>(a.sev_t);
   p.alpha = a.alpha; p.gamma = a.gamma; p.batch = a.batch; p.sums = a.sums_ws;
   p.d_cls = a.d_cls; p.d_ord = a.d_ord; p.d_mu = a.d_mu; p.d_lv = a.d_lv; p.d_kan = a.d_kan;
   joint_loss_kernel<<<(a.batch + 255) / 256, 256, 0, stream>>>(p);

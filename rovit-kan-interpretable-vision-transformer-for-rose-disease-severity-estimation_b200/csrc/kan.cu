@@ -397,6 +397,9 @@ int rvk_kan_layer_fwd_launch(const KanLayerDesc& L, const float* x, float* y, in
   const int64_t wp = static_cast<int64_t>(in_pad) * 8 * out_pad;
   float* Wp = workspace;
   float* WpT = with_backward ? workspace + wp : nullptr;
+  // algorithmic: dense-7 contraction + linear branch; x read, y written
+  RvkScopedTimer timer(stream, 2.0 * batch * L.in_features * 8.0 * L.out_features,
+                       4.0 * batch * (L.in_features + L.out_features), RVK_T_KAN_FWD);
   Knots kn;
   for (int i = 0; i < kKnots; ++i) kn.k[i] = L.knots_host[i];
   const int pack_blocks = static_cast<int>((wp + 255) / 256 < 1184 ? (wp + 255) / 256 : 1184);
@@ -453,6 +456,9 @@ int rvk_kan_layer_bwd_launch(const KanLayerDesc& L, const float* x, const float*
   const int64_t wp = static_cast<int64_t>(in_pad) * 8 * out_pad;
   const float* WpT = workspace + wp;      // written by the forward launch
   float* dWp = workspace + 2 * wp;
+  // algorithmic: dW and dx contractions; x, y, gy read, dx written
+  RvkScopedTimer timer(stream, 2.0 * batch * L.in_features * 8.0 * L.out_features * ((dspline ? 1 : 0) + (dx ? 1 : 0)),
+                       4.0 * batch * (L.in_features * (dx ? 2.0 : 1.0) + 2.0 * L.out_features), RVK_T_KAN_BWD);
   Knots kn;
   for (int i = 0; i < kKnots; ++i) kn.k[i] = L.knots_host[i];
   if (dspline != nullptr) {
@@ -545,6 +551,8 @@ int rvk_heads_fused_launch(const float* features, const float* ws, const float* 
   RVK_SET_MAX_SMEM(heads_fused_kernel, kHfSmemBytes);
   Knots kn;
   for (int i = 0; i < kKnots; ++i) kn.k[i] = knots_host[i];
+  RvkScopedTimer timer(stream, 2.0 * batch * (3.0 * 192 * 128 + 128.0 * 9 + 8.0 * (192 * 64 + 64 * 16 + 16)), 4.0 * batch * (192 + 10),
+                       RVK_T_HEADS_FUSED);
   heads_fused_kernel<<<(batch + kHfS - 1) / kHfS, kHfThreads, kHfSmemBytes, stream>>>(features, ws, kn, batch, cls, ord, mu,
                                                                                      log_var, kan);
   return rvk_launch_check();

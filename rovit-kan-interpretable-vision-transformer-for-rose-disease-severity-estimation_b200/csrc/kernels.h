@@ -55,7 +55,8 @@ int rvk_attention_bwd_tc_launch(const void* qkv, const void* ctx, const void* dc
                                 int batch, cudaStream_t stream);
 
 // ---- token-stream kernels (encoder_kernels.cu) -----------------------------------------------------
-int rvk_im2col_launch(const void* images, int images_bf16, void* patches_bf16, int batch, cudaStream_t stream);
+// fmt: 0 fp32, 1 bf16, 2 uint8 (+ norm6_host = {scale[3], shift[3]}: pixel * scale[c] + shift[c])
+int rvk_im2col_launch(const void* images, int fmt, void* patches_bf16, int batch, const float* norm6_host, cudaStream_t stream);
 int rvk_token_table_launch(const float* cls_token, const float* pos_embed, const float* patch_bias, float* table,
                            cudaStream_t stream);
 int rvk_cast_bf16_launch(const float* src, void* dst, int64_t n, cudaStream_t stream);
@@ -130,7 +131,7 @@ struct JointLossArgs {
   const float* ord_logits = nullptr;
   const float* mu = nullptr; const float* log_var = nullptr;
   const float* kan = nullptr;
-  const int64_t* class_t = nullptr; const int64_t* sev_t = nullptr;
+  const int64_t* class_t = nullptr; const float* sev_t = nullptr;
   const float* alpha = nullptr;
   float gamma = 2.0f, lambda_ord = 1.0f, mu_unc = 0.5f, nu_kan = 0.5f;
   int batch = 0;

@@ -3,6 +3,7 @@
 #include <atomic>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "common.cuh"
 
@@ -32,6 +33,66 @@ void rvk_set_last_cuda_error(int code, const char* what) {
 }
 const char* rvk_last_error_cstr() { return g_last_error.c_str(); }
 void rvk_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+// ---- in-situ launch timing ------------------------------------------------------------------------------------
+namespace {
+struct TimedLaunch { cudaEvent_t beg, end; double flops, bytes; int kind; };
+bool g_timing = false;
+std::mutex g_timing_mu;
+std::vector<TimedLaunch*> g_timed;
+std::vector<TimedLaunch*> g_timer_pool;
+double g_kind_ms[RVK_T_COUNT], g_kind_flops[RVK_T_COUNT], g_kind_bytes[RVK_T_COUNT];
+int g_kind_n[RVK_T_COUNT];
+const char* const kKindNames[RVK_T_COUNT] = {"gemm_nt_kernel", "gemm_tn_kernel", "mlp_fused_kernel", "attn_fwd_tc_kernel",
+                                             "attn_bwd_tc_kernel", "layernorm_bwd_kernel", "kan_fwd", "kan_bwd", "heads_fused_kernel",
+                                             "im2col_kernel", "optimizer_tail", "heads_train"};
+}  // namespace
+
+void* rvk_timer_begin(cudaStream_t s, double flops, double bytes, int kind) {
+  if (!g_timing || kind < 0 || kind >= RVK_T_COUNT) return nullptr;
+  TimedLaunch* t = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_timing_mu);
+    if (!g_timer_pool.empty()) { t = g_timer_pool.back(); g_timer_pool.pop_back(); }
+  }
+  if (t == nullptr) {
+    t = new TimedLaunch();
+    if (cudaEventCreate(&t->beg) != cudaSuccess || cudaEventCreate(&t->end) != cudaSuccess) { delete t; return nullptr; }
+  }
+  t->flops = flops; t->bytes = bytes; t->kind = kind;
+  cudaEventRecord(t->beg, s);
+  return t;
+}
+void rvk_timer_end(void* handle, cudaStream_t s) {
+  TimedLaunch* t = static_cast<TimedLaunch*>(handle);
+  cudaEventRecord(t->end, s);
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  g_timed.push_back(t);
+}
+void rvk_timing_enable_impl(int on) { g_timing = on != 0; }
+// Sums the device time of every timed launch since the last collect (caller must have synchronised the device).
+int rvk_timing_collect_impl() {
+  std::lock_guard<std::mutex> lk(g_timing_mu);
+  for (int k = 0; k < RVK_T_COUNT; ++k) { g_kind_ms[k] = g_kind_flops[k] = g_kind_bytes[k] = 0.0; g_kind_n[k] = 0; }
+  int n = 0;
+  for (TimedLaunch* t : g_timed) {
+    float e = 0.0f;
+    if (cudaEventElapsedTime(&e, t->beg, t->end) == cudaSuccess) {
+      g_kind_ms[t->kind] += e; g_kind_flops[t->kind] += t->flops; g_kind_bytes[t->kind] += t->bytes; ++g_kind_n[t->kind]; ++n;
+    }
+    g_timer_pool.push_back(t);
+  }
+  g_timed.clear();
+  return n;
+}
+int rvk_timing_kind_impl(int kind, double* ms, double* flops, double* bytes) {
+  if (kind < 0 || kind >= RVK_T_COUNT) return -1;
+  if (ms) *ms = g_kind_ms[kind];
+  if (flops) *flops = g_kind_flops[kind];
+  if (bytes) *bytes = g_kind_bytes[kind];
+  return g_kind_n[kind];
+}
+const char* rvk_timing_kind_name_impl(int kind) { return (kind >= 0 && kind < RVK_T_COUNT) ? kKindNames[kind] : nullptr; }
 long long rvk_launch_count_impl() { return g_launches.load(std::memory_order_relaxed); }
 
 int rvk_make_tmap_2d(CUtensorMap* out, const void* base, int dtype, int64_t rows, int64_t cols, int64_t ld,

@@ -107,12 +107,43 @@ class VisionTransformerB200(nn.Module):
         return ops.EncoderFn.apply(self._state, *ops.nograd(x, *self._ordered_params()))
 
 
+PRETRAINED_ENV = 'ROVITKAN_PRETRAINED'
+
+
+def _pretrained_state_dict(name: str):
+    """Weights for `pretrained=True` (the reference's default, configs/config.py:60), without a network:
+    $ROVITKAN_PRETRAINED = path of a timm `deit_tiny_patch16_224` checkpoint (a state_dict, or a dict holding one under
+    'model' / 'state_dict' / 'model_state_dict'; classifier `head.*` keys are ignored), or `timm` itself if it is
+    importable (its own cache / download), or the literal `random` to opt in to a randomly initialised trunk."""
+    import os
+    src = os.environ.get(PRETRAINED_ENV, '')
+    if src.lower() == 'random':
+        warnings.warn(f'{PRETRAINED_ENV}=random: pretrained=True was requested but the trunk is randomly initialised', stacklevel=4)
+        return None
+    if src:
+        obj = torch.load(src, map_location='cpu', weights_only=False)
+        for key in ('model', 'state_dict', 'model_state_dict'):
+            if isinstance(obj, dict) and key in obj and isinstance(obj[key], dict):
+                obj = obj[key]
+        sd = {k[len('backbone.model.'):] if k.startswith('backbone.model.') else k: v for k, v in obj.items()}
+        return {k: v for k, v in sd.items() if not k.startswith(('head.', 'head_dist.', 'fc_norm.'))}
+    try:
+        import timm
+    except ImportError:
+        raise RuntimeError(
+            f"pretrained=True needs ImageNet weights for {name}, and this machine has neither `timm` nor a checkpoint: set "
+            f"{PRETRAINED_ENV}=/path/to/deit_tiny_patch16_224.pth (timm parameter names), or {PRETRAINED_ENV}=random to train "
+            f"from a random initialisation on purpose, or construct the model with pretrained=False.") from None
+    return timm.create_model(name, pretrained=True, num_classes=0).state_dict()
+
+
 def create_model(name: str = 'deit_tiny_patch16_224', pretrained: bool = False, num_classes: int = 0, **kwargs):
     """Stand-in for the one `timm.create_model` call the reference makes (models/backbone.py:12-16)."""
     if name != 'deit_tiny_patch16_224' or num_classes != 0:
         raise NotImplementedError('only deit_tiny_patch16_224 with num_classes=0 (what RoViT-KAN uses) is built')
+    model = VisionTransformerB200()
     if pretrained:
-        warnings.warn('pretrained=True: no network access from this implementation; the trunk is randomly '
-                      'initialised. Load a timm deit_tiny_patch16_224 checkpoint with load_state_dict '
-                      '(parameter names are timm\'s).', stacklevel=3)
-    return VisionTransformerB200()
+        sd = _pretrained_state_dict(name)
+        if sd is not None:
+            model.load_state_dict(sd, strict=True)
+    return model

@@ -170,7 +170,7 @@ class JointLossFn(torch.autograd.Function):
         t = lambda v: None if v is None else _f32c(v)
         cl, ol, m, lv, kn = t(cls_logits), t(ord_logits), t(mu), t(log_var), t(kan)
         ct = class_t.to(device=dev, dtype=torch.int64).contiguous()
-        st = sev_t.to(device=dev, dtype=torch.int64).contiguous()
+        st = sev_t.to(device=dev, dtype=torch.float32).contiguous()      # the reference casts severities with .float() (losses.py:92,112)
         al = None if alpha is None else alpha.to(device=dev, dtype=torch.float32).contiguous()
         out = torch.empty(5, device=dev, dtype=torch.float32)
         sums = torch.empty(4, device=dev, dtype=torch.float32)
@@ -211,12 +211,23 @@ class EncoderState:
         self.wkey = None
         self.infer_ws = None
         self.infer_key = None
+        # uint8 input: (pixel / 255 - mean) / std, ImageNet statistics as in the reference's transforms
+        self.pixel_mean = (0.485, 0.456, 0.406)
+        self.pixel_std = (0.229, 0.224, 0.225)
+
+    def pixel_scale_shift(self):
+        scale = [1.0 / (255.0 * s) for s in self.pixel_std]
+        shift = [-m / s for m, s in zip(self.pixel_mean, self.pixel_std)]
+        return scale, shift
 
     def param_table(self, tensors):
         return (C.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
 
-    def weights(self, params, training: bool, device):
-        key = (training, tuple(p.data_ptr() for p in params), tuple(p._version for p in params))
+    def weights(self, params, training: bool, device, key_params=None):
+        # the key comes from the tensors the CALLER owns (`key_params`): for a non-fp32 module `params` are fresh
+        # `.float()` copies that sit at version 0 (and usually at the same address) on every call
+        kp = params if key_params is None else key_params
+        key = (training, tuple(p.data_ptr() for p in kp), tuple(p._version for p in kp), tuple(p.dtype for p in kp))
         if self.wbuf is None or self.wkey != key:
             lib = _lib.load()
             nbytes = lib.rvk_encoder_weight_bytes(int(training))
@@ -247,9 +258,12 @@ class EncoderFn(torch.autograd.Function):
             raise ValueError(f'expected images of shape (B, 3, 224, 224), got {tuple(images.shape)}')
         for p in params:
             require_cuda(p, 'DeiTTinyBackbone parameters')
-        # bf16 images are consumed as they are (the trunk rounds pixels to bf16 first anyway); anything else as fp32
+        # bf16 images are consumed as they are (the trunk rounds pixels to bf16 first anyway); uint8 pixels are normalised
+        # inside the patch gather with state.pixel_norm (ToTensor + Normalize folded in); anything else runs as fp32
         img_bf16 = images.dtype == torch.bfloat16
-        img = images.contiguous() if img_bf16 else _f32c(images)
+        img_u8 = images.dtype == torch.uint8
+        img = images.contiguous() if (img_bf16 or img_u8) else _f32c(images)
+        owner_params = params
         params = tuple(p.float() if p.dtype != torch.float32 else p for p in params)
         batch = img.shape[0]
         dev = img.device
@@ -258,14 +272,19 @@ class EncoderFn(torch.autograd.Function):
         feats = torch.empty(batch, 192, device=dev, dtype=torch.float32)
         pc = [p.detach() for p in params]
         with torch.cuda.device(dev):
-            wbuf = state.weights(pc, training, dev)
+            wbuf = state.weights(pc, training, dev, key_params=owner_params)
             if training:
                 nbytes = _lib.load().rvk_encoder_workspace_bytes(batch, 1, chunk)
                 ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)
             else:
                 ws = state.inference_workspace(batch, chunk, dev)
-            _lib.call('rvk_encoder_forward_bf16' if img_bf16 else 'rvk_encoder_forward', state.param_table(pc), _p(wbuf),
-                      _p(img), batch, int(training), chunk, _p(ws), _p(feats), _stream())
+            if img_u8:
+                scale, shift = state.pixel_scale_shift()
+                _lib.call('rvk_encoder_forward_u8', state.param_table(pc), _p(wbuf), _p(img), _host_floats(scale),
+                          _host_floats(shift), batch, int(training), chunk, _p(ws), _p(feats), _stream())
+            else:
+                _lib.call('rvk_encoder_forward_bf16' if img_bf16 else 'rvk_encoder_forward', state.param_table(pc), _p(wbuf),
+                          _p(img), batch, int(training), chunk, _p(ws), _p(feats), _stream())
         if training:
             ctx.state, ctx.ws, ctx.wbuf, ctx.batch, ctx.chunk = state, ws, wbuf, batch, chunk
             ctx.params = pc

@@ -42,7 +42,7 @@ class OrdinalBCELoss(nn.Module):
 
     def forward(self, cum_logits: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
         dummy = torch.zeros(cum_logits.shape[0], self.num_classes, device=cum_logits.device)
-        zeros = torch.zeros_like(targets)
+        zeros = torch.zeros(targets.shape, dtype=torch.int64, device=targets.device)
         return _joint(dummy, cum_logits, None, None, None, zeros, targets, None, 2.0, 1.0, 0.0, 0.0)[1]
 
 
@@ -54,8 +54,8 @@ class UncertaintyLoss(nn.Module):
 
     def forward(self, mu: torch.Tensor, log_var: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
         dummy = torch.zeros(mu.shape[0], 2, device=mu.device)
-        t = targets.reshape(-1).long()
-        return _joint(dummy, None, mu, log_var, None, torch.zeros_like(t), t, None, 2.0, 0.0, 1.0, 0.0)[2]
+        t = targets.reshape(-1).float()
+        return _joint(dummy, None, mu, log_var, None, torch.zeros_like(t, dtype=torch.int64), t, None, 2.0, 0.0, 1.0, 0.0)[2]
 
 
 class KANRegressionLoss(nn.Module):
@@ -66,8 +66,8 @@ class KANRegressionLoss(nn.Module):
 
     def forward(self, predictions: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
         dummy = torch.zeros(predictions.shape[0], 2, device=predictions.device)
-        t = targets.reshape(-1).long()
-        return _joint(dummy, None, None, None, predictions, torch.zeros_like(t), t, None, 2.0, 0.0, 0.0, 1.0)[3]
+        t = targets.reshape(-1).float()
+        return _joint(dummy, None, None, None, predictions, torch.zeros_like(t, dtype=torch.int64), t, None, 2.0, 0.0, 0.0, 1.0)[3]
 
 
 class JointLoss(nn.Module):

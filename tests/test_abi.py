@@ -97,3 +97,59 @@ def test_product_never_imports_the_oracle():
             if f.endswith(('.py', '.cu', '.cuh', '.h')):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M), os.path.join(dirpath, f)
+
+
+def test_pretrained_true_needs_weights_or_an_explicit_opt_in(tmp_path, monkeypatch):
+    """pretrained=True (the reference default) must not silently train from scratch."""
+    from rovitkan_b200.models import deit
+    from rovitkan_b200.models import RoViTKAN
+    monkeypatch.delenv(deit.PRETRAINED_ENV, raising=False)
+    try:
+        import timm  # noqa: F401
+        have_timm = True
+    except ImportError:
+        have_timm = False
+    if not have_timm:
+        with pytest.raises(RuntimeError, match='ROVITKAN_PRETRAINED'):
+            RoViTKAN(pretrained=True)
+    monkeypatch.setenv(deit.PRETRAINED_ENV, 'random')
+    with pytest.warns(UserWarning, match='randomly initialised'):
+        RoViTKAN(pretrained=True)
+    # a timm-style checkpoint (with a classifier head that num_classes=0 drops) is loaded strictly
+    src = deit.create_model(pretrained=False)
+    sd = {k: torch.full_like(v, 0.25) for k, v in src.state_dict().items()}
+    sd['head.weight'] = torch.zeros(1000, 192)
+    sd['head.bias'] = torch.zeros(1000)
+    ck = tmp_path / 'deit_tiny.pth'
+    torch.save({'model': sd}, ck)
+    monkeypatch.setenv(deit.PRETRAINED_ENV, str(ck))
+    m = RoViTKAN(pretrained=True)
+    assert all(bool((p == 0.25).all()) for p in m.backbone.model.parameters())
+
+
+def test_trunk_weight_cache_key_follows_the_owner_parameters():
+    """for a non-fp32 module the trunk received fresh .float() copies (version 0, recycled address) and
+    kept stale bf16 weights after optimizer.step(); the key is now taken from the owner's parameters."""
+    from rovitkan_b200 import ops
+    st = ops.EncoderState()
+    seen = []
+    st.wbuf = torch.empty(1)
+
+    class _Lib:
+        @staticmethod
+        def rvk_encoder_weight_bytes(training):
+            return 1
+    real_load, real_call, real_stream = ops._lib.load, ops._lib.call, ops._stream
+    ops._lib.load = lambda: _Lib
+    ops._lib.call = lambda name, *a: seen.append(name)
+    ops._stream = lambda: 0
+    try:
+        owner = [torch.zeros(4, dtype=torch.bfloat16)]
+        for _ in range(2):
+            st.weights([owner[0].float()], False, torch.device('cpu'), key_params=owner)
+        assert seen == ['rvk_encoder_prepare_weights']            # second call: cache hit
+        owner[0].add_(1)                                          # what optimizer.step() does
+        st.weights([owner[0].float()], False, torch.device('cpu'), key_params=owner)
+        assert len(seen) == 2
+    finally:
+        ops._lib.load, ops._lib.call, ops._stream = real_load, real_call, real_stream

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _run(*extra):
-    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1', *extra],
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '1', '--no-subs', *extra],
                          capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.startswith('{')]
@@ -30,6 +30,17 @@ def test_reference_arm_prints_the_contract_line():
     assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and 'batch 32' in cb['sample']
     assert d['e2e'] == {'value': d['value'], 'unit': 'images/sec', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
     assert d['gpu_launches'] == 0
+    # same config object as our arm (the sample description lives outside it), same warm-up rule (W = max(3, --warmup))
+    assert d['config'] == bench.workload_config(False, 1024, 1) and d['warmup'] == 3
+    # the reference's KAN loop costs per batch: one forward at the labelled batch is reported next to the batch-32 steps
+    assert d['same_batch']['batch'] == 1024 and d['same_batch']['value'] > 0
+
+
+def test_cpu_reference_kan_leg_runs_the_loop_port():
+    sys.path.insert(0, ROOT)
+    import bench
+    r = bench.cpu_reference_kan(batches=(4,), dims=(12, 5, 1))
+    assert r['kind'] == 'port' and r['runs'][0]['batch'] == 4 and r['runs'][0]['fwd_bwd_ms'] > r['runs'][0]['fwd_ms'] > 0
 
 
 def test_reference_arm_other_ranks_stay_silent():

@@ -20,7 +20,8 @@ PLOT_STUBS = ("import sys\nfrom unittest import mock\n"
 
 
 def _run(code, cwd, timeout=300, env_extra=None):
-    env = dict(os.environ, PYTHONPATH=ROOT, ROVITKAN_SYNTH_PER_CLASS='4', ROVITKAN_DATA_WORKERS='0', CUDA_VISIBLE_DEVICES='')
+    env = dict(os.environ, PYTHONPATH=ROOT, ROVITKAN_SYNTH_PER_CLASS='4', ROVITKAN_DATA_WORKERS='0', CUDA_VISIBLE_DEVICES='',
+               ROVITKAN_PRETRAINED='random')      # the reference's config asks for pretrained=True; no weights on this box
     env.update(env_extra or {})
     return subprocess.run([sys.executable, '-c', code], cwd=str(cwd), env=env, capture_output=True, text=True, timeout=timeout)
 
