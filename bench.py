@@ -455,6 +455,11 @@ def bench_train(ctx, K, W, batch, with_variants=True):
     opt, fused_tail = build_optimizer(model, not os.environ.get('RVK_TORCH_OPTIMIZER'))
     params = [p for p in model.parameters()]
     ev = {}
+    from rovitkan_b200 import dist as rdist
+    overlap = ctx.world > 1 and not os.environ.get('RVK_DP_NO_OVERLAP') and rdist.enable_overlap(int(os.environ.get('RVK_DP_BUCKETS', '3')))
+    average = True
+    if ctx.world > 1 and fused_tail:
+        opt.grad_mult, average = 1.0 / ctx.world, False      # the 1/world scale rides in the optimizer kernel
 
     def mark(name):
         if ev.get('on'):
@@ -474,7 +479,7 @@ def bench_train(ctx, K, W, batch, with_variants=True):
         loss.backward()
         mark('backward_done')
         if ctx.world > 1:
-            ev['collectives'] = all_reduce_gradients(params, ctx.world)
+            ev['collectives'] = all_reduce_gradients(params, ctx.world, average=average)
         mark('allreduce_done')
         if fused_tail:
             opt.step()                        # unscale + global-norm clip + AdamW + weight shadows in one pass
@@ -512,7 +517,18 @@ def bench_train(ctx, K, W, batch, with_variants=True):
         ph['clip_optimizer'] += c.elapsed_time(d)
     res['phases_ms'] = {k: ctx.max_over_ranks(v / K) for k, v in ph.items()}
     res['allreduce'] = {'ms_exposed': res['phases_ms']['allreduce_exposed'], 'bytes': sum(p.numel() for p in params) * 4,
-                        'collectives_per_step': ev.get('collectives', 0)}
+                        'collectives_per_step': ev.get('collectives', 0), 'overlapped_with_backward': bool(overlap),
+                        'buckets': rdist.overlap_state()['buckets'] if overlap else 0,
+                        'scale_1_over_world': 'folded into the optimizer kernel' if not average else 'separate mul_'}
+    if ctx.world > 1:      # the same payload reduced on its own (nothing to hide behind): hidden = standalone - exposed
+        buf = torch.zeros(sum(p.numel() for p in params), device=ctx.dev)
+        for _ in range(3):
+            dist.all_reduce(buf)
+        ms_ar = ctx.timed(lambda: dist.all_reduce(buf), 10) / 10
+        res['allreduce']['ms_standalone'] = ms_ar
+        res['allreduce']['ms_hidden'] = max(0.0, ms_ar - res['allreduce']['ms_exposed'])
+        res['allreduce']['algbw_gbs'] = buf.numel() * 4 / (ms_ar * 1e-3) / 1e9
+        del buf
     if with_variants:
         for _ in range(2):
             step(images, cutmix=True)
@@ -540,12 +556,15 @@ def bench_train(ctx, K, W, batch, with_variants=True):
         for p in params:
             p.grad = None
         opt, fused_tail = build_optimizer(model, fused_tail)
+        if ctx.world > 1 and fused_tail:
+            opt.grad_mult = 1.0 / ctx.world
         params = [p for p in model.parameters()]
         for _ in range(3):
             step(images)
         ms_f = ctx.timed(lambda: step(images), K)
         res['frozen_backbone'] = {'value': batch * ctx.world * K / (ms_f / 1e3), 'ms_per_step': ms_f / K,
                                   'trainable_params': sum(p.numel() for p in params if p.requires_grad)}
+    rdist.disable_overlap()
     del model, opt, images, host_images
     torch.cuda.empty_cache()
     return res
@@ -652,6 +671,26 @@ def bench_sweep(ctx, K, W):
 
 
 # ------------------------------------------------------------------------------------------ PyTorch eager on the same GPU
+def eager_trunk_sdpa(sd, x, prefix='backbone.model.'):
+    """timm's deit_tiny_patch16_224 forward as timm >= 0.9 runs it on a GPU: library kernels only (cuDNN conv, cuBLAS linears,
+    F.scaled_dot_product_attention = the flash / mem-efficient SDPA backend, ATen LayerNorm / GELU)."""
+    import torch
+    import torch.nn.functional as F
+    g = lambda k: sd[prefix + k]
+    t = F.conv2d(x, g('patch_embed.proj.weight').to(x.dtype), g('patch_embed.proj.bias').to(x.dtype), stride=16).flatten(2).transpose(1, 2)
+    t = torch.cat([g('cls_token').to(t.dtype).expand(t.shape[0], -1, -1), t], dim=1) + g('pos_embed').to(t.dtype)
+    B, N, D = t.shape
+    for i in range(12):
+        b = f'blocks.{i}.'
+        h = F.layer_norm(t, (D,), g(b + 'norm1.weight'), g(b + 'norm1.bias'), 1e-6)
+        qkv = F.linear(h, g(b + 'attn.qkv.weight'), g(b + 'attn.qkv.bias')).reshape(B, N, 3, 3, 64).permute(2, 0, 3, 1, 4)
+        a = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2]).transpose(1, 2).reshape(B, N, D)
+        t = t + F.linear(a, g(b + 'attn.proj.weight'), g(b + 'attn.proj.bias'))
+        h = F.layer_norm(t, (D,), g(b + 'norm2.weight'), g(b + 'norm2.bias'), 1e-6)
+        t = t + F.linear(F.gelu(F.linear(h, g(b + 'mlp.fc1.weight'), g(b + 'mlp.fc1.bias'))), g(b + 'mlp.fc2.weight'), g(b + 'mlp.fc2.bias'))
+    return F.layer_norm(t, (D,), g('norm.weight'), g('norm.bias'), 1e-6)[:, 0]
+
+
 def gpu_eager_baseline(ctx, batch_infer=1024, batch_train=256, steps=5):
     """The "existing Blackwell kernels" bar (SURVEY.md section 2 / BASELINE.md section 3): the oracle restatement of the
     reference modules run by PyTorch eager on this B200 (cuBLAS / SDPA / ATen kernels; the KAN contraction vectorised as an
@@ -668,13 +707,14 @@ def gpu_eager_baseline(ctx, batch_infer=1024, batch_train=256, steps=5):
     x = torch.randn(batch_infer, 3, 224, 224, generator=g).to(ctx.dev)
     out = {'note': 'oracle/vit.py + vectorised KAN + heads through PyTorch eager on the same GPU, CUDA-event timed', 'steps': steps}
 
-    def fwd(autocast):
+    def fwd(autocast, sdpa=False):
+        trunk = eager_trunk_sdpa if sdpa else (lambda s, xx: ovit.forward_functional(s, xx, prefix='backbone.model.'))
         with torch.no_grad():
             if autocast:
                 with torch.autocast('cuda', dtype=torch.bfloat16):
-                    f = ovit.forward_functional(sd, x, prefix='backbone.model.').float()
+                    f = trunk(sd, x).float()
             else:
-                f = ovit.forward_functional(sd, x, prefix='backbone.model.')
+                f = trunk(sd, x)
             return omodel.heads_forward(sd, f, 4)['kan_severity']
 
     def time_it(fn, n):
@@ -688,9 +728,13 @@ def gpu_eager_baseline(ctx, batch_infer=1024, batch_train=256, steps=5):
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n
-    for tag, ac in (('infer_fp32_no_tf32', False), ('infer_bf16_autocast', True)):
-        ms = time_it(lambda: fwd(ac), steps)
+    for tag, ac, sdpa in (('infer_fp32_no_tf32', False, False), ('infer_bf16_autocast', True, False),
+                          ('infer_bf16_autocast_sdpa', True, True)):
+        ms = time_it(lambda: fwd(ac, sdpa), steps)
         out[tag] = {'batch': batch_infer, 'ms_per_step': ms, 'images_per_sec': batch_infer / (ms / 1e3)}
+    with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16):       # the SDPA restatement is the same function
+        a, b = eager_trunk_sdpa(sd, x[:8]).float(), ovit.forward_functional(sd, x[:8], prefix='backbone.model.').float()
+    out['sdpa_trunk_vs_oracle_rel_l2'] = float((a - b).norm() / b.norm())
     del x
     sdt = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and 'knots' not in k else v) for k, v in sd.items()}
     xt = torch.randn(batch_train, 3, 224, 224, generator=g).to(ctx.dev)
@@ -701,10 +745,10 @@ def gpu_eager_baseline(ctx, batch_infer=1024, batch_train=256, steps=5):
             if v.requires_grad:
                 v.grad = None
         with torch.autocast('cuda', dtype=torch.bfloat16):
-            f = ovit.forward_functional(sdt, xt, prefix='backbone.model.').float()
+            f = eager_trunk_sdpa(sdt, xt).float()
         olosses.joint(omodel.heads_forward(sdt, f, 4), y, y, 4)['total_loss'].backward()
     ms = time_it(train_step, steps)
-    out['train_bf16_autocast_fwd_bwd'] = {'batch': batch_train, 'ms_per_step': ms, 'images_per_sec': batch_train / (ms / 1e3),
+    out['train_bf16_autocast_sdpa_fwd_bwd'] = {'batch': batch_train, 'ms_per_step': ms, 'images_per_sec': batch_train / (ms / 1e3),
                                           'note': 'forward + joint loss + backward, no optimizer'}
     torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
     del sd, sdt, xt
@@ -744,10 +788,10 @@ def run_ours(args, rank, local_rank, world):
             if rank == 0 and world == 1:
                 try:
                     line['gpu_eager_baseline'] = gpu_eager_baseline(ctx)
-                    fast = line['gpu_eager_baseline']['infer_bf16_autocast']['images_per_sec']
+                    fast = line['gpu_eager_baseline']['infer_bf16_autocast_sdpa']['images_per_sec']
                     line['gpu_eager_baseline']['ours_over_eager_bf16_infer'] = line['value'] / fast
                     line['gpu_eager_baseline']['ours_over_eager_bf16_train'] = (
-                        line['train']['value'] / line['gpu_eager_baseline']['train_bf16_autocast_fwd_bwd']['images_per_sec'])
+                        line['train']['value'] / line['gpu_eager_baseline']['train_bf16_autocast_sdpa_fwd_bwd']['images_per_sec'])
                 except Exception as e:      # a baseline leg must never take the measurement down
                     line['gpu_eager_baseline'] = {'error': repr(e)}
         if rank == 0 and world == 1 and not args.no_cpu_baseline:

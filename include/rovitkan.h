@@ -55,6 +55,10 @@ int64_t rvk_kan_layer_workspace_floats(int in_features, int out_features, int wi
 /* BSplineBasis.compute_basis (models/kan.py:10-44): t holds n already-normalised inputs, out is [n,7]. */
 int rvk_kan_basis(const float* t, const float* knots_host, int num_knots_total, int64_t n, float* out,
                   void* stream);
+/* with_backward: bit 0 = the matching backward call will follow (its operands are prepared too); bit 1 = `workspace`
+ * already holds the packed / split weights of exactly these parameters from an earlier call with the same bit 0
+ * (callers key this on the parameter versions), so the prepare launches are skipped.  Layers with <= 16 outputs run a
+ * shuffle-reduction kernel that needs no prepared weights at all. */
 int rvk_kan_layer_forward(const float* x, const float* spline, const float* lin_w, const float* lin_b,
                           const float* knots_host, int num_knots_total, int batch, int in_features,
                           int out_features, int act, float* y, float* workspace, int with_backward,
@@ -129,6 +133,34 @@ int rvk_encoder_forward_u8(const void* const* params_host, const void* wbuf, con
 int rvk_encoder_backward(const void* const* params_host, const void* wbuf, void* workspace,
                          const float* dfeatures, int batch, int chunk_images, void* const* grads_host,
                          void* stream);
+
+/* The same backward pass in pieces, so that a data-parallel caller can start the gradient all-reduce of finished blocks
+ * while earlier blocks are still being differentiated ("overlapped with the encoder backward in 2-3
+ * buckets: heads + KAN first, then blocks 11 -> 0").  Stages: 0 = final LayerNorm, 1 + j = block 11 - j, 13 = patch / class
+ * token / position embedding; call with consecutive [stage_begin, stage_end) ranges covering 0..14 in order, whole batch in
+ * one chunk.  After stage 1 + j the gradients of blocks 11 - j .. 11 and of norm.* are final, plus mlp.fc2.bias of block
+ * 10 - j (it is produced by the LayerNorm backward of the block above it). */
+#define RVK_ENCODER_BACKWARD_STAGES 14
+int rvk_encoder_backward_range(const void* const* params_host, const void* wbuf, void* workspace,
+                               const float* dfeatures, int batch, int chunk_images, void* const* grads_host,
+                               int stage_begin, int stage_end, void* stream);
+
+/* ---- fused optimizer tail ---------------------------------------------------------------
+ * Replaces what the reference's trainer runs after loss.backward() (training/trainer.py:118-129): GradScaler.unscale_ and
+ * its inf check, clip_grad_norm_(parameters, max_norm), AdamW.step with the two learning-rate groups of
+ * training/optimizer.py:18-25 -- three launches over all tensors.  `params_host` / `grads_host`: host arrays of n DEVICE
+ * pointers (fp32; a NULL gradient skips that tensor as torch does); `group_host[i]` selects lr_host[group]; exp_avg /
+ * exp_avg_sq: rvk_optimizer_state_floats(n, numel) floats each, zero-initialised by the caller; state4 (device, zeroed
+ * once): {scratch, step count, last gradient norm (after grad_mult and unscaling), 1 if the last step ran}.
+ * Gradients are used as g * grad_mult / *grad_scale_dev (grad_scale_dev may be NULL); when the resulting global norm is
+ * non-finite or *found_inf_dev != 0 the whole update is skipped and the step count is not advanced (GradScaler.step).
+ * max_grad_norm <= 0 disables clipping.  AdamW arithmetic follows torch's fused kernel (decoupled weight decay,
+ * lerp moment update, bias corrections in double). */
+int64_t rvk_optimizer_state_floats(int n_tensors, const int64_t* numel_host);
+int rvk_optimizer_step(int n_tensors, void* const* params_host, const void* const* grads_host, const int64_t* numel_host,
+                       const int* group_host, float* exp_avg, float* exp_avg_sq, float* state4, const float* lr_host,
+                       int n_groups, float beta1, float beta2, float eps, float weight_decay, float max_grad_norm,
+                       float grad_mult, const float* grad_scale_dev, const float* found_inf_dev, void* stream);
 
 /* ---- fused inference tail: all four heads of RoViTKAN.forward (models/rovit_kan.py:96-124 in eval mode) in ONE kernel:
  * the three Linear-ReLU-Linear heads (models/heads.py:17-22, 38-43, 91-102, log_var clamped to +-10) and the KAN severity

@@ -39,12 +39,15 @@ SIGNATURES = {
     'rvk_heads_fused': (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P]),
     'rvk_joint_loss_forward': (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     'rvk_joint_loss_backward': (_I, [_P, _P, _I, _F, _P, _I, _P]),
+    'rvk_optimizer_state_floats': (_L, [_I, _P]),
+    'rvk_optimizer_step': (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _F, _F, _P, _P, _P]),
     'rvk_encoder_weight_bytes': (_L, [_I]),
     'rvk_encoder_workspace_bytes': (_L, [_I, _I, _I]),
     'rvk_encoder_prepare_weights': (_I, [_P, _P, _I, _P]),
     'rvk_encoder_forward': (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     'rvk_encoder_forward_bf16': (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     'rvk_encoder_forward_u8': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    'rvk_encoder_backward_range': (_I, [_P, _P, _P, _P, _I, _I, _P, _I, _I, _P]),
     'rvk_encoder_backward': (_I, [_P, _P, _P, _P, _I, _I, _P, _P]),
     'rvk_gemm_nt': (_I, [_I, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _P, _P, _I, _F, _P, _P, _P]),
     'rvk_mlp_fused': (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _F, _P, _I, _I, _P]),

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, 'build')
 LIB = os.path.join(HERE, 'librovitkan.so')
-SOURCES = ['tma_host.cu', 'gemm.cu', 'attention.cu', 'attention_tc.cu', 'encoder_kernels.cu', 'kan.cu', 'heads.cu', 'encoder.cu', 'api.cu']
+SOURCES = ['tma_host.cu', 'gemm.cu', 'attention.cu', 'attention_tc.cu', 'encoder_kernels.cu', 'kan.cu', 'heads.cu', 'encoder.cu', 'optimizer.cu', 'api.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
          '-Xcompiler', '-fvisibility=hidden', '--expt-relaxed-constexpr']

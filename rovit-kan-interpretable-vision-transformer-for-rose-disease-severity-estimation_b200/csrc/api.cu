@@ -87,7 +87,7 @@ int rvk_gemm_timing_collect(double* total_ms_host, double* total_flops_host) {
 
 // ---- KAN
 int64_t rvk_kan_layer_workspace_floats(int in_features, int out_features, int with_backward) {
-  return rvk_kan_workspace_floats(in_features, out_features, with_backward);
+  return rvk_kan_workspace_floats(in_features, out_features, with_backward & 1);
 }
 int rvk_kan_layer_forward(const float* x, const float* spline, const float* lin_w, const float* lin_b,
                           const float* knots_host, int num_knots_total, int batch, int in_features,
@@ -232,7 +232,30 @@ int rvk_encoder_forward_u8(const void* const* params_host, const void* wbuf, con
 int rvk_encoder_backward(const void* const* params_host, const void* wbuf, void* workspace, const float* dfeatures,
                          int batch, int chunk_images, void* const* grads_host, void* stream) {
   if (batch < 0) return RVK_ERR_BAD_ARG;
-  return rvk_encoder_backward_impl(params_host, wbuf, workspace, dfeatures, batch, chunk_images, grads_host, S(stream));
+  return rvk_encoder_backward_impl(params_host, wbuf, workspace, dfeatures, batch, chunk_images, grads_host, 0,
+                                   RVK_ENCODER_BACKWARD_STAGES, S(stream));
+}
+int rvk_encoder_backward_range(const void* const* params_host, const void* wbuf, void* workspace, const float* dfeatures,
+                               int batch, int chunk_images, void* const* grads_host, int stage_begin, int stage_end,
+                               void* stream) {
+  if (batch < 0) return RVK_ERR_BAD_ARG;
+  return rvk_encoder_backward_impl(params_host, wbuf, workspace, dfeatures, batch, chunk_images, grads_host, stage_begin,
+                                   stage_end, S(stream));
+}
+
+// ---- fused optimizer tail
+int64_t rvk_optimizer_state_floats(int n_tensors, const int64_t* numel_host) {
+  if (n_tensors < 0 || (n_tensors > 0 && numel_host == nullptr)) return -1;
+  return rvk_optimizer_state_floats_impl(n_tensors, numel_host);
+}
+int rvk_optimizer_step(int n_tensors, void* const* params_host, const void* const* grads_host, const int64_t* numel_host,
+                       const int* group_host, float* exp_avg, float* exp_avg_sq, float* state4, const float* lr_host,
+                       int n_groups, float beta1, float beta2, float eps, float weight_decay, float max_grad_norm,
+                       float grad_mult, const float* grad_scale_dev, const float* found_inf_dev, void* stream) {
+  if (n_tensors < 0) return RVK_ERR_BAD_ARG;
+  return rvk_optimizer_step_impl(n_tensors, params_host, grads_host, numel_host, group_host, exp_avg, exp_avg_sq, state4,
+                                 lr_host, n_groups, beta1, beta2, eps, weight_decay, max_grad_norm, grad_mult, grad_scale_dev,
+                                 found_inf_dev, S(stream));
 }
 
 // ---- individual kernels

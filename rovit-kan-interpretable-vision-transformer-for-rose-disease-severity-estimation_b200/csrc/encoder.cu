@@ -198,20 +198,30 @@ int64_t rvk_encoder_workspace_bytes_impl(int batch, int training, int chunk_imag
 int rvk_encoder_prepare_weights_impl(const void* const* params, void* wbuf, int training, cudaStream_t s) {
   if (params == nullptr || wbuf == nullptr) return RVK_ERR_BAD_ARG;
   const WeightLayout W = weight_layout(training != 0);
-  RVK_TRY(rvk_cast_bf16_launch(P(params, P_PATCH_W), at(wbuf, W.patch_w), int64_t(kD) * kPatchK, s));
+  RvkCastTable T{};
+  auto add = [&](const float* src, void* dst, int rows, int cols, int mode) -> int {
+    if (T.n == kRvkMaxCastJobs) {
+      RVK_TRY(rvk_cast_multi_launch(T, s));
+      T.n = 0;
+    }
+    T.job[T.n++] = RvkCastJob{src, dst, rows, cols, mode, 0};
+    return RVK_OK;
+  };
+  RVK_TRY(add(P(params, P_PATCH_W), at(wbuf, W.patch_w), kD, kPatchK, 0));
   for (int i = 0; i < kDepth; ++i) {
-    RVK_TRY(rvk_cast_bf16_launch(P(params, bp(i, B_QKVW)), at(wbuf, W.qkv[i]), int64_t(kQkv) * kD, s));
-    RVK_TRY(rvk_cast_bf16_launch(P(params, bp(i, B_PROJW)), at(wbuf, W.proj[i]), int64_t(kD) * kD, s));
-    RVK_TRY(rvk_cast_bf16_launch(P(params, bp(i, B_FC1W)), at(wbuf, W.fc1[i]), int64_t(kMlp) * kD, s));
-    RVK_TRY(rvk_cast_bf16_launch(P(params, bp(i, B_FC2W)), at(wbuf, W.fc2[i]), int64_t(kD) * kMlp, s));
-    if (!training) RVK_TRY(rvk_cast_f16_launch(P(params, bp(i, B_FC2W)), at(wbuf, W.fc2h[i]), int64_t(kD) * kMlp, s));
+    RVK_TRY(add(P(params, bp(i, B_QKVW)), at(wbuf, W.qkv[i]), kQkv, kD, 0));
+    RVK_TRY(add(P(params, bp(i, B_PROJW)), at(wbuf, W.proj[i]), kD, kD, 0));
+    RVK_TRY(add(P(params, bp(i, B_FC1W)), at(wbuf, W.fc1[i]), kMlp, kD, 0));
+    RVK_TRY(add(P(params, bp(i, B_FC2W)), at(wbuf, W.fc2[i]), kD, kMlp, 0));
+    if (!training) RVK_TRY(add(P(params, bp(i, B_FC2W)), at(wbuf, W.fc2h[i]), kD, kMlp, 2));
     if (training) {
-      RVK_TRY(rvk_cast_transpose_bf16_launch(P(params, bp(i, B_QKVW)), at(wbuf, W.qkvT[i]), kQkv, kD, s));
-      RVK_TRY(rvk_cast_transpose_bf16_launch(P(params, bp(i, B_PROJW)), at(wbuf, W.projT[i]), kD, kD, s));
-      RVK_TRY(rvk_cast_transpose_bf16_launch(P(params, bp(i, B_FC1W)), at(wbuf, W.fc1T[i]), kMlp, kD, s));
-      RVK_TRY(rvk_cast_transpose_bf16_launch(P(params, bp(i, B_FC2W)), at(wbuf, W.fc2T[i]), kD, kMlp, s));
+      RVK_TRY(add(P(params, bp(i, B_QKVW)), at(wbuf, W.qkvT[i]), kQkv, kD, 1));
+      RVK_TRY(add(P(params, bp(i, B_PROJW)), at(wbuf, W.projT[i]), kD, kD, 1));
+      RVK_TRY(add(P(params, bp(i, B_FC1W)), at(wbuf, W.fc1T[i]), kMlp, kD, 1));
+      RVK_TRY(add(P(params, bp(i, B_FC2W)), at(wbuf, W.fc2T[i]), kD, kMlp, 1));
     }
   }
+  RVK_TRY(rvk_cast_multi_launch(T, s));
   return rvk_token_table_launch(P(params, P_CLS), P(params, P_POS), P(params, P_PATCH_B),
                                 reinterpret_cast<float*>(at(wbuf, W.table)), s);
 }
@@ -321,9 +331,15 @@ int rvk_encoder_forward_impl(const void* const* params, const void* wbuf, const 
   return RVK_OK;
 }
 
+// Stages of the backward pass: 0 = final LayerNorm (class-token rows), 1 + j = block 11 - j (j = 0..11), 13 = patch embedding /
+// class token / position embedding.  [stage_begin, stage_end) lets the caller issue the gradient all-reduce of the blocks that
+// are already complete while the remaining ones are still being computed (data-parallel training, dist.py).  Gradients
+// written by stage s: its own tensors, except that mlp.fc2.bias of block i is written by the stage of block i + 1 (by stage 0
+// for block 11): after stage 1 + j every tensor of blocks 11 - j .. 11, norm.* and mlp.fc2.bias of block 10 - j are final.
 int rvk_encoder_backward_impl(const void* const* params, const void* wbuf, void* workspace, const float* dfeatures,
-                              int batch, int chunk_images, void* const* grads, cudaStream_t s) {
+                              int batch, int chunk_images, void* const* grads, int stage_begin, int stage_end, cudaStream_t s) {
   if (batch <= 0) return RVK_OK;
+  if (stage_begin < 0 || stage_end > kDepth + 2 || stage_begin >= stage_end) return RVK_ERR_BAD_ARG;
   if (params == nullptr || wbuf == nullptr || workspace == nullptr || dfeatures == nullptr || grads == nullptr)
     return RVK_ERR_BAD_ARG;
   const WeightLayout W = weight_layout(true);
@@ -344,7 +360,9 @@ int rvk_encoder_backward_impl(const void* const* params, const void* wbuf, void*
     uint8_t* dctx = b16(A.dctx, kD);
     uint8_t* dqkv = b16(A.dqkv, kQkv);
 
+    if (chunk < batch && !(stage_begin == 0 && stage_end == kDepth + 2)) return RVK_ERR_UNSUPPORTED_SHAPE;   // ranges: one chunk only
     // final LayerNorm backward: only the class-token rows carry gradient
+    if (stage_begin == 0) {
     RVK_CUDA_TRY(cudaMemsetAsync(dx, 0, size_t(M) * kD * 4, s));
     RVK_CUDA_TRY(cudaMemsetAsync(dxb, 0, size_t(M) * kD * 2, s));
     RVK_TRY(rvk_layernorm_bwd_launch(dfeatures + size_t(b0) * kD, 0, kD, f32(A.x_final, kD), int64_t(kTok) * kD,
@@ -352,8 +370,11 @@ int rvk_encoder_backward_impl(const void* const* params, const void* wbuf, void*
                                      reinterpret_cast<float*>(at(workspace, A.rstd_f)) + b0, P(params, P_NORM_W),
                                      nullptr, dx, int64_t(kTok) * kD, dxb, G(grads, P_NORM_W), G(grads, P_NORM_B),
                                      G(grads, bp(kDepth - 1, B_FC2B)), nb, s));
+    }
 
     for (int i = kDepth - 1; i >= 0; --i) {
+      const int stage = 1 + (kDepth - 1 - i);
+      if (stage < stage_begin || stage >= stage_end) continue;
       const BlockSaved& B = A.blk[i];
       // ---- MLP: x_next = x_mid + fc2(gelu(fc1(ln2)))
       RVK_TRY(rvk_gemm_tn_launch(dxb, kD, b16(B.h, kMlp), kMlp, G(grads, bp(i, B_FC2W)), kMlp, M, kD, kMlp, 1.0f, nullptr, s));
@@ -387,9 +408,11 @@ int rvk_encoder_backward_impl(const void* const* params, const void* wbuf, void*
                                        G(grads, bp(i, B_N1B)), i > 0 ? G(grads, bp(i - 1, B_FC2B)) : nullptr, M, s));
     }
     // ---- patch embedding, class token, position embedding
+    if (stage_end == kDepth + 2) {
     RVK_TRY(rvk_gemm_tn_launch(dxb, kD, b16(A.patches, kPatchK), kPatchK, G(grads, P_PATCH_W), kPatchK, M, kD, kPatchK,
                                1.0f, nullptr, s));
     RVK_TRY(rvk_token_grad_reduce_launch(dx, nb, G(grads, P_POS), G(grads, P_CLS), G(grads, P_PATCH_B), s));
+    }
   }
   return RVK_OK;
 }

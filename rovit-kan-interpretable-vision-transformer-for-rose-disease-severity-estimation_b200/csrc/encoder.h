@@ -10,4 +10,4 @@ int rvk_encoder_prepare_weights_impl(const void* const* params, void* wbuf, int 
 int rvk_encoder_forward_impl(const void* const* params, const void* wbuf, const void* images, int image_fmt, const float* norm6_host, int batch, int training,
                              int chunk_images, void* workspace, float* features, cudaStream_t s);
 int rvk_encoder_backward_impl(const void* const* params, const void* wbuf, void* workspace, const float* dfeatures,
-                              int batch, int chunk_images, void* const* grads, cudaStream_t s);
+                              int batch, int chunk_images, void* const* grads, int stage_begin, int stage_end, cudaStream_t s);

@@ -64,6 +64,49 @@ __global__ void token_table_kernel(const float* __restrict__ cls, const float* _
   table[i] = pos[i] + (tok == 0 ? cls[c] : pbias[c]);
 }
 
+// All weight shadows of the trunk in one launch (was ~97 per optimizer step): every job is a [rows x cols] fp32 matrix cast
+// tile by tile (32 x 32) to bf16, to bf16 transposed [cols x rows] (dgrad operands), or to fp16 (fc2 of the fused MLP kernel).
+__global__ void __launch_bounds__(256) cast_multi_kernel(const __grid_constant__ RvkCastTable T) {
+  __shared__ float tile[32][33];
+  __shared__ int s_j;
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    int lo = 0, hi = T.n - 1;
+    const int b = static_cast<int>(blockIdx.x);
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (T.job[mid].tile_start <= b) lo = mid; else hi = mid - 1;
+    }
+    s_j = lo;
+  }
+  __syncthreads();
+  const RvkCastJob& J = T.job[s_j];
+  const int local = static_cast<int>(blockIdx.x) - J.tile_start;
+  const int tiles_x = (J.cols + 31) / 32;
+  const int r0 = (local / tiles_x) * 32, c0 = (local % tiles_x) * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;          // block (32, 8)
+  if (J.mode == 1) {
+    for (int i = ty; i < 32; i += 8) {
+      const int r = r0 + i, c = c0 + tx;
+      tile[i][tx] = (r < J.rows && c < J.cols) ? J.src[static_cast<size_t>(r) * J.cols + c] : 0.0f;
+    }
+    __syncthreads();
+    auto* dst = static_cast<__nv_bfloat16*>(J.dst);
+    for (int i = ty; i < 32; i += 8) {
+      const int c = c0 + i, r = r0 + tx;
+      if (r < J.rows && c < J.cols) dst[static_cast<size_t>(c) * J.rows + r] = __float2bfloat16(tile[tx][i]);
+    }
+  } else {
+    for (int i = ty; i < 32; i += 8) {
+      const int r = r0 + i, c = c0 + tx;
+      if (r < J.rows && c < J.cols) {
+        const size_t o = static_cast<size_t>(r) * J.cols + c;
+        if (J.mode == 0) static_cast<__nv_bfloat16*>(J.dst)[o] = __float2bfloat16(J.src[o]);
+        else static_cast<__half*>(J.dst)[o] = __float2half(J.src[o]);
+      }
+    }
+  }
+}
+
 __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
   const long long i = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
@@ -326,6 +369,19 @@ int rvk_im2col_launch(const void* images, int fmt, void* patches_bf16, int batch
 int rvk_token_table_launch(const float* cls_token, const float* pos_embed, const float* patch_bias, float* table,
                            cudaStream_t stream) {
   token_table_kernel<<<(kTok * kD + 255) / 256, 256, 0, stream>>>(cls_token, pos_embed, patch_bias, table);
+  return rvk_launch_check();
+}
+
+int rvk_cast_multi_launch(RvkCastTable& T, cudaStream_t stream) {
+  if (T.n <= 0) return RVK_OK;
+  int tiles = 0;
+  for (int i = 0; i < T.n; ++i) {
+    const RvkCastJob& J = T.job[i];
+    if (J.src == nullptr || J.dst == nullptr || J.rows <= 0 || J.cols <= 0 || J.mode < 0 || J.mode > 2) return RVK_ERR_BAD_ARG;
+    T.job[i].tile_start = tiles;
+    tiles += ((J.rows + 31) / 32) * ((J.cols + 31) / 32);
+  }
+  cast_multi_kernel<<<tiles, dim3(32, 8), 0, stream>>>(T);
   return rvk_launch_check();
 }
 

@@ -367,6 +367,7 @@ bool kan_use_tc(int batch, int n_in, int n_out) {
 }
 
 #include "kan_tc.cuh"
+#include "kan_small.cuh"
 #include "heads_fused.cuh"
 
 }  // namespace
@@ -390,8 +391,12 @@ int rvk_kan_basis_launch(const float* t, const float* knots_host, float* out, in
 }
 
 int rvk_kan_layer_fwd_launch(const KanLayerDesc& L, const float* x, float* y, int act, int batch, float* workspace,
-                             int with_backward, cudaStream_t stream) {
+                             int with_backward_flags, cudaStream_t stream) {
   if (batch <= 0) return RVK_OK;
+  // bit 0: the backward pass will follow (also prepare its operands); bit 1: this workspace already holds the packed / split
+  // weights of these parameters (the caller keys that on the parameter versions), skip the prepare launches
+  const int with_backward = with_backward_flags & 1;
+  const bool prepared = (with_backward_flags & 2) != 0;
   if (L.num_basis != kNB || L.num_knots != kKnots) return RVK_ERR_UNSUPPORTED_SHAPE;
   const int in_pad = pad_to(L.in_features, 16), out_pad = pad_to(L.out_features, 64);
   const int64_t wp = static_cast<int64_t>(in_pad) * 8 * out_pad;
@@ -402,17 +407,23 @@ int rvk_kan_layer_fwd_launch(const KanLayerDesc& L, const float* x, float* y, in
                        4.0 * batch * (L.in_features + L.out_features), RVK_T_KAN_FWD);
   Knots kn;
   for (int i = 0; i < kKnots; ++i) kn.k[i] = L.knots_host[i];
+  if (kan_small_ok(L.in_features, L.out_features) && !kan_small_disabled())      // few outputs: no packing, support-4 contraction
+    return kan_small_fwd_launch(L, x, y, act, batch, kn, stream);
   const int pack_blocks = static_cast<int>((wp + 255) / 256 < 1184 ? (wp + 255) / 256 : 1184);
-  kan_pack_kernel<<<pack_blocks, 256, 0, stream>>>(L.spline, L.lin_w, L.in_features, L.out_features, in_pad, out_pad, Wp, WpT);
-  RVK_TRY(rvk_launch_check());
+  if (!prepared) {
+    kan_pack_kernel<<<pack_blocks, 256, 0, stream>>>(L.spline, L.lin_w, L.in_features, L.out_features, in_pad, out_pad, Wp, WpT);
+    RVK_TRY(rvk_launch_check());
+  }
   if (kan_use_tc(batch, L.in_features, L.out_features)) {
     // tensor-core path: operands split hi + lo in bf16, activations generated on the fly (kan_tc.cuh)
     const int kp = in_pad * 8;
     auto* w_hi = reinterpret_cast<__nv_bfloat16*>(workspace + (with_backward ? 3 : 1) * wp);
     auto* w_lo = w_hi + static_cast<size_t>(64) * kp;
-    kan_split_weights_kernel<<<pack_blocks, 256, 0, stream>>>(L.spline, L.lin_w, L.in_features, L.out_features, kp, w_hi, w_lo);
-    RVK_TRY(rvk_launch_check());
-    if (with_backward) {      // packed-row-major split for the tensor-core dx kernel (after the 64 threshold floats)
+    if (!prepared) {
+      kan_split_weights_kernel<<<pack_blocks, 256, 0, stream>>>(L.spline, L.lin_w, L.in_features, L.out_features, kp, w_hi, w_lo);
+      RVK_TRY(rvk_launch_check());
+    }
+    if (with_backward && !prepared) {      // packed-row-major split for the tensor-core dx kernel (after the 64 threshold floats)
       auto* w2_hi = reinterpret_cast<__nv_bfloat16*>(workspace + 4 * wp + 64);
       kan_split_weights_rows_kernel<<<pack_blocks, 256, 0, stream>>>(L.spline, L.lin_w, L.in_features, L.out_features, kp, w2_hi,
                                                                     w2_hi + static_cast<size_t>(64) * kp);
@@ -426,8 +437,10 @@ int rvk_kan_layer_fwd_launch(const KanLayerDesc& L, const float* x, float* y, in
     const int grid = tiles < kNumSMsB200 ? tiles : kNumSMsB200;
     KanTcTables tb;
     float* xthr = reinterpret_cast<float*>(w_lo + static_cast<size_t>(64) * kp);     // 16 floats after the split weights
-    kan_tc_thresholds_kernel<<<1, 32, 0, stream>>>(kn, xthr);
-    RVK_TRY(rvk_launch_check());
+    if (!prepared) {
+      kan_tc_thresholds_kernel<<<1, 32, 0, stream>>>(kn, xthr);
+      RVK_TRY(rvk_launch_check());
+    }
     tb.xthr = xthr;
     for (int j = 0; j < 8; ++j) {
       tb.knot[j] = L.knots_host[j];
@@ -461,6 +474,8 @@ int rvk_kan_layer_bwd_launch(const KanLayerDesc& L, const float* x, const float*
                        4.0 * batch * (L.in_features * (dx ? 2.0 : 1.0) + 2.0 * L.out_features), RVK_T_KAN_BWD);
   Knots kn;
   for (int i = 0; i < kKnots; ++i) kn.k[i] = L.knots_host[i];
+  if (kan_small_ok(L.in_features, L.out_features) && !kan_small_disabled())      // one kernel: dx, dW, dWl, db (accumulated, +=)
+    return kan_small_bwd_launch(L, x, y, gy, act, dx, dspline, dlin_w, dlin_b, batch, kn, stream);
   if (dspline != nullptr) {
     RVK_CUDA_TRY(cudaMemsetAsync(dWp, 0, wp * sizeof(float), stream));
     const int tiles = (in_pad / kIC) * (out_pad / kTO);

@@ -55,6 +55,17 @@ int rvk_attention_bwd_tc_launch(const void* qkv, const void* ctx, const void* dc
                                 int batch, cudaStream_t stream);
 
 // ---- token-stream kernels (encoder_kernels.cu) -----------------------------------------------------
+// fused optimizer tail (optimizer.cu)
+int64_t rvk_optimizer_state_floats_impl(int n, const int64_t* numel_host);
+int rvk_optimizer_step_impl(int n, void* const* params_host, const void* const* grads_host, const int64_t* numel_host,
+                            const int* group_host, float* exp_avg, float* exp_avg_sq, float* state4, const float* lr_host,
+                            int n_groups, float beta1, float beta2, float eps, float weight_decay, float max_grad_norm,
+                            float grad_mult, const float* grad_scale_dev, const float* found_inf_dev, cudaStream_t stream);
+// several fp32 -> bf16 / bf16-transposed / fp16 matrix casts in one launch (tile_start is filled in by the launcher)
+struct RvkCastJob { const float* src; void* dst; int rows, cols, mode, tile_start; };      // mode 0 bf16, 1 bf16 transposed, 2 fp16
+constexpr int kRvkMaxCastJobs = 64;
+struct RvkCastTable { RvkCastJob job[kRvkMaxCastJobs]; int n; };
+int rvk_cast_multi_launch(RvkCastTable& T, cudaStream_t stream);
 // fmt: 0 fp32, 1 bf16, 2 uint8 (+ norm6_host = {scale[3], shift[3]}: pixel * scale[c] + shift[c])
 int rvk_im2col_launch(const void* images, int fmt, void* patches_bf16, int batch, const float* norm6_host, cudaStream_t stream);
 int rvk_token_table_launch(const float* cls_token, const float* pos_embed, const float* patch_bias, float* table,

@@ -1,16 +1,66 @@
-"""Data-parallel plumbing: one process per GPU, one sum-all-reduce of the flat gradient per step.
+"""Data-parallel plumbing: one process per GPU, sum-all-reduce of the flat gradient, overlapped with the trunk backward.
 
-The reference is single-process (no torch.distributed anywhere); RoViT-KAN has no BatchNorm and every
-loss is a per-rank mean over equal local batches, so averaging gradients over ranks reproduces the
-single-GPU large-batch step exactly.  The trunk's backward already writes its 150 gradients into one
-contiguous fp32 buffer (ops.EncoderFn.backward); when autograd hands those views to `.grad` unchanged
-they are reduced in place with a single NCCL call, everything else is coalesced into one flat buffer.
+The reference is single-process (no torch.distributed anywhere); RoViT-KAN has no BatchNorm and every loss is a per-rank
+mean over equal local batches, so averaging gradients over ranks reproduces the single-GPU large-batch step exactly.
+
+The trunk's backward writes its 150 gradients into one contiguous fp32 buffer in parameter order (ops.EncoderFn.backward),
+walking the blocks 11 -> 0.  With `enable_overlap()` that backward runs in `buckets` pieces (rvk_encoder_backward_range) and
+the slice of the flat buffer that is final after each piece is all-reduced asynchronously (NCCL's own stream) while the
+next piece computes; `all_reduce_gradients` then reduces the 23 head / KAN gradients in one more call and joins the pending
+work.  The 1/world scale is either applied here (`average=True`) or left to the optimizer kernel
+(`FusedAdamW(grad_mult=1/world)`): one pass less over the gradients.
 """
 
 from __future__ import annotations
 
 import torch
 import torch.distributed as dist
+
+_overlap = None          # {'group', 'world', 'buckets', 'pending': [(work, flat_slice)], 'calls'}
+
+
+def enable_overlap(buckets: int = 3, group=None) -> bool:
+    """Reduce the trunk gradient bucket by bucket from inside the backward pass.  No-op (False) without a process group."""
+    global _overlap
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        _overlap = None
+        return False
+    _overlap = {'group': group, 'world': dist.get_world_size(group), 'buckets': max(1, min(int(buckets), 13)), 'pending': [],
+                'calls': 0}
+    return True
+
+
+def disable_overlap() -> None:
+    global _overlap
+    _overlap = None
+
+
+def overlap_state():
+    return _overlap
+
+
+def bucket_stage_ranges(buckets: int):
+    """Split the 14 backward stages (0 final LayerNorm, 1 + j block 11 - j, 13 patch embedding) into `buckets` consecutive
+    ranges; returns [(stage_begin, stage_end, first_block_final)] where after the range every gradient of blocks
+    >= first_block_final (and the final norm) is complete; the last range completes everything (first_block_final = -1)."""
+    per = -(-12 // buckets)
+    out, blk_hi = [], 11
+    while blk_hi >= 0:
+        blk_lo = max(blk_hi - per + 1, 0)
+        s_begin = 0 if blk_hi == 11 else 1 + (11 - blk_hi)
+        s_end = 14 if blk_lo == 0 else 1 + (11 - blk_lo) + 1
+        out.append((s_begin, s_end, -1 if blk_lo == 0 else blk_lo))
+        blk_hi = blk_lo - 1
+    return out
+
+
+def launch_bucket(flat: torch.Tensor, lo: int, hi: int) -> None:
+    """Called by ops.EncoderFn.backward after a stage range: all-reduce flat[lo:hi] without blocking the compute stream."""
+    st = _overlap
+    piece = flat[lo:hi]
+    work = dist.all_reduce(piece, op=dist.ReduceOp.SUM, group=st['group'], async_op=True)
+    st['pending'].append((work, piece))
+    st['calls'] += 1
 
 
 def _contiguous_run(grads):
@@ -27,8 +77,9 @@ def _contiguous_run(grads):
     return base >= st.data_ptr() and base + off <= st.data_ptr() + st.nbytes()
 
 
-def all_reduce_gradients(params, world_size: int | None = None, group=None) -> int:
-    """Average `.grad` of `params` over the process group.  Returns the number of collectives issued."""
+def all_reduce_gradients(params, world_size: int | None = None, group=None, average: bool = True) -> int:
+    """Sum (average=False) or average `.grad` of `params` over the process group.  Gradient slices that the overlapped
+    backward has already put in flight are only joined here.  Returns the number of collectives issued for this step."""
     if not dist.is_available() or not dist.is_initialized():
         return 0
     world = world_size or dist.get_world_size(group)
@@ -38,25 +89,44 @@ def all_reduce_gradients(params, world_size: int | None = None, group=None) -> i
     if not grads:
         return 0
     calls = 0
-    # longest prefix that is already one flat buffer
-    n = len(grads)
-    while n > 0 and not _contiguous_run(grads[:n]):
+    scale = 1.0 / world
+    pending = _overlap['pending'] if _overlap is not None else []
+    done_ranges = [(piece.data_ptr(), piece.data_ptr() + piece.numel() * piece.element_size()) for _, piece in pending]
+
+    def in_flight(g):
+        a = g.data_ptr()
+        return any(lo <= a < hi for lo, hi in done_ranges)
+    rest_all = [g for g in grads if not in_flight(g)]
+    # longest prefix of the remaining gradients that is already one flat buffer (trunk gradient when overlap is off)
+    n = len(rest_all)
+    while n > 0 and not _contiguous_run(rest_all[:n]):
         n -= 1 if n <= 150 else n - 150
+    works = []
     if n > 1:
-        total = sum(g.numel() for g in grads[:n])
-        flat = torch.empty(0, dtype=grads[0].dtype, device=grads[0].device).set_(
-            grads[0].untyped_storage(), grads[0].storage_offset(), (total,), (1,))
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        flat.mul_(1.0 / world)
+        total = sum(g.numel() for g in rest_all[:n])
+        flat = torch.empty(0, dtype=rest_all[0].dtype, device=rest_all[0].device).set_(
+            rest_all[0].untyped_storage(), rest_all[0].storage_offset(), (total,), (1,))
+        works.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True), flat, None))
         calls += 1
     else:
         n = 0
-    rest = grads[n:]
+    rest = rest_all[n:]
     if rest:
         flat = torch._utils._flatten_dense_tensors(rest)
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-        flat.mul_(1.0 / world)
-        for g, r in zip(rest, torch._utils._unflatten_dense_tensors(flat, rest)):
-            g.copy_(r)
+        works.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True), flat, rest))
         calls += 1
+    for work, piece in pending:
+        work.wait()
+        if average:
+            piece.mul_(scale)
+    if _overlap is not None:
+        calls += len(pending)
+        _overlap['pending'] = []
+    for work, flat, back in works:
+        work.wait()
+        if average:
+            flat.mul_(scale)
+        if back is not None:
+            for g, r in zip(back, torch._utils._unflatten_dense_tensors(flat, back)):
+                g.copy_(r)
     return calls

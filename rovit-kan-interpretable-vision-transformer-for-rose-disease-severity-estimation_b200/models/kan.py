@@ -60,8 +60,10 @@ class KANLayer(nn.Module):
 
     def _forward_act(self, x: torch.Tensor, act: int) -> torch.Tensor:
         ops = _ops()
+        if getattr(self, '_ws_state', None) is None:
+            self._ws_state = ops.KanLayerState()
         return ops.KanLayerFn.apply(*ops.nograd(x, self.spline_weights, self.linear.weight, self.linear.bias),
-                                    self.knots_host(), act)
+                                    self.knots_host(), act, self._ws_state)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return self._forward_act(x, 0)

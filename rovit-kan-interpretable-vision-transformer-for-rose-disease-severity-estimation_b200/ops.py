@@ -77,20 +77,28 @@ class KanLayerFn(torch.autograd.Function):
 
     @staticmethod
     @custom_fwd(device_type='cuda', cast_inputs=torch.float32)
-    def forward(ctx, x, spline, lin_w, lin_b, knots_host, act):
+    def forward(ctx, x, spline, lin_w, lin_b, knots_host, act, state=None):
         require_cuda(x, 'KANLayer.forward')
         xc, sw, lw, lb = _f32c(x), _f32c(spline), _f32c(lin_w), _f32c(lin_b)
         batch, n_in = xc.shape
         n_out = lw.shape[0]
         need_bwd = any(ctx.needs_input_grad[:4])
         lib = _lib.load()
-        ws = torch.empty(lib.rvk_kan_layer_workspace_floats(n_in, n_out, int(need_bwd)), device=xc.device,
-                         dtype=torch.float32)
+        # packed / split weight operands live in a workspace that is reused while the parameters are unchanged
+        key = (xc.device, need_bwd, tuple(knots_host), tuple((t.data_ptr(), t._version, t.dtype) for t in (spline, lin_w)))
+        prepared = state is not None and state.key == key and state.ws is not None
+        if prepared:
+            ws = state.ws
+        else:
+            ws = torch.empty(lib.rvk_kan_layer_workspace_floats(n_in, n_out, int(need_bwd)), device=xc.device,
+                             dtype=torch.float32)
+            if state is not None:
+                state.ws, state.key = ws, key
         y = torch.empty(batch, n_out, device=xc.device, dtype=torch.float32)
         kh = _host_floats(knots_host)
         with torch.cuda.device(xc.device):
             _lib.call('rvk_kan_layer_forward', _p(xc), _p(sw), _p(lw), _p(lb), kh, len(knots_host), batch, n_in, n_out,
-                      int(act), _p(y), _p(ws), int(need_bwd), _stream())
+                      int(act), _p(y), _p(ws), int(need_bwd) | (2 if prepared else 0), _stream())
         if need_bwd:
             ctx.save_for_backward(xc, y, sw, lw)
             ctx.ws, ctx.knots_host, ctx.act = ws, tuple(knots_host), int(act)
@@ -113,7 +121,15 @@ class KanLayerFn(torch.autograd.Function):
             _lib.call('rvk_kan_layer_backward', _p(xc), _p(y), _p(g), _p(sw), _p(lw), _host_floats(ctx.knots_host),
                       len(ctx.knots_host), batch, n_in, n_out, ctx.act, _p(dx), _p(dsw), _p(dlw), _p(dlb), _p(ctx.ws),
                       _stream())
-        return dx, dsw, dlw, dlb, None, None
+        return dx, dsw, dlw, dlb, None, None, None
+
+
+class KanLayerState:
+    """Per-layer cache of the prepared weight workspace (see KanLayerFn.forward)."""
+
+    def __init__(self):
+        self.ws = None
+        self.key = None
 
 
 # --------------------------------------------------------------------------------------------- heads
@@ -301,9 +317,24 @@ class EncoderFn(torch.autograd.Function):
         for p, n in zip(params, sizes):
             views.append(flat[off:off + n].view(p.shape))
             off += n
+        from . import dist as rdist
+        ov = rdist.overlap_state()
         with torch.cuda.device(g.device):
-            _lib.call('rvk_encoder_backward', ctx.state.param_table(params), _p(ctx.wbuf), _p(ctx.ws), _p(g), ctx.batch,
-                      ctx.chunk, ctx.state.param_table(views), _stream())
+            if ov is None or ctx.batch > ctx.chunk:
+                _lib.call('rvk_encoder_backward', ctx.state.param_table(params), _p(ctx.wbuf), _p(ctx.ws), _p(g), ctx.batch,
+                          ctx.chunk, ctx.state.param_table(views), _stream())
+            else:
+                # data-parallel training: the gradient slice that is final after each stage range goes to NCCL while the next
+                # range computes.  Parameter order = buffer order: [cls, pos, patch w/b | block 0 .. block 11 | norm w/b]
+                ptab, gtab = ctx.state.param_table(params), ctx.state.param_table(views)
+                block_start = lambda b: sum(sizes[:4 + 12 * b])
+                hi = len(flat)
+                for s_begin, s_end, first_final in rdist.bucket_stage_ranges(ov['buckets']):
+                    _lib.call('rvk_encoder_backward_range', ptab, _p(ctx.wbuf), _p(ctx.ws), _p(g), ctx.batch, ctx.chunk, gtab,
+                              s_begin, s_end, _stream())
+                    lo = 0 if first_final < 0 else block_start(first_final)
+                    rdist.launch_bucket(flat, lo, hi)
+                    hi = lo
         ctx.ws = None
         return (None, None, *views)
 

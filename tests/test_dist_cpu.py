@@ -33,7 +33,22 @@ def _worker(rank, world, port, q):
     calls = all_reduce_gradients(params, world)
     want = [(1 + 2) / 2 * (i + 1) for i in range(len(params))]
     ok = all(torch.allclose(p.grad, torch.full_like(p.grad, w)) for p, w in zip(params, want))
-    q.put((rank, ok, calls))
+    # ---- overlapped mode: the trunk slices are put in flight bucket by bucket (as ops.EncoderFn.backward does after each
+    # stage range), all_reduce_gradients then only adds the head reduce and joins; average=False leaves the 1/world scale to
+    # the optimizer kernel (FusedAdamW(grad_mult=1/world))
+    from rovitkan_b200 import dist as rdist
+    assert rdist.enable_overlap(buckets=3)
+    assert rdist.bucket_stage_ranges(3) == [(0, 5, 8), (5, 9, 4), (9, 14, -1)]
+    for i, p in enumerate(params):
+        p.grad.fill_(float((rank + 1) * (i + 1)))
+    cuts = [len(flat), 600, 250, 0]
+    for hi, lo in zip(cuts[:-1], cuts[1:]):
+        rdist.launch_bucket(flat, lo, hi)
+    calls2 = all_reduce_gradients(params, world, average=False)
+    ok2 = all(torch.allclose(p.grad, torch.full_like(p.grad, 2 * w)) for p, w in zip(params, want))
+    ok2 = ok2 and rdist.overlap_state()['pending'] == []
+    rdist.disable_overlap()
+    q.put((rank, ok and ok2, (calls, calls2)))
     dist.destroy_process_group()
 
 
@@ -48,4 +63,5 @@ def test_all_reduce_gradients_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
-    assert all(calls == 2 for _, _, calls in res), res      # one flat trunk reduce + one coalesced heads reduce
+    # plain: one flat trunk reduce + one coalesced heads reduce; overlapped: three trunk buckets + the heads reduce
+    assert all(calls == (2, 4) for _, _, calls in res), res

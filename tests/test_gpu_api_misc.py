@@ -72,7 +72,8 @@ def test_non_default_kan_layers_model(kan_layers):
     out = m(x)
     JointLoss()(out, torch.tensor([0, 1, 2, 3, 0, 1], device=DEV), torch.tensor([0, 1, 2, 3, 0, 1], device=DEV), 4)['total_loss'].backward()
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
-    assert_close(out['kan_severity'], o['kan_severity'], rtol=1e-5, atol=1e-6, what='train-mode KAN (dropout 0) == eval')
+    # (train and eval trunks round differently, and the KAN is discontinuous: compare the tails at identical features)
+    assert_close(m.kan_module(o['features']), o['kan_severity'], rtol=1e-5, atol=1e-6, what='train-mode KAN == eval-mode KAN')
 
 
 def test_fractional_severity_targets_follow_the_reference_float_cast():

@@ -337,3 +337,20 @@ def test_bf16_images_give_bit_identical_features():
         b = m(x.float())
     for k in ('features', 'cls_logits', 'kan_severity'):
         assert torch.equal(a[k], b[k]), k
+
+
+def test_uint8_images_are_normalised_in_the_patch_gather():
+    """model(uint8 NCHW) == model((pixels / 255 - mean) / std rounded to bf16): ToTensor + Normalize (the reference's transforms)
+    folded into im2col; the serving loop then moves a quarter of the fp32 bytes over PCIe."""
+    torch.manual_seed(3)
+    m = RoViTKAN(pretrained=False).to(DEV).eval()
+    u8 = torch.randint(0, 256, (6, 3, 224, 224), dtype=torch.uint8, device=DEV)
+    mean = torch.tensor([0.485, 0.456, 0.406], device=DEV).view(1, 3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225], device=DEV).view(1, 3, 1, 1)
+    with torch.no_grad():
+        a = m(u8)
+        b = m((u8.float() / 255.0 - mean) / std)
+    for k in ('features', 'cls_logits', 'ordinal_logits', 'mu', 'log_var'):
+        # the two paths round (p*scale + shift) vs ((p/255 - mean)/std) to bf16: at most one bf16 ulp per pixel
+        assert_close(a[k], b[k], rtol=2e-2, atol=0, scale_tol=2e-2, what=k)
+    assert rel_l2(a['features'], b['features']) < 5e-3

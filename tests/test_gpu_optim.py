@@ -1,0 +1,165 @@
+"""Fused optimizer tail (csrc/optimizer.cu, training/optim.py) against torch: GradScaler.unscale_ +
+clip_grad_norm_ + torch.optim.AdamW with the reference's two learning-rate groups (training/optimizer.py:18-25), and the
+device-side step accounting (N3)."""
+
+import pytest
+import torch
+
+from conftest import assert_close
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from rovitkan_b200.models import RoViTKAN
+    from rovitkan_b200.training import FusedAdamW, JointLoss, StepStats
+
+DEV = 'cuda'
+SHAPES = [(1, 1, 192), (192, 3, 16, 16), (576, 192), (576,), (4097,), (3, 7), (64, 64, 7), (1,)]
+
+
+def _make(seed):
+    g = torch.Generator().manual_seed(seed)
+    return [torch.randn(*s, generator=g).to(DEV).requires_grad_(True) for s in SHAPES]
+
+
+def _grads(step, scale=1.0):
+    g = torch.Generator().manual_seed(100 + step)
+    return [(torch.randn(*s, generator=g) * (0.3 + 0.2 * i) * scale).to(DEV) for i, s in enumerate(SHAPES)]
+
+
+def _groups(ps):
+    return [{'params': ps[:4], 'lr': 1e-4}, {'params': ps[4:], 'lr': 1e-3}]
+
+
+@pytest.mark.parametrize('max_norm', [None, 1.0, 1e4])
+def test_matches_torch_adamw_with_clipping(max_norm):
+    ours, ref = _make(0), _make(0)
+    o = FusedAdamW(_groups(ours), weight_decay=1e-4, max_grad_norm=max_norm)
+    r = torch.optim.AdamW(_groups(ref), weight_decay=1e-4, foreach=False, fused=False)
+    exact = True
+    for step in range(3):
+        for p, q, g in zip(ours, ref, _grads(step)):
+            p.grad, q.grad = g.clone(), g.clone()
+        if max_norm is not None:
+            want_norm = torch.nn.utils.clip_grad_norm_(ref, max_norm)
+        r.step()
+        o.step()
+        if max_norm is not None:
+            assert_close(o.last_grad_norm, want_norm, rtol=1e-5, atol=0, what='global gradient norm')
+        for i, (p, q) in enumerate(zip(ours, ref)):
+            assert_close(p, q, rtol=2e-6, atol=1e-7, what=f'step {step} tensor {i}')
+            exact = exact and torch.equal(p, q)
+            assert_close(o.state[p]['exp_avg'], r.state[q]['exp_avg'], rtol=2e-6, atol=1e-9, what='exp_avg')
+            assert_close(o.state[p]['exp_avg_sq'], r.state[q]['exp_avg_sq'], rtol=2e-6, atol=1e-12, what='exp_avg_sq')
+    print(f'\n  max_norm={max_norm}: bitwise equal to torch.optim.AdamW after 3 steps: {exact}')
+    assert float(o.step_count) == 3.0 and float(o.last_step_ran) == 1.0
+
+
+def test_non_finite_gradient_skips_the_step_like_gradscaler():
+    ours = _make(1)
+    o = FusedAdamW(_groups(ours), weight_decay=1e-4, max_grad_norm=1.0)
+    before = [p.detach().clone() for p in ours]
+    gs = _grads(0)
+    gs[5][1, 2] = float('inf')
+    for p, g in zip(ours, gs):
+        p.grad = g
+    o.step()
+    assert all(torch.equal(a, b) for a, b in zip(before, ours)) and float(o.step_count) == 0.0 and float(o.last_step_ran) == 0.0
+    for p, g in zip(ours, _grads(1)):
+        p.grad = g
+    o.step()
+    assert float(o.step_count) == 1.0 and not torch.equal(before[0], ours[0])
+    assert torch.isfinite(ours[5]).all()
+
+
+@pytest.mark.parametrize('flow', ['reference', 'fused'])
+def test_gradscaler_flows(flow):
+    """'reference' = trainer.py:118-129 (unscale_, clip_grad_norm_, scaler.step); 'fused' = scaler.step alone, with unscale,
+    inf check and clipping inside the optimizer kernels.  Both must equal torch AdamW driven the reference way."""
+    ours, ref = _make(2), _make(2)
+    o = FusedAdamW(_groups(ours), weight_decay=1e-4, max_grad_norm=1.0 if flow == 'fused' else None)
+    r = torch.optim.AdamW(_groups(ref), weight_decay=1e-4, foreach=False, fused=False)
+    so, sr = torch.amp.GradScaler('cuda', init_scale=1024.0), torch.amp.GradScaler('cuda', init_scale=1024.0)
+    for step in range(3):
+        for p, q, g in zip(ours, ref, _grads(step, scale=1024.0)):
+            p.grad, q.grad = g.clone(), g.clone()
+        if step == 1:
+            ours[2].grad[0, 0] = float('nan')
+            ref[2].grad[0, 0] = float('nan')
+        # torch side, as the reference's trainer drives it (scale() is emulated by the pre-scaled gradients)
+        sr._lazy_init_scale_growth_tracker(torch.device(DEV))
+        so._lazy_init_scale_growth_tracker(torch.device(DEV))
+        sr.unscale_(r)
+        torch.nn.utils.clip_grad_norm_(ref, 1.0)
+        sr.step(r)
+        sr.update()
+        if flow == 'reference':
+            so.unscale_(o)
+            torch.nn.utils.clip_grad_norm_(ours, 1.0)
+        so.step(o)
+        so.update()
+        for i, (p, q) in enumerate(zip(ours, ref)):
+            assert_close(p, q, rtol=3e-6, atol=1e-7, what=f'{flow} step {step} tensor {i}')
+    assert float(so.get_scale()) == float(sr.get_scale()) == 512.0         # the NaN step halved both scales
+    assert float(o.step_count) == 2.0
+
+
+def test_unfreezing_keeps_moments_and_state_dict_round_trip():
+    ps = _make(3)
+    for p in ps[:4]:
+        p.requires_grad_(False)                                  # frozen backbone group (trainer.py:244-246)
+    o = FusedAdamW(_groups(ps), weight_decay=1e-4)
+    for p, g in zip(ps, _grads(0)):
+        p.grad = g if p.requires_grad else None
+    o.step()
+    m_before = o.state[ps[6]]['exp_avg'].clone()
+    for p in ps[:4]:
+        p.requires_grad_(True)                                   # epoch 6: unfreeze (trainer.py:62-63)
+    for p, g in zip(ps, _grads(1)):
+        p.grad = g
+    frozen_before = ps[0].detach().clone()
+    o.step()
+    assert not torch.equal(frozen_before, ps[0]) and float(o.step_count) == 2.0
+    assert_close(o.state[ps[6]]['exp_avg'], 0.9 * m_before + 0.1 * _grads(1)[6], rtol=1e-5, atol=1e-8, what='moments kept')
+    sd = o.state_dict()
+    ps2 = [p.detach().clone().requires_grad_(True) for p in ps]
+    o2 = FusedAdamW(_groups(ps2), weight_decay=1e-4)
+    o2.load_state_dict(sd)
+    for p, q, g in zip(ps, ps2, _grads(2)):
+        p.grad, q.grad = g.clone(), g.clone()
+    o.step()
+    o2.step()
+    assert all(torch.equal(p, q) for p, q in zip(ps, ps2))
+
+
+def test_train_step_with_the_fused_tail_refreshes_the_trunk_weights():
+    """The kernels update parameters through raw pointers: the version bump must reach the trunk's bf16 weight shadows."""
+    torch.manual_seed(0)
+    m = RoViTKAN(pretrained=False, dropout=0.0).to(DEV).train()
+    backbone = [p for n, p in m.named_parameters() if 'backbone' in n]
+    heads = [p for n, p in m.named_parameters() if 'backbone' not in n]
+    opt = FusedAdamW([{'params': backbone, 'lr': 1e-3}, {'params': heads, 'lr': 1e-2}], weight_decay=1e-4, max_grad_norm=1.0)
+    x = torch.randn(4, 3, 224, 224, device=DEV)
+    y = torch.tensor([0, 1, 2, 3], device=DEV)
+    stats = StepStats(DEV)
+    feats = []
+    for _ in range(3):
+        out = m(x)
+        losses = JointLoss()(out, y, y, 4)
+        opt.zero_grad(set_to_none=True)
+        losses['total_loss'].backward()
+        opt.step()
+        stats.update(losses, out['cls_logits'], y)
+        feats.append(out['features'].detach().clone())
+    assert not torch.equal(feats[0], feats[1]) and not torch.equal(feats[1], feats[2])
+    res = stats.result()
+    assert set(res) == {'loss', 'cls_loss', 'ord_loss', 'unc_loss', 'kan_loss', 'accuracy'} and 0.0 <= res['accuracy'] <= 100.0
+    assert float(opt.step_count) == 3.0 and torch.isfinite(opt.last_grad_norm)
+    m.eval()
+    with torch.no_grad():
+        f_eval = m(x)['features']
+    assert rel(f_eval, feats[2]) > 1e-4                       # eval shadows were rebuilt from the updated weights too
+
+
+def rel(a, b):
+    return float((a - b).norm() / b.norm())
