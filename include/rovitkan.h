@@ -134,6 +134,17 @@ int rvk_encoder_backward(const void* const* params_host, const void* wbuf, void*
                          const float* dfeatures, int batch, int chunk_images, void* const* grads_host,
                          void* stream);
 
+/* Hook / explainability support (reference models/backbone.py:36-62, explainability/attention_maps.py:16-34).
+ * rvk_encoder_saved_offset: byte offset, inside the workspace of a training-mode forward over `batch` images (one chunk), of a
+ * tensor that forward saved for block `block` -- which: 0 x_in fp32 [M,192] (block input), 1 ln1 bf16 [M,192] (norm1 output),
+ * 2 qkv bf16 [M,576], 3 ctx bf16 [M,192] (attention output before proj), 4 x_mid fp32 [M,192] (after the attention
+ * residual), 5 ln2 bf16 [M,192], 6 z bf16 [M,768] (fc1 output), 7 h bf16 [M,768] (GELU output); block 12 / which 0 = the
+ * stream after the last block.  M = batch * 197.  Returns -1 for an invalid request.
+ * rvk_attention_probs: softmax(q k^T / 8) of one block as an explicit fp32 [batch, 3, 197, 197] tensor (timm Attention's
+ * `attn` before dropout): the fused attention kernels keep it on chip. */
+int64_t rvk_encoder_saved_offset(int batch, int block, int which);
+int rvk_attention_probs(const void* qkv_bf16, float* probs, int batch, void* stream);
+
 /* The same backward pass in pieces, so that a data-parallel caller can start the gradient all-reduce of finished blocks
  * while earlier blocks are still being differentiated ("overlapped with the encoder backward in 2-3
  * buckets: heads + KAN first, then blocks 11 -> 0").  Stages: 0 = final LayerNorm, 1 + j = block 11 - j, 13 = patch / class
@@ -158,8 +169,8 @@ int rvk_encoder_backward_range(const void* const* params_host, const void* wbuf,
  * lerp moment update, bias corrections in double). */
 int64_t rvk_optimizer_state_floats(int n_tensors, const int64_t* numel_host);
 int rvk_optimizer_step(int n_tensors, void* const* params_host, const void* const* grads_host, const int64_t* numel_host,
-                       const int* group_host, float* exp_avg, float* exp_avg_sq, float* state4, const float* lr_host,
-                       int n_groups, float beta1, float beta2, float eps, float weight_decay, float max_grad_norm,
+                       const int* group_host, float* exp_avg, float* exp_avg_sq, float* state4, const double* lr_host,
+                       int n_groups, double beta1, double beta2, double eps, double weight_decay, float max_grad_norm,
                        float grad_mult, const float* grad_scale_dev, const float* found_inf_dev, void* stream);
 
 /* ---- fused inference tail: all four heads of RoViTKAN.forward (models/rovit_kan.py:96-124 in eval mode) in ONE kernel:

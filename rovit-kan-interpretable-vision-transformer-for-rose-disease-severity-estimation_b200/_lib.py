@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'librovitkan.so')
 
-_P, _I, _L, _F, _U64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
+_P, _I, _L, _F, _U64, _D = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64, C.c_double
 
 # name -> (restype, argtypes); must list every function include/rovitkan.h declares
 SIGNATURES = {
@@ -40,13 +40,15 @@ SIGNATURES = {
     'rvk_joint_loss_forward': (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     'rvk_joint_loss_backward': (_I, [_P, _P, _I, _F, _P, _I, _P]),
     'rvk_optimizer_state_floats': (_L, [_I, _P]),
-    'rvk_optimizer_step': (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _F, _F, _F, _F, _F, _F, _P, _P, _P]),
+    'rvk_optimizer_step': (_I, [_I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _D, _D, _D, _D, _F, _F, _P, _P, _P]),
     'rvk_encoder_weight_bytes': (_L, [_I]),
     'rvk_encoder_workspace_bytes': (_L, [_I, _I, _I]),
     'rvk_encoder_prepare_weights': (_I, [_P, _P, _I, _P]),
     'rvk_encoder_forward': (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     'rvk_encoder_forward_bf16': (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
     'rvk_encoder_forward_u8': (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    'rvk_encoder_saved_offset': (_L, [_I, _I, _I]),
+    'rvk_attention_probs': (_I, [_P, _P, _I, _P]),
     'rvk_encoder_backward_range': (_I, [_P, _P, _P, _P, _I, _I, _P, _I, _I, _P]),
     'rvk_encoder_backward': (_I, [_P, _P, _P, _P, _I, _I, _P, _P]),
     'rvk_gemm_nt': (_I, [_I, _P, _L, _P, _L, _P, _L, _P, _L, _P, _L, _I, _I, _I, _P, _P, _P, _P, _I, _F, _P, _P, _P]),

@@ -243,14 +243,20 @@ int rvk_encoder_backward_range(const void* const* params_host, const void* wbuf,
                                    stage_end, S(stream));
 }
 
+int64_t rvk_encoder_saved_offset(int batch, int block, int which) { return rvk_encoder_saved_offset_impl(batch, block, which); }
+int rvk_attention_probs(const void* qkv_bf16, float* probs, int batch, void* stream) {
+  if (batch < 0 || (batch > 0 && (qkv_bf16 == nullptr || probs == nullptr))) return RVK_ERR_BAD_ARG;
+  return rvk_attention_probs_launch(qkv_bf16, probs, batch, S(stream));
+}
+
 // ---- fused optimizer tail
 int64_t rvk_optimizer_state_floats(int n_tensors, const int64_t* numel_host) {
   if (n_tensors < 0 || (n_tensors > 0 && numel_host == nullptr)) return -1;
   return rvk_optimizer_state_floats_impl(n_tensors, numel_host);
 }
 int rvk_optimizer_step(int n_tensors, void* const* params_host, const void* const* grads_host, const int64_t* numel_host,
-                       const int* group_host, float* exp_avg, float* exp_avg_sq, float* state4, const float* lr_host,
-                       int n_groups, float beta1, float beta2, float eps, float weight_decay, float max_grad_norm,
+                       const int* group_host, float* exp_avg, float* exp_avg_sq, float* state4, const double* lr_host,
+                       int n_groups, double beta1, double beta2, double eps, double weight_decay, float max_grad_norm,
                        float grad_mult, const float* grad_scale_dev, const float* found_inf_dev, void* stream) {
   if (n_tensors < 0) return RVK_ERR_BAD_ARG;
   return rvk_optimizer_step_impl(n_tensors, params_host, grads_host, numel_host, group_host, exp_avg, exp_avg_sq, state4,

@@ -195,6 +195,18 @@ int64_t rvk_encoder_workspace_bytes_impl(int batch, int training, int chunk_imag
   return static_cast<int64_t>(act_layout(imgs * kTok, imgs, training != 0).total);
 }
 
+// byte offset, inside a training workspace of `batch` images, of one tensor the forward saved for block `block`
+// (which: 0 x_in fp32 [M,192], 1 ln1 bf16 [M,192], 2 qkv bf16 [M,576], 3 ctx bf16 [M,192], 4 x_mid fp32 [M,192], 5 ln2 bf16
+// [M,192], 6 z bf16 [M,768], 7 h bf16 [M,768]); block == 12: which 0 = x_final fp32 [M,192].  -1 if out of range.
+int64_t rvk_encoder_saved_offset_impl(int batch, int block, int which) {
+  if (batch <= 0 || block < 0 || block > kDepth || which < 0 || which > 7) return -1;
+  const ActLayout A = act_layout(int64_t(batch) * kTok, batch, true);
+  if (block == kDepth) return which == 0 ? static_cast<int64_t>(A.x_final) : -1;
+  const BlockSaved& B = A.blk[block];
+  const size_t off[8] = {B.x_in, B.ln1, B.qkv, B.ctx, B.x_mid, B.ln2, B.z, B.h};
+  return static_cast<int64_t>(off[which]);
+}
+
 int rvk_encoder_prepare_weights_impl(const void* const* params, void* wbuf, int training, cudaStream_t s) {
   if (params == nullptr || wbuf == nullptr) return RVK_ERR_BAD_ARG;
   const WeightLayout W = weight_layout(training != 0);

@@ -407,7 +407,7 @@ int rvk_kan_layer_fwd_launch(const KanLayerDesc& L, const float* x, float* y, in
                        4.0 * batch * (L.in_features + L.out_features), RVK_T_KAN_FWD);
   Knots kn;
   for (int i = 0; i < kKnots; ++i) kn.k[i] = L.knots_host[i];
-  if (kan_small_ok(L.in_features, L.out_features) && !kan_small_disabled())      // few outputs: no packing, support-4 contraction
+  if (kan_small_ok(L.in_features, L.out_features, kan_use_tc(batch, L.in_features, L.out_features)) && !kan_small_disabled())      // few outputs: no packing
     return kan_small_fwd_launch(L, x, y, act, batch, kn, stream);
   const int pack_blocks = static_cast<int>((wp + 255) / 256 < 1184 ? (wp + 255) / 256 : 1184);
   if (!prepared) {
@@ -474,7 +474,7 @@ int rvk_kan_layer_bwd_launch(const KanLayerDesc& L, const float* x, const float*
                        4.0 * batch * (L.in_features * (dx ? 2.0 : 1.0) + 2.0 * L.out_features), RVK_T_KAN_BWD);
   Knots kn;
   for (int i = 0; i < kKnots; ++i) kn.k[i] = L.knots_host[i];
-  if (kan_small_ok(L.in_features, L.out_features) && !kan_small_disabled())      // one kernel: dx, dW, dWl, db (accumulated, +=)
+  if (kan_small_ok(L.in_features, L.out_features, kan_use_tc(batch, L.in_features, L.out_features)) && !kan_small_disabled())      // one kernel: dx, dW, dWl, db (+=)
     return kan_small_bwd_launch(L, x, y, gy, act, dx, dspline, dlin_w, dlin_b, batch, kn, stream);
   if (dspline != nullptr) {
     RVK_CUDA_TRY(cudaMemsetAsync(dWp, 0, wp * sizeof(float), stream));

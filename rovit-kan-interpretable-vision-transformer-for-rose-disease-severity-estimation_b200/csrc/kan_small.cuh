@@ -124,7 +124,6 @@ kan_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ yv, 
   constexpr int OQ = NOUT / OPT;
   extern __shared__ __align__(16) float sm_small[];
   float* sW = sm_small;                                   // [n_in*8][NOUT]
-  float* sG = sW + n_in * kKW * NOUT;                     // [G][NOUT] gpre of the sample each stream is working on
   kan_small_load_weights<NOUT>(sW, spline, lin_w, n_in, n_out);
   const int tps = n_in * OQ;
   const int G = kSmThreads / tps;
@@ -144,20 +143,22 @@ kan_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ yv, 
   const int b_begin = blockIdx.x * samples_per_cta;
   const int b_end = min(batch, b_begin + samples_per_cta);
   __syncthreads();
-  // every stream runs the same number of rounds so that the barriers below are uniform
+  // all lanes of a warp run the same number of rounds (the shuffles below are warp-wide); no block-level barrier in the loop
   const int rounds = (b_end - b_begin + G - 1) / (G > 0 ? G : 1);
+  const float* row = sW + i * kKW * NOUT + q * OPT;
   for (int r = 0; r < rounds; ++r) {
     const int b = b_begin + r * G + stream;
     const bool live_b = active && b < b_end;
-    if (live_b && within < NOUT) {
-      float g = 0.0f;
-      if (within < n_out) {
-        const size_t off = static_cast<size_t>(b) * n_out + within;
-        g = gy[off] * act_grad(act, yv[off]);
+    float g[OPT];
+#pragma unroll
+    for (int c = 0; c < OPT; ++c) {
+      g[c] = 0.0f;
+      const int o = q * OPT + c;
+      if (live_b && o < n_out) {
+        const size_t off = static_cast<size_t>(b) * n_out + o;
+        g[c] = gy[off] * act_grad(act, yv[off]);          // the same few words for every input of the sample: L1 broadcast
       }
-      sG[stream * NOUT + within] = g;
     }
-    __syncthreads();
     float xv = 0.0f, dtdx = 0.0f;
     int j = 8;
     float v[4] = {0.f, 0.f, 0.f, 0.f}, d[4] = {0.f, 0.f, 0.f, 0.f};
@@ -179,10 +180,6 @@ kan_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ yv, 
     }
     float dxp = 0.0f;
     if (live_b) {
-      float g[OPT];
-#pragma unroll
-      for (int c = 0; c < OPT; ++c) g[c] = sG[stream * NOUT + q * OPT + c];
-      const float* row = sW + i * kKW * NOUT + q * OPT;
       // linear branch (slot 7)
 #pragma unroll
       for (int c = 0; c < OPT; ++c) {
@@ -212,7 +209,6 @@ kan_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ yv, 
       for (int s = 1; s < OQ; s <<= 1) dxp += __shfl_xor_sync(0xffffffffu, dxp, s);
     }
     if (live_b && q == 0 && dx != nullptr) dx[static_cast<size_t>(b) * n_in + i] = dxp;
-    __syncthreads();
   }
   if (!active || dspline == nullptr) return;
   // per-CTA results -> global, straight into the reference layouts (dspline [in][out][7], dlin_w [out][in])
@@ -228,8 +224,12 @@ kan_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ yv, 
   }
 }
 
-bool kan_small_ok(int n_in, int n_out) {
+// few outputs: always; up to 16 outputs: only where the tensor-core formulation is not available (small batches, odd
+// shapes) -- at 16 outputs the support-4 gather costs 5 x 16 FMAs + loads per (sample, input) on the CUDA cores, more than
+// the dense-7 product costs on the tensor pipe (measured: 64 -> 16 at batch 65536, 170 us against 45 us)
+bool kan_small_ok(int n_in, int n_out, bool tc_available) {
   if (n_out > 16 || n_in < 1) return false;
+  if (n_out > 4 && tc_available) return false;
   const int nout = n_out <= 1 ? 1 : n_out <= 2 ? 2 : n_out <= 4 ? 4 : n_out <= 8 ? 8 : 16;
   const int oq = nout <= 4 ? 1 : nout / 4;
   return n_in * oq <= kSmThreads && static_cast<size_t>(n_in) * kKW * nout * 4 <= 96 * 1024;
@@ -256,12 +256,13 @@ int kan_small_bwd_launch_t(const KanLayerDesc& L, const float* x, const float* y
                            float* dlin_w, float* dlin_b, int batch, const Knots& kn, cudaStream_t stream) {
   constexpr int OQ = NOUT <= 4 ? 1 : NOUT / 4;
   const int G = kSmThreads / (L.in_features * OQ);
-  const int smem = (L.in_features * kKW * NOUT + G * NOUT) * 4;
+  const int smem = L.in_features * kKW * NOUT * 4;
   auto kernel = kan_small_bwd_kernel<NOUT>;
   if (smem > 48 * 1024) RVK_SET_MAX_SMEM(kernel, 100 * 1024);
-  // enough CTAs to fill the machine, each with at least a few rounds of work (its register accumulators are flushed once)
-  int ctas = kNumSMsB200 * 2;
-  const int min_per_cta = G * 4;
+  // enough resident warps to hide the load latency of the sample loop (8 CTAs per SM), each CTA with at least a few rounds of
+  // work: its register accumulators are flushed once, n_in * 8 * n_out atomics per CTA
+  int ctas = kNumSMsB200 * 8;
+  const int min_per_cta = G * 8;
   if (static_cast<long long>(ctas) * min_per_cta > batch) ctas = (batch + min_per_cta - 1) / min_per_cta;
   if (ctas < 1) ctas = 1;
   const int spc = (batch + ctas - 1) / ctas;

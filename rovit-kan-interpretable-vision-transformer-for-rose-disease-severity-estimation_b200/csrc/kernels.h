@@ -49,6 +49,7 @@ bool rvk_pdl_enabled();
 
 // ---- attention -----------------------------------------------------------------------------------
 int rvk_attention_fwd_launch(const void* qkv, void* ctx, float* lse, int batch, cudaStream_t stream);
+int rvk_attention_probs_launch(const void* qkv, float* probs, int batch, cudaStream_t stream);
 int rvk_attention_bwd_launch(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
                              int batch, cudaStream_t stream);
 int rvk_attention_bwd_tc_launch(const void* qkv, const void* ctx, const void* dctx, const float* lse, void* dqkv,
@@ -58,8 +59,8 @@ int rvk_attention_bwd_tc_launch(const void* qkv, const void* ctx, const void* dc
 // fused optimizer tail (optimizer.cu)
 int64_t rvk_optimizer_state_floats_impl(int n, const int64_t* numel_host);
 int rvk_optimizer_step_impl(int n, void* const* params_host, const void* const* grads_host, const int64_t* numel_host,
-                            const int* group_host, float* exp_avg, float* exp_avg_sq, float* state4, const float* lr_host,
-                            int n_groups, float beta1, float beta2, float eps, float weight_decay, float max_grad_norm,
+                            const int* group_host, float* exp_avg, float* exp_avg_sq, float* state4, const double* lr_host,
+                            int n_groups, double beta1, double beta2, double eps, double weight_decay, float max_grad_norm,
                             float grad_mult, const float* grad_scale_dev, const float* found_inf_dev, cudaStream_t stream);
 // several fp32 -> bf16 / bf16-transposed / fp16 matrix casts in one launch (tile_start is filled in by the launcher)
 struct RvkCastJob { const float* src; void* dst; int rows, cols, mode, tile_start; };      // mode 0 bf16, 1 bf16 transposed, 2 fp16

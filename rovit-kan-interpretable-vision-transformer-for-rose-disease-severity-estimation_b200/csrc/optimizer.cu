@@ -32,7 +32,10 @@ struct OptTable {
 
 struct OptHyper {
   float lr[4];
+  float decay[4];                                    // 1 - lr * weight_decay, evaluated in double on the host as torch does
   float beta1, beta2, eps, weight_decay, max_norm;   // max_norm <= 0: no clipping
+  float om_beta1, om_beta2;                          // 1 - beta, rounded from double (torch passes them as Python floats)
+  double lr_d[4], beta1_d, beta2_d;                  // bias corrections and step size are evaluated in double
   float grad_mult;                                   // e.g. 1 / world_size
   const float* grad_scale;                           // device, nullable: gradients are divided by *grad_scale
   const float* found_inf;                            // device, nullable: != 0 skips the update
@@ -103,13 +106,12 @@ optim_update_kernel(const __grid_constant__ OptTable T, const OptHyper H, float*
   if (H.max_norm > 0.0f) clip = fminf(1.0f, H.max_norm / (norm + 1e-6f));      // clip_grad_norm_: clamp(max_norm / (norm + 1e-6), max=1)
   const float gm = mult * clip;
   const float step = state[1] + 1.0f;
-  const float lr = H.lr[T.group[t]];
   // torch/aten fused_adam_utils.cuh (adamw): bias corrections in double, the rest in fp32
-  const double bc1 = 1.0 - pow(static_cast<double>(H.beta1), static_cast<double>(step));
-  const double bc2 = 1.0 - pow(static_cast<double>(H.beta2), static_cast<double>(step));
-  const float step_size = static_cast<float>(static_cast<double>(lr) / bc1);
+  const double bc1 = 1.0 - pow(H.beta1_d, static_cast<double>(step));
+  const double bc2 = 1.0 - pow(H.beta2_d, static_cast<double>(step));
+  const float step_size = static_cast<float>(H.lr_d[T.group[t]] / bc1);
   const float bc2_sqrt = static_cast<float>(sqrt(bc2));
-  const float decay = 1.0f - lr * H.weight_decay;
+  const float decay = H.decay[T.group[t]];
   float* p = T.p[t];
   const int base = (static_cast<int>(blockIdx.x) - T.chunk_start[t]) * kChunk;
   const int n = T.numel[t];
@@ -119,8 +121,8 @@ optim_update_kernel(const __grid_constant__ OptTable T, const OptHyper H, float*
     float w = p[i] * decay;
     float m = exp_avg[sbase + i];
     float v = exp_avg_sq[sbase + i];
-    m = m + (1.0f - H.beta1) * (gr - m);                      // lerp(exp_avg, grad, 1 - beta1)
-    v = H.beta2 * v + (1.0f - H.beta2) * gr * gr;
+    m = m + H.om_beta1 * (gr - m);                            // lerp(exp_avg, grad, 1 - beta1)
+    v = H.beta2 * v + H.om_beta2 * gr * gr;
     const float denom = sqrtf(v) / bc2_sqrt + H.eps;
     w -= step_size * m / denom;
     p[i] = w;
@@ -151,16 +153,24 @@ int64_t rvk_optimizer_state_floats_impl(int n, const int64_t* numel_host) {
 }
 
 int rvk_optimizer_step_impl(int n, void* const* params_host, const void* const* grads_host, const int64_t* numel_host,
-                            const int* group_host, float* exp_avg, float* exp_avg_sq, float* state4, const float* lr_host,
-                            int n_groups, float beta1, float beta2, float eps, float weight_decay, float max_grad_norm,
+                            const int* group_host, float* exp_avg, float* exp_avg_sq, float* state4, const double* lr_host,
+                            int n_groups, double beta1, double beta2, double eps, double weight_decay, float max_grad_norm,
                             float grad_mult, const float* grad_scale_dev, const float* found_inf_dev, cudaStream_t stream) {
   if (n <= 0) return RVK_OK;
   if (params_host == nullptr || grads_host == nullptr || numel_host == nullptr || group_host == nullptr || exp_avg == nullptr ||
       exp_avg_sq == nullptr || state4 == nullptr || lr_host == nullptr || n_groups < 1 || n_groups > 4)
     return RVK_ERR_BAD_ARG;
   OptHyper H{};
-  for (int i = 0; i < n_groups; ++i) H.lr[i] = lr_host[i];
-  H.beta1 = beta1; H.beta2 = beta2; H.eps = eps; H.weight_decay = weight_decay; H.max_norm = max_grad_norm;
+  for (int i = 0; i < n_groups; ++i) {
+    H.lr[i] = static_cast<float>(lr_host[i]);
+    H.lr_d[i] = lr_host[i];
+    H.decay[i] = static_cast<float>(1.0 - lr_host[i] * weight_decay);
+  }
+  H.om_beta1 = static_cast<float>(1.0 - beta1);
+  H.om_beta2 = static_cast<float>(1.0 - beta2);
+  H.beta1_d = beta1; H.beta2_d = beta2;
+  H.beta1 = static_cast<float>(beta1); H.beta2 = static_cast<float>(beta2); H.eps = static_cast<float>(eps);
+  H.weight_decay = static_cast<float>(weight_decay); H.max_norm = max_grad_norm;
   H.grad_mult = grad_mult; H.grad_scale = grad_scale_dev; H.found_inf = found_inf_dev;
   double bytes = 0.0;
   for (int i = 0; i < n; ++i)

@@ -32,10 +32,20 @@ class DeiTTinyBackbone(nn.Module):
         print("Backbone unfrozen")
 
     def get_attention_maps(self, x: torch.Tensor):
-        raise NotImplementedError(
-            'attention-map capture relies on forward hooks on blocks[i].attn (backbone.py:51-53); the fused '
-            'trunk keeps attention probabilities on chip and never materialises them. Out of scope for the '
-            'forward/backward hot path (see DESIGN.md).')
+        """backbone.py:36-62: the outputs of `blocks[i].attn` captured by forward hooks -- with timm's Attention that is the
+        attention block output (B, 197, 192) per block (timm returns no weights).  Same mechanism here: the hooks fire from
+        the trunk's hook mode.  For the attention PROBABILITIES (B, 3, 197, 197) use `self.model.attention_probabilities(x)`."""
+        attention_maps = []
+
+        def hook_fn(module, input, output):
+            attention_maps.append(output[1] if isinstance(output, tuple) else output)
+        hooks = [block.attn.register_forward_hook(hook_fn) for block in self.model.blocks]
+        try:
+            _ = self.model(x)
+        finally:
+            for hook in hooks:
+                hook.remove()
+        return attention_maps
 
 
 def freeze_backbone(model: nn.Module, freeze: bool = True):

@@ -104,7 +104,61 @@ class VisionTransformerB200(nn.Module):
         ops = _ops()
         if self._state is None:
             self._state = ops.EncoderState()
+        if self._hooked_modules():
+            return self._forward_with_hooks(x)
         return ops.EncoderFn.apply(self._state, *ops.nograd(x, *self._ordered_params()))
+
+    # ---- hook mode -----------------------------------------------------------------------------
+    def _hooked_modules(self):
+        mods = [self.patch_embed, self.norm]
+        for b in self.blocks:
+            mods += [b, b.norm1, b.attn, b.norm2, b.mlp]
+        return [m for m in mods if m._forward_hooks]
+
+    def trace(self, x: torch.Tensor):
+        """Forward that keeps every block's intermediate tensors: returns (features, record) with
+        record[i] = {'input', 'norm1', 'attn_out', 'attn_probs', 'mid', 'norm2', 'mlp_out', 'output'} for block i and
+        record['final'] = the token stream entering the last LayerNorm.  No autograd graph is built."""
+        ops = _ops()
+        if self._state is None:
+            self._state = ops.EncoderState()
+        with torch.no_grad():
+            feats, saved, ws = ops.encoder_traced_forward(self._state, x, self._ordered_params())
+            rec = {}
+            for i in range(DEPTH):
+                x_in, x_mid = saved(i, 0), saved(i, 4)
+                x_out = saved(i + 1, 0)
+                rec[i] = {'input': x_in, 'norm1': saved(i, 1).float(), 'attn_out': x_mid - x_in, 'qkv': saved(i, 2), 'mid': x_mid,
+                          'norm2': saved(i, 5).float(), 'mlp_out': x_out - x_mid, 'output': x_out}
+            rec['final'] = saved(DEPTH, 0)
+        return feats, rec
+
+    def _forward_with_hooks(self, x: torch.Tensor) -> torch.Tensor:
+        """Forward hooks registered on `blocks[i]`, `.norm1`, `.attn`, `.norm2`, `.mlp` or `norm` (the reference's
+        explainability code: backbone.py:51-53, attention_maps.py:31-33, gradcam.py:40) fire with the tensors the fused
+        kernels produced for that module.  The tensors are detached (no autograd through them: backward hooks do not fire)
+        and a hook's return value cannot replace the module output."""
+        feats, rec = self.trace(x)
+
+        def fire(mod, inp, out):
+            for hook in list(mod._forward_hooks.values()):
+                if hook(mod, (inp,), out) is not None:
+                    raise RuntimeError('forward hooks of the fused DeiT-Tiny trunk cannot replace the module output')
+        for i, b in enumerate(self.blocks):
+            r = rec[i]
+            fire(b.norm1, r['input'], r['norm1'])
+            fire(b.attn, r['norm1'], r['attn_out'])
+            fire(b.norm2, r['mid'], r['norm2'])
+            fire(b.mlp, r['norm2'], r['mlp_out'])
+            fire(b, r['input'], r['output'])
+        fire(self.norm, rec['final'], feats)
+        return feats
+
+    def attention_probabilities(self, x: torch.Tensor):
+        """softmax(q k^T / sqrt(64)) of every block, each (B, 3, 197, 197) fp32: what timm's Attention calls `attn`."""
+        ops = _ops()
+        _, rec = self.trace(x)
+        return [ops.attention_probabilities(rec[i]['qkv']) for i in range(DEPTH)]
 
 
 PRETRAINED_ENV = 'ROVITKAN_PRETRAINED'

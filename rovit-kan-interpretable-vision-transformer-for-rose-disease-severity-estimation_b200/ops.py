@@ -339,6 +339,49 @@ class EncoderFn(torch.autograd.Function):
         return (None, None, *views)
 
 
+def encoder_traced_forward(state: EncoderState, images: torch.Tensor, params):
+    """Trunk forward in the activation-saving (training) layout WITHOUT autograd, returning the features and a function
+    `saved(block, which)` that views the tensors the kernels left in the workspace (rvk_encoder_saved_offset).  This is the
+    hook / explainability mode: the fused trunk never runs `blocks[i].attn` etc. as modules, so their forward
+    hooks are fed from here."""
+    require_cuda(images, 'DeiTTinyBackbone (hook mode)')
+    if images.dim() != 4 or tuple(images.shape[1:]) != (3, 224, 224):
+        raise ValueError(f'expected images of shape (B, 3, 224, 224), got {tuple(images.shape)}')
+    lib = _lib.load()
+    img = _f32c(images)
+    batch, dev = img.shape[0], img.device
+    pc = [(p.detach().float() if p.dtype != torch.float32 else p.detach()) for p in params]
+    feats = torch.empty(batch, 192, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        wbuf = state.weights(pc, True, dev, key_params=list(params))
+        ws = torch.empty(lib.rvk_encoder_workspace_bytes(batch, 1, batch), device=dev, dtype=torch.uint8)
+        _lib.call('rvk_encoder_forward', state.param_table(pc), _p(wbuf), _p(img), batch, 1, batch, _p(ws), _p(feats), _stream())
+    widths = {0: (192, torch.float32), 1: (192, torch.bfloat16), 2: (576, torch.bfloat16), 3: (192, torch.bfloat16),
+              4: (192, torch.float32), 5: (192, torch.bfloat16), 6: (768, torch.bfloat16), 7: (768, torch.bfloat16)}
+    rows = batch * 197
+
+    def saved(block: int, which: int) -> torch.Tensor:
+        off = lib.rvk_encoder_saved_offset(batch, block, which)
+        if off < 0:
+            raise ValueError(f'no saved tensor (block {block}, which {which})')
+        width, dtype = widths[which]
+        nbytes = rows * width * (4 if dtype == torch.float32 else 2)
+        return ws[off:off + nbytes].view(dtype).view(batch, 197, width)
+
+    return feats, saved, ws
+
+
+def attention_probabilities(qkv: torch.Tensor) -> torch.Tensor:
+    """softmax(q k^T / 8) per (image, head) from a saved qkv tensor (B, 197, 576) bf16 -> (B, 3, 197, 197) fp32."""
+    require_cuda(qkv, 'attention_probabilities')
+    q = qkv.contiguous()
+    batch = q.shape[0]
+    out = torch.empty(batch, 3, 197, 197, device=q.device, dtype=torch.float32)
+    with torch.cuda.device(q.device):
+        _lib.call('rvk_attention_probs', _p(q), _p(out), batch, _stream())
+    return out
+
+
 # --------------------------------------------------------------------------------------------- fused inference tail
 class HeadsFusedState:
     """Cache of the repacked head / KAN weights for the one-kernel inference tail (rvk_heads_fused)."""

@@ -125,7 +125,7 @@ class FusedAdamW(torch.optim.Optimizer):
         if all(g is None for g in grads):
             return loss
         gtable = (C.c_void_p * len(ps))(*[0 if g is None else g.data_ptr() for g in grads])
-        lrs = (C.c_float * len(self.param_groups))(*[float(g['lr']) for g in self.param_groups])
+        lrs = (C.c_double * len(self.param_groups))(*[float(g['lr']) for g in self.param_groups])
         g0 = self.param_groups[0]
         grad_scale = getattr(self, 'grad_scale', None)
         found_inf = getattr(self, 'found_inf', None)

@@ -122,3 +122,52 @@ def test_non_integer_focal_gamma_with_saturated_probability():
     assert_close(loss, ref, rtol=1e-4, atol=1e-7, what='focal gamma=1.5')
     assert torch.isfinite(logits.grad).all()
     assert_close(logits.grad[1], lc.grad[1], rtol=1e-3, atol=1e-7, what='focal gradient')
+
+
+def test_hook_mode_attention_maps_and_probabilities():
+    """SURVEY N4 / VERDICT B7: forward hooks on blocks[i].attn / .norm1 / .mlp / norm fire with the tensors of the fused
+    trunk (the reference's explainability code registers exactly those: backbone.py:51-53, attention_maps.py:31-33,
+    gradcam.py:40); checked against the oracle trunk's own intermediate tensors."""
+    from oracle import vit as ovit
+    sd = omodel.random_state_dict(7)
+    m = RoViTKAN(pretrained=False, dropout=0.0)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).eval()
+    x = torch.randn(3, 3, 224, 224, device=DEV)
+    maps = m.get_attention_maps(x)                                   # rovit_kan.py:163-165 -> backbone.py:36-62
+    assert len(maps) == 12 and all(t.shape == (3, 197, 192) for t in maps)
+    # oracle intermediates
+    trunk = ovit.DeiTTinyOracle()
+    trunk.load_state_dict({k[len('backbone.model.'):]: v for k, v in sd.items() if k.startswith('backbone.model.')})
+    trunk = trunk.to(DEV).eval()
+    ref_attn, ref_norm1, ref_probs = [], [], []
+    hooks = [b.attn.register_forward_hook(lambda mod, i, o: ref_attn.append(o)) for b in trunk.blocks]
+    hooks += [b.norm1.register_forward_hook(lambda mod, i, o: ref_norm1.append(o)) for b in trunk.blocks]
+    with torch.no_grad():
+        f_ref = trunk(x)
+    for h in hooks:
+        h.remove()
+    for i in (0, 5, 11):
+        assert_close(maps[i], ref_attn[i], rtol=3e-2, atol=0, scale_tol=3e-2, what=f'blocks[{i}].attn output')
+    got_norm1, got_final = [], []
+    h1 = m.backbone.model.blocks[-1].norm1.register_forward_hook(lambda mod, i, o: got_norm1.append((i[0], o)))   # gradcam.py:40
+    h2 = m.backbone.model.norm.register_forward_hook(lambda mod, i, o: got_final.append(o))
+    with torch.no_grad():
+        out = m(x)
+    h1.remove(); h2.remove()
+    assert len(got_norm1) == 1 and got_norm1[0][1].shape == (3, 197, 192)
+    assert_close(got_norm1[0][1], ref_norm1[-1], rtol=3e-2, atol=0, scale_tol=3e-2, what='blocks[-1].norm1 output')
+    assert torch.equal(got_final[0], out['features'])
+    assert_close(out['features'], f_ref, rtol=2e-2, atol=0, scale_tol=2e-2, what='features in hook mode')
+    with torch.no_grad():
+        plain = m(x)                                                 # hooks removed: back on the fused inference path
+    assert_close(plain['features'], out['features'], rtol=2e-2, atol=0, scale_tol=2e-2, what='hook mode vs fused path')
+    probs = m.backbone.model.attention_probabilities(x)
+    assert len(probs) == 12 and probs[0].shape == (3, 3, 197, 197)
+    assert_close(probs[3].sum(-1), torch.ones(3, 3, 197, device=DEV), rtol=1e-5, atol=1e-5, what='rows of P sum to 1')
+    # against softmax(q k^T / 8) recomputed from the oracle's qkv of that block
+    blk = trunk.blocks[3]
+    with torch.no_grad():
+        qkv = blk.attn.qkv(ref_norm1[3]).reshape(3, 197, 3, 3, 64).permute(2, 0, 3, 1, 4)
+        want = torch.softmax(qkv[0] @ qkv[1].transpose(-2, -1) * 0.125, dim=-1)
+    assert_close(probs[3], want, rtol=5e-2, atol=2e-4, what='attention probabilities of block 3')

@@ -9,8 +9,11 @@ the benchmark batch (per-image results do not depend on batch size, chunking or 
 Tolerances.  Heads/KAN/loss run in fp32 (1e-3 relative, see test_gpu_heads.py).  The trunk computes
 its GEMMs and attention with bf16 operands and fp32 accumulation; the fp32 residual stream sums 25
 such products, so trunk outputs are compared with the STATED bf16 tolerance
-    |a - b| <= BF16_RTOL*|b| + BF16_STOL*max|b|      (BF16_RTOL = BF16_STOL = 3e-2)
-and gradients with a relative L2 bound of GRAD_REL_L2 = 6e-2 per tensor.
+    |a - b| <= BF16_RTOL*|b| + BF16_STOL*max|b|      (BF16_RTOL = BF16_STOL = 2e-2: twice the worst deviation measured on
+                                                      B200, 0.85e-2 at batch 1024 -- tests/test_gpu_parity_full.py)
+and gradients with a relative L2 bound per tensor: GRAD_REL_L2 = 2e-2 for the trunk VJP (measured 5-8e-3), 6e-2 for the
+trunk and 1e-1 for the heads on the 2-image golden batch (measured 3-4e-2: a single ReLU flip in a 128-unit hidden layer is
+a visible share of a 2-image gradient).
 
 `kan_severity` needs its own bound.  The reference's KAN basis is DISCONTINUOUS at tanh(x) = knots[7] = 0.4
 (the basis jumps from [0,0,0,0,1/6,2/3,1/6] to 0), and with 192 features per image about 2.6 %
@@ -39,9 +42,11 @@ if torch.cuda.is_available():
     from rovitkan_b200.training.losses import JointLoss
 
 DEV = 'cuda'
-BF16_RTOL = 3e-2
-BF16_STOL = 3e-2
-GRAD_REL_L2 = 6e-2
+BF16_RTOL = 2e-2
+BF16_STOL = 2e-2
+GRAD_REL_L2 = 2e-2
+GRAD_REL_L2_GOLDEN_B2 = 6e-2
+GRAD_REL_L2_GOLDEN_B2_HEADS = 1e-1
 KAN_BF16_ATOL = 0.35
 
 
@@ -144,7 +149,7 @@ def test_loss_and_gradients_match_reference(golden_setup):
     # at batch 2 a single ReLU flip in a head's 128-unit hidden layer (bf16-sized feature noise) is a visible share
     # of that head's gradient; the heads are checked to 1e-3 at identical features in
     # test_heads_kan_loss_backward_at_our_features, so only the trunk gets the tight bound here
-    bad = {k: v for k, v in report.items() if not v < (GRAD_REL_L2 if k.startswith('backbone') else 0.3)}
+    bad = {k: v for k, v in report.items() if not v < (GRAD_REL_L2_GOLDEN_B2 if k.startswith('backbone') else GRAD_REL_L2_GOLDEN_B2_HEADS)}
     assert not bad, bad
     assert all(p.grad is None for p in m.kan_module.parameters())
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for n, p in m.named_parameters()
@@ -217,7 +222,7 @@ def test_heads_kan_loss_backward_at_our_features(batch):
 
 def test_stage4_end_to_end_deviation_report():
     """Composed stage-4 forward/backward vs the oracle: outputs within the stated bf16 bounds; gradients are
-    reported (they inherit the KAN basis flips) and only required to stay finite and correlated."""
+    reported (they inherit the KAN's hypersensitivity, see test_gpu_parity_full.py)."""
     batch = 33
     sd, sdd, images = _oracle_setup(3, batch)
     yc = torch.randint(0, 4, (batch,))
@@ -237,10 +242,11 @@ def test_stage4_end_to_end_deviation_report():
     errs = {k: rel_l2(named[k].grad, sdd[k].grad) for k in named}
     print('stage-4 end-to-end gradient rel-L2: worst', max((v, k) for k, v in errs.items()),
           'median', sorted(errs.values())[len(errs) // 2])
-    for k, p in named.items():
-        a, b = p.grad.flatten().double(), sdd[k].grad.flatten().double()
-        cos = float((a @ b) / (a.norm() * b.norm() + 1e-30))
-        assert torch.isfinite(p.grad).all() and cos > 0.3, (k, cos)
+    # the composed stage-4 gradient is judged at full size against the bf16-autocast yard-stick
+    # (test_gpu_parity_full.py::test_train_step_batch_256_losses_and_all_gradients); here: finite, and the part of the loss
+    # that does not pass through the KAN must already be close
+    assert all(torch.isfinite(p.grad).all() for p in named.values())
+    assert errs['classification_head.fc2.weight'] < 5e-2 and errs['ordinal_head.fc2.weight'] < 5e-2, errs
 
 
 def test_batch_and_chunk_invariance_at_benchmark_size():

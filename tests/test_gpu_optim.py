@@ -80,6 +80,8 @@ def test_gradscaler_flows(flow):
     o = FusedAdamW(_groups(ours), weight_decay=1e-4, max_grad_norm=1.0 if flow == 'fused' else None)
     r = torch.optim.AdamW(_groups(ref), weight_decay=1e-4, foreach=False, fused=False)
     so, sr = torch.amp.GradScaler('cuda', init_scale=1024.0), torch.amp.GradScaler('cuda', init_scale=1024.0)
+    sr._lazy_init_scale_growth_tracker(torch.device(DEV))
+    so._lazy_init_scale_growth_tracker(torch.device(DEV))
     for step in range(3):
         for p, q, g in zip(ours, ref, _grads(step, scale=1024.0)):
             p.grad, q.grad = g.clone(), g.clone()
@@ -87,8 +89,6 @@ def test_gradscaler_flows(flow):
             ours[2].grad[0, 0] = float('nan')
             ref[2].grad[0, 0] = float('nan')
         # torch side, as the reference's trainer drives it (scale() is emulated by the pre-scaled gradients)
-        sr._lazy_init_scale_growth_tracker(torch.device(DEV))
-        so._lazy_init_scale_growth_tracker(torch.device(DEV))
         sr.unscale_(r)
         torch.nn.utils.clip_grad_norm_(ref, 1.0)
         sr.step(r)

@@ -173,43 +173,70 @@ def test_inference_batch_1024_against_fp32_oracle_and_bf16_yardstick():
 
 
 def test_train_step_batch_256_losses_and_all_gradients():
+    """BASELINE configs[3] at full size.  Two backward passes per implementation:
+      (i)  the stage-3 loss (focal + ordinal + uncertainty): well conditioned -> absolute bounds on all 164 gradients it reaches;
+      (ii) the full stage-4 loss.  The reference's KAN makes d(loss)/d(features) hypersensitive: with the ORACLE alone, relative
+           feature noise of 1e-4 already moves the KAN gradients by 0.5 %, 2.5e-3 (the size of any bf16 trunk's error) by 10 %
+           (measured; cascaded cubic segments of width 0.2 plus the jump at tanh(x) = 0.4).  An absolute bound would only
+           measure that conditioning, so stage 4 is judged by the survey's second yard-stick: the reference's own trunk under
+           torch.autocast(bfloat16) on this device, against the same fp32 oracle."""
     batch = 256
     sd = _weights(4)
-    sdd = {k: (v.to(DEV).requires_grad_(True) if not k.endswith('knots') else v.to(DEV)) for k, v in sd.items()}
     g = torch.Generator().manual_seed(4)
     images = torch.randn(batch, 3, 224, 224, generator=g).to(DEV)
     yc = torch.randint(0, 4, (batch,), generator=g).to(DEV)
     alpha = torch.tensor([0.7, 1.1, 0.9, 1.3], device=DEV)
-    m = _model(sd, train=True)
-    o = m(images)
-    oo = omodel.forward(sdd, images)
-    clean = _flip_free(m, sdd, o['features'].detach(), oo['features'].detach())[:, None]
-    # samples whose KAN basis flipped between the two runs keep their forward value but carry no KAN gradient (both sides)
-    o_m = dict(o, kan_severity=torch.where(clean, o['kan_severity'], o['kan_severity'].detach()))
-    oo_m = dict(oo, kan_severity=torch.where(clean, oo['kan_severity'], oo['kan_severity'].detach()))
-    r = JointLoss(focal_alpha=alpha)(o_m, yc, yc, 4)
-    rr = olosses.joint(oo_m, yc, yc, 4, alpha=alpha)
-    r['total_loss'].backward()
-    rr['total_loss'].backward()
-    print(f'\n  flip-free samples {int(clean.sum())}/{batch}')
-    assert 1.0 - float(clean.float().mean()) <= KAN_FLIP_RATE_MAX
-    for k in ('cls_loss', 'ord_loss', 'unc_loss'):
-        print(f'  {k}: ours {float(r[k]):.6f} oracle {float(rr[k]):.6f}')
-        assert_close(r[k], rr[k], rtol=1e-2, atol=1e-3, what=k)
-    kan_c = ((o['kan_severity'] - yc[:, None].float()) ** 2)[clean].mean()
-    kan_r = ((oo['kan_severity'] - yc[:, None].float()) ** 2)[clean].mean()
-    print(f'  kan_loss on flip-free samples: ours {float(kan_c):.6f} oracle {float(kan_r):.6f}; all samples {float(r["kan_loss"]):.6f} / {float(rr["kan_loss"]):.6f}')
-    assert_close(kan_c, kan_r, rtol=5e-2, atol=5e-3, what='kan_loss (flip-free samples)')
-    named = dict(m.named_parameters())
-    assert len(named) == 173
-    errs = {k: rel_l2(p.grad, sdd[k].grad) for k, p in named.items()}
+
+    def oracle_run(stage, autocast):
+        sdd = {k: (v.to(DEV).requires_grad_(True) if not k.endswith('knots') else v.to(DEV)) for k, v in sd.items()}
+        if autocast:
+            with torch.autocast('cuda', dtype=torch.bfloat16):
+                f = ovit.forward_functional(sdd, images, prefix='backbone.model.')
+            out = omodel.heads_forward(sdd, f.float(), 4)
+        else:
+            out = omodel.forward(sdd, images)
+        losses = olosses.joint(out, yc, yc, stage, alpha=alpha)
+        losses['total_loss'].backward()
+        return {k: v.detach() for k, v in losses.items()}, {k: v.grad for k, v in sdd.items() if v.requires_grad and v.grad is not None}
+
+    def ours_run(stage):
+        m = _model(sd, train=True)
+        losses = JointLoss(focal_alpha=alpha)(m(images), yc, yc, stage)
+        losses['total_loss'].backward()
+        return {k: v.detach() for k, v in losses.items()}, {k: p.grad for k, p in m.named_parameters() if p.grad is not None}
+
+    print()
+    # ---- (i) stage-3 loss
+    l_ref, g_ref = oracle_run(3, False)
+    l_our, g_our = ours_run(3)
+    for k in ('cls_loss', 'ord_loss', 'unc_loss', 'total_loss'):
+        print(f'  stage 3 {k}: ours {float(l_our[k]):.6f} oracle {float(l_ref[k]):.6f}')
+        assert_close(l_our[k], l_ref[k], rtol=1e-2, atol=1e-3, what=k)
+    assert set(g_our) == set(g_ref) and len(g_our) == 173 - 9
+    errs = {k: rel_l2(g_our[k], g_ref[k]) for k in g_ref}
     trunk = {k: v for k, v in errs.items() if k.startswith('backbone')}
     heads = {k: v for k, v in errs.items() if not k.startswith('backbone')}
-    print('  trunk gradients (150): worst', max((v, k) for k, v in trunk.items()), 'median', sorted(trunk.values())[75])
-    print('  head/KAN gradients (23):', {k: f'{v:.1e}' for k, v in heads.items()})
+    print('  stage 3 trunk gradients (150): worst', max((v, k) for k, v in trunk.items()), 'median', sorted(trunk.values())[75])
+    print('  stage 3 head gradients (14): worst', max((v, k) for k, v in heads.items()))
     bad = {k: v for k, v in trunk.items() if not v <= GRAD_REL_L2_TRUNK}
     bad.update({k: v for k, v in heads.items() if not v <= GRAD_REL_L2_HEADS})
     assert not bad, bad
+    # ---- (ii) stage-4 loss against the bf16-autocast yard-stick
+    l_ref, g_ref = oracle_run(4, False)
+    l_yard, g_yard = oracle_run(4, True)
+    l_our, g_our = ours_run(4)
+    assert len(g_our) == 173
+    for k in ('cls_loss', 'ord_loss', 'unc_loss', 'kan_loss', 'total_loss'):
+        print(f'  stage 4 {k}: ours {float(l_our[k]):.6f} oracle {float(l_ref[k]):.6f} oracle under autocast(bf16) {float(l_yard[k]):.6f}')
+        assert abs(float(l_our[k]) - float(l_ref[k])) <= max(1.5 * abs(float(l_yard[k]) - float(l_ref[k])), 1e-2 * abs(float(l_ref[k])) + 1e-3), k
+    e_our = {k: rel_l2(g_our[k], g_ref[k]) for k in g_ref}
+    e_yard = {k: rel_l2(g_yard[k], g_ref[k]) for k in g_ref}
+    ratio = sorted(e_our[k] / max(e_yard[k], 1e-12) for k in g_ref)
+    print('  stage 4 gradient rel-L2 vs fp32 oracle: ours median', sorted(e_our.values())[86], 'worst', max((v, k) for k, v in e_our.items()))
+    print('                  oracle under autocast(bf16): median', sorted(e_yard.values())[86], 'worst', max((v, k) for k, v in e_yard.items()))
+    print(f'  ours / yard-stick per tensor: median {ratio[86]:.2f}, 90th percentile {ratio[155]:.2f}, max {ratio[-1]:.2f}')
+    assert ratio[86] <= 1.0, 'half of the gradient tensors are further from the fp32 reference than the reference under bf16 autocast'
+    assert ratio[155] <= 1.5 and all(torch.isfinite(v).all() for v in g_our.values())
 
 
 def test_kan_microbench_config_batch_65536_forward_backward():
