@@ -156,6 +156,24 @@ int rvk_encoder_backward_range(const void* const* params_host, const void* wbuf,
                                const float* dfeatures, int batch, int chunk_images, void* const* grads_host,
                                int stage_begin, int stage_end, void* stream);
 
+/* The same tail for the TRAINING step (north_star (c): "heads and their losses become one fused epilogue", forward and
+ * backward): one forward launch and -- after rvk_joint_loss_forward / _backward produced d(loss)/d(head outputs) -- one
+ * backward launch (+ a memset and an unpack launch) replace ~50 per-layer launches.  Forward: Dropout(drop_p) on the three
+ * hidden layers with a Philox keep mask (seed, offset); h_save [batch,384], a1_save [batch,64], a2_save [batch,16] receive
+ * the activations the backward needs.  Backward: d_* = gradients of the five outputs (NULL = that head is stage-gated
+ * off: its parameters get no gradient), dfeatures [batch,192] is overwritten, dws = scratch of
+ * rvk_heads_fused_workspace_floats() floats, grads23_host = host array of 23 device pointers in the parameter order of
+ * rvk_heads_fused_prepare (NULL entries are skipped); gradients are OVERWRITTEN, not accumulated. */
+int rvk_heads_train_forward(const float* features, const float* ws, const float* knots_host, int batch, float drop_p,
+                            uint64_t seed, uint64_t offset, float* cls_logits, float* ordinal_logits, float* mu,
+                            float* log_var, float* kan_severity, float* h_save, float* a1_save, float* a2_save,
+                            void* stream);
+int rvk_heads_train_backward(const float* features, const float* ws, const float* knots_host, int batch, float drop_p,
+                             const float* h_save, const float* a1_save, const float* a2_save, const float* log_var,
+                             const float* kan_severity, const float* d_cls, const float* d_ord, const float* d_mu,
+                             const float* d_log_var, const float* d_kan, float* dfeatures, float* dws,
+                             float* const* grads23_host, void* stream);
+
 /* ---- fused optimizer tail ---------------------------------------------------------------
  * Replaces what the reference's trainer runs after loss.backward() (training/trainer.py:118-129): GradScaler.unscale_ and
  * its inf check, clip_grad_norm_(parameters, max_norm), AdamW.step with the two learning-rate groups of

@@ -249,6 +249,24 @@ int rvk_attention_probs(const void* qkv_bf16, float* probs, int batch, void* str
   return rvk_attention_probs_launch(qkv_bf16, probs, batch, S(stream));
 }
 
+// ---- fused multi-task tail, training
+int rvk_heads_train_forward(const float* features, const float* ws, const float* knots_host, int batch, float drop_p,
+                            uint64_t seed, uint64_t offset, float* cls_logits, float* ordinal_logits, float* mu, float* log_var,
+                            float* kan_severity, float* h_save, float* a1_save, float* a2_save, void* stream) {
+  if (batch < 0) return RVK_ERR_BAD_ARG;
+  return rvk_heads_train_fwd_launch(features, ws, knots_host, batch, drop_p, seed, offset, cls_logits, ordinal_logits, mu, log_var,
+                                    kan_severity, h_save, a1_save, a2_save, S(stream));
+}
+int rvk_heads_train_backward(const float* features, const float* ws, const float* knots_host, int batch, float drop_p,
+                             const float* h_save, const float* a1_save, const float* a2_save, const float* log_var,
+                             const float* kan_severity, const float* d_cls, const float* d_ord, const float* d_mu,
+                             const float* d_log_var, const float* d_kan, float* dfeatures, float* dws,
+                             float* const* grads23_host, void* stream) {
+  if (batch < 0) return RVK_ERR_BAD_ARG;
+  return rvk_heads_train_bwd_launch(features, ws, knots_host, batch, drop_p, h_save, a1_save, a2_save, log_var, kan_severity, d_cls,
+                                    d_ord, d_mu, d_log_var, d_kan, dfeatures, dws, grads23_host, S(stream));
+}
+
 // ---- fused optimizer tail
 int64_t rvk_optimizer_state_floats(int n_tensors, const int64_t* numel_host) {
   if (n_tensors < 0 || (n_tensors > 0 && numel_host == nullptr)) return -1;

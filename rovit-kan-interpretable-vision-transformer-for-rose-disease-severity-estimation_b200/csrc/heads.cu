@@ -12,26 +12,6 @@
 
 namespace {
 
-// ------------------------------------------------------------------ Philox4x32-10 (counter-based RNG)
-__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
-  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-  for (int r = 0; r < 10; ++r) {
-    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
-    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
-    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-    key.x += W0;
-    key.y += W1;
-  }
-  return ctr;
-}
-__device__ __forceinline__ float uniform01(unsigned long long seed, unsigned long long offset, unsigned long long idx) {
-  const uint4 r = philox4x32_10(make_uint4(static_cast<uint32_t>(idx), static_cast<uint32_t>(idx >> 32),
-                                           static_cast<uint32_t>(offset), static_cast<uint32_t>(offset >> 32)),
-                                make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
-  return (r.x >> 8) * (1.0f / 16777216.0f);
-}
-
 // ------------------------------------------------------------------ register-tiled fp32 GEMM
 // C[M,N] = epilogue(op(A)[M,K] * op(B)[K,N]); 64x64 tile, 4x4 per thread, K chunks of 16.
 struct SgemmParams {

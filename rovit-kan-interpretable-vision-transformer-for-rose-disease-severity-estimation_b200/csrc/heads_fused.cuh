@@ -97,10 +97,19 @@ __device__ __forceinline__ void hf_cp_async16(float* smem_dst, const float* gsrc
                "l"(gsrc) : "memory");
 }
 
+// TRAIN: the same kernel as the forward of the training step -- dropout on the three hidden layers (Philox keep mask, scaled
+// by 1 / (1 - p), heads.py:20,41,94) and the activations the backward kernel (heads_train.cuh) needs are written out: the
+// hidden layers after ReLU + dropout [B,384], the KAN hidden activations after ReLU [B,64] and [B,16].
+struct HeadsTrainSave {
+  float* h;  float* a1;  float* a2;
+  float drop_p;  unsigned long long seed, offset;
+};
+
+template <bool TRAIN>
 __global__ void __launch_bounds__(kHfThreads, 1)
 heads_fused_kernel(const float* __restrict__ feat, const float* __restrict__ ws, Knots kn, int batch,
                    float* __restrict__ cls, float* __restrict__ ord, float* __restrict__ mu, float* __restrict__ log_var,
-                   float* __restrict__ kan) {
+                   float* __restrict__ kan, const HeadsTrainSave sv) {
   extern __shared__ __align__(16) float hsm[];
   float* sF = hsm + kHfSmF;
   float* sA = hsm + kHfSmA;
@@ -201,7 +210,15 @@ heads_fused_kernel(const float* __restrict__ feat, const float* __restrict__ ws,
     float v = __ldg(ws + kHfOffB1 + u);
 #pragma unroll
     for (int q = 0; q < kHfG1; ++q) v += sP1[(q * kHfU + u) * kHfS + s];
-    sH[s * kHfHStride + u] = fmaxf(v, 0.0f);
+    v = fmaxf(v, 0.0f);
+    if (TRAIN) {
+      if (sv.drop_p > 0.0f) {
+        const float r = uniform01(sv.seed, sv.offset, static_cast<unsigned long long>(s0 + s) * kHfU + u);
+        v = (r >= sv.drop_p) ? v * (1.0f / (1.0f - sv.drop_p)) : 0.0f;
+      }
+      if (s0 + s < batch) sv.h[static_cast<size_t>(s0 + s) * kHfU + u] = v;
+    }
+    sH[s * kHfHStride + u] = v;
   }
   // ---- ... and KAN layer-0 outputs (bias, ReLU), expanded straight into the layer-1 activations
   {
@@ -210,7 +227,9 @@ heads_fused_kernel(const float* __restrict__ feat, const float* __restrict__ ws,
 #pragma unroll
     for (int g = 0; g < kHfG0; ++g) v += sP0[(g * kHfO0 + o) * kHfS + s];
     float a[kKW], da[kKW], dt;
-    kan_expand<false>(fmaxf(v, 0.0f), kn, a, da, dt);
+    v = fmaxf(v, 0.0f);
+    if (TRAIN && s0 + s < batch) sv.a1[static_cast<size_t>(s0 + s) * kHfO0 + o] = v;
+    kan_expand<false>(v, kn, a, da, dt);
 #pragma unroll
     for (int k = 0; k < kKW; ++k) sA[o * kHfAStride + k * kHfS + s] = a[k];
   }
@@ -233,7 +252,9 @@ heads_fused_kernel(const float* __restrict__ feat, const float* __restrict__ ws,
 #pragma unroll
     for (int q = 0; q < kHfG1; ++q) v += sP0[q * 128 + s * kHfO1 + i];
     float a[kKW], da[kKW], dt;
-    kan_expand<false>(fmaxf(v, 0.0f), kn, a, da, dt);
+    v = fmaxf(v, 0.0f);
+    if (TRAIN && s0 + s < batch) sv.a2[static_cast<size_t>(s0 + s) * kHfO1 + i] = v;
+    kan_expand<false>(v, kn, a, da, dt);
     float acc = 0.0f;
 #pragma unroll
     for (int k = 0; k < kKW; ++k) acc = fmaf(a[k], sWp2[i * 8 + k], acc);

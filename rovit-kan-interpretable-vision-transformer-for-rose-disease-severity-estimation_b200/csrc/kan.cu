@@ -369,6 +369,7 @@ bool kan_use_tc(int batch, int n_in, int n_out) {
 #include "kan_tc.cuh"
 #include "kan_small.cuh"
 #include "heads_fused.cuh"
+#include "heads_train.cuh"
 
 }  // namespace
 
@@ -563,12 +564,59 @@ int rvk_heads_fused_launch(const float* features, const float* ws, const float* 
   if (features == nullptr || ws == nullptr || knots_host == nullptr || cls == nullptr || ord == nullptr || mu == nullptr ||
       log_var == nullptr || kan == nullptr)
     return RVK_ERR_BAD_ARG;
-  RVK_SET_MAX_SMEM(heads_fused_kernel, kHfSmemBytes);
+  RVK_SET_MAX_SMEM(heads_fused_kernel<false>, kHfSmemBytes);
   Knots kn;
   for (int i = 0; i < kKnots; ++i) kn.k[i] = knots_host[i];
   RvkScopedTimer timer(stream, 2.0 * batch * (3.0 * 192 * 128 + 128.0 * 9 + 8.0 * (192 * 64 + 64 * 16 + 16)), 4.0 * batch * (192 + 10),
                        RVK_T_HEADS_FUSED);
-  heads_fused_kernel<<<(batch + kHfS - 1) / kHfS, kHfThreads, kHfSmemBytes, stream>>>(features, ws, kn, batch, cls, ord, mu,
-                                                                                     log_var, kan);
+  heads_fused_kernel<false><<<(batch + kHfS - 1) / kHfS, kHfThreads, kHfSmemBytes, stream>>>(features, ws, kn, batch, cls, ord, mu,
+                                                                                            log_var, kan, HeadsTrainSave{});
+  return rvk_launch_check();
+}
+
+// ---- fused multi-task tail of the TRAINING step (heads_fused.cuh<true>, heads_train.cuh) -----------------------
+int rvk_heads_train_fwd_launch(const float* features, const float* ws, const float* knots_host, int batch, float drop_p,
+                               unsigned long long seed, unsigned long long offset, float* cls, float* ord, float* mu,
+                               float* log_var, float* kan, float* h_save, float* a1_save, float* a2_save, cudaStream_t stream) {
+  if (batch <= 0) return RVK_OK;
+  if (features == nullptr || ws == nullptr || knots_host == nullptr || cls == nullptr || ord == nullptr || mu == nullptr ||
+      log_var == nullptr || kan == nullptr || h_save == nullptr || a1_save == nullptr || a2_save == nullptr || drop_p < 0.0f ||
+      drop_p >= 1.0f)
+    return RVK_ERR_BAD_ARG;
+  RVK_SET_MAX_SMEM(heads_fused_kernel<true>, kHfSmemBytes);
+  Knots kn;
+  for (int i = 0; i < kKnots; ++i) kn.k[i] = knots_host[i];
+  HeadsTrainSave sv{h_save, a1_save, a2_save, drop_p, seed, offset};
+  RvkScopedTimer timer(stream, 2.0 * batch * (3.0 * 192 * 128 + 128.0 * 9 + 8.0 * (192 * 64 + 64 * 16 + 16)),
+                       4.0 * batch * (192 + 10 + 384 + 80), RVK_T_HEADS_TRAIN);
+  heads_fused_kernel<true><<<(batch + kHfS - 1) / kHfS, kHfThreads, kHfSmemBytes, stream>>>(features, ws, kn, batch, cls, ord, mu,
+                                                                                           log_var, kan, sv);
+  return rvk_launch_check();
+}
+
+int rvk_heads_train_bwd_launch(const float* features, const float* ws, const float* knots_host, int batch, float drop_p,
+                               const float* h_save, const float* a1_save, const float* a2_save, const float* lv_out,
+                               const float* kan_out, const float* d_cls, const float* d_ord, const float* d_mu, const float* d_lv,
+                               const float* d_kan, float* dfeat, float* dws, float* const* grads23_host, cudaStream_t stream) {
+  if (batch <= 0) return RVK_OK;
+  if (features == nullptr || ws == nullptr || knots_host == nullptr || h_save == nullptr || a1_save == nullptr ||
+      a2_save == nullptr || lv_out == nullptr || kan_out == nullptr || dfeat == nullptr || dws == nullptr || grads23_host == nullptr)
+    return RVK_ERR_BAD_ARG;
+  RVK_SET_MAX_SMEM(heads_train_bwd_kernel, kHtSmemBytes);
+  Knots kn;
+  for (int i = 0; i < kKnots; ++i) kn.k[i] = knots_host[i];
+  RvkScopedTimer timer(stream, 4.0 * batch * (3.0 * 192 * 128 + 128.0 * 9 + 8.0 * (192 * 64 + 64 * 16 + 16)),
+                       4.0 * batch * (2 * 192 + 10 + 384 + 80) + 8.0 * kHfWsFloats, RVK_T_HEADS_TRAIN);
+  RVK_CUDA_TRY(cudaMemsetAsync(dws, 0, sizeof(float) * kHfWsFloats, stream));
+  HeadsTrainBwdArgs a{features, ws, h_save, a1_save, a2_save, lv_out, kan_out, d_cls, d_ord, d_mu, d_lv, d_kan, dfeat, dws, drop_p, batch};
+  heads_train_bwd_kernel<<<(batch + kHfS - 1) / kHfS, kHtThreads, kHtSmemBytes, stream>>>(a, kn);
+  RVK_TRY(rvk_launch_check());
+  HeadsGradPtrs g;
+  auto G = [&](int i) { return grads23_host[i]; };
+  g.fc1_w[0] = G(0); g.fc1_b[0] = G(1); g.fc2_w[0] = G(2); g.fc2_b[0] = G(3);
+  g.fc1_w[1] = G(4); g.fc1_b[1] = G(5); g.fc2_w[1] = G(6); g.fc2_b[1] = G(7);
+  g.fc1_w[2] = G(8); g.fc1_b[2] = G(9); g.fc2_w[2] = G(10); g.fc2_b[2] = G(11); g.fc2_w[3] = G(12); g.fc2_b[3] = G(13);
+  for (int l = 0; l < 3; ++l) { g.spline[l] = G(14 + 3 * l); g.lin_w[l] = G(15 + 3 * l); g.lin_b[l] = G(16 + 3 * l); }
+  heads_fused_unpack_grad_kernel<<<(kHfWsFloats + 255) / 256, 256, 0, stream>>>(dws, g);
   return rvk_launch_check();
 }

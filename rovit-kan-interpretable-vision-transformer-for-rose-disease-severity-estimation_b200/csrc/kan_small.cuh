@@ -27,8 +27,8 @@ __device__ __forceinline__ bool kan_segment(float t, const Knots& kn, int& j, fl
 #pragma unroll
   for (int m = 1; m < kNB; ++m)
     if (j == m) { k0 = kn.k[m]; k1 = kn.k[m + 1]; }
-  const float h = k1 - k0;
-  const float u = (t - k0) / h;
+  const float ih = 1.0f / (k1 - k0);
+  const float u = (t - k0) * ih;
   const float u2 = u * u, u3 = u2 * u;
   const float om = 1.0f - u;
   v[0] = u3 * (1.0f / 6.0f);
@@ -36,7 +36,6 @@ __device__ __forceinline__ bool kan_segment(float t, const Knots& kn, int& j, fl
   v[2] = (4.0f - 6.0f * u2 + 3.0f * u3) * (1.0f / 6.0f);
   v[3] = om * om * om * (1.0f / 6.0f);
   if (DERIV) {
-    const float ih = 1.0f / h;
     d[0] = 0.5f * u2 * ih;
     d[1] = (3.0f + 6.0f * u - 9.0f * u2) * (1.0f / 6.0f) * ih;
     d[2] = (-12.0f * u + 9.0f * u2) * (1.0f / 6.0f) * ih;
@@ -132,11 +131,14 @@ kan_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ yv, 
   const int i = within / OQ, q = within % OQ;
   const int lane = threadIdx.x & 31;
   const int lead = lane - (lane % OQ);                    // lane of q == 0 for this input (same warp: OQ divides 32, tps % OQ == 0)
-  float acc[kKW][OPT];
+  // weight-gradient accumulators: PRIVATE per thread, but in shared memory ([slot][c][thread]: conflict-free) so that the
+  // slot j - m can index them directly; with register accumulators the one-hot placement cost ~110 select instructions per
+  // (sample, input) (ncu: 320 instructions per pair, ALU pipe 44 %)
+  float* sAcc = sW + n_in * kKW * NOUT;                   // [8][OPT][256]
 #pragma unroll
   for (int k = 0; k < kKW; ++k)
 #pragma unroll
-    for (int c = 0; c < OPT; ++c) acc[k][c] = 0.0f;
+    for (int c = 0; c < OPT; ++c) sAcc[(k * OPT + c) * kSmThreads + threadIdx.x] = 0.0f;
   float db[OPT];
 #pragma unroll
   for (int c = 0; c < OPT; ++c) db[c] = 0.0f;
@@ -183,22 +185,22 @@ kan_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ yv, 
       // linear branch (slot 7)
 #pragma unroll
       for (int c = 0; c < OPT; ++c) {
-        acc[7][c] = fmaf(xv, g[c], acc[7][c]);
+        sAcc[(7 * OPT + c) * kSmThreads + threadIdx.x] += xv * g[c];
         dxp = fmaf(g[c], row[7 * NOUT + c], dxp);
         db[c] += g[c];
       }
-      // spline branch: coefficient of slot k is v[j-k] when 0 <= j-k < 4 (j = 8 in the dead zone: nothing matches)
+      // spline branch: segment m lives in slot j - m (j = 8 in the dead zone: skipped)
       float sp = 0.0f;
+      if (j < kNB) {
 #pragma unroll
-      for (int k = 0; k < kNB; ++k) {
-        const int m = j - k;
-        if (m >= 0 && m < 4) {
-          const float vm = (m == 0) ? v[0] : (m == 1) ? v[1] : (m == 2) ? v[2] : v[3];
-          const float dm = (m == 0) ? d[0] : (m == 1) ? d[1] : (m == 2) ? d[2] : d[3];
+        for (int m = 0; m < 4; ++m) {
+          const int slot = j - m;
+          if (slot >= 0) {
 #pragma unroll
-          for (int c = 0; c < OPT; ++c) {
-            acc[k][c] = fmaf(vm, g[c], acc[k][c]);
-            sp = fmaf(g[c] * row[k * NOUT + c], dm, sp);
+            for (int c = 0; c < OPT; ++c) {
+              sAcc[(slot * OPT + c) * kSmThreads + threadIdx.x] += v[m] * g[c];
+              sp = fmaf(g[c] * row[slot * NOUT + c], d[m], sp);
+            }
           }
         }
       }
@@ -210,7 +212,25 @@ kan_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ yv, 
     }
     if (live_b && q == 0 && dx != nullptr) dx[static_cast<size_t>(b) * n_in + i] = dxp;
   }
-  if (!active || dspline == nullptr) return;
+  if (dspline == nullptr) return;
+  // reduce the G streams of this CTA, then ONE atomicAdd per gradient element and CTA: with one flush per thread the 513
+  // addresses of a 64 -> 1 layer took millions of same-address atomics (measured: 232 us for the kernel, 76 us without)
+  constexpr int kPer = kKW * OPT + OPT;
+  float* sDb = sAcc + kKW * OPT * kSmThreads;             // [OPT][256]
+#pragma unroll
+  for (int c = 0; c < OPT; ++c) sDb[c * kSmThreads + threadIdx.x] = db[c];
+  __syncthreads();
+  if (stream != 0 || !active) return;
+  float tot[kPer];
+#pragma unroll
+  for (int e = 0; e < kPer; ++e) tot[e] = 0.0f;
+  for (int g = 0; g < G; ++g) {
+    const int t = g * tps + within;                       // the thread of stream g that owns the same (input, output quad)
+#pragma unroll
+    for (int e = 0; e < kKW * OPT; ++e) tot[e] += sAcc[e * kSmThreads + t];
+#pragma unroll
+    for (int c = 0; c < OPT; ++c) tot[kKW * OPT + c] += sDb[c * kSmThreads + t];
+  }
   // per-CTA results -> global, straight into the reference layouts (dspline [in][out][7], dlin_w [out][in])
 #pragma unroll
   for (int c = 0; c < OPT; ++c) {
@@ -218,9 +238,14 @@ kan_small_bwd_kernel(const float* __restrict__ x, const float* __restrict__ yv, 
     if (o >= n_out) continue;
 #pragma unroll
     for (int k = 0; k < kNB; ++k)
-      if (acc[k][c] != 0.0f) atomicAdd(&dspline[(static_cast<size_t>(i) * n_out + o) * kNB + k], acc[k][c]);
-    atomicAdd(&dlin_w[static_cast<size_t>(o) * n_in + i], acc[7][c]);
-    if (i == 0) atomicAdd(&dlin_b[o], db[c]);
+      if (tot[k * OPT + c] != 0.0f) atomicAdd(&dspline[(static_cast<size_t>(i) * n_out + o) * kNB + k], tot[k * OPT + c]);
+    atomicAdd(&dlin_w[static_cast<size_t>(o) * n_in + i], tot[7 * OPT + c]);
+  }
+  // bias gradient: every input thread of an output quad holds the same sum; input 0 writes it
+  if (i == 0) {
+#pragma unroll
+    for (int c = 0; c < OPT; ++c)
+      if (q * OPT + c < n_out) atomicAdd(&dlin_b[q * OPT + c], tot[kKW * OPT + c]);
   }
 }
 
@@ -232,7 +257,7 @@ bool kan_small_ok(int n_in, int n_out, bool tc_available) {
   if (n_out > 4 && tc_available) return false;
   const int nout = n_out <= 1 ? 1 : n_out <= 2 ? 2 : n_out <= 4 ? 4 : n_out <= 8 ? 8 : 16;
   const int oq = nout <= 4 ? 1 : nout / 4;
-  return n_in * oq <= kSmThreads && static_cast<size_t>(n_in) * kKW * nout * 4 <= 96 * 1024;
+  return n_in * oq <= kSmThreads && static_cast<size_t>(n_in) * kKW * nout * 4 <= 60 * 1024;
 }
 bool kan_small_disabled() {
   static const bool off = [] { const char* e = getenv("RVK_KAN_NO_SMALL"); return e != nullptr && e[0] == '1'; }();
@@ -255,13 +280,16 @@ template <int NOUT>
 int kan_small_bwd_launch_t(const KanLayerDesc& L, const float* x, const float* y, const float* gy, int act, float* dx, float* dspline,
                            float* dlin_w, float* dlin_b, int batch, const Knots& kn, cudaStream_t stream) {
   constexpr int OQ = NOUT <= 4 ? 1 : NOUT / 4;
+  constexpr int OPT = NOUT < 4 ? NOUT : 4;
   const int G = kSmThreads / (L.in_features * OQ);
-  const int smem = L.in_features * kKW * NOUT * 4;
+  (void)G;
+  const int smem = (L.in_features * kKW * NOUT + (kKW * OPT + OPT) * kSmThreads) * 4;    // weights + per-thread accumulators
   auto kernel = kan_small_bwd_kernel<NOUT>;
   if (smem > 48 * 1024) RVK_SET_MAX_SMEM(kernel, 100 * 1024);
   // enough resident warps to hide the load latency of the sample loop (8 CTAs per SM), each CTA with at least a few rounds of
   // work: its register accumulators are flushed once, n_in * 8 * n_out atomics per CTA
-  int ctas = kNumSMsB200 * 8;
+  static const int per_sm = [] { const char* e = getenv("RVK_KAN_SMALL_CTAS_PER_SM"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 4; }();
+  int ctas = kNumSMsB200 * per_sm;
   const int min_per_cta = G * 8;
   if (static_cast<long long>(ctas) * min_per_cta > batch) ctas = (batch + min_per_cta - 1) / min_per_cta;
   if (ctas < 1) ctas = 1;

@@ -56,6 +56,14 @@ int rvk_attention_bwd_tc_launch(const void* qkv, const void* ctx, const void* dc
                                 int batch, cudaStream_t stream);
 
 // ---- token-stream kernels (encoder_kernels.cu) -----------------------------------------------------
+// fused multi-task tail of the training step (kan.cu: heads_fused.cuh<true>, heads_train.cuh)
+int rvk_heads_train_fwd_launch(const float* features, const float* ws, const float* knots_host, int batch, float drop_p,
+                               unsigned long long seed, unsigned long long offset, float* cls, float* ord, float* mu,
+                               float* log_var, float* kan, float* h_save, float* a1_save, float* a2_save, cudaStream_t stream);
+int rvk_heads_train_bwd_launch(const float* features, const float* ws, const float* knots_host, int batch, float drop_p,
+                               const float* h_save, const float* a1_save, const float* a2_save, const float* lv_out,
+                               const float* kan_out, const float* d_cls, const float* d_ord, const float* d_mu, const float* d_lv,
+                               const float* d_kan, float* dfeat, float* dws, float* const* grads23_host, cudaStream_t stream);
 // fused optimizer tail (optimizer.cu)
 int64_t rvk_optimizer_state_floats_impl(int n, const int64_t* numel_host);
 int rvk_optimizer_step_impl(int n, void* const* params_host, const void* const* grads_host, const int64_t* numel_host,

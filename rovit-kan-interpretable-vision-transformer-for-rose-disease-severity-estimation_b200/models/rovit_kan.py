@@ -22,6 +22,11 @@ def _serial_heads() -> bool:
     return os.environ.get('RVK_SERIAL_HEADS', '0') == '1'
 
 
+def _fused_train_tail() -> bool:
+    import os
+    return os.environ.get('RVK_FUSED_TAIL', '1') != '0'
+
+
 class RoViTKAN(nn.Module):
     def __init__(self, config_or_embed_dim=None, hidden_dim: int = 128, num_classes: int = 4,
                  kan_layers: list = None, kan_num_knots: int = 5, kan_degree: int = 3, dropout: float = 0.3,
@@ -92,6 +97,21 @@ class RoViTKAN(nn.Module):
                 return {'cls_logits': cls, 'features': features, 'ordinal_logits': ordl, 'mu': mu, 'log_var': lv,
                         'kan_severity': kan}
         out = {'cls_logits': None, 'features': features, 'ordinal_logits': None, 'mu': None, 'log_var': None, 'kan_severity': None}
+        if torch.is_grad_enabled() and features.is_cuda and _fused_train_tail():
+            # training: the whole tail is one forward and one backward kernel (csrc/heads_fused.cuh<true>, heads_train.cuh);
+            # gated outputs are simply not handed out, so their parameters receive no gradient
+            ps = self._fused_tail_params()
+            drops = {h.dropout.p if self.training else 0.0 for h in (self.classification_head, self.ordinal_head, self.uncertainty_head)}
+            if ps is not None and len(drops) == 1:
+                cls, ordl, mu, lv, kan = _ops().HeadsTrainFn.apply(features, self.kan_module.kan_layers[0].knots_host(), drops.pop(), *ps)
+                out['cls_logits'] = cls
+                if stage >= 2:
+                    out['ordinal_logits'] = ordl
+                if stage >= 3:
+                    out['mu'], out['log_var'] = mu, lv
+                if stage >= 4:
+                    out['kan_severity'] = kan
+                return out
         branches = [('cls', self.classification_head)]
         if stage >= 2:
             branches.append(('ord', self.ordinal_head))

@@ -415,3 +415,55 @@ def heads_fused(state: HeadsFusedState, features: torch.Tensor, params, knots_ho
         _lib.call('rvk_heads_fused', _p(f), _p(state.ws), _host_floats(knots_host), batch, _p(cls), _p(ordl), _p(mu), _p(lv),
                   _p(kan), _stream())
     return cls, ordl, mu, lv, kan
+
+
+class HeadsTrainFn(torch.autograd.Function):
+    """The whole multi-task tail of the TRAINING step as one forward and one backward kernel (north_star (c); reference
+    rovit_kan.py:96-124 with heads.py:17-22, 38-43, 91-102 and kan.py:138-149).  Inputs: features (B,192) and the 23 head / KAN
+    parameters in rvk_heads_fused_prepare order; outputs (cls_logits, ordinal_logits, mu, log_var, kan_severity).  Outputs the
+    caller does not use receive no gradient, and the parameters behind them get `None` (stage gating, rovit_kan.py:77)."""
+
+    @staticmethod
+    @custom_fwd(device_type='cuda', cast_inputs=torch.float32)
+    def forward(ctx, features, knots_host, drop_p, *params):
+        require_cuda(features, 'RoViTKAN heads (training)')
+        f = _f32c(features)
+        batch, dev = f.shape[0], f.device
+        pc = [_f32c(p) for p in params]
+        lib = _lib.load()
+        nws = lib.rvk_heads_fused_workspace_floats()
+        ws = torch.empty(nws, device=dev, dtype=torch.float32)
+        seed, offset = _rng_keys() if drop_p > 0.0 else (0, 0)
+        mk = lambda n: torch.empty(batch, n, device=dev, dtype=torch.float32)
+        cls, ordl, mu, lv, kan = mk(4), mk(3), mk(1), mk(1), mk(1)
+        h, a1, a2 = mk(384), mk(64), mk(16)
+        kh = _host_floats(knots_host)
+        with torch.cuda.device(dev):
+            table = (C.c_void_p * len(pc))(*[p.data_ptr() for p in pc])
+            _lib.call('rvk_heads_fused_prepare', table, _p(ws), _stream())
+            _lib.call('rvk_heads_train_forward', _p(f), _p(ws), kh, batch, float(drop_p), seed, offset, _p(cls), _p(ordl), _p(mu),
+                      _p(lv), _p(kan), _p(h), _p(a1), _p(a2), _stream())
+        ctx.set_materialize_grads(False)
+        ctx.save_for_backward(f, ws, h, a1, a2, lv, kan)
+        ctx.cfg = (tuple(knots_host), float(drop_p), [tuple(p.shape) for p in pc])
+        return cls, ordl, mu, lv, kan
+
+    @staticmethod
+    @custom_bwd(device_type='cuda')
+    def backward(ctx, g_cls, g_ord, g_mu, g_lv, g_kan):
+        f, ws, h, a1, a2, lv, kan = ctx.saved_tensors
+        knots_host, drop_p, shapes = ctx.cfg
+        batch, dev = f.shape[0], f.device
+        gs = [None if g is None else _f32c(g) for g in (g_cls, g_ord, g_mu, g_lv, g_kan)]
+        need = ctx.needs_input_grad
+        # parameter blocks: 0-3 classification, 4-7 ordinal, 8-13 uncertainty, 14-22 KAN
+        live = [gs[0] is not None] * 4 + [gs[1] is not None] * 4 + [gs[2] is not None or gs[3] is not None] * 6 + [gs[4] is not None] * 9
+        grads = [torch.empty(shp, device=dev, dtype=torch.float32) if (live[i] and need[3 + i]) else None
+                 for i, shp in enumerate(shapes)]
+        dfeat = torch.empty_like(f)
+        dws = torch.empty_like(ws)
+        with torch.cuda.device(dev):
+            gtable = (C.c_void_p * len(grads))(*[_p(g) for g in grads])
+            _lib.call('rvk_heads_train_backward', _p(f), _p(ws), _host_floats(knots_host), batch, drop_p, _p(h), _p(a1), _p(a2),
+                      _p(lv), _p(kan), _p(gs[0]), _p(gs[1]), _p(gs[2]), _p(gs[3]), _p(gs[4]), _p(dfeat), _p(dws), gtable, _stream())
+        return (dfeat if need[0] else None, None, None, *grads)

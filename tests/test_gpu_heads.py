@@ -310,3 +310,71 @@ def test_fused_inference_tail_matches_per_head_kernels_and_oracle(batch):
         m.classification_head.fc2.bias.add_(1.0)
     cls2 = ops.heads_fused(st, fd, m._fused_tail_params(), m.kan_module.kan_layers[0].knots_host())[0]
     assert_close(cls2, cls + 1.0, rtol=1e-5, atol=1e-5, what='repack after parameter update')
+
+
+@pytest.mark.parametrize('batch', [5, 33, 256])
+def test_fused_training_tail_matches_oracle_forward_and_backward(batch):
+    """north_star (c): the heads + KAN stack of the training step as ONE forward and ONE backward kernel (HeadsTrainFn), against
+    autograd through the oracle at identical features: outputs, d(loss)/d(features) and all 23 parameter gradients, fp32 1e-3."""
+    from oracle import losses as olosses
+    from oracle import model as omodel
+    from rovitkan_b200 import ops
+    from rovitkan_b200.models import RoViTKAN
+    from rovitkan_b200.training.losses import JointLoss
+    sd = omodel.random_state_dict(21)
+    m = RoViTKAN(pretrained=False, dropout=0.0)
+    m.load_state_dict(sd, strict=True)
+    m = m.to(DEV).train()
+    g = torch.Generator().manual_seed(3)
+    feats = torch.randn(batch, 192, generator=g)
+    yc = torch.randint(0, 4, (batch,), generator=g)
+    ys = torch.rand(batch, generator=g) * 3
+    f1 = feats.to(DEV).requires_grad_(True)
+    ps = m._fused_tail_params()
+    cls, ordl, mu, lv, kan = ops.HeadsTrainFn.apply(f1, m.kan_module.kan_layers[0].knots_host(), 0.0, *ps)
+    o = {'cls_logits': cls, 'ordinal_logits': ordl, 'mu': mu, 'log_var': lv, 'kan_severity': kan}
+    r = JointLoss()(o, yc.to(DEV), ys.to(DEV), 4)
+    r['total_loss'].backward()
+    sdd = {k: (v.clone().requires_grad_(True) if not k.endswith('knots') else v) for k, v in sd.items()}
+    f2 = feats.clone().requires_grad_(True)
+    oo = omodel.heads_forward(sdd, f2, 4)
+    rr = olosses.joint(oo, yc, ys, 4)
+    rr['total_loss'].backward()
+    for k in o:
+        assert_close(o[k], oo[k], rtol=1e-3, atol=1e-5, what=k)
+    assert_close(f1.grad, f2.grad, rtol=1e-3, atol=1e-6, scale_tol=1e-4, what='d loss / d features')
+    for k, p in m.named_parameters():
+        if not k.startswith('backbone'):
+            assert_close(p.grad, sdd[k].grad, rtol=1e-3, atol=1e-6, scale_tol=2e-4, what=k)
+
+
+def test_fused_training_tail_stage_gating_clamp_and_dropout():
+    from rovitkan_b200 import ops
+    from rovitkan_b200.models import RoViTKAN
+    torch.manual_seed(4)
+    m = RoViTKAN(pretrained=False, dropout=0.3).to(DEV).train()
+    with torch.no_grad():
+        m.uncertainty_head.fc_logvar.bias.fill_(50.0)          # log_var saturates at the +10 clamp: zero gradient through it
+    ps = m._fused_tail_params()
+    knots = m.kan_module.kan_layers[0].knots_host()
+    f = torch.randn(64, 192, device=DEV, requires_grad=True)
+    cls, ordl, mu, lv, kan = ops.HeadsTrainFn.apply(f, knots, 0.3, *ps)
+    assert float(lv.min()) == 10.0
+    (cls.sum() + ordl.sum() + lv.sum()).backward()              # stage-3-like use: KAN output unused, mu unused
+    assert all(p.grad is None for p in m.kan_module.parameters())
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.classification_head.parameters())
+    assert float(m.uncertainty_head.fc_logvar.weight.grad.abs().max()) == 0.0     # clamped everywhere
+    assert float(m.uncertainty_head.fc_mu.weight.grad.abs().max()) == 0.0         # mu got no upstream gradient
+    assert float(m.uncertainty_head.fc1.weight.grad.abs().max()) == 0.0
+    # dropout: two passes differ, and the expectation is preserved (keep mask scaled by 1 / (1 - p))
+    torch.manual_seed(5)
+    a = ops.HeadsTrainFn.apply(f.detach(), knots, 0.3, *[p.detach() for p in ps])[0]
+    b = ops.HeadsTrainFn.apply(f.detach(), knots, 0.3, *[p.detach() for p in ps])[0]
+    c = ops.HeadsTrainFn.apply(f.detach(), knots, 0.0, *[p.detach() for p in ps])[0]
+    assert not torch.equal(a, b)
+    many = torch.stack([ops.HeadsTrainFn.apply(f.detach(), knots, 0.3, *[p.detach() for p in ps])[0] for _ in range(200)]).mean(0)
+    assert_close(many, c, rtol=0, atol=0.08 * float(c.abs().max()) + 0.02, what='dropout preserves the expectation')
+    # the model-level training forward goes through the same path and honours the curriculum stage
+    m.curriculum_stage = 2
+    out = m(torch.randn(3, 3, 224, 224, device=DEV))
+    assert out['kan_severity'] is None and out['mu'] is None and out['ordinal_logits'] is not None

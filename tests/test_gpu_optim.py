@@ -120,7 +120,7 @@ def test_unfreezing_keeps_moments_and_state_dict_round_trip():
     frozen_before = ps[0].detach().clone()
     o.step()
     assert not torch.equal(frozen_before, ps[0]) and float(o.step_count) == 2.0
-    assert_close(o.state[ps[6]]['exp_avg'], 0.9 * m_before + 0.1 * _grads(1)[6], rtol=1e-5, atol=1e-8, what='moments kept')
+    assert_close(o.state[ps[6]]['exp_avg'], 0.9 * m_before + 0.1 * _grads(1)[6], rtol=1e-5, atol=2e-7, what='moments kept')
     sd = o.state_dict()
     ps2 = [p.detach().clone().requires_grad_(True) for p in ps]
     o2 = FusedAdamW(_groups(ps2), weight_decay=1e-4)
