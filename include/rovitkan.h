@@ -156,6 +156,14 @@ int rvk_encoder_backward_range(const void* const* params_host, const void* wbuf,
                                const float* dfeatures, int batch, int chunk_images, void* const* grads_host,
                                int stage_begin, int stage_end, void* stream);
 
+/* RoViTKAN.predict epilogue (models/rovit_kan.py:126-161; OrdinalHead.predict_probabilities / predict_severity,
+ * models/heads.py:45-77): class_probs = softmax(cls_logits) [batch,C], class_index = argmax (int64), ordinal_probs [batch,C]
+ * from the C-1 cumulative logits, ordinal_severity [batch] = sum_k k * p_k, uncertainty_std [batch] = exp(log_var / 2).
+ * ordinal_logits / log_var may be NULL (stage-gated heads). */
+int rvk_predict_decode(const float* cls_logits, int num_classes, const float* ordinal_logits, const float* log_var,
+                       int batch, int64_t* class_index, float* class_probs, float* ordinal_probs,
+                       float* ordinal_severity, float* uncertainty_std, void* stream);
+
 /* The same tail for the TRAINING step (north_star (c): "heads and their losses become one fused epilogue", forward and
  * backward): one forward launch and -- after rvk_joint_loss_forward / _backward produced d(loss)/d(head outputs) -- one
  * backward launch (+ a memset and an unpack launch) replace ~50 per-layer launches.  Forward: Dropout(drop_p) on the three

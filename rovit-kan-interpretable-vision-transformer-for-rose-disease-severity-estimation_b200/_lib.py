@@ -37,6 +37,7 @@ SIGNATURES = {
     'rvk_heads_fused_workspace_floats': (_L, []),
     'rvk_heads_fused_prepare': (_I, [_P, _P, _P]),
     'rvk_heads_fused': (_I, [_P, _P, _P, _I, _P, _P, _P, _P, _P, _P]),
+    'rvk_predict_decode': (_I, [_P, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P]),
     'rvk_heads_train_forward': (_I, [_P, _P, _P, _I, _F, _U64, _U64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'rvk_heads_train_backward': (_I, [_P, _P, _P, _I, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     'rvk_joint_loss_forward': (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _F, _F, _F, _F, _I, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -249,6 +249,15 @@ int rvk_attention_probs(const void* qkv_bf16, float* probs, int batch, void* str
   return rvk_attention_probs_launch(qkv_bf16, probs, batch, S(stream));
 }
 
+int rvk_predict_decode(const float* cls_logits, int num_classes, const float* ordinal_logits, const float* log_var, int batch,
+                       int64_t* class_index, float* class_probs, float* ordinal_probs, float* ordinal_severity,
+                       float* uncertainty_std, void* stream) {
+  if (batch < 0) return RVK_ERR_BAD_ARG;
+  return rvk_predict_decode_launch(cls_logits, num_classes, ordinal_logits, log_var, batch,
+                                   reinterpret_cast<long long*>(class_index), class_probs, ordinal_probs, ordinal_severity,
+                                   uncertainty_std, S(stream));
+}
+
 // ---- fused multi-task tail, training
 int rvk_heads_train_forward(const float* features, const float* ws, const float* knots_host, int batch, float drop_p,
                             uint64_t seed, uint64_t offset, float* cls_logits, float* ordinal_logits, float* mu, float* log_var,

@@ -216,6 +216,49 @@ __global__ void __launch_bounds__(256) joint_loss_kernel(const LossParams p) {
   }
 }
 
+// RoViTKAN.predict epilogue (rovit_kan.py:126-161 with heads.py:45-77): softmax + argmax of the class logits, the ordinal
+// decode c = sigmoid(logits), p0 = c0, pk = ck - ck-1, pK-1 = 1 - cK-2 and its expected value, std = exp(log_var / 2) --
+// one launch instead of ~12 elementwise / reduction kernels (and the reference runs the ordinal head three times for it)
+__global__ void predict_decode_kernel(const float* __restrict__ cls, int C, const float* __restrict__ ordl,
+                                      const float* __restrict__ log_var, int batch, long long* __restrict__ cls_idx,
+                                      float* __restrict__ probs, float* __restrict__ ord_probs, float* __restrict__ ord_sev,
+                                      float* __restrict__ unc_std) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  {
+    const float* z = cls + static_cast<size_t>(b) * C;
+    float mx = z[0];
+    for (int j = 1; j < C; ++j) mx = fmaxf(mx, z[j]);
+    float se = 0.0f;
+    for (int j = 0; j < C; ++j) se += expf(z[j] - mx);
+    const float inv = 1.0f / se;
+    int best = 0;
+    float bp = -1.0f;
+    for (int j = 0; j < C; ++j) {
+      const float pj = expf(z[j] - mx) * inv;
+      probs[static_cast<size_t>(b) * C + j] = pj;
+      if (pj > bp) { bp = pj; best = j; }            // first maximum, like torch.argmax
+    }
+    cls_idx[b] = best;
+  }
+  if (ordl != nullptr) {
+    const int K = C - 1;
+    const float* z = ordl + static_cast<size_t>(b) * K;
+    float prev = 0.0f, sev = 0.0f;
+    for (int k = 0; k < K; ++k) {
+      const float c = 1.0f / (1.0f + expf(-z[k]));
+      const float pk = (k == 0) ? c : c - prev;
+      ord_probs[static_cast<size_t>(b) * C + k] = pk;
+      sev = fmaf(static_cast<float>(k), pk, sev);
+      prev = c;
+    }
+    const float pl = 1.0f - prev;
+    ord_probs[static_cast<size_t>(b) * C + K] = pl;
+    ord_sev[b] = fmaf(static_cast<float>(K), pl, sev);
+  }
+  if (log_var != nullptr) unc_std[b] = expf(0.5f * log_var[b]);
+}
+
 // out = {cls, ord, unc, kan, cls + l_ord*ord + m_unc*unc + n_kan*kan}
 __global__ void loss_finalize_kernel(const float* sums, float l_ord, float m_unc, float n_kan, float* out) {
   if (threadIdx.x == 0) {
@@ -305,5 +348,17 @@ int rvk_loss_scale_grad_launch(const float* local, const float* upstream5, int t
                                cudaStream_t stream) {
   if (n <= 0) return RVK_OK;
   loss_scale_grad_kernel<<<(n + 255) / 256, 256, 0, stream>>>(local, upstream5, term, w_total, dst, n);
+  return rvk_launch_check();
+}
+
+int rvk_predict_decode_launch(const float* cls, int num_classes, const float* ordl, const float* log_var, int batch,
+                              long long* cls_idx, float* probs, float* ord_probs, float* ord_sev, float* unc_std,
+                              cudaStream_t stream) {
+  if (batch <= 0) return RVK_OK;
+  if (cls == nullptr || cls_idx == nullptr || probs == nullptr || num_classes < 2 || num_classes > 64 ||
+      (ordl != nullptr && (ord_probs == nullptr || ord_sev == nullptr)) || (log_var != nullptr && unc_std == nullptr))
+    return RVK_ERR_BAD_ARG;
+  predict_decode_kernel<<<(batch + 255) / 256, 256, 0, stream>>>(cls, num_classes, ordl, log_var, batch, cls_idx, probs, ord_probs,
+                                                                 ord_sev, unc_std);
   return rvk_launch_check();
 }

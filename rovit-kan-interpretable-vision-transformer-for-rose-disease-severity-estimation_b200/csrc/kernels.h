@@ -160,5 +160,8 @@ struct JointLossArgs {
   float* d_cls = nullptr; float* d_ord = nullptr; float* d_mu = nullptr; float* d_lv = nullptr; float* d_kan = nullptr;
 };
 int rvk_joint_loss_launch(const JointLossArgs& a, cudaStream_t stream);
+int rvk_predict_decode_launch(const float* cls, int num_classes, const float* ordl, const float* log_var, int batch,
+                              long long* cls_idx, float* probs, float* ord_probs, float* ord_sev, float* unc_std,
+                              cudaStream_t stream);
 int rvk_loss_scale_grad_launch(const float* local, const float* upstream5, int term, float w_total, float* dst, int n,
                                cudaStream_t stream);

@@ -168,18 +168,16 @@ class RoViTKAN(nn.Module):
         self.eval()
         with torch.no_grad():
             out = self.forward(x)
-            probs = torch.softmax(out['cls_logits'], dim=1)
-            pred = {'class': torch.argmax(probs, dim=1), 'class_probs': probs, 'features': out['features']}
+            # one decode launch (csrc/heads.cu::predict_decode_kernel).  The reference re-runs the ordinal head twice here
+            # (rovit_kan.py:143-148); in eval mode that recomputes the same logits, so the ones already in hand are decoded
+            idx, probs, oprobs, osev, std = _ops().predict_decode(out['cls_logits'], out['ordinal_logits'], out['log_var'])
+            pred = {'class': idx, 'class_probs': probs, 'features': out['features']}
             if out['ordinal_logits'] is not None:
-                # the reference re-runs the ordinal head twice here (rovit_kan.py:143-148); in eval mode that
-                # recomputes the same logits, so decode the ones already in hand
-                p = OrdinalHead.probabilities_from_logits(out['ordinal_logits'])
-                levels = torch.arange(p.shape[1], dtype=torch.float32, device=p.device)
-                pred['ordinal_probs'] = p
-                pred['ordinal_severity'] = (p * levels).sum(dim=1, keepdim=True)
+                pred['ordinal_probs'] = oprobs
+                pred['ordinal_severity'] = osev
             if out['mu'] is not None:
                 pred['uncertainty_mu'] = out['mu']
-                pred['uncertainty_std'] = torch.exp(0.5 * out['log_var'])
+                pred['uncertainty_std'] = std
             if out['kan_severity'] is not None:
                 pred['kan_severity'] = out['kan_severity']
             return pred

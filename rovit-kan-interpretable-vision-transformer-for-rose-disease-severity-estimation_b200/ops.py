@@ -467,3 +467,21 @@ class HeadsTrainFn(torch.autograd.Function):
             _lib.call('rvk_heads_train_backward', _p(f), _p(ws), _host_floats(knots_host), batch, drop_p, _p(h), _p(a1), _p(a2),
                       _p(lv), _p(kan), _p(gs[0]), _p(gs[1]), _p(gs[2]), _p(gs[3]), _p(gs[4]), _p(dfeat), _p(dws), gtable, _stream())
         return (dfeat if need[0] else None, None, None, *grads)
+
+
+def predict_decode(cls_logits, ordinal_logits, log_var):
+    """RoViTKAN.predict epilogue in one launch (rvk_predict_decode): (class, class_probs, ordinal_probs, ordinal_severity, std)."""
+    require_cuda(cls_logits, 'RoViTKAN.predict')
+    cl = _f32c(cls_logits)
+    batch, ncls = cl.shape
+    dev = cl.device
+    ol = None if ordinal_logits is None else _f32c(ordinal_logits)
+    lv = None if log_var is None else _f32c(log_var)
+    idx = torch.empty(batch, device=dev, dtype=torch.int64)
+    probs = torch.empty(batch, ncls, device=dev, dtype=torch.float32)
+    oprobs = torch.empty(batch, ncls, device=dev, dtype=torch.float32) if ol is not None else None
+    osev = torch.empty(batch, 1, device=dev, dtype=torch.float32) if ol is not None else None
+    std = torch.empty(batch, 1, device=dev, dtype=torch.float32) if lv is not None else None
+    with torch.cuda.device(dev):
+        _lib.call('rvk_predict_decode', _p(cl), ncls, _p(ol), _p(lv), batch, _p(idx), _p(probs), _p(oprobs), _p(osev), _p(std), _stream())
+    return idx, probs, oprobs, osev, std
