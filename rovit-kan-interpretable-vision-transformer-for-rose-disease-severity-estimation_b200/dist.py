@@ -97,20 +97,30 @@ def all_reduce_gradients(params, world_size: int | None = None, group=None, aver
         a = g.data_ptr()
         return any(lo <= a < hi for lo, hi in done_ranges)
     rest_all = [g for g in grads if not in_flight(g)]
-    # longest prefix of the remaining gradients that is already one flat buffer (trunk gradient when overlap is off)
-    n = len(rest_all)
-    while n > 0 and not _contiguous_run(rest_all[:n]):
-        n -= 1 if n <= 150 else n - 150
-    works = []
-    if n > 1:
-        total = sum(g.numel() for g in rest_all[:n])
-        flat = torch.empty(0, dtype=rest_all[0].dtype, device=rest_all[0].device).set_(
-            rest_all[0].untyped_storage(), rest_all[0].storage_offset(), (total,), (1,))
+    # split what is left into maximal runs that are already one flat buffer (the trunk gradient when overlap is off, the 23
+    # head / KAN gradients of the fused training tail): those are reduced IN PLACE; single leftovers are coalesced
+    runs = []              # one linear pass: a gradient extends the current run iff it starts where the previous one ended
+    end_ptr, cur = None, None
+    for g in rest_all:
+        ptr = g.data_ptr()
+        ok = (cur is not None and ptr == end_ptr and g.is_contiguous() and g.dtype == cur[0].dtype
+              and g.untyped_storage().data_ptr() == cur[0].untyped_storage().data_ptr())
+        if ok:
+            cur.append(g)
+        else:
+            cur = [g]
+            runs.append(cur)
+        end_ptr = ptr + g.numel() * g.element_size() if g.is_contiguous() else None
+    works, rest = [], []
+    for run in runs:
+        if len(run) == 1 and run[0].numel() < (1 << 16):
+            rest.append(run[0])
+            continue
+        total = sum(g.numel() for g in run)
+        flat = torch.empty(0, dtype=run[0].dtype, device=run[0].device).set_(
+            run[0].untyped_storage(), run[0].storage_offset(), (total,), (1,))
         works.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True), flat, None))
         calls += 1
-    else:
-        n = 0
-    rest = rest_all[n:]
     if rest:
         flat = torch._utils._flatten_dense_tensors(rest)
         works.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True), flat, rest))

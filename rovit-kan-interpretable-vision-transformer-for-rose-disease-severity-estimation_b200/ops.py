@@ -458,8 +458,14 @@ class HeadsTrainFn(torch.autograd.Function):
         need = ctx.needs_input_grad
         # parameter blocks: 0-3 classification, 4-7 ordinal, 8-13 uncertainty, 14-22 KAN
         live = [gs[0] is not None] * 4 + [gs[1] is not None] * 4 + [gs[2] is not None or gs[3] is not None] * 6 + [gs[4] is not None] * 9
-        grads = [torch.empty(shp, device=dev, dtype=torch.float32) if (live[i] and need[3 + i]) else None
-                 for i, shp in enumerate(shapes)]
+        # the live gradients are views of ONE flat buffer in parameter order: a data-parallel caller reduces them in place
+        # with a single collective (dist.all_reduce_gradients), like the trunk's flat gradient
+        numels = [int(torch.Size(shp).numel()) if (live[i] and need[3 + i]) else 0 for i, shp in enumerate(shapes)]
+        flat_g = torch.empty(sum(numels), device=dev, dtype=torch.float32)
+        grads, off = [], 0
+        for n, shp in zip(numels, shapes):
+            grads.append(flat_g[off:off + n].view(shp) if n else None)
+            off += n
         dfeat = torch.empty_like(f)
         dws = torch.empty_like(ws)
         with torch.cuda.device(dev):

@@ -45,7 +45,10 @@ def _worker(rank, world, port, q):
     g_plain, c_plain = grads(False)
     g_over, c_over = grads(True)
     rdist.disable_overlap()
-    same = all((a is None and b is None) or torch.equal(a, b) for a, b in zip(g_plain, g_over))
+    # (the weight-gradient GEMMs accumulate with red.global.add: two backward passes differ in the last bits anyway)
+    num = sum(float((a - b).double().pow(2).sum()) for a, b in zip(g_plain, g_over) if a is not None)
+    den = sum(float(b.double().pow(2).sum()) for a, b in zip(g_plain, g_over) if a is not None)
+    same = (num / den) ** 0.5 < 1e-5 and all((a is None) == (b is None) for a, b in zip(g_plain, g_over))
     # single-GPU full batch on rank 0 (stage 3: the KAN branch is hypersensitive to rounding, see test_gpu_parity_full.py)
     rel = None
     if rank == 0:
@@ -73,5 +76,5 @@ def test_overlapped_allreduce_equals_plain_and_matches_the_full_batch():
         p.join(timeout=120)
     print('\n  ', res)
     assert all(r[1] for r in res), 'overlapped buckets changed the reduced gradients'
-    assert all(r[2] == 2 and r[3] == 4 for r in res), res          # plain: trunk + heads; overlapped: 3 buckets + heads
+    assert all(r[2] == 2 and r[3] == 4 for r in res), res          # plain: trunk + heads (each one flat buffer, reduced in place); overlapped: 3 buckets + heads
     assert res[0][4] < 2e-2, res[0][4]                               # two half batches == one full batch (bf16 trunk rounding)
