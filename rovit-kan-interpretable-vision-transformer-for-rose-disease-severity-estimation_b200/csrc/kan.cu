@@ -443,10 +443,7 @@ int rvk_kan_layer_fwd_launch(const KanLayerDesc& L, const float* x, float* y, in
       RVK_TRY(rvk_launch_check());
     }
     tb.xthr = xthr;
-    for (int j = 0; j < 8; ++j) {
-      tb.knot[j] = L.knots_host[j];
-      tb.inv_h[j] = 1.0f / (L.knots_host[j + 1] - L.knots_host[j]);
-    }
+    kan_tc_fill_tables(tb, L.knots_host);
     kan_fwd_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(tmWhi, tmWlo, x, L.lin_b, tb, y, act, batch, L.in_features,
                                                                  L.out_features, L.in_features / 8);
     return rvk_launch_check();
@@ -490,10 +487,7 @@ int rvk_kan_layer_bwd_launch(const KanLayerDesc& L, const float* x, const float*
       RVK_SET_MAX_SMEM(kan_bwd_w_tc_kernel, kTcWgSmemBytes);
       KanTcTables tb;
       tb.xthr = workspace + 4 * wp;          // written by the forward launch
-      for (int j = 0; j < 8; ++j) {
-        tb.knot[j] = L.knots_host[j];
-        tb.inv_h[j] = 1.0f / (L.knots_host[j + 1] - L.knots_host[j]);
-      }
+      kan_tc_fill_tables(tb, L.knots_host);
       const int groups = L.in_features / 64;
       const int tiles128 = (batch + 127) / 128;
       int slices = kNumSMsB200 / groups;
@@ -522,10 +516,7 @@ int rvk_kan_layer_bwd_launch(const KanLayerDesc& L, const float* x, const float*
     RVK_TRY(rvk_make_tmap_2d(&tmWlo, w2_lo, RVK_BF16, kp, 64, 64, 64, 64));
     KanTcTables tb;
     tb.xthr = workspace + 4 * wp;            // = the 16 floats after the forward's split weights
-    for (int j = 0; j < 8; ++j) {
-      tb.knot[j] = L.knots_host[j];
-      tb.inv_h[j] = 1.0f / (L.knots_host[j + 1] - L.knots_host[j]);
-    }
+    kan_tc_fill_tables(tb, L.knots_host);
     const int tiles = (batch + 127) / 128;
     const int grid = tiles < kNumSMsB200 ? tiles : kNumSMsB200;
     kan_bwd_x_tc_kernel<<<grid, kTcThreads, kTcBxSmemBytes, stream>>>(tmWhi, tmWlo, x, y, gy, tb, dx, act, batch, L.in_features,

@@ -32,7 +32,17 @@ struct KanTcTables {
   const float* xthr; // device [9]: xthr[m] = smallest float x with tanhf(x) >= knot_m (m = 1..7); xthr[0] = -inf, xthr[8] = +inf
   float knot[8];     // knot_0 .. knot_7
   float inv_h[8];    // 1 / (knot_{j+1} - knot_j), j = 0..6 (inv_h[7] unused)
+  int uniform;       // the knot vector is the reference's linspace(-1, 1, 11) (to 1e-6): u = 5 (t + 1) - j, no table loads
 };
+inline void kan_tc_fill_tables(KanTcTables& tb, const float* knots_host) {
+  tb.uniform = 1;
+  for (int j = 0; j < 8; ++j) {
+    tb.knot[j] = knots_host[j];
+    tb.inv_h[j] = 1.0f / (knots_host[j + 1] - knots_host[j]);
+  }
+  for (int j = 0; j < 11; ++j)
+    if (fabsf(knots_host[j] - (-1.0f + 0.2f * static_cast<float>(j))) > 1e-6f) tb.uniform = 0;
+}
 
 // The thresholds are calibrated against the SAME tanhf the CUDA-core kernels (and the parity tests) use, so that
 // both paths take identical interval decisions even for inputs sitting exactly on a knot: scan +-32 ulps around
@@ -69,41 +79,68 @@ __global__ void kan_split_weights_kernel(const float* __restrict__ spline, const
 
 // The 8 packed activations [N_0(tanh x) .. N_6(tanh x), x] of one (sample, input), split hi + lo in bf16, written as one
 // 16-byte K chunk each at byte offset `off` of the hi / lo operand tiles.
+//
+// Round-2 version (ncu on the round-1 one: 125 instructions per (sample, input), 8.7 M shared-memory bank conflicts per launch
+// from eight predicated 2-byte stores per pair, 10 % of all warp samples waiting for the threshold / knot table loads):
+//   * interval from s = 5 (tanh x + 1) directly; the calibrated x-space thresholds (exact decisions, incl. the reference's
+//     jump at tanh x = 0.4) are only consulted when s is within 1e-4 of an integer (fast-tanh error: 2e-6 in s);
+//   * the local coordinate is u = s - j when the knot vector is the reference's uniform linspace(-1, 1, 11) (checked on the
+//     host, `tb.uniform`), the knot tables otherwise;
+//   * the four live cubics in Horner form, converted to bf16 hi / lo two at a time (cvt.rn.bf16x2.f32);
+//   * one-hot placement = a 128-bit shift of the packed 4 x bf16 group by 16 (j - 3) bits, one 16-byte store per tile.
 __device__ __forceinline__ void kan_tc_expand_store(float xe, uint32_t off, uint8_t* ahi, uint8_t* alo, const float* sXthr,
-                                                    const float* sKnot, const float* sInvH) {
-  // tanh (branch-free, MUFU): values only; the interval comes from x-space thresholds
+                                                    const float* sKnot, const float* sInvH, bool uniform = true) {
+  // tanh (branch-free, MUFU): values only; the interval comes from x-space thresholds where it matters
   const float ex = ex2_approx(fabsf(xe) * 2.8853900817779268f);
   float rc;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(ex + 1.0f));
   const float tt = copysignf(fmaf(-2.0f, rc, 1.0f), xe);
-  int j = static_cast<int>((tt + 1.0f) * 5.0f);
-  j = min(max(j, 0), 7);
-  if (xe < sXthr[j]) --j;
-  else if (xe >= sXthr[j + 1]) ++j;           // j = #{m >= 1 : x >= xthr[m]}, capped at 8 (>= 7: dead zone)
-  // slot 7 = raw x (hi / lo); slots 0..6 zero unless overwritten below
+  const float s = fmaf(tt, 5.0f, 5.0f);                    // in [0, 10]
+  const int jf = __float2int_rd(s);
+  int j = min(jf, 7);
+  const float frac = s - static_cast<float>(jf);
+  if ((frac < 1e-4f || frac > 1.0f - 1e-4f) && jf <= 7) { // rare (2e-4 of the inputs below the dead zone): exact decision
+    j = min(max(j, 0), 7);
+    if (xe < sXthr[j]) --j;
+    else if (xe >= sXthr[j + 1]) ++j;                       // j = #{m >= 1 : x >= xthr[m]}, capped at 8 (>= 7: dead zone)
+  }
+  const int jc = min(max(j, 0), 6);
+  const float u = uniform ? s - static_cast<float>(jc) : (tt - sKnot[jc]) * sInvH[jc];
+  const float u2 = u * u, om = 1.0f - u;
+  const float v0 = u2 * u * (1.0f / 6.0f);                                            // slot j
+  const float v1 = fmaf(fmaf(fmaf(-0.5f, u, 0.5f), u, 0.5f), u, 1.0f / 6.0f);         // slot j-1
+  const float v2 = fmaf(fmaf(0.5f, u, -1.0f), u2, 2.0f / 3.0f);                       // slot j-2
+  const float v3 = om * om * om * (1.0f / 6.0f);                                      // slot j-3
+  // hi / lo split, two values per conversion: word = [second : first] as bf16 pairs
+  const __nv_bfloat162 h32 = __floats2bfloat162_rn(v3, v2), h10 = __floats2bfloat162_rn(v1, v0);
+  uint32_t w32 = *reinterpret_cast<const uint32_t*>(&h32), w10 = *reinterpret_cast<const uint32_t*>(&h10);
+  const __nv_bfloat162 l32 = __floats2bfloat162_rn(v3 - __uint_as_float(w32 << 16), v2 - __uint_as_float(w32 & 0xffff0000u));
+  const __nv_bfloat162 l10 = __floats2bfloat162_rn(v1 - __uint_as_float(w10 << 16), v0 - __uint_as_float(w10 & 0xffff0000u));
+  uint32_t q32 = *reinterpret_cast<const uint32_t*>(&l32), q10 = *reinterpret_cast<const uint32_t*>(&l10);
+  const bool live = (j >= 0) && (j < 7);                   // dead zone (and x below the first knot: impossible for tanh): zeros
+  if (!live) { w32 = w10 = q32 = q10 = 0u; }
+  // slots j-3 .. j <- (v3, v2, v1, v0): shift the 64-bit group by 16 * (j - 3) bits inside the 128-bit row
+  const int sh = (jc - 3) * 16;                            // -48 .. 48
+  const unsigned long long vh = (static_cast<unsigned long long>(w10) << 32) | w32;
+  const unsigned long long vl = (static_cast<unsigned long long>(q10) << 32) | q32;
+  unsigned long long h_lo, h_hi, l_lo, l_hi;
+  if (sh >= 0) {
+    h_lo = vh << sh; l_lo = vl << sh;
+    h_hi = sh ? (vh >> (64 - sh)) : 0ull;
+    l_hi = sh ? (vl >> (64 - sh)) : 0ull;
+  } else {
+    h_lo = vh >> (-sh); l_lo = vl >> (-sh);
+    h_hi = 0ull; l_hi = 0ull;
+  }
+  // slot 7 = raw x (hi / lo)
   const __nv_bfloat16 xh = __float2bfloat16(xe);
   const __nv_bfloat16 xl = __float2bfloat16(xe - __bfloat162float(xh));
-  *reinterpret_cast<uint4*>(ahi + off) = make_uint4(0u, 0u, 0u, static_cast<uint32_t>(__bfloat16_as_ushort(xh)) << 16);
-  *reinterpret_cast<uint4*>(alo + off) = make_uint4(0u, 0u, 0u, static_cast<uint32_t>(__bfloat16_as_ushort(xl)) << 16);
-  if (j < 7) {
-    const float u = (tt - sKnot[j]) * sInvH[j];
-    const float u2 = u * u, u3 = u2 * u, om = 1.0f - u;
-    float v[4];
-    v[0] = u3 * (1.0f / 6.0f);                                            // slot j
-    v[1] = (1.0f + 3.0f * u + 3.0f * u2 - 3.0f * u3) * (1.0f / 6.0f);     // slot j-1
-    v[2] = (4.0f - 6.0f * u2 + 3.0f * u3) * (1.0f / 6.0f);                // slot j-2
-    v[3] = om * om * om * (1.0f / 6.0f);                                  // slot j-3
-#pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      const int slot = j - m;
-      if (slot >= 0) {
-        const __nv_bfloat16 h = __float2bfloat16(v[m]);
-        const __nv_bfloat16 l = __float2bfloat16(v[m] - __bfloat162float(h));
-        *reinterpret_cast<__nv_bfloat16*>(ahi + off + slot * 2) = h;
-        *reinterpret_cast<__nv_bfloat16*>(alo + off + slot * 2) = l;
-      }
-    }
-  }
+  h_hi |= static_cast<unsigned long long>(__bfloat16_as_ushort(xh)) << 48;
+  l_hi |= static_cast<unsigned long long>(__bfloat16_as_ushort(xl)) << 48;
+  *reinterpret_cast<uint4*>(ahi + off) = make_uint4(static_cast<uint32_t>(h_lo), static_cast<uint32_t>(h_lo >> 32),
+                                                     static_cast<uint32_t>(h_hi), static_cast<uint32_t>(h_hi >> 32));
+  *reinterpret_cast<uint4*>(alo + off) = make_uint4(static_cast<uint32_t>(l_lo), static_cast<uint32_t>(l_lo >> 32),
+                                                     static_cast<uint32_t>(l_hi), static_cast<uint32_t>(l_hi >> 32));
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -235,22 +272,32 @@ kan_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_consta
           for (long long o = static_cast<long long>(pt) * 128; o < bytes; o += 512 * 128) prefetch_l2(base + o);
         }
       }
-      float2 xnext = load_x(0);
-#pragma unroll 1
-      for (int c = 0; c < num_chunks; ++c) {
-        const float2 xv = xnext;
-        xnext = load_x(c + 1);                       // next chunk's inputs are in flight while this one is expanded
-        mbar_wait(&a_empty[sa], pha ^ 1);
-        uint8_t* ahi = sA + sa * kTcAStageBytes;
-        uint8_t* alo = ahi + 16384;
+      // the inputs of the next FOUR chunks are in flight while one is expanded (round 1 kept one chunk ahead: 15 % of all
+      // warp samples sat on the first use of x, ncu source view)
+      float2 xq[4];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          kan_tc_expand_store(e == 0 ? xv.x : xv.y, sw128_offset(srow, 2 * ip + e), ahi, alo, sXthr, sKnot, sInvH);
+      for (int k = 0; k < 4; ++k) xq[k] = load_x(k);
+#pragma unroll 1
+      for (int c0 = 0; c0 < num_chunks; c0 += 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int c = c0 + k;
+          if (c < num_chunks) {                        // warp-uniform
+            const float2 xv = xq[k];
+            xq[k] = load_x(c + 4);
+            mbar_wait(&a_empty[sa], pha ^ 1);
+            uint8_t* ahi = sA + sa * kTcAStageBytes;
+            uint8_t* alo = ahi + 16384;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              kan_tc_expand_store(e == 0 ? xv.x : xv.y, sw128_offset(srow, 2 * ip + e), ahi, alo, sXthr, sKnot, sInvH, tb.uniform != 0);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&a_full[sa]);
+            if (++sa == kTcAStages) { sa = 0; pha ^= 1; }
+          }
         }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&a_full[sa]);
-        if (++sa == kTcAStages) { sa = 0; pha ^= 1; }
       }
       // ---- epilogue of this tile
       mbar_wait(&d_full[acc], acc_ph);
@@ -524,14 +571,20 @@ kan_bwd_x_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_cons
           asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(ex + 1.0f));
           const float tt = copysignf(fmaf(-2.0f, rc, 1.0f), xe);
           const float dt = 4.0f * rc * (1.0f - rc);                 // 1 - tanh^2, without cancellation
-          int j = static_cast<int>((tt + 1.0f) * 5.0f);
-          j = min(max(j, 0), 7);
-          if (xe < sXthr[j]) --j;
-          else if (xe >= sXthr[j + 1]) ++j;
+          const float s5 = fmaf(tt, 5.0f, 5.0f);
+          const int jf = __float2int_rd(s5);
+          int j = min(jf, 7);
+          const float frac = s5 - static_cast<float>(jf);
+          if ((frac < 1e-4f || frac > 1.0f - 1e-4f) && jf <= 7) {       // near a knot: the calibrated x-space thresholds decide
+            j = min(max(j, 0), 7);
+            if (xe < sXthr[j]) --j;
+            else if (xe >= sXthr[j + 1]) ++j;
+          }
           float sp = 0.0f;
-          if (j < 7) {
-            const float ih = sInvH[j];
-            const float u = (tt - sKnot[j]) * ih;
+          if (j >= 0 && j < 7) {
+            const bool uni = tb.uniform != 0;
+            const float ih = uni ? 5.0f : sInvH[j];
+            const float u = uni ? s5 - static_cast<float>(j) : (tt - sKnot[j]) * ih;
             const float u2 = u * u, om = 1.0f - u;
             float d[4];
             d[0] = 0.5f * u2 * ih;                                               // slot j
@@ -714,21 +767,21 @@ kan_bwd_w_tc_kernel(const float* __restrict__ x, const float* __restrict__ yv, c
         if (tn < num_tiles && ip == 0 && tn * 128 + srow < batch)
           prefetch_l2(x + static_cast<size_t>(tn * 128 + srow) * n_in + group * 64);
       }
-      float2 xnext = live ? *reinterpret_cast<const float2*>(xr) : make_float2(0.f, 0.f);
-#pragma unroll 1
+      float2 xq[8];                                   // this thread's inputs of all eight chunks of the tile, loaded up front
+#pragma unroll
+      for (int cn = 0; cn < 8; ++cn) xq[cn] = live ? *reinterpret_cast<const float2*>(xr + cn * 8) : make_float2(0.f, 0.f);
+#pragma unroll
       for (int pr = 0; pr < 4; ++pr) {
         mbar_wait(&a_empty[sa], pha ^ 1);
         uint8_t* stage = sA + sa * kTcWgAStageBytes;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const float2 xv = xnext;
-          const int cn = pr * 2 + h + 1;
-          if (live && cn < 8) xnext = *reinterpret_cast<const float2*>(xr + cn * 8);
+          const float2 xv = xq[pr * 2 + h];
           uint8_t* ahi = stage + h * 16384;
           uint8_t* alo = ahi + 32768;
           if (live) {
-            kan_tc_expand_store(xv.x, sw128_offset(srow, 2 * ip), ahi, alo, sXthr, sKnot, sInvH);
-            kan_tc_expand_store(xv.y, sw128_offset(srow, 2 * ip + 1), ahi, alo, sXthr, sKnot, sInvH);
+            kan_tc_expand_store(xv.x, sw128_offset(srow, 2 * ip), ahi, alo, sXthr, sKnot, sInvH, tb.uniform != 0);
+            kan_tc_expand_store(xv.y, sw128_offset(srow, 2 * ip + 1), ahi, alo, sXthr, sKnot, sInvH, tb.uniform != 0);
           } else {                                  // rows past the batch must not contribute (raw-x slot of x = 0 is 0 anyway,
             const uint4 z = make_uint4(0u, 0u, 0u, 0u);   // but the spline slots of tanh(0) are not)
             *reinterpret_cast<uint4*>(ahi + sw128_offset(srow, 2 * ip)) = z;
