@@ -186,9 +186,7 @@ layernorm_bwd_kernel(const void* __restrict__ g, long long gs, const float* __re
                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ gamma,
                      const float* dx_in, float* dx_out, long long dxs, __nv_bfloat16* __restrict__ dx_bf16,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dcolsum, int rows) {
-  __shared__ float s_acc[3][kD];
-  for (int i = threadIdx.x; i < 3 * kD; i += blockDim.x) (&s_acc[0][0])[i] = 0.0f;
-  __syncthreads();
+  __shared__ float s_part[8][3][kD];   // per-warp column sums (blockDim.x == 256)
   griddep_wait();                    // (programmatic dependent launch)
   griddep_launch_dependents();
   const int hl = threadIdx.x & 15;                                   // lane within the half-warp that shares a row
@@ -268,18 +266,32 @@ layernorm_bwd_kernel(const void* __restrict__ g, long long gs, const float* __re
       }
     }
   }
+  // column sums over the rows of this block: the two half-warps of a warp by one shuffle, the 8 warps through shared memory
+  // (round 1 used shared-memory atomicAdd here: a compare-and-swap loop on sm_100, 16 row slots contending for every column)
+  const int wid = threadIdx.x >> 5;
 #pragma unroll
-  for (int j = 0; j < 3; ++j)
+  for (int i = 0; i < 12; ++i) {
+    dg[i] += __shfl_xor_sync(0xffffffffu, dg[i], 16);
+    db[i] += __shfl_xor_sync(0xffffffffu, db[i], 16);
+    ds[i] += __shfl_xor_sync(0xffffffffu, ds[i], 16);
+  }
+  if ((threadIdx.x & 16) == 0) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int c = 4 * hl + 64 * j + e, i = 4 * j + e;
-      if (dgamma != nullptr) { atomicAdd(&s_acc[0][c], dg[i]); atomicAdd(&s_acc[1][c], db[i]); }
-      if (dcolsum != nullptr) atomicAdd(&s_acc[2][c], ds[i]);
+    for (int j = 0; j < 3; ++j) {
+      const int c = 4 * hl + 64 * j;
+      *reinterpret_cast<float4*>(&s_part[wid][0][c]) = make_float4(dg[4 * j], dg[4 * j + 1], dg[4 * j + 2], dg[4 * j + 3]);
+      *reinterpret_cast<float4*>(&s_part[wid][1][c]) = make_float4(db[4 * j], db[4 * j + 1], db[4 * j + 2], db[4 * j + 3]);
+      *reinterpret_cast<float4*>(&s_part[wid][2][c]) = make_float4(ds[4 * j], ds[4 * j + 1], ds[4 * j + 2], ds[4 * j + 3]);
     }
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < kD; i += blockDim.x) {
-    if (dgamma != nullptr) { atomicAdd(&dgamma[i], s_acc[0][i]); atomicAdd(&dbeta[i], s_acc[1][i]); }
-    if (dcolsum != nullptr) atomicAdd(&dcolsum[i], s_acc[2][i]);
+  for (int i = threadIdx.x; i < 3 * kD; i += blockDim.x) {
+    const int which = i / kD, c = i % kD;
+    if (which < 2 ? dgamma == nullptr : dcolsum == nullptr) continue;
+    float t = 0.0f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += s_part[w][which][c];
+    atomicAdd(which == 0 ? &dgamma[c] : which == 1 ? &dbeta[c] : &dcolsum[c], t);
   }
 }
 

@@ -43,11 +43,19 @@ struct HeadsTrainBwdArgs {
   float drop_p; int batch;
 };
 
-__device__ __forceinline__ void ht_warp_sum8(float (&p)[kHfS]) {
+// Sum eight per-lane values over the warp in 9 shuffles (recursive halving: each exchange hands the partner the half of the
+// values it keeps); on return every lane holds the warp total of p[(lane >> 2) & 7].
+__device__ __forceinline__ float ht_warp_sum8(const float (&p)[kHfS], int lane) {
+  const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+  float q[4], r[2];
 #pragma unroll
-  for (int s = 0; s < kHfS; ++s)
+  for (int i = 0; i < 4; ++i) q[i] = (b4 ? p[i + 4] : p[i]) + __shfl_xor_sync(0xffffffffu, b4 ? p[i] : p[i + 4], 16);
 #pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) p[s] += __shfl_xor_sync(0xffffffffu, p[s], d);
+  for (int i = 0; i < 2; ++i) r[i] = (b3 ? q[i + 2] : q[i]) + __shfl_xor_sync(0xffffffffu, b3 ? q[i] : q[i + 2], 8);
+  float t = (b2 ? r[1] : r[0]) + __shfl_xor_sync(0xffffffffu, b2 ? r[0] : r[1], 4);
+  t += __shfl_xor_sync(0xffffffffu, t, 2);
+  t += __shfl_xor_sync(0xffffffffu, t, 1);
+  return t;
 }
 
 __global__ void __launch_bounds__(kHtThreads, 1) heads_train_bwd_kernel(const HeadsTrainBwdArgs a, Knots kn) {
@@ -236,14 +244,8 @@ __global__ void __launch_bounds__(kHtThreads, 1) heads_train_bwd_kernel(const He
     float p[kHfS];
 #pragma unroll
     for (int s = 0; s < kHfS; ++s) p[s] = fmaf(w0, sG0[s * kHfO0 + lane], w1 * sG0[s * kHfO0 + lane + 32]);
-    ht_warp_sum8(p);
-    if (lane < kHfS) {
-      float mine = p[0];
-#pragma unroll
-      for (int s = 1; s < kHfS; ++s)
-        if (lane == s) mine = p[s];
-      sT[r * kHfS + lane] = mine;
-    }
+    const float tot = ht_warp_sum8(p, lane);
+    if ((lane & 3) == 0) sT[r * kHfS + (lane >> 2)] = tot;
   }
   __syncthreads();
   for (int idx = tid; idx < kHfS * kHfK0; idx += kHtThreads) {
@@ -321,14 +323,8 @@ __global__ void __launch_bounds__(kHtThreads, 1) heads_train_bwd_kernel(const He
 #pragma unroll
       for (int s = 0; s < kHfS; ++s) p[s] = fmaf(w, sDH[s * kHfHStride + u], p[s]);
     }
-    ht_warp_sum8(p);
-    if (lane < kHfS) {
-      float mine = p[0];
-#pragma unroll
-      for (int s = 1; s < kHfS; ++s)
-        if (lane == s) mine = p[s];
-      sDK[lane * kHfD + k] += mine;                  // (this warp owns column k; sDK was completed before the last barrier)
-    }
+    const float tot = ht_warp_sum8(p, lane);
+    if ((lane & 3) == 0) sDK[(lane >> 2) * kHfD + k] += tot;      // (this warp owns column k; sDK was completed before the last barrier)
   }
   __syncthreads();
   for (int idx = tid; idx < kHfS * kHfD; idx += kHtThreads) {
