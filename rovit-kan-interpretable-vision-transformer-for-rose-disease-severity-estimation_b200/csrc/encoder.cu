@@ -67,6 +67,7 @@ struct ActLayout {
   size_t x_final, mean_f, rstd_f;
   // backward temporaries (training only)
   size_t dx, dxb, g, dz, dctx, dqkv;
+  size_t dxb2, dz2, dqkv2;     // second copies: the weight-gradient GEMMs on the side stream still read the first ones
   size_t total;
 };
 ActLayout act_layout(int64_t rows, int64_t images, bool training) {
@@ -101,6 +102,9 @@ ActLayout act_layout(int64_t rows, int64_t images, bool training) {
     L.dz = take(R * kMlp * 2);
     L.dctx = take(R * kD * 2);
     L.dqkv = take(R * kQkv * 2);
+    L.dxb2 = take(R * kD * 2);
+    L.dz2 = take(R * kMlp * 2);
+    L.dqkv2 = take(R * kQkv * 2);
   } else {
     BlockSaved b{};
     b.x_in = take((R + 127) / 128 * 128 * kD * 4);      // tiled layout (xt_offset): rows padded to 128
@@ -176,6 +180,36 @@ bool fuse_proj() {        // RVK_FUSE_PROJ=0: keep the attention output projecti
   }();
   return on;
 }
+// RVK_TN_SIDE_STREAM=1: the weight-gradient GEMMs (off the critical path: nothing in the backward pass reads a weight
+// gradient) run on a second, lower-priority stream next to the dgrad / LayerNorm / attention kernels of the main stream.
+bool tn_side_stream() {
+  static const bool on = [] { const char* e = getenv("RVK_TN_SIDE_STREAM"); return e != nullptr && e[0] == '1'; }();
+  return on;
+}
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  static constexpr int kEvents = 64;
+  cudaEvent_t ev[kEvents];
+  int next = 0;
+  bool ok = false;
+  cudaEvent_t take() { cudaEvent_t e = ev[next]; next = (next + 1) % kEvents; return e; }
+};
+SideStream* side_stream_for_current_device() {
+  static SideStream per_dev[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  SideStream& S = per_dev[dev];
+  if (!S.ok) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);          // lo = least priority
+    if (cudaStreamCreateWithPriority(&S.stream, cudaStreamNonBlocking, lo) != cudaSuccess) return nullptr;
+    for (int i = 0; i < SideStream::kEvents; ++i)
+      if (cudaEventCreateWithFlags(&S.ev[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    S.ok = true;
+  }
+  return &S;
+}
+
 int mlp_cta_group() {
   static const int g = [] {
     const char* e = getenv("RVK_MLP_CTA_GROUP");
@@ -371,6 +405,35 @@ int rvk_encoder_backward_impl(const void* const* params, const void* wbuf, void*
     uint8_t* dz = b16(A.dz, kMlp);
     uint8_t* dctx = b16(A.dctx, kD);
     uint8_t* dqkv = b16(A.dqkv, kQkv);
+    // ---- optional side stream for the weight-gradient GEMMs.  `dxb` ping-pongs between two buffers at every LayerNorm
+    // backward, dz / dqkv between two buffers per block, so the side stream's reads (launched up to one block earlier)
+    // never race with the main stream's writes; `side_done_*` events order the remaining reuse.
+    SideStream* side = tn_side_stream() ? side_stream_for_current_device() : nullptr;
+    uint8_t* dxb_pp[2] = {dxb, b16(A.dxb2, kD)};
+    uint8_t* dz_pp[2] = {dz, b16(A.dz2, kMlp)};
+    uint8_t* dqkv_pp[2] = {dqkv, b16(A.dqkv2, kQkv)};
+    int dxb_cur = 0;                                  // which dxb buffer holds the current gradient (bf16 copy)
+    cudaEvent_t dxb_reader[2] = {nullptr, nullptr};   // last side-stream reader of each dxb buffer
+    cudaEvent_t dz_reader[2] = {nullptr, nullptr}, dqkv_reader[2] = {nullptr, nullptr};
+    cudaEvent_t last_side = nullptr;
+    // weight gradient C += A^T B on the side stream (after everything enqueued on `s` so far), or inline
+    auto tn = [&](const void* Ab, int64_t lda, const void* Bb, int64_t ldb, float* C, int64_t ldc, int Mr, int Pp, int Qq,
+                  float* colsum, cudaEvent_t* reader_a) -> int {
+      if (side == nullptr) return rvk_gemm_tn_launch(Ab, lda, Bb, ldb, C, ldc, Mr, Pp, Qq, 1.0f, colsum, s);
+      cudaEvent_t ready = side->take();
+      RVK_CUDA_TRY(cudaEventRecord(ready, s));
+      RVK_CUDA_TRY(cudaStreamWaitEvent(side->stream, ready, 0));
+      RVK_TRY(rvk_gemm_tn_launch(Ab, lda, Bb, ldb, C, ldc, Mr, Pp, Qq, 1.0f, colsum, side->stream));
+      cudaEvent_t done = side->take();
+      RVK_CUDA_TRY(cudaEventRecord(done, side->stream));
+      if (reader_a != nullptr) *reader_a = done;
+      last_side = done;
+      return RVK_OK;
+    };
+    auto wait_reader = [&](cudaEvent_t e) -> int {     // main stream must not overwrite a buffer the side stream still reads
+      if (side != nullptr && e != nullptr) RVK_CUDA_TRY(cudaStreamWaitEvent(s, e, 0));
+      return RVK_OK;
+    };
 
     if (chunk < batch && !(stage_begin == 0 && stage_end == kDepth + 2)) return RVK_ERR_UNSUPPORTED_SHAPE;   // ranges: one chunk only
     // final LayerNorm backward: only the class-token rows carry gradient
@@ -388,8 +451,15 @@ int rvk_encoder_backward_impl(const void* const* params, const void* wbuf, void*
       const int stage = 1 + (kDepth - 1 - i);
       if (stage < stage_begin || stage >= stage_end) continue;
       const BlockSaved& B = A.blk[i];
+      if (side != nullptr) {      // (stage ranges: every range starts with dxb in buffer 0, see the end of the block)
+        dz = dz_pp[i & 1];
+        dqkv = dqkv_pp[i & 1];
+        RVK_TRY(wait_reader(dz_reader[i & 1]));
+        RVK_TRY(wait_reader(dqkv_reader[i & 1]));
+      }
+      dxb = dxb_pp[dxb_cur];
       // ---- MLP: x_next = x_mid + fc2(gelu(fc1(ln2)))
-      RVK_TRY(rvk_gemm_tn_launch(dxb, kD, b16(B.h, kMlp), kMlp, G(grads, bp(i, B_FC2W)), kMlp, M, kD, kMlp, 1.0f, nullptr, s));
+      RVK_TRY(tn(dxb, kD, b16(B.h, kMlp), kMlp, G(grads, bp(i, B_FC2W)), kMlp, M, kD, kMlp, nullptr, &dxb_reader[dxb_cur]));
       // (fc2 bias gradient = column sums of dx: accumulated by the LayerNorm backward that wrote dx)
       {   // dz = (dx * W2) o gelu'(z)
         GemmNtArgs a;
@@ -401,30 +471,43 @@ int rvk_encoder_backward_impl(const void* const* params, const void* wbuf, void*
         RVK_TRY(rvk_gemm_nt_launch(a, s));
       }
       // (fc1 bias gradient = column sums of dz: the ones column of the same GEMM)
-      RVK_TRY(rvk_gemm_tn_launch(dz, kMlp, b16(B.ln2, kD), kD, G(grads, bp(i, B_FC1W)), kD, M, kMlp, kD, 1.0f,
-                                 G(grads, bp(i, B_FC1B)), s));
+      RVK_TRY(tn(dz, kMlp, b16(B.ln2, kD), kD, G(grads, bp(i, B_FC1W)), kD, M, kMlp, kD, G(grads, bp(i, B_FC1B)),
+                 &dz_reader[i & 1]));
       RVK_TRY(gemm_plain(dz, kMlp, at(wbuf, W.fc1T[i]), kMlp, g, kD, M, kD, kMlp, nullptr, s));
+      if (side != nullptr) {      // the LayerNorm backward writes the OTHER dxb buffer
+        dxb_cur ^= 1;
+        dxb = dxb_pp[dxb_cur];
+        RVK_TRY(wait_reader(dxb_reader[dxb_cur]));
+      }
       RVK_TRY(rvk_layernorm_bwd_launch(g, 1, kD, f32(B.x_mid, kD), kD, stat(B.mean2), stat(B.rstd2),
                                        P(params, bp(i, B_N2W)), dx, dx, kD, dxb, G(grads, bp(i, B_N2W)),
                                        G(grads, bp(i, B_N2B)), G(grads, bp(i, B_PROJB)), M, s));
       // ---- attention: x_mid = x_in + proj(attn(qkv(ln1)))
-      RVK_TRY(rvk_gemm_tn_launch(dxb, kD, b16(B.ctx, kD), kD, G(grads, bp(i, B_PROJW)), kD, M, kD, kD, 1.0f, nullptr, s));
+      RVK_TRY(tn(dxb, kD, b16(B.ctx, kD), kD, G(grads, bp(i, B_PROJW)), kD, M, kD, kD, nullptr, &dxb_reader[dxb_cur]));
       RVK_TRY(gemm_plain(dxb, kD, at(wbuf, W.projT[i]), kD, dctx, kD, M, kD, kD, nullptr, s));
       RVK_TRY(rvk_attention_bwd_launch(b16(B.qkv, kQkv), b16(B.ctx, kD), dctx,
                                        reinterpret_cast<float*>(at(workspace, B.lse)) + size_t(b0) * 3 * kTok, dqkv, nb, s));
-      RVK_TRY(rvk_gemm_tn_launch(dqkv, kQkv, b16(B.ln1, kD), kD, G(grads, bp(i, B_QKVW)), kD, M, kQkv, kD, 1.0f,
-                                 G(grads, bp(i, B_QKVB)), s));
+      RVK_TRY(tn(dqkv, kQkv, b16(B.ln1, kD), kD, G(grads, bp(i, B_QKVW)), kD, M, kQkv, kD, G(grads, bp(i, B_QKVB)),
+                 &dqkv_reader[i & 1]));
       RVK_TRY(gemm_plain(dqkv, kQkv, at(wbuf, W.qkvT[i]), kQkv, g, kD, M, kD, kQkv, nullptr, s));
+      if (side != nullptr) {
+        dxb_cur ^= 1;                         // back to buffer 0: every block (and stage range) starts and ends there
+        dxb = dxb_pp[dxb_cur];
+        RVK_TRY(wait_reader(dxb_reader[dxb_cur]));
+      }
       RVK_TRY(rvk_layernorm_bwd_launch(g, 1, kD, f32(B.x_in, kD), kD, stat(B.mean1), stat(B.rstd1),
                                        P(params, bp(i, B_N1W)), dx, dx, kD, dxb, G(grads, bp(i, B_N1W)),
                                        G(grads, bp(i, B_N1B)), i > 0 ? G(grads, bp(i - 1, B_FC2B)) : nullptr, M, s));
     }
     // ---- patch embedding, class token, position embedding
     if (stage_end == kDepth + 2) {
+    dxb = dxb_pp[0];
     RVK_TRY(rvk_gemm_tn_launch(dxb, kD, b16(A.patches, kPatchK), kPatchK, G(grads, P_PATCH_W), kPatchK, M, kD, kPatchK,
                                1.0f, nullptr, s));
     RVK_TRY(rvk_token_grad_reduce_launch(dx, nb, G(grads, P_POS), G(grads, P_CLS), G(grads, P_PATCH_B), s));
     }
+    // every weight gradient of this range is complete before the caller (optimizer, all-reduce bucket) continues on `s`
+    if (side != nullptr && last_side != nullptr) RVK_CUDA_TRY(cudaStreamWaitEvent(s, last_side, 0));
   }
   return RVK_OK;
 }
