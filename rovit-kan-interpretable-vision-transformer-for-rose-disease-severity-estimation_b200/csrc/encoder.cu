@@ -180,10 +180,11 @@ bool fuse_proj() {        // RVK_FUSE_PROJ=0: keep the attention output projecti
   }();
   return on;
 }
-// RVK_TN_SIDE_STREAM=1: the weight-gradient GEMMs (off the critical path: nothing in the backward pass reads a weight
-// gradient) run on a second, lower-priority stream next to the dgrad / LayerNorm / attention kernels of the main stream.
+// The weight-gradient GEMMs (off the critical path: nothing in the backward pass reads a weight gradient) run on a second,
+// lower-priority stream next to the dgrad / LayerNorm / attention kernels of the main stream: 40.0 k -> 42.1 k img/s on
+// the batch-256 train step (A/B in one gpurun call).  RVK_TN_SIDE_STREAM=0 keeps everything on the caller's stream.
 bool tn_side_stream() {
-  static const bool on = [] { const char* e = getenv("RVK_TN_SIDE_STREAM"); return e != nullptr && e[0] == '1'; }();
+  static const bool on = [] { const char* e = getenv("RVK_TN_SIDE_STREAM"); return !(e != nullptr && e[0] == '0'); }();
   return on;
 }
 struct SideStream {
