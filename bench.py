@@ -543,11 +543,18 @@ def bench_train(ctx, K, W, batch, with_variants=True):
     tc_ms = sum(e['ms_per_step'] for e in tc)
     tc_fl = sum(e['gflop_per_launch'] * e['launches_per_step'] for e in tc) * 1e9
     traffic, traffic_src = traffic_entry('train', batch)
-    res['roofline'] = {'bound': 'tensor', 'achieved': tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else None,
-                       'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
-                       'frac': tc_fl / (tc_ms * 1e-3) / 1e12 / pk['tflops_sustained'] if tc_ms > 0 else None,
-                       'kernel': 'all tcgen05 kernels of the step (gemm_nt / gemm_tn / attention forward + backward); per kernel: `kernels`',
-                       'ms_per_step': tc_ms, 'traffic': traffic, 'traffic_source': traffic_src,
+    # dominant single kernel of the train step: the weight-gradient GEMM (one symbol, 49 launches per step); the four
+    # gemm_nt epilogue variants together take more time but are four different kernels (see `kernels`)
+    dom = kernels.get('gemm_tn_kernel')
+    res['roofline'] = {'bound': 'tensor', 'achieved': dom['tflops'] if dom else None, 'peak': pk['tflops_sustained'],
+                       'unit': 'TFLOP/s', 'frac': dom['frac_tensor'] if dom else None,
+                       'kernel': 'gemm_tn_kernel<192,4> (weight gradients dW = A^T B over the token rows, both operands MN-major, split over '
+                                 'the rows, red.global.add epilogue; algorithmic FLOPs 2*M*P*Q per launch)',
+                       'us_per_launch': dom['us_per_launch'] if dom else None, 'gflop_per_launch': dom['gflop_per_launch'] if dom else None,
+                       'share_of_step': dom['share_of_step'] if dom else None, 'launches_timed': dom['launches'] if dom else 0,
+                       'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': pk['source'] + ' sustained bf16',
+                       'all_tcgen05_kernels': {'tflops': tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else None, 'ms_per_step': tc_ms,
+                                               'frac': tc_fl / (tc_ms * 1e-3) / 1e12 / pk['tflops_sustained'] if tc_ms > 0 else None},
                        'whole_step_tflops': value / ctx.world * TRAIN_FLOP_PER_IMG / 1e12,
                        'whole_step_frac': value / ctx.world * TRAIN_FLOP_PER_IMG / 1e12 / pk['tflops_sustained']}
     if with_variants:

@@ -27,6 +27,13 @@ const char* rvk_strerror(int status);
 const char* rvk_last_error(void);            /* detail of the last failure on the calling thread */
 int rvk_device_check(void);                  /* 0 iff the current device is compute capability 10.x */
 
+/* Every entry point only enqueues work; a fault inside a kernel (every mbarrier wait of this library is bounded: a protocol
+ * error ends in a device-side trap after ~4 s, never in a hung GPU) is asynchronous.  rvk_stream_check synchronises the
+ * stream and returns RVK_ERR_CUDA (detail in rvk_last_error) if anything enqueued on it faulted.
+ * rvk_debug_mbar_timeout launches a kernel that provokes exactly that trap (tests). */
+int rvk_stream_check(void* stream);
+int rvk_debug_mbar_timeout(void* stream);
+
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------------
  * rvk_launch_count: kernels this library has launched in this process so far.
  * rvk_gemm_timing_enable(1): bracket every tensor-core GEMM launch with CUDA events on its own stream;

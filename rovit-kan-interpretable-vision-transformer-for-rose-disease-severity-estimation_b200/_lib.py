@@ -21,6 +21,8 @@ SIGNATURES = {
     'rvk_last_error': (C.c_char_p, []),
     'rvk_device_check': (_I, []),
     'rvk_launch_count': (_L, []),
+    'rvk_stream_check': (_I, [_P]),
+    'rvk_debug_mbar_timeout': (_I, [_P]),
     'rvk_gemm_timing_enable': (None, [_I]),
     'rvk_gemm_timing_collect': (_I, [_P, _P]),
     'rvk_gemm_timing_kind': (_I, [_I, _P, _P]),

@@ -60,6 +60,16 @@ int rvk_device_check(void) {
 }
 
 int64_t rvk_launch_count(void) { return rvk_launch_count_impl(); }
+int rvk_stream_check(void* stream) {
+  cudaError_t e = cudaStreamSynchronize(S(stream));
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    rvk_set_last_cuda_error(static_cast<int>(e), "asynchronous kernel fault");
+    return RVK_ERR_CUDA;
+  }
+  return RVK_OK;
+}
+int rvk_debug_mbar_timeout(void* stream) { return rvk_debug_mbar_timeout_launch(S(stream)); }
 void rvk_timing_enable(int on) { rvk_timing_enable_impl(on); }
 int rvk_timing_collect(void) { return rvk_timing_collect_impl(); }
 int rvk_timing_kind(int kind, double* ms_host, double* flops_host, double* bytes_host) {

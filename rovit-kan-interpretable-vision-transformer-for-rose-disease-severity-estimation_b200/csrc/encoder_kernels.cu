@@ -384,6 +384,24 @@ int rvk_token_table_launch(const float* cls_token, const float* pos_embed, const
   return rvk_launch_check();
 }
 
+// Debugging / test aid: a kernel that waits on an mbarrier nobody arrives on, i.e. the protocol error every bounded wait of
+// this library guards against (common.cuh::mbar_wait: ~4 s, device printf, trap).
+namespace {
+__global__ void debug_mbar_timeout_kernel() {
+  __shared__ uint64_t bar;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) mbar_wait(&bar, 0);
+}
+}  // namespace
+int rvk_debug_mbar_timeout_launch(cudaStream_t stream) {
+  debug_mbar_timeout_kernel<<<1, 32, 0, stream>>>();
+  return rvk_launch_check();
+}
+
 int rvk_cast_multi_launch(RvkCastTable& T, cudaStream_t stream) {
   if (T.n <= 0) return RVK_OK;
   int tiles = 0;

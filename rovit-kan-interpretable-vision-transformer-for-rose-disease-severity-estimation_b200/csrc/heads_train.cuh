@@ -238,14 +238,30 @@ __global__ void __launch_bounds__(kHtThreads, 1) heads_train_bwd_kernel(const He
   }
   __syncthreads();          // sA0 is free: T may overwrite it
   // T[r][s] = sum_o g0[s][o] * Wp0[r][o]: one warp per packed row, lanes over the 64 outputs
-  for (int r = warp; r < kHfK0 * 8; r += kHtThreads / 32) {
-    const float w0 = __ldg(a.ws + kHfOffWp0 + static_cast<size_t>(r) * kHfO0 + lane);
-    const float w1 = __ldg(a.ws + kHfOffWp0 + static_cast<size_t>(r) * kHfO0 + lane + 32);
-    float p[kHfS];
+  {
+    float g0a[kHfS], g0b[kHfS];                       // this lane's two output columns of g0, for the 8 samples
 #pragma unroll
-    for (int s = 0; s < kHfS; ++s) p[s] = fmaf(w0, sG0[s * kHfO0 + lane], w1 * sG0[s * kHfO0 + lane + 32]);
-    const float tot = ht_warp_sum8(p, lane);
-    if ((lane & 3) == 0) sT[r * kHfS + (lane >> 2)] = tot;
+    for (int s = 0; s < kHfS; ++s) { g0a[s] = sG0[s * kHfO0 + lane]; g0b[s] = sG0[s * kHfO0 + lane + 32]; }
+    constexpr int kWarps = kHtThreads / 32, kRows = kHfK0 * 8 / kWarps;      // 96 rows per warp
+    static_assert(kRows % 4 == 0, "row batches of 4");
+    for (int rb = 0; rb < kRows; rb += 4) {           // four rows per batch: eight L2 loads in flight per lane
+      float w0[4], w1[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = warp + (rb + q) * kWarps;
+        w0[q] = __ldg(a.ws + kHfOffWp0 + static_cast<size_t>(r) * kHfO0 + lane);
+        w1[q] = __ldg(a.ws + kHfOffWp0 + static_cast<size_t>(r) * kHfO0 + lane + 32);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int r = warp + (rb + q) * kWarps;
+        float p[kHfS];
+#pragma unroll
+        for (int s = 0; s < kHfS; ++s) p[s] = fmaf(w0[q], g0a[s], w1[q] * g0b[s]);
+        const float tot = ht_warp_sum8(p, lane);
+        if ((lane & 3) == 0) sT[r * kHfS + (lane >> 2)] = tot;
+      }
+    }
   }
   __syncthreads();
   for (int idx = tid; idx < kHfS * kHfK0; idx += kHtThreads) {
@@ -316,12 +332,14 @@ __global__ void __launch_bounds__(kHtThreads, 1) heads_train_bwd_kernel(const He
     float p[kHfS];
 #pragma unroll
     for (int s = 0; s < kHfS; ++s) p[s] = 0.0f;
-#pragma unroll 4
+    float w[kHfU / 32];                               // the whole row slice of this lane first: 12 L2 loads in flight
+#pragma unroll
+    for (int m = 0; m < kHfU / 32; ++m) w[m] = __ldg(a.ws + kHfOffW1T + static_cast<size_t>(k) * kHfU + lane + 32 * m);
+#pragma unroll
     for (int m = 0; m < kHfU / 32; ++m) {
       const int u = lane + 32 * m;
-      const float w = __ldg(a.ws + kHfOffW1T + static_cast<size_t>(k) * kHfU + u);
 #pragma unroll
-      for (int s = 0; s < kHfS; ++s) p[s] = fmaf(w, sDH[s * kHfHStride + u], p[s]);
+      for (int s = 0; s < kHfS; ++s) p[s] = fmaf(w[m], sDH[s * kHfHStride + u], p[s]);
     }
     const float tot = ht_warp_sum8(p, lane);
     if ((lane & 3) == 0) sDK[(lane >> 2) * kHfD + k] += tot;      // (this warp owns column k; sDK was completed before the last barrier)

@@ -75,6 +75,7 @@ struct RvkCastJob { const float* src; void* dst; int rows, cols, mode, tile_star
 constexpr int kRvkMaxCastJobs = 64;
 struct RvkCastTable { RvkCastJob job[kRvkMaxCastJobs]; int n; };
 int rvk_cast_multi_launch(RvkCastTable& T, cudaStream_t stream);
+int rvk_debug_mbar_timeout_launch(cudaStream_t stream);
 // fmt: 0 fp32, 1 bf16, 2 uint8 (+ norm6_host = {scale[3], shift[3]}: pixel * scale[c] + shift[c])
 int rvk_im2col_launch(const void* images, int fmt, void* patches_bf16, int batch, const float* norm6_host, cudaStream_t stream);
 int rvk_token_table_launch(const float* cls_token, const float* pos_embed, const float* patch_bias, float* table,

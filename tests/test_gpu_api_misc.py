@@ -171,3 +171,30 @@ def test_hook_mode_attention_maps_and_probabilities():
         qkv = blk.attn.qkv(ref_norm1[3]).reshape(3, 197, 3, 3, 64).permute(2, 0, 3, 1, 4)
         want = torch.softmax(qkv[0] @ qkv[1].transpose(-2, -1) * 0.125, dim=-1)
     assert_close(probs[3], want, rtol=5e-2, atol=2e-4, what='attention probabilities of block 3')
+
+
+def test_kernel_protocol_error_surfaces_as_rovitkan_error():
+    """every mbarrier wait of the library is bounded; a protocol error must end in a device-side trap that
+    the host sees as RovitKanError (RVK_ERR_CUDA), not in a hung GPU.  Runs in its own process: the trap poisons the context."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, torch\n"
+        f"sys.path.insert(0, {root!r})\n"
+        "from rovitkan_b200 import _lib\n"
+        "torch.cuda.init(); s = torch.cuda.current_stream().cuda_stream\n"
+        "_lib.call('rvk_stream_check', s)\n"
+        "_lib.call('rvk_debug_mbar_timeout', s)\n"
+        "try:\n"
+        "    _lib.call('rvk_stream_check', s)\n"
+        "    print('NO ERROR')\n"
+        "except _lib.RovitKanError as e:\n"
+        "    print('SURFACED', e)\n")
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=120)
+    assert 'SURFACED' in r.stdout and 'CUDA runtime error' in r.stdout, r.stdout + r.stderr
+    assert 'mbarrier wait timed out' in r.stdout + r.stderr
+    # the device is fine for the next process
+    x = torch.ones(4, device=DEV)
+    assert float(x.sum()) == 4.0
