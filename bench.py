@@ -281,12 +281,14 @@ class Ctx:
         on its own stream (this serialises programmatic dependent launches, so the sum can exceed the step time)."""
         lib, pk = self.lib, self.pk
         lib.rvk_timing_enable(1)
+        lib.rvk_set_side_stream(0)          # every kernel timed on its own: no concurrent weight-gradient GEMMs next to it
         self.torch.cuda.synchronize()
         for _ in range(n):
             fn()
         self.torch.cuda.synchronize()
         lib.rvk_timing_collect()
         lib.rvk_timing_enable(0)
+        lib.rvk_set_side_stream(-1)
         table, kind = {}, 0
         while True:
             name = lib.rvk_timing_kind_name(kind)

@@ -32,6 +32,10 @@ int rvk_device_check(void);                  /* 0 iff the current device is comp
  * stream and returns RVK_ERR_CUDA (detail in rvk_last_error) if anything enqueued on it faulted.
  * rvk_debug_mbar_timeout launches a kernel that provokes exactly that trap (tests). */
 int rvk_stream_check(void* stream);
+/* The trunk backward runs its weight-gradient GEMMs on a second, lower-priority stream (joined before it returns);
+ * 0 keeps everything on the caller's stream (per-kernel timing, debugging), 1 forces the side stream, -1 = default
+ * (on unless RVK_TN_SIDE_STREAM=0). */
+void rvk_set_side_stream(int on);
 int rvk_debug_mbar_timeout(void* stream);
 
 /* ---- measurement hooks (bench.py) -------------------------------------------------------------------

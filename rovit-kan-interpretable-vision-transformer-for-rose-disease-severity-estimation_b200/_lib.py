@@ -22,6 +22,7 @@ SIGNATURES = {
     'rvk_device_check': (_I, []),
     'rvk_launch_count': (_L, []),
     'rvk_stream_check': (_I, [_P]),
+    'rvk_set_side_stream': (None, [_I]),
     'rvk_debug_mbar_timeout': (_I, [_P]),
     'rvk_gemm_timing_enable': (None, [_I]),
     'rvk_gemm_timing_collect': (_I, [_P, _P]),

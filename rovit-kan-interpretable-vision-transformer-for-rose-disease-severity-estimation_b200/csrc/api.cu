@@ -69,6 +69,7 @@ int rvk_stream_check(void* stream) {
   }
   return RVK_OK;
 }
+void rvk_set_side_stream(int on) { rvk_set_side_stream_impl(on); }
 int rvk_debug_mbar_timeout(void* stream) { return rvk_debug_mbar_timeout_launch(S(stream)); }
 void rvk_timing_enable(int on) { rvk_timing_enable_impl(on); }
 int rvk_timing_collect(void) { return rvk_timing_collect_impl(); }

@@ -183,9 +183,10 @@ bool fuse_proj() {        // RVK_FUSE_PROJ=0: keep the attention output projecti
 // The weight-gradient GEMMs (off the critical path: nothing in the backward pass reads a weight gradient) run on a second,
 // lower-priority stream next to the dgrad / LayerNorm / attention kernels of the main stream: 40.0 k -> 42.1 k img/s on
 // the batch-256 train step (A/B in one gpurun call).  RVK_TN_SIDE_STREAM=0 keeps everything on the caller's stream.
+int g_side_stream_override = -1;      // rvk_set_side_stream: -1 = environment default, 0 / 1 = forced
 bool tn_side_stream() {
   static const bool on = [] { const char* e = getenv("RVK_TN_SIDE_STREAM"); return !(e != nullptr && e[0] == '0'); }();
-  return on;
+  return g_side_stream_override < 0 ? on : g_side_stream_override != 0;
 }
 struct SideStream {
   cudaStream_t stream = nullptr;
@@ -220,6 +221,8 @@ int mlp_cta_group() {
 }
 
 }  // namespace
+
+void rvk_set_side_stream_impl(int on) { g_side_stream_override = on; }
 
 int64_t rvk_encoder_weight_bytes_impl(int training) { return static_cast<int64_t>(weight_layout(training != 0).total); }
 

@@ -163,3 +163,72 @@ def test_train_step_with_the_fused_tail_refreshes_the_trunk_weights():
 
 def rel(a, b):
     return float((a - b).norm() / b.norm())
+
+
+def _tiny_config(tmp_path, epochs=2, freeze=1, cutmix=True):
+    from types import SimpleNamespace as NS
+    cfg = NS()
+    cfg.flags = NS(mixed_precision=True, use_cutmix=cutmix, use_mixup=cutmix, cutmix_alpha=1.0, mixup_alpha=0.2,
+                   freeze_backbone_epochs=freeze, gradient_clip=1.0, curriculum=True)
+    cfg.train = NS(epochs=epochs, early_stop_patience=10)
+    cfg.paths = NS(checkpoints_dir=tmp_path)
+    cfg.get_stage_for_epoch = lambda epoch: min(4, 2 + epoch)          # stage 3, then 4
+    return cfg
+
+
+def test_fast_trainer_matches_per_step_item_accounting_and_runs_the_schedule(tmp_path, monkeypatch):
+    """FastTrainer (device-side StepStats, fused optimizer tail) against the reference trainer's accounting
+    (trainer.py:142-153: .item() every step), then a 2-epoch fit with freeze -> unfreeze, stage switch, CutMix, checkpoint."""
+    monkeypatch.setenv('ROVITKAN_SYNTH_PER_CLASS', '6')
+    monkeypatch.setenv('ROVITKAN_DATA_WORKERS', '0')
+    from rovitkan_b200.data.dataset import DEFAULT_CLASSES, create_dataloaders
+    from rovitkan_b200.data.transforms import original_transforms
+    from rovitkan_b200.training.fast_trainer import FastTrainer
+    sev = {c: i for i, c in enumerate(DEFAULT_CLASSES)}
+    tr, va, _ = create_dataloaders(tmp_path / 'a', tmp_path / 'o', DEFAULT_CLASSES, sev, original_transforms(), original_transforms(),
+                                   batch_size=8, train_val_split=0.67, num_workers=0, seed=3)
+    torch.manual_seed(0)
+    m = RoViTKAN(pretrained=False, dropout=0.0).to(DEV)
+    groups = [{'params': [p for n, p in m.named_parameters() if 'backbone' in n], 'lr': 0.0},
+              {'params': [p for n, p in m.named_parameters() if 'backbone' not in n], 'lr': 0.0}]
+    opt = FusedAdamW(groups, weight_decay=0.0, max_grad_norm=1.0)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=2, eta_min=0.0)
+    loss_fn = JointLoss(focal_alpha=torch.ones(4, device=DEV))
+    cfg = _tiny_config(tmp_path, cutmix=False)
+    t = FastTrainer(m, va, va, opt, sched, loss_fn, cfg, torch.device(DEV))          # unshuffled loader, lr = 0: deterministic
+    got = t.train_epoch(2)
+    # the reference's accounting on the same (unchanged) weights
+    m.train()
+    m.curriculum_stage = 4
+    tot = {k: 0.0 for k in ('total_loss', 'cls_loss', 'ord_loss', 'unc_loss', 'kan_loss')}
+    correct = n = 0
+    for x, y, s in va:
+        x, y, s = x.to(DEV), y.to(DEV), s.to(DEV)
+        with torch.autocast('cuda'):
+            out = m(x)
+            l = loss_fn(out, y, s, 4)
+        for k in tot:
+            tot[k] += l[k].item()
+        correct += out['cls_logits'].max(1)[1].eq(y).sum().item()
+        n += y.size(0)
+    nb = len(va)
+    want = {'loss': tot['total_loss'] / nb, 'cls_loss': tot['cls_loss'] / nb, 'ord_loss': tot['ord_loss'] / nb,
+            'unc_loss': tot['unc_loss'] / nb, 'kan_loss': tot['kan_loss'] / nb, 'accuracy': 100.0 * correct / n}
+    assert set(got) == set(want)
+    for k in want:
+        assert abs(got[k] - want[k]) <= 1e-4 * abs(want[k]) + 1e-5, (k, got[k], want[k])
+    # ---- the whole schedule with a learning optimizer
+    torch.manual_seed(1)
+    m2 = RoViTKAN(pretrained=False).to(DEV)
+    groups = [{'params': [p for n, p in m2.named_parameters() if 'backbone' in n], 'lr': 1e-5},
+              {'params': [p for n, p in m2.named_parameters() if 'backbone' not in n], 'lr': 1e-4}]
+    opt2 = FusedAdamW(groups, weight_decay=1e-4, max_grad_norm=1.0)
+    sched2 = torch.optim.lr_scheduler.CosineAnnealingLR(opt2, T_max=2, eta_min=1e-6)
+    t2 = FastTrainer(m2, tr, va, opt2, sched2, JointLoss(focal_alpha=torch.ones(4, device=DEV)), _tiny_config(tmp_path), torch.device(DEV))
+    hist = t2.fit()
+    assert len(hist['train_loss']) == 2 and all(v == v and abs(v) < 1e4 for v in hist['train_loss'] + hist['val_loss'])
+    assert all(p.requires_grad for p in m2.backbone.parameters())                   # unfrozen at epoch 2
+    ck = t2.load_checkpoint(tmp_path / 'best_model.pth')
+    assert {'epoch', 'model_state_dict', 'optimizer_state_dict', 'scheduler_state_dict', 'best_val_loss', 'metrics', 'config',
+            'scaler_state_dict'} <= set(ck)
+    assert float(opt2.step_count) > 0
