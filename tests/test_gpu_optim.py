@@ -165,15 +165,24 @@ def rel(a, b):
     return float((a - b).norm() / b.norm())
 
 
+class _NS:
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+class _TinyConfig:                                              # picklable (the checkpoint stores the config, trainer.py:318)
+    def __init__(self, tmp_path, epochs=2, freeze=1, cutmix=True):
+        self.flags = _NS(mixed_precision=True, use_cutmix=cutmix, use_mixup=cutmix, cutmix_alpha=1.0, mixup_alpha=0.2,
+                         freeze_backbone_epochs=freeze, gradient_clip=1.0, curriculum=True)
+        self.train = _NS(epochs=epochs, early_stop_patience=10)
+        self.paths = _NS(checkpoints_dir=str(tmp_path))
+
+    def get_stage_for_epoch(self, epoch):
+        return min(4, 2 + epoch)                                # stage 3, then 4
+
+
 def _tiny_config(tmp_path, epochs=2, freeze=1, cutmix=True):
-    from types import SimpleNamespace as NS
-    cfg = NS()
-    cfg.flags = NS(mixed_precision=True, use_cutmix=cutmix, use_mixup=cutmix, cutmix_alpha=1.0, mixup_alpha=0.2,
-                   freeze_backbone_epochs=freeze, gradient_clip=1.0, curriculum=True)
-    cfg.train = NS(epochs=epochs, early_stop_patience=10)
-    cfg.paths = NS(checkpoints_dir=tmp_path)
-    cfg.get_stage_for_epoch = lambda epoch: min(4, 2 + epoch)          # stage 3, then 4
-    return cfg
+    return _TinyConfig(tmp_path, epochs, freeze, cutmix)
 
 
 def test_fast_trainer_matches_per_step_item_accounting_and_runs_the_schedule(tmp_path, monkeypatch):
