@@ -19,3 +19,4 @@ d=json.loads([l for l in open('gpurun_out/bench_train_n${N}_noov.log') if l.star
 print('N=$N train no-overlap', round(d['value']), d['ms_per_step'], d['phases_ms'], d['allreduce'])
 PY
 timeout 600 python -m pytest tests/test_gpu_dist.py -q -m gpu -s > gpurun_out/test_gpu_dist.log 2>&1; echo "dist test exit $?"; tail -3 gpurun_out/test_gpu_dist.log
+timeout 300 python -m pytest tests/test_gpu_optim.py -q -m gpu -k fast_trainer > gpurun_out/test_fast_trainer.log 2>&1; echo "fast trainer test exit $?"; tail -2 gpurun_out/test_fast_trainer.log
