@@ -458,7 +458,12 @@ def bench_train(ctx, K, W, batch, with_variants=True):
     params = [p for p in model.parameters()]
     ev = {}
     from rovitkan_b200 import dist as rdist
-    overlap = ctx.world > 1 and not os.environ.get('RVK_DP_NO_OVERLAP') and rdist.enable_overlap(int(os.environ.get('RVK_DP_BUCKETS', '3')))
+    # default: ONE in-place all-reduce of the trunk's flat gradient + one of the heads' after the backward pass.  Bucketed
+    # all-reduce launched from inside the backward (RVK_DP_OVERLAP=1) hides ~0.04 ms of a 0.12 ms transfer but its NCCL CTAs
+    # run next to the backward kernels: measured 322.6 k vs 326.9 k img/s at 8 GPUs, 74.0 k vs 74.4 k at 2 -- both are
+    # measured below (`allreduce.overlap_ab`) at every N > 1
+    want_overlap = os.environ.get('RVK_DP_OVERLAP') == '1'
+    overlap = ctx.world > 1 and want_overlap and rdist.enable_overlap(int(os.environ.get('RVK_DP_BUCKETS', '3')))
     average = True
     if ctx.world > 1 and fused_tail:
         opt.grad_mult, average = 1.0 / ctx.world, False      # the 1/world scale rides in the optimizer kernel
@@ -531,6 +536,21 @@ def bench_train(ctx, K, W, batch, with_variants=True):
         res['allreduce']['ms_hidden'] = max(0.0, ms_ar - res['allreduce']['ms_exposed'])
         res['allreduce']['algbw_gbs'] = buf.numel() * 4 / (ms_ar * 1e-3) / 1e9
         del buf
+        # A/B: the other all-reduce schedule, same process, same data
+        other = not bool(overlap)
+        if other:
+            rdist.enable_overlap(int(os.environ.get('RVK_DP_BUCKETS', '3')))
+        else:
+            rdist.disable_overlap()
+        for _ in range(3):
+            step(images)
+        ms_o = ctx.timed(lambda: step(images), K)
+        res['allreduce']['overlap_ab'] = {'overlapped_with_backward': other, 'value': batch * ctx.world * K / (ms_o / 1e3),
+                                          'ms_per_step': ms_o / K, 'collectives_per_step': ev.get('collectives', 0)}
+        if overlap:
+            rdist.enable_overlap(int(os.environ.get('RVK_DP_BUCKETS', '3')))
+        else:
+            rdist.disable_overlap()
     if with_variants:
         for _ in range(2):
             step(images, cutmix=True)

@@ -9,8 +9,8 @@ swapped in where a script builds `Trainer(...)`.  What differs is only WHERE the
   * with `FusedAdamW(max_grad_norm=...)` the tail `scaler.unscale_ -> clip_grad_norm_ -> scaler.step` (trainer.py:122-128) is
     one fused pass (unscale + inf check + global-norm clip + AdamW) with no host round trip; any other optimizer is driven
     exactly as the reference drives it;
-  * host->device copies are non-blocking, and under torch.distributed the gradient all-reduce is overlapped with the trunk
-    backward (dist.enable_overlap) -- the reference is single-process.
+  * host->device copies are non-blocking, and under torch.distributed the flat trunk / head gradients are all-reduced in place
+    (two NCCL calls, the 1/world scale folded into the optimizer kernel) -- the reference is single-process.
 """
 
 from __future__ import annotations
@@ -40,10 +40,8 @@ class FastTrainer:
         self.patience_counter = 0
         self.best_epoch = 0
         self.world = torch.distributed.get_world_size() if (torch.distributed.is_available() and torch.distributed.is_initialized()) else 1
-        if self.world > 1:
-            rdist.enable_overlap()
-            if isinstance(optimizer, FusedAdamW):
-                optimizer.grad_mult = 1.0 / self.world
+        if self.world > 1 and isinstance(optimizer, FusedAdamW):
+            optimizer.grad_mult = 1.0 / self.world
 
     # ------------------------------------------------------------------------------------------------ one epoch
     def _fused_tail(self) -> bool:
