@@ -549,11 +549,18 @@ kan_bwd_x_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_cons
           for (long long o = static_cast<long long>(pt) * 128; o < bytes; o += 512 * 128) prefetch_l2(base + o);
         }
       }
-      float2 xnext = live ? *reinterpret_cast<const float2*>(xr) : make_float2(0.f, 0.f);
+      // the inputs of the next four chunks are in flight while one T block is contracted
+      float2 xq[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) xq[k] = (live && k < num_chunks) ? *reinterpret_cast<const float2*>(xr + k * 8) : make_float2(0.f, 0.f);
 #pragma unroll 1
-      for (int c = 0; c < num_chunks; ++c) {
-        const float2 xv = xnext;
-        if (live && c + 1 < num_chunks) xnext = *reinterpret_cast<const float2*>(xr + (c + 1) * 8);
+      for (int c0 = 0; c0 < num_chunks; c0 += 4) {
+#pragma unroll
+      for (int kq = 0; kq < 4; ++kq) {
+        const int c = c0 + kq;
+        if (c >= num_chunks) break;                    // warp-uniform
+        const float2 xv = xq[kq];
+        if (live && c + 4 < num_chunks) xq[kq] = *reinterpret_cast<const float2*>(xr + (c + 4) * 8);
         mbar_wait(&d_full[acc], acc_ph);
         tc_fence_after();
         float T[16];
@@ -602,6 +609,7 @@ kan_bwd_x_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_cons
           out[e] = fmaf(dt, sp, T[e * 8 + 7]);
         }
         if (live) *reinterpret_cast<float2*>(dxr + c * 8) = make_float2(out[0], out[1]);
+      }
       }
     }
   }
