@@ -827,7 +827,8 @@ kan_bwd_w_tc_kernel(const float* __restrict__ x, const float* __restrict__ yv, c
         kan_tmem_ld16(tmem_base + pr * 64 + cg * 16 + lane_sel, v);
         float* dst = dWp + (static_cast<size_t>(group) * 512 + pr * 128 + quad * 32 + lane) * 64 + cg * 16;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) atomicAdd(dst + i, v[i]);
+        for (int i = 0; i < 16; i += 4)      // 16-byte vector reductions (red.global.add.v4.f32): a quarter of the L2 transactions
+          atomicAdd(reinterpret_cast<float4*>(dst + i), make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
       }
     }
     named_bar_sync(1, 16 * 32);
