@@ -236,6 +236,50 @@ class Ctx:
         self.lib = _lib.load()
         self.pk = peaks()
         self._flush = None
+        self.numa = self._gpu_local_cpus()
+
+    def _gpu_local_cpus(self):
+        """CPUs of the NUMA node this rank's GPU hangs off (NVML), so that the pinned staging buffers of the e2e loops are
+        allocated on that node: with 8 ranks on a two-socket host every buffer on one node would funnel half of the
+        host->device traffic through the socket interconnect."""
+        info = {'bound': False}
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            prop = self.torch.cuda.get_device_properties(self.local_rank)
+            try:
+                bus = '%08x:%02x:%02x.0' % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+                h = pynvml.nvmlDeviceGetHandleByPciBusId(bus)
+            except Exception:
+                vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+                ids = [v for v in vis.split(',') if v.strip().isdigit()]
+                h = pynvml.nvmlDeviceGetHandleByIndex(int(ids[self.local_rank]) if ids else self.local_rank)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+            info['gpu_cpus'] = len(cpus)
+            try:
+                info['numa_node'] = int(pynvml.nvmlDeviceGetNumaNodeId(h))
+            except Exception:
+                pass
+            self._local_cpus = cpus & os.sched_getaffinity(0)
+            info['bound'] = bool(self._local_cpus) and len(self._local_cpus) < len(os.sched_getaffinity(0))
+        except Exception as e:                         # NVML absent / container without topology: allocate as before
+            self._local_cpus = set()
+            info['error'] = type(e).__name__
+        return info
+
+    def pinned(self, t):
+        """Pinned host copy of `t`, allocated (cudaHostAlloc places the pages) and filled while this thread runs on the
+        GPU's own NUMA node; the affinity is restored afterwards (the CPU baseline legs use every core)."""
+        old = os.sched_getaffinity(0)
+        try:
+            if self._local_cpus and os.environ.get('RVK_BENCH_NUMA', '1') != '0':
+                os.sched_setaffinity(0, self._local_cpus)
+            out = self.torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            out.copy_(t)
+            return out
+        finally:
+            os.sched_setaffinity(0, old)
 
     def barrier(self):
         if self.world > 1:
@@ -353,7 +397,8 @@ class Ctx:
         ms = self.timed_run(run, K)
         return {'value': batch * self.world * K / (ms / 1e3), 'unit': 'images/sec',
                 'h2d_bytes_per_step': host_batch.numel() * host_batch.element_size(), 'd2h_bytes_per_step': d2h_bytes,
-                'ms_per_step': ms / K, 'input_dtype': str(host_batch.dtype).replace('torch.', '')}
+                'ms_per_step': ms / K, 'input_dtype': str(host_batch.dtype).replace('torch.', ''),
+                'pinned_on_gpu_numa_node': self.numa}
 
 
 def traffic_entry(key, batch):
@@ -374,7 +419,7 @@ def bench_infer(ctx, K, W, batch, with_e2e=True):
     torch.manual_seed(0)
     model = RoViTKAN(pretrained=False).to(ctx.dev).eval()
     g = torch.Generator().manual_seed(1000 + ctx.rank)
-    host_images = torch.randn(batch, 3, 224, 224, generator=g).pin_memory()
+    host_images = ctx.pinned(torch.randn(batch, 3, 224, 224, generator=g))
     images = host_images.to(ctx.dev)
 
     def step(x):
@@ -396,8 +441,8 @@ def bench_infer(ctx, K, W, batch, with_e2e=True):
         res['e2e'] = ctx.e2e(step, host_images, K, batch, batch * 4)
         # serving variants: the host batch already bf16 (bit-identical results: the trunk rounds pixels to bf16 first) or
         # uint8 pixels as an image decoder produces them (ToTensor + Normalize folded into the patch gather)
-        res['e2e_bf16_input'] = ctx.e2e(step, host_images.to(torch.bfloat16).pin_memory(), K, batch, batch * 4)
-        host_u8 = torch.randint(0, 256, (batch, 3, 224, 224), dtype=torch.uint8, generator=g).pin_memory()
+        res['e2e_bf16_input'] = ctx.e2e(step, ctx.pinned(host_images.to(torch.bfloat16)), K, batch, batch * 4)
+        host_u8 = ctx.pinned(torch.randint(0, 256, (batch, 3, 224, 224), dtype=torch.uint8, generator=g))
         res['e2e_uint8_input'] = ctx.e2e(step, host_u8, K, batch, batch * 4)
     kernels = ctx.kernel_table(lambda: step(images), K, step_ms)
     res['kernels'] = kernels
@@ -449,7 +494,7 @@ def bench_train(ctx, K, W, batch, with_variants=True):
     torch.manual_seed(0)
     model = RoViTKAN(pretrained=False).to(ctx.dev).train()
     g = torch.Generator().manual_seed(2000 + ctx.rank)
-    host_images = torch.randn(batch, 3, 224, 224, generator=g).pin_memory()
+    host_images = ctx.pinned(torch.randn(batch, 3, 224, 224, generator=g))
     yd = torch.randint(0, 4, (batch,), generator=g).to(ctx.dev)
     yb = yd.flip(0)
     images = host_images.to(ctx.dev)
@@ -638,20 +683,55 @@ def bench_kan(ctx, K, W, batch):
                 torch.cuda.synchronize()
                 tot += e0.elapsed_time(e1)
             res[tag] = {'ms': ctx.max_over_ranks(tot / K), 'launches': (ctx.lib.rvk_launch_count() - l0) // K}
+        # the same six launches replayed from a CUDA graph: the Python autograd round trip between the launches (about as
+        # long as the kernels themselves at this size) drops out; values are identical (same kernels, same buffers)
+        try:
+            side = torch.cuda.Stream(device=ctx.dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    fwdbwd()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                fwdbwd()
+            for _ in range(W):
+                graph.replay()
+            torch.cuda.synchronize()
+            tot = 0.0
+            for _ in range(K):
+                ctx.flush_l2()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                graph.replay()
+                e1.record()
+                torch.cuda.synchronize()
+                tot += e0.elapsed_time(e1)
+            res['fwd_bwd_graph'] = {'ms': ctx.max_over_ranks(tot / K), 'launches': res['fwd_bwd']['launches']}
+            del graph
+        except Exception as e:                     # capture is an extra; the eager number above stands on its own
+            res['fwd_bwd_graph'] = {'error': repr(e)[:200]}
+            torch.cuda.synchronize()
         out[name] = res
         if name == '192-64-1':
-            kernels = ctx.kernel_table(fwdbwd, K, res['fwd_bwd']['ms'])
+            kernels = ctx.kernel_table(fwdbwd, K, min(res['fwd_bwd']['ms'], res['fwd_bwd_graph'].get('ms', 1e9)))
         del m, x, gy
     pk = ctx.pk
     r = out['192-64-1']
-    ms = r['fwd_bwd']['ms']
+    ms_eager = r['fwd_bwd']['ms']
+    ms_graph = r.get('fwd_bwd_graph', {}).get('ms')
+    graphed = ms_graph is not None and ms_graph < ms_eager
+    ms = ms_graph if graphed else ms_eager
     gbs = KAN_BYTES_PER_SAMPLE * batch / (ms * 1e-3) / 1e9
     traffic, traffic_src = traffic_entry('kan', batch)
     return {'metric': 'samples/sec KANSeverityModule([192,64,1]) forward+backward', 'value': batch * ctx.world / (ms * 1e-3),
-            'unit': 'samples/sec', 'ms_per_step': ms, 'fwd_ms': r['fwd']['ms'], 'steps': K, 'warmup': W, 'batch_per_gpu': batch,
-            'dtype': 'f32', 'gpu_launches': int(r['fwd_bwd']['launches']) * K,
+            'unit': 'samples/sec', 'ms_per_step': ms, 'ms_per_step_eager_launch': ms_eager, 'fwd_ms': r['fwd']['ms'], 'steps': K,
+            'warmup': W, 'batch_per_gpu': batch, 'dtype': 'f32', 'gpu_launches': int(r['fwd_bwd']['launches']) * K,
             'config': {'workload': 'KANLayer microbench: 192->64->1 spline head, grid=5 k=3, batch %d fwd+bwd' % batch,
-                       'l2': 'L2 flushed (256 MB memset) between timed iterations'},
+                       'l2': 'L2 flushed (256 MB memset) between timed iterations',
+                       'launch': ('torch.cuda.graph replay of module(x) + backward (same kernels as the eager call; '
+                                  '`ms_per_step_eager_launch` is the Python-driven call)') if graphed else 'eager module call'},
             'roofline': {'bound': 'hbm', 'achieved': gbs, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': gbs / pk['hbm_gbs'],
                          'traffic': traffic, 'traffic_source': traffic_src,
                          'kernel': 'whole fwd+bwd of the [192,64,1] stack (algorithmic 152 MB / 38.7 GFLOP at batch 65536); per kernel family: `kernels`',
