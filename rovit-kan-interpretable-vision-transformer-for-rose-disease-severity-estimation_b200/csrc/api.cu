@@ -1,6 +1,7 @@
 // extern "C" surface declared in include/rovitkan.h: argument checking + dispatch to the launchers.
 #include "../../include/rovitkan.h"
 
+#include <cmath>
 #include <cstdlib>
 
 #include "encoder.h"
@@ -13,13 +14,31 @@ int rvk_timing_collect_impl();
 int rvk_timing_kind_impl(int kind, double* ms, double* flops, double* bytes);
 const char* rvk_timing_kind_name_impl(int kind);
 
+void rvk_set_last_error_text(const char* what);
+
 namespace {
 inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+// The KAN kernels are written for the reference's knot buffer, linspace(-1, 1, 11) (models/kan.py:47-48: never trained, never
+// changed by the reference): closed uniform-knot cubic segments, no clamp of tanh(x) to the knot range (it covers tanh's
+// image), interval index from 5 (tanh x + 1).  The reference's Cox-de Boor recursion would also accept another knot vector;
+// these kernels would evaluate a different spline for it -- refuse it here.
+int check_knots(const float* k, int n) {
+  if (k == nullptr) return RVK_ERR_BAD_ARG;
+  if (n != 11) return RVK_ERR_UNSUPPORTED_SHAPE;   // reference config: 5 + 2*3 knots, 7 basis functions
+  for (int i = 0; i < 11; ++i) {
+    if (!(fabsf(k[i] - (-1.0f + 0.2f * static_cast<float>(i))) <= 2e-6f)) {
+      rvk_set_last_error_text("KAN knots must be the reference's linspace(-1, 1, 11) (closed-form uniform cubic B-spline kernels)");
+      return RVK_ERR_UNSUPPORTED_SHAPE;
+    }
+  }
+  return RVK_OK;
+}
 
 int fill_kan_desc(KanLayerDesc& L, const float* spline, const float* lin_w, const float* lin_b,
                   const float* knots_host, int num_knots_total, int in_features, int out_features) {
   if (knots_host == nullptr || in_features <= 0 || out_features <= 0) return RVK_ERR_BAD_ARG;
-  if (num_knots_total != 11) return RVK_ERR_UNSUPPORTED_SHAPE;   // reference config: 5 + 2*3 knots, 7 basis functions
+  RVK_TRY(check_knots(knots_host, num_knots_total));
   L.spline = spline; L.lin_w = lin_w; L.lin_b = lin_b;
   for (int i = 0; i < 11; ++i) L.knots_host[i] = knots_host[i];
   L.num_knots = 11; L.num_basis = 7;
@@ -127,7 +146,7 @@ int rvk_kan_layer_backward(const float* x, const float* y, const float* gy, cons
 int rvk_kan_basis(const float* t, const float* knots_host, int num_knots_total, int64_t n, float* out, void* stream) {
   if (n == 0) return RVK_OK;
   if (t == nullptr || knots_host == nullptr || out == nullptr || n < 0) return RVK_ERR_BAD_ARG;
-  if (num_knots_total != 11) return RVK_ERR_UNSUPPORTED_SHAPE;
+  RVK_TRY(check_knots(knots_host, num_knots_total));
   return rvk_kan_basis_launch(t, knots_host, out, n, S(stream));
 }
 
@@ -187,6 +206,7 @@ int rvk_heads_fused_prepare(const void* const* params23_host, float* ws, void* s
 int rvk_heads_fused(const float* features, const float* ws, const float* knots_host, int batch, float* cls_logits,
                     float* ordinal_logits, float* mu, float* log_var, float* kan_severity, void* stream) {
   if (batch < 0) return RVK_ERR_BAD_ARG;
+  RVK_TRY(check_knots(knots_host, 11));
   return rvk_heads_fused_launch(features, ws, knots_host, batch, cls_logits, ordinal_logits, mu, log_var, kan_severity,
                                 S(stream));
 }
@@ -274,6 +294,7 @@ int rvk_heads_train_forward(const float* features, const float* ws, const float*
                             uint64_t seed, uint64_t offset, float* cls_logits, float* ordinal_logits, float* mu, float* log_var,
                             float* kan_severity, float* h_save, float* a1_save, float* a2_save, void* stream) {
   if (batch < 0) return RVK_ERR_BAD_ARG;
+  RVK_TRY(check_knots(knots_host, 11));
   return rvk_heads_train_fwd_launch(features, ws, knots_host, batch, drop_p, seed, offset, cls_logits, ordinal_logits, mu, log_var,
                                     kan_severity, h_save, a1_save, a2_save, S(stream));
 }
@@ -283,6 +304,7 @@ int rvk_heads_train_backward(const float* features, const float* ws, const float
                              const float* d_log_var, const float* d_kan, float* dfeatures, float* dws,
                              float* const* grads23_host, void* stream) {
   if (batch < 0) return RVK_ERR_BAD_ARG;
+  RVK_TRY(check_knots(knots_host, 11));
   return rvk_heads_train_bwd_launch(features, ws, knots_host, batch, drop_p, h_save, a1_save, a2_save, log_var, kan_severity, d_cls,
                                     d_ord, d_mu, d_log_var, d_kan, dfeatures, dws, grads23_host, S(stream));
 }

@@ -430,7 +430,6 @@ int rvk_kan_layer_fwd_launch(const KanLayerDesc& L, const float* x, float* y, in
                                                                     w2_hi + static_cast<size_t>(64) * kp);
       RVK_TRY(rvk_launch_check());
     }
-    RVK_SET_MAX_SMEM(kan_fwd_tc_kernel, kTcSmemBytes);
     CUtensorMap tmWhi, tmWlo;
     RVK_TRY(rvk_make_tmap_2d(&tmWhi, w_hi, RVK_BF16, 64, kp, kp, 64, 64));
     RVK_TRY(rvk_make_tmap_2d(&tmWlo, w_lo, RVK_BF16, 64, kp, kp, 64, 64));
@@ -443,9 +442,9 @@ int rvk_kan_layer_fwd_launch(const KanLayerDesc& L, const float* x, float* y, in
       RVK_TRY(rvk_launch_check());
     }
     tb.xthr = xthr;
-    kan_tc_fill_tables(tb, L.knots_host);
-    kan_fwd_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(tmWhi, tmWlo, x, L.lin_b, tb, y, act, batch, L.in_features,
-                                                                 L.out_features, L.in_features / 8);
+    RVK_SET_MAX_SMEM(kan_fwd_tc_kernel, kTcSmemBytes);
+    kan_fwd_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(tmWhi, tmWlo, x, L.lin_b, tb, y, act, batch,
+                                                                     L.in_features, L.out_features, L.in_features / 8);
     return rvk_launch_check();
   }
   if (batch <= 4096) {
@@ -484,16 +483,15 @@ int rvk_kan_layer_bwd_launch(const KanLayerDesc& L, const float* x, const float*
     splits = (batch + sps - 1) / sps;
     if (kan_use_tc(batch, L.in_features, L.out_features) && L.in_features % 64 == 0) {
       // tensor-core weight gradient (kan_tc.cuh): grid = (batch slices) x (groups of 64 inputs)
-      RVK_SET_MAX_SMEM(kan_bwd_w_tc_kernel, kTcWgSmemBytes);
       KanTcTables tb;
       tb.xthr = workspace + 4 * wp;          // written by the forward launch
-      kan_tc_fill_tables(tb, L.knots_host);
-      const int groups = L.in_features / 64;
+        const int groups = L.in_features / 64;
       const int tiles128 = (batch + 127) / 128;
       int slices = kNumSMsB200 / groups;
       if (slices > tiles128) slices = tiles128;
+      RVK_SET_MAX_SMEM(kan_bwd_w_tc_kernel, kTcWgSmemBytes);
       kan_bwd_w_tc_kernel<<<dim3(slices, groups), kTcThreads, kTcWgSmemBytes, stream>>>(x, y, gy, tb, dWp, dlin_b, act, batch,
-                                                                                        L.in_features, L.out_features);
+                                                                                                L.in_features, L.out_features);
     } else {
       dim3 grid(in_pad / kIC, out_pad / kTO, splits);
       kan_bwd_w_kernel<<<grid, 256, 0, stream>>>(x, y, gy, act, kn, dWp, dlin_b, batch, L.in_features, L.out_features,
@@ -510,17 +508,16 @@ int rvk_kan_layer_bwd_launch(const KanLayerDesc& L, const float* x, const float*
     const int kp = in_pad * 8;
     auto* w2_hi = reinterpret_cast<__nv_bfloat16*>(workspace + 4 * wp + 64);
     auto* w2_lo = w2_hi + static_cast<size_t>(64) * kp;
-    RVK_SET_MAX_SMEM(kan_bwd_x_tc_kernel, kTcBxSmemBytes);
     CUtensorMap tmWhi, tmWlo;
     RVK_TRY(rvk_make_tmap_2d(&tmWhi, w2_hi, RVK_BF16, kp, 64, 64, 64, 64));
     RVK_TRY(rvk_make_tmap_2d(&tmWlo, w2_lo, RVK_BF16, kp, 64, 64, 64, 64));
     KanTcTables tb;
     tb.xthr = workspace + 4 * wp;            // = the 16 floats after the forward's split weights
-    kan_tc_fill_tables(tb, L.knots_host);
     const int tiles = (batch + 127) / 128;
     const int grid = tiles < kNumSMsB200 ? tiles : kNumSMsB200;
-    kan_bwd_x_tc_kernel<<<grid, kTcThreads, kTcBxSmemBytes, stream>>>(tmWhi, tmWlo, x, y, gy, tb, dx, act, batch, L.in_features,
-                                                                     L.out_features, L.in_features / 8);
+    RVK_SET_MAX_SMEM(kan_bwd_x_tc_kernel, kTcBxSmemBytes);
+    kan_bwd_x_tc_kernel<<<grid, kTcThreads, kTcBxSmemBytes, stream>>>(tmWhi, tmWlo, x, y, gy, tb, dx, act, batch,
+                                                                             L.in_features, L.out_features, L.in_features / 8);
     RVK_TRY(rvk_launch_check());
   } else if (dx != nullptr) {
     kan_bwd_x_kernel<<<dim3((batch + kTS - 1) / kTS, (L.in_features + kDxIC - 1) / kDxIC), 256, 0, stream>>>(

@@ -30,19 +30,7 @@ constexpr int kTcSmemBytes = 1024 + kTcAStages * kTcAStageBytes + kTcWStages * k
 // tanh = 1 - 2 / (2^(2 log2(e) |x|) + 1) on MUFU.EX2 / MUFU.RCP (absolute error ~3e-7) is enough for them.
 struct KanTcTables {
   const float* xthr; // device [9]: xthr[m] = smallest float x with tanhf(x) >= knot_m (m = 1..7); xthr[0] = -inf, xthr[8] = +inf
-  float knot[8];     // knot_0 .. knot_7
-  float inv_h[8];    // 1 / (knot_{j+1} - knot_j), j = 0..6 (inv_h[7] unused)
-  int uniform;       // the knot vector is the reference's linspace(-1, 1, 11) (to 1e-6): u = 5 (t + 1) - j, no table loads
 };
-inline void kan_tc_fill_tables(KanTcTables& tb, const float* knots_host) {
-  tb.uniform = 1;
-  for (int j = 0; j < 8; ++j) {
-    tb.knot[j] = knots_host[j];
-    tb.inv_h[j] = 1.0f / (knots_host[j + 1] - knots_host[j]);
-  }
-  for (int j = 0; j < 11; ++j)
-    if (fabsf(knots_host[j] - (-1.0f + 0.2f * static_cast<float>(j))) > 1e-6f) tb.uniform = 0;
-}
 
 // The thresholds are calibrated against the SAME tanhf the CUDA-core kernels (and the parity tests) use, so that
 // both paths take identical interval decisions even for inputs sitting exactly on a knot: scan +-32 ulps around
@@ -84,28 +72,39 @@ __global__ void kan_split_weights_kernel(const float* __restrict__ spline, const
 // from eight predicated 2-byte stores per pair, 10 % of all warp samples waiting for the threshold / knot table loads):
 //   * interval from s = 5 (tanh x + 1) directly; the calibrated x-space thresholds (exact decisions, incl. the reference's
 //     jump at tanh x = 0.4) are only consulted when s is within 1e-4 of an integer (fast-tanh error: 2e-6 in s);
-//   * the local coordinate is u = s - j when the knot vector is the reference's uniform linspace(-1, 1, 11) (checked on the
-//     host, `tb.uniform`), the knot tables otherwise;
+//   * the local coordinate is u = s - j: the knot vector is the reference's linspace(-1, 1, 11) (api.cu::check_knots);
 //   * the four live cubics in Horner form, converted to bf16 hi / lo two at a time (cvt.rn.bf16x2.f32);
 //   * one-hot placement = a 128-bit shift of the packed 4 x bf16 group by 16 (j - 3) bits, one 16-byte store per tile.
-__device__ __forceinline__ void kan_tc_expand_store(float xe, uint32_t off, uint8_t* ahi, uint8_t* alo, const float* sXthr,
-                                                    const float* sKnot, const float* sInvH, bool uniform = true) {
+// Knot interval j of x (j = #{m >= 1 : x >= xthr[m]}: 0..6 live, >= 7 dead zone) and float(j), for the reference's knot
+// vector linspace(-1, 1, 11) (the only one the C ABI accepts, api.cu::check_knots): j = floor(s), s = 5 (tanh x + 1) in
+// [0, 10], taken WITHOUT F2I / I2F (XU-pipe conversions in the middle of the dependent chain): a round-down add of
+// 1.5 * 2^23 leaves floor(s) in the low mantissa bits and, minus the constant, as an exact float.  The calibrated x-space
+// thresholds are consulted only within 1e-4 of a knot (fast-tanh error in s: 2e-6).
+__device__ __forceinline__ void kan_tc_interval(float xe, float s, const float* sXthr, int& j, float& jfl) {
+  const float sm = __fadd_rd(s, 12582912.0f);
+  const int jf = __float_as_int(sm) - 0x4B400000;
+  const float jff = sm - 12582912.0f;
+  j = min(jf, 7);
+  jfl = fminf(jff, 7.0f);
+  const float frac = s - jff;
+  if ((frac < 1e-4f || frac > 1.0f - 1e-4f) && jf <= 7) { // rare (2e-4 of the inputs below the dead zone): exact decision
+    if (xe < sXthr[j]) { --j; jfl -= 1.0f; }
+    else if (xe >= sXthr[j + 1]) { ++j; jfl += 1.0f; }
+  }
+}
+
+__device__ __forceinline__ void kan_tc_expand_store(float xe, uint32_t off, uint8_t* ahi, uint8_t* alo, const float* sXthr) {
   // tanh (branch-free, MUFU): values only; the interval comes from x-space thresholds where it matters
   const float ex = ex2_approx(fabsf(xe) * 2.8853900817779268f);
   float rc;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(ex + 1.0f));
   const float tt = copysignf(fmaf(-2.0f, rc, 1.0f), xe);
   const float s = fmaf(tt, 5.0f, 5.0f);                    // in [0, 10]
-  const int jf = __float2int_rd(s);
-  int j = min(jf, 7);
-  const float frac = s - static_cast<float>(jf);
-  if ((frac < 1e-4f || frac > 1.0f - 1e-4f) && jf <= 7) { // rare (2e-4 of the inputs below the dead zone): exact decision
-    j = min(max(j, 0), 7);
-    if (xe < sXthr[j]) --j;
-    else if (xe >= sXthr[j + 1]) ++j;                       // j = #{m >= 1 : x >= xthr[m]}, capped at 8 (>= 7: dead zone)
-  }
+  int j;
+  float jfl;
+  kan_tc_interval(xe, s, sXthr, j, jfl);
   const int jc = min(max(j, 0), 6);
-  const float u = uniform ? s - static_cast<float>(jc) : (tt - sKnot[jc]) * sInvH[jc];
+  const float u = s - fminf(fmaxf(jfl, 0.0f), 6.0f);
   const float u2 = u * u, om = 1.0f - u;
   const float v0 = u2 * u * (1.0f / 6.0f);                                            // slot j
   const float v1 = fmaf(fmaf(fmaf(-0.5f, u, 0.5f), u, 0.5f), u, 1.0f / 6.0f);         // slot j-1
@@ -133,10 +132,10 @@ __device__ __forceinline__ void kan_tc_expand_store(float xe, uint32_t off, uint
     h_hi = 0ull; l_hi = 0ull;
   }
   // slot 7 = raw x (hi / lo)
-  const __nv_bfloat16 xh = __float2bfloat16(xe);
-  const __nv_bfloat16 xl = __float2bfloat16(xe - __bfloat162float(xh));
-  h_hi |= static_cast<unsigned long long>(__bfloat16_as_ushort(xh)) << 48;
-  l_hi |= static_cast<unsigned long long>(__bfloat16_as_ushort(xl)) << 48;
+  const uint32_t xh = pack_bf16x2(0.0f, xe) & 0xffff0000u;             // packed conversions run on the ALU pipe (F2F: XU)
+  const uint32_t xl = pack_bf16x2(0.0f, xe - __uint_as_float(xh)) & 0xffff0000u;
+  h_hi |= static_cast<unsigned long long>(xh) << 32;
+  l_hi |= static_cast<unsigned long long>(xl) << 32;
   *reinterpret_cast<uint4*>(ahi + off) = make_uint4(static_cast<uint32_t>(h_lo), static_cast<uint32_t>(h_lo >> 32),
                                                      static_cast<uint32_t>(h_hi), static_cast<uint32_t>(h_hi >> 32));
   *reinterpret_cast<uint4*>(alo + off) = make_uint4(static_cast<uint32_t>(l_lo), static_cast<uint32_t>(l_lo >> 32),
@@ -153,9 +152,7 @@ kan_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_consta
   uint8_t* sW = sA + kTcAStages * kTcAStageBytes;
   float* sBias = reinterpret_cast<float*>(sW + kTcWStages * kTcWStageBytes);
   float* sXthr = sBias + 64;     // [12]
-  float* sKnot = sXthr + 12;     // [8]
-  float* sInvH = sKnot + 8;      // [8]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sInvH + 8 + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sXthr + 32);
   uint64_t* a_full = bars;                       // [3]
   uint64_t* a_empty = a_full + kTcAStages;       // [3]
   uint64_t* w_full = a_empty + kTcAStages;       // [4]
@@ -169,7 +166,6 @@ kan_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_consta
 
   if (threadIdx.x < 64) sBias[threadIdx.x] = (threadIdx.x < n_out) ? bias[threadIdx.x] : 0.0f;
   if (threadIdx.x < 9) sXthr[threadIdx.x] = tb.xthr[threadIdx.x];     // written by kan_tc_thresholds_kernel on this stream
-  if (threadIdx.x < 8) { sKnot[threadIdx.x] = tb.knot[threadIdx.x]; sInvH[threadIdx.x] = tb.inv_h[threadIdx.x]; }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmWhi);
     tma_prefetch_desc(&tmWlo);
@@ -272,32 +268,38 @@ kan_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_consta
           for (long long o = static_cast<long long>(pt) * 128; o < bytes; o += 512 * 128) prefetch_l2(base + o);
         }
       }
-      // the inputs of the next FOUR chunks are in flight while one is expanded (round 1 kept one chunk ahead: 15 % of all
-      // warp samples sat on the first use of x, ncu source view)
-      float2 xq[4];
+      // the inputs of the next four-chunk GROUP are in flight while one group is expanded.  Two register sets with fixed
+      // roles (xa: chunks c0..c0+3, xb: c0+4..c0+7): a rotating queue `xq[k] = load(c + 4)` made the compiler funnel every load
+      // through one temporary pair and copy it into place at the end of the SAME chunk, i.e. one chunk of distance and a
+      // long-scoreboard stall per chunk (ncu source view: 13 % of the producers' samples on the first use of x)
+      float2 xa[4], xb[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) xq[k] = load_x(k);
-#pragma unroll 1
-      for (int c0 = 0; c0 < num_chunks; c0 += 4) {
+      for (int k = 0; k < 4; ++k) xa[k] = load_x(k);
+      auto expand_group = [&](const float2 (&xg)[4], int cbase) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const int c = c0 + k;
+          const int c = cbase + k;
           if (c < num_chunks) {                        // warp-uniform
-            const float2 xv = xq[k];
-            xq[k] = load_x(c + 4);
             mbar_wait(&a_empty[sa], pha ^ 1);
             uint8_t* ahi = sA + sa * kTcAStageBytes;
             uint8_t* alo = ahi + 16384;
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              kan_tc_expand_store(e == 0 ? xv.x : xv.y, sw128_offset(srow, 2 * ip + e), ahi, alo, sXthr, sKnot, sInvH, tb.uniform != 0);
-            }
+            kan_tc_expand_store(xg[k].x, sw128_offset(srow, 2 * ip), ahi, alo, sXthr);
+            kan_tc_expand_store(xg[k].y, sw128_offset(srow, 2 * ip + 1), ahi, alo, sXthr);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&a_full[sa]);
             if (++sa == kTcAStages) { sa = 0; pha ^= 1; }
           }
         }
+      };
+#pragma unroll 1
+      for (int c0 = 0; c0 < num_chunks; c0 += 8) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xb[k] = load_x(c0 + 4 + k);
+        expand_group(xa, c0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xa[k] = load_x(c0 + 8 + k);
+        expand_group(xb, c0 + 4);
       }
       // ---- epilogue of this tile
       mbar_wait(&d_full[acc], acc_ph);
@@ -399,9 +401,7 @@ kan_bwd_x_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_cons
   uint8_t* sG = smem;
   uint8_t* sW = sG + 2 * kTcGBufBytes;
   float* sXthr = reinterpret_cast<float*>(sW + kTcWStages * kTcWStageBytes);     // [12]
-  float* sKnot = sXthr + 12;     // [8]
-  float* sInvH = sKnot + 8;      // [8]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sInvH + 8 + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sXthr + 32);
   uint64_t* g_full = bars;                       // [2]
   uint64_t* g_empty = g_full + 2;                // [2]
   uint64_t* w_full = g_empty + 2;                // [4]
@@ -414,7 +414,6 @@ kan_bwd_x_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_cons
   const int num_tiles = (batch + 127) / 128;
 
   if (threadIdx.x < 9) sXthr[threadIdx.x] = tb.xthr[threadIdx.x];
-  if (threadIdx.x < 8) { sKnot[threadIdx.x] = tb.knot[threadIdx.x]; sInvH[threadIdx.x] = tb.inv_h[threadIdx.x]; }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmWhi);
     tma_prefetch_desc(&tmWlo);
@@ -522,11 +521,9 @@ kan_bwd_x_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_cons
           uint32_t wh[4], wl[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float a = g[h * 8 + 2 * e], b = g[h * 8 + 2 * e + 1];
-            const __nv_bfloat16 ah = __float2bfloat16(a), bh = __float2bfloat16(b);
-            const __nv_bfloat16 al = __float2bfloat16(a - __bfloat162float(ah)), bl = __float2bfloat16(b - __bfloat162float(bh));
-            wh[e] = static_cast<uint32_t>(__bfloat16_as_ushort(ah)) | (static_cast<uint32_t>(__bfloat16_as_ushort(bh)) << 16);
-            wl[e] = static_cast<uint32_t>(__bfloat16_as_ushort(al)) | (static_cast<uint32_t>(__bfloat16_as_ushort(bl)) << 16);
+            const float a = g[h * 8 + 2 * e], b = g[h * 8 + 2 * e + 1];      // two values per (ALU-pipe) packed conversion
+            wh[e] = pack_bf16x2(a, b);
+            wl[e] = pack_bf16x2(a - __uint_as_float(wh[e] << 16), b - __uint_as_float(wh[e] & 0xffff0000u));
           }
           const uint32_t off = sw128_offset(srow, gq * 2 + h);
           *reinterpret_cast<uint4*>(ghi + off) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
@@ -549,18 +546,20 @@ kan_bwd_x_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_cons
           for (long long o = static_cast<long long>(pt) * 128; o < bytes; o += 512 * 128) prefetch_l2(base + o);
         }
       }
-      // the inputs of the next four chunks are in flight while one T block is contracted
-      float2 xq[4];
+      // the inputs of the next four-chunk group are in flight while one group is contracted (two register sets with fixed
+      // roles, see kan_fwd_tc_kernel: a rotating queue degenerates into one chunk of prefetch distance)
+      auto load_x = [&](int c) -> float2 {
+        return (live && c < num_chunks) ? *reinterpret_cast<const float2*>(xr + c * 8) : make_float2(0.f, 0.f);
+      };
+      float2 xa[4], xb[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) xq[k] = (live && k < num_chunks) ? *reinterpret_cast<const float2*>(xr + k * 8) : make_float2(0.f, 0.f);
-#pragma unroll 1
-      for (int c0 = 0; c0 < num_chunks; c0 += 4) {
+      for (int k = 0; k < 4; ++k) xa[k] = load_x(k);
+      auto contract_group = [&](const float2 (&xg)[4], int cbase) {
 #pragma unroll
       for (int kq = 0; kq < 4; ++kq) {
-        const int c = c0 + kq;
+        const int c = cbase + kq;
         if (c >= num_chunks) break;                    // warp-uniform
-        const float2 xv = xq[kq];
-        if (live && c + 4 < num_chunks) xq[kq] = *reinterpret_cast<const float2*>(xr + (c + 4) * 8);
+        const float2 xv = xg[kq];
         mbar_wait(&d_full[acc], acc_ph);
         tc_fence_after();
         float T[16];
@@ -579,19 +578,13 @@ kan_bwd_x_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_cons
           const float tt = copysignf(fmaf(-2.0f, rc, 1.0f), xe);
           const float dt = 4.0f * rc * (1.0f - rc);                 // 1 - tanh^2, without cancellation
           const float s5 = fmaf(tt, 5.0f, 5.0f);
-          const int jf = __float2int_rd(s5);
-          int j = min(jf, 7);
-          const float frac = s5 - static_cast<float>(jf);
-          if ((frac < 1e-4f || frac > 1.0f - 1e-4f) && jf <= 7) {       // near a knot: the calibrated x-space thresholds decide
-            j = min(max(j, 0), 7);
-            if (xe < sXthr[j]) --j;
-            else if (xe >= sXthr[j + 1]) ++j;
-          }
+          int j;
+          float jfl;
+          kan_tc_interval(xe, s5, sXthr, j, jfl);
           float sp = 0.0f;
           if (j >= 0 && j < 7) {
-            const bool uni = tb.uniform != 0;
-            const float ih = uni ? 5.0f : sInvH[j];
-            const float u = uni ? s5 - static_cast<float>(j) : (tt - sKnot[j]) * ih;
+            constexpr float ih = 5.0f;                 // 1 / knot spacing
+            const float u = s5 - jfl;
             const float u2 = u * u, om = 1.0f - u;
             float d[4];
             d[0] = 0.5f * u2 * ih;                                               // slot j
@@ -610,6 +603,15 @@ kan_bwd_x_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_cons
         }
         if (live) *reinterpret_cast<float2*>(dxr + c * 8) = make_float2(out[0], out[1]);
       }
+      };
+#pragma unroll 1
+      for (int c0 = 0; c0 < num_chunks; c0 += 8) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xb[k] = load_x(c0 + 4 + k);
+        contract_group(xa, c0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) xa[k] = load_x(c0 + 8 + k);
+        contract_group(xb, c0 + 4);
       }
     }
   }
@@ -641,9 +643,7 @@ kan_bwd_w_tc_kernel(const float* __restrict__ x, const float* __restrict__ yv, c
   uint8_t* sG = sA + 2 * kTcWgAStageBytes;
   float* sDb = reinterpret_cast<float*>(sG + 2 * kTcGBufBytes);     // [64]
   float* sXthr = sDb + 64;       // [12]
-  float* sKnot = sXthr + 12;     // [8]
-  float* sInvH = sKnot + 8;      // [8]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sInvH + 8 + 4);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sXthr + 32);
   uint64_t* a_full = bars;                       // [2]
   uint64_t* a_empty = a_full + 2;                // [2]
   uint64_t* g_full = a_empty + 2;                // [2]
@@ -658,7 +658,6 @@ kan_bwd_w_tc_kernel(const float* __restrict__ x, const float* __restrict__ yv, c
 
   if (threadIdx.x < 64) sDb[threadIdx.x] = 0.0f;
   if (threadIdx.x < 9) sXthr[threadIdx.x] = tb.xthr[threadIdx.x];
-  if (threadIdx.x < 8) { sKnot[threadIdx.x] = tb.knot[threadIdx.x]; sInvH[threadIdx.x] = tb.inv_h[threadIdx.x]; }
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&a_full[i], 16); mbar_init(&a_empty[i], 1);
@@ -718,10 +717,21 @@ kan_bwd_w_tc_kernel(const float* __restrict__ x, const float* __restrict__ yv, c
     float db[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) db[i] = 0.0f;
+    // this thread's inputs of all eight chunks of a tile; the NEXT tile's are loaded while the current tile is expanded
+    auto load_tile_x = [&](int it2, float2 (&xn)[8]) {
+      const int sg2 = (blockIdx.x + it2 * static_cast<int>(gridDim.x)) * 128 + srow;
+      const bool ok = it2 < n_my && sg2 < batch;
+      const float* xr2 = x + static_cast<size_t>(ok ? sg2 : 0) * n_in + group * 64 + 2 * ip;
+#pragma unroll
+      for (int cn = 0; cn < 8; ++cn) xn[cn] = ok ? *reinterpret_cast<const float2*>(xr2 + cn * 8) : make_float2(0.f, 0.f);
+    };
+    float2 xq[8], xnext[8];
+    load_tile_x(0, xq);
     for (int it = 0; it < n_my; ++it) {
       const int t = blockIdx.x + it * gridDim.x;
       const int sg = t * 128 + srow;
       const bool live = sg < batch;
+      load_tile_x(it + 1, xnext);
       // ---- g tile (hi | lo), and this thread's share of the bias gradient
       {
         const int gb = it & 1;
@@ -754,11 +764,9 @@ kan_bwd_w_tc_kernel(const float* __restrict__ x, const float* __restrict__ yv, c
           uint32_t wh[4], wl[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float a = g[h * 8 + 2 * e], b = g[h * 8 + 2 * e + 1];
-            const __nv_bfloat16 ah = __float2bfloat16(a), bh = __float2bfloat16(b);
-            const __nv_bfloat16 al = __float2bfloat16(a - __bfloat162float(ah)), bl = __float2bfloat16(b - __bfloat162float(bh));
-            wh[e] = static_cast<uint32_t>(__bfloat16_as_ushort(ah)) | (static_cast<uint32_t>(__bfloat16_as_ushort(bh)) << 16);
-            wl[e] = static_cast<uint32_t>(__bfloat16_as_ushort(al)) | (static_cast<uint32_t>(__bfloat16_as_ushort(bl)) << 16);
+            const float a = g[h * 8 + 2 * e], b = g[h * 8 + 2 * e + 1];      // two values per (ALU-pipe) packed conversion
+            wh[e] = pack_bf16x2(a, b);
+            wl[e] = pack_bf16x2(a - __uint_as_float(wh[e] << 16), b - __uint_as_float(wh[e] & 0xffff0000u));
           }
           const uint32_t off = sw128_offset(srow, ip * 2 + h);
           *reinterpret_cast<uint4*>(ghi + off) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
@@ -769,15 +777,11 @@ kan_bwd_w_tc_kernel(const float* __restrict__ x, const float* __restrict__ yv, c
         if (lane == 0) mbar_arrive(&g_full[gb]);
       }
       // ---- expanded activations of this CTA's 64 inputs: four stages of two chunks
-      const float* xr = x + static_cast<size_t>(live ? sg : 0) * n_in + group * 64 + 2 * ip;
-      {   // next tile's x rows (this group's 256-byte slice of each) -> L2
-        const int tn = t + gridDim.x;
+      {   // the x rows of the tile after the next one (this group's 256-byte slice of each) -> L2
+        const int tn = t + 2 * gridDim.x;
         if (tn < num_tiles && ip == 0 && tn * 128 + srow < batch)
           prefetch_l2(x + static_cast<size_t>(tn * 128 + srow) * n_in + group * 64);
       }
-      float2 xq[8];                                   // this thread's inputs of all eight chunks of the tile, loaded up front
-#pragma unroll
-      for (int cn = 0; cn < 8; ++cn) xq[cn] = live ? *reinterpret_cast<const float2*>(xr + cn * 8) : make_float2(0.f, 0.f);
 #pragma unroll
       for (int pr = 0; pr < 4; ++pr) {
         mbar_wait(&a_empty[sa], pha ^ 1);
@@ -788,8 +792,8 @@ kan_bwd_w_tc_kernel(const float* __restrict__ x, const float* __restrict__ yv, c
           uint8_t* ahi = stage + h * 16384;
           uint8_t* alo = ahi + 32768;
           if (live) {
-            kan_tc_expand_store(xv.x, sw128_offset(srow, 2 * ip), ahi, alo, sXthr, sKnot, sInvH, tb.uniform != 0);
-            kan_tc_expand_store(xv.y, sw128_offset(srow, 2 * ip + 1), ahi, alo, sXthr, sKnot, sInvH, tb.uniform != 0);
+            kan_tc_expand_store(xv.x, sw128_offset(srow, 2 * ip), ahi, alo, sXthr);
+            kan_tc_expand_store(xv.y, sw128_offset(srow, 2 * ip + 1), ahi, alo, sXthr);
           } else {                                  // rows past the batch must not contribute (raw-x slot of x = 0 is 0 anyway,
             const uint4 z = make_uint4(0u, 0u, 0u, 0u);   // but the spline slots of tanh(0) are not)
             *reinterpret_cast<uint4*>(ahi + sw128_offset(srow, 2 * ip)) = z;
@@ -803,6 +807,8 @@ kan_bwd_w_tc_kernel(const float* __restrict__ x, const float* __restrict__ yv, c
         if (lane == 0) mbar_arrive(&a_full[sa]);
         if (++sa == 2) { sa = 0; pha ^= 1; }
       }
+#pragma unroll
+      for (int cn = 0; cn < 8; ++cn) xq[cn] = xnext[cn];
     }
     // ---- bias gradient: columns ip*16 .. +15, summed over this thread's rows -> shared -> global (group 0 only)
     if (group == 0 && dlin_b != nullptr) {

@@ -31,6 +31,7 @@ std::atomic<long long> g_launches{0};
 void rvk_set_last_cuda_error(int code, const char* what) {
   g_last_error = std::string(what) + ": " + cudaGetErrorString(static_cast<cudaError_t>(code));
 }
+void rvk_set_last_error_text(const char* what) { g_last_error = what; }
 const char* rvk_last_error_cstr() { return g_last_error.c_str(); }
 void rvk_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 

@@ -461,7 +461,8 @@ class HeadsTrainFn(torch.autograd.Function):
         # the live gradients are views of ONE flat buffer in parameter order: a data-parallel caller reduces them in place
         # with a single collective (dist.all_reduce_gradients), like the trunk's flat gradient
         numels = [int(torch.Size(shp).numel()) if (live[i] and need[3 + i]) else 0 for i, shp in enumerate(shapes)]
-        flat_g = torch.empty(sum(numels), device=dev, dtype=torch.float32)
+        # (an empty batch launches nothing: its gradients are zeros, not whatever the allocator hands out)
+        flat_g = (torch.empty if batch > 0 else torch.zeros)(sum(numels), device=dev, dtype=torch.float32)
         grads, off = [], 0
         for n, shp in zip(numels, shapes):
             grads.append(flat_g[off:off + n].view(shp) if n else None)

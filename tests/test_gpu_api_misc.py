@@ -198,3 +198,42 @@ def test_kernel_protocol_error_surfaces_as_rovitkan_error():
     # the device is fine for the next process
     x = torch.ones(4, device=DEV)
     assert float(x.sum()) == 4.0
+
+
+OUT_SHAPES = {'cls_logits': (4,), 'ordinal_logits': (3,), 'mu': (1,), 'log_var': (1,), 'kan_severity': (1,), 'features': (192,)}
+
+
+@pytest.mark.parametrize('train', [False, True])
+def test_empty_batch_gives_empty_outputs(train):
+    """The reference's modules are shape-polymorphic in the batch: a 0-image batch (the tail of a drained loader) returns
+    empty tensors of the right trailing shape, and its backward is a no-op that leaves zero gradients."""
+    m = RoViTKAN(pretrained=False).to(DEV).train(train)
+    x = torch.empty(0, 3, 224, 224, device=DEV)
+    with torch.set_grad_enabled(train):
+        o = m(x)
+    for k, tail in OUT_SHAPES.items():
+        assert tuple(o[k].shape) == (0,) + tail, (k, tuple(o[k].shape))
+    if train:
+        sum(o[k].sum() for k in OUT_SHAPES if k != 'features').backward()
+        assert all(p.grad is None or float(p.grad.abs().max()) == 0.0 for p in m.parameters())
+    else:
+        p = m.predict(x)
+        assert p['class'].shape == (0,) and tuple(p['class_probs'].shape) == (0, 4)
+        assert tuple(p['ordinal_probs'].shape) == (0, 4) and p['ordinal_severity'].shape[0] == 0
+
+
+def test_strided_and_channels_last_images_match_the_contiguous_call():
+    """Loaders hand over channels_last / sliced batches; the kernels read packed NCHW, so the module must normalise the
+    layout itself (the reference's Conv2d patch embedding accepts any strides)."""
+    torch.manual_seed(1)
+    m = RoViTKAN(pretrained=False).to(DEV).eval()
+    big = torch.randn(7, 3, 224, 448, device=DEV)
+    x = big[:, :, :, ::2]                                    # strided view
+    assert not x.is_contiguous()
+    with torch.no_grad():
+        ref = m(x.contiguous())
+        o1 = m(x)
+        o2 = m(x.contiguous().to(memory_format=torch.channels_last))
+    for k in OUT_SHAPES:
+        assert torch.equal(o1[k], ref[k]), k
+        assert torch.equal(o2[k], ref[k]), k

@@ -378,3 +378,25 @@ def test_fused_training_tail_stage_gating_clamp_and_dropout():
     m.curriculum_stage = 2
     out = m(torch.randn(3, 3, 224, 224, device=DEV))
     assert out['kan_severity'] is None and out['mu'] is None and out['ordinal_logits'] is not None
+
+
+@pytest.mark.parametrize('knots', ['rescaled', 'uneven'])
+def test_foreign_knot_vectors_are_refused(knots):
+    """Every kernel is written for the reference's knot buffer linspace(-1, 1, 11) (closed uniform cubic segments, interval
+    from 5 (tanh x + 1), no clamp to the knot range).  The buffer travels in the state_dict; a vector the reference's
+    Cox-de Boor recursion would accept but these kernels would evaluate differently is an error, not a silently different
+    spline -- on the per-layer path and on the fused tail of the model."""
+    from rovitkan_b200 import _lib
+    from rovitkan_b200.models import RoViTKAN
+    layer = KANLayer(16, 4).to(DEV)
+    model = RoViTKAN(pretrained=False).to(DEV).eval()
+    with torch.no_grad():
+        for kb in (layer.knots, model.kan_module.kan_layers[1].knots):
+            if knots == 'rescaled':
+                kb.copy_(torch.linspace(-0.9, 0.8, 11))
+            else:
+                kb[4] += 0.05
+    with pytest.raises(_lib.RovitKanError, match='linspace'):
+        layer(torch.randn(8, 16, device=DEV))
+    with pytest.raises(_lib.RovitKanError, match='linspace'), torch.no_grad():
+        model(torch.randn(2, 3, 224, 224, device=DEV))
