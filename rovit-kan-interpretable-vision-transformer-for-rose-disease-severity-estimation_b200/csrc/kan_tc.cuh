@@ -75,50 +75,56 @@ __global__ void kan_split_weights_kernel(const float* __restrict__ spline, const
 //   * the local coordinate is u = s - j: the knot vector is the reference's linspace(-1, 1, 11) (api.cu::check_knots);
 //   * the four live cubics in Horner form, converted to bf16 hi / lo two at a time (cvt.rn.bf16x2.f32);
 //   * one-hot placement = a 128-bit shift of the packed 4 x bf16 group by 16 (j - 3) bits, one 16-byte store per tile.
-// Knot interval j of x (j = #{m >= 1 : x >= xthr[m]}: 0..6 live, >= 7 dead zone) and float(j), for the reference's knot
-// vector linspace(-1, 1, 11) (the only one the C ABI accepts, api.cu::check_knots): j = floor(s), s = 5 (tanh x + 1) in
-// [0, 10], taken WITHOUT F2I / I2F (XU-pipe conversions in the middle of the dependent chain): a round-down add of
-// 1.5 * 2^23 leaves floor(s) in the low mantissa bits and, minus the constant, as an exact float.  The calibrated x-space
-// thresholds are consulted only within 1e-4 of a knot (fast-tanh error in s: 2e-6).
+// Knot interval j of x and float(j) for the reference's knot vector linspace(-1, 1, 11) (the only one the C ABI accepts,
+// api.cu::check_knots): j = floor(s), s = 5 (tanh x + 1) in [0, 10]; 0..6 live, >= 7 dead zone (a negative j can only come
+// out of a NaN input: callers test `unsigned(j) < 7`).  Taken WITHOUT F2I / I2F (XU-pipe conversions in the middle of the
+// dependent chain): a round-down add of 1.5 * 2^23 leaves floor(s) in the low mantissa bits and, minus the constant, as an
+// exact float.  The calibrated x-space thresholds are consulted only within 1e-4 of a knot (fast-tanh error in s: 2e-6);
+// sXthr[9..11] = +inf, so no range check on j is needed.  These kernels are bound by the half-rate ALU pipe (compares,
+// selects, min/max, shifts, conversions): no clamps here, the callers mask dead lanes instead.
 __device__ __forceinline__ void kan_tc_interval(float xe, float s, const float* sXthr, int& j, float& jfl) {
   const float sm = __fadd_rd(s, 12582912.0f);
-  const int jf = __float_as_int(sm) - 0x4B400000;
-  const float jff = sm - 12582912.0f;
-  j = min(jf, 7);
-  jfl = fminf(jff, 7.0f);
-  const float frac = s - jff;
-  if ((frac < 1e-4f || frac > 1.0f - 1e-4f) && jf <= 7) { // rare (2e-4 of the inputs below the dead zone): exact decision
+  j = __float_as_int(sm) - 0x4B400000;
+  jfl = sm - 12582912.0f;
+  if (fabsf((s - jfl) - 0.5f) > 0.5f - 1e-4f) {           // rare (2e-4 of the inputs): exact decision
     if (xe < sXthr[j]) { --j; jfl -= 1.0f; }
     else if (xe >= sXthr[j + 1]) { ++j; jfl += 1.0f; }
   }
 }
 
-__device__ __forceinline__ void kan_tc_expand_store(float xe, uint32_t off, uint8_t* ahi, uint8_t* alo, const float* sXthr) {
-  // tanh (branch-free, MUFU): values only; the interval comes from x-space thresholds where it matters
-  const float ex = ex2_approx(fabsf(xe) * 2.8853900817779268f);
-  float rc;
+// tanh x = 1 - 2 / (2^(2 log2(e) x) + 1), branch-free on MUFU.EX2 / MUFU.RCP (absolute error ~3e-7) for either sign of x
+// (no |x| / copysign: one ALU-pipe instruction less); rc = 1 / (e^(2x) + 1), so 1 - tanh^2 = 4 rc (1 - rc)
+__device__ __forceinline__ float kan_tc_tanh(float xe, float& rc) {
+  const float ex = ex2_approx(xe * 2.8853900817779268f);
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(ex + 1.0f));
-  const float tt = copysignf(fmaf(-2.0f, rc, 1.0f), xe);
+  return fmaf(-2.0f, rc, 1.0f);
+}
+
+__device__ __forceinline__ void kan_tc_expand_store(float xe, uint32_t off, uint8_t* ahi, uint8_t* alo, const float* sXthr) {
+  float rc;
+  const float tt = kan_tc_tanh(xe, rc);                    // values only; the interval comes from x-space thresholds where it matters
   const float s = fmaf(tt, 5.0f, 5.0f);                    // in [0, 10]
   int j;
   float jfl;
   kan_tc_interval(xe, s, sXthr, j, jfl);
-  const int jc = min(max(j, 0), 6);
-  const float u = s - fminf(fmaxf(jfl, 0.0f), 6.0f);
+  const bool live = static_cast<unsigned>(j) < 7u;         // dead zone: zeros (the mask rides in the polynomial scale)
+  const int jc = static_cast<int>(min(static_cast<unsigned>(j), 6u));
+  const float c6 = live ? (1.0f / 6.0f) : 0.0f;
+  const float u = s - jfl;
   const float u2 = u * u, om = 1.0f - u;
-  const float v0 = u2 * u * (1.0f / 6.0f);                                            // slot j
-  const float v1 = fmaf(fmaf(fmaf(-0.5f, u, 0.5f), u, 0.5f), u, 1.0f / 6.0f);         // slot j-1
-  const float v2 = fmaf(fmaf(0.5f, u, -1.0f), u2, 2.0f / 3.0f);                       // slot j-2
-  const float v3 = om * om * om * (1.0f / 6.0f);                                      // slot j-3
+  const float v0 = u2 * u * c6;                                                        // slot j
+  const float v1 = fmaf(fmaf(fmaf(-3.0f, u, 3.0f), u, 3.0f), u, 1.0f) * c6;            // slot j-1
+  const float v2 = fmaf(fmaf(3.0f, u, -6.0f), u2, 4.0f) * c6;                          // slot j-2
+  const float v3 = om * om * om * c6;                                                  // slot j-3
   // hi / lo split, two values per conversion: word = [second : first] as bf16 pairs
   const __nv_bfloat162 h32 = __floats2bfloat162_rn(v3, v2), h10 = __floats2bfloat162_rn(v1, v0);
-  uint32_t w32 = *reinterpret_cast<const uint32_t*>(&h32), w10 = *reinterpret_cast<const uint32_t*>(&h10);
+  const uint32_t w32 = *reinterpret_cast<const uint32_t*>(&h32), w10 = *reinterpret_cast<const uint32_t*>(&h10);
   const __nv_bfloat162 l32 = __floats2bfloat162_rn(v3 - __uint_as_float(w32 << 16), v2 - __uint_as_float(w32 & 0xffff0000u));
   const __nv_bfloat162 l10 = __floats2bfloat162_rn(v1 - __uint_as_float(w10 << 16), v0 - __uint_as_float(w10 & 0xffff0000u));
-  uint32_t q32 = *reinterpret_cast<const uint32_t*>(&l32), q10 = *reinterpret_cast<const uint32_t*>(&l10);
-  const bool live = (j >= 0) && (j < 7);                   // dead zone (and x below the first knot: impossible for tanh): zeros
-  if (!live) { w32 = w10 = q32 = q10 = 0u; }
-  // slots j-3 .. j <- (v3, v2, v1, v0): shift the 64-bit group by 16 * (j - 3) bits inside the 128-bit row
+  const uint32_t q32 = *reinterpret_cast<const uint32_t*>(&l32), q10 = *reinterpret_cast<const uint32_t*>(&l10);
+  // slots j-3 .. j <- (v3, v2, v1, v0): shift the 64-bit group by 16 * (j - 3) bits inside the 128-bit row.
+  // (A branch-free form -- three funnel shifts + a two-level select on (7 - jc) / 2 -- measured 4-6 % SLOWER: the selects
+  // land on the half-rate ALU pipe, which is what bounds this kernel; the shift pairs + short branches below are cheaper.)
   const int sh = (jc - 3) * 16;                            // -48 .. 48
   const unsigned long long vh = (static_cast<unsigned long long>(w10) << 32) | w32;
   const unsigned long long vl = (static_cast<unsigned long long>(q10) << 32) | q32;
@@ -165,7 +171,7 @@ kan_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_consta
   const int num_tiles = (batch + 127) / 128;
 
   if (threadIdx.x < 64) sBias[threadIdx.x] = (threadIdx.x < n_out) ? bias[threadIdx.x] : 0.0f;
-  if (threadIdx.x < 9) sXthr[threadIdx.x] = tb.xthr[threadIdx.x];     // written by kan_tc_thresholds_kernel on this stream
+  if (threadIdx.x < 12) sXthr[threadIdx.x] = threadIdx.x < 9 ? tb.xthr[threadIdx.x] : INFINITY;     // written by kan_tc_thresholds_kernel on this stream
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmWhi);
     tma_prefetch_desc(&tmWlo);
@@ -413,7 +419,7 @@ kan_bwd_x_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_tiles = (batch + 127) / 128;
 
-  if (threadIdx.x < 9) sXthr[threadIdx.x] = tb.xthr[threadIdx.x];
+  if (threadIdx.x < 12) sXthr[threadIdx.x] = threadIdx.x < 9 ? tb.xthr[threadIdx.x] : INFINITY;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmWhi);
     tma_prefetch_desc(&tmWlo);
@@ -572,33 +578,35 @@ kan_bwd_x_tc_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_cons
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const float xe = e == 0 ? xv.x : xv.y;
-          const float ex = ex2_approx(fabsf(xe) * 2.8853900817779268f);
           float rc;
-          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rc) : "f"(ex + 1.0f));
-          const float tt = copysignf(fmaf(-2.0f, rc, 1.0f), xe);
-          const float dt = 4.0f * rc * (1.0f - rc);                 // 1 - tanh^2, without cancellation
+          const float tt = kan_tc_tanh(xe, rc);
+          const float rc4 = 4.0f * rc;
+          const float dt = fmaf(-rc4, rc, rc4);                        // 1 - tanh^2 = 4 rc (1 - rc), without cancellation
           const float s5 = fmaf(tt, 5.0f, 5.0f);
           int j;
           float jfl;
           kan_tc_interval(xe, s5, sXthr, j, jfl);
-          float sp = 0.0f;
-          if (j >= 0 && j < 7) {
-            constexpr float ih = 5.0f;                 // 1 / knot spacing
-            const float u = s5 - jfl;
-            const float u2 = u * u, om = 1.0f - u;
-            float d[4];
-            d[0] = 0.5f * u2 * ih;                                               // slot j
-            d[1] = (3.0f + 6.0f * u - 9.0f * u2) * (1.0f / 6.0f) * ih;           // slot j-1
-            d[2] = (-12.0f * u + 9.0f * u2) * (1.0f / 6.0f) * ih;                // slot j-2
-            d[3] = -0.5f * om * om * ih;                                         // slot j-3
+          // basis derivatives d/dt of the four live cubics (knot spacing 1/5 folded into the coefficients)
+          const float u = s5 - jfl, om = 1.0f - u;
+          const float d0 = 2.5f * u * u;                               // slot j
+          const float d1 = fmaf(fmaf(-7.5f, u, 5.0f), u, 2.5f);        // slot j-1
+          const float d2 = u * fmaf(7.5f, u, -10.0f);                  // slot j-2
+          const float d3 = -2.5f * om * om;                            // slot j-3
+          // the four T columns j-3 .. j (zero below slot 0) through a 3-level select on the bits of j -- a barrel shifter in
+          // registers: 16 selects instead of 28 compares + 28 predicated FMAs for the `slot == k` form (49 of ~125
+          // instructions per (sample, input) in the round-2 profile)
+          const float* Te = T + e * 8;
+          const bool b2 = (j & 4) != 0, b1 = (j & 2) != 0, b0 = (j & 1) != 0;
+          const float E[11] = {0.0f, 0.0f, 0.0f, Te[0], Te[1], Te[2], Te[3], Te[4], Te[5], Te[6], 0.0f};
+          float F[7], G[5], H[4];
 #pragma unroll
-            for (int m = 0; m < 4; ++m) {
-              const int slot = j - m;
+          for (int i = 0; i < 7; ++i) F[i] = b2 ? E[i + 4] : E[i];
 #pragma unroll
-              for (int k = 0; k < 7; ++k)
-                if (slot == k) sp = fmaf(T[e * 8 + k], d[m], sp);
-            }
-          }
+          for (int i = 0; i < 5; ++i) G[i] = b1 ? F[i + 2] : F[i];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) H[i] = b0 ? G[i + 1] : G[i];       // H[i] = T column j - 3 + i
+          float sp = fmaf(d0, H[3], fmaf(d1, H[2], fmaf(d2, H[1], d3 * H[0])));
+          sp = static_cast<unsigned>(j) < 7u ? sp : 0.0f;              // dead zone (and NaN inputs): linear branch only
           out[e] = fmaf(dt, sp, T[e * 8 + 7]);
         }
         if (live) *reinterpret_cast<float2*>(dxr + c * 8) = make_float2(out[0], out[1]);
@@ -657,7 +665,7 @@ kan_bwd_w_tc_kernel(const float* __restrict__ x, const float* __restrict__ yv, c
   const int n_my = (blockIdx.x < num_tiles) ? (num_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (threadIdx.x < 64) sDb[threadIdx.x] = 0.0f;
-  if (threadIdx.x < 9) sXthr[threadIdx.x] = tb.xthr[threadIdx.x];
+  if (threadIdx.x < 12) sXthr[threadIdx.x] = threadIdx.x < 9 ? tb.xthr[threadIdx.x] : INFINITY;
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&a_full[i], 16); mbar_init(&a_empty[i], 1);
