@@ -10,13 +10,14 @@ namespace {
 
 constexpr int kBN = 192;       // every N on this path (192, 576, 768) is a multiple of 192
 constexpr int kNtStages = 3;
+constexpr bool kTwoStageAll = false;   // measured: see launch_nt
 constexpr int kBQ = 192;
 constexpr int kTnStages = 4;
 
-template <int MODE>
-int launch_nt(const GemmNtArgs& a, cudaStream_t stream) {
-  using L = GemmNtSmem<kBN, kNtStages>;
-  auto kernel = gemm_nt_kernel<kBN, MODE, kNtStages>;
+template <int MODE, int kStages>
+int launch_nt_stages(const GemmNtArgs& a, cudaStream_t stream) {
+  using L = GemmNtSmem<kBN, kStages>;
+  auto kernel = gemm_nt_kernel<kBN, MODE, kStages>;
   RVK_SET_MAX_SMEM(kernel, L::kTotal);
   const GemmNtParams& p = a.p;
   CUtensorMap tmA, tmB, tmOut, tmOut2, tmAux;
@@ -54,6 +55,16 @@ int launch_nt(const GemmNtArgs& a, cudaStream_t stream) {
   cfg.numAttrs = 1;
   RVK_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, tmA, tmB, tmOut, tmOut2, tmAux, p));
   return rvk_launch_check();
+}
+
+// K = 192 (three K blocks per tile) needs little operand prefetch: two ring stages, and the 40 KB they free hold two more
+// epilogue panel slots (8 instead of 6) -- what the epilogue warps of the aux-loading DGELU mode were waiting for.
+template <int MODE>
+int launch_nt(const GemmNtArgs& a, cudaStream_t stream) {
+  static const int force = [] { const char* e = getenv("RVK_NT_STAGES"); return e != nullptr ? atoi(e) : 0; }();
+  // RVK_NT_STAGES=2: every K <= 192 GEMM on the two-stage variant; =3: none (experiments)
+  const bool two = a.p.K <= 192 && force != 3 && (force == 2 || MODE == EPI_DGELU || kTwoStageAll);
+  return two ? launch_nt_stages<MODE, 2>(a, stream) : launch_nt_stages<MODE, kNtStages>(a, stream);
 }
 
 }  // namespace

@@ -55,7 +55,6 @@ struct GemmNtParams {
 constexpr int kGemmThreads = 480;
 constexpr int kNumTeams = 3;
 constexpr int kPanelBytes = 128 * 128;   // 16 KB
-constexpr int kNumSlots = 6;
 
 template <int BN, int STAGES>
 struct GemmNtSmem {
@@ -63,6 +62,9 @@ struct GemmNtSmem {
   static constexpr int kBBytes = BN * 64 * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kOperandBytes = STAGES * kStageBytes;
+  // epilogue staging slots (16 KB panels): 6 next to a 3-stage operand ring; a 2-stage ring (K = 192 needs little operand
+  // prefetch) leaves room for 8 -- used by the aux-loading DGELU mode, whose slots are held from the z load to the dz store
+  static constexpr int kNumSlots = STAGES >= 3 ? 6 : 8;
   static constexpr int kSlotBytes = kNumSlots * kPanelBytes;
   static constexpr int kVecBytes = (768 + 192 + 192) * 4;   // bias / gamma / beta
   static constexpr int kBarBytes = 256;
@@ -108,9 +110,9 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty = full + STAGES;             // [STAGES]
   uint64_t* tmem_full = empty + STAGES;        // [2]
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
-  uint64_t* slot_full = tmem_empty + 2;        // [kNumSlots]
-  uint64_t* slot_empty = slot_full + kNumSlots;  // [kNumSlots]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(slot_empty + kNumSlots);
+  uint64_t* slot_full = tmem_empty + 2;        // [L::kNumSlots]
+  uint64_t* slot_empty = slot_full + L::kNumSlots;  // [L::kNumSlots]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(slot_empty + L::kNumSlots);
   float* sPart = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + L::kBarBytes);   // [2][2][128]
 
   const int warp = threadIdx.x >> 5;
@@ -141,7 +143,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 128 * kNumTeams);
     }
-    for (int i = 0; i < kNumSlots; ++i) {
+    for (int i = 0; i < L::kNumSlots; ++i) {
       mbar_init(&slot_full[i], 1);
       mbar_init(&slot_empty[i], 4);     // one arrival per epilogue warp
     }
@@ -166,6 +168,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int m0 = (t / num_n_tiles) * 128;
         const int n0 = (t % num_n_tiles) * BN;
+        // (an L2 prefetch of the next tile's A rows from here measured 2-8 % SLOWER in every epilogue mode: the loads are
+        // not what the tiles wait for)
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           mbar_arrive_expect_tx(&full[s], L::kStageBytes);
@@ -217,9 +221,19 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int m0 = (t / num_n_tiles) * 128;
         const int n0 = (t % num_n_tiles) * BN;
         const int np = panels_per_tile<BN, MODE>(p);
+        if constexpr (MODE == EPI_DGELU) {
+          // A slot is held from the aux load until its output store has drained, so the loads cannot run far ahead of the
+          // epilogue: with the z panels coming from HBM the epilogue warps spent 23 % of their samples waiting for slot_full
+          // (ncu source view).  Pull the panels of the tile after the next one into L2 now; the slot load then hits L2.
+          const int t2 = t + 2 * static_cast<int>(gridDim.x);
+          if (t2 < num_tiles) {
+            for (int i = 0; i < np; ++i)
+              tma_prefetch_2d(&tmAux, (t2 % num_n_tiles) * BN + i * 64, (t2 / num_n_tiles) * 128);
+          }
+        }
         for (int i = 0; i < np; ++i, ++cnt) {
-          const int slot = cnt % kNumSlots;
-          const uint32_t par = (cnt / kNumSlots) & 1;
+          const int slot = cnt % L::kNumSlots;
+          const uint32_t par = (cnt / L::kNumSlots) & 1;
           mbar_wait(&slot_empty[slot], par ^ 1);
           if (panel_has_aux<BN, MODE>(p, i)) {
             mbar_arrive_expect_tx(&slot_full[slot], kPanelBytes);
@@ -246,8 +260,8 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // panels go round-robin over the teams; `cnt` walks the CTA's whole panel sequence
     auto mine = [&]() -> bool { return cnt % kNumTeams == static_cast<uint32_t>(team); };
     auto acquire = [&](int& slot) -> uint8_t* {
-      slot = cnt % kNumSlots;
-      mbar_wait(&slot_full[slot], (cnt / kNumSlots) & 1);
+      slot = cnt % L::kNumSlots;
+      mbar_wait(&slot_full[slot], (cnt / L::kNumSlots) & 1);
       ++cnt;
       return sSlots + slot * kPanelBytes;
     };
