@@ -17,6 +17,9 @@ timeout 600 $NCU -k regex:kan_small_fwd -s 3 -c 1 -o gpurun_out/prof_kan_small_f
 for k in gemm_tn layernorm_bwd attn_bwd_tc; do
   timeout 600 $NCU -k regex:$k -s 60 -c 1 -o gpurun_out/prof_$k $BT > gpurun_out/ncu_$k.log 2>&1; echo "$k $?"
 done
+NCUD="$NCU --kernel-name-base demangled"
+timeout 600 $NCUD -k "regex:gemm_nt_kernel<.int.192, .int.1," -s 14 -c 1 -o gpurun_out/prof_gemm_nt_gelu $BT > gpurun_out/ncu_k.log 2>&1; echo "gemm_nt gelu $?"
+timeout 600 $NCUD -k "regex:gemm_nt_kernel<.int.192, .int.2," -s 14 -c 1 -o gpurun_out/prof_gemm_nt_dgelu $BT > gpurun_out/ncu_l.log 2>&1; echo "gemm_nt dgelu $?"
 timeout 600 $NCU -k regex:heads_train_bwd -s 3 -c 1 -o gpurun_out/prof_heads_train_bwd $BT > gpurun_out/ncu_f.log 2>&1; echo "heads_train_bwd $?"
 timeout 600 $NCU -k regex:heads_fused_kernel -s 3 -c 1 -o gpurun_out/prof_heads_train_fwd $BT > gpurun_out/ncu_g.log 2>&1; echo "heads_train_fwd $?"
 timeout 600 $NCU -k regex:optim_update -s 3 -c 1 -o gpurun_out/prof_optim_update $BT > gpurun_out/ncu_h.log 2>&1; echo "optim_update $?"
