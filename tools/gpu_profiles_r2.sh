@@ -1,5 +1,7 @@
-# final validation + evidence: all tests, default bench line, launch lists, --set full captures
-GPU_TEST_FILES="test_gpu_mlp_fused test_gpu_gemm test_gpu_encoder_kernels test_gpu_heads test_gpu_model test_gpu_api_misc test_gpu_parity_full test_gpu_dropin_flow test_gpu_optim" bash tools/gpu_trip_r2.sh tests bench noncu
+# final validation + evidence: all tests, default bench line, launch lists, --set full captures; the reports are summarised ON the
+# box (gpurun merges at most 64 MiB back): text summaries land in gpurun_out/profiles_r2/, only three reports travel.
+# usage: bash tools/gpu_profiles_r2.sh [tests|notests]
+GPU_TEST_FILES="test_gpu_mlp_fused test_gpu_gemm test_gpu_encoder_kernels test_gpu_heads test_gpu_model test_gpu_api_misc test_gpu_parity_full test_gpu_dropin_flow test_gpu_optim" bash tools/gpu_trip_r2.sh ${1:-tests} bench noncu
 NCU_LIST="ncu --metrics gpu__time_duration.sum --clock-control none --csv"
 BT="python bench.py --mode train --steps 1 --warmup 3 --no-cpu-baseline"
 BK="python bench.py --mode kan --steps 2 --warmup 3 --no-cpu-baseline"
@@ -26,3 +28,10 @@ timeout 600 $NCU -k regex:optim_update -s 3 -c 1 -o gpurun_out/prof_optim_update
 timeout 600 $NCU -k regex:heads_fused_kernel -s 3 -c 1 -o gpurun_out/prof_heads_fused $BI > gpurun_out/ncu_i.log 2>&1; echo "heads_fused $?"
 timeout 600 $NCU -k regex:mlp_fused -s 40 -c 1 -o gpurun_out/prof_mlp $BI > gpurun_out/ncu_j.log 2>&1; echo "mlp $?"
 ls -la gpurun_out/*.ncu-rep
+python tools/make_profiles.py r2 > gpurun_out/make_profiles.log 2>&1; echo "make_profiles $?"
+mkdir -p gpurun_out/profiles_r2 gpurun_out/keep
+cp profiles/r2_* profiles/roofline_traffic.json gpurun_out/profiles_r2/
+for k in kan_fwd_tc gemm_nt_dgelu mlp; do mv gpurun_out/prof_$k.ncu-rep gpurun_out/keep/ 2>/dev/null; done
+rm -f gpurun_out/prof_*.ncu-rep gpurun_out/launches_*.csv
+mv gpurun_out/keep/*.ncu-rep gpurun_out/ 2>/dev/null; rmdir gpurun_out/keep
+du -sh gpurun_out
