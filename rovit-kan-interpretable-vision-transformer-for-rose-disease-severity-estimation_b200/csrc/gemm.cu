@@ -10,7 +10,6 @@ namespace {
 
 constexpr int kBN = 192;       // every N on this path (192, 576, 768) is a multiple of 192
 constexpr int kNtStages = 3;
-constexpr bool kTwoStageAll = false;   // measured: see launch_nt
 constexpr int kBQ = 192;
 constexpr int kTnStages = 4;
 
@@ -57,13 +56,16 @@ int launch_nt_stages(const GemmNtArgs& a, cudaStream_t stream) {
   return rvk_launch_check();
 }
 
-// K = 192 (three K blocks per tile) needs little operand prefetch: two ring stages, and the 40 KB they free hold two more
-// epilogue panel slots (8 instead of 6) -- what the epilogue warps of the aux-loading DGELU mode were waiting for.
+// The aux-loading DGELU mode holds an epilogue panel slot from the load of the saved z panel until the dz store out of the same
+// slot has drained; with six slots its epilogue warps spent 23 % of their samples waiting for a panel (ncu).  K = 192 (three K
+// blocks per tile) needs little operand prefetch, so this mode runs two ring stages and the 40 KB they free hold two more
+// slots: 54.5 -> 44.5 us per launch at 256 images.  The other K = 192 modes do not hold slots across a load and measured
+// SLOWER on that variant (train 42.7 k -> 41.9 k img/s, inference 213.5 k -> 203.9 k): they keep three stages.
+// RVK_NT_STAGES=2 / 3 forces one variant for every K <= 192 launch (experiments).
 template <int MODE>
 int launch_nt(const GemmNtArgs& a, cudaStream_t stream) {
   static const int force = [] { const char* e = getenv("RVK_NT_STAGES"); return e != nullptr ? atoi(e) : 0; }();
-  // RVK_NT_STAGES=2: every K <= 192 GEMM on the two-stage variant; =3: none (experiments)
-  const bool two = a.p.K <= 192 && force != 3 && (force == 2 || MODE == EPI_DGELU || kTwoStageAll);
+  const bool two = a.p.K <= 192 && force != 3 && (force == 2 || MODE == EPI_DGELU);
   return two ? launch_nt_stages<MODE, 2>(a, stream) : launch_nt_stages<MODE, kNtStages>(a, stream);
 }
 

@@ -443,8 +443,8 @@ int rvk_kan_layer_fwd_launch(const KanLayerDesc& L, const float* x, float* y, in
     }
     tb.xthr = xthr;
     RVK_SET_MAX_SMEM(kan_fwd_tc_kernel, kTcSmemBytes);
-    kan_fwd_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(tmWhi, tmWlo, x, L.lin_b, tb, y, act, batch,
-                                                                     L.in_features, L.out_features, L.in_features / 8);
+    kan_fwd_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, stream>>>(tmWhi, tmWlo, x, L.lin_b, tb, y, act, batch, L.in_features,
+                                                                 L.out_features, L.in_features / 8);
     return rvk_launch_check();
   }
   if (batch <= 4096) {
@@ -485,13 +485,13 @@ int rvk_kan_layer_bwd_launch(const KanLayerDesc& L, const float* x, const float*
       // tensor-core weight gradient (kan_tc.cuh): grid = (batch slices) x (groups of 64 inputs)
       KanTcTables tb;
       tb.xthr = workspace + 4 * wp;          // written by the forward launch
-        const int groups = L.in_features / 64;
+      const int groups = L.in_features / 64;
       const int tiles128 = (batch + 127) / 128;
       int slices = kNumSMsB200 / groups;
       if (slices > tiles128) slices = tiles128;
       RVK_SET_MAX_SMEM(kan_bwd_w_tc_kernel, kTcWgSmemBytes);
       kan_bwd_w_tc_kernel<<<dim3(slices, groups), kTcThreads, kTcWgSmemBytes, stream>>>(x, y, gy, tb, dWp, dlin_b, act, batch,
-                                                                                                L.in_features, L.out_features);
+                                                                                        L.in_features, L.out_features);
     } else {
       dim3 grid(in_pad / kIC, out_pad / kTO, splits);
       kan_bwd_w_kernel<<<grid, 256, 0, stream>>>(x, y, gy, act, kn, dWp, dlin_b, batch, L.in_features, L.out_features,
@@ -516,8 +516,8 @@ int rvk_kan_layer_bwd_launch(const KanLayerDesc& L, const float* x, const float*
     const int tiles = (batch + 127) / 128;
     const int grid = tiles < kNumSMsB200 ? tiles : kNumSMsB200;
     RVK_SET_MAX_SMEM(kan_bwd_x_tc_kernel, kTcBxSmemBytes);
-    kan_bwd_x_tc_kernel<<<grid, kTcThreads, kTcBxSmemBytes, stream>>>(tmWhi, tmWlo, x, y, gy, tb, dx, act, batch,
-                                                                             L.in_features, L.out_features, L.in_features / 8);
+    kan_bwd_x_tc_kernel<<<grid, kTcThreads, kTcBxSmemBytes, stream>>>(tmWhi, tmWlo, x, y, gy, tb, dx, act, batch, L.in_features,
+                                                                     L.out_features, L.in_features / 8);
     RVK_TRY(rvk_launch_check());
   } else if (dx != nullptr) {
     kan_bwd_x_kernel<<<dim3((batch + kTS - 1) / kTS, (L.in_features + kDxIC - 1) / kDxIC), 256, 0, stream>>>(
