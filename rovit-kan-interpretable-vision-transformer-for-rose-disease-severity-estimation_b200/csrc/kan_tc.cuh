@@ -80,8 +80,7 @@ __global__ void kan_split_weights_kernel(const float* __restrict__ spline, const
 // out of a NaN input: callers test `unsigned(j) < 7`).  Taken WITHOUT F2I / I2F (XU-pipe conversions in the middle of the
 // dependent chain): a round-down add of 1.5 * 2^23 leaves floor(s) in the low mantissa bits and, minus the constant, as an
 // exact float.  The calibrated x-space thresholds are consulted only within 1e-4 of a knot (fast-tanh error in s: 2e-6);
-// sXthr[9..11] = +inf, so no range check on j is needed.  These kernels are bound by the half-rate ALU pipe (compares,
-// selects, min/max, shifts, conversions): no clamps here, the callers mask dead lanes instead.
+// sXthr[9..11] = +inf, so no range check on j is needed.  No clamps here: the callers mask dead lanes.
 __device__ __forceinline__ void kan_tc_interval(float xe, float s, const float* sXthr, int& j, float& jfl) {
   const float sm = __fadd_rd(s, 12582912.0f);
   j = __float_as_int(sm) - 0x4B400000;
@@ -123,8 +122,8 @@ __device__ __forceinline__ void kan_tc_expand_store(float xe, uint32_t off, uint
   const __nv_bfloat162 l10 = __floats2bfloat162_rn(v1 - __uint_as_float(w10 << 16), v0 - __uint_as_float(w10 & 0xffff0000u));
   const uint32_t q32 = *reinterpret_cast<const uint32_t*>(&l32), q10 = *reinterpret_cast<const uint32_t*>(&l10);
   // slots j-3 .. j <- (v3, v2, v1, v0): shift the 64-bit group by 16 * (j - 3) bits inside the 128-bit row.
-  // (A branch-free form -- three funnel shifts + a two-level select on (7 - jc) / 2 -- measured 4-6 % SLOWER: the selects
-  // land on the half-rate ALU pipe, which is what bounds this kernel; the shift pairs + short branches below are cheaper.)
+  // (A branch-free form -- three funnel shifts + a two-level select on (7 - jc) / 2 -- measured 4-6 % SLOWER than the shift
+  // pairs + short branches below.)
   const int sh = (jc - 3) * 16;                            // -48 .. 48
   const unsigned long long vh = (static_cast<unsigned long long>(w10) << 32) | w32;
   const unsigned long long vl = (static_cast<unsigned long long>(q10) << 32) | q32;
