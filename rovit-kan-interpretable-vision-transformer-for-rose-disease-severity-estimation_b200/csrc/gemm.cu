@@ -1,6 +1,7 @@
 // Host launchers for the tcgen05 GEMM kernels: build the TMA tensor maps, pick the grid, launch.
 #include "kernels.h"
 #include "mlp_fused.cuh"
+#include "mlp_fused2.cuh"
 #include "tma_host.h"
 
 #include <cstdlib>
@@ -182,6 +183,51 @@ static int launch_mlp_fused(const MlpFusedArgs& a, cudaStream_t stream) {
   return rvk_launch_check();
 }
 
+// two row tiles in flight per CTA pair (mlp_fused2.cuh); needs the folded attention projection
+template <int kProjC>
+static int launch_mlp_fused2(const MlpFusedArgs& a, cudaStream_t stream) {
+  using L = Mlp2Smem;
+  auto kernel = mlp_fused2_kernel<kProjC>;
+  RVK_SET_MAX_SMEM(kernel, L::kTotal);
+  const MlpFusedParams& p = a.p;
+  CUtensorMap tmW1, tmW2, tmLn, tmCtx, tmWp;
+  RVK_TRY(rvk_make_tmap_2d(&tmW1, a.w1, RVK_BF16, 768, 192, 192, 64, 64));
+  RVK_TRY(rvk_make_tmap_2d(&tmW2, a.w2_f16, RVK_BF16 /* 2-byte elements */, 192, 768, 768, 96, 64));
+  tmLn = tmW1;
+  if (p.has_ln) RVK_TRY(rvk_make_tmap_2d(&tmLn, a.ln_out, RVK_BF16, p.M, 192, 192, 32, 64));
+  RVK_TRY(rvk_make_tmap_2d(&tmCtx, a.ctx, RVK_BF16, p.M, 192, 192, 128, 64));
+  RVK_TRY(rvk_make_tmap_2d(&tmWp, a.wproj, RVK_BF16, 192, 192, 192, 32, 64));
+  const int tiles = (p.M + 127) / 128;
+  const int units = (tiles + 1) / 2;
+  const int max_clusters = kNumSMsB200 / 2;
+  const int clusters = units < max_clusters ? units : max_clusters;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * 2);
+  cfg.blockDim = dim3(kMlpThreads);
+  cfg.dynamicSmemBytes = L::kTotal;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = rvk_pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  RvkScopedTimer timer(stream, 2.0 * p.M * 192.0 * (768.0 * 2.0 + 192.0), 0.0, RVK_T_MLP_FUSED);
+  RVK_CUDA_TRY(cudaLaunchKernelEx(&cfg, kernel, tmW1, tmW2, tmLn, tmCtx, tmWp, p));
+  return rvk_launch_check();
+}
+
+static int mlp2_proj_chunk() {      // RVK_MLP2_PROJC=0..3: chunk of tile i at which the projection of tile i+1 is issued (A/B runs)
+  static const int c = [] {
+    const char* e = getenv("RVK_MLP2_PROJC");
+    return (e != nullptr && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 2;
+  }();
+  return c;
+}
+
 int rvk_mlp_fused_launch(const MlpFusedArgs& a, cudaStream_t stream) {
   const MlpFusedParams& p = a.p;
   if (p.M <= 0) return RVK_OK;
@@ -192,5 +238,10 @@ int rvk_mlp_fused_launch(const MlpFusedArgs& a, cudaStream_t stream) {
   if (p.has_proj && (a.ctx == nullptr || a.wproj == nullptr || p.bp == nullptr)) return RVK_ERR_BAD_ARG;
   if (a.cta_group == 1) return launch_mlp_fused<1>(a, stream);
   if (a.cta_group == 2) return launch_mlp_fused<2>(a, stream);
+  if (a.cta_group == 4) {           // CTA pairs, two row tiles in flight
+    if (!p.has_proj) return RVK_ERR_BAD_ARG;
+    const int c = mlp2_proj_chunk();
+    return c == 0 ? launch_mlp_fused2<0>(a, stream) : c == 1 ? launch_mlp_fused2<1>(a, stream) : c == 3 ? launch_mlp_fused2<3>(a, stream) : launch_mlp_fused2<2>(a, stream);
+  }
   return RVK_ERR_BAD_ARG;
 }

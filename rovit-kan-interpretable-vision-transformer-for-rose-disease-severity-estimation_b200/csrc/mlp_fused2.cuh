@@ -1,0 +1,595 @@
+// Fused transformer block tail, TWO ROW TILES IN FLIGHT per CTA pair (inference path, sm_100a).  Same arithmetic as
+// mlp_fused.cuh (timm Block.forward: x + proj(attn), x + mlp(norm2(x)), then the NEXT block's norm1; oracle/vit.py::_Block),
+//
+//     x_mid = x + ctx . Wproj^T + bp ;  a = LayerNorm2(x_mid) ;  x_out = x_mid + fc2(gelu(fc1(a) + b1)) + b2 ;  ln_out = LayerNorm1'(x_out)
+//
+// restructured after the clock traces of that kernel: there ONE set of sixteen epilogue warps runs
+// GELU x6 -> LayerNorm-on-load of the next tile -> final epilogue back to back, each phase bound by its own latency chain
+// (13.5 k + 7.4 k + 7.5 k cycles per tile), while the tensor pipe needs 10.4 k and idles through both LayerNorm phases.
+// Here the sixteen warps form TWO GROUPS of eight; group g owns every second tile of the CTA (slot = tile & 1 = g) from its
+// LayerNorm-on-load to its final epilogue, and the two groups run half a tile period apart: while group 0 feeds the tensor
+// pipe with GELU chunks of tile i, group 1 drains tile i-1 and prepares tile i+1.
+//
+// What makes two tiles fit:
+//   TMEM (512 columns): D1 [0,128) = ONE fc1 accumulator (drained into registers half way through a GELU chunk, so the next
+//         fc1 runs under the GELU arithmetic), D2[slot] [128+192*slot, +192) = per-tile accumulator that carries, in turn,
+//         the attention projection (read by the LayerNorm-on-load), then the projected residual row x_mid PARKED by
+//         tcgen05.st, then fc2 accumulating on top of it: the final epilogue reads x_mid + fc2(..) in one piece, so
+//         neither x_mid nor a residual re-read touches memory (HBM/L2 traffic per row: x in, ctx in, x out, ln out only).
+//   smem: A[slot] 2 x 48 KB (ctx tile, then the normalised rows), H[slot] 2 x 32 KB (one 128-column hidden chunk; reused as the
+//         staging buffer of ln_out in two rounds), a 4-stage ring of 12 KB weight panels.
+//   registers: a thread owns 96 columns of a row in the LayerNorm phases; it walks them as two pieces of 48 and re-reads the
+//         pieces from TMEM for the second (normalising) pass instead of keeping them.
+// The tensor-pipe program is static and identical in the producer and the issuer (tiles in order; inside tile i:
+// fc1(c+1) | [projection of tile i+1 at chunk kProjC] | fc2(c); the first fc1 of tile i+1 goes in front of the last fc2).
+//
+// Warp roles (608 threads): w0 TMA producer, w1 UMMA issuer (leader CTA) + TMEM owner, w2 idle, w3..w10 group 0, w11..w18
+// group 1; inside a group: team = 64-column half of a hidden chunk / 96-column half of a token row, quad = TMEM lane quadrant.
+#pragma once
+
+#include <cuda_fp16.h>
+
+#include "mlp_fused.cuh"
+
+struct Mlp2Smem {
+  static constexpr int kABytes = 3 * 16384;                 // per slot: three [128 x 64] K panels
+  static constexpr int kHBytes = 2 * 16384;                 // per slot: one hidden chunk = two K panels
+  static constexpr int kWStage = 12288;                     // this CTA's half of a W2 / Wproj panel [96 x 64]; W1 halves [64 x 64] use 2/3
+  static constexpr int kWStages = 4;
+  static constexpr int kW1Bytes = 8192;
+  static constexpr int kVecBytes = 768 * 2 + 6 * 192 * 4;   // b1 (fp16); b2, gamma2, beta2, gamma, beta, bp (fp32)
+  static constexpr int kPartBytes = 2 * 2 * 2 * 128 * 8;    // LayerNorm partial (sum, sumsq): [use parity][group][team][row]
+  static constexpr int kBarBytes = 256;
+  static constexpr int kTotal = 1024 + 2 * kABytes + 2 * kHBytes + kWStages * kWStage + kVecBytes + kPartBytes + kBarBytes;
+};
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+      "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])),
+      "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])),
+      "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
+      "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+// kProjC: the hidden chunk of tile i at which the projection of tile i+1 is issued (its D2 slot must have been drained by the
+// other group's final epilogue of tile i-1 by then, and the LayerNorm-on-load of tile i+1 must fit behind it)
+template <int kProjC>
+__global__ void __launch_bounds__(kMlpThreads, 1)
+mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                  const __grid_constant__ CUtensorMap tmLn, const __grid_constant__ CUtensorMap tmCtx,
+                  const __grid_constant__ CUtensorMap tmWp, const MlpFusedParams p) {
+  using L = Mlp2Smem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;                                  // [2][kABytes]
+  uint8_t* sH = sA + 2 * L::kABytes;                   // [2][kHBytes]
+  uint8_t* sW = sH + 2 * L::kHBytes;
+  __half* sB1 = reinterpret_cast<__half*>(sW + L::kWStages * L::kWStage);
+  float* sB2 = reinterpret_cast<float*>(sB1 + 768);
+  float* sGamma2 = sB2 + 192;
+  float* sBeta2 = sGamma2 + 192;
+  float* sGamma = sBeta2 + 192;
+  float* sBeta = sGamma + 192;
+  float* sBp = sBeta + 192;
+  float2* sPart = reinterpret_cast<float2*>(sBp + 192);          // [2][2][2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sPart + 2 * 2 * 2 * 128);
+  // per slot [2]:
+  uint64_t* ctx_full = bars + 0;      // leader: ctx tiles of both CTAs landed in A[slot]
+  uint64_t* proj_full = bars + 2;     // projection accumulator complete (commit, both CTAs)
+  uint64_t* a_full = bars + 4;        // leader: A operand written (and x_mid parked in D2[slot]) by the group's warps of the pair
+  uint64_t* a_empty = bars + 6;       // the tile's last fc1 has read A[slot] (commit)
+  uint64_t* d1_full = bars + 8;       // fc1 chunk complete (commit); per slot so that each group counts its own chunks
+  uint64_t* d1_empty = bars + 10;     // leader: D1 drained by the group's warps of the pair
+  uint64_t* h_full = bars + 12;       // leader: hidden chunk written
+  uint64_t* h_empty = bars + 14;      // fc2 chunk has read H[slot] (commit)
+  uint64_t* d2_full = bars + 16;      // the tile's last fc2 complete (commit)
+  uint64_t* d2_empty = bars + 18;     // leader: D2[slot] read out by the final epilogue
+  uint64_t* w_full = bars + 20;       // [kWStages]
+  uint64_t* w_empty = w_full + L::kWStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_empty + L::kWStages);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int cluster_id = blockIdx.x / 2;
+  const int num_clusters = gridDim.x / 2;
+  const int num_tiles = (p.M + 127) / 128;
+  const int num_units = (num_tiles + 1) / 2;               // a unit = 2 consecutive 128-row tiles, one per CTA of the pair
+  const int n_my = (cluster_id < num_units) ? (num_units - cluster_id + num_clusters - 1) / num_clusters : 0;
+  auto tile_row0 = [&](int it) { return ((cluster_id + it * num_clusters) * 2 + static_cast<int>(rank)) * 128; };
+  constexpr int kGroupArrivals = 8 * 2;                    // eight warps per group, two CTAs
+
+  // ---- one-time setup
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+    sB1[i] = __float2half_rn(p.b1[i]);
+    if (i < 192) {
+      sB2[i] = p.b2[i];
+      sGamma2[i] = p.gamma2[i];
+      sBeta2[i] = p.beta2[i];
+      sGamma[i] = p.has_ln ? p.gamma[i] : 1.0f;
+      sBeta[i] = p.has_ln ? p.beta[i] : 0.0f;
+      sBp[i] = p.bp[i];
+    }
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    tma_prefetch_desc(&tmLn);
+    tma_prefetch_desc(&tmCtx);
+    tma_prefetch_desc(&tmWp);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&ctx_full[s], 1);
+      mbar_init(&proj_full[s], 1);
+      mbar_init(&a_full[s], kGroupArrivals);
+      mbar_init(&a_empty[s], 1);
+      mbar_init(&d1_full[s], 1);
+      mbar_init(&d1_empty[s], kGroupArrivals);
+      mbar_init(&h_full[s], kGroupArrivals);
+      mbar_init(&h_empty[s], 1);
+      mbar_init(&d2_full[s], 1);
+      mbar_init(&d2_empty[s], kGroupArrivals);
+    }
+    for (int i = 0; i < L::kWStages; ++i) {
+      mbar_init(&w_full[i], 1);
+      mbar_init(&w_empty[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_pair(tmem_ptr, 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  griddep_wait();
+  griddep_launch_dependents();
+  // event log: role 0 = UMMA issuer, 1 = first warp of group 0, 2 = first warp of group 1; entry = (tag << 48) | clock
+  int trace_n = 0;
+  auto trace = [&](int role, int tag) {
+    if (p.trace != nullptr && blockIdx.x == 0 && trace_n < 512) {
+      p.trace[role * 512 + trace_n++] = (static_cast<long long>(tag) << 48) | (clock64() & 0xFFFFFFFFFFFFLL);
+    }
+  };
+
+  if (warp == 0) {
+    // ================================================================= TMA producer (every CTA loads its own share)
+    if (lane == 0 && n_my > 0) {
+      int ws = 0;
+      uint32_t wph = 0;
+      auto load_panel = [&](const CUtensorMap* tm, int bytes, int c0, int c1) {
+        mbar_wait(&w_empty[ws], wph ^ 1);
+        if (leader) mbar_arrive_expect_tx(&w_full[ws], 2 * bytes);
+        tma_load_2d_pair(sW + ws * L::kWStage, tm, mapa_u32(smem_u32(&w_full[ws]), 0), c0, c1);
+        if (++ws == L::kWStages) { ws = 0; wph ^= 1; }
+      };
+      auto load_w1 = [&](int c) {        // W1 rows [c*128, c*128+128): this CTA stages 64 of them
+        for (int kp = 0; kp < 3; ++kp) load_panel(&tmW1, L::kW1Bytes, kp * 64, c * 128 + static_cast<int>(rank) * 64);
+      };
+      auto load_w2 = [&](int c) {        // W2 columns [c*128, c*128+128) of all 192 rows: this CTA stages 96 rows
+        for (int kp = 0; kp < 2; ++kp) load_panel(&tmW2, L::kWStage, c * 128 + kp * 64, static_cast<int>(rank) * 96);
+      };
+      auto load_wp = [&]() {             // Wproj [192 out, 192 in], three K panels, this CTA's 96 rows as three 32-row boxes
+        for (int kp = 0; kp < 3; ++kp) {
+          mbar_wait(&w_empty[ws], wph ^ 1);
+          if (leader) mbar_arrive_expect_tx(&w_full[ws], 2 * L::kWStage);
+          uint8_t* dst = sW + ws * L::kWStage;
+          for (int j = 0; j < 3; ++j)
+            tma_load_2d_pair(dst + j * 4096, &tmWp, mapa_u32(smem_u32(&w_full[ws]), 0), kp * 64, static_cast<int>(rank) * 96 + j * 32);
+          if (++ws == L::kWStages) { ws = 0; wph ^= 1; }
+        }
+      };
+      auto load_ctx = [&](int it) {      // attention output rows of tile `it` into A[slot] once the slot's previous tile is through fc1
+        const int s = it & 1, k = it >> 1;
+        mbar_wait(&a_empty[s], (k & 1) ^ 1);
+        if (leader) mbar_arrive_expect_tx(&ctx_full[s], 2 * L::kABytes);
+        const int m0 = tile_row0(it);
+        for (int kp = 0; kp < 3; ++kp)
+          tma_load_2d_pair(sA + s * L::kABytes + kp * 16384, &tmCtx, mapa_u32(smem_u32(&ctx_full[s]), 0), kp * 64, m0);
+      };
+      load_ctx(0);
+      load_wp();
+      load_w1(0);
+      for (int it = 0; it < n_my; ++it) {
+        for (int c = 0; c < 6; ++c) {
+          // the ctx tile does not go through the ring: its buffer has been free since the last fc1 of tile it-1
+          if (c == 0 && it + 1 < n_my) load_ctx(it + 1);
+          if (c < 5) load_w1(c + 1);
+          else if (it + 1 < n_my) load_w1(0);
+          if (c == kProjC && it + 1 < n_my) load_wp();
+          load_w2(c);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================= UMMA issuer (leader CTA only); the whole warp walks
+    // the loop with warp-uniform values, one elected lane issues (see mlp_fused.cuh)
+    if (leader && n_my > 0) {
+      constexpr uint32_t idesc1 = umma_idesc_bf16(256, 128, 0, 0);
+      constexpr uint32_t idesc2 = umma_idesc_f16(256, 192);
+      constexpr uint32_t idescP = umma_idesc_bf16(256, 192, 0, 0);
+      const bool issuer = elect_one();
+      int ws = 0;
+      uint32_t wph = 0;
+      const uint32_t a_lo0 = umma_desc_lo(smem_u32(sA));
+      const uint32_t h_lo0 = umma_desc_lo(smem_u32(sH));
+      const uint32_t w_lo0 = umma_desc_lo(smem_u32(sW));
+      auto commit = [&](uint64_t* bar) {
+        if (issuer) umma_commit_pair(bar);
+      };
+      // one weight panel = 4 MMAs of K = 16
+      auto panel_mmas = [&](uint32_t d, uint32_t a_lo, uint32_t idesc, bool acc_first) {
+        mbar_wait(&w_full[ws], wph);
+        tc_fence_after();
+        const uint32_t b_lo = w_lo0 + ws * (L::kWStage >> 4);
+        if (issuer) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma_f16_split<2>(d, a_lo + 2 * k, b_lo + 2 * k, idesc, (acc_first || k != 0) ? 1u : 0u);
+        }
+        __syncwarp();
+        commit(&w_empty[ws]);
+        if (++ws == L::kWStages) { ws = 0; wph ^= 1; }
+      };
+      auto fc1 = [&](int it, int c) {
+        const int s = it & 1;
+#pragma unroll
+        for (int kp = 0; kp < 3; ++kp) panel_mmas(tmem_base, a_lo0 + (s * L::kABytes + kp * 16384) / 16, idesc1, kp != 0);
+        commit(&d1_full[s]);
+        if (c == 5) commit(&a_empty[s]);
+      };
+      auto fc2 = [&](int it, int c) {    // accumulates on top of the parked residual row
+        const int s = it & 1;
+#pragma unroll
+        for (int kp = 0; kp < 2; ++kp) panel_mmas(tmem_base + 128 + s * 192, h_lo0 + (s * L::kHBytes + kp * 16384) / 16, idesc2, true);
+        commit(&h_empty[s]);
+        if (c == 5) commit(&d2_full[s]);
+      };
+      auto proj = [&](int it) {
+        const int s = it & 1, k = it >> 1;
+        mbar_wait(&ctx_full[s], k & 1);
+        if (k > 0) mbar_wait(&d2_empty[s], (k - 1) & 1);
+        tc_fence_after();
+        if (lane == 0) trace(0, 7);
+#pragma unroll
+        for (int kp = 0; kp < 3; ++kp) panel_mmas(tmem_base + 128 + s * 192, a_lo0 + (s * L::kABytes + kp * 16384) / 16, idescP, kp != 0);
+        commit(&proj_full[s]);
+      };
+      proj(0);
+      mbar_wait(&a_full[0], 0);
+      tc_fence_after();
+      fc1(0, 0);
+      for (int it = 0; it < n_my; ++it) {
+        const int s = it & 1, k = it >> 1;
+#pragma unroll 1
+        for (int c = 0; c < 6; ++c) {
+          const uint32_t j = static_cast<uint32_t>(k * 6 + c);
+          if (c < 5) {
+            mbar_wait(&d1_empty[s], j & 1);
+            tc_fence_after();
+            if (lane == 0) trace(0, 1);
+            fc1(it, c + 1);
+            if (lane == 0) trace(0, 5);
+          } else if (it + 1 < n_my) {
+            mbar_wait(&a_full[s ^ 1], ((it + 1) >> 1) & 1);
+            mbar_wait(&d1_empty[s], j & 1);
+            tc_fence_after();
+            if (lane == 0) trace(0, 2);
+            fc1(it + 1, 0);
+          }
+          if (c == kProjC && it + 1 < n_my) {
+            proj(it + 1);
+            if (lane == 0) trace(0, 4);
+          }
+          mbar_wait(&h_full[s], j & 1);
+          tc_fence_after();
+          if (lane == 0) trace(0, 3);
+          fc2(it, c);
+          if (lane == 0) trace(0, 6);
+        }
+      }
+    }
+  } else if (warp >= 3) {
+    // ================================================================= epilogue warps: two groups, one per tile slot
+    const int ew = warp - 3;
+    const int grp = ew >> 3;                            // == slot of the tiles this group owns
+    const int team = (ew >> 2) & 1;
+    const int quad = warp & 3;                          // TMEM lane quadrant this warp may access
+    const int row = quad * 32 + lane;                   // token row of the tile == TMEM lane
+    const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
+    const uint32_t bar_id = 2 + grp * 4 + quad;         // the two warps (teams) of this group that share the 32 rows
+    const bool tr = (ew == grp * 8 && lane == 0);
+    const int trole = 1 + grp;
+    const uint32_t af_l = mapa_u32(smem_u32(&a_full[grp]), 0);
+    const uint32_t d1e_l = mapa_u32(smem_u32(&d1_empty[grp]), 0);
+    const uint32_t hf_l = mapa_u32(smem_u32(&h_full[grp]), 0);
+    const uint32_t d2e_l = mapa_u32(smem_u32(&d2_empty[grp]), 0);
+    uint8_t* sAg = sA + grp * L::kABytes;
+    uint8_t* sHg = sH + grp * L::kHBytes;
+    const uint32_t tD1 = tmem_base + lane_sel + 64 * team;
+    const uint32_t tD2 = tmem_base + lane_sel + 128 + grp * 192 + 96 * team;
+    uint32_t part_use = 0;
+
+    // (sum, sumsq) of this thread's 96 columns -> (mean, rstd) of the row
+    auto row_stats = [&](float s, float ss, float& mean, float& rstd) {
+      float2* part = sPart + ((part_use & 1) * 2 + grp) * 2 * 128;
+      ++part_use;
+      part[team * 128 + row] = make_float2(s, ss);
+      named_bar_sync(bar_id, 64);
+      const float2 o = part[(team ^ 1) * 128 + row];
+      const float ts = s + o.x, tss = ss + o.y;
+      mean = ts * (1.0f / 192.0f);
+      rstd = rsqrtf(fmaxf(tss * (1.0f / 192.0f) - mean * mean, 0.0f) + p.eps);
+    };
+    // LayerNorm of N8*8 consecutive columns starting at column `col` (a multiple of 8) -> bf16 -> the K-major swizzled
+    // panel tile at `dst` (panel = 64 columns = 16 KB); panel_shift re-bases the panel index (ln_out staging, second round)
+    auto store_ln = [&](uint8_t* dst, const float* x, int n8, int col, int panel_shift, float mean, float rstd, const float* gam,
+                        const float* bet) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        if (j < n8) {
+          const int g = (col >> 3) + j;
+          float o[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = fmaf((x[j * 8 + e] - mean) * rstd, gam[col + j * 8 + e], bet[col + j * 8 + e]);
+          *reinterpret_cast<uint4*>(dst + ((g >> 3) - panel_shift) * 16384 + sw128_offset(row, g & 7)) =
+              make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+        }
+      }
+    };
+    auto ld48 = [&](uint32_t taddr, float (&x)[48]) {
+      float v[32];
+      tmem_ld32(taddr, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) x[i] = v[i];
+      float w[16];
+      tmem_ld16(taddr + 32, w);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) x[32 + i] = w[i];
+    };
+    auto prefetch_rows = [&](int it) {               // this thread's row of tile `it`: one 128-byte line per 8 lanes
+      const int grow = tile_row0(it) + row;
+      if (grow < p.M && (lane & 7) == 0) {
+        const float* xp = p.x_in + xt_offset(grow, 0, 0) + 24 * team * 128;
+#pragma unroll
+        for (int j = 0; j < 24; ++j) prefetch_l2(xp + j * 128);
+      }
+    };
+
+    // LayerNorm-on-load of tile `it`: x_mid = x + projection + bp parked in D2[slot], LayerNorm2(x_mid) -> A[slot]
+    auto produce_a = [&](int it) {
+      const int k = it >> 1;
+      const int grow = tile_row0(it) + row;
+      const bool valid = grow < p.M;
+      const float* src = p.x_in + xt_offset(valid ? grow : 0, 0, 0) + 24 * team * 128;
+      if (tr) trace(trole, 30);
+      float s = 0.0f, ss = 0.0f;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        float x[48];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid) r = *reinterpret_cast<const float4*>(src + (12 * h + i) * 128);
+          x[i * 4 + 0] = r.x; x[i * 4 + 1] = r.y; x[i * 4 + 2] = r.z; x[i * 4 + 3] = r.w;
+        }
+        if (h == 0) {
+          mbar_wait(&proj_full[grp], k & 1);
+          tc_fence_after();
+          if (tr) trace(trole, 31);
+        }
+        const int cb = 96 * team + 48 * h;
+        {
+          float v[32];
+          tmem_ld32(tD2 + 48 * h, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] += v[i] + sBp[cb + i];
+        }
+        {
+          float v[16];
+          tmem_ld16(tD2 + 48 * h + 32, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) x[32 + i] += v[i] + sBp[cb + 32 + i];
+        }
+        {
+          float v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = x[i];
+          tmem_st32(tD2 + 48 * h, v);
+        }
+        tmem_st16(tD2 + 48 * h + 32, &x[32]);
+#pragma unroll
+        for (int i = 0; i < 48; ++i) { s += x[i]; ss = fmaf(x[i], x[i], ss); }
+      }
+      if (tr) trace(trole, 32);
+      float mean, rstd;
+      row_stats(s, ss, mean, rstd);
+      if (tr) trace(trole, 33);
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        float x[48];
+        ld48(tD2 + 48 * h, x);
+        store_ln(sAg, x, 6, 96 * team + 48 * h, 0, mean, rstd, sGamma2, sBeta2);
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(af_l);
+      if (tr) trace(trole, 34);
+    };
+
+    // final epilogue of tile `it`: x_out = D2 + b2 (D2 = x_mid + fc2), ln_out = LayerNorm(x_out) through H[slot] and TMA.
+    // D2[slot] is released after the FIRST pass (the projection of the slot's next tile is waiting for it); the normalising
+    // pass re-reads the rows this thread has just written to x_out (L2 hits)
+    auto final_tile = [&](int it) {
+      const int k = it >> 1;
+      const int m0 = tile_row0(it);
+      const int grow = m0 + row;
+      const bool valid = grow < p.M;
+      float* dstx = p.x_out + xt_offset(valid ? grow : 0, 0, 0) + 24 * team * 128;
+      if (tr) trace(trole, 40);
+      mbar_wait(&d2_full[grp], k & 1);
+      tc_fence_after();
+      if (tr) trace(trole, 41);
+      float s = 0.0f, ss = 0.0f;
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        float x[48];
+        ld48(tD2 + 48 * h, x);
+        const int cb = 96 * team + 48 * h;
+#pragma unroll
+        for (int i = 0; i < 48; ++i) { x[i] += sB2[cb + i]; s += x[i]; ss = fmaf(x[i], x[i], ss); }
+        if (valid) {
+#pragma unroll
+          for (int i = 0; i < 12; ++i)
+            *reinterpret_cast<float4*>(dstx + (12 * h + i) * 128) = make_float4(x[i * 4], x[i * 4 + 1], x[i * 4 + 2], x[i * 4 + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(d2e_l);
+      if (tr) trace(trole, 42);
+      if (!p.has_ln) return;
+      float mean, rstd;
+      row_stats(s, ss, mean, rstd);
+      if (tr) trace(trole, 43);
+      // n4 float4 slots of this thread's row, starting at slot f0 of its 24
+      auto reload = [&](float* x, int f0, int n4) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          if (i < n4) {
+            float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) r = *reinterpret_cast<const float4*>(dstx + (f0 + i) * 128);
+            x[i * 4 + 0] = r.x; x[i * 4 + 1] = r.y; x[i * 4 + 2] = r.z; x[i * 4 + 3] = r.w;
+          }
+        }
+      };
+      // ln_out leaves through H[slot] (idle between the tile's last fc2 and the group's next GELU chunk): 32 KB = panels 0 and
+      // 1 in the first round (team 0: columns 0..95, team 1: columns 96..127), panel 2 (team 1: columns 128..191) in the second
+      if (team == 0) {
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+          float x[48];
+          reload(x, 12 * h, 12);
+          store_ln(sHg, x, 6, 48 * h, 0, mean, rstd, sGamma, sBeta);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 64);
+        if (lane == 0) {
+          if (m0 + quad * 32 < p.M) {
+            tma_store_2d(&tmLn, sHg + quad * 4096, 0, m0 + quad * 32);
+            tma_store_2d(&tmLn, sHg + 16384 + quad * 4096, 64, m0 + quad * 32);
+          }
+          tma_store_commit();
+          tma_store_wait_read<0>();
+        }
+        __syncwarp();
+        named_bar_sync(bar_id, 64);                       // staging panel 0 may be overwritten (second round)
+      } else {
+        float y0[32], y1[32];                             // columns 128..159 / 160..191, normalised in the second round
+        {
+          float x[32];
+          reload(x, 0, 8);                                // columns 96..127
+          reload(y0, 8, 8);
+          reload(y1, 16, 8);
+          store_ln(sHg, x, 4, 96, 0, mean, rstd, sGamma, sBeta);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(bar_id, 64);
+        named_bar_sync(bar_id, 64);                       // team 0's store has read panels 0 and 1
+        store_ln(sHg, y0, 4, 128, 2, mean, rstd, sGamma, sBeta);
+        store_ln(sHg, y1, 4, 160, 2, mean, rstd, sGamma, sBeta);
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (m0 + quad * 32 < p.M) tma_store_2d(&tmLn, sHg + quad * 4096, 128, m0 + quad * 32);
+          tma_store_commit();
+          tma_store_wait_read<0>();                       // H[slot] may be overwritten by the group's next GELU chunk
+        }
+        __syncwarp();
+      }
+      if (tr) trace(trole, 44);
+    };
+
+    // one hidden chunk: D1 (this team's 64 columns) -> GELU -> fp16 K-major panel `team` of H[slot]
+    auto gelu_chunk = [&](int it, int c) {
+      const uint32_t j = static_cast<uint32_t>((it >> 1) * 6 + c);
+      if (tr) trace(trole, 10);
+      mbar_wait(&d1_full[grp], j & 1);
+      tc_fence_after();
+      if (tr) trace(trole, 12);
+      uint8_t* panel = sHg + team * 16384;
+      const uint4* bb = reinterpret_cast<const uint4*>(sB1 + c * 128 + team * 64);
+      auto gelu32 = [&](const float (&v)[32], int half, uint32_t (&o)[16]) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 bq = bb[half * 4 + q];                     // 8 fp16 biases
+          const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __half2 hx = __floats2half2_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
+            hx = __hadd2(hx, *reinterpret_cast<const __half2*>(&bw[e]));
+            const __half2 g = gelu_erf_h2(hx);
+            o[q * 4 + e] = *reinterpret_cast<const uint32_t*>(&g);
+          }
+        }
+      };
+      auto store16 = [&](const uint32_t (&o)[16], int half) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(panel + sw128_offset(row, half * 4 + q)) = make_uint4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
+      };
+      uint32_t o[16];
+      {
+        float v[32];
+        tmem_ld32(tD1, v);
+        gelu32(v, 0, o);
+      }
+      if (tr) trace(trole, 11);
+      mbar_wait(&h_empty[grp], (j & 1) ^ 1);               // the previous chunk's fc2 has read H[slot]
+      if (tr) trace(trole, 14);
+      store16(o, 0);
+      {
+        float v[32];
+        tmem_ld32(tD1 + 32, v);
+        tc_fence_before();                                 // D1 is in registers: the next fc1 may overwrite it
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(d1e_l);
+        gelu32(v, 1, o);
+      }
+      store16(o, 1);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(hf_l);
+      if (tr) trace(trole, 13);
+    };
+
+    if (grp < n_my) {
+      prefetch_rows(grp);
+      produce_a(grp);
+    }
+    for (int it = grp; it < n_my; it += 2) {
+      if (it + 2 < n_my) prefetch_rows(it + 2);
+#pragma unroll 1
+      for (int c = 0; c < 6; ++c) gelu_chunk(it, c);
+      final_tile(it);
+      if (it + 2 < n_my) produce_a(it + 2);
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  // ---- teardown
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, 512);
+}
+
+#endif  // __CUDACC__

@@ -89,7 +89,7 @@ def test_mlp_fused_no_layernorm_in_place(G):
     run_case(197 * 40, G, True, seed=8, inplace=True)
 
 
-@pytest.mark.parametrize('G', [1, 2])
+@pytest.mark.parametrize('G', [1, 2, 4])
 @pytest.mark.parametrize('M', [128, 300, 1000, 197 * 64, 197 * 300 + 5])
 def test_attn_proj_mlp_fused(M, G):
     """rvk_attn_proj_mlp_fused: x + proj(ctx) computed in the idle TMEM columns, then the MLP half on the new rows."""

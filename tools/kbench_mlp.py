@@ -61,9 +61,9 @@ if os.environ.get('MLP_TRACE'):
     torch.cuda.synchronize()
     _lib.load().rvk_debug_set_mlp_trace(0)
     t = tr.cpu().view(4, 512)
-    for role, name in ((0, 'mma'), (1, 'epi')):
+    for role, name in ((0, 'mma'), (1, 'epi'), (2, 'epi1')):
         ev = [(int(v) >> 48, int(v) & 0xFFFFFFFFFFFF) for v in t[role].tolist() if v != 0]
         if not ev:
             continue
         t0 = ev[0][1]
-        print(name, ' '.join(f'{tag}@{(c - t0)}' for tag, c in ev[:140]))
+        print(name, ' '.join(f'{tag}@{(c - t0)}' for tag, c in ev[:400]))
