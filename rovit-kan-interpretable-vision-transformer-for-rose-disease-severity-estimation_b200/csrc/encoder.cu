@@ -215,7 +215,7 @@ SideStream* side_stream_for_current_device() {
 int mlp_cta_group() {
   static const int g = [] {
     const char* e = getenv("RVK_MLP_CTA_GROUP");
-    return (e != nullptr && e[0] == '1') ? 1 : 2;
+    return (e != nullptr && e[0] == '1') ? 1 : (e != nullptr && e[0] == '2') ? 2 : 4;   // 4 = CTA pairs, two row tiles in flight
   }();
   return g;
 }
@@ -320,7 +320,7 @@ int rvk_encoder_forward_impl(const void* const* params, const void* wbuf, const 
         MlpFusedArgs m;
         m.w1 = at(wbuf, W.fc1[i]); m.w2_f16 = at(wbuf, W.fc2h[i]);
         m.ln_out = last ? nullptr : ln;
-        m.cta_group = mlp_cta_group();
+        m.cta_group = (mlp_cta_group() == 4 && !fuse_proj()) ? 2 : mlp_cta_group();   // 4 (two tiles in flight) needs the folded projection
         m.p.M = M; m.p.x_in = x; m.p.x_out = x;
         m.p.gamma2 = P(params, bp(i, B_N2W)); m.p.beta2 = P(params, bp(i, B_N2B));
         m.p.b1 = P(params, bp(i, B_FC1B)); m.p.b2 = P(params, bp(i, B_FC2B));

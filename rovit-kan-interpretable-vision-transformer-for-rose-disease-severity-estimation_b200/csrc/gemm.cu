@@ -184,14 +184,14 @@ static int launch_mlp_fused(const MlpFusedArgs& a, cudaStream_t stream) {
 }
 
 // two row tiles in flight per CTA pair (mlp_fused2.cuh); needs the folded attention projection
-template <int kProjC>
+template <int kProjQ, int kVar>
 static int launch_mlp_fused2(const MlpFusedArgs& a, cudaStream_t stream) {
   using L = Mlp2Smem;
-  auto kernel = mlp_fused2_kernel<kProjC>;
+  auto kernel = mlp_fused2_kernel<kProjQ, kVar>;
   RVK_SET_MAX_SMEM(kernel, L::kTotal);
   const MlpFusedParams& p = a.p;
   CUtensorMap tmW1, tmW2, tmLn, tmCtx, tmWp;
-  RVK_TRY(rvk_make_tmap_2d(&tmW1, a.w1, RVK_BF16, 768, 192, 192, 64, 64));
+  RVK_TRY(rvk_make_tmap_2d(&tmW1, a.w1, RVK_BF16, 768, 192, 192, 32, 64));
   RVK_TRY(rvk_make_tmap_2d(&tmW2, a.w2_f16, RVK_BF16 /* 2-byte elements */, 192, 768, 768, 96, 64));
   tmLn = tmW1;
   if (p.has_ln) RVK_TRY(rvk_make_tmap_2d(&tmLn, a.ln_out, RVK_BF16, p.M, 192, 192, 32, 64));
@@ -203,7 +203,7 @@ static int launch_mlp_fused2(const MlpFusedArgs& a, cudaStream_t stream) {
   const int clusters = units < max_clusters ? units : max_clusters;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * 2);
-  cfg.blockDim = dim3(kMlpThreads);
+  cfg.blockDim = dim3(kMlp2Threads);
   cfg.dynamicSmemBytes = L::kTotal;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
@@ -220,12 +220,16 @@ static int launch_mlp_fused2(const MlpFusedArgs& a, cudaStream_t stream) {
   return rvk_launch_check();
 }
 
-static int mlp2_proj_chunk() {      // RVK_MLP2_PROJC=0..3: chunk of tile i at which the projection of tile i+1 is issued (A/B runs)
-  static const int c = [] {
-    const char* e = getenv("RVK_MLP2_PROJC");
-    return (e != nullptr && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 2;
-  }();
-  return c;
+static int mlp2_env(const char* name, int lo, int hi, int dflt) {
+  const char* e = getenv(name);
+  return (e != nullptr && e[0] >= '0' + lo && e[0] <= '0' + hi) ? e[0] - '0' : dflt;
+}
+// A/B switches of the two-tile kernel: RVK_MLP2_PROJQ=3..5 (half-chunk of tile i at which the projection of tile i+1 is issued),
+// RVK_MLP2_VAR=0..3 (mlp_fused2.cuh: kVar)
+template <int kVar>
+static int launch_mlp_fused2_q(const MlpFusedArgs& a, cudaStream_t stream) {
+  static const int q = mlp2_env("RVK_MLP2_PROJQ", 3, 5, 4);
+  return q == 3 ? launch_mlp_fused2<3, kVar>(a, stream) : q == 5 ? launch_mlp_fused2<5, kVar>(a, stream) : launch_mlp_fused2<4, kVar>(a, stream);
 }
 
 int rvk_mlp_fused_launch(const MlpFusedArgs& a, cudaStream_t stream) {
@@ -240,8 +244,13 @@ int rvk_mlp_fused_launch(const MlpFusedArgs& a, cudaStream_t stream) {
   if (a.cta_group == 2) return launch_mlp_fused<2>(a, stream);
   if (a.cta_group == 4) {           // CTA pairs, two row tiles in flight
     if (!p.has_proj) return RVK_ERR_BAD_ARG;
-    const int c = mlp2_proj_chunk();
-    return c == 0 ? launch_mlp_fused2<0>(a, stream) : c == 1 ? launch_mlp_fused2<1>(a, stream) : c == 3 ? launch_mlp_fused2<3>(a, stream) : launch_mlp_fused2<2>(a, stream);
+    static const int var = mlp2_env("RVK_MLP2_VAR", 0, 3, 0);
+    switch (var) {
+      case 1: return launch_mlp_fused2_q<1>(a, stream);
+      case 2: return launch_mlp_fused2_q<2>(a, stream);
+      case 3: return launch_mlp_fused2_q<3>(a, stream);
+      default: return launch_mlp_fused2_q<0>(a, stream);
+    }
   }
   return RVK_ERR_BAD_ARG;
 }

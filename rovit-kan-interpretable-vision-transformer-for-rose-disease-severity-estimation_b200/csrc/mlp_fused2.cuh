@@ -11,32 +11,36 @@
 // pipe with GELU chunks of tile i, group 1 drains tile i-1 and prepares tile i+1.
 //
 // What makes two tiles fit:
-//   TMEM (512 columns): D1 [0,128) = ONE fc1 accumulator (drained into registers half way through a GELU chunk, so the next
-//         fc1 runs under the GELU arithmetic), D2[slot] [128+192*slot, +192) = per-tile accumulator that carries, in turn,
-//         the attention projection (read by the LayerNorm-on-load), then the projected residual row x_mid PARKED by
-//         tcgen05.st, then fc2 accumulating on top of it: the final epilogue reads x_mid + fc2(..) in one piece, so
-//         neither x_mid nor a residual re-read touches memory (HBM/L2 traffic per row: x in, ctx in, x out, ln out only).
-//   smem: A[slot] 2 x 48 KB (ctx tile, then the normalised rows), H[slot] 2 x 32 KB (one 128-column hidden chunk; reused as the
-//         staging buffer of ln_out in two rounds), a 4-stage ring of 12 KB weight panels.
+//   TMEM (512 columns): D1 [0,128) = two fc1 accumulators of 64 columns (the hidden dimension is walked in twelve half-chunks
+//         of 64; fc1 of half-chunk q+2 runs under the GELU arithmetic of q+1), D2[slot] [128+192*slot, +192) = per-tile
+//         accumulator that carries, in turn, the attention projection (read by the LayerNorm-on-load), then the projected
+//         residual row x_mid PARKED by tcgen05.st, then fc2 accumulating on top of it: the final epilogue reads
+//         x_mid + fc2(..) in one piece, so neither x_mid nor a residual re-read touches memory (HBM/L2 traffic per row:
+//         x in, ctx in, x out, ln out only).
+//   smem: A[slot] 2 x 48 KB (ctx tile, then the normalised rows), H[slot] 2 x 2 x 16 KB (two 64-column hidden panels per tile,
+//         ping-pong; reused as the staging buffer of ln_out in two rounds), a 4-stage ring of 12 KB weight stages (one stage
+//         = the three K panels of a W1 half-chunk, or one K panel of W2 / Wproj).
 //   registers: a thread owns 96 columns of a row in the LayerNorm phases; it walks them as two pieces of 48 and re-reads the
-//         pieces from TMEM for the second (normalising) pass instead of keeping them.
-// The tensor-pipe program is static and identical in the producer and the issuer (tiles in order; inside tile i:
-// fc1(c+1) | [projection of tile i+1 at chunk kProjC] | fc2(c); the first fc1 of tile i+1 goes in front of the last fc2).
+//         pieces (from TMEM on load, from its own x_out rows in the final epilogue) for the normalising pass.
+// The tensor-pipe program is static and identical in the producer and the issuer (tiles in order; inside tile i, per
+// half-chunk q: fc1(q+2) | [projection of tile i+1 at q = kProjQ] | fc2(q); the first two fc1 of tile i+1 take the place of
+// fc1(12), fc1(13)).
 //
-// Warp roles (608 threads): w0 TMA producer, w1 UMMA issuer (leader CTA) + TMEM owner, w2 idle, w3..w10 group 0, w11..w18
-// group 1; inside a group: team = 64-column half of a hidden chunk / 96-column half of a token row, quad = TMEM lane quadrant.
+// Warp roles (576 threads, 112 registers each): w0 TMA producer, w1 UMMA issuer (leader CTA) + TMEM owner, w2..w9 group 0,
+// w10..w17 group 1; inside a group: team = 32-column half of a hidden half-chunk / 96-column half of a token row, quad = TMEM lane quadrant.
 #pragma once
 
 #include <cuda_fp16.h>
 
 #include "mlp_fused.cuh"
 
+constexpr int kMlp2Threads = (2 + 16) * 32;   // 576
+
 struct Mlp2Smem {
   static constexpr int kABytes = 3 * 16384;                 // per slot: three [128 x 64] K panels
-  static constexpr int kHBytes = 2 * 16384;                 // per slot: one hidden chunk = two K panels
-  static constexpr int kWStage = 12288;                     // this CTA's half of a W2 / Wproj panel [96 x 64]; W1 halves [64 x 64] use 2/3
+  static constexpr int kHBytes = 2 * 16384;                 // per slot: two hidden half-chunk panels [128 x 64] fp16 (ping-pong)
+  static constexpr int kWStage = 12288;                     // this CTA's half of a W2 / Wproj panel [96 x 64], or of three W1 panels [32 x 64]
   static constexpr int kWStages = 4;
-  static constexpr int kW1Bytes = 8192;
   static constexpr int kVecBytes = 768 * 2 + 6 * 192 * 4;   // b1 (fp16); b2, gamma2, beta2, gamma, beta, bp (fp32)
   static constexpr int kPartBytes = 2 * 2 * 2 * 128 * 8;    // LayerNorm partial (sum, sumsq): [use parity][group][team][row]
   static constexpr int kBarBytes = 256;
@@ -58,10 +62,12 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-// kProjC: the hidden chunk of tile i at which the projection of tile i+1 is issued (its D2 slot must have been drained by the
+// kVar (measurement switches): bit 0 = the final epilogue's normalising pass re-reads D2 from TMEM (D2 released after it)
+// instead of the x_out rows from L2; bit 1 = the two 48-column pieces of the LayerNorm passes fully unrolled.
+// kProjQ: the hidden half-chunk (0..11) of tile i at which the projection of tile i+1 is issued (its D2 slot must have been drained by the
 // other group's final epilogue of tile i-1 by then, and the LayerNorm-on-load of tile i+1 must fit behind it)
-template <int kProjC>
-__global__ void __launch_bounds__(kMlpThreads, 1)
+template <int kProjQ, int kVar>
+__global__ void __launch_bounds__(kMlp2Threads, 1)
 mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
                   const __grid_constant__ CUtensorMap tmLn, const __grid_constant__ CUtensorMap tmCtx,
                   const __grid_constant__ CUtensorMap tmWp, const MlpFusedParams p) {
@@ -85,13 +91,13 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
   uint64_t* proj_full = bars + 2;     // projection accumulator complete (commit, both CTAs)
   uint64_t* a_full = bars + 4;        // leader: A operand written (and x_mid parked in D2[slot]) by the group's warps of the pair
   uint64_t* a_empty = bars + 6;       // the tile's last fc1 has read A[slot] (commit)
-  uint64_t* d1_full = bars + 8;       // fc1 chunk complete (commit); per slot so that each group counts its own chunks
-  uint64_t* d1_empty = bars + 10;     // leader: D1 drained by the group's warps of the pair
-  uint64_t* h_full = bars + 12;       // leader: hidden chunk written
-  uint64_t* h_empty = bars + 14;      // fc2 chunk has read H[slot] (commit)
-  uint64_t* d2_full = bars + 16;      // the tile's last fc2 complete (commit)
-  uint64_t* d2_empty = bars + 18;     // leader: D2[slot] read out by the final epilogue
-  uint64_t* w_full = bars + 20;       // [kWStages]
+  uint64_t* d2_full = bars + 8;       // the tile's last fc2 complete (commit)
+  uint64_t* d2_empty = bars + 10;     // leader: D2[slot] read out by the final epilogue
+  // per slot and buffer [2][2] (index slot * 2 + buffer; each group counts the uses of a buffer by its own tiles):
+  uint64_t* d1_full = bars + 12;      // fc1 half-chunk complete in D1[buffer] (commit)
+  uint64_t* gelu_done = bars + 16;    // leader: D1[buffer] drained and H[slot][buffer] written by the group's warps of the pair
+  uint64_t* h_empty = bars + 20;      // fc2 has read H[slot][buffer] (commit)
+  uint64_t* w_full = bars + 24;       // [kWStages]
   uint64_t* w_empty = w_full + L::kWStages;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_empty + L::kWStages);
 
@@ -130,12 +136,13 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       mbar_init(&proj_full[s], 1);
       mbar_init(&a_full[s], kGroupArrivals);
       mbar_init(&a_empty[s], 1);
-      mbar_init(&d1_full[s], 1);
-      mbar_init(&d1_empty[s], kGroupArrivals);
-      mbar_init(&h_full[s], kGroupArrivals);
-      mbar_init(&h_empty[s], 1);
       mbar_init(&d2_full[s], 1);
       mbar_init(&d2_empty[s], kGroupArrivals);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&d1_full[i], 1);
+      mbar_init(&gelu_done[i], kGroupArrivals);
+      mbar_init(&h_empty[i], 1);
     }
     for (int i = 0; i < L::kWStages; ++i) {
       mbar_init(&w_full[i], 1);
@@ -166,17 +173,19 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
     if (lane == 0 && n_my > 0) {
       int ws = 0;
       uint32_t wph = 0;
-      auto load_panel = [&](const CUtensorMap* tm, int bytes, int c0, int c1) {
+      auto load_w1 = [&](int q) {        // W1 rows [q*64, q*64+64), all of K: this CTA stages 32 of them, one stage = three K panels
         mbar_wait(&w_empty[ws], wph ^ 1);
-        if (leader) mbar_arrive_expect_tx(&w_full[ws], 2 * bytes);
-        tma_load_2d_pair(sW + ws * L::kWStage, tm, mapa_u32(smem_u32(&w_full[ws]), 0), c0, c1);
+        if (leader) mbar_arrive_expect_tx(&w_full[ws], 2 * L::kWStage);
+        uint8_t* dst = sW + ws * L::kWStage;
+        for (int kp = 0; kp < 3; ++kp)
+          tma_load_2d_pair(dst + kp * 4096, &tmW1, mapa_u32(smem_u32(&w_full[ws]), 0), kp * 64, q * 64 + static_cast<int>(rank) * 32);
         if (++ws == L::kWStages) { ws = 0; wph ^= 1; }
       };
-      auto load_w1 = [&](int c) {        // W1 rows [c*128, c*128+128): this CTA stages 64 of them
-        for (int kp = 0; kp < 3; ++kp) load_panel(&tmW1, L::kW1Bytes, kp * 64, c * 128 + static_cast<int>(rank) * 64);
-      };
-      auto load_w2 = [&](int c) {        // W2 columns [c*128, c*128+128) of all 192 rows: this CTA stages 96 rows
-        for (int kp = 0; kp < 2; ++kp) load_panel(&tmW2, L::kWStage, c * 128 + kp * 64, static_cast<int>(rank) * 96);
+      auto load_w2 = [&](int q) {        // W2 columns [q*64, q*64+64) of all 192 rows: this CTA stages 96 rows
+        mbar_wait(&w_empty[ws], wph ^ 1);
+        if (leader) mbar_arrive_expect_tx(&w_full[ws], 2 * L::kWStage);
+        tma_load_2d_pair(sW + ws * L::kWStage, &tmW2, mapa_u32(smem_u32(&w_full[ws]), 0), q * 64, static_cast<int>(rank) * 96);
+        if (++ws == L::kWStages) { ws = 0; wph ^= 1; }
       };
       auto load_wp = [&]() {             // Wproj [192 out, 192 in], three K panels, this CTA's 96 rows as three 32-row boxes
         for (int kp = 0; kp < 3; ++kp) {
@@ -199,14 +208,15 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       load_ctx(0);
       load_wp();
       load_w1(0);
+      load_w1(1);
       for (int it = 0; it < n_my; ++it) {
-        for (int c = 0; c < 6; ++c) {
+        for (int q = 0; q < 12; ++q) {
           // the ctx tile does not go through the ring: its buffer has been free since the last fc1 of tile it-1
-          if (c == 0 && it + 1 < n_my) load_ctx(it + 1);
-          if (c < 5) load_w1(c + 1);
-          else if (it + 1 < n_my) load_w1(0);
-          if (c == kProjC && it + 1 < n_my) load_wp();
-          load_w2(c);
+          if (q == 0 && it + 1 < n_my) load_ctx(it + 1);
+          if (q < 10) load_w1(q + 2);
+          else if (it + 1 < n_my) load_w1(q - 10);
+          if (q == kProjQ && it + 1 < n_my) load_wp();
+          load_w2(q);
         }
       }
     }
@@ -214,7 +224,7 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
     // ================================================================= UMMA issuer (leader CTA only); the whole warp walks
     // the loop with warp-uniform values, one elected lane issues (see mlp_fused.cuh)
     if (leader && n_my > 0) {
-      constexpr uint32_t idesc1 = umma_idesc_bf16(256, 128, 0, 0);
+      constexpr uint32_t idesc1 = umma_idesc_bf16(256, 64, 0, 0);
       constexpr uint32_t idesc2 = umma_idesc_f16(256, 192);
       constexpr uint32_t idescP = umma_idesc_bf16(256, 192, 0, 0);
       const bool issuer = elect_one();
@@ -226,32 +236,33 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       auto commit = [&](uint64_t* bar) {
         if (issuer) umma_commit_pair(bar);
       };
-      // one weight panel = 4 MMAs of K = 16
-      auto panel_mmas = [&](uint32_t d, uint32_t a_lo, uint32_t idesc, bool acc_first) {
+      // one ring stage: NP K panels (4 MMAs of K = 16 each); A panels 16 KB apart, B panels b_step bytes apart inside the stage
+      auto stage_mmas = [&](uint32_t d, uint32_t a_lo, uint32_t idesc, int np, uint32_t b_step, bool acc_first) {
         mbar_wait(&w_full[ws], wph);
         tc_fence_after();
         const uint32_t b_lo = w_lo0 + ws * (L::kWStage >> 4);
         if (issuer) {
+          for (int kp = 0; kp < np; ++kp) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma_f16_split<2>(d, a_lo + 2 * k, b_lo + 2 * k, idesc, (acc_first || k != 0) ? 1u : 0u);
+            for (int k = 0; k < 4; ++k)
+              umma_f16_split<2>(d, a_lo + kp * (16384 >> 4) + 2 * k, b_lo + kp * (b_step >> 4) + 2 * k, idesc, (acc_first || (kp | k) != 0) ? 1u : 0u);
+          }
         }
         __syncwarp();
         commit(&w_empty[ws]);
         if (++ws == L::kWStages) { ws = 0; wph ^= 1; }
       };
-      auto fc1 = [&](int it, int c) {
-        const int s = it & 1;
-#pragma unroll
-        for (int kp = 0; kp < 3; ++kp) panel_mmas(tmem_base, a_lo0 + (s * L::kABytes + kp * 16384) / 16, idesc1, kp != 0);
-        commit(&d1_full[s]);
-        if (c == 5) commit(&a_empty[s]);
+      auto fc1 = [&](int it, int q) {     // half-chunk q of tile it -> D1[q & 1] (64 columns)
+        const int s = it & 1, b = q & 1;
+        stage_mmas(tmem_base + 64 * b, a_lo0 + (s * L::kABytes) / 16, idesc1, 3, 4096, false);
+        commit(&d1_full[s * 2 + b]);
+        if (q == 11) commit(&a_empty[s]);
       };
-      auto fc2 = [&](int it, int c) {    // accumulates on top of the parked residual row
-        const int s = it & 1;
-#pragma unroll
-        for (int kp = 0; kp < 2; ++kp) panel_mmas(tmem_base + 128 + s * 192, h_lo0 + (s * L::kHBytes + kp * 16384) / 16, idesc2, true);
-        commit(&h_empty[s]);
-        if (c == 5) commit(&d2_full[s]);
+      auto fc2 = [&](int it, int q) {     // K panel q of fc2, accumulating on top of the parked residual row
+        const int s = it & 1, b = q & 1;
+        stage_mmas(tmem_base + 128 + s * 192, h_lo0 + (s * L::kHBytes + b * 16384) / 16, idesc2, 1, 0, true);
+        commit(&h_empty[s * 2 + b]);
+        if (q == 11) commit(&d2_full[s]);
       };
       auto proj = [&](int it) {
         const int s = it & 1, k = it >> 1;
@@ -259,47 +270,46 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
         if (k > 0) mbar_wait(&d2_empty[s], (k - 1) & 1);
         tc_fence_after();
         if (lane == 0) trace(0, 7);
-#pragma unroll
-        for (int kp = 0; kp < 3; ++kp) panel_mmas(tmem_base + 128 + s * 192, a_lo0 + (s * L::kABytes + kp * 16384) / 16, idescP, kp != 0);
+        for (int kp = 0; kp < 3; ++kp)
+          stage_mmas(tmem_base + 128 + s * 192, a_lo0 + (s * L::kABytes + kp * 16384) / 16, idescP, 1, 0, kp != 0);
         commit(&proj_full[s]);
       };
       proj(0);
       mbar_wait(&a_full[0], 0);
       tc_fence_after();
       fc1(0, 0);
+      fc1(0, 1);
       for (int it = 0; it < n_my; ++it) {
         const int s = it & 1, k = it >> 1;
 #pragma unroll 1
-        for (int c = 0; c < 6; ++c) {
-          const uint32_t j = static_cast<uint32_t>(k * 6 + c);
-          if (c < 5) {
-            mbar_wait(&d1_empty[s], j & 1);
-            tc_fence_after();
-            if (lane == 0) trace(0, 1);
-            fc1(it, c + 1);
-            if (lane == 0) trace(0, 5);
+        for (int q = 0; q < 12; ++q) {
+          const int b = q & 1;
+          const uint32_t u = static_cast<uint32_t>(k * 6 + (q >> 1));     // use count of buffer b by this slot
+          mbar_wait(&gelu_done[s * 2 + b], u & 1);                        // D1[b] drained, H[slot][b] written
+          tc_fence_after();
+          if (lane == 0) trace(0, 1);
+          if (q < 10) {
+            fc1(it, q + 2);
           } else if (it + 1 < n_my) {
-            mbar_wait(&a_full[s ^ 1], ((it + 1) >> 1) & 1);
-            mbar_wait(&d1_empty[s], j & 1);
-            tc_fence_after();
-            if (lane == 0) trace(0, 2);
-            fc1(it + 1, 0);
+            if (q == 10) {
+              mbar_wait(&a_full[s ^ 1], ((it + 1) >> 1) & 1);
+              tc_fence_after();
+              if (lane == 0) trace(0, 2);
+            }
+            fc1(it + 1, q - 10);
           }
-          if (c == kProjC && it + 1 < n_my) {
+          if (q == kProjQ && it + 1 < n_my) {
             proj(it + 1);
             if (lane == 0) trace(0, 4);
           }
-          mbar_wait(&h_full[s], j & 1);
-          tc_fence_after();
-          if (lane == 0) trace(0, 3);
-          fc2(it, c);
+          fc2(it, q);
           if (lane == 0) trace(0, 6);
         }
       }
     }
-  } else if (warp >= 3) {
+  } else {
     // ================================================================= epilogue warps: two groups, one per tile slot
-    const int ew = warp - 3;
+    const int ew = warp - 2;
     const int grp = ew >> 3;                            // == slot of the tiles this group owns
     const int team = (ew >> 2) & 1;
     const int quad = warp & 3;                          // TMEM lane quadrant this warp may access
@@ -309,12 +319,11 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
     const bool tr = (ew == grp * 8 && lane == 0);
     const int trole = 1 + grp;
     const uint32_t af_l = mapa_u32(smem_u32(&a_full[grp]), 0);
-    const uint32_t d1e_l = mapa_u32(smem_u32(&d1_empty[grp]), 0);
-    const uint32_t hf_l = mapa_u32(smem_u32(&h_full[grp]), 0);
+    const uint32_t gd_l[2] = {mapa_u32(smem_u32(&gelu_done[grp * 2 + 0]), 0), mapa_u32(smem_u32(&gelu_done[grp * 2 + 1]), 0)};
     const uint32_t d2e_l = mapa_u32(smem_u32(&d2_empty[grp]), 0);
     uint8_t* sAg = sA + grp * L::kABytes;
     uint8_t* sHg = sH + grp * L::kHBytes;
-    const uint32_t tD1 = tmem_base + lane_sel + 64 * team;
+    const uint32_t tD1 = tmem_base + lane_sel + 32 * team;
     const uint32_t tD2 = tmem_base + lane_sel + 128 + grp * 192 + 96 * team;
     uint32_t part_use = 0;
 
@@ -372,7 +381,7 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       const float* src = p.x_in + xt_offset(valid ? grow : 0, 0, 0) + 24 * team * 128;
       if (tr) trace(trole, 30);
       float s = 0.0f, ss = 0.0f;
-#pragma unroll 1
+#pragma unroll (kVar & 2 ? 2 : 1)
       for (int h = 0; h < 2; ++h) {
         float x[48];
 #pragma unroll
@@ -413,7 +422,7 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       float mean, rstd;
       row_stats(s, ss, mean, rstd);
       if (tr) trace(trole, 33);
-#pragma unroll 1
+#pragma unroll (kVar & 2 ? 2 : 1)
       for (int h = 0; h < 2; ++h) {
         float x[48];
         ld48(tD2 + 48 * h, x);
@@ -440,7 +449,7 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       tc_fence_after();
       if (tr) trace(trole, 41);
       float s = 0.0f, ss = 0.0f;
-#pragma unroll 1
+#pragma unroll (kVar & 2 ? 2 : 1)
       for (int h = 0; h < 2; ++h) {
         float x[48];
         ld48(tD2 + 48 * h, x);
@@ -453,16 +462,32 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
             *reinterpret_cast<float4*>(dstx + (12 * h + i) * 128) = make_float4(x[i * 4], x[i * 4 + 1], x[i * 4 + 2], x[i * 4 + 3]);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(d2e_l);
+      auto release_d2 = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(d2e_l);
+      };
+      if (!(kVar & 1) || !p.has_ln) release_d2();
       if (tr) trace(trole, 42);
       if (!p.has_ln) return;
       float mean, rstd;
       row_stats(s, ss, mean, rstd);
       if (tr) trace(trole, 43);
-      // n4 float4 slots of this thread's row, starting at slot f0 of its 24
+      // n4 float4 slots (12 or 8) of this thread's row of x_out, starting at slot f0 of its 24: from L2, or again from D2
       auto reload = [&](float* x, int f0, int n4) {
+        if (kVar & 1) {
+          float v[32];
+          tmem_ld32(tD2 + 4 * f0, v);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) x[i] = v[i] + sB2[96 * team + 4 * f0 + i];
+          if (n4 == 12) {
+            float w[16];
+            tmem_ld16(tD2 + 4 * f0 + 32, w);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) x[32 + i] = w[i] + sB2[96 * team + 4 * f0 + 32 + i];
+          }
+          return;
+        }
 #pragma unroll
         for (int i = 0; i < 12; ++i) {
           if (i < n4) {
@@ -475,12 +500,13 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       // ln_out leaves through H[slot] (idle between the tile's last fc2 and the group's next GELU chunk): 32 KB = panels 0 and
       // 1 in the first round (team 0: columns 0..95, team 1: columns 96..127), panel 2 (team 1: columns 128..191) in the second
       if (team == 0) {
-#pragma unroll 1
+#pragma unroll (kVar & 2 ? 2 : 1)
         for (int h = 0; h < 2; ++h) {
           float x[48];
           reload(x, 12 * h, 12);
           store_ln(sHg, x, 6, 48 * h, 0, mean, rstd, sGamma, sBeta);
         }
+        if (kVar & 1) release_d2();
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 64);
         if (lane == 0) {
@@ -500,6 +526,7 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
           reload(x, 0, 8);                                // columns 96..127
           reload(y0, 8, 8);
           reload(y1, 16, 8);
+          if (kVar & 1) release_d2();
           store_ln(sHg, x, 4, 96, 0, mean, rstd, sGamma, sBeta);
         }
         fence_proxy_async_smem();
@@ -519,56 +546,40 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       if (tr) trace(trole, 44);
     };
 
-    // one hidden chunk: D1 (this team's 64 columns) -> GELU -> fp16 K-major panel `team` of H[slot]
-    auto gelu_chunk = [&](int it, int c) {
-      const uint32_t j = static_cast<uint32_t>((it >> 1) * 6 + c);
+    // one hidden half-chunk (64 columns): D1[q & 1] (this team's 32 columns) -> GELU -> fp16 K-major panel q & 1 of H[slot]
+    auto gelu_chunk = [&](int it, int q) {
+      const int b = q & 1;
+      const uint32_t u = static_cast<uint32_t>((it >> 1) * 6 + (q >> 1));
       if (tr) trace(trole, 10);
-      mbar_wait(&d1_full[grp], j & 1);
+      mbar_wait(&d1_full[grp * 2 + b], u & 1);
       tc_fence_after();
       if (tr) trace(trole, 12);
-      uint8_t* panel = sHg + team * 16384;
-      const uint4* bb = reinterpret_cast<const uint4*>(sB1 + c * 128 + team * 64);
-      auto gelu32 = [&](const float (&v)[32], int half, uint32_t (&o)[16]) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const uint4 bq = bb[half * 4 + q];                     // 8 fp16 biases
-          const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            __half2 hx = __floats2half2_rn(v[q * 8 + 2 * e], v[q * 8 + 2 * e + 1]);
-            hx = __hadd2(hx, *reinterpret_cast<const __half2*>(&bw[e]));
-            const __half2 g = gelu_erf_h2(hx);
-            o[q * 4 + e] = *reinterpret_cast<const uint32_t*>(&g);
-          }
-        }
-      };
-      auto store16 = [&](const uint32_t (&o)[16], int half) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(panel + sw128_offset(row, half * 4 + q)) = make_uint4(o[q * 4], o[q * 4 + 1], o[q * 4 + 2], o[q * 4 + 3]);
-      };
+      float v[32];
+      tmem_ld32(tD1 + 64 * b, v);
+      const uint4* bb = reinterpret_cast<const uint4*>(sB1 + q * 64 + team * 32);
+      uint8_t* panel = sHg + b * 16384;
       uint32_t o[16];
-      {
-        float v[32];
-        tmem_ld32(tD1, v);
-        gelu32(v, 0, o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 bq = bb[j];                              // 8 fp16 biases
+        const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          __half2 hx = __floats2half2_rn(v[j * 8 + 2 * e], v[j * 8 + 2 * e + 1]);
+          hx = __hadd2(hx, *reinterpret_cast<const __half2*>(&bw[e]));
+          const __half2 g = gelu_erf_h2(hx);
+          o[j * 4 + e] = *reinterpret_cast<const uint32_t*>(&g);
+        }
       }
       if (tr) trace(trole, 11);
-      mbar_wait(&h_empty[grp], (j & 1) ^ 1);               // the previous chunk's fc2 has read H[slot]
-      if (tr) trace(trole, 14);
-      store16(o, 0);
-      {
-        float v[32];
-        tmem_ld32(tD1 + 32, v);
-        tc_fence_before();                                 // D1 is in registers: the next fc1 may overwrite it
-        __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(d1e_l);
-        gelu32(v, 1, o);
-      }
-      store16(o, 1);
+      mbar_wait(&h_empty[grp * 2 + b], (u & 1) ^ 1);       // fc2 of half-chunk q-2 has read the panel
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(panel + sw128_offset(row, team * 4 + j)) = make_uint4(o[j * 4], o[j * 4 + 1], o[j * 4 + 2], o[j * 4 + 3]);
+      tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(hf_l);
+      if (lane == 0) mbar_arrive_cluster(gd_l[b]);
       if (tr) trace(trole, 13);
     };
 
@@ -579,7 +590,7 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
     for (int it = grp; it < n_my; it += 2) {
       if (it + 2 < n_my) prefetch_rows(it + 2);
 #pragma unroll 1
-      for (int c = 0; c < 6; ++c) gelu_chunk(it, c);
+      for (int q = 0; q < 12; ++q) gelu_chunk(it, q);
       final_tile(it);
       if (it + 2 < n_my) produce_a(it + 2);
     }
