@@ -184,10 +184,10 @@ static int launch_mlp_fused(const MlpFusedArgs& a, cudaStream_t stream) {
 }
 
 // two row tiles in flight per CTA pair (mlp_fused2.cuh); needs the folded attention projection
-template <int kProjQ, int kVar>
+template <int kProjQ, bool kTrace>
 static int launch_mlp_fused2(const MlpFusedArgs& a, cudaStream_t stream) {
   using L = Mlp2Smem;
-  auto kernel = mlp_fused2_kernel<kProjQ, kVar>;
+  auto kernel = mlp_fused2_kernel<kProjQ, kTrace>;
   RVK_SET_MAX_SMEM(kernel, L::kTotal);
   const MlpFusedParams& p = a.p;
   CUtensorMap tmW1, tmW2, tmLn, tmCtx, tmWp;
@@ -220,16 +220,13 @@ static int launch_mlp_fused2(const MlpFusedArgs& a, cudaStream_t stream) {
   return rvk_launch_check();
 }
 
-static int mlp2_env(const char* name, int lo, int hi, int dflt) {
-  const char* e = getenv(name);
-  return (e != nullptr && e[0] >= '0' + lo && e[0] <= '0' + hi) ? e[0] - '0' : dflt;
-}
-// A/B switches of the two-tile kernel: RVK_MLP2_PROJQ=3..5 (half-chunk of tile i at which the projection of tile i+1 is issued),
-// RVK_MLP2_VAR=0..3 (mlp_fused2.cuh: kVar)
-template <int kVar>
-static int launch_mlp_fused2_q(const MlpFusedArgs& a, cudaStream_t stream) {
-  static const int q = mlp2_env("RVK_MLP2_PROJQ", 3, 5, 4);
-  return q == 3 ? launch_mlp_fused2<3, kVar>(a, stream) : q == 5 ? launch_mlp_fused2<5, kVar>(a, stream) : launch_mlp_fused2<4, kVar>(a, stream);
+// A/B switch of the two-tile kernel: RVK_MLP2_PROJQ=3..5 (half-chunk of tile i at which the projection of tile i+1 is issued)
+static int mlp2_proj_q() {
+  static const int q = [] {
+    const char* e = getenv("RVK_MLP2_PROJQ");
+    return (e != nullptr && e[0] >= '3' && e[0] <= '5') ? e[0] - '0' : 4;
+  }();
+  return q;
 }
 
 int rvk_mlp_fused_launch(const MlpFusedArgs& a, cudaStream_t stream) {
@@ -244,13 +241,9 @@ int rvk_mlp_fused_launch(const MlpFusedArgs& a, cudaStream_t stream) {
   if (a.cta_group == 2) return launch_mlp_fused<2>(a, stream);
   if (a.cta_group == 4) {           // CTA pairs, two row tiles in flight
     if (!p.has_proj) return RVK_ERR_BAD_ARG;
-    static const int var = mlp2_env("RVK_MLP2_VAR", 0, 3, 0);
-    switch (var) {
-      case 1: return launch_mlp_fused2_q<1>(a, stream);
-      case 2: return launch_mlp_fused2_q<2>(a, stream);
-      case 3: return launch_mlp_fused2_q<3>(a, stream);
-      default: return launch_mlp_fused2_q<0>(a, stream);
-    }
+    if (p.trace != nullptr) return launch_mlp_fused2<4, true>(a, stream);     // debugging build with the clock64 event log
+    const int q = mlp2_proj_q();
+    return q == 3 ? launch_mlp_fused2<3, false>(a, stream) : q == 5 ? launch_mlp_fused2<5, false>(a, stream) : launch_mlp_fused2<4, false>(a, stream);
   }
   return RVK_ERR_BAD_ARG;
 }

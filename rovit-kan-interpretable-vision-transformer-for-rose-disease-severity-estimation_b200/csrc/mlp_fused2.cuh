@@ -62,11 +62,13 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-// kVar (measurement switches): bit 0 = the final epilogue's normalising pass re-reads D2 from TMEM (D2 released after it)
-// instead of the x_out rows from L2; bit 1 = the two 48-column pieces of the LayerNorm passes fully unrolled.
+// kTrace: build with the clock64 event log (p.trace); the production instantiation carries no trace code.
+// Measured and dropped (A/B in one gpurun call, 191 us either way or slower): the final epilogue's normalising pass re-reading D2
+// from TMEM instead of the x_out rows from L2 (D2 released later), and the two 48-column pieces of the LayerNorm passes
+// fully unrolled (spills at the 96-register cap).
 // kProjQ: the hidden half-chunk (0..11) of tile i at which the projection of tile i+1 is issued (its D2 slot must have been drained by the
 // other group's final epilogue of tile i-1 by then, and the LayerNorm-on-load of tile i+1 must fit behind it)
-template <int kProjQ, int kVar>
+template <int kProjQ, bool kTrace>
 __global__ void __launch_bounds__(kMlp2Threads, 1)
 mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
                   const __grid_constant__ CUtensorMap tmLn, const __grid_constant__ CUtensorMap tmCtx,
@@ -163,7 +165,7 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
   // event log: role 0 = UMMA issuer, 1 = first warp of group 0, 2 = first warp of group 1; entry = (tag << 48) | clock
   int trace_n = 0;
   auto trace = [&](int role, int tag) {
-    if (p.trace != nullptr && blockIdx.x == 0 && trace_n < 512) {
+    if (kTrace && p.trace != nullptr && blockIdx.x == 0 && trace_n < 512) {
       p.trace[role * 512 + trace_n++] = (static_cast<long long>(tag) << 48) | (clock64() & 0xFFFFFFFFFFFFLL);
     }
   };
@@ -269,7 +271,7 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
         mbar_wait(&ctx_full[s], k & 1);
         if (k > 0) mbar_wait(&d2_empty[s], (k - 1) & 1);
         tc_fence_after();
-        if (lane == 0) trace(0, 7);
+        if (kTrace && lane == 0) trace(0, 7);
         for (int kp = 0; kp < 3; ++kp)
           stage_mmas(tmem_base + 128 + s * 192, a_lo0 + (s * L::kABytes + kp * 16384) / 16, idescP, 1, 0, kp != 0);
         commit(&proj_full[s]);
@@ -287,23 +289,23 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
           const uint32_t u = static_cast<uint32_t>(k * 6 + (q >> 1));     // use count of buffer b by this slot
           mbar_wait(&gelu_done[s * 2 + b], u & 1);                        // D1[b] drained, H[slot][b] written
           tc_fence_after();
-          if (lane == 0) trace(0, 1);
+          if (kTrace && lane == 0) trace(0, 1);
           if (q < 10) {
             fc1(it, q + 2);
           } else if (it + 1 < n_my) {
             if (q == 10) {
               mbar_wait(&a_full[s ^ 1], ((it + 1) >> 1) & 1);
               tc_fence_after();
-              if (lane == 0) trace(0, 2);
+              if (kTrace && lane == 0) trace(0, 2);
             }
             fc1(it + 1, q - 10);
           }
           if (q == kProjQ && it + 1 < n_my) {
             proj(it + 1);
-            if (lane == 0) trace(0, 4);
+            if (kTrace && lane == 0) trace(0, 4);
           }
           fc2(it, q);
-          if (lane == 0) trace(0, 6);
+          if (kTrace && lane == 0) trace(0, 6);
         }
       }
     }
@@ -316,7 +318,7 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
     const int row = quad * 32 + lane;                   // token row of the tile == TMEM lane
     const uint32_t lane_sel = static_cast<uint32_t>(quad * 32) << 16;
     const uint32_t bar_id = 2 + grp * 4 + quad;         // the two warps (teams) of this group that share the 32 rows
-    const bool tr = (ew == grp * 8 && lane == 0);
+    const bool tr = kTrace && (ew == grp * 8 && lane == 0);
     const int trole = 1 + grp;
     const uint32_t af_l = mapa_u32(smem_u32(&a_full[grp]), 0);
     const uint32_t gd_l[2] = {mapa_u32(smem_u32(&gelu_done[grp * 2 + 0]), 0), mapa_u32(smem_u32(&gelu_done[grp * 2 + 1]), 0)};
@@ -381,7 +383,7 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       const float* src = p.x_in + xt_offset(valid ? grow : 0, 0, 0) + 24 * team * 128;
       if (tr) trace(trole, 30);
       float s = 0.0f, ss = 0.0f;
-#pragma unroll (kVar & 2 ? 2 : 1)
+#pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         float x[48];
 #pragma unroll
@@ -422,7 +424,7 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       float mean, rstd;
       row_stats(s, ss, mean, rstd);
       if (tr) trace(trole, 33);
-#pragma unroll (kVar & 2 ? 2 : 1)
+#pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         float x[48];
         ld48(tD2 + 48 * h, x);
@@ -449,7 +451,7 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       tc_fence_after();
       if (tr) trace(trole, 41);
       float s = 0.0f, ss = 0.0f;
-#pragma unroll (kVar & 2 ? 2 : 1)
+#pragma unroll 1
       for (int h = 0; h < 2; ++h) {
         float x[48];
         ld48(tD2 + 48 * h, x);
@@ -467,27 +469,14 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(d2e_l);
       };
-      if (!(kVar & 1) || !p.has_ln) release_d2();
+      release_d2();
       if (tr) trace(trole, 42);
       if (!p.has_ln) return;
       float mean, rstd;
       row_stats(s, ss, mean, rstd);
       if (tr) trace(trole, 43);
-      // n4 float4 slots (12 or 8) of this thread's row of x_out, starting at slot f0 of its 24: from L2, or again from D2
+      // n4 float4 slots (12 or 8) of this thread's row of x_out, starting at slot f0 of its 24 (L2 hits)
       auto reload = [&](float* x, int f0, int n4) {
-        if (kVar & 1) {
-          float v[32];
-          tmem_ld32(tD2 + 4 * f0, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) x[i] = v[i] + sB2[96 * team + 4 * f0 + i];
-          if (n4 == 12) {
-            float w[16];
-            tmem_ld16(tD2 + 4 * f0 + 32, w);
-#pragma unroll
-            for (int i = 0; i < 16; ++i) x[32 + i] = w[i] + sB2[96 * team + 4 * f0 + 32 + i];
-          }
-          return;
-        }
 #pragma unroll
         for (int i = 0; i < 12; ++i) {
           if (i < n4) {
@@ -500,13 +489,12 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       // ln_out leaves through H[slot] (idle between the tile's last fc2 and the group's next GELU chunk): 32 KB = panels 0 and
       // 1 in the first round (team 0: columns 0..95, team 1: columns 96..127), panel 2 (team 1: columns 128..191) in the second
       if (team == 0) {
-#pragma unroll (kVar & 2 ? 2 : 1)
+#pragma unroll 1
         for (int h = 0; h < 2; ++h) {
           float x[48];
           reload(x, 12 * h, 12);
           store_ln(sHg, x, 6, 48 * h, 0, mean, rstd, sGamma, sBeta);
         }
-        if (kVar & 1) release_d2();
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 64);
         if (lane == 0) {
@@ -526,8 +514,7 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
           reload(x, 0, 8);                                // columns 96..127
           reload(y0, 8, 8);
           reload(y1, 16, 8);
-          if (kVar & 1) release_d2();
-          store_ln(sHg, x, 4, 96, 0, mean, rstd, sGamma, sBeta);
+            store_ln(sHg, x, 4, 96, 0, mean, rstd, sGamma, sBeta);
         }
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 64);
