@@ -455,8 +455,9 @@ def bench_infer(ctx, K, W, batch, with_e2e=True):
     res['roofline'] = {
         'bound': 'tensor', 'achieved': dom['tflops'] if dom else None, 'peak': pk['tflops_sustained'], 'unit': 'TFLOP/s',
         'frac': dom['frac_tensor'] if dom else None, 'traffic': traffic, 'traffic_source': traffic_src,
-        'kernel': ('mlp_fused_kernel<2> (attention out-projection + LayerNorm2 + fc1 + GELU + fc2 + residual + LayerNorm1, '
-                   'one launch per block; algorithmic FLOPs 2*M*192*(192 + 2*768) per launch, M = batch*197)'),
+        'kernel': ('mlp_fused2_kernel (CTA pairs, two row tiles in flight; RVK_MLP_CTA_GROUP=2: mlp_fused_kernel<2>): attention '
+                   'out-projection + LayerNorm2 + fc1 + GELU + fc2 + residual + LayerNorm1, '
+                   'one launch per block; algorithmic FLOPs 2*M*192*(192 + 2*768) per launch, M = batch*197'),
         'us_per_launch': dom['us_per_launch'] if dom else None, 'gflop_per_launch': dom['gflop_per_launch'] if dom else None,
         'share_of_step': dom['share_of_step'] if dom else None, 'launches_timed': dom['launches'] if dom else 0,
         'peak_source': pk['source'] + ' sustained bf16', 'kernels': kernels,

@@ -236,14 +236,16 @@ int rvk_gemm_nt(int mode, const void* a_bf16, int64_t lda, const void* b_bf16, i
  * x_in / x_out fp32 in the TILED token-stream layout (element (r,c) at
  * (((r/32)*6 + c/32)*8 + (c%32)/4)*128 + (r%32)*4 + c%4, rows padded to 128; x_out may alias x_in); w1 bf16 [768,192];
  * w2 FP16 [192,768] (the hidden activation stays on chip in fp16: GELU runs as packed half2 arithmetic); ln_out bf16
- * [m,192].  cta_group: 2 = CTA pairs sharing one tcgen05.mma.cta_group::2 (default), 1 = single CTAs. */
+ * [m,192].  cta_group: 2 = CTA pairs sharing one tcgen05.mma.cta_group::2, 1 = single CTAs (4: see below, needs the projection). */
 int rvk_mlp_fused(const float* x_in_tiled, float* x_out_tiled, const float* gamma2, const float* beta2,
                   const void* w1_bf16, const float* b1, const void* w2_f16, const float* b2, const float* gamma,
                   const float* beta, float eps, void* ln_out_bf16, int m, int cta_group, void* stream);
 /* The same kernel with the attention output projection folded in (timm Block.forward first half: x + proj(attn),
  * Attention.proj): before the MLP half it computes  x_in += ctx . wproj^T + bproj  on the tensor cores (accumulator in
  * the TMEM columns that are idle between two row tiles), so the projected residual stream never makes its own round
- * trip through memory.  ctx bf16 [m,192] (rvk_attention_forward output), wproj bf16 [192,192], bproj fp32 [192]. */
+ * trip through memory.  ctx bf16 [m,192] (rvk_attention_forward output), wproj bf16 [192,192], bproj fp32 [192].
+ * cta_group 4 = CTA pairs with TWO row tiles in flight (two groups of epilogue warps, the projected row parked in TMEM under
+ * fc2; csrc/mlp_fused2.cuh) -- what the inference trunk runs by default; RVK_ERR_BAD_ARG in rvk_mlp_fused (no projection). */
 int rvk_attn_proj_mlp_fused(const float* x_in_tiled, float* x_out_tiled, const void* ctx_bf16, const void* wproj_bf16,
                             const float* bproj, const float* gamma2, const float* beta2, const void* w1_bf16, const float* b1,
                             const void* w2_f16, const float* b2, const float* gamma, const float* beta, float eps,

@@ -1,6 +1,7 @@
 """GPU parity of the fused MLP block kernel (fc1 + GELU + fc2 + residual + LayerNorm in one tcgen05 kernel, the
 LayerNorm applied on load, hidden activation never leaving the SM) against an fp32 restatement of timm's Block MLP half on the same
-bf16-rounded operands (oracle/vit.py::_Block).  Both the CTA-pair (cta_group::2) and the single-CTA variant.
+bf16-rounded operands (oracle/vit.py::_Block).  The CTA-pair (cta_group::2) kernel, its single-CTA variant (G = 1) and the
+two-row-tiles-in-flight kernel the inference path runs by default (G = 4, csrc/mlp_fused2.cuh; needs the folded projection).
 Tolerances: GELU is evaluated in packed fp16 arithmetic and the hidden activation is rounded to fp16 before fc2
 (together about one bf16 rounding, 2^-9 relative, per hidden element -- the unfused path rounds it to bf16);
 x_out is fp32, ln_out carries one more bf16 rounding."""
@@ -92,12 +93,14 @@ def test_mlp_fused_no_layernorm_in_place(G):
 @pytest.mark.parametrize('G', [1, 2, 4])
 @pytest.mark.parametrize('M', [128, 300, 1000, 197 * 64, 197 * 300 + 5])
 def test_attn_proj_mlp_fused(M, G):
-    """rvk_attn_proj_mlp_fused: x + proj(ctx) computed in the idle TMEM columns, then the MLP half on the new rows."""
+    """rvk_attn_proj_mlp_fused: x + proj(ctx) on the tensor cores (G = 1, 2: in the idle TMEM columns; G = 4: in the tile's own
+    accumulator slot, where the projected row then stays parked under fc2), then the MLP half on the new rows."""
     run_case(M, G, True, seed=M + 11, proj=True)
     run_case(M, G, M % 2 == 0, seed=M + 12, inplace=True, proj=True)
 
 
-def test_attn_proj_mlp_fused_equals_two_launches_at_benchmark_size():
+@pytest.mark.parametrize('G', [2, 4])
+def test_attn_proj_mlp_fused_equals_two_launches_at_benchmark_size(G):
     """BASELINE configs[1] size (1024 images = 201 728 token rows): folding the attention output projection into the MLP kernel
     must give what the separate projection GEMM followed by rvk_mlp_fused gives (same bf16 operands, fp32 accumulation; the
     only difference is the order of two fp32 additions per element)."""
@@ -115,7 +118,7 @@ def test_attn_proj_mlp_fused_equals_two_launches_at_benchmark_size():
             beta.data_ptr(), 1e-6)
     xa, lna = x.clone(), torch.empty(M, 192, device=DEV, dtype=torch.bfloat16)
     _lib.call('rvk_attn_proj_mlp_fused', xa.data_ptr(), xa.data_ptr(), ctx.data_ptr(), wp.data_ptr(), bp.data_ptr(), *tail,
-              lna.data_ptr(), M, 2, s)
+              lna.data_ptr(), M, G, s)
     # two launches: x += ctx . Wp^T + bp through the fp32 GEMM epilogue (row-major round trip), then the MLP kernel
     xr = from_tiled(x, M).contiguous()
     t = torch.empty(M, 192, device=DEV)

@@ -72,11 +72,12 @@ def main():
                      'algorithmic_bytes_per_launch': 152.0e6,
                      'source': f'profiles/{TAG}_ncu_full_kan_*.txt (ncu --set full, dram read + write of one launch of each of the five kernels '
                                'of one forward+backward at batch 65536; "launch" = one fwd+bwd of the stack)'}
-    if 'mlp' in names and names['mlp']:
-        n, b, d = names['mlp'][0]
-        tj['infer'] = {'batch_per_gpu': 1024, 'kernel': 'mlp_fused_kernel<2>', 'dram_bytes_per_launch': b,
+    mlp_key = 'mlp2' if names.get('mlp2') else 'mlp'       # mlp2 = the two-tile kernel the inference path runs by default
+    if names.get(mlp_key):
+        n, b, d = names[mlp_key][0]
+        tj['infer'] = {'batch_per_gpu': 1024, 'kernel': n.split('(')[0].replace('void ', ''), 'dram_bytes_per_launch': b,
                        'algorithmic_bytes_per_launch': 465444864,
-                       'source': f'profiles/{TAG}_ncu_full_mlp.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch at batch 1024)'}
+                       'source': f'profiles/{TAG}_ncu_full_{mlp_key}.txt (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, one launch at batch 1024)'}
     json.dump(tj, open(tj_path, 'w'), indent=1)
     print(json.dumps(tj, indent=1)[:1500])
 
