@@ -38,13 +38,13 @@ constexpr int kMlp2Threads = (2 + 16) * 32;   // 576
 
 struct Mlp2Smem {
   static constexpr int kABytes = 3 * 16384;                 // per slot: three [128 x 64] K panels
-  static constexpr int kHBytes = 2 * 16384;                 // per slot: two hidden half-chunk panels [128 x 64] fp16 (ping-pong)
+  static constexpr int kStageBytes = 3 * 16384;             // ln_out staging (bf16 [128 x 192] as three swizzled panels), shared by the groups
   static constexpr int kWStage = 12288;                     // this CTA's half of a W2 / Wproj panel [96 x 64], or of three W1 panels [32 x 64]
-  static constexpr int kWStages = 4;
+  static constexpr int kWStages = 5;
   static constexpr int kVecBytes = 768 * 2 + 6 * 192 * 4;   // b1 (fp16); b2, gamma2, beta2, gamma, beta, bp (fp32)
   static constexpr int kPartBytes = 2 * 2 * 2 * 128 * 8;    // LayerNorm partial (sum, sumsq): [use parity][group][team][row]
   static constexpr int kBarBytes = 256;
-  static constexpr int kTotal = 1024 + 2 * kABytes + 2 * kHBytes + kWStages * kWStage + kVecBytes + kPartBytes + kBarBytes;
+  static constexpr int kTotal = 1024 + 2 * kABytes + kStageBytes + kWStages * kWStage + kVecBytes + kPartBytes + kBarBytes;
 };
 
 #ifdef __CUDACC__
@@ -62,6 +62,26 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float* v) {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_st16u(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+// D[tmem] (+)= A[tmem: this CTA's 128 rows, K-major packed 16-bit pairs, 8 columns per K = 16] * B[smem desc], CTA pair
+__device__ __forceinline__ void umma_ts_pair(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "mov.b64 db, {%2, %5};\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], db, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kUmmaDescHiSw128)
+      : "memory");
+}
+
 // kTrace: build with the clock64 event log (p.trace); the production instantiation carries no trace code.
 // Measured and dropped (A/B in one gpurun call, 191 us either way or slower): the final epilogue's normalising pass re-reading D2
 // from TMEM instead of the x_out rows from L2 (D2 released later), and the two 48-column pieces of the LayerNorm passes
@@ -77,8 +97,8 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;                                  // [2][kABytes]
-  uint8_t* sH = sA + 2 * L::kABytes;                   // [2][kHBytes]
-  uint8_t* sW = sH + 2 * L::kHBytes;
+  uint8_t* sStage = sA + 2 * L::kABytes;               // [kStageBytes]
+  uint8_t* sW = sStage + L::kStageBytes;
   __half* sB1 = reinterpret_cast<__half*>(sW + L::kWStages * L::kWStage);
   float* sB2 = reinterpret_cast<float*>(sB1 + 768);
   float* sGamma2 = sB2 + 192;
@@ -95,11 +115,11 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
   uint64_t* a_empty = bars + 6;       // the tile's last fc1 has read A[slot] (commit)
   uint64_t* d2_full = bars + 8;       // the tile's last fc2 complete (commit)
   uint64_t* d2_empty = bars + 10;     // leader: D2[slot] read out by the final epilogue
-  // per slot and buffer [2][2] (index slot * 2 + buffer; each group counts the uses of a buffer by its own tiles):
+  // per slot and D1 buffer [2][2] (index slot * 2 + buffer; each group counts the uses of a buffer by its own tiles):
   uint64_t* d1_full = bars + 12;      // fc1 half-chunk complete in D1[buffer] (commit)
-  uint64_t* gelu_done = bars + 16;    // leader: D1[buffer] drained and H[slot][buffer] written by the group's warps of the pair
-  uint64_t* h_empty = bars + 20;      // fc2 has read H[slot][buffer] (commit)
-  uint64_t* w_full = bars + 24;       // [kWStages]
+  uint64_t* h_full = bars + 16;       // leader: the hidden half-chunk sits in D1[buffer] as packed fp16 (group's warps of the pair)
+  uint64_t* stage_free = bars + 20;   // this CTA: the ln_out staging buffer has been read by the previous tile's TMA stores
+  uint64_t* w_full = bars + 21;       // [kWStages]
   uint64_t* w_empty = w_full + L::kWStages;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_empty + L::kWStages);
 
@@ -143,9 +163,9 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&d1_full[i], 1);
-      mbar_init(&gelu_done[i], kGroupArrivals);
-      mbar_init(&h_empty[i], 1);
+      mbar_init(&h_full[i], kGroupArrivals);
     }
+    mbar_init(stage_free, 4);
     for (int i = 0; i < L::kWStages; ++i) {
       mbar_init(&w_full[i], 1);
       mbar_init(&w_empty[i], 1);
@@ -215,10 +235,10 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
         for (int q = 0; q < 12; ++q) {
           // the ctx tile does not go through the ring: its buffer has been free since the last fc1 of tile it-1
           if (q == 0 && it + 1 < n_my) load_ctx(it + 1);
+          load_w2(q);
           if (q < 10) load_w1(q + 2);
           else if (it + 1 < n_my) load_w1(q - 10);
           if (q == kProjQ && it + 1 < n_my) load_wp();
-          load_w2(q);
         }
       }
     }
@@ -233,7 +253,6 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       int ws = 0;
       uint32_t wph = 0;
       const uint32_t a_lo0 = umma_desc_lo(smem_u32(sA));
-      const uint32_t h_lo0 = umma_desc_lo(smem_u32(sH));
       const uint32_t w_lo0 = umma_desc_lo(smem_u32(sW));
       auto commit = [&](uint64_t* bar) {
         if (issuer) umma_commit_pair(bar);
@@ -260,10 +279,19 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
         commit(&d1_full[s * 2 + b]);
         if (q == 11) commit(&a_empty[s]);
       };
-      auto fc2 = [&](int it, int q) {     // K panel q of fc2, accumulating on top of the parked residual row
-        const int s = it & 1, b = q & 1;
-        stage_mmas(tmem_base + 128 + s * 192, h_lo0 + (s * L::kHBytes + b * 16384) / 16, idesc2, 1, 0, true);
-        commit(&h_empty[s * 2 + b]);
+      auto fc2 = [&](int it, int q) {     // K panel q of fc2: A = the packed hidden half-chunk in D1[q & 1] (this team layout: hidden
+        const int s = it & 1, b = q & 1;  // columns 32t..32t+31 in TMEM columns 64b+32t .. +16), accumulating on the parked residual row
+        mbar_wait(&w_full[ws], wph);
+        tc_fence_after();
+        const uint32_t b_lo = w_lo0 + ws * (L::kWStage >> 4);
+        if (issuer) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_ts_pair(tmem_base + 128 + s * 192, tmem_base + 64 * b + 32 * (k >> 1) + 8 * (k & 1), b_lo + 2 * k, idesc2, 1u);
+        }
+        __syncwarp();
+        commit(&w_empty[ws]);
+        if (++ws == L::kWStages) { ws = 0; wph ^= 1; }
         if (q == 11) commit(&d2_full[s]);
       };
       auto proj = [&](int it) {
@@ -287,9 +315,11 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
         for (int q = 0; q < 12; ++q) {
           const int b = q & 1;
           const uint32_t u = static_cast<uint32_t>(k * 6 + (q >> 1));     // use count of buffer b by this slot
-          mbar_wait(&gelu_done[s * 2 + b], u & 1);                        // D1[b] drained, H[slot][b] written
+          mbar_wait(&h_full[s * 2 + b], u & 1);                           // hidden half-chunk q sits in D1[b]
           tc_fence_after();
           if (kTrace && lane == 0) trace(0, 1);
+          fc2(it, q);
+          // D1[b] is free again behind fc2(q) (tcgen05.mma of one thread execute in order)
           if (q < 10) {
             fc1(it, q + 2);
           } else if (it + 1 < n_my) {
@@ -304,7 +334,6 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
             proj(it + 1);
             if (kTrace && lane == 0) trace(0, 4);
           }
-          fc2(it, q);
           if (kTrace && lane == 0) trace(0, 6);
         }
       }
@@ -321,10 +350,9 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
     const bool tr = kTrace && (ew == grp * 8 && lane == 0);
     const int trole = 1 + grp;
     const uint32_t af_l = mapa_u32(smem_u32(&a_full[grp]), 0);
-    const uint32_t gd_l[2] = {mapa_u32(smem_u32(&gelu_done[grp * 2 + 0]), 0), mapa_u32(smem_u32(&gelu_done[grp * 2 + 1]), 0)};
+    const uint32_t hf_l[2] = {mapa_u32(smem_u32(&h_full[grp * 2 + 0]), 0), mapa_u32(smem_u32(&h_full[grp * 2 + 1]), 0)};
     const uint32_t d2e_l = mapa_u32(smem_u32(&d2_empty[grp]), 0);
     uint8_t* sAg = sA + grp * L::kABytes;
-    uint8_t* sHg = sH + grp * L::kHBytes;
     const uint32_t tD1 = tmem_base + lane_sel + 32 * team;
     const uint32_t tD2 = tmem_base + lane_sel + 128 + grp * 192 + 96 * team;
     uint32_t part_use = 0;
@@ -486,54 +514,32 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
           }
         }
       };
-      // ln_out leaves through H[slot] (idle between the tile's last fc2 and the group's next GELU chunk): 32 KB = panels 0 and
-      // 1 in the first round (team 0: columns 0..95, team 1: columns 96..127), panel 2 (team 1: columns 128..191) in the second
-      if (team == 0) {
+      // ln_out leaves through the staging buffer and TMA (three swizzled panels; team 0: columns 0..95, team 1: 96..191), once
+      // the previous tile's stores have read it
+      mbar_wait(stage_free, (it & 1) ^ 1);
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-          float x[48];
-          reload(x, 12 * h, 12);
-          store_ln(sHg, x, 6, 48 * h, 0, mean, rstd, sGamma, sBeta);
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(bar_id, 64);
-        if (lane == 0) {
-          if (m0 + quad * 32 < p.M) {
-            tma_store_2d(&tmLn, sHg + quad * 4096, 0, m0 + quad * 32);
-            tma_store_2d(&tmLn, sHg + 16384 + quad * 4096, 64, m0 + quad * 32);
-          }
-          tma_store_commit();
-          tma_store_wait_read<0>();
-        }
-        __syncwarp();
-        named_bar_sync(bar_id, 64);                       // staging panel 0 may be overwritten (second round)
-      } else {
-        float y0[32], y1[32];                             // columns 128..159 / 160..191, normalised in the second round
-        {
-          float x[32];
-          reload(x, 0, 8);                                // columns 96..127
-          reload(y0, 8, 8);
-          reload(y1, 16, 8);
-            store_ln(sHg, x, 4, 96, 0, mean, rstd, sGamma, sBeta);
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(bar_id, 64);
-        named_bar_sync(bar_id, 64);                       // team 0's store has read panels 0 and 1
-        store_ln(sHg, y0, 4, 128, 2, mean, rstd, sGamma, sBeta);
-        store_ln(sHg, y1, 4, 160, 2, mean, rstd, sGamma, sBeta);
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          if (m0 + quad * 32 < p.M) tma_store_2d(&tmLn, sHg + quad * 4096, 128, m0 + quad * 32);
-          tma_store_commit();
-          tma_store_wait_read<0>();                       // H[slot] may be overwritten by the group's next GELU chunk
-        }
-        __syncwarp();
+      for (int h = 0; h < 2; ++h) {
+        float x[48];
+        reload(x, 12 * h, 12);
+        store_ln(sStage, x, 6, 96 * team + 48 * h, 0, mean, rstd, sGamma, sBeta);
       }
+      fence_proxy_async_smem();
+      named_bar_sync(bar_id, 64);
+      if (team == 0 && lane == 0) {
+        if (m0 + quad * 32 < p.M) {
+#pragma unroll
+          for (int pn = 0; pn < 3; ++pn) tma_store_2d(&tmLn, sStage + pn * 16384 + quad * 4096, pn * 64, m0 + quad * 32);
+        }
+        tma_store_commit();
+        tma_store_wait_read<0>();
+        mbar_arrive(stage_free);
+      }
+      __syncwarp();
       if (tr) trace(trole, 44);
     };
 
-    // one hidden half-chunk (64 columns): D1[q & 1] (this team's 32 columns) -> GELU -> fp16 K-major panel q & 1 of H[slot]
+    // one hidden half-chunk (64 columns): D1[q & 1] (this team's 32 fp32 columns) -> GELU -> packed fp16 pairs written back over
+    // the first 16 of the SAME columns, from where fc2 takes them as its A operand: no shared-memory round trip, no proxy fence
     auto gelu_chunk = [&](int it, int q) {
       const int b = q & 1;
       const uint32_t u = static_cast<uint32_t>((it >> 1) * 6 + (q >> 1));
@@ -544,7 +550,6 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
       float v[32];
       tmem_ld32(tD1 + 64 * b, v);
       const uint4* bb = reinterpret_cast<const uint4*>(sB1 + q * 64 + team * 32);
-      uint8_t* panel = sHg + b * 16384;
       uint32_t o[16];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -559,14 +564,10 @@ mlp_fused2_kernel(const __grid_constant__ CUtensorMap tmW1, const __grid_constan
         }
       }
       if (tr) trace(trole, 11);
-      mbar_wait(&h_empty[grp * 2 + b], (u & 1) ^ 1);       // fc2 of half-chunk q-2 has read the panel
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        *reinterpret_cast<uint4*>(panel + sw128_offset(row, team * 4 + j)) = make_uint4(o[j * 4], o[j * 4 + 1], o[j * 4 + 2], o[j * 4 + 3]);
+      tmem_st16u(tD1 + 64 * b, o);
       tc_fence_before();
-      fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(gd_l[b]);
+      if (lane == 0) mbar_arrive_cluster(hf_l[b]);
       if (tr) trace(trole, 13);
     };
 
