@@ -220,11 +220,11 @@ static int launch_mlp_fused2(const MlpFusedArgs& a, cudaStream_t stream) {
   return rvk_launch_check();
 }
 
-// A/B switch of the two-tile kernel: RVK_MLP2_PROJQ=3..5 (half-chunk of tile i at which the projection of tile i+1 is issued)
+// A/B switch of the two-tile kernel: RVK_MLP2_PROJQ=1..5 (half-chunk of tile i at which the projection of tile i+1 is issued)
 static int mlp2_proj_q() {
   static const int q = [] {
     const char* e = getenv("RVK_MLP2_PROJQ");
-    return (e != nullptr && e[0] >= '3' && e[0] <= '5') ? e[0] - '0' : 4;
+    return (e != nullptr && e[0] >= '1' && e[0] <= '5') ? e[0] - '0' : 3;
   }();
   return q;
 }
@@ -241,9 +241,14 @@ int rvk_mlp_fused_launch(const MlpFusedArgs& a, cudaStream_t stream) {
   if (a.cta_group == 2) return launch_mlp_fused<2>(a, stream);
   if (a.cta_group == 4) {           // CTA pairs, two row tiles in flight
     if (!p.has_proj) return RVK_ERR_BAD_ARG;
-    if (p.trace != nullptr) return launch_mlp_fused2<4, true>(a, stream);     // debugging build with the clock64 event log
-    const int q = mlp2_proj_q();
-    return q == 3 ? launch_mlp_fused2<3, false>(a, stream) : q == 5 ? launch_mlp_fused2<5, false>(a, stream) : launch_mlp_fused2<4, false>(a, stream);
+    if (p.trace != nullptr) return launch_mlp_fused2<3, true>(a, stream);     // debugging build with the clock64 event log
+    switch (mlp2_proj_q()) {
+      case 1: return launch_mlp_fused2<1, false>(a, stream);
+      case 2: return launch_mlp_fused2<2, false>(a, stream);
+      case 4: return launch_mlp_fused2<4, false>(a, stream);
+      case 5: return launch_mlp_fused2<5, false>(a, stream);
+      default: return launch_mlp_fused2<3, false>(a, stream);
+    }
   }
   return RVK_ERR_BAD_ARG;
 }
