@@ -12,22 +12,26 @@
 //
 // What makes two tiles fit:
 //   TMEM (512 columns): D1 [0,128) = two fc1 accumulators of 64 columns (the hidden dimension is walked in twelve half-chunks
-//         of 64; fc1 of half-chunk q+2 runs under the GELU arithmetic of q+1), D2[slot] [128+192*slot, +192) = per-tile
-//         accumulator that carries, in turn, the attention projection (read by the LayerNorm-on-load), then the projected
-//         residual row x_mid PARKED by tcgen05.st, then fc2 accumulating on top of it: the final epilogue reads
-//         x_mid + fc2(..) in one piece, so neither x_mid nor a residual re-read touches memory (HBM/L2 traffic per row:
-//         x in, ctx in, x out, ln out only).
-//   smem: A[slot] 2 x 48 KB (ctx tile, then the normalised rows), H[slot] 2 x 2 x 16 KB (two 64-column hidden panels per tile,
-//         ping-pong; reused as the staging buffer of ln_out in two rounds), a 4-stage ring of 12 KB weight stages (one stage
-//         = the three K panels of a W1 half-chunk, or one K panel of W2 / Wproj).
+//         of 64, ping-pong), D2[slot] [128+192*slot, +192) = per-tile accumulator that carries, in turn, the attention
+//         projection (read by the LayerNorm-on-load), then the projected residual row x_mid PARKED by tcgen05.st, then fc2
+//         accumulating on top of it: the final epilogue reads x_mid + fc2(..) in one piece, so neither x_mid nor a residual
+//         re-read touches memory (HBM/L2 traffic per row: x in, ctx in, x out, ln out only).
+//   The hidden activation never leaves TMEM: a GELU warp reads its 32 fp32 columns of D1[b] and writes the packed fp16 pairs back
+//         over the first 16 of the SAME columns; fc2 takes them from there as its A operand (tcgen05.mma.cta_group::2 with a
+//         TMEM A operand: each CTA of the pair supplies its own 128 rows), and the next fc1 into D1[b] is issued right behind
+//         that fc2 (tcgen05.mma of one thread execute in order).  No swizzled shared-memory stores / proxy fence per half-chunk.
+//   smem: A[slot] 2 x 48 KB (ctx tile, then the normalised rows), one 48 KB staging buffer for ln_out (handed from tile to tile
+//         through the stage_free barrier), a 5-stage ring of 12 KB weight stages (one stage = the three K panels of a W1
+//         half-chunk, or one K panel of W2 / Wproj).
 //   registers: a thread owns 96 columns of a row in the LayerNorm phases; it walks them as two pieces of 48 and re-reads the
 //         pieces (from TMEM on load, from its own x_out rows in the final epilogue) for the normalising pass.
 // The tensor-pipe program is static and identical in the producer and the issuer (tiles in order; inside tile i, per
-// half-chunk q: fc1(q+2) | [projection of tile i+1 at q = kProjQ] | fc2(q); the first two fc1 of tile i+1 take the place of
+// half-chunk q: fc2(q) | fc1(q+2) | [projection of tile i+1 at q = kProjQ]; the first two fc1 of tile i+1 take the place of
 // fc1(12), fc1(13)).
 //
-// Warp roles (576 threads, 112 registers each): w0 TMA producer, w1 UMMA issuer (leader CTA) + TMEM owner, w2..w9 group 0,
-// w10..w17 group 1; inside a group: team = 32-column half of a hidden half-chunk / 96-column half of a token row, quad = TMEM lane quadrant.
+// Warp roles (576 threads, 96 registers each: ptxas budgets registers for 640 threads): w0 TMA producer, w1 UMMA issuer (leader
+// CTA) + TMEM owner, w2..w9 group 0, w10..w17 group 1; inside a group: team = 32-column half of a hidden half-chunk / 96-column
+// half of a token row, quad = TMEM lane quadrant.
 #pragma once
 
 #include <cuda_fp16.h>
