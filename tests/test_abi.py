@@ -61,6 +61,19 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions(lib_path):
         assert mnemonic in out, f'{mnemonic} missing from SASS: not a tcgen05/TMA build'
 
 
+def test_fused_mlp_variants_are_validated_before_any_cuda_call(lib_path):
+    """cta_group of rvk_mlp_fused / rvk_attn_proj_mlp_fused: 1 = single CTAs, 2 = CTA pairs, 4 = CTA pairs with two row tiles in flight
+    (needs the folded projection, csrc/mlp_fused2.cuh); anything else, or 4 without the projection, is RVK_ERR_BAD_ARG.  The check
+    sits in front of the launch, so it runs without a GPU (the pointers are never dereferenced)."""
+    from rovitkan_b200 import _lib
+    fake = 4096
+    with pytest.raises(_lib.RovitKanError, match='bad argument'):
+        _lib.call('rvk_mlp_fused', *([fake] * 10), 1e-6, fake, 128, 4, 0)
+    with pytest.raises(_lib.RovitKanError, match='bad argument'):
+        _lib.call('rvk_attn_proj_mlp_fused', *([fake] * 13), 1e-6, fake, 128, 3, 0)
+    _lib.call('rvk_attn_proj_mlp_fused', *([fake] * 13), 1e-6, fake, 0, 4, 0)      # an empty batch is a no-op, not an error
+
+
 def test_module_mirror_matches_reference_layout_and_rejects_cpu():
     from rovitkan_b200.models import KANLayer, RoViTKAN
     m = RoViTKAN(pretrained=False)
