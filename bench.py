@@ -882,6 +882,20 @@ def headline(ctx, args, res, train):
     return line
 
 
+def guarded_sub(fn, world):
+    """A sub-benchmark (configs[2..4]) next to the headline.  On one GPU its failure is recorded in its own sub-object and the
+    headline line is still printed; with several ranks an exception stays fatal (the other ranks would wait in a barrier
+    or collective the failed rank never reaches, and torchrun tears the job down at once instead)."""
+    if world > 1:
+        return fn()
+    try:
+        return fn()
+    except Exception as e:
+        import traceback
+        traceback.print_exc(file=sys.stderr)
+        return {'error': repr(e)}
+
+
 def run_ours(args, rank, local_rank, world):
     ctx = Ctx(rank, local_rank, world)
     K, W = args.steps, max(3, args.warmup)
@@ -892,9 +906,9 @@ def run_ours(args, rank, local_rank, world):
         line = headline(ctx, args, res, False)
         if mode == 'all' and not args.no_subs:
             Ks = max(5, min(K, 20))
-            line['train'] = bench_train(ctx, Ks, W, 256)
-            line['kan'] = bench_kan(ctx, Ks, W, 65536)
-            line['sweep'] = bench_sweep(ctx, max(3, min(K, 8)), 3)
+            for key, fn in (('train', lambda: bench_train(ctx, Ks, W, 256)), ('kan', lambda: bench_kan(ctx, Ks, W, 65536)),
+                            ('sweep', lambda: bench_sweep(ctx, max(3, min(K, 8)), 3))):
+                line[key] = guarded_sub(fn, world)
             if rank == 0 and world == 1:
                 try:
                     line['gpu_eager_baseline'] = gpu_eager_baseline(ctx)

@@ -48,3 +48,16 @@ def test_reference_arm_other_ranks_stay_silent():
     out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2', '--steps', '1'],
                          capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ''
+
+
+def test_a_failing_sub_benchmark_does_not_take_the_headline_down_on_one_gpu():
+    sys.path.insert(0, ROOT)
+    import bench
+    import pytest
+
+    def boom():
+        raise RuntimeError('sub-benchmark failed')
+    assert bench.guarded_sub(lambda: {'value': 1.0}, 1) == {'value': 1.0}
+    assert 'sub-benchmark failed' in bench.guarded_sub(boom, 1)['error']
+    with pytest.raises(RuntimeError):            # several ranks: stay fatal, the peers would hang in the next collective
+        bench.guarded_sub(boom, 2)
