@@ -166,3 +166,46 @@ def test_trunk_weight_cache_key_follows_the_owner_parameters():
         assert len(seen) == 2
     finally:
         ops._lib.load, ops._lib.call, ops._stream = real_load, real_call, real_stream
+
+
+HOUSEKEEPING = {'rvk_abi_version', 'rvk_strerror', 'rvk_last_error', 'rvk_device_check', 'rvk_launch_count', 'rvk_stream_check',
+                'rvk_set_side_stream', 'rvk_debug_mbar_timeout', 'rvk_gemm_timing_enable', 'rvk_gemm_timing_collect',
+                'rvk_gemm_timing_kind', 'rvk_timing_enable', 'rvk_timing_collect', 'rvk_timing_kind', 'rvk_timing_kind_name',
+                'rvk_debug_set_mlp_trace', 'rvk_debug_set_attn_trace'}
+
+
+def test_every_compute_entry_point_refuses_null_pointers_with_a_status(lib_path):
+    """Error behaviour of the boundary: the C entry points never throw and never dereference an argument
+    they have not checked -- null pointers come back as RVK_ERR_BAD_ARG, which the binding turns into RovitKanError (a
+    RuntimeError, as the reference's callers would see from torch).  The checks sit in front of every CUDA call, so this
+    runs without a GPU."""
+    from rovitkan_b200 import _lib
+    lib = _lib.load()
+    assert issubclass(_lib.RovitKanError, RuntimeError)
+    checked = 0
+    for name, (res, args) in _lib.SIGNATURES.items():
+        if name in HOUSEKEEPING or res is not ctypes.c_int:
+            continue
+        vals = [None if a is ctypes.c_void_p else (0.5 if a in (ctypes.c_float, ctypes.c_double) else 1) for a in args]
+        assert getattr(lib, name)(*vals) == 1, f'{name}: null pointers must give RVK_ERR_BAD_ARG'
+        with pytest.raises(_lib.RovitKanError, match='bad argument'):
+            _lib.call(name, *vals)
+        checked += 1
+    assert checked >= 30
+    # size queries: a negative or null size table is refused the same way (no allocation request derived from it)
+    assert lib.rvk_optimizer_state_floats(1, None) == -1
+
+
+def test_knot_vector_other_than_the_reference_linspace_is_refused_at_the_boundary(lib_path):
+    """Every KAN kernel evaluates the closed uniform-knot cubic segments of the reference's linspace(-1, 1, 11) buffer
+    (models/kan.py:59-60); another knot vector, which the reference's Cox-de Boor recursion would accept, is refused with a
+    message instead of being evaluated as a different spline.  The check precedes the launch: no pointer is dereferenced."""
+    from rovitkan_b200 import _lib
+    fake = 4096
+    good = (ctypes.c_float * 11)(*[-1.0 + 0.2 * i for i in range(11)])
+    bad = (ctypes.c_float * 11)(*[-1.0 + 0.2 * i + (0.01 if i == 4 else 0.0) for i in range(11)])
+    with pytest.raises(_lib.RovitKanError, match='linspace'):
+        _lib.call('rvk_kan_layer_forward', fake, fake, fake, fake, bad, 11, 8, 192, 64, 0, fake, fake, 0, 0)
+    with pytest.raises(_lib.RovitKanError, match='not supported'):
+        _lib.call('rvk_kan_layer_forward', fake, fake, fake, fake, good, 9, 8, 192, 64, 0, fake, fake, 0, 0)
+    _lib.call('rvk_kan_layer_forward', fake, fake, fake, fake, good, 11, 0, 192, 64, 0, fake, fake, 0, 0)   # empty batch: no-op
