@@ -65,3 +65,20 @@ def test_all_reduce_gradients_world2_gloo():
     assert all(ok for _, ok, _ in res), res
     # plain: one flat trunk reduce + one coalesced heads reduce; overlapped: three trunk buckets + the heads reduce
     assert all(calls == (2, 4) for _, _, calls in res), res
+
+
+def test_bucket_stage_ranges_tile_the_backward_for_every_bucket_count():
+    """The overlapped schedule cuts the 14 backward stages (0 = final LayerNorm, 1 + j = block 11 - j, 13 = patch embedding)
+    into consecutive ranges; whatever the bucket count, the ranges must tile [0, 14) in order, every cut must fall on a block
+    boundary, and the block index from which the flat gradient is final must fall strictly until the last range (-1 = all)."""
+    sys.path.insert(0, ROOT)
+    from rovitkan_b200.dist import bucket_stage_ranges
+    for buckets in range(1, 14):
+        ranges = bucket_stage_ranges(buckets)
+        assert 1 <= len(ranges) <= min(buckets, 12)
+        assert ranges[0][0] == 0 and ranges[-1][1] == 14 and ranges[-1][2] == -1
+        for (b0, e0, f0), (b1, e1, f1) in zip(ranges[:-1], ranges[1:]):
+            assert e0 == b1 and b0 < e0 and b1 < e1
+            assert f0 > f1 and f0 == 11 - (e0 - 2)          # stage e0 - 1 was block f0: blocks >= f0 are complete
+    assert bucket_stage_ranges(1) == [(0, 14, -1)]
+    assert [r[2] for r in bucket_stage_ranges(12)] == list(range(11, 0, -1)) + [-1]
