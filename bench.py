@@ -627,7 +627,9 @@ def bench_train(ctx, K, W, batch, with_variants=True):
                        'whole_step_frac': value / ctx.world * TRAIN_FLOP_PER_IMG / 1e12 / pk['tflops_sustained']}
     if with_variants:
         # epochs 1-5 of the reference schedule (trainer.py:244-246): backbone frozen, only the 181 978 head parameters train
-        model.freeze_backbone()
+        import contextlib
+        with contextlib.redirect_stdout(sys.stderr):      # the module prints "Backbone frozen" like the reference (backbone.py:30);
+            model.freeze_backbone()                       # stdout carries the ONE JSON line only
         for p in params:
             p.grad = None
         opt, fused_tail = build_optimizer(model, fused_tail)
