@@ -1,0 +1,33 @@
+"""The oracle against the LIVE reference on randomised cases (build container only: skipped where the reference tree is absent,
+e.g. on the GPU box).  Complements tests/test_oracle_golden.py, which pins the oracle to committed vectors the reference
+produced: here shapes, weights, inputs, stages and focal parameters are drawn at random and the reference's own modules
+(`models/kan.py`, `models/heads.py`, `training/losses.py`) run side by side with the oracle, forward and backward."""
+
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.environ.get('ROVIT_REFERENCE', '/root/reference')
+
+pytestmark = pytest.mark.skipif(not os.path.exists(os.path.join(REF, 'models', 'kan.py')),
+                                reason='reference tree not present (GPU box): the committed golden vectors pin the oracle there')
+
+
+@pytest.mark.parametrize('seed', [0, 1])
+def test_oracle_matches_the_live_reference_on_random_cases(seed):
+    env = dict(os.environ, LIVE_SEED=str(seed), LIVE_CASES='10')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'tests', 'live_reference_check.py')], capture_output=True, text=True,
+                         timeout=600, cwd=ROOT, env=env)
+    assert out.returncode == 0, out.stderr[-3000:]
+    r = json.loads([l for l in out.stdout.splitlines() if l.startswith('{')][-1])
+    # fp32 on both sides; the only freedom is summation order (einsum vs the reference's per-pair loop): 1e-5 is ~50x measured
+    assert r['basis']['max_abs'] <= 1e-6 and r['basis']['dead_zone_exactly_zero_from_0.4'] is True
+    for family in ('kan_layer', 'kan_module'):
+        for k, v in r[family].items():
+            assert v <= 1e-5, (family, k, v)
+    assert r['heads']['max_rel'] <= 1e-5
+    assert r['losses']['max_rel_loss'] <= 1e-5 and r['losses']['max_rel_grad'] <= 1e-5
