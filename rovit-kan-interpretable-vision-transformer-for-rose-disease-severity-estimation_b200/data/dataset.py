@@ -1,10 +1,16 @@
 """`data.dataset` surface used by the reference (scripts/train.py:12,73-84,110-111; scripts/evaluate.py:10,40-54;
 scripts/run_ablation.py:26-42,147-152): `RoseLeafDataset` with `.samples` / `.classes` / `.get_class_weights()` and
-`create_dataloaders(...) -> (train, val, test)` whose train/val datasets are `Subset`s of one RoseLeafDataset."""
+`create_dataloaders(...) -> (train, val, test)` whose train/val datasets are `Subset`s of one RoseLeafDataset.
+
+Without image folders the dataset is synthetic, and its samples are REAL files: `scripts/run_ablation.py:34-42` and
+`scripts/run_baselines.py` re-open `samples[i]['path']` with PIL themselves (to swap the transform of a Subset), so every
+synthetic image is written once as a PNG under `$ROVITKAN_SYNTH_DIR` (default: `<tmp>/rovitkan_synthetic_<uid>`) and read back
+from there by both routes."""
 
 from __future__ import annotations
 
 import os
+import tempfile
 import zlib
 from typing import Dict, List, Optional
 
@@ -34,6 +40,25 @@ def synthetic_image(class_idx: int, index: int, size: int = IMAGE_SIZE) -> torch
     return (base + 0.08 * torch.randn(3, size, size, generator=g)).clamp_(0.0, 1.0)
 
 
+def synthetic_root() -> str:
+    return os.environ.get('ROVITKAN_SYNTH_DIR') or os.path.join(tempfile.gettempdir(), f'rovitkan_synthetic_{os.getuid()}')
+
+
+def _materialise(mode: str, class_name: str, class_idx: int, index: int) -> str:
+    """Path of the PNG of synthetic sample (class, index), written on first use (atomically: DataLoader workers and parallel
+    ranks may ask for the same file)."""
+    d = os.path.join(synthetic_root(), mode, class_name)
+    path = os.path.join(d, f'{index}.png')
+    if not os.path.exists(path):
+        from PIL import Image
+        os.makedirs(d, exist_ok=True)
+        pixels = (synthetic_image(class_idx, index) * 255.0).round().to(torch.uint8).permute(1, 2, 0).contiguous().numpy()
+        tmp = f'{path}.{os.getpid()}.tmp'
+        Image.fromarray(pixels).save(tmp, format='PNG', compress_level=1)
+        os.replace(tmp, path)
+    return path
+
+
 class RoseLeafDataset(Dataset):
     def __init__(self, root_dir, class_names: Optional[List[str]] = None, severity_map: Optional[Dict[str, int]] = None,
                  transform=None, mode: str = 'augmented'):
@@ -55,15 +80,13 @@ class RoseLeafDataset(Dataset):
             n = _synthetic_per_class()
             for ci, cname in enumerate(self.classes):
                 for i in range(n):
-                    self.samples.append({'path': f'synthetic://{mode}/{cname}/{i}', 'class_idx': ci,
-                                         'severity': int(self.severity_map[cname])})
+                    path = _materialise(mode, cname, ci, i + (0 if mode == 'augmented' else 1 << 20))
+                    self.samples.append({'path': path, 'class_idx': ci, 'severity': int(self.severity_map[cname])})
 
     def __len__(self) -> int:
         return len(self.samples)
 
     def _load(self, sample, idx):
-        if sample['path'].startswith('synthetic://'):
-            return synthetic_image(sample['class_idx'], idx + (0 if self.mode == 'augmented' else 1 << 20))
         from PIL import Image
         return Image.open(sample['path']).convert('RGB')
 

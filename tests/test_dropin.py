@@ -21,7 +21,8 @@ PLOT_STUBS = ("import sys\nfrom unittest import mock\n"
 
 def _run(code, cwd, timeout=300, env_extra=None):
     env = dict(os.environ, PYTHONPATH=ROOT, ROVITKAN_SYNTH_PER_CLASS='4', ROVITKAN_DATA_WORKERS='0', CUDA_VISIBLE_DEVICES='',
-               ROVITKAN_PRETRAINED='random')      # the reference's config asks for pretrained=True; no weights on this box
+               ROVITKAN_PRETRAINED='random',      # the reference's config asks for pretrained=True; no weights on this box
+               ROVITKAN_SYNTH_DIR=os.path.join(str(cwd), 'synthetic_images'))
     env.update(env_extra or {})
     return subprocess.run([sys.executable, '-c', code], cwd=str(cwd), env=env, capture_output=True, text=True, timeout=timeout)
 
@@ -128,7 +129,7 @@ def test_reference_modules_resolve_through_the_hook(tmp_path):
 
 
 @pytest.mark.skipif(not os.path.isdir(REFERENCE), reason='the reference tree is not on this machine')
-@pytest.mark.parametrize('script', ['train.py', 'evaluate.py'])
+@pytest.mark.parametrize('script', ['train.py', 'evaluate.py', 'run_ablation.py'])
 def test_unmodified_reference_scripts_run_up_to_the_cuda_boundary(tmp_path, script):
     """No GPU here and no reference tree on the GPU box, so this is as far as the unmodified scripts can be driven: every
     import, the synthetic dataloaders, RoViTKAN(embed_dim=...), build_optimizer, JointLoss, Trainer(...) and trainer.fit() up
@@ -136,6 +137,8 @@ def test_unmodified_reference_scripts_run_up_to_the_cuda_boundary(tmp_path, scri
     args = ['--data_root', str(tmp_path / 'nodata')]
     if script == 'train.py':
         args += ['--output_dir', str(tmp_path / 'out')]
+    elif script == 'run_ablation.py':            # its own flag spelling (run_ablation.py:45-106); 5 epochs x 7 experiments in --fast
+        args = ['--data-root', str(tmp_path / 'nodata'), '--output-dir', str(tmp_path / 'out'), '--fast', '--num-workers', '0']
     else:
         from rovitkan_b200.models import RoViTKAN
         ck = tmp_path / 'ck.pth'
@@ -152,12 +155,15 @@ def test_unmodified_reference_scripts_run_up_to_the_cuda_boundary(tmp_path, scri
     assert 'BOUNDARY' in r.stdout and 'no CPU fallback' in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
     if script == 'train.py':
         assert 'backbone: 5,524,416' in r.stdout and 'Backbone frozen' in r.stdout and 'Epoch 1/' in r.stdout
+    if script == 'run_ablation.py':
+        assert 'Experiment: full_model' in r.stdout and 'Backbone frozen' in r.stdout and 'Epoch 1/' in r.stdout
 
 
 # ----------------------------------------------------------------------------------------- the data package itself
 def test_synthetic_dataloaders_have_the_surface_the_scripts_use(tmp_path, monkeypatch):
     monkeypatch.setenv('ROVITKAN_SYNTH_PER_CLASS', '5')
     monkeypatch.setenv('ROVITKAN_DATA_WORKERS', '0')
+    monkeypatch.setenv('ROVITKAN_SYNTH_DIR', str(tmp_path / 'synthetic_images'))
     from rovitkan_b200.data.dataset import DEFAULT_CLASSES, RoseLeafDataset, create_dataloaders
     from rovitkan_b200.data.transforms import augmented_transforms, inference_transforms, original_transforms
     sev = {c: i for i, c in enumerate(DEFAULT_CLASSES)}
@@ -174,6 +180,14 @@ def test_synthetic_dataloaders_have_the_surface_the_scripts_use(tmp_path, monkey
     ds = RoseLeafDataset(tmp_path / 'o', DEFAULT_CLASSES, sev, transform=inference_transforms(), mode='original')
     a, b = ds[3][0], ds[3][0]
     assert torch.equal(a, b)                                    # deterministic without augmentation
+    # scripts/run_ablation.py:34-42 (TransformSubset) and run_baselines.py re-open samples[i]['path'] with PIL themselves to swap
+    # the transform of a Subset: synthetic samples are therefore real files, and both routes see the same pixels
+    from PIL import Image
+    tf = inference_transforms()
+    for i in (0, 7, len(ds) - 1):
+        assert os.path.isfile(ds.samples[i]['path'])
+        assert torch.equal(tf(Image.open(ds.samples[i]['path']).convert('RGB')), ds[i][0])
+    assert ds.samples[0]['path'] != base.samples[0]['path']     # the 'original' (test) images are not the training images
 
 
 def test_image_folders_are_read_when_present(tmp_path):
