@@ -83,3 +83,78 @@ def test_gelu_backward_is_the_derivative_of_the_forward_polynomial(grid):
     bwd = np.where(x >= 0, 1 - d, d)
     h = 1e-4
     assert np.abs((fwd(x + h) - fwd(x - h)) / (2 * h) - bwd).max() <= 2e-4
+
+
+# ------------------------------------------------------------------------------------------ the KAN basis device function on the host
+KAN_CU = os.path.join(os.path.dirname(COMMON), 'kan.cu')
+HARNESS = r'''
+#include <cmath>
+#define __device__
+#define __forceinline__ inline
+namespace {
+%s
+}
+extern "C" void basis_host(const float* t, int n, const float* knots, float* out, float* dout) {
+  Knots kn;
+  for (int i = 0; i < kKnots; ++i) kn.k[i] = knots[i];
+  for (int i = 0; i < n; ++i) {
+    float a[kKW], da[kKW];
+    const float tc = fminf(fmaxf(t[i], kn.k[0]), kn.k[kKnots - 1]);     // as kan_basis_kernel does (kan.py:16)
+    kan_basis_at<true>(tc, kn, a, da);
+    for (int k = 0; k < kNB; ++k) { out[i * kNB + k] = a[k]; dout[i * kNB + k] = da[k]; }
+  }
+}
+'''
+
+
+@pytest.fixture(scope='module')
+def basis_host(tmp_path_factory):
+    """`kan_basis_at` -- the closed-form truncated cubic B-spline every fp32 KAN kernel evaluates -- cut out of csrc/kan.cu
+    VERBATIM (constants + the function) and compiled for the host with g++: the device source itself runs on the CPU."""
+    import ctypes
+    import subprocess
+    src = open(KAN_CU).read()
+    cut = src[src.index('constexpr int kNB'):src.index('// the 8 packed activations')]
+    assert 'kan_basis_at' in cut and '__global__' not in cut
+    d = tmp_path_factory.mktemp('kan_host')
+    (d / 'h.cpp').write_text(HARNESS % cut)
+    subprocess.run(['g++', '-O1', '-ffp-contract=off', '-shared', '-fPIC', '-o', str(d / 'h.so'), str(d / 'h.cpp')], check=True)
+    lib = ctypes.CDLL(str(d / 'h.so'))
+
+    def run(t, knots):
+        t = np.ascontiguousarray(t, dtype=F).ravel()
+        k = np.ascontiguousarray(knots, dtype=F)
+        out, dout = np.zeros((t.size, 7), F), np.zeros((t.size, 7), F)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        lib.basis_host(p(t), ctypes.c_int(t.size), p(k), p(out), p(dout))
+        return out, dout
+    return run
+
+
+def test_device_basis_function_reproduces_the_reference_vectors_on_the_host(basis_host):
+    """Against tests/golden/kan_basis.npz = outputs of the reference's own BSplineBasis.compute_basis (models/kan.py:10-44) on
+    the knots, their +-1e-6 neighbours, the jump at 0.4 and 4096 random points."""
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'kan_basis.npz'))
+    t, want = g['t'].reshape(-1), g['basis'].reshape(-1, 7)
+    got, _ = basis_host(t, g['knots'])
+    assert np.abs(got - want).max() <= 2e-7
+    assert np.array_equal(got == 0, want == 0)                     # same support, incl. identically zero from t >= 0.4
+    # SURVEY.md section 4 known answers (RNG-free)
+    kat = {-1.0: [0] * 7, -0.9: [.0208333] + [0] * 6, 0.0: [0, 0, .1666667, .6666667, .1666666, 0, 0],
+           0.3: [0, 0, 0, .0208333, .4791667, .4791667, .0208333], 0.4: [0] * 7, 1.0: [0] * 7}
+    got, _ = basis_host(np.array(list(kat), F), g['knots'])
+    assert np.abs(got - np.array(list(kat.values()), F)).max() <= 2e-6
+
+
+def test_device_basis_derivative_matches_a_finite_difference_on_the_host(basis_host):
+    knots = np.linspace(-1, 1, 11).astype(F)
+    rng = np.random.default_rng(0)
+    t = rng.uniform(-0.99, 0.39, 4000).astype(F)
+    t = t[np.abs((t + 1) / 0.2 - np.round((t + 1) / 0.2)) > 0.02]        # stay inside one knot interval for the difference
+    h = F(1e-3)
+    lo, _ = basis_host(t - h, knots)
+    hi, _ = basis_host(t + h, knots)
+    _, d = basis_host(t, knots)
+    assert np.abs((hi - lo) / (2 * h) - d).max() <= 2e-2 * np.abs(d).max()     # O(h^2) + fp32 cancellation
+    _, dead = basis_host(np.array([0.4, 0.7, 1.0], F), knots)
+    assert not dead.any()
