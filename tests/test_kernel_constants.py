@@ -158,3 +158,28 @@ def test_device_basis_derivative_matches_a_finite_difference_on_the_host(basis_h
     assert np.abs((hi - lo) / (2 * h) - d).max() <= 2e-2 * np.abs(d).max()     # O(h^2) + fp32 cancellation
     _, dead = basis_host(np.array([0.4, 0.7, 1.0], F), knots)
     assert not dead.any()
+
+
+def test_tiled_residual_stream_layout_is_a_bijection(tmp_path):
+    """`xt_offset` / `xt_elem_offset` (common.cuh) place element (row, col) of the fp32 inference residual stream at
+    [32-row block][32-col panel][float4 index][lane][4].  Compiled from the header text for the host: every
+    (row < R, col < 192) must map to a distinct offset in [0, R * 192) for R a multiple of 32, and a warp (32 consecutive rows)
+    reading one float4 index of one panel must touch 512 contiguous bytes."""
+    import ctypes
+    import subprocess
+    text = open(COMMON).read()
+    cut = text[text.index('__host__ __device__ __forceinline__ size_t xt_offset'):text.index('#endif  // __CUDACC__')]
+    (tmp_path / 'x.cpp').write_text('#include <cstddef>\n#define __host__\n#define __device__\n#define __forceinline__ inline\n' + cut +
+                                    '\nextern "C" void offsets(int rows, long long* out) {\n'
+                                    '  for (int r = 0; r < rows; ++r) for (int c = 0; c < 192; ++c) out[r * 192 + c] = (long long)xt_elem_offset(r, c);\n}\n'
+                                    'extern "C" long long vec_offset(int row, int panel, int j) { return (long long)xt_offset(row, panel, j); }\n')
+    subprocess.run(['g++', '-O1', '-shared', '-fPIC', '-o', str(tmp_path / 'x.so'), str(tmp_path / 'x.cpp')], check=True)
+    lib = ctypes.CDLL(str(tmp_path / 'x.so'))
+    lib.vec_offset.restype = ctypes.c_longlong
+    rows = 256
+    out = np.zeros(rows * 192, np.int64)
+    lib.offsets(rows, out.ctypes.data_as(ctypes.c_void_p))
+    assert np.array_equal(np.sort(out), np.arange(rows * 192))
+    for panel, j, base_row in ((0, 0, 0), (5, 7, 96), (3, 2, 224)):
+        offs = np.array([lib.vec_offset(base_row + lane, panel, j) for lane in range(32)])
+        assert np.array_equal(offs - offs[0], 4 * np.arange(32))           # lane l -> floats [4 l, 4 l + 4): 512 contiguous bytes
