@@ -183,3 +183,38 @@ def test_tiled_residual_stream_layout_is_a_bijection(tmp_path):
     for panel, j, base_row in ((0, 0, 0), (5, 7, 96), (3, 2, 224)):
         offs = np.array([lib.vec_offset(base_row + lane, panel, j) for lane in range(32)])
         assert np.array_equal(offs - offs[0], 4 * np.arange(32))           # lane l -> floats [4 l, 4 l + 4): 512 contiguous bytes
+
+
+def test_dropout_rng_is_philox4x32_10(tmp_path):
+    """The dropout stream of the heads (`philox4x32_10`, `uniform01` in common.cuh) compiled from the header text for the host
+    and checked against the published Random123 known-answer vectors of Philox4x32-10; `uniform01` must be a 24-bit uniform
+    in [0, 1) keyed by (seed, offset, element index)."""
+    import ctypes
+    import subprocess
+    text = open(COMMON).read()
+    cut = text[text.index('__device__ __forceinline__ uint4 philox4x32_10'):text.index('__device__ __forceinline__ uint32_t smem_u32')]
+    shim = ('#include <cstdint>\n#define __device__\n#define __forceinline__ inline\n'
+            'struct uint4 { uint32_t x, y, z, w; }; struct uint2 { uint32_t x, y; };\n'
+            'static inline uint4 make_uint4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return uint4{a, b, c, d}; }\n'
+            'static inline uint2 make_uint2(uint32_t a, uint32_t b) { return uint2{a, b}; }\n'
+            'static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }\n')
+    (tmp_path / 'p.cpp').write_text(shim + cut.replace('#pragma unroll', '') +
+                                    '\nextern "C" void philox(const uint32_t* c, const uint32_t* k, uint32_t* out) {\n'
+                                    '  uint4 r = philox4x32_10(make_uint4(c[0], c[1], c[2], c[3]), make_uint2(k[0], k[1]));\n'
+                                    '  out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;\n}\n'
+                                    'extern "C" float uni(unsigned long long s, unsigned long long o, unsigned long long i) { return uniform01(s, o, i); }\n')
+    subprocess.run(['g++', '-O1', '-shared', '-fPIC', '-o', str(tmp_path / 'p.so'), str(tmp_path / 'p.cpp')], check=True)
+    lib = ctypes.CDLL(str(tmp_path / 'p.so'))
+    lib.uni.restype = ctypes.c_float
+    lib.uni.argtypes = [ctypes.c_ulonglong] * 3
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0), (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        out = (ctypes.c_uint32 * 4)()
+        lib.philox((ctypes.c_uint32 * 4)(*ctr), (ctypes.c_uint32 * 2)(*key), out)
+        assert tuple(out) == want, [hex(v) for v in out]
+    u = np.array([lib.uni(1234, 77, i) for i in range(20000)])
+    assert u.min() >= 0.0 and u.max() < 1.0 and np.all(u * 16777216 == np.round(u * 16777216))
+    assert abs(u.mean() - 0.5) < 0.01 and abs((u < 0.3).mean() - 0.3) < 0.01           # keep rate of p = 0.3 dropout
+    assert lib.uni(1234, 77, 5) != lib.uni(1234, 78, 5) != lib.uni(1235, 77, 5)
