@@ -147,10 +147,12 @@ struct LossParams {
   float* d_cls; float* d_ord; float* d_mu; float* d_lv; float* d_kan;   // local gradients (may be null)
 };
 
-__global__ void __launch_bounds__(256) joint_loss_kernel(const LossParams p) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  float l_cls = 0.0f, l_ord = 0.0f, l_unc = 0.0f, l_kan = 0.0f;
-  if (b < p.batch) {
+// The four per-sample loss terms of sample b (each already divided by its denominator) and, where the d_* pointers are set,
+// their local gradients.  A plain function of (p, b) so that tests/test_kernel_constants.py can compile it for the host and
+// check it against the reference-generated vectors without a GPU.
+__device__ __forceinline__ void joint_loss_sample(const LossParams& p, int b, float& l_cls, float& l_ord, float& l_unc,
+                                                  float& l_kan) {
+  {
     const float inv_b = 1.0f / static_cast<float>(p.batch);
     const int C = p.num_classes;
     {   // focal cross-entropy (losses.py:15-38)
@@ -204,6 +206,12 @@ __global__ void __launch_bounds__(256) joint_loss_kernel(const LossParams p) {
       if (p.d_kan != nullptr) p.d_kan[b] = 2.0f * d * inv_b;
     }
   }
+}
+
+__global__ void __launch_bounds__(256) joint_loss_kernel(const LossParams p) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  float l_cls = 0.0f, l_ord = 0.0f, l_unc = 0.0f, l_kan = 0.0f;
+  if (b < p.batch) joint_loss_sample(p, b, l_cls, l_ord, l_unc, l_kan);
   __shared__ float part[4][8];
   const float v[4] = {warp_sum(l_cls), warp_sum(l_ord), warp_sum(l_unc), warp_sum(l_kan)};
   if ((threadIdx.x & 31) == 0)

@@ -218,3 +218,96 @@ def test_dropout_rng_is_philox4x32_10(tmp_path):
     assert u.min() >= 0.0 and u.max() < 1.0 and np.all(u * 16777216 == np.round(u * 16777216))
     assert abs(u.mean() - 0.5) < 0.01 and abs((u < 0.3).mean() - 0.3) < 0.01           # keep rate of p = 0.3 dropout
     assert lib.uni(1234, 77, 5) != lib.uni(1234, 78, 5) != lib.uni(1235, 77, 5)
+
+
+# ------------------------------------------------------------------------------------------ the joint-loss device function on the host
+HEADS_CU = os.path.join(os.path.dirname(COMMON), 'heads.cu')
+LOSS_HARNESS = r'''
+#include <cmath>
+#include <cstddef>
+#include <cstring>
+#define __device__
+#define __forceinline__ inline
+static inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
+namespace {
+%s
+}
+extern "C" void loss_host(const float* cls, int C, const float* ordl, const float* mu, const float* lv, const float* kan,
+                          const long long* yc, const float* ys, const float* alpha, float gamma, int batch, float* sums,
+                          float* d_cls, float* d_ord, float* d_mu, float* d_lv, float* d_kan) {
+  LossParams p;
+  p.cls_logits = cls; p.num_classes = C; p.ord_logits = ordl; p.mu = mu; p.log_var = lv; p.kan = kan;
+  p.class_t = yc; p.sev_t = ys; p.alpha = alpha; p.gamma = gamma; p.batch = batch; p.sums = sums;
+  p.d_cls = d_cls; p.d_ord = d_ord; p.d_mu = d_mu; p.d_lv = d_lv; p.d_kan = d_kan;
+  for (int b = 0; b < batch; ++b) {
+    float l[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    joint_loss_sample(p, b, l[0], l[1], l[2], l[3]);
+    for (int i = 0; i < 4; ++i) sums[i] += l[i];
+  }
+}
+'''
+
+
+@pytest.fixture(scope='module')
+def loss_host(tmp_path_factory):
+    """`LossParams` + `joint_loss_sample` -- the per-sample arithmetic of the fused JointLoss kernel, forward terms and local
+    gradients -- cut verbatim out of csrc/heads.cu and compiled for the host."""
+    import ctypes
+    import subprocess
+    src = open(HEADS_CU).read()
+    cut = src[src.index('struct LossParams {'):src.index('__global__ void __launch_bounds__(256) joint_loss_kernel')]
+    assert 'joint_loss_sample' in cut and '__global__' not in cut
+    d = tmp_path_factory.mktemp('loss_host')
+    (d / 'l.cpp').write_text(LOSS_HARNESS % cut)
+    subprocess.run(['g++', '-O1', '-ffp-contract=off', '-shared', '-fPIC', '-o', str(d / 'l.so'), str(d / 'l.cpp')], check=True)
+    lib = ctypes.CDLL(str(d / 'l.so'))
+
+    def run(cls, ordl, mu, lv, kan, yc, ys, alpha, gamma=2.0):
+        c = lambda a, dt=F: None if a is None else np.ascontiguousarray(a, dtype=dt)
+        cls, ordl, mu, lv, kan, ys, alpha = c(cls), c(ordl), c(mu), c(lv), c(kan), c(ys), c(alpha)
+        yc = c(yc, np.int64)
+        outs = [np.zeros_like(a) if a is not None else None for a in (cls, ordl, mu, lv, kan)]
+        sums = np.zeros(4, F)
+        p = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+        lib.loss_host(p(cls), ctypes.c_int(cls.shape[1]), p(ordl), p(mu), p(lv), p(kan), p(yc), p(ys), p(alpha),
+                      ctypes.c_float(gamma), ctypes.c_int(cls.shape[0]), p(sums), *[p(o) for o in outs])
+        return sums, outs
+    return run
+
+
+def test_joint_loss_device_function_reproduces_the_reference_vectors_on_the_host(loss_host):
+    """tests/golden/losses.npz = the reference's JointLoss (training/losses.py:139-181, focal alpha given, gamma 2, weights
+    1 / 0.5 / 0.5) and its autograd gradients at stage 4; the stage gating itself is the launcher's (null pointers)."""
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'losses.npz'))
+    sums, (d_cls, d_ord, d_mu, d_lv, d_kan) = loss_host(g['in_cls_logits'], g['in_ordinal_logits'], g['in_mu'], g['in_log_var'],
+                                                        g['in_kan_severity'], g['yc'], g['ys'], g['alpha'])
+    for i, k in enumerate(('cls_loss', 'ord_loss', 'unc_loss', 'kan_loss')):
+        assert abs(float(sums[i]) - float(g['s4_' + k])) <= 2e-6 * max(1.0, abs(float(g['s4_' + k]))), k
+    total = sums[0] + 1.0 * sums[1] + 0.5 * sums[2] + 0.5 * sums[3]
+    assert abs(float(total) - float(g['s4_total_loss'])) <= 5e-6
+    for got, w, k in ((d_cls, 1.0, 'cls_logits'), (d_ord, 1.0, 'ordinal_logits'), (d_mu, 0.5, 'mu'), (d_lv, 0.5, 'log_var'),
+                      (d_kan, 0.5, 'kan_severity')):
+        want = g['s4_d_' + k]
+        assert np.abs(w * got - want).max() <= 1e-5 * np.abs(want).max() + 1e-8, k
+    # stage 1 = only the focal term reaches the total; its value and gradient do not depend on the other heads
+    s1, (d1, *_) = loss_host(g['in_cls_logits'], None, None, None, None, g['yc'], g['ys'], g['alpha'])
+    assert abs(float(s1[0]) - float(g['s1_cls_loss'])) <= 2e-6 and not s1[1:].any()
+    assert np.abs(d1 - g['s1_d_cls_logits']).max() <= 1e-5 * np.abs(g['s1_d_cls_logits']).max() + 1e-8
+
+
+def test_joint_loss_device_function_known_answer_and_label_guards(loss_host):
+    """SURVEY.md section 4 (1b): the RNG-free known answer of JointLoss(focal_alpha=None), and the label guards: an out-of-range
+    class label gives a NaN loss (loud) and a zero gradient instead of an out-of-bounds read; a non-integer focal gamma never
+    sees a negative base; fractional severities are compared as floats (`y > k`, losses.py:59)."""
+    cls = [[2, .5, -1, 0], [.1, .2, .3, .4]]
+    sums, _ = loss_host(cls, [[1, -1, -2], [.5, .5, -.5]], [[.5], [2.5]], [[0], [-1]], [[.3], [2]], [0, 3], [0, 3], None)
+    for got, want in zip(sums, (0.328758, 0.612614, -0.017607, 0.545000)):
+        assert abs(float(got) - want) <= 2e-6
+    assert abs(float(sums[0] + sums[1] + 0.5 * sums[2] + 0.5 * sums[3]) - 1.205068) <= 3e-6
+    s, (d, *_) = loss_host(cls, None, None, None, None, [7, 3], [0, 3], None)
+    assert np.isnan(s[0]) and not d[0].any() and np.isfinite(d[1]).all() and d[1].any()
+    s, (d, *_) = loss_host([[30.0, 0, 0, 0]], None, None, None, None, [0], [0], None, gamma=1.5)       # pt rounds to 1
+    assert np.isfinite(s[0]) and np.isfinite(d).all()
+    a, _ = loss_host(cls, [[1, -1, -2], [.5, .5, -.5]], None, None, None, [0, 3], [1.5, 0.5], None)
+    b, _ = loss_host(cls, [[1, -1, -2], [.5, .5, -.5]], None, None, None, [0, 3], [2.0, 1.0], None)
+    assert abs(float(a[1]) - float(b[1])) <= 1e-7             # [1.5 > k] == [2 > k] and [0.5 > k] == [1 > k] for integer k
