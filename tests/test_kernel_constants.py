@@ -311,3 +311,132 @@ def test_joint_loss_device_function_known_answer_and_label_guards(loss_host):
     a, _ = loss_host(cls, [[1, -1, -2], [.5, .5, -.5]], None, None, None, [0, 3], [1.5, 0.5], None)
     b, _ = loss_host(cls, [[1, -1, -2], [.5, .5, -.5]], None, None, None, [0, 3], [2.0, 1.0], None)
     assert abs(float(a[1]) - float(b[1])) <= 1e-7             # [1.5 > k] == [2 > k] and [0.5 > k] == [1 > k] for integer k
+
+
+# ------------------------------------------------------------------------------------------ the tensor-core KAN producer on the host
+KAN_TC = os.path.join(os.path.dirname(COMMON), 'kan_tc.cuh')
+TC_SHIM = r'''
+#include <algorithm>
+#include <cfenv>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#define __device__
+#define __forceinline__ inline
+#define __global__
+#define __restrict__
+using std::min;
+struct uint4 { uint32_t x, y, z, w; };
+static inline uint4 make_uint4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return uint4{a, b, c, d}; }
+static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline float __fadd_rd(float a, float b) {             // add.rd.f32
+  const int old = fegetround();
+  fesetround(FE_DOWNWARD);
+  volatile float va = a, vb = b;
+  volatile float r = va + vb;
+  fesetround(old);
+  return r;
+}
+static inline uint16_t bf16_rn(float f) {                       // cvt.rn.bf16.f32 (finite inputs)
+  uint32_t u; std::memcpy(&u, &f, 4);
+  return static_cast<uint16_t>((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+}
+struct __nv_bfloat162 { uint16_t x, y; };                       // .x = low half of the 32-bit word
+static inline __nv_bfloat162 __floats2bfloat162_rn(float a, float b) { return __nv_bfloat162{bf16_rn(a), bf16_rn(b)}; }
+static inline uint32_t pack_bf16x2(float lo, float hi) { return bf16_rn(lo) | (static_cast<uint32_t>(bf16_rn(hi)) << 16); }
+// the two MUFU approximations (ex2.approx, rcp.approx: ~2 ulp) are modelled by the exact operations
+static inline float ex2_approx(float x) { return exp2f(x); }
+static inline float kan_tc_tanh(float xe, float& rc) {
+  const float ex = ex2_approx(xe * 2.8853900817779268f);
+  rc = 1.0f / (ex + 1.0f);
+  return fmaf(-2.0f, rc, 1.0f);
+}
+struct Knots { float k[11]; };
+struct Dim3 { int x; };
+static Dim3 threadIdx;
+namespace {
+%s
+}
+extern "C" float host_tanhf(float x) { return tanhf(x); }
+extern "C" void thresholds(const float* knots, float* xthr12) {
+  Knots kn;
+  for (int i = 0; i < 11; ++i) kn.k[i] = knots[i];
+  for (int m = 0; m < 9; ++m) { threadIdx.x = m; kan_tc_thresholds_kernel(kn, xthr12); }
+  xthr12[9] = xthr12[10] = xthr12[11] = INFINITY;
+}
+extern "C" void expand(const float* x, int n, const float* xthr12, uint8_t* hi, uint8_t* lo) {
+  for (int i = 0; i < n; ++i) kan_tc_expand_store(x[i], 16u * i, hi, lo, xthr12);
+}
+'''
+
+
+@pytest.fixture(scope='module')
+def tc_producer(tmp_path_factory):
+    """`kan_tc_thresholds_kernel`, `kan_tc_interval` and `kan_tc_expand_store` -- the operand producer of the three tcgen05 KAN
+    kernels: interval by a round-down add, calibrated x-space thresholds next to a knot, Horner cubics, bf16 hi / lo split, one-hot
+    placement as a 128-bit shift -- cut verbatim out of csrc/kan_tc.cuh and compiled for the host (CUDA intrinsics shimmed)."""
+    import ctypes
+    import subprocess
+    src = open(KAN_TC).read()
+    a = src.index('__global__ void kan_tc_thresholds_kernel')
+    cut = src[a:src.index('// WpT (fp32', a)]
+    b = src.index('__device__ __forceinline__ void kan_tc_interval')
+    cut += src[b:src.index('// tanh x = 1 - 2 /', b)]
+    c = src.index('__device__ __forceinline__ void kan_tc_expand_store')
+    cut += src[c:src.index('__global__ void __launch_bounds__(kTcThreads, 1)', c)]
+    d = tmp_path_factory.mktemp('tc_host')
+    (d / 't.cpp').write_text(TC_SHIM % cut)
+    subprocess.run(['g++', '-O1', '-frounding-math', '-fno-strict-aliasing', '-ffp-contract=off', '-shared', '-fPIC', '-o',
+                    str(d / 't.so'), str(d / 't.cpp')], check=True)
+    lib = ctypes.CDLL(str(d / 't.so'))
+    lib.host_tanhf.restype = ctypes.c_float
+    lib.host_tanhf.argtypes = [ctypes.c_float]
+    # torch.linspace(-1, 1, 11) in fp32 (knots[5] = -1.49e-8, knots[7] = 0.39999998): numpy's linspace rounds differently
+    knots = np.load(os.path.join(ROOT, 'tests', 'golden', 'kan_basis.npz'))['knots'].astype(F)
+    xthr = np.zeros(12, F)
+    p = lambda arr: arr.ctypes.data_as(ctypes.c_void_p)
+    lib.thresholds(p(knots), p(xthr))
+
+    def expand(x):
+        x = np.ascontiguousarray(x, dtype=F)
+        hi, lo = np.zeros((x.size, 8), np.uint16), np.zeros((x.size, 8), np.uint16)
+        lib.expand(p(x), ctypes.c_int(x.size), p(xthr), p(hi), p(lo))
+        f = lambda h: (h.astype(np.uint32) << 16).view(F)
+        return f(hi), f(lo)
+    return lib, knots, xthr, expand
+
+
+def test_tensor_core_kan_producer_on_the_host(tc_producer, basis_host):
+    lib, knots, xthr, expand = tc_producer
+    assert knots.shape == (11,) and abs(float(knots[7]) - 0.4) < 1e-7
+    # thresholds: xthr[m] is the smallest float whose tanhf reaches knot m
+    for m in range(1, 8):
+        assert lib.host_tanhf(float(xthr[m])) >= knots[m] > lib.host_tanhf(float(np.nextafter(xthr[m], F(-np.inf))))
+    assert xthr[0] == -np.inf and np.all(np.isinf(xthr[8:]))
+    rng = np.random.default_rng(0)
+    near = np.concatenate([[np.nextafter(F(xthr[m]), F(s * np.inf)) if k else F(xthr[m]) for k in (0, 1, 2) for s in (-1, 1)]
+                           for m in range(1, 8)]).astype(F)
+    for m in range(1, 8):                                   # +-2 ulps as well
+        near = np.concatenate([near, [np.nextafter(np.nextafter(F(xthr[m]), F(np.inf)), F(np.inf)),
+                                      np.nextafter(np.nextafter(F(xthr[m]), F(-np.inf)), F(-np.inf))]]).astype(F)
+    x = np.concatenate([rng.normal(0, 1.5, 20000), rng.uniform(-0.01, 0.01, 500), near, [0.0, -0.0, 12.0, -12.0, 40.0, -40.0]]).astype(F)
+    hi, lo = expand(x)
+    got = hi.astype(np.float64) + lo.astype(np.float64)
+    # expected: the reference basis at t = tanhf(x) through the verbatim fp32 device function (itself pinned to the reference's
+    # vectors above), and the raw input in slot 7
+    t = np.array([lib.host_tanhf(float(v)) for v in x], F)
+    want, _ = basis_host(t, knots)
+    assert np.abs(got[:, :7] - want).max() <= 1e-5              # measured 4.1e-6: bf16 hi + lo = 16 mantissa bits, fast tanh 3e-7 in t
+    assert np.abs(got[:, 7] - x).max() <= 2.0 ** -16 * np.abs(x).max()
+    # identical interval decisions, also ON a threshold and one / two ulps either side: nothing outside the live window j-3 .. j,
+    # nothing at all in the dead zone tanh x >= 0.4
+    j = (t[:, None] >= knots[None, 1:]).sum(1)
+    slots = np.arange(7)[None, :]
+    outside = (slots > j[:, None]) | (slots < j[:, None] - 3) | (j[:, None] >= 7)
+    assert not hi[:, :7][outside].any() and not lo[:, :7][outside].any()
+    inside = ~outside & (want > 1e-6)
+    assert np.all(hi[:, :7][inside] > 0)
+    dead = t >= knots[7]
+    assert dead.sum() > 3000 and not got[dead, :7].any()
+    assert np.abs(got[~dead, :7].sum(1) - want[~dead].sum(1)).max() <= 2e-5
