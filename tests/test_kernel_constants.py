@@ -440,3 +440,51 @@ def test_tensor_core_kan_producer_on_the_host(tc_producer, basis_host):
     dead = t >= knots[7]
     assert dead.sum() > 3000 and not got[dead, :7].any()
     assert np.abs(got[~dead, :7].sum(1) - want[~dead].sum(1)).max() <= 2e-5
+
+
+def test_small_kan_segment_function_and_activations_on_the_host(tmp_path, basis_host):
+    """`kan_segment` (csrc/kan_small.cuh: the four live cubic segments without the one-hot placement -- what the small-layer
+    kernels and the fused heads + KAN tail evaluate) against `kan_basis_at`, itself pinned to the reference's vectors above; and
+    `act_grad` (the activation derivative recovered from the layer OUTPUT, kan.cu) against a finite difference of `kan_act`
+    (ReLU between the KAN layers, 3 * sigmoid on the last one: models/kan.py:138-149)."""
+    import ctypes
+    import subprocess
+    kan = open(KAN_CU).read()
+    small = open(os.path.join(os.path.dirname(COMMON), 'kan_small.cuh')).read()
+    consts = kan[kan.index('constexpr int kNB'):kan.index('// basis values (and optionally d/dt)')]
+    seg = small[small.index('template <bool DERIV>\n__device__ __forceinline__ bool kan_segment'):small.index('// sW[(i*8 + k) * NOUT + o]')]
+    act = small[small.index('__device__ __forceinline__ float kan_act'):small.index('template <int NOUT>\n__global__')]
+    agrad = kan[kan.index('__device__ __forceinline__ float act_grad'):kan.index('// ------------------------------------------------------------------ weight packing')]
+    (tmp_path / 's.cpp').write_text('#include <cmath>\n#define __device__\n#define __forceinline__ inline\nnamespace {\n' + consts + seg + act + agrad + '}\n'
+                                    'extern "C" int segment(float t, const float* knots, float* v, float* d) {\n'
+                                    '  Knots kn; for (int i = 0; i < kKnots; ++i) kn.k[i] = knots[i];\n'
+                                    '  int j = -1; float vv[4] = {0, 0, 0, 0}, dd[4] = {0, 0, 0, 0};\n'
+                                    '  const bool live = kan_segment<true>(t, kn, j, vv, dd);\n'
+                                    '  for (int m = 0; m < 4; ++m) { v[m] = vv[m]; d[m] = dd[m]; }\n'
+                                    '  return live ? j : -1;\n}\n'
+                                    'extern "C" float act_fwd(int a, float v) { return kan_act(a, v); }\n'
+                                    'extern "C" float act_bwd(int a, float y) { return act_grad(a, y); }\n')
+    subprocess.run(['g++', '-O1', '-ffp-contract=off', '-shared', '-fPIC', '-o', str(tmp_path / 's.so'), str(tmp_path / 's.cpp')], check=True)
+    lib = ctypes.CDLL(str(tmp_path / 's.so'))
+    lib.act_fwd.restype = lib.act_bwd.restype = ctypes.c_float
+    lib.act_fwd.argtypes = lib.act_bwd.argtypes = [ctypes.c_int, ctypes.c_float]
+    lib.segment.argtypes = [ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'kan_basis.npz'))
+    knots = g['knots'].astype(F)
+    t = np.clip(g['t'].reshape(-1), knots[0], knots[-1]).astype(F)
+    want, dwant = basis_host(t, knots)
+    got, dgot = np.zeros_like(want), np.zeros_like(dwant)
+    v, d = np.zeros(4, F), np.zeros(4, F)
+    for n, tv in enumerate(t):
+        j = lib.segment(float(tv), knots.ctypes.data_as(ctypes.c_void_p), v.ctypes.data_as(ctypes.c_void_p), d.ctypes.data_as(ctypes.c_void_p))
+        for m in range(4):
+            if j >= 0 and 0 <= j - m < 7:
+                got[n, j - m], dgot[n, j - m] = v[m], d[m]
+    assert np.abs(got - want).max() <= 2e-7 and np.abs(dgot - dwant).max() <= 2e-5 * np.abs(dwant).max()
+    assert np.array_equal(got == 0, want == 0)
+    for a in (0, 1, 2):
+        for z in (-3.0, -0.7, 0.3, 1.9, 4.0):
+            y = lib.act_fwd(a, z)
+            fd = (lib.act_fwd(a, z + 1e-2) - lib.act_fwd(a, z - 1e-2)) / 2e-2
+            assert abs(lib.act_bwd(a, y) - fd) <= 2e-3, (a, z)
+    assert lib.act_fwd(2, 0.0) == 1.5 and lib.act_fwd(1, -1.0) == 0.0 and lib.act_bwd(1, 0.0) == 0.0
