@@ -488,3 +488,44 @@ def test_small_kan_segment_function_and_activations_on_the_host(tmp_path, basis_
             fd = (lib.act_fwd(a, z + 1e-2) - lib.act_fwd(a, z - 1e-2)) / 2e-2
             assert abs(lib.act_bwd(a, y) - fd) <= 2e-3, (a, z)
     assert lib.act_fwd(2, 0.0) == 1.5 and lib.act_fwd(1, -1.0) == 0.0 and lib.act_bwd(1, 0.0) == 0.0
+
+
+def test_predict_decode_kernel_on_the_host(tmp_path):
+    """`predict_decode_kernel` (csrc/heads.cu: the epilogue of RoViTKAN.predict, rovit_kan.py:126-161 with heads.py:45-77) run
+    thread by thread on the host against the oracle's restatement: softmax, first-maximum argmax, the ordinal decode
+    p0 = c0, pk = ck - ck-1, p3 = 1 - c2 (negative entries included), its expected value, std = exp(log_var / 2)."""
+    import ctypes
+    import subprocess
+    import sys
+    import torch
+    sys.path.insert(0, ROOT)
+    from oracle import heads as oheads
+    src = open(HEADS_CU).read()
+    a = src.index('__global__ void predict_decode_kernel')
+    cut = src[a:src.index('// out = {cls, ord, unc, kan', a)]
+    (tmp_path / 'd.cpp').write_text('#include <cmath>\n#include <cstddef>\n#define __global__\n#define __restrict__\n'
+                                    'struct D3 { int x; }; static D3 blockIdx, blockDim, threadIdx;\n' + cut +
+                                    'extern "C" void decode(const float* cls, int C, const float* ordl, const float* lv, int batch, long long* idx,\n'
+                                    '                       float* probs, float* oprobs, float* osev, float* std_) {\n'
+                                    '  blockIdx.x = 0; blockDim.x = batch + 3;\n'
+                                    '  for (int b = 0; b < batch + 3; ++b) { threadIdx.x = b; predict_decode_kernel(cls, C, ordl, lv, batch, idx, probs, oprobs, osev, std_); }\n}\n')
+    subprocess.run(['g++', '-O1', '-ffp-contract=off', '-shared', '-fPIC', '-o', str(tmp_path / 'd.so'), str(tmp_path / 'd.cpp')], check=True)
+    lib = ctypes.CDLL(str(tmp_path / 'd.so'))
+    rng = np.random.default_rng(3)
+    B, C = 257, 4
+    cls = rng.normal(0, 2, (B, C)).astype(F)
+    cls[5] = [1.0, 3.0, 3.0, -1.0]                                # a tie: torch.argmax returns the first maximum
+    ordl = rng.normal(0, 2, (B, C - 1)).astype(F)                 # unordered cumulative logits -> some negative "probabilities"
+    lv = rng.uniform(-10, 10, (B, 1)).astype(F)
+    idx, probs, oprobs = np.full(B, -1, np.int64), np.zeros((B, C), F), np.zeros((B, C), F)
+    osev, std = np.zeros((B, 1), F), np.zeros((B, 1), F)
+    p = lambda arr: arr.ctypes.data_as(ctypes.c_void_p)
+    lib.decode(p(cls), ctypes.c_int(C), p(ordl), p(lv), ctypes.c_int(B), p(idx), p(probs), p(oprobs), p(osev), p(std))
+    tc, to, tl = torch.from_numpy(cls), torch.from_numpy(ordl), torch.from_numpy(lv)
+    want_probs = torch.softmax(tc, dim=1)
+    assert np.abs(probs - want_probs.numpy()).max() <= 2e-7
+    assert np.array_equal(idx, torch.argmax(want_probs, dim=1).numpy()) and idx[5] == 1
+    want_op = oheads.ordinal_probabilities(to).numpy()
+    assert np.abs(oprobs - want_op).max() <= 2e-7 and (want_op < 0).any()
+    assert np.abs(osev - oheads.ordinal_severity(to).numpy()).max() <= 1e-6
+    assert np.abs(std - torch.exp(0.5 * tl).numpy()).max() <= 1e-6 * float(torch.exp(0.5 * tl).max())
