@@ -529,3 +529,127 @@ def test_predict_decode_kernel_on_the_host(tmp_path):
     assert np.abs(oprobs - want_op).max() <= 2e-7 and (want_op < 0).any()
     assert np.abs(osev - oheads.ordinal_severity(to).numpy()).max() <= 1e-6
     assert np.abs(std - torch.exp(0.5 * tl).numpy()).max() <= 1e-6 * float(torch.exp(0.5 * tl).max())
+
+
+# ------------------------------------------------------------------------------------------ the fused optimizer tail on the host
+OPT_SHIM = r'''
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#define __global__
+#define __launch_bounds__(n)
+#define __grid_constant__
+#define __shared__ static
+#define __restrict__
+#define __device__
+#define __forceinline__ inline
+using std::isfinite;
+struct float4 { float x, y, z, w; };
+struct D3 { unsigned x; };
+static D3 threadIdx, blockIdx;
+static inline void __syncthreads() {}
+static inline float __shfl_xor_sync(unsigned, float v, int) { return v; }      // (the norm kernel is compiled, never run here)
+static inline void atomicAdd(float* p, float v) { *p += v; }
+namespace {
+%s
+}
+// table + hyper-parameters exactly as rvk_optimizer_step_impl fills them (optimizer.cu), then the update kernel block by block,
+// thread by thread (thread 0 first: it publishes the block's tensor index), then the finish kernel
+extern "C" void opt_step(int n, float** params, const float** grads, const long long* numel, const int* group, float* exp_avg,
+                         float* exp_avg_sq, float* state4, const double* lr, int n_groups, double beta1, double beta2, double eps,
+                         double weight_decay, float max_grad_norm, float grad_mult, const float* grad_scale, const float* found_inf) {
+  OptHyper H{};
+  for (int i = 0; i < n_groups; ++i) {
+    H.lr[i] = static_cast<float>(lr[i]); H.lr_d[i] = lr[i];
+    H.decay[i] = static_cast<float>(1.0 - lr[i] * weight_decay);
+  }
+  H.om_beta1 = static_cast<float>(1.0 - beta1); H.om_beta2 = static_cast<float>(1.0 - beta2);
+  H.beta1_d = beta1; H.beta2_d = beta2;
+  H.beta1 = static_cast<float>(beta1); H.beta2 = static_cast<float>(beta2); H.eps = static_cast<float>(eps);
+  H.weight_decay = static_cast<float>(weight_decay); H.max_norm = max_grad_norm;
+  H.grad_mult = grad_mult; H.grad_scale = grad_scale; H.found_inf = found_inf;
+  OptTable T{};
+  T.n = n;
+  int chunks = 0;
+  for (int i = 0; i < n; ++i) {
+    T.p[i] = params[i]; T.g[i] = grads[i]; T.chunk_start[i] = chunks; T.numel[i] = static_cast<int>(numel[i]);
+    T.group[i] = static_cast<unsigned char>(group[i]);
+    chunks += chunks_of(numel[i]);
+  }
+  T.chunk_start[n] = chunks;
+  for (int b = 0; b < chunks; ++b)
+    for (int t = 0; t < kOptThreads; ++t) { blockIdx.x = b; threadIdx.x = t; optim_update_kernel(T, H, exp_avg, exp_avg_sq, state4, 0); }
+  blockIdx.x = 0; threadIdx.x = 0;
+  optim_finish_kernel(H, state4);
+}
+extern "C" long long padded(long long numel) { return static_cast<long long>(chunks_of(numel)) * kChunk; }
+'''
+
+
+def test_fused_adamw_update_kernel_matches_torch_on_the_host(tmp_path):
+    """`optim_update_kernel` + `optim_finish_kernel` (csrc/optimizer.cu: GradScaler unscale + inf check + global-norm clip + AdamW
+    with the reference's two LR groups, training/trainer.py:118-129, training/optimizer.py:18-25) run on the host against
+    `clip_grad_norm_` + `torch.optim.AdamW` for three steps; the sum of squares the norm kernel would deliver is supplied."""
+    import ctypes
+    import subprocess
+    import torch
+    src = open(os.path.join(os.path.dirname(COMMON), 'optimizer.cu')).read()
+    cut = src[src.index('constexpr int kChunk'):src.index('}  // namespace')]
+    (tmp_path / 'o.cpp').write_text(OPT_SHIM % cut)
+    subprocess.run(['g++', '-O1', '-ffp-contract=off', '-shared', '-fPIC', '-o', str(tmp_path / 'o.so'), str(tmp_path / 'o.cpp')], check=True)
+    lib = ctypes.CDLL(str(tmp_path / 'o.so'))
+    lib.padded.restype = ctypes.c_longlong
+    lib.padded.argtypes = [ctypes.c_longlong]
+    torch.manual_seed(0)
+    sizes, groups, lrs = [5000, 17, 4096, 300, 1], [0, 0, 1, 1, 1], [1e-5, 1e-4]
+    ref = [torch.nn.Parameter(torch.randn(s)) for s in sizes]
+    opt = torch.optim.AdamW([{'params': ref[:2], 'lr': lrs[0]}, {'params': ref[2:], 'lr': lrs[1]}], weight_decay=1e-4, foreach=False)
+    ours = [p.detach().clone().numpy() for p in ref]
+    offs = np.cumsum([0] + [lib.padded(s) for s in sizes])
+    m, v, state = np.zeros(offs[-1], F), np.zeros(offs[-1], F), np.zeros(4, F)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+
+    def step(grads, scale=None, found_inf=None, max_norm=1.0):
+        total = np.float32(sum(float((g.astype(np.float64) ** 2).sum()) for g in grads))
+        state[0] = total
+        P = (ctypes.c_void_p * 5)(*[a.ctypes.data for a in ours])
+        G = (ctypes.c_void_p * 5)(*[g.ctypes.data for g in grads])
+        lib.opt_step(5, P, G, vp(np.array(sizes, np.int64)), vp(np.array(groups, np.int32)), vp(m), vp(v), vp(state),
+                     vp(np.array(lrs, np.float64)), 2, ctypes.c_double(0.9), ctypes.c_double(0.999), ctypes.c_double(1e-8),
+                     ctypes.c_double(1e-4), ctypes.c_float(max_norm), ctypes.c_float(1.0),
+                     None if scale is None else vp(scale), None if found_inf is None else vp(found_inf))
+
+    for it, gscale in enumerate((0.002, 0.05, 0.0005)):               # clipping active in the second step only
+        grads = [(torch.randn(s) * gscale) for s in sizes]
+        for p, g in zip(ref, grads):
+            p.grad = g.clone()
+        norm = torch.nn.utils.clip_grad_norm_(ref, 1.0)
+        opt.step()
+        step([g.numpy().copy() for g in grads])
+        assert state[1] == it + 1 and state[3] == 1.0 and state[0] == 0.0
+        assert abs(float(state[2]) - float(norm)) <= 2e-6 * float(norm)
+        assert (float(norm) > 1.0) == (it == 1)
+        for a, p, o in zip(ours, ref, offs):
+            assert np.abs(a - p.detach().numpy()).max() <= 2e-6 * float(p.detach().abs().max()), it
+            st = opt.state[p]
+            assert np.abs(m[o:o + a.size] - st['exp_avg'].numpy()).max() <= 2e-6 * float(st['exp_avg'].abs().max()) + 1e-12
+            assert np.abs(v[o:o + a.size] - st['exp_avg_sq'].numpy()).max() <= 2e-6 * float(st['exp_avg_sq'].abs().max()) + 1e-20
+    # GradScaler path: gradients arrive multiplied by the loss scale; a non-finite gradient or found_inf skips the step entirely
+    before = [a.copy() for a in ours]
+    grads = [np.random.default_rng(1).normal(0, 0.01, s).astype(F) for s in sizes]
+    bad = [g.copy() for g in grads]
+    bad[2][7] = np.inf
+    step(bad)
+    assert state[3] == 0.0 and state[1] == 3 and all(np.array_equal(a, b) for a, b in zip(ours, before))
+    step(grads, found_inf=np.ones(1, F))
+    assert state[3] == 0.0 and state[1] == 3 and all(np.array_equal(a, b) for a, b in zip(ours, before))
+    saved = ([a.copy() for a in ours], m.copy(), v.copy())
+    step([g * np.float32(1024.0) for g in grads], scale=np.full(1, 1024.0, F), found_inf=np.zeros(1, F))
+    assert state[3] == 1.0 and state[1] == 4
+    from_scaled = ([a.copy() for a in ours], m.copy(), v.copy())
+    for a, b in zip(ours, saved[0]):
+        a[...] = b
+    m[...], v[...], state[1] = saved[1], saved[2], 3
+    step(grads)                               # the same step from unscaled gradients: 1024 is a power of two, the unscale is exact
+    assert all(np.array_equal(a, b) for a, b in zip(ours, from_scaled[0]))
+    assert np.array_equal(m, from_scaled[1]) and np.array_equal(v, from_scaled[2]) and not all(np.array_equal(a, b) for a, b in zip(ours, before))
