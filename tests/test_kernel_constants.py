@@ -653,3 +653,63 @@ def test_fused_adamw_update_kernel_matches_torch_on_the_host(tmp_path):
     step(grads)                               # the same step from unscaled gradients: 1024 is a power of two, the unscale is exact
     assert all(np.array_equal(a, b) for a, b in zip(ours, from_scaled[0]))
     assert np.array_equal(m, from_scaled[1]) and np.array_equal(v, from_scaled[2]) and not all(np.array_equal(a, b) for a, b in zip(ours, before))
+
+
+def test_patch_gather_kernel_on_the_host(tmp_path):
+    """`im2col_kernel<FMT>` (csrc/encoder_kernels.cu: timm's PatchEmbed Conv2d(3,192,16,16) as a gather, fp32 / bf16 / uint8 pixels)
+    run thread by thread on the host: column = c*256 + ky*16 + kx (the flattened Conv2d weight), token 0 an all-zero row, fp32
+    pixels rounded to nearest-even bf16 (bit-exact against torch), uint8 pixels normalised as pixel * 1/(255 std) - mean/std
+    (the reference's ToTensor + Normalize folded in: within one bf16 ulp of the transform, exact against the folded form)."""
+    import ctypes
+    import subprocess
+    import torch
+    src = open(os.path.join(os.path.dirname(COMMON), 'encoder_kernels.cu')).read()
+    consts = src[src.index('constexpr int kD = 192;'):src.index('// ------------------------------------------------------------------ patch extraction')]
+    a = src.index('struct PixelNorm')
+    cut = consts + src[a:src.index('// table[0] = cls_token', a)]
+    shim = ('#include <cmath>\n#include <cstddef>\n#include <cstdint>\n#include <cstring>\n#define __global__\n#define __restrict__\n'
+            'struct uint4 { uint32_t x, y, z, w; }; struct uint2 { uint32_t x, y; }; struct float4 { float x, y, z, w; };\n'
+            'struct __nv_bfloat16 { uint16_t v; };\n'
+            'static inline uint4 make_uint4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return uint4{a, b, c, d}; }\n'
+            'static inline uint16_t bf16_rn(float f) { uint32_t u; std::memcpy(&u, &f, 4); return (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16); }\n'
+            'static inline uint32_t pack_bf16x2(float lo, float hi) { return bf16_rn(lo) | ((uint32_t)bf16_rn(hi) << 16); }\n'
+            'struct D3 { unsigned x; }; static D3 threadIdx, blockIdx, blockDim;\n')
+    run = ('\ntemplate <int FMT> static void run(const void* img, uint16_t* out, int batch, const float* n6) {\n'
+           '  PixelNorm nrm{}; for (int i = 0; i < 3; ++i) { nrm.scale[i] = n6[i]; nrm.shift[i] = n6[3 + i]; }\n'
+           '  const long long threads = (long long)batch * kTok * 3 * 32;\n'
+           '  blockDim.x = 256;\n'
+           '  for (long long t = 0; t < threads + 64; ++t) { blockIdx.x = (unsigned)(t / 256); threadIdx.x = (unsigned)(t % 256);\n'
+           '    im2col_kernel<FMT>(img, reinterpret_cast<__nv_bfloat16*>(out), batch, nrm); }\n}\n'
+           'extern "C" void gather(int fmt, const void* img, uint16_t* out, int batch, const float* n6) {\n'
+           '  if (fmt == 0) run<0>(img, out, batch, n6); else if (fmt == 1) run<1>(img, out, batch, n6); else run<2>(img, out, batch, n6);\n}\n')
+    (tmp_path / 'g.cpp').write_text(shim + cut + run)
+    subprocess.run(['g++', '-O1', '-ffp-contract=off', '-fno-strict-aliasing', '-shared', '-fPIC', '-o', str(tmp_path / 'g.so'), str(tmp_path / 'g.cpp')], check=True)
+    lib = ctypes.CDLL(str(tmp_path / 'g.so'))
+    vp = lambda arr: arr.ctypes.data_as(ctypes.c_void_p)
+    B = 2
+    g = torch.Generator().manual_seed(0)
+    img = torch.randn(B, 3, 224, 224, generator=g)
+
+    def unfold(x):          # (B,3,224,224) -> (B,197,768), column c*256 + ky*16 + kx, row 0 zero
+        p = x.reshape(B, 3, 14, 16, 14, 16).permute(0, 2, 4, 1, 3, 5).reshape(B, 196, 768)
+        return torch.cat([torch.zeros(B, 1, 768, dtype=x.dtype), p], dim=1)
+    bits = lambda t: t.to(torch.bfloat16).view(torch.int16).numpy().astype(np.uint16)
+    zero6 = np.zeros(6, F)
+    out = np.full((B, 197, 768), 0xffff, np.uint16)
+    lib.gather(0, vp(img.numpy()), vp(out), B, vp(zero6))
+    assert np.array_equal(out, bits(unfold(img)))                                          # fp32 pixels: bit-exact
+    out1 = np.full_like(out, 0xffff)
+    img16 = np.ascontiguousarray(bits(img))
+    lib.gather(1, vp(img16), vp(out1), B, vp(zero6))
+    assert np.array_equal(out1, out)                                                       # bf16 pixels: identical result
+    u8 = torch.randint(0, 256, (B, 3, 224, 224), generator=g, dtype=torch.uint8)
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    n6 = np.array([1.0 / (255.0 * s) for s in std] + [-m / s for m, s in zip(mean, std)], F)
+    out2 = np.full_like(out, 0xffff)
+    lib.gather(2, vp(np.ascontiguousarray(u8.numpy())), vp(out2), B, vp(n6))
+    folded = torch.from_numpy(np.float32(u8.numpy()) * n6[:3].reshape(1, 3, 1, 1) + n6[3:].reshape(1, 3, 1, 1))   # one rounding less than fmaf
+    normal = (u8.float() / 255.0 - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+    got = torch.from_numpy(out2.astype(np.int16)).view(torch.bfloat16).float()
+    assert float((got - unfold(normal)).abs().max()) <= 2.0 ** -7 * 2.7                   # one bf16 ulp at |x| <= 2.7
+    assert float((got - unfold(folded)).abs().max()) <= 2.0 ** -7 * 2.7 and float((got - unfold(folded)).abs().mean()) < 2e-3
+    assert not out2[:, 0].any() and not out[:, 0].any()
