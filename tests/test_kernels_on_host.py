@@ -133,3 +133,68 @@ def test_layernorm_backward_kernel_on_the_host(layernorm_lib, rows, grid, with_d
     assert np.abs(dcol - want_dx.sum(0).numpy()).max() <= 2e-5 * float(want_dx.sum(0).abs().max())
     got_b = torch.from_numpy(dxb.astype(np.int16)).view(torch.bfloat16).float()
     assert float((got_b - want_dx).abs().max()) <= 2.0 ** -8 * float(want_dx.abs().max())
+
+
+# ------------------------------------------------------------------------------------------ the fp32 KAN layer kernels
+@pytest.fixture(scope='module')
+def kan_lib(tmp_path_factory):
+    k = read('kan.cu')
+    body = ('namespace {\n' + between(k, 'constexpr int kNB = 7;', 'int pad_to(int v, int m)') + '}\n' + r'''
+static int pad_to_(int v, int m) { return (v + m - 1) / m * m; }
+// the launch sequence of rvk_kan_layer_fwd_launch / rvk_kan_layer_bwd_launch (kan.cu) for the fp32 CUDA-core path
+extern "C" void kan_layer(const float* x, const float* spline, const float* lin_w, const float* lin_b, const float* knots, int batch,
+                          int n_in, int n_out, int act, int spt, float* y, const float* gy, float* dx, float* dspline, float* dlin_w,
+                          float* dlin_b) {
+  Knots kn;
+  for (int i = 0; i < kKnots; ++i) kn.k[i] = knots[i];
+  const int in_pad = pad_to_(n_in, 16), out_pad = pad_to_(n_out, 64);
+  const long long wp = static_cast<long long>(in_pad) * 8 * out_pad;
+  std::vector<float> ws(3 * wp, -7.0f);                 // workspaces come uninitialised
+  float *Wp = ws.data(), *WpT = ws.data() + wp, *dWp = ws.data() + 2 * wp;
+  EmuDim b256; b256.x = 256;
+  EmuDim g; g.x = static_cast<unsigned>(std::min<long long>((wp + 255) / 256, 1184));
+  emu_launch(g, b256, 0, [=] { kan_pack_kernel(spline, lin_w, n_in, n_out, in_pad, out_pad, Wp, WpT); });
+  EmuDim gf; gf.y = out_pad / kTO;
+  if (spt == 1) { gf.x = (batch + 15) / 16; emu_launch(gf, b256, 0, [=] { kan_fwd_kernel<1>(x, Wp, lin_b, kn, y, act, batch, n_in, n_out, in_pad, out_pad); }); }
+  else { gf.x = (batch + kTS - 1) / kTS; emu_launch(gf, b256, 0, [=] { kan_fwd_kernel<4>(x, Wp, lin_b, kn, y, act, batch, n_in, n_out, in_pad, out_pad); }); }
+  if (gy == nullptr) return;
+  std::fill(dWp, dWp + wp, 0.0f);                        // cudaMemsetAsync
+  const int tiles = (in_pad / kIC) * (out_pad / kTO);
+  int splits = (2 * 148 + tiles - 1) / tiles;
+  const int sub_tiles = (batch + kTS - 1) / kTS;
+  if (splits > sub_tiles) splits = sub_tiles;
+  const int sps = ((sub_tiles + splits - 1) / splits) * kTS;
+  splits = (batch + sps - 1) / sps;
+  EmuDim gw; gw.x = in_pad / kIC; gw.y = out_pad / kTO; gw.z = splits;
+  emu_launch(gw, b256, 0, [=] { kan_bwd_w_kernel(x, y, gy, act, kn, dWp, dlin_b, batch, n_in, n_out, out_pad, sps); });
+  const long long tot = static_cast<long long>(n_in) * n_out * 8;
+  EmuDim gu; gu.x = static_cast<unsigned>(std::min<long long>((tot + 255) / 256, 1184));
+  emu_launch(gu, b256, 0, [=] { kan_unpack_grad_kernel(dWp, n_in, n_out, out_pad, dspline, dlin_w); });
+  EmuDim gx; gx.x = (batch + kTS - 1) / kTS; gx.y = (n_in + kDxIC - 1) / kDxIC;
+  emu_launch(gx, b256, 0, [=] { kan_bwd_x_kernel(x, y, gy, act, kn, WpT, dx, batch, n_in, n_out, in_pad, out_pad); });
+}
+''')
+    lib = compile_host(tmp_path_factory.mktemp('kan'), 'kan', body)
+    P, I = ctypes.c_void_p, ctypes.c_int
+    lib.kan_layer.argtypes = [P, P, P, P, P, I, I, I, I, I, P, P, P, P, P, P]
+    return lib
+
+
+@pytest.mark.parametrize('tag,spt', [('l0', 1), ('l1', 1), ('l2', 4), ('odd', 1), ('odd', 4)])
+def test_kan_layer_kernels_reproduce_the_reference_on_the_host(kan_lib, tag, spt):
+    """The fused KAN layer as the library launches it below batch 8192 -- `kan_pack_kernel` -> `kan_fwd_kernel<SPT>`; backward
+    `kan_bwd_w_kernel` -> `kan_unpack_grad_kernel`, `kan_bwd_x_kernel` -- against tests/golden/kan_layers.npz: outputs and autograd
+    gradients of the reference's own KANLayer (models/kan.py:70-95: tanh, truncated basis, per-pair loop, linear branch on the raw
+    input) for 192->64, 64->16, 16->1 and a ragged 10->3 layer at batch 7."""
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'kan_layers.npz'))
+    c = lambda k: np.ascontiguousarray(g[f'{tag}_{k}'], dtype=F)
+    x, sw, lw, lb, gy, knots = c('x'), c('sw'), c('lw'), c('lb'), c('gy'), c('knots')
+    batch, n_in = x.shape
+    n_out = lw.shape[0]
+    y, dx = np.full((batch, n_out), np.nan, F), np.full((batch, n_in), np.nan, F)
+    dsw, dlw, dlb = np.zeros_like(sw), np.zeros_like(lw), np.zeros_like(lb)          # gradients accumulate (+=)
+    kan_lib.kan_layer(vp(x), vp(sw), vp(lw), vp(lb), vp(knots), batch, n_in, n_out, 0, spt, vp(y), vp(gy), vp(dx), vp(dsw), vp(dlw), vp(dlb))
+    for got, key in ((y, 'y'), (dx, 'dx'), (dsw, 'dsw'), (dlw, 'dlw'), (dlb, 'dlb')):
+        want = c(key)
+        assert np.isfinite(got).all(), key
+        assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max() + 1e-6, (key, float(np.abs(got - want).max()), float(np.abs(want).max()))
