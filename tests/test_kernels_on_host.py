@@ -198,3 +198,116 @@ def test_kan_layer_kernels_reproduce_the_reference_on_the_host(kan_lib, tag, spt
         want = c(key)
         assert np.isfinite(got).all(), key
         assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max() + 1e-6, (key, float(np.abs(got - want).max()), float(np.abs(want).max()))
+
+
+# ------------------------------------------------------------------------------------------ the small-output KAN kernels
+@pytest.fixture(scope='module')
+def kan_small_lib(tmp_path_factory):
+    k, s = read('kan.cu'), read('kan_small.cuh')
+    cut = between(s, 'constexpr int kSmThreads', '// few outputs: always')
+    dyn = 'extern __shared__ __align__(16) float sm_small[];'
+    assert cut.count(dyn) == 2
+    cut = cut.replace(dyn, 'float* sm_small = static_cast<float*>(emu_dynamic_smem());')
+    body = ('namespace {\n' + between(k, 'constexpr int kNB = 7;', '// basis values (and optionally d/dt)')
+            + between(k, '__device__ __forceinline__ float act_grad', '// ------------------------------------------------------------------ weight packing')
+            + cut + '}\n' + r'''
+// launch geometry of kan_small_fwd_launch_t / kan_small_bwd_launch_t (kan_small.cuh), 148 SMs
+template <int NOUT>
+static void run_small(const float* x, const float* spline, const float* lin_w, const float* lin_b, const Knots& kn, int batch, int n_in,
+                      int n_out, int act, float* y, const float* gy, float* dx, float* dspline, float* dlin_w, float* dlin_b) {
+  EmuDim blk; blk.x = kSmThreads;
+  {
+    const int warps = kSmThreads / 32;
+    int grid = (batch + warps - 1) / warps;
+    if (grid > 148 * 4) grid = 148 * 4;
+    EmuDim g; g.x = grid;
+    emu_launch(g, blk, static_cast<size_t>(n_in) * kKW * NOUT * 4,
+               [=] { kan_small_fwd_kernel<NOUT>(x, spline, lin_w, lin_b, kn, y, act, batch, n_in, n_out); });
+  }
+  if (gy == nullptr) return;
+  constexpr int OQ = NOUT <= 4 ? 1 : NOUT / 4;
+  constexpr int OPT = NOUT < 4 ? NOUT : 4;
+  const int G = kSmThreads / (n_in * OQ);
+  int ctas = 148 * 4;
+  const int min_per_cta = G * 8;
+  if (static_cast<long long>(ctas) * min_per_cta > batch) ctas = (batch + min_per_cta - 1) / min_per_cta;
+  if (ctas < 1) ctas = 1;
+  const int spc = (batch + ctas - 1) / ctas;
+  ctas = (batch + spc - 1) / spc;
+  EmuDim g; g.x = ctas;
+  emu_launch(g, blk, static_cast<size_t>(n_in * kKW * NOUT + (kKW * OPT + OPT) * kSmThreads) * 4,
+             [=] { kan_small_bwd_kernel<NOUT>(x, y, gy, spline, lin_w, kn, act, dx, dspline, dlin_w, dlin_b, batch, n_in, n_out, spc); });
+}
+extern "C" void kan_small(const float* x, const float* spline, const float* lin_w, const float* lin_b, const float* knots, int batch,
+                          int n_in, int n_out, int act, float* y, const float* gy, float* dx, float* dspline, float* dlin_w,
+                          float* dlin_b) {
+  Knots kn;
+  for (int i = 0; i < kKnots; ++i) kn.k[i] = knots[i];
+#define RUN(N) run_small<N>(x, spline, lin_w, lin_b, kn, batch, n_in, n_out, act, y, gy, dx, dspline, dlin_w, dlin_b)
+  if (n_out <= 1) RUN(1); else if (n_out <= 2) RUN(2); else if (n_out <= 4) RUN(4); else if (n_out <= 8) RUN(8); else RUN(16);
+}
+''')
+    lib = compile_host(tmp_path_factory.mktemp('kan_small'), 'kan_small', body)
+    P, I = ctypes.c_void_p, ctypes.c_int
+    lib.kan_small.argtypes = [P, P, P, P, P, I, I, I, I, P, P, P, P, P, P]
+    return lib
+
+
+@pytest.mark.parametrize('tag', ['l1', 'l2', 'odd'])
+def test_small_kan_kernels_reproduce_the_reference_on_the_host(kan_small_lib, tag):
+    """`kan_small_fwd_kernel` / `kan_small_bwd_kernel` (the kernels the library actually launches for the 64->16 and 16->1 layers
+    of the production stack and the 64->1 layer of the microbenchmark: warp per sample forward; ONE backward kernel for dx, dW,
+    dWl, db with shared-memory accumulators, shuffles between output quads and a per-CTA flush) against the reference's KANLayer."""
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'kan_layers.npz'))
+    c = lambda k: np.ascontiguousarray(g[f'{tag}_{k}'], dtype=F)
+    x, sw, lw, lb, gy, knots = c('x'), c('sw'), c('lw'), c('lb'), c('gy'), c('knots')
+    batch, n_in = x.shape
+    n_out = lw.shape[0]
+    y, dx = np.full((batch, n_out), np.nan, F), np.full((batch, n_in), np.nan, F)
+    dsw, dlw, dlb = np.zeros_like(sw), np.zeros_like(lw), np.zeros_like(lb)
+    kan_small_lib.kan_small(vp(x), vp(sw), vp(lw), vp(lb), vp(knots), batch, n_in, n_out, 0, vp(y), vp(gy), vp(dx), vp(dsw), vp(dlw), vp(dlb))
+    for got, key in ((y, 'y'), (dx, 'dx'), (dsw, 'dsw'), (dlw, 'dlw'), (dlb, 'dlb')):
+        want = c(key)
+        assert np.isfinite(got).all(), key
+        assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max() + 1e-6, (key, float(np.abs(got - want).max()), float(np.abs(want).max()))
+
+
+def test_kan_stack_on_the_host_matches_the_reference_module(kan_lib, kan_small_lib):
+    """KANSeverityModule (models/kan.py:138-149) as the library chains it below batch 8192: 192->64 through the general kernels
+    with the ReLU fused (act 1), 64->16 (ReLU) and 16->1 (3 * sigmoid, act 2) through the small-output kernels; forward and the
+    input gradient through all three layers against the reference module's output / autograd (golden `mod_*`, seed 11)."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from oracle import kan as okan
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'kan_layers.npz'))
+    x, gy, want_y, want_dx = (np.ascontiguousarray(g[k], dtype=F) for k in ('mod_x', 'mod_gy', 'mod_y', 'mod_dx'))
+    torch.manual_seed(11)                                   # the module's parameters are re-derived from the seed of make_golden.py
+    layers = []
+    for a, b in ((192, 64), (64, 16), (16, 1)):
+        sw = torch.randn(a, b, 7) * 0.1
+        lin = torch.nn.Linear(a, b)
+        layers.append((sw.numpy().copy(), lin.weight.detach().numpy().copy(), lin.bias.detach().numpy().copy()))
+    knots = np.ascontiguousarray(g['l0_knots'], dtype=F)
+    check = okan.severity_forward(torch.from_numpy(x), [tuple(torch.from_numpy(t) for t in l) for l in layers], torch.from_numpy(knots))
+    if float((check - torch.from_numpy(want_y)).abs().max()) > 1e-5:
+        pytest.skip('torch RNG stream differs from the one the golden file was made with')
+    acts, ys, cur = (1, 1, 2), [], x
+    for li, (sw, lw, lb) in enumerate(layers):
+        y = np.full((x.shape[0], lw.shape[0]), np.nan, F)
+        if li == 0:
+            kan_lib.kan_layer(vp(cur), vp(sw), vp(lw), vp(lb), vp(knots), x.shape[0], lw.shape[1], lw.shape[0], acts[li], 1, vp(y), None, None, None, None, None)
+        else:
+            kan_small_lib.kan_small(vp(cur), vp(sw), vp(lw), vp(lb), vp(knots), x.shape[0], lw.shape[1], lw.shape[0], acts[li], vp(y), None, None, None, None, None)
+        ys.append(y)
+        cur = y
+    assert np.abs(ys[-1] - want_y).max() <= 1e-5 and ys[-1].min() >= 0.0 and ys[-1].max() <= 3.0
+    grad, ins = gy, [x] + ys[:-1]
+    for li in (2, 1, 0):
+        sw, lw, lb = layers[li]
+        dx = np.full_like(ins[li], np.nan)
+        dsw, dlw, dlb, yy = np.zeros_like(sw), np.zeros_like(lw), np.zeros_like(lb), ys[li].copy()
+        fn = kan_lib.kan_layer if li == 0 else kan_small_lib.kan_small
+        args = [vp(ins[li]), vp(sw), vp(lw), vp(lb), vp(knots), x.shape[0], lw.shape[1], lw.shape[0], acts[li]] + ([1] if li == 0 else [])
+        fn(*args, vp(yy), vp(np.ascontiguousarray(grad)), vp(dx), vp(dsw), vp(dlw), vp(dlb))
+        grad = dx
+    assert np.abs(grad - want_dx).max() <= 2e-5 * np.abs(want_dx).max() + 1e-7
