@@ -60,6 +60,8 @@ static inline float __bfloat162float(__nv_bfloat16 h) { return __uint_as_float(s
 static inline __nv_bfloat162 __floats2bfloat162_rn(float a, float b) { return __nv_bfloat162{emu_bf16_rn(a), emu_bf16_rn(b)}; }
 static inline uint32_t pack_bf16x2(float lo, float hi) { return emu_bf16_rn(lo) | (static_cast<uint32_t>(emu_bf16_rn(hi)) << 16); }
 static inline float2 unpack_bf16x2(uint32_t v) { return float2{__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u)}; }
+template <class T> static inline T __ldg(const T* p) { return *p; }
+static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return static_cast<uint32_t>((static_cast<uint64_t>(a) * b) >> 32); }
 static inline void griddep_wait() {}                   // programmatic dependent launch: nothing to wait for here
 static inline void griddep_launch_dependents() {}
 

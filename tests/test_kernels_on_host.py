@@ -311,3 +311,126 @@ def test_kan_stack_on_the_host_matches_the_reference_module(kan_lib, kan_small_l
         fn(*args, vp(yy), vp(np.ascontiguousarray(grad)), vp(dx), vp(dsw), vp(dlw), vp(dlb))
         grad = dx
     assert np.abs(grad - want_dx).max() <= 2e-5 * np.abs(want_dx).max() + 1e-7
+
+
+# ------------------------------------------------------------------------------------------ the fused multi-task tail (north_star (c))
+HEAD_KEYS = ['classification_head.fc1.weight', 'classification_head.fc1.bias', 'classification_head.fc2.weight', 'classification_head.fc2.bias',
+             'ordinal_head.fc1.weight', 'ordinal_head.fc1.bias', 'ordinal_head.fc2.weight', 'ordinal_head.fc2.bias',
+             'uncertainty_head.fc1.weight', 'uncertainty_head.fc1.bias', 'uncertainty_head.fc_mu.weight', 'uncertainty_head.fc_mu.bias',
+             'uncertainty_head.fc_logvar.weight', 'uncertainty_head.fc_logvar.bias'] + [
+    f'kan_module.kan_layers.{l}.{n}' for l in range(3) for n in ('spline_weights', 'linear.weight', 'linear.bias')]
+
+
+@pytest.fixture(scope='module')
+def tail_lib(tmp_path_factory):
+    import re
+    k, c = read('kan.cu'), read('common.cuh')
+    hf, ht = read('heads_fused.cuh'), read('heads_train.cuh')
+    cp = between(hf, '__device__ __forceinline__ void hf_cp_async16', '// TRAIN: the same kernel')
+    hf = hf.replace(cp, 'static inline void hf_cp_async16(float* smem_dst, const float* gsrc) { std::memcpy(smem_dst, gsrc, 16); }   // cp.async 16 B\n\n')
+    dyn = 'extern __shared__ __align__(16) float hsm[];'
+    both = (hf + ht).replace('#pragma once', '')
+    assert both.count(dyn) == 2 and both.count('asm volatile("cp.async') == 4
+    both = both.replace(dyn, 'float* hsm = static_cast<float*>(emu_dynamic_smem());')
+    both = re.sub(r'asm volatile\("cp\.async\.(commit_group|wait_group 0);" ::: "memory"\);', ';', both)
+    assert 'asm' not in both
+    body = ('namespace {\n' + between(c, '__device__ __forceinline__ uint4 philox4x32_10', '__device__ __forceinline__ uint32_t smem_u32')
+            + between(k, 'constexpr int kNB = 7;', '// ------------------------------------------------------------------ weight packing')
+            + both + '}\n' + r'''
+// the launch sequences of rvk_heads_fused_prepare / rvk_heads_fused / rvk_heads_train_forward / rvk_heads_train_backward (kan.cu)
+static HeadsFusedParams params_of(const float* const* p23) {
+  HeadsFusedParams p;
+  auto Fp = [&](int i) { return p23[i]; };
+  p.fc1_w[0] = Fp(0); p.fc1_b[0] = Fp(1); p.fc2_w[0] = Fp(2); p.fc2_b[0] = Fp(3);
+  p.fc1_w[1] = Fp(4); p.fc1_b[1] = Fp(5); p.fc2_w[1] = Fp(6); p.fc2_b[1] = Fp(7);
+  p.fc1_w[2] = Fp(8); p.fc1_b[2] = Fp(9); p.fc2_w[2] = Fp(10); p.fc2_b[2] = Fp(11); p.fc2_w[3] = Fp(12); p.fc2_b[3] = Fp(13);
+  for (int l = 0; l < 3; ++l) { p.spline[l] = Fp(14 + 3 * l); p.lin_w[l] = Fp(15 + 3 * l); p.lin_b[l] = Fp(16 + 3 * l); }
+  return p;
+}
+extern "C" int tail_ws_floats() { return kHfWsFloats; }
+extern "C" void tail_forward(const float* const* p23, const float* knots, const float* feat, int batch, int train, float drop_p,
+                             unsigned long long seed, unsigned long long offset, float* ws, float* cls, float* ord, float* mu,
+                             float* lv, float* kan, float* h, float* a1, float* a2) {
+  Knots kn;
+  for (int i = 0; i < kKnots; ++i) kn.k[i] = knots[i];
+  const HeadsFusedParams p = params_of(p23);
+  EmuDim g; g.x = (kHfWsFloats + 255) / 256; EmuDim b; b.x = 256;
+  emu_launch(g, b, 0, [=] { heads_fused_pack_kernel(p, ws); });
+  EmuDim gt; gt.x = (batch + kHfS - 1) / kHfS; EmuDim bt; bt.x = kHfThreads;
+  if (train) {
+    HeadsTrainSave sv{h, a1, a2, drop_p, seed, offset};
+    emu_launch(gt, bt, kHfSmemBytes, [=] { heads_fused_kernel<true>(feat, ws, kn, batch, cls, ord, mu, lv, kan, sv); });
+  } else {
+    emu_launch(gt, bt, kHfSmemBytes, [=] { heads_fused_kernel<false>(feat, ws, kn, batch, cls, ord, mu, lv, kan, HeadsTrainSave{}); });
+  }
+}
+extern "C" void tail_backward(const float* knots, const float* feat, const float* ws, int batch, float drop_p, const float* h,
+                              const float* a1, const float* a2, const float* lv, const float* kan, const float* d_cls, const float* d_ord,
+                              const float* d_mu, const float* d_lv, const float* d_kan, float* dfeat, float* dws, float* const* g23) {
+  Knots kn;
+  for (int i = 0; i < kKnots; ++i) kn.k[i] = knots[i];
+  std::fill(dws, dws + kHfWsFloats, 0.0f);               // cudaMemsetAsync
+  HeadsTrainBwdArgs a{feat, ws, h, a1, a2, lv, kan, d_cls, d_ord, d_mu, d_lv, d_kan, dfeat, dws, drop_p, batch};
+  EmuDim gt; gt.x = (batch + kHfS - 1) / kHfS; EmuDim bt; bt.x = kHtThreads;
+  emu_launch(gt, bt, kHtSmemBytes, [=] { heads_train_bwd_kernel(a, kn); });
+  HeadsGradPtrs gp;
+  auto G = [&](int i) { return g23[i]; };
+  gp.fc1_w[0] = G(0); gp.fc1_b[0] = G(1); gp.fc2_w[0] = G(2); gp.fc2_b[0] = G(3);
+  gp.fc1_w[1] = G(4); gp.fc1_b[1] = G(5); gp.fc2_w[1] = G(6); gp.fc2_b[1] = G(7);
+  gp.fc1_w[2] = G(8); gp.fc1_b[2] = G(9); gp.fc2_w[2] = G(10); gp.fc2_b[2] = G(11); gp.fc2_w[3] = G(12); gp.fc2_b[3] = G(13);
+  for (int l = 0; l < 3; ++l) { gp.spline[l] = G(14 + 3 * l); gp.lin_w[l] = G(15 + 3 * l); gp.lin_b[l] = G(16 + 3 * l); }
+  EmuDim g; g.x = (kHfWsFloats + 255) / 256; EmuDim b; b.x = 256;
+  emu_launch(g, b, 0, [=] { heads_fused_unpack_grad_kernel(dws, gp); });
+}
+''')
+    lib = compile_host(tmp_path_factory.mktemp('tail'), 'tail', body)
+    P, I, Fl, U = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_ulonglong
+    lib.tail_forward.argtypes = [P, P, P, I, I, Fl, U, U, P, P, P, P, P, P, P, P, P]
+    lib.tail_backward.argtypes = [P, P, P, I, Fl, P, P, P, P, P, P, P, P, P, P, P, P, P]
+    return lib
+
+
+def _tail_setup(batch, seed=0):
+    import sys
+    sys.path.insert(0, ROOT)
+    from oracle import model as omodel
+    sd = {k: v.clone() for k, v in omodel.random_state_dict(0).items() if not k.startswith('backbone')}
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():          # timm-style init leaves the head biases at their defaults; move everything off zero, and drive
+        for key in HEAD_KEYS:      # some log-variances into the clamp at +-10 (heads.py:99)
+            if key.endswith('bias'):
+                sd[key] += torch.randn(sd[key].shape, generator=g) * 0.05
+        sd['uncertainty_head.fc_logvar.weight'] *= 60.0
+    feat = torch.randn(batch, 192, generator=g) * 0.8
+    return omodel, sd, feat
+
+
+def _run_tail_forward(lib, sd, feat, train, drop_p=0.0, seed=0, offset=0):
+    batch = feat.shape[0]
+    params = [np.ascontiguousarray(sd[k].numpy(), dtype=F) for k in HEAD_KEYS]
+    table = (ctypes.c_void_p * 23)(*[p.ctypes.data for p in params])
+    knots = np.ascontiguousarray(sd['kan_module.kan_layers.0.knots'].numpy(), dtype=F)
+    ws = np.full(lib.tail_ws_floats(), np.nan, F)
+    f = np.ascontiguousarray(feat.numpy(), dtype=F)
+    mk = lambda n: np.full((batch, n), np.nan, F)
+    out = {'cls': mk(4), 'ord': mk(3), 'mu': mk(1), 'lv': mk(1), 'kan': mk(1), 'h': mk(384), 'a1': mk(64), 'a2': mk(16)}
+    lib.tail_forward(table, vp(knots), vp(f), batch, int(train), drop_p, seed, offset, vp(ws), *[vp(out[k]) for k in ('cls', 'ord', 'mu', 'lv', 'kan', 'h', 'a1', 'a2')])
+    return params, knots, ws, f, out
+
+
+@pytest.mark.parametrize('batch', [13, 8])
+def test_fused_inference_tail_kernel_on_the_host(tail_lib, batch):
+    """`heads_fused_pack_kernel` + `heads_fused_kernel<false>`: the three MLP heads and the KAN stack 192->64->16->1 of
+    RoViTKAN.forward (rovit_kan.py:96-124) in ONE kernel -- 512 threads x 8 samples per CTA, split-K partial sums through shared
+    memory, cp.async-prefetched late weights, 16- and 32-lane shuffle reductions -- against the oracle (itself pinned to the
+    reference's heads / KAN modules); batch 13 leaves a ragged last CTA."""
+    omodel, sd, feat = _tail_setup(batch)
+    _, _, _, _, out = _run_tail_forward(tail_lib, sd, feat, train=False)
+    with torch.no_grad():
+        ref = omodel.heads_forward(sd, feat, 4)
+    for k, rk in (('cls', 'cls_logits'), ('ord', 'ordinal_logits'), ('mu', 'mu'), ('lv', 'log_var'), ('kan', 'kan_severity')):
+        want = ref[rk].numpy()
+        assert np.abs(out[k] - want).max() <= 2e-5 * max(1.0, float(np.abs(want).max())), k
+    assert (np.abs(out['lv']) == 10.0).any() and (np.abs(out['lv']) < 10.0).any()          # both sides of the clamp are exercised
+    assert np.array_equal(out['cls'].argmax(1), ref['cls_logits'].numpy().argmax(1))
+    assert np.array_equal((out['ord'] > 0).sum(1), (ref['ordinal_logits'].numpy() > 0).sum(1))
