@@ -434,3 +434,70 @@ def test_fused_inference_tail_kernel_on_the_host(tail_lib, batch):
     assert (np.abs(out['lv']) == 10.0).any() and (np.abs(out['lv']) < 10.0).any()          # both sides of the clamp are exercised
     assert np.array_equal(out['cls'].argmax(1), ref['cls_logits'].numpy().argmax(1))
     assert np.array_equal((out['ord'] > 0).sum(1), (ref['ordinal_logits'].numpy() > 0).sum(1))
+
+
+def test_fused_training_tail_kernels_on_the_host(tail_lib):
+    """north_star (c) in training: `heads_fused_kernel<true>` (forward, saves the hidden activations) and `heads_train_bwd_kernel`
+    + `heads_fused_unpack_grad_kernel` (ONE backward kernel for d features and all 23 parameter gradients, atomics into a packed
+    buffer) against torch autograd through the oracle: outputs, d features and every parameter gradient, clamp zero-gradient
+    included; then with Dropout p = 0.3: the keep mask recovered from the saved activations is a Philox mask of the right rate,
+    and outputs and gradients equal the oracle's under that very mask (heads.py:20,41,94)."""
+    batch = 11
+    omodel, sd, feat = _tail_setup(batch, seed=5)
+    from oracle import heads as oheads
+    from oracle import kan as okan
+    gen = torch.Generator().manual_seed(9)
+    ups = {k: torch.randn(batch, n, generator=gen) for k, n in (('cls', 4), ('ord', 3), ('mu', 1), ('lv', 1), ('kan', 1))}
+
+    def oracle(keep3=None):
+        sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items() if k in HEAD_KEYS}
+        sdg['kan_module.kan_layers.0.knots'] = sd['kan_module.kan_layers.0.knots']
+        f = feat.clone().requires_grad_(True)
+        w = lambda k: sdg[k]
+        kc, ko, ku = keep3 if keep3 is not None else (None, None, None)
+        cls = oheads.classification_forward(f, w(HEAD_KEYS[0]), w(HEAD_KEYS[1]), w(HEAD_KEYS[2]), w(HEAD_KEYS[3]), kc)
+        ordl = oheads.ordinal_forward(f, w(HEAD_KEYS[4]), w(HEAD_KEYS[5]), w(HEAD_KEYS[6]), w(HEAD_KEYS[7]), ko)
+        mu, lv = oheads.uncertainty_forward(f, *[w(k) for k in HEAD_KEYS[8:14]], ku)
+        kan = okan.severity_forward(f, [tuple(w(k) for k in HEAD_KEYS[14 + 3 * l:17 + 3 * l]) for l in range(3)], sdg['kan_module.kan_layers.0.knots'])
+        outs = {'cls': cls, 'ord': ordl, 'mu': mu, 'lv': lv, 'kan': kan}
+        torch.autograd.backward([outs[k] for k in ups], [ups[k] for k in ups])
+        return outs, f.grad, [sdg[k].grad for k in HEAD_KEYS]
+
+    def ours(drop_p, seed=0, offset=0):
+        params, knots, ws, f, out = _run_tail_forward(tail_lib, sd, feat, train=True, drop_p=drop_p, seed=seed, offset=offset)
+        grads = [np.full_like(p, np.nan) for p in params]
+        gtable = (ctypes.c_void_p * 23)(*[g.ctypes.data for g in grads])
+        dfeat, dws = np.full_like(f, np.nan), np.full_like(ws, np.nan)
+        u = {k: np.ascontiguousarray(v.numpy(), dtype=F) for k, v in ups.items()}
+        tail_lib.tail_backward(vp(knots), vp(f), vp(ws), batch, drop_p, vp(out['h']), vp(out['a1']), vp(out['a2']), vp(out['lv']), vp(out['kan']),
+                               vp(u['cls']), vp(u['ord']), vp(u['mu']), vp(u['lv']), vp(u['kan']), vp(dfeat), vp(dws), gtable)
+        return out, dfeat, grads
+
+    def compare(out, dfeat, grads, ref_out, ref_df, ref_grads):
+        for k in ups:
+            want = ref_out[k].detach().numpy()
+            assert np.abs(out[k] - want).max() <= 2e-5 * max(1.0, float(np.abs(want).max())), k
+        assert np.abs(dfeat - ref_df.numpy()).max() <= 3e-5 * float(ref_df.abs().max())
+        for key, got, want in zip(HEAD_KEYS, grads, ref_grads):
+            want = want.numpy()
+            assert np.isfinite(got).all(), key
+            assert np.abs(got - want).max() <= 3e-5 * float(np.abs(want).max()) + 1e-7, (key, float(np.abs(got - want).max()), float(np.abs(want).max()))
+
+    out, dfeat, grads = ours(0.0)
+    compare(out, dfeat, grads, *oracle())
+    clamped = np.abs(out['lv'][:, 0]) == 10.0
+    assert clamped.any() and not clamped.all()
+    # ---- Dropout p = 0.3: recover the mask from the saved hidden activations (zero <=> dropped or ReLU-gated)
+    out, dfeat, grads = ours(0.3, seed=1234, offset=77)
+    with torch.no_grad():
+        hidden = torch.cat([oheads.mlp_hidden(feat, sd[HEAD_KEYS[i]], sd[HEAD_KEYS[i + 1]]) for i in (0, 4, 8)], dim=1).numpy()
+    live = hidden > 1e-4
+    ratio = out['h'][live] / hidden[live]
+    kept = ratio > 0.5
+    assert np.abs(ratio[kept] - 1.0 / 0.7).max() <= 1e-4 and not ratio[~kept].any()
+    assert abs((~kept).mean() - 0.3) < 0.04, (~kept).mean()
+    keep = np.where(live, np.where(out['h'] != 0, 1.0 / 0.7, 0.0), 1.0 / 0.7).astype(F)
+    keep3 = tuple(torch.from_numpy(np.ascontiguousarray(keep[:, i * 128:(i + 1) * 128])) for i in range(3))
+    compare(out, dfeat, grads, *oracle(keep3))
+    out2, _, _ = ours(0.3, seed=1234, offset=78)
+    assert not np.array_equal(out2['h'] != 0, out['h'] != 0)            # another offset, another mask
