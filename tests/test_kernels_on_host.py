@@ -499,5 +499,5 @@ def test_fused_training_tail_kernels_on_the_host(tail_lib):
     keep = np.where(live, np.where(out['h'] != 0, 1.0 / 0.7, 0.0), 1.0 / 0.7).astype(F)
     keep3 = tuple(torch.from_numpy(np.ascontiguousarray(keep[:, i * 128:(i + 1) * 128])) for i in range(3))
     compare(out, dfeat, grads, *oracle(keep3))
-    out2, _, _ = ours(0.3, seed=1234, offset=78)
+    out2 = _run_tail_forward(tail_lib, sd, feat, train=True, drop_p=0.3, seed=1234, offset=78)[-1]
     assert not np.array_equal(out2['h'] != 0, out['h'] != 0)            # another offset, another mask
