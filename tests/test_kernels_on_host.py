@@ -501,3 +501,111 @@ def test_fused_training_tail_kernels_on_the_host(tail_lib):
     compare(out, dfeat, grads, *oracle(keep3))
     out2 = _run_tail_forward(tail_lib, sd, feat, train=True, drop_p=0.3, seed=1234, offset=78)[-1]
     assert not np.array_equal(out2['h'] != 0, out['h'] != 0)            # another offset, another mask
+
+
+# ------------------------------------------------------------------------------------------ attention probabilities, loss reduction, gradient norm
+def test_attention_probabilities_kernel_on_the_host(tmp_path):
+    """`attn_probs_kernel` (csrc/attention.cu: softmax(q k^T / 8) per (image, head, query) as an explicit tensor for the reference's
+    attention rollout, explainability/attention_maps.py:46-80; warp per query row, two shuffle reductions) against torch on the same
+    bf16 qkv tensor in timm's `reshape(B, N, 3, H, d)` layout."""
+    a = read('attention.cu')
+    body = ('namespace {\n' + between(a, 'constexpr int kTok = 197', '}  // namespace') + '}\n' + r'''
+extern "C" void probs(const uint16_t* qkv, float* out, int batch) {
+  const long long warps = static_cast<long long>(batch) * kHeads * kTok;
+  EmuDim g; g.x = static_cast<unsigned>((warps * 32 + 255) / 256); EmuDim b; b.x = 256;
+  emu_launch(g, b, 0, [=] { attn_probs_kernel(reinterpret_cast<const __nv_bfloat16*>(qkv), out, batch); });
+}
+''')
+    lib = compile_host(tmp_path, 'attn', body)
+    lib.probs.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    torch.manual_seed(0)
+    qkv = (torch.randn(1, 197, 576) * 1.5).to(torch.bfloat16)
+    out = np.full((1, 3, 197, 197), np.nan, F)
+    lib.probs(vp(np.ascontiguousarray(qkv.view(torch.int16).numpy())), vp(out), 1)
+    t = qkv.float().reshape(1, 197, 3, 3, 64).permute(2, 0, 3, 1, 4)
+    want = torch.softmax(t[0] @ t[1].transpose(-1, -2) * 0.125, dim=-1).numpy()
+    assert np.abs(out - want).max() <= 2e-6 and np.abs(out.sum(-1) - 1.0).max() <= 1e-5
+
+
+def test_joint_loss_kernel_with_its_block_reduction_on_the_host(tmp_path):
+    """The whole `joint_loss_kernel` (per-sample terms -> warp sums -> shared partials -> one atomicAdd per block and term) and
+    `loss_finalize_kernel` at a batch that spans three blocks, against the oracle (pinned to the reference's JointLoss)."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from oracle import losses as olosses
+    h, c = read('heads.cu'), read('common.cuh')
+    body = ('namespace {\n' + between(c, '__device__ __forceinline__ float warp_sum', '__device__ __forceinline__ float warp_max')
+            + between(h, 'struct LossParams {', '// RoViTKAN.predict epilogue')
+            + between(h, '// out = {cls, ord, unc, kan, cls + l_ord', '// dst[i] = src[i] * (g[term]') + '}\n' + r'''
+extern "C" void loss(const float* cls, const float* ordl, const float* mu, const float* lv, const float* kan, const long long* yc,
+                     const float* ys, const float* alpha, float gamma, int batch, float* sums, float* out5, float* d_cls, float* d_ord,
+                     float* d_mu, float* d_lv, float* d_kan) {
+  LossParams p;
+  p.cls_logits = cls; p.num_classes = 4; p.ord_logits = ordl; p.mu = mu; p.log_var = lv; p.kan = kan; p.class_t = yc; p.sev_t = ys;
+  p.alpha = alpha; p.gamma = gamma; p.batch = batch; p.sums = sums;
+  p.d_cls = d_cls; p.d_ord = d_ord; p.d_mu = d_mu; p.d_lv = d_lv; p.d_kan = d_kan;
+  for (int i = 0; i < 4; ++i) sums[i] = 0.0f;
+  EmuDim g; g.x = (batch + 255) / 256; EmuDim b; b.x = 256;
+  emu_launch(g, b, 0, [=] { joint_loss_kernel(p); });
+  EmuDim one; EmuDim b32; b32.x = 32;
+  emu_launch(one, b32, 0, [=] { loss_finalize_kernel(sums, 1.0f, 0.5f, 0.5f, out5); });
+}
+''')
+    lib = compile_host(tmp_path, 'loss', body)
+    P = ctypes.c_void_p
+    lib.loss.argtypes = [P, P, P, P, P, P, P, P, ctypes.c_float, ctypes.c_int] + [P] * 7
+    g = torch.Generator().manual_seed(1)
+    B = 600
+    o = {'cls_logits': torch.randn(B, 4, generator=g) * 2, 'ordinal_logits': torch.randn(B, 3, generator=g) * 2, 'mu': torch.randn(B, 1, generator=g),
+         'log_var': torch.randn(B, 1, generator=g), 'kan_severity': torch.rand(B, 1, generator=g) * 3}
+    y = torch.randint(0, 4, (B,), generator=g)
+    alpha = torch.rand(4, generator=g) + 0.5
+    og = {k: v.clone().requires_grad_(True) for k, v in o.items()}
+    ref = olosses.joint(og, y, y, 4, alpha=alpha)
+    ref['total_loss'].backward()
+    n = lambda t, dt=F: np.ascontiguousarray(t.numpy(), dtype=dt)
+    sums, out5 = np.zeros(4, F), np.zeros(5, F)
+    d = [np.full((B, k), np.nan, F) for k in (4, 3, 1, 1, 1)]
+    lib.loss(vp(n(o['cls_logits'])), vp(n(o['ordinal_logits'])), vp(n(o['mu'])), vp(n(o['log_var'])), vp(n(o['kan_severity'])), vp(n(y, np.int64)),
+             vp(n(y.float())), vp(n(alpha)), 2.0, B, vp(sums), vp(out5), *[vp(a) for a in d])
+    for i, k in enumerate(('cls_loss', 'ord_loss', 'unc_loss', 'kan_loss', 'total_loss')):
+        assert abs(float(out5[i]) - float(ref[k].detach())) <= 3e-6 * max(1.0, abs(float(ref[k].detach()))), k
+    for got, w, k in zip(d, (1.0, 1.0, 0.5, 0.5, 0.5), o):
+        assert np.abs(w * got - og[k].grad.numpy()).max() <= 1e-5 * float(og[k].grad.abs().max()) + 1e-9, k
+
+
+def test_gradient_norm_kernel_on_the_host(tmp_path):
+    """`optim_norm_kernel` (csrc/optimizer.cu: sum of squares of every gradient over a padded chunk space, float4 loads where the
+    pointer allows, warp + shared reduction, one atomicAdd per block) = what clip_grad_norm_ computes; a tensor without gradient and
+    an unaligned gradient pointer are part of the table."""
+    o = read('optimizer.cu')
+    body = ('namespace {\n' + between(o, 'constexpr int kChunk', '// state: [0] running sum of squares') + '}\n' + r'''
+extern "C" float sumsq(int n, const float** grads, const long long* numel) {
+  OptTable T{};
+  T.n = n;
+  int chunks = 0;
+  for (int i = 0; i < n; ++i) { T.g[i] = grads[i]; T.numel[i] = static_cast<int>(numel[i]); T.chunk_start[i] = chunks;
+                                chunks += static_cast<int>((numel[i] + kChunk - 1) / kChunk); }
+  T.chunk_start[n] = chunks;
+  static float state[4];
+  state[0] = 0.0f;
+  EmuDim g; g.x = chunks; EmuDim b; b.x = kOptThreads;
+  float* st = state;
+  emu_launch(g, b, 0, [=] { optim_norm_kernel(T, st); });
+  return state[0];
+}
+''')
+    lib = compile_host(tmp_path, 'norm', body)
+    lib.sumsq.restype = ctypes.c_float
+    lib.sumsq.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    rng = np.random.default_rng(0)
+    sizes = [5000, 17, 4096, 8193, 1]
+    bufs = [rng.normal(0, 1, s + 1).astype(F) for s in sizes]
+    grads = [b[:-1] for b in bufs]
+    grads[3] = bufs[3][1:]                                              # 4-byte aligned only: the scalar path
+    ptrs = [g.ctypes.data for g in grads]
+    ptrs[1] = None                                                     # a parameter without gradient
+    table = (ctypes.c_void_p * 5)(*ptrs)
+    got = lib.sumsq(5, table, vp(np.array(sizes, np.int64)))
+    want = sum(float((g.astype(np.float64) ** 2).sum()) for i, g in enumerate(grads) if i != 1)
+    assert abs(got - want) <= 2e-6 * want
