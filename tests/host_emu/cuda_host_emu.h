@@ -62,6 +62,26 @@ static inline uint32_t pack_bf16x2(float lo, float hi) { return emu_bf16_rn(lo) 
 static inline float2 unpack_bf16x2(uint32_t v) { return float2{__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u)}; }
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return static_cast<uint32_t>((static_cast<uint64_t>(a) * b) >> 32); }
+static inline uint16_t emu_f16_rn(float f) {           // cvt.rn.f16.f32
+  uint32_t u; std::memcpy(&u, &f, 4);
+  const uint32_t sign = (u >> 16) & 0x8000u;
+  const int32_t e = static_cast<int32_t>((u >> 23) & 0xffu) - 127 + 15;
+  uint32_t m = u & 0x7fffffu;
+  if (((u >> 23) & 0xffu) == 0xffu) return static_cast<uint16_t>(sign | 0x7c00u | (m ? 0x200u : 0u));
+  if (e >= 31) return static_cast<uint16_t>(sign | 0x7c00u);
+  if (e <= 0) {                                         // subnormal half (or zero)
+    if (e < -10) return static_cast<uint16_t>(sign);
+    m |= 0x800000u;
+    const int shift = 14 - e;                           // 14 .. 24
+    const uint32_t half = m >> shift, rem = m & ((1u << shift) - 1u), mid = 1u << (shift - 1);
+    return static_cast<uint16_t>(sign | (half + ((rem > mid || (rem == mid && (half & 1u))) ? 1u : 0u)));
+  }
+  const uint32_t half = (static_cast<uint32_t>(e) << 10) | (m >> 13), rem = m & 0x1fffu;
+  return static_cast<uint16_t>(sign | (half + ((rem > 0x1000u || (rem == 0x1000u && (half & 1u))) ? 1u : 0u)));
+}
+struct __half { uint16_t v; };
+static inline __half __float2half(float f) { return __half{emu_f16_rn(f)}; }
+static inline __half __float2half_rn(float f) { return __half{emu_f16_rn(f)}; }
 static inline void griddep_wait() {}                   // programmatic dependent launch: nothing to wait for here
 static inline void griddep_launch_dependents() {}
 

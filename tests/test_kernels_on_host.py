@@ -609,3 +609,87 @@ extern "C" float sumsq(int n, const float** grads, const long long* numel) {
     got = lib.sumsq(5, table, vp(np.array(sizes, np.int64)))
     want = sum(float((g.astype(np.float64) ** 2).sum()) for i, g in enumerate(grads) if i != 1)
     assert abs(got - want) <= 2e-6 * want
+
+
+# ------------------------------------------------------------------------------------------ trunk plumbing kernels
+def test_weight_shadow_token_and_column_sum_kernels_on_the_host(tmp_path):
+    """The HBM-bound helpers around the tcgen05 trunk kernels, emulated: `cast_multi_kernel` (all bf16 / transposed-bf16 / fp16
+    weight shadows in one launch, tile index by binary search over a job table), `token_table_kernel` (cls_token + pos_embed and
+    patch bias + pos_embed folded into one additive table), `token_grad_reduce_kernel` (their gradients) and `colsum_kernel`
+    (bias gradients from fp32 / bf16 rows)."""
+    k, c = read('encoder_kernels.cu'), read('common.cuh')
+    kh = read('kernels.h')
+    body = (between(kh, 'struct RvkCastJob', 'int rvk_cast_multi_launch') + 'namespace {\n'
+            + between(c, '__device__ __forceinline__ float warp_sum', '__device__ __forceinline__ float warp_max')
+            + between(k, 'constexpr int kD = 192;', '// ------------------------------------------------------------------ patch extraction')
+            + between(k, '// table[0] = cls_token + pos[0]', '__global__ void cast_bf16_kernel')
+            + between(k, '// ------------------------------------------------------------------ column sums', '}  // namespace') + '}\n' + r'''
+extern "C" void cast_multi(int n, const float** src, void** dst, const int* rows, const int* cols, const int* mode) {
+  RvkCastTable T{};
+  T.n = n;
+  int tiles = 0;
+  for (int i = 0; i < n; ++i) {          // rvk_cast_multi_launch
+    T.job[i].src = src[i]; T.job[i].dst = dst[i]; T.job[i].rows = rows[i]; T.job[i].cols = cols[i]; T.job[i].mode = mode[i];
+    T.job[i].tile_start = tiles;
+    tiles += ((rows[i] + 31) / 32) * ((cols[i] + 31) / 32);
+  }
+  EmuDim g; g.x = tiles; EmuDim b; b.x = 32; b.y = 8;
+  emu_launch(g, b, 0, [=] { cast_multi_kernel(T); });
+}
+extern "C" void token_table(const float* cls, const float* pos, const float* pbias, float* table) {
+  EmuDim g; g.x = (kTok * kD + 255) / 256; EmuDim b; b.x = 256;
+  emu_launch(g, b, 0, [=] { token_table_kernel(cls, pos, pbias, table); });
+}
+extern "C" void token_grads(const float* dx0, int batch, int b_per_block, float* dpos, float* dcls, float* dpbias) {
+  EmuDim g; g.x = kTok; g.y = (batch + b_per_block - 1) / b_per_block; EmuDim b; b.x = kD;
+  emu_launch(g, b, 0, [=] { token_grad_reduce_kernel(dx0, batch, b_per_block, dpos, dcls, dpbias); });
+}
+extern "C" void colsum(int bf16, const void* src, long long ld, int rows, int cols, float* out, float scale, int rows_per_block) {
+  EmuDim g; g.x = (rows + rows_per_block - 1) / rows_per_block; EmuDim b; b.x = 256;
+  if (bf16) emu_launch(g, b, 0, [=] { colsum_kernel<true>(src, ld, rows, cols, out, scale, rows_per_block); });
+  else emu_launch(g, b, 0, [=] { colsum_kernel<false>(src, ld, rows, cols, out, scale, rows_per_block); });
+}
+''')
+    lib = compile_host(tmp_path, 'plumb', body)
+    P, I = ctypes.c_void_p, ctypes.c_int
+    lib.cast_multi.argtypes = [I, P, P, P, P, P]
+    lib.token_table.argtypes = [P, P, P, P]
+    lib.token_grads.argtypes = [P, I, I, P, P, P]
+    lib.colsum.argtypes = [I, P, ctypes.c_longlong, I, I, P, ctypes.c_float, I]
+    rng = np.random.default_rng(0)
+    # ---- weight shadows: qkv-like [576,192] -> bf16, fc2-like [192,768] -> fp16, proj-like [192,192] -> transposed bf16, ragged [70,45] x 3
+    shapes = [(576, 192, 0), (192, 768, 2), (192, 192, 1), (70, 45, 0), (70, 45, 1), (70, 45, 2)]
+    srcs = [rng.normal(0, 0.05, (r, c)).astype(F) for r, c, _ in shapes]
+    srcs[3][0, 0], srcs[5][0, 0], srcs[5][0, 1] = 1e-40, 3e-6, 70000.0                 # denormal input, fp16 subnormal, fp16 overflow
+    dsts = [np.full((c, r) if m == 1 else (r, c), 0xffff, np.uint16) for r, c, m in shapes]
+    arr = lambda vals, dt: np.array(vals, dt)
+    lib.cast_multi(len(shapes), (ctypes.c_void_p * 6)(*[s.ctypes.data for s in srcs]), (ctypes.c_void_p * 6)(*[d.ctypes.data for d in dsts]),
+                   vp(arr([s[0] for s in shapes], np.int32)), vp(arr([s[1] for s in shapes], np.int32)), vp(arr([s[2] for s in shapes], np.int32)))
+    for (r, c, m), s, d in zip(shapes, srcs, dsts):
+        t = torch.from_numpy(s)
+        if m == 2:
+            assert np.array_equal(d, t.to(torch.float16).view(torch.int16).numpy().astype(np.uint16)), (r, c, m)
+        else:
+            want = (t.t().contiguous() if m == 1 else t).to(torch.bfloat16).view(torch.int16).numpy().astype(np.uint16)
+            assert np.array_equal(d, want), (r, c, m)
+    # ---- additive token table and its gradients
+    cls, pos, pb = (rng.normal(0, 1, s).astype(F) for s in ((192,), (197, 192), (192,)))
+    table = np.full((197, 192), np.nan, F)
+    lib.token_table(vp(cls), vp(pos), vp(pb), vp(table))
+    want = pos.copy(); want[0] += cls; want[1:] += pb
+    assert np.array_equal(table, want)
+    dx0 = rng.normal(0, 1, (5, 197, 192)).astype(F)
+    dpos, dcls, dpb = np.zeros((197, 192), F), np.zeros(192, F), np.zeros(192, F)
+    lib.token_grads(vp(dx0), 5, 2, vp(dpos), vp(dcls), vp(dpb))
+    assert np.abs(dpos - dx0.sum(0)).max() <= 1e-5 and np.abs(dcls - dx0[:, 0].sum(0)).max() <= 1e-5
+    assert np.abs(dpb - dx0[:, 1:].sum((0, 1))).max() <= 2e-5 * np.abs(dx0[:, 1:].sum((0, 1))).max()
+    # ---- column sums (bias gradients): fp32 rows of 192, bf16 rows of 768 and 576, accumulate into `out` with a scale
+    x32 = rng.normal(0, 1, (333, 192)).astype(F)
+    out = np.ones(192, F)
+    lib.colsum(0, vp(x32), 192, 333, 192, vp(out), 0.5, 64)
+    assert np.abs(out - (1 + 0.5 * x32.sum(0))).max() <= 2e-5 * np.abs(x32.sum(0)).max()
+    for cols in (768, 576):
+        xb = torch.from_numpy(rng.normal(0, 1, (200, cols)).astype(F)).to(torch.bfloat16)
+        out = np.zeros(cols, F)
+        lib.colsum(1, vp(np.ascontiguousarray(xb.view(torch.int16).numpy())), cols, 200, cols, vp(out), 1.0, 50)
+        assert np.abs(out - xb.float().sum(0).numpy()).max() <= 2e-5 * float(xb.float().sum(0).abs().max())
