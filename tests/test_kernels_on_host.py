@@ -693,3 +693,79 @@ extern "C" void colsum(int bf16, const void* src, long long ld, int rows, int co
         out = np.zeros(cols, F)
         lib.colsum(1, vp(np.ascontiguousarray(xb.view(torch.int16).numpy())), cols, 200, cols, vp(out), 1.0, 50)
         assert np.abs(out - xb.float().sum(0).numpy()).max() <= 2e-5 * float(xb.float().sum(0).abs().max())
+
+
+# ------------------------------------------------------------------------------------------ the per-layer heads path
+def test_per_layer_linear_kernels_on_the_host(tmp_path):
+    """`rvk_linear_forward` / `rvk_linear_backward` as launched for a head layer outside the fused tail (a module called on its own,
+    e.g. OrdinalHead.predict_probabilities heads.py:45-67, or a non-default `kan_layers` model): `sgemm_kernel<1>` with the fused
+    bias / ReLU / clamp epilogue, `epilogue_grad_kernel` (mask recovered from the OUTPUT), dx = g W, the split-K weight gradient with
+    atomics and `colsum_small_kernel` -- against torch autograd, ragged sizes."""
+    h, c = read('heads.cu'), read('common.cuh')
+    body = ('namespace {\n' + between(c, '__device__ __forceinline__ uint4 philox4x32_10', '__device__ __forceinline__ uint32_t smem_u32')
+            + between(c, '__device__ __forceinline__ float warp_sum', '__device__ __forceinline__ float warp_max')
+            + between(h, 'struct SgemmParams {', '// ------------------------------------------------------------------ joint loss') + '}\n' + r'''
+static void sgemm(const float* A, long long lda, int transA, const float* B, long long ldb, int transB, float* C, long long ldc, int M, int N,
+                  int K, const float* bias, int relu, float lo, float hi, int accumulate, int split_k) {
+  SgemmParams p{};
+  p.A = A; p.lda = lda; p.transA = transA; p.B = B; p.ldb = ldb; p.transB = transB; p.C = C; p.ldc = ldc; p.M = M; p.N = N; p.K = K;
+  p.bias = bias; p.relu = relu; p.clamp_lo = lo; p.clamp_hi = hi; p.accumulate = accumulate;
+  int splits = 1;
+  if (split_k) {                                             // rvk_sgemm_launch
+    const int tiles = ((M + 63) / 64) * ((N + 63) / 64);
+    splits = (148 + tiles - 1) / tiles;
+    const int max_splits = (K + 63) / 64;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+  }
+  p.k_per_split = ((K + splits - 1) / splits + 15) / 16 * 16;
+  splits = (K + p.k_per_split - 1) / p.k_per_split;
+  EmuDim g; g.x = (M + 15) / 16; g.y = (N + 63) / 64; g.z = splits; EmuDim b; b.x = 256;
+  emu_launch(g, b, 0, [=] { sgemm_kernel<1>(p); });
+}
+extern "C" void linear_fwd(const float* x, const float* w, const float* bias, int batch, int n_in, int n_out, int relu, float lo, float hi, float* y) {
+  sgemm(x, n_in, 0, w, n_in, 1, y, n_out, batch, n_out, n_in, bias, relu, lo, hi, 0, 0);
+}
+extern "C" void linear_bwd(const float* x, const float* w, const float* y, const float* gy, int batch, int n_in, int n_out, int relu, float lo,
+                           float hi, float* dx, float* dw, float* db, float* gpre_ws) {
+  const float* gpre = gy;
+  if (relu || lo < hi) {                                     // rvk_linear_backward
+    EmuDim g; g.x = (batch * n_out + 255) / 256; EmuDim b; b.x = 256;
+    emu_launch(g, b, 0, [=] { epilogue_grad_kernel(y, gy, gpre_ws, relu, 1.0f, lo, hi, batch * n_out); });
+    gpre = gpre_ws;
+  }
+  sgemm(gpre, n_out, 0, w, n_in, 0, dx, n_in, batch, n_in, n_out, nullptr, 0, 0.f, 0.f, 0, 0);
+  sgemm(gpre, n_out, 1, x, n_in, 0, dw, n_in, n_out, n_in, batch, nullptr, 0, 0.f, 0.f, 1, 1);
+  EmuDim g; g.x = n_out; EmuDim b; b.x = 256;
+  emu_launch(g, b, 0, [=] { colsum_small_kernel(gpre, n_out, batch, n_out, db); });
+}
+''')
+    lib = compile_host(tmp_path, 'lin', body)
+    P, I, Fl = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    lib.linear_fwd.argtypes = [P, P, P, I, I, I, I, Fl, Fl, P]
+    lib.linear_bwd.argtypes = [P, P, P, P, I, I, I, I, Fl, Fl, P, P, P, P]
+    torch.manual_seed(0)
+    for batch, n_in, n_out, relu, clamp in ((37, 192, 128, 1, None), (37, 128, 4, 0, None), (150, 128, 1, 0, (-10.0, 10.0))):
+        lin = torch.nn.Linear(n_in, n_out)
+        if clamp:
+            with torch.no_grad():
+                lin.weight.mul_(40.0)
+        x = torch.randn(batch, n_in, requires_grad=True)
+        y_ref = lin(x)
+        y_ref = torch.relu(y_ref) if relu else y_ref
+        y_ref = torch.clamp(y_ref, *clamp) if clamp else y_ref
+        gy = torch.randn(batch, n_out)
+        y_ref.backward(gy)
+        lo, hi = clamp if clamp else (0.0, 0.0)
+        n = lambda t: np.ascontiguousarray(t.detach().numpy(), dtype=F)
+        y = np.full((batch, n_out), np.nan, F)
+        lib.linear_fwd(vp(n(x)), vp(n(lin.weight)), vp(n(lin.bias)), batch, n_in, n_out, relu, lo, hi, vp(y))
+        assert np.abs(y - n(y_ref)).max() <= 2e-5 * float(y_ref.detach().abs().max())
+        dx, ws = np.full((batch, n_in), np.nan, F), np.full((batch, n_out), np.nan, F)
+        dw, db = np.zeros((n_out, n_in), F), np.zeros(n_out, F)
+        lib.linear_bwd(vp(n(x)), vp(n(lin.weight)), vp(y), vp(n(gy)), batch, n_in, n_out, relu, lo, hi, vp(dx), vp(dw), vp(db), vp(ws))
+        for got, want in ((dx, x.grad), (dw, lin.weight.grad), (db, lin.bias.grad)):
+            assert np.abs(got - n(want)).max() <= 3e-5 * float(want.abs().max()) + 1e-7
+        if clamp:
+            sat = np.abs(y[:, 0]) == 10.0
+            assert sat.any() and not sat.all() and not dx[sat].any()             # clamp: zero gradient outside (-10, 10)
