@@ -1,20 +1,21 @@
 // Thread-level CUDA emulation for the CPU test-suite (TEST INFRASTRUCTURE ONLY, used by tests/test_kernels_on_host.py).
 //
 // A kernel cut verbatim out of a .cu file is compiled by g++ against this header and run block by block, every CUDA thread of a
-// block as one std::thread: threadIdx / blockIdx are thread-local, `__shared__` variables are statics of the (single) running
-// block, `__syncthreads()` is a barrier over the live threads of the block and the warp shuffles exchange through a per-warp
-// barrier, so kernels that reduce with `__shfl_xor_sync`, stage through shared memory and finish with `atomicAdd` run with their
-// real control flow.  Threads that return early are dropped from the barriers (a CUDA block does not wait for exited threads
+// block as one FIBER (ucontext) of a single OS thread, scheduled round-robin: a fiber runs until it reaches a barrier and then
+// hands the core to the next one.  `__shared__` variables are statics of the (single) running block, `__syncthreads()` is a
+// barrier over the live threads of the block and the warp shuffles exchange through a per-warp barrier, so kernels that reduce
+// with `__shfl_xor_sync`, stage through shared memory and finish with `atomicAdd` run with their real control flow -- and
+// deterministically.  Threads that return early are dropped from the barriers (a CUDA block does not wait for exited threads
 // either).  Not modelled: tensor cores, TMA, mbarriers, inline PTX -- the tcgen05 kernels are tested on the GPU only.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cmath>
-#include <condition_variable>
 #include <cstddef>
 #include <cstdint>
 #include <cstring>
-#include <mutex>
-#include <thread>
+#include <functional>
+#include <ucontext.h>
 #include <vector>
 
 #define __global__
@@ -33,7 +34,7 @@ using std::isfinite;
 
 struct EmuDim { unsigned x = 1, y = 1, z = 1; };
 struct EmuIdx { unsigned x = 0, y = 0, z = 0; };
-static thread_local EmuIdx threadIdx, blockIdx;
+static EmuIdx threadIdx, blockIdx;          // of the fiber that is running
 static EmuDim blockDim, gridDim;
 
 // ---- vector types / conversions the kernels use
@@ -85,30 +86,31 @@ static inline __half __float2half_rn(float f) { return __half{emu_f16_rn(f)}; }
 static inline void griddep_wait() {}                   // programmatic dependent launch: nothing to wait for here
 static inline void griddep_launch_dependents() {}
 
-// ---- barriers that tolerate threads leaving
+// ---- fibers and barriers that tolerate threads leaving
+struct EmuFiber { ucontext_t ctx; EmuIdx tidx; bool done = false; };
+static ucontext_t emu_sched_ctx;
+static EmuFiber* emu_cur = nullptr;
+static std::function<void()> emu_kernel_call;
+static inline void emu_yield() { swapcontext(&emu_cur->ctx, &emu_sched_ctx); }
+
 class EmuBarrier {
-  std::mutex m_;
-  std::condition_variable cv_;
   int expected_ = 0, waiting_ = 0;
   unsigned long gen_ = 0;
  public:
   void reset(int n) { expected_ = n; waiting_ = 0; }
   void arrive_and_wait() {
-    std::unique_lock<std::mutex> l(m_);
     const unsigned long g = gen_;
-    if (++waiting_ >= expected_) { waiting_ = 0; ++gen_; cv_.notify_all(); }
-    else cv_.wait(l, [&] { return gen_ != g; });
+    if (++waiting_ >= expected_) { waiting_ = 0; ++gen_; return; }
+    while (gen_ == g) emu_yield();
   }
   void drop() {
-    std::unique_lock<std::mutex> l(m_);
     --expected_;
-    if (expected_ > 0 && waiting_ >= expected_) { waiting_ = 0; ++gen_; cv_.notify_all(); }
+    if (expected_ > 0 && waiting_ >= expected_) { waiting_ = 0; ++gen_; }
   }
 };
 static EmuBarrier emu_block_bar;
 static EmuBarrier emu_warp_bar[32];
 static uint32_t emu_xchg[1024];
-static std::mutex emu_atomic_mutex;
 static std::vector<unsigned char> emu_dyn_smem;
 
 static inline unsigned emu_tid() { return threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z); }
@@ -133,35 +135,57 @@ template <class T> static inline T __shfl_down_sync(unsigned, T v, unsigned d) {
   return r;
 }
 static inline float atomicAdd(float* p, float v) {
-  std::lock_guard<std::mutex> l(emu_atomic_mutex);
   const float old = *p;
   *p = old + v;
   return old;
 }
 static inline void* emu_dynamic_smem() { return emu_dyn_smem.data(); }
 
-// ---- launch: blocks one after the other, the threads of a block concurrently
+// ---- launch: blocks one after the other, the threads of a block as round-robin fibers
+static constexpr size_t kEmuStackBytes = 256 * 1024;
+static std::vector<unsigned char*> emu_stacks;
+static void emu_trampoline() {
+  emu_kernel_call();
+  emu_cur->done = true;
+  const unsigned t = emu_cur->tidx.x + blockDim.x * (emu_cur->tidx.y + blockDim.y * emu_cur->tidx.z);
+  emu_warp_bar[t >> 5].drop();
+  emu_block_bar.drop();
+  swapcontext(&emu_cur->ctx, &emu_sched_ctx);
+}
 template <class F>
 static void emu_launch(EmuDim grid, EmuDim block, size_t dyn_smem_bytes, F kernel_call) {
   gridDim = grid;
   blockDim = block;
+  emu_kernel_call = kernel_call;
   emu_dyn_smem.assign(dyn_smem_bytes + 64, 0xCD);      // "uninitialised" shared memory is not zero
   const unsigned nthreads = block.x * block.y * block.z;
+  while (emu_stacks.size() < nthreads) emu_stacks.push_back(new unsigned char[kEmuStackBytes]);
+  std::vector<EmuFiber> fibers(nthreads);
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {
+        blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
         emu_block_bar.reset(static_cast<int>(nthreads));
         for (unsigned w = 0; w * 32 < nthreads; ++w) emu_warp_bar[w].reset(static_cast<int>(std::min(32u, nthreads - w * 32)));
-        std::vector<std::thread> ts;
-        ts.reserve(nthreads);
-        for (unsigned t = 0; t < nthreads; ++t)
-          ts.emplace_back([=] {
-            threadIdx.x = t % block.x; threadIdx.y = (t / block.x) % block.y; threadIdx.z = t / (block.x * block.y);
-            blockIdx.x = bx; blockIdx.y = by; blockIdx.z = bz;
-            kernel_call();
-            emu_warp_bar[t >> 5].drop();
-            emu_block_bar.drop();
-          });
-        for (auto& th : ts) th.join();
+        for (unsigned t = 0; t < nthreads; ++t) {
+          EmuFiber& f = fibers[t];
+          f.done = false;
+          f.tidx.x = t % block.x; f.tidx.y = (t / block.x) % block.y; f.tidx.z = t / (block.x * block.y);
+          getcontext(&f.ctx);
+          f.ctx.uc_stack.ss_sp = emu_stacks[t];
+          f.ctx.uc_stack.ss_size = kEmuStackBytes;
+          f.ctx.uc_link = &emu_sched_ctx;
+          makecontext(&f.ctx, emu_trampoline, 0);
+        }
+        unsigned remaining = nthreads;
+        while (remaining > 0)
+          for (unsigned t = 0; t < nthreads; ++t) {
+            EmuFiber& f = fibers[t];
+            if (f.done) continue;
+            emu_cur = &f;
+            threadIdx = f.tidx;
+            swapcontext(&emu_sched_ctx, &f.ctx);
+            if (f.done) --remaining;
+          }
       }
 }

@@ -32,7 +32,7 @@ def compile_host(tmp, name, body):
     src = tmp / f'{name}.cpp'
     src.write_text('#include "cuda_host_emu.h"\n' + body)
     so = tmp / f'{name}.so'
-    r = subprocess.run(['g++', '-O1', '-std=c++17', '-ffp-contract=off', '-fno-strict-aliasing', '-I', EMU, '-shared', '-fPIC', '-pthread',
+    r = subprocess.run(['g++', '-O1', '-std=c++17', '-ffp-contract=off', '-fno-strict-aliasing', '-I', EMU, '-shared', '-fPIC',
                         '-o', str(so), str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-4000:]
     return ctypes.CDLL(str(so))
