@@ -1,6 +1,6 @@
 """Whole CUDA kernels on the CPU (no GPU): the kernel text is cut VERBATIM out of the .cu sources and compiled by g++ against
-tests/host_emu/cuda_host_emu.h, a thread-level emulation (one std::thread per CUDA thread, real __syncthreads / warp-shuffle /
-shared-memory / atomicAdd semantics), then run with the launch geometry the library uses and compared with PyTorch on the same
+tests/host_emu/cuda_host_emu.h, a thread-level emulation (every CUDA thread of a block a fiber scheduled round-robin between barriers:
+real __syncthreads / warp-shuffle / shared-memory / atomicAdd semantics, deterministic), then run with the launch geometry the library uses and compared with PyTorch on the same
 inputs.  Covers the CUDA-core kernels whose correctness rests on cross-thread traffic: LayerNorm forward and backward (with the
 fused column sums), the joint-loss kernel with its block reduction, the optimizer's global-norm kernel.  The tcgen05 / TMA kernels
 cannot be emulated this way and are tested on the GPU (`-m gpu`)."""
