@@ -1,9 +1,14 @@
 """Whole CUDA kernels on the CPU (no GPU): the kernel text is cut VERBATIM out of the .cu sources and compiled by g++ against
-tests/host_emu/cuda_host_emu.h, a thread-level emulation (every CUDA thread of a block a fiber scheduled round-robin between barriers:
-real __syncthreads / warp-shuffle / shared-memory / atomicAdd semantics, deterministic), then run with the launch geometry the library uses and compared with PyTorch on the same
-inputs.  Covers the CUDA-core kernels whose correctness rests on cross-thread traffic: LayerNorm forward and backward (with the
-fused column sums), the joint-loss kernel with its block reduction, the optimizer's global-norm kernel.  The tcgen05 / TMA kernels
-cannot be emulated this way and are tested on the GPU (`-m gpu`)."""
+tests/host_emu/cuda_host_emu.h, a thread-level emulation (every CUDA thread of a block a fiber scheduled round-robin between
+barriers: real __syncthreads / warp-shuffle / shared-memory / atomicAdd semantics, deterministic), then run with the launch
+geometry the library uses and compared with the reference-generated vectors, the oracle or PyTorch on the same inputs.
+
+Covered: the CUDA-core kernels -- the fp32 KAN layer kernels and the small-output KAN kernels (forward and every gradient), the
+fused heads + KAN tail in inference and in training (forward, backward, all 23 parameter gradients, dropout), the per-layer linear
+path, the joint-loss kernel with its block reduction, LayerNorm forward / backward, the optimizer's gradient-norm kernel, attention
+probabilities, weight shadows, token table, column sums.  The tcgen05 / TMA kernels (trunk GEMMs, attention, the fused MLP block,
+the tensor-core KAN path) cannot be emulated this way and are tested on the GPU (`-m gpu`); their CUDA-core operand producer is
+covered in tests/test_kernel_constants.py."""
 
 import ctypes
 import os
