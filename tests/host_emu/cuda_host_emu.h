@@ -157,7 +157,7 @@ static void emu_launch(EmuDim grid, EmuDim block, size_t dyn_smem_bytes, F kerne
   gridDim = grid;
   blockDim = block;
   emu_kernel_call = kernel_call;
-  emu_dyn_smem.assign(dyn_smem_bytes + 64, 0xCD);      // "uninitialised" shared memory is not zero
+  emu_dyn_smem.assign(dyn_smem_bytes, 0xCD);           // exact size (bounds-checked under ASan); "uninitialised" is not zero
   const unsigned nthreads = block.x * block.y * block.z;
   while (emu_stacks.size() < nthreads) emu_stacks.push_back(new unsigned char[kEmuStackBytes]);
   std::vector<EmuFiber> fibers(nthreads);
