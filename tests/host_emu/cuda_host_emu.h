@@ -38,10 +38,11 @@ static EmuIdx threadIdx, blockIdx;          // of the fiber that is running
 static EmuDim blockDim, gridDim;
 
 // ---- vector types / conversions the kernels use
-struct float2 { float x, y; };
-struct float4 { float x, y, z, w; };
-struct uint2 { uint32_t x, y; };
-struct uint4 { uint32_t x, y, z, w; };
+// (CUDA's alignment requirements: an 8- / 16-byte vector access must be naturally aligned -- UBSan's alignment check sees these)
+struct alignas(8) float2 { float x, y; };
+struct alignas(16) float4 { float x, y, z, w; };
+struct alignas(8) uint2 { uint32_t x, y; };
+struct alignas(16) uint4 { uint32_t x, y, z, w; };
 static inline float2 make_float2(float a, float b) { return float2{a, b}; }
 static inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
 static inline uint2 make_uint2(uint32_t a, uint32_t b) { return uint2{a, b}; }

@@ -39,7 +39,7 @@ def compile_host(tmp, name, body):
     so = tmp / f'{name}.so'
     # ROVITKAN_EMU_SANITIZE=1 (with libasan preloaded into the interpreter, see test_kernels_under_address_sanitizer): every global /
     # shared / workspace access of the emulated kernels is bounds-checked
-    san = ['-fsanitize=address', '-fno-omit-frame-pointer'] if os.environ.get('ROVITKAN_EMU_SANITIZE') == '1' else []
+    san = ['-fsanitize=address,undefined', '-fno-sanitize-recover=undefined', '-fno-omit-frame-pointer'] if os.environ.get('ROVITKAN_EMU_SANITIZE') == '1' else []
     r = subprocess.run(['g++', '-O1', '-std=c++17', '-ffp-contract=off', '-fno-strict-aliasing', '-I', EMU, '-shared', '-fPIC', *san,
                         '-o', str(so), str(src)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-4000:]

@@ -1,8 +1,10 @@
-"""The emulated kernels under AddressSanitizer (the CPU stand-in for `compute-sanitizer --tool memcheck`, which needs a GPU): the
-host-emulation suite (tests/test_kernels_on_host.py) is re-run in a subprocess with the harnesses compiled `-fsanitize=address` and
-libasan preloaded into the interpreter, so every global, workspace and shared-memory access of every emulated kernel -- ragged last
-tiles, padded weight buffers, exactly-sized outputs and dynamic shared memory -- is bounds-checked.  A negative control proves the
-check is live: the same LayerNorm kernel with an output buffer one row short must be reported."""
+"""The emulated kernels under AddressSanitizer + UndefinedBehaviorSanitizer (the CPU stand-in for `compute-sanitizer --tool memcheck`,
+which needs a GPU): the host-emulation suite (tests/test_kernels_on_host.py) is re-run in a subprocess with the harnesses compiled
+`-fsanitize=address,undefined` and the sanitizer runtimes preloaded into the interpreter, so every global, workspace and shared-memory
+access of every emulated kernel -- ragged last tiles, padded weight buffers, exactly-sized outputs and dynamic shared memory -- is
+bounds-checked, every 8- / 16-byte vector access is checked for CUDA's natural alignment (the emulation's float4 / uint4 carry
+alignas(16)), and shifts / signed overflow are checked.  A negative control proves the check is live: the same LayerNorm kernel with an
+output buffer one row short must be reported."""
 
 import os
 import subprocess
@@ -15,26 +17,31 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _asan():
-    try:
-        path = subprocess.run(['gcc', '-print-file-name=libasan.so'], capture_output=True, text=True).stdout.strip()
-    except OSError:
-        return None
-    return path if os.path.isabs(path) and os.path.exists(path) else None
+    libs = []
+    for name in ('libasan.so', 'libubsan.so'):
+        try:
+            path = subprocess.run(['gcc', f'-print-file-name={name}'], capture_output=True, text=True).stdout.strip()
+        except OSError:
+            return None
+        if not (os.path.isabs(path) and os.path.exists(path)):
+            return None
+        libs.append(path)
+    return ' '.join(libs)
 
 
 ASAN = _asan()
-pytestmark = pytest.mark.skipif(ASAN is None, reason='libasan not available')
+pytestmark = pytest.mark.skipif(ASAN is None, reason='libasan / libubsan not available')
 
 
 def _env():
     return dict(os.environ, LD_PRELOAD=ASAN, ASAN_OPTIONS='detect_leaks=0:detect_stack_use_after_return=0', ROVITKAN_EMU_SANITIZE='1')
 
 
-def test_emulated_kernels_are_clean_under_address_sanitizer():
+def test_emulated_kernels_are_clean_under_address_and_ub_sanitizers():
     r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(ROOT, 'tests', 'test_kernels_on_host.py'), '-q', '-x', '-p', 'no:cacheprovider'],
                        cwd=ROOT, env=_env(), capture_output=True, text=True, timeout=1500)
     out = r.stdout + r.stderr
-    assert r.returncode == 0 and ' passed' in out and 'AddressSanitizer' not in out, out[-4000:]
+    assert r.returncode == 0 and ' passed' in out and 'AddressSanitizer' not in out and 'runtime error' not in out, out[-4000:]
 
 
 def test_address_sanitizer_reports_a_kernel_that_writes_out_of_bounds(tmp_path):
