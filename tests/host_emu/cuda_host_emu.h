@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <ucontext.h>
@@ -178,9 +179,13 @@ static void emu_launch(EmuDim grid, EmuDim block, size_t dyn_smem_bytes, F kerne
           f.ctx.uc_link = &emu_sched_ctx;
           makecontext(&f.ctx, emu_trampoline, 0);
         }
+        // ROVITKAN_EMU_ORDER=reverse resumes the fibers from the last thread to the first: a kernel whose result depended on the
+        // order in which threads reach a barrier-free stretch (a missing __syncthreads / __syncwarp) would differ between the orders
+        static const bool reverse = [] { const char* e = std::getenv("ROVITKAN_EMU_ORDER"); return e != nullptr && e[0] == 'r'; }();
         unsigned remaining = nthreads;
         while (remaining > 0)
-          for (unsigned t = 0; t < nthreads; ++t) {
+          for (unsigned i = 0; i < nthreads; ++i) {
+            const unsigned t = reverse ? nthreads - 1 - i : i;
             EmuFiber& f = fibers[t];
             if (f.done) continue;
             emu_cur = &f;

@@ -4,7 +4,11 @@ which needs a GPU): the host-emulation suite (tests/test_kernels_on_host.py) is 
 access of every emulated kernel -- ragged last tiles, padded weight buffers, exactly-sized outputs and dynamic shared memory -- is
 bounds-checked, every 8- / 16-byte vector access is checked for CUDA's natural alignment (the emulation's float4 / uint4 carry
 alignas(16)), and shifts / signed overflow are checked.  A negative control proves the check is live: the same LayerNorm kernel with an
-output buffer one row short must be reported."""
+output buffer one row short must be reported.
+
+The sanitized run also resumes the fibers in REVERSE thread order (ROVITKAN_EMU_ORDER=reverse; the plain run uses ascending order):
+a kernel with a missing __syncthreads / __syncwarp, whose result depends on which thread reaches a barrier-free stretch first, cannot
+pass under both orders -- the emulation's stand-in for `compute-sanitizer --tool racecheck`."""
 
 import os
 import subprocess
@@ -34,7 +38,7 @@ pytestmark = pytest.mark.skipif(ASAN is None, reason='libasan / libubsan not ava
 
 
 def _env():
-    return dict(os.environ, LD_PRELOAD=ASAN, ASAN_OPTIONS='detect_leaks=0:detect_stack_use_after_return=0', ROVITKAN_EMU_SANITIZE='1')
+    return dict(os.environ, LD_PRELOAD=ASAN, ASAN_OPTIONS='detect_leaks=0:detect_stack_use_after_return=0', ROVITKAN_EMU_SANITIZE='1', ROVITKAN_EMU_ORDER='reverse')
 
 
 def test_emulated_kernels_are_clean_under_address_and_ub_sanitizers():
@@ -68,3 +72,43 @@ def test_address_sanitizer_reports_a_kernel_that_writes_out_of_bounds(tmp_path):
     r = subprocess.run([sys.executable, '-c', code], cwd=ROOT, env=_env(), capture_output=True, text=True, timeout=600)
     assert r.returncode != 0 and 'AddressSanitizer' in r.stderr and 'heap-buffer-overflow' in r.stderr, (r.stdout + r.stderr)[-3000:]
     assert 'NOT DETECTED' not in r.stdout
+
+
+def test_the_two_fiber_orders_expose_a_missing_barrier(tmp_path):
+    """Control for the order check: a kernel that reads its neighbour's shared-memory slot WITHOUT a __syncthreads gives different
+    results under the ascending and the reverse fiber order; with the barrier both orders agree."""
+    code = textwrap.dedent(f'''
+        import ctypes, pathlib, sys
+        import numpy as np
+        sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})
+        import test_kernels_on_host as T
+        body = """
+        template <bool SYNC> __global__ void neighbour(float* out, float base) {{
+          __shared__ float s[64];
+          s[threadIdx.x] = base + threadIdx.x;
+          if (SYNC) __syncthreads();
+          out[threadIdx.x] = s[(threadIdx.x + 1) % 64];
+        }}
+        extern "C" void run(int sync, float* out) {{
+          EmuDim g; EmuDim b; b.x = 64;
+          if (sync) emu_launch(g, b, 0, [=] {{ neighbour<true>(out, 100.0f); }}); else emu_launch(g, b, 0, [=] {{ neighbour<false>(out, 100.0f); }});
+          if (sync) emu_launch(g, b, 0, [=] {{ neighbour<true>(out + 64, 1.0f); }}); else emu_launch(g, b, 0, [=] {{ neighbour<false>(out + 64, 1.0f); }});
+        }}
+        """
+        lib = T.compile_host(pathlib.Path({str(tmp_path)!r}), 'racy_' + sys.argv[1], body)
+        lib.run.argtypes = [ctypes.c_int, ctypes.c_void_p]
+        for sync in (0, 1):
+            out = np.zeros(128, np.float32)
+            lib.run(sync, T.vp(out))
+            print('RESULT', sync, out[64:].tolist())       # second launch: the static shared array holds the previous block's values
+    ''')
+    res = {}
+    for order in ('ascending', 'reverse'):
+        env = dict(os.environ, ROVITKAN_EMU_ORDER=order)
+        env.pop('ROVITKAN_EMU_SANITIZE', None)
+        r = subprocess.run([sys.executable, '-c', code, order], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        res[order] = {l.split()[1]: l.split(None, 2)[2] for l in r.stdout.splitlines() if l.startswith('RESULT')}
+    want = str([float(1 + (t + 1) % 64) for t in range(64)])
+    assert res['ascending']['1'] == res['reverse']['1'] == want
+    assert res['ascending']['0'] != res['reverse']['0'] and res['ascending']['0'] != want and res['reverse']['0'] != want
