@@ -777,3 +777,40 @@ extern "C" void linear_bwd(const float* x, const float* w, const float* y, const
         if clamp:
             sat = np.abs(y[:, 0]) == 10.0
             assert sat.any() and not sat.all() and not dx[sat].any()             # clamp: zero gradient outside (-10, 10)
+
+
+def test_tensor_core_kan_weight_split_kernels_on_the_host(tmp_path):
+    """The weight operands of the tcgen05 KAN kernels: `kan_split_weights_kernel` ([64 outputs][in * 8] for the forward / dW
+    kernels) and `kan_split_weights_rows_kernel` ([in * 8][64] for the dx kernel) pack W[i,o,k] (k < 7) and Wl[o,i] (k = 7) like the
+    fp32 path and split every value into bf16 hi + lo: hi + lo must reproduce the fp32 weight to 2^-16 relative (three MMAs per product
+    then give an fp32-grade result) and the padding must be exact zeros."""
+    t = read('kan_tc.cuh')
+    body = ('namespace {\n' + between(t, '// WpT (fp32 [out_pad=64][kp]) -> bf16 hi / lo', '// The 8 packed activations')
+            + between(t, '// Wp (fp32 [kp][out_pad=64]) -> bf16 hi / lo', '__global__ void __launch_bounds__(kTcThreads, 1)') + '}\n' + r'''
+extern "C" void split(int rows_major, const float* spline, const float* lin_w, int n_in, int n_out, int kp, uint16_t* hi, uint16_t* lo) {
+  EmuDim g; g.x = 7; EmuDim b; b.x = 256;
+  auto* h = reinterpret_cast<__nv_bfloat16*>(hi); auto* l = reinterpret_cast<__nv_bfloat16*>(lo);
+  if (rows_major) emu_launch(g, b, 0, [=] { kan_split_weights_rows_kernel(spline, lin_w, n_in, n_out, kp, h, l); });
+  else emu_launch(g, b, 0, [=] { kan_split_weights_kernel(spline, lin_w, n_in, n_out, kp, h, l); });
+}
+''')
+    lib = compile_host(tmp_path, 'split', body)
+    P, I = ctypes.c_void_p, ctypes.c_int
+    lib.split.argtypes = [I, P, P, I, I, I, P, P]
+    rng = np.random.default_rng(0)
+    n_in, n_out = 72, 50                                    # padded to 80 inputs (kp = 640) and 64 outputs
+    kp = 80 * 8
+    spline, lin_w = rng.normal(0, 0.1, (n_in, n_out, 7)).astype(F), rng.normal(0, 0.1, (n_out, n_in)).astype(F)
+    want = np.zeros((64, kp), F)                             # [o][i * 8 + k]
+    for k in range(7):
+        want[:n_out, np.arange(n_in) * 8 + k] = spline[:, :, k].T
+    want[:n_out, np.arange(n_in) * 8 + 7] = lin_w
+    f32 = lambda a: (a.astype(np.uint32) << 16).view(F)
+    for rows_major in (0, 1):
+        hi, lo = np.full(64 * kp, 0xffff, np.uint16), np.full(64 * kp, 0xffff, np.uint16)
+        lib.split(rows_major, vp(spline), vp(lin_w), n_in, n_out, kp, vp(hi), vp(lo))
+        w = want.T if rows_major else want
+        got = (f32(hi).astype(np.float64) + f32(lo).astype(np.float64)).reshape(w.shape)
+        assert np.abs(got - w).max() <= 2.0 ** -16 * np.abs(w).max()
+        assert not hi.reshape(w.shape)[w == 0].any() and not lo.reshape(w.shape)[w == 0].any()
+        assert np.array_equal(hi.reshape(w.shape), torch.from_numpy(np.ascontiguousarray(w)).to(torch.bfloat16).view(torch.int16).numpy().astype(np.uint16))
