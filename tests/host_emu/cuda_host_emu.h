@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -94,6 +95,7 @@ static ucontext_t emu_sched_ctx;
 static EmuFiber* emu_cur = nullptr;
 static std::function<void()> emu_kernel_call;
 static inline void emu_yield() { swapcontext(&emu_cur->ctx, &emu_sched_ctx); }
+static unsigned long emu_progress = 0;       // barrier arrivals / releases + finished fibers: a scheduler pass without any is a deadlock
 
 class EmuBarrier {
   int expected_ = 0, waiting_ = 0;
@@ -102,12 +104,13 @@ class EmuBarrier {
   void reset(int n) { expected_ = n; waiting_ = 0; }
   void arrive_and_wait() {
     const unsigned long g = gen_;
+    ++emu_progress;                                    // an arrival is a state change, released or not
     if (++waiting_ >= expected_) { waiting_ = 0; ++gen_; return; }
     while (gen_ == g) emu_yield();
   }
   void drop() {
     --expected_;
-    if (expected_ > 0 && waiting_ >= expected_) { waiting_ = 0; ++gen_; }
+    if (expected_ > 0 && waiting_ >= expected_) { waiting_ = 0; ++gen_; ++emu_progress; }
   }
 };
 static EmuBarrier emu_block_bar;
@@ -149,6 +152,7 @@ static std::vector<unsigned char*> emu_stacks;
 static void emu_trampoline() {
   emu_kernel_call();
   emu_cur->done = true;
+  ++emu_progress;
   const unsigned t = emu_cur->tidx.x + blockDim.x * (emu_cur->tidx.y + blockDim.y * emu_cur->tidx.z);
   emu_warp_bar[t >> 5].drop();
   emu_block_bar.drop();
@@ -183,7 +187,8 @@ static void emu_launch(EmuDim grid, EmuDim block, size_t dyn_smem_bytes, F kerne
         // order in which threads reach a barrier-free stretch (a missing __syncthreads / __syncwarp) would differ between the orders
         static const bool reverse = [] { const char* e = std::getenv("ROVITKAN_EMU_ORDER"); return e != nullptr && e[0] == 'r'; }();
         unsigned remaining = nthreads;
-        while (remaining > 0)
+        while (remaining > 0) {
+          const unsigned long before = emu_progress;
           for (unsigned i = 0; i < nthreads; ++i) {
             const unsigned t = reverse ? nthreads - 1 - i : i;
             EmuFiber& f = fibers[t];
@@ -193,5 +198,11 @@ static void emu_launch(EmuDim grid, EmuDim block, size_t dyn_smem_bytes, F kerne
             swapcontext(&emu_sched_ctx, &f.ctx);
             if (f.done) --remaining;
           }
+          if (remaining > 0 && emu_progress == before) {        // every live fiber is parked at a barrier that cannot complete
+            std::fprintf(stderr, "cuda_host_emu: deadlock in block (%u,%u,%u): %u threads wait at a barrier the others never reach "
+                                 "(divergent __syncthreads / partial-warp shuffle)\n", bx, by, bz, remaining);
+            std::abort();
+          }
+        }
       }
 }

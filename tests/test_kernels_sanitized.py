@@ -112,3 +112,33 @@ def test_the_two_fiber_orders_expose_a_missing_barrier(tmp_path):
     want = str([float(1 + (t + 1) % 64) for t in range(64)])
     assert res['ascending']['1'] == res['reverse']['1'] == want
     assert res['ascending']['0'] != res['reverse']['0'] and res['ascending']['0'] != want and res['reverse']['0'] != want
+
+
+def test_the_emulation_reports_a_divergent_barrier_instead_of_hanging(tmp_path):
+    """Control for the watchdog: a kernel in which part of a block waits at a __syncthreads and the rest at a full-warp shuffle that
+    half of its warp never executes (threads that RETURN are dropped from the barriers, as on the GPU; threads that stay alive and
+    never arrive are a deadlock) must abort with a message, not spin forever."""
+    code = textwrap.dedent(f'''
+        import ctypes, pathlib, sys
+        sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})
+        import test_kernels_on_host as T
+        body = """
+        __global__ void divergent(float* out) {{
+          float v = 1.0f + threadIdx.x;
+          if (threadIdx.x < 32 || (threadIdx.x & 16)) __syncthreads();   // 48 of the 64 threads arrive at the block barrier ...
+          else v = __shfl_xor_sync(0xffffffffu, v, 1);                   // ... 16 lanes of a 32-lane warp wait for a full-warp shuffle
+          out[threadIdx.x] = v;
+        }}
+        extern "C" void run(float* out) {{ EmuDim g; EmuDim b; b.x = 64; emu_launch(g, b, 0, [=] {{ divergent(out); }}); }}
+        """
+        lib = T.compile_host(pathlib.Path({str(tmp_path)!r}), 'dead', body)
+        import numpy as np
+        out = np.zeros(64, np.float32)
+        lib.run.argtypes = [ctypes.c_void_p]
+        lib.run(T.vp(out))
+        print('RETURNED')
+    ''')
+    env = dict(os.environ)
+    env.pop('ROVITKAN_EMU_SANITIZE', None)
+    r = subprocess.run([sys.executable, '-c', code], cwd=ROOT, env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode != 0 and 'cuda_host_emu: deadlock' in r.stderr and 'RETURNED' not in r.stdout, (r.stdout + r.stderr)[-2000:]
