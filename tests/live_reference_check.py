@@ -166,10 +166,50 @@ def check_losses(rng):
     return {'max_rel_loss': worst, 'max_rel_grad': worst_grad}
 
 
+def check_model(rng):
+    """The composed RoViTKAN of the reference (models/rovit_kan.py, unmodified; the absent third-party timm replaced by the oracle's
+    restatement of deit_tiny_patch16_224) against oracle.model.forward / predict at every curriculum stage: same keys, the same
+    entries gated to None, same numbers."""
+    import types
+    from oracle import model as omodel
+    from oracle import vit as ovit
+    shim = types.ModuleType('timm')
+    shim.create_model = ovit.create_model
+    sys.modules['timm'] = shim
+    from models.rovit_kan import RoViTKAN
+    assert os.path.abspath(sys.modules['models.rovit_kan'].__file__).startswith(os.path.abspath(REF))
+    sd = omodel.random_state_dict(int(torch.randint(0, 1000, (1,), generator=rng)))
+    with torch.no_grad():
+        for k, v in sd.items():            # timm initialises every bias to zero: move them so that they count
+            if k.endswith('bias'):
+                v.add_(torch.randn(v.shape, generator=rng) * 0.05)
+    ref = RoViTKAN(pretrained=False, dropout=0.0)
+    ref.load_state_dict(sd, strict=True)
+    ref.eval()
+    x = torch.randn(2, 3, 224, 224, generator=rng)
+    worst, gating_ok, keys_ok = 0.0, True, True
+    for stage in (1, 2, 3, 4):
+        ref.curriculum_stage = stage
+        with torch.no_grad():
+            a, b = ref(x), omodel.forward(sd, x, stage=stage)
+            pa, pb = ref.predict(x), omodel.predict(sd, x, stage=stage)
+        keys_ok &= set(a) == set(b) and set(pa) == set(pb)
+        for d_ref, d_or in ((a, b), (pa, pb)):
+            for k in d_ref:
+                gating_ok &= (d_ref[k] is None) == (d_or[k] is None)
+                if d_ref[k] is None:
+                    continue
+                if d_ref[k].dtype == torch.int64:
+                    keys_ok &= bool(torch.equal(d_ref[k], d_or[k]))
+                else:
+                    worst = max(worst, rel(d_or[k], d_ref[k]))
+    return {'max_rel': worst, 'stage_gating_matches': gating_ok, 'keys_and_classes_match': keys_ok}
+
+
 def main():
     rng = torch.Generator().manual_seed(int(os.environ.get('LIVE_SEED', '0')))
     out = {'reference': REF, 'cases': CASES, 'basis': check_basis(rng), 'kan_layer': check_kan_layer(rng),
-           'kan_module': check_kan_module(rng), 'heads': check_heads(rng), 'losses': check_losses(rng)}
+           'kan_module': check_kan_module(rng), 'heads': check_heads(rng), 'losses': check_losses(rng), 'model': check_model(rng)}
     print(json.dumps(out))
 
 

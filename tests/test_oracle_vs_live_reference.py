@@ -31,3 +31,5 @@ def test_oracle_matches_the_live_reference_on_random_cases(seed):
             assert v <= 1e-5, (family, k, v)
     assert r['heads']['max_rel'] <= 1e-5
     assert r['losses']['max_rel_loss'] <= 1e-5 and r['losses']['max_rel_grad'] <= 1e-5
+    # the composed reference model (timm -> the oracle's restatement) at every curriculum stage, forward and predict
+    assert r['model']['max_rel'] <= 2e-5 and r['model']['stage_gating_matches'] is True and r['model']['keys_and_classes_match'] is True
