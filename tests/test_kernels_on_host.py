@@ -814,3 +814,59 @@ extern "C" void split(int rows_major, const float* spline, const float* lin_w, i
         assert np.abs(got - w).max() <= 2.0 ** -16 * np.abs(w).max()
         assert not hi.reshape(w.shape)[w == 0].any() and not lo.reshape(w.shape)[w == 0].any()
         assert np.array_equal(hi.reshape(w.shape), torch.from_numpy(np.ascontiguousarray(w)).to(torch.bfloat16).view(torch.int16).numpy().astype(np.uint16))
+
+
+# ------------------------------------------------------------------------------------------ a tcgen05 kernel, functionally
+def test_weight_gradient_tcgen05_kernel_on_the_host(tmp_path):
+    """`gemm_tn_kernel<192, 4>` (csrc/gemm_tn.cuh: dW = A^T B on tcgen05 / TMEM, both operands MN-major through TMA with the
+    128-byte swizzle, split over the rows, fused bias gradient through a constant ones panel, red.global.add epilogue) run under a
+    FUNCTIONAL emulation of the Blackwell pieces it uses (tests/host_emu/tcgen05_host_emu.h: mbarriers with transaction counts,
+    swizzled TMA tiles, tensor memory, tcgen05.mma decoded from the shared-memory / instruction descriptors that common.cuh's own,
+    verbatim builders produce).  Warp roles, pipeline phases, descriptor strides, the ones-panel column and the split-K epilogue all
+    execute; the row count is ragged (zero-filled TMA rows) and the result accumulates into a non-zero C."""
+    c, t = read('common.cuh'), read('gemm_tn.cuh')
+    kernel = between(t, 'struct GemmTnParams {', '#endif  // __CUDACC__').replace('#ifdef __CUDACC__', '')
+    dyn = 'extern __shared__ uint8_t smem_raw[];'
+    assert kernel.count(dyn) == 1
+    kernel = kernel.replace(dyn, 'uint8_t* smem_raw = static_cast<uint8_t*>(emu_dynamic_smem());')
+    body = ('#include "tcgen05_host_emu.h"\nnamespace {\n'
+            + between(c, '// Shared-memory matrix descriptor (64-bit).', '// byte offset of 16-byte chunk')      # umma_smem_desc + umma_idesc_bf16, verbatim
+            + kernel + '}\n' + r'''
+extern "C" void gemm_tn(const uint16_t* A, long long lda, const uint16_t* B, long long ldb, float* C, long long ldc, int M, int P, int Q,
+                        float scale, float* colsum, int splits_wanted) {
+  constexpr int kBQ = 192, kStages = 4;
+  using L = GemmTnSmem<kBQ, kStages>;
+  const CUtensorMap tmA = emu_make_tmap_2d(A, 2, M, P, lda, 64, 64), tmB = emu_make_tmap_2d(B, 2, M, Q, ldb, 64, 64);   // rvk_gemm_tn_launch
+  const int tiles = ((P + 127) / 128) * ((Q + kBQ - 1) / kBQ);
+  const int total_chunks = (M + 63) / 64;
+  int splits = splits_wanted;
+  if (splits > total_chunks) splits = total_chunks;
+  if (splits < 1) splits = 1;
+  GemmTnParams p;
+  p.M = M; p.P = P; p.Q = Q; p.ldc = static_cast<int>(ldc);
+  p.chunks_per_split = (total_chunks + splits - 1) / splits;
+  p.C = C; p.scale = scale; p.colsum = colsum;
+  splits = (total_chunks + p.chunks_per_split - 1) / p.chunks_per_split;
+  EmuDim g; g.x = tiles; g.y = splits; EmuDim b; b.x = kTnThreads;
+  for (int i = 0; i < 16; ++i) emu_named_n[i] = 0;
+  emu_launch(g, b, L::kTotal, [=] { gemm_tn_kernel<kBQ, kStages>(tmA, tmB, p); });
+}
+''')
+    lib = compile_host(tmp_path, 'gemm_tn', body)
+    P_, I, L_, Fl = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+    lib.gemm_tn.argtypes = [P_, L_, P_, L_, P_, L_, I, I, I, Fl, P_, I]
+    g = torch.Generator().manual_seed(0)
+    M, P, Q = 330, 192, 192                                  # 330 rows: the sixth 64-row chunk is mostly zero-filled by TMA
+    A = (torch.randn(M, P, generator=g)).to(torch.bfloat16)
+    B = (torch.randn(M, Q, generator=g)).to(torch.bfloat16)
+    bits = lambda x: np.ascontiguousarray(x.view(torch.int16).numpy())
+    want = A.double().t() @ B.double()
+    for splits, with_colsum in ((1, False), (3, True), (6, True)):
+        C0 = torch.randn(P, Q, generator=g)
+        C = C0.numpy().copy()
+        cs = np.full(P, 2.0, F)
+        lib.gemm_tn(vp(bits(A)), P, vp(bits(B)), Q, vp(C), Q, M, P, Q, 0.5, vp(cs) if with_colsum else None, splits)
+        ref = C0.double() + 0.5 * want
+        assert np.abs(C - ref.numpy()).max() <= 1e-5 * float(ref.abs().max()), (splits, float(np.abs(C - ref.numpy()).max()))
+        if with_colsum:
+            assert np.abs(cs - (2.0 + 0.5 * A.double().sum(0)).numpy()).max() <= 1e-5 * float(A.double().sum(0).abs().max() + 2)
