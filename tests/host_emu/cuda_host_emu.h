@@ -107,6 +107,7 @@ class EmuBarrier {
     ++emu_progress;                                    // an arrival is a state change, released or not
     if (++waiting_ >= expected_) { waiting_ = 0; ++gen_; return; }
     while (gen_ == g) emu_yield();
+    ++emu_progress;                                    // so is leaving a wait
   }
   void drop() {
     --expected_;

@@ -42,7 +42,7 @@ static inline void mbar_arrive(uint64_t* bar) { EmuMbar& b = emu_mbars.at(bar); 
 static inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) { EmuMbar& b = emu_mbars.at(bar); b.tx += bytes; --b.pending; emu_mbar_check(b); }
 static inline void emu_complete_tx(uint64_t* bar, uint32_t bytes) { EmuMbar& b = emu_mbars.at(bar); b.tx -= bytes; emu_mbar_check(b); }
 static inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return emu_mbars.at(bar).phase != (parity & 1u); }
-static inline void mbar_wait(uint64_t* bar, uint32_t parity) { while (!mbar_try_wait(bar, parity)) emu_yield(); }
+static inline void mbar_wait(uint64_t* bar, uint32_t parity) { while (!mbar_try_wait(bar, parity)) emu_yield(); ++emu_progress; }
 static inline void fence_proxy_async_smem() {}
 static inline void tc_fence_before() {}
 static inline void tc_fence_after() {}
@@ -107,3 +107,33 @@ static inline void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, 
   ++emu_progress;
 }
 static inline void umma_commit(uint64_t* bar) { mbar_arrive(bar); }
+
+// ---- the rest of the single-CTA surface (gemm_nt.cuh): split descriptors, TMA stores, tensor-memory stores
+// common.cuh passes the K-major SW128 descriptor as (low word, constant high word); the test takes umma_desc_lo / kUmmaDescHiSw128
+// verbatim and this only glues the halves together
+template <int G>
+static inline void umma_f16_split(uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate);
+static inline void emu_umma_split(uint32_t hi, uint32_t d_tmem, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  umma_bf16(d_tmem, (static_cast<uint64_t>(hi) << 32) | a_lo, (static_cast<uint64_t>(hi) << 32) | b_lo, idesc, accumulate);
+}
+static inline void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  const uint32_t src = smem_u32(smem_src);
+  for (int r = 0; r < m->box_rows; ++r)
+    for (int e = 0; e < m->box_cols; ++e) {
+      const long long gr = static_cast<long long>(c1) + r, gc = static_cast<long long>(c0) + e;
+      if (gr < 0 || gr >= m->rows || gc < 0 || gc >= m->cols) continue;                    // clipped by the tensor map
+      std::memcpy(const_cast<unsigned char*>(static_cast<const unsigned char*>(m->base)) + (gr * m->ld + gc) * m->elem_bytes,
+                  emu_smem_ptr(emu_sw128(src + static_cast<uint32_t>(r) * 128u + static_cast<uint32_t>(e * m->elem_bytes))), m->elem_bytes);
+    }
+  ++emu_progress;
+}
+static inline void tma_store_commit() {}
+template <int N> static inline void tma_store_wait_read() {}
+template <int N = 0> static inline void tma_store_wait_all() {}
+static inline void tma_prefetch_2d(const CUtensorMap*, int, int) {}
+static inline void prefetch_l2(const void*) {}
+static inline void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+  const uint32_t lane = (taddr >> 16) + lane_id(), col = taddr & 0xffffu;
+  for (int i = 0; i < 32; ++i) std::memcpy(&emu_tmem[lane][col + i], &v[i], 4);
+}
+static inline float ex2_approx(float x) { return exp2f(x); }          // ex2.approx.ftz.f32 (2 ulp) modelled by the exact function

@@ -870,3 +870,81 @@ extern "C" void gemm_tn(const uint16_t* A, long long lda, const uint16_t* B, lon
         assert np.abs(C - ref.numpy()).max() <= 1e-5 * float(ref.abs().max()), (splits, float(np.abs(C - ref.numpy()).max()))
         if with_colsum:
             assert np.abs(cs - (2.0 + 0.5 * A.double().sum(0)).numpy()).max() <= 1e-5 * float(A.double().sum(0).abs().max() + 2)
+
+
+@pytest.fixture(scope='module')
+def gemm_nt_lib(tmp_path_factory):
+    c, t = read('common.cuh'), read('gemm_nt.cuh')
+    kernel = between(t, 'enum GemmEpilogue', '#endif  // __CUDACC__').replace('#ifdef __CUDACC__', '')
+    dyn = 'extern __shared__ uint8_t smem_raw[];'
+    assert kernel.count(dyn) == 1
+    kernel = kernel.replace(dyn, 'uint8_t* smem_raw = static_cast<uint8_t*>(emu_dynamic_smem());')
+    gelu = between(c, '// Phi(-a) for a >= 0', '// ----------------------------------------------------------------------------- mbarrier')
+    body = ('#include "tcgen05_host_emu.h"\nnamespace {\n'
+            + between(c, '// Shared-memory matrix descriptor (64-bit).', '// ----------------------------------------------------------------------------- CTA pairs')   # descriptor builders + sw128_offset, verbatim
+            + between(c, 'constexpr uint32_t kUmmaDescHiSw128', 'template <int G>\n__device__ __forceinline__ void umma_f16_split')                                   # umma_desc_lo, verbatim
+            + 'template <int G> inline void umma_f16_split(uint32_t d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t acc) {\n'
+              '  static_assert(G == 1, "single-CTA emulation"); emu_umma_split(kUmmaDescHiSw128, d, a_lo, b_lo, idesc, acc); }\n'
+            + gelu + between(c, '__host__ __device__ __forceinline__ size_t xt_offset', '#endif  // __CUDACC__')
+            + kernel + '}\n' + r'''
+// tensor maps, grid and stage choice of launch_nt_stages / launch_nt (gemm.cu); `grid_cap` stands for the SM count
+template <int MODE, int STAGES>
+static void run_nt(const uint16_t* A, const uint16_t* B, void* out, void* out2, const void* aux, GemmNtParams p, int grid_cap) {
+  constexpr int kBN = 192;
+  using L = GemmNtSmem<kBN, STAGES>;
+  const bool out_f32 = (MODE == EPI_F32 || MODE == EPI_RES_LN);
+  const CUtensorMap tmA = emu_make_tmap_2d(A, 2, p.M, p.K, p.K, 128, 64), tmB = emu_make_tmap_2d(B, 2, p.N, p.K, p.K, kBN, 64);
+  CUtensorMap tmOut = (MODE == EPI_RES_LN && p.out_tiled != nullptr) ? tmA : emu_make_tmap_2d(out, out_f32 ? 4 : 2, p.M, p.N, p.N, 32, out_f32 ? 32 : 64);
+  CUtensorMap tmOut2 = tmOut, tmAux = tmOut;
+  if (p.has_out2) tmOut2 = emu_make_tmap_2d(out2, 2, p.M, p.N, p.N, 32, 64);
+  if (MODE == EPI_DGELU) tmAux = emu_make_tmap_2d(aux, 2, p.M, p.N, p.N, 128, 64);
+  else if (MODE == EPI_RES_LN && p.has_res && p.res_table == nullptr && p.out_tiled == nullptr) tmAux = emu_make_tmap_2d(aux, 4, p.M, p.N, p.N, 128, 32);
+  const int tiles = ((p.M + 127) / 128) * (p.N / kBN);
+  EmuDim g; g.x = tiles < grid_cap ? tiles : grid_cap; EmuDim b; b.x = kGemmThreads;
+  for (int i = 0; i < 16; ++i) emu_named_n[i] = 0;
+  emu_launch(g, b, L::kTotal, [=] { gemm_nt_kernel<kBN, MODE, STAGES>(tmA, tmB, tmOut, tmOut2, tmAux, p); });
+}
+extern "C" void gemm_nt(int mode, const uint16_t* A, const uint16_t* B, void* out, void* out2, const void* aux, int M, int N, int K,
+                        const float* bias, const float* gamma, const float* beta, const float* res_table, int table_rows, float eps,
+                        float* mean, float* rstd, int has_out2, int has_res, int grid_cap) {
+  GemmNtParams p{};
+  p.M = M; p.N = N; p.K = K; p.bias = bias; p.gamma = gamma; p.beta = beta; p.res_table = res_table; p.table_rows = table_rows;
+  p.ln_eps = eps; p.mean_out = mean; p.rstd_out = rstd; p.has_out2 = has_out2; p.has_res = has_res;
+  const bool two = K <= 192 && mode == EPI_DGELU;
+  if (mode == EPI_BF16) run_nt<EPI_BF16, 3>(A, B, out, out2, aux, p, grid_cap);
+  else if (mode == EPI_GELU) run_nt<EPI_GELU, 3>(A, B, out, out2, aux, p, grid_cap);
+  else if (mode == EPI_DGELU) { if (two) run_nt<EPI_DGELU, 2>(A, B, out, out2, aux, p, grid_cap); else run_nt<EPI_DGELU, 3>(A, B, out, out2, aux, p, grid_cap); }
+  else if (mode == EPI_F32) run_nt<EPI_F32, 3>(A, B, out, out2, aux, p, grid_cap);
+  else run_nt<EPI_RES_LN, 3>(A, B, out, out2, aux, p, grid_cap);
+}
+''')
+    lib = compile_host(tmp_path_factory.mktemp('gemm_nt'), 'gemm_nt', body)
+    P_, I, Fl = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    lib.gemm_nt.argtypes = [I, P_, P_, P_, P_, P_, I, I, I, P_, P_, P_, P_, I, Fl, P_, P_, I, I, I]
+    return lib
+
+
+def _bf16_bits(x):
+    return np.ascontiguousarray(x.view(torch.int16).numpy())
+
+
+def _from_bits(a):
+    return torch.from_numpy(a.astype(np.int16)).view(torch.bfloat16).float()
+
+
+def test_forward_gemm_tcgen05_kernel_bf16_epilogue_on_the_host(gemm_nt_lib):
+    """`gemm_nt_kernel<192, EPI_BF16, 3>` (the qkv projection: persistent, warp-specialised -- TMA producer, UMMA issuer over
+    K-major swizzled operands through split descriptors, epilogue-panel producer, twelve epilogue warps in three teams, double-
+    buffered TMEM accumulator, swizzled staging panels leaving by TMA store) under the functional emulation: M = 330 (ragged last
+    tile, clipped stores), N = 576 = three N tiles, K = 192, on 2 "SMs" so that every CTA walks several tiles."""
+    g = torch.Generator().manual_seed(0)
+    M, N, K = 330, 576, 192
+    A = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) * 0.1).to(torch.bfloat16)
+    bias = torch.randn(N, generator=g)
+    out = np.full((M, N), 0x7fc0, np.uint16)
+    gemm_nt_lib.gemm_nt(0, vp(_bf16_bits(A)), vp(_bf16_bits(W)), vp(out), None, None, M, N, K, vp(bias.numpy()), None, None, None, 0, 0.0, None, None, 0, 0, 2)
+    want = (A.double() @ W.double().t() + bias.double()).float()
+    got = _from_bits(out)
+    assert float((got - want).abs().max()) <= 2.0 ** -8 * float(want.abs().max())            # one bf16 rounding of the output
+    assert float((got - want.to(torch.bfloat16).float()).abs().max()) <= 2.0 ** -7 * float(want.abs().max()) and torch.isfinite(got).all()
