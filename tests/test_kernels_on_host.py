@@ -948,3 +948,56 @@ def test_forward_gemm_tcgen05_kernel_bf16_epilogue_on_the_host(gemm_nt_lib):
     got = _from_bits(out)
     assert float((got - want).abs().max()) <= 2.0 ** -8 * float(want.abs().max())            # one bf16 rounding of the output
     assert float((got - want.to(torch.bfloat16).float()).abs().max()) <= 2.0 ** -7 * float(want.abs().max()) and torch.isfinite(got).all()
+
+
+def test_forward_gemm_tcgen05_kernel_fused_epilogues_on_the_host(gemm_nt_lib):
+    """The other epilogue modes of `gemm_nt_kernel` under the functional emulation, against torch on the same bf16 operands:
+    EPI_GELU with both outputs (fc1: z = acc + bias and h = gelu(z), exact-erf GELU), EPI_DGELU (fc2's input gradient: acc * gelu'(z)
+    with the saved z panels arriving by TMA into the staging slots, two operand stages / eight slots), EPI_F32, and EPI_RES_LN as the
+    patch embedding runs it in training (acc + bias + token table by row % 197, fp32 stream out by TMA, LayerNorm1 of block 0 as a second
+    bf16 output, per-row mean / rstd)."""
+    g = torch.Generator().manual_seed(1)
+    M = 300
+    # ---- fc1: [M,192] x [768,192]^T, GELU, z kept
+    A = torch.randn(M, 192, generator=g).to(torch.bfloat16)
+    W = (torch.randn(768, 192, generator=g) * 0.1).to(torch.bfloat16)
+    bias = torch.randn(768, generator=g) * 0.5
+    h, z = np.full((M, 768), 0x7fc0, np.uint16), np.full((M, 768), 0x7fc0, np.uint16)
+    gemm_nt_lib.gemm_nt(1, vp(_bf16_bits(A)), vp(_bf16_bits(W)), vp(h), vp(z), None, M, 768, 192, vp(bias.numpy()), None, None, None, 0, 0.0, None, None, 1, 0, 3)
+    zw = (A.double() @ W.double().t() + bias.double()).float()
+    assert float((_from_bits(z) - zw).abs().max()) <= 2.0 ** -8 * float(zw.abs().max())
+    hw = torch.nn.functional.gelu(zw)
+    assert float((_from_bits(h) - hw).abs().max()) <= 2.0 ** -8 * float(hw.abs().max()) + 1e-5
+    # ---- fc2 dgrad: dz = (dy W2) * gelu'(z): A = dy [M,192], B = W2^T as [768,192], aux = z
+    dy = torch.randn(M, 192, generator=g).to(torch.bfloat16)
+    W2T = (torch.randn(768, 192, generator=g) * 0.1).to(torch.bfloat16)
+    zsaved = _from_bits(z).to(torch.bfloat16)
+    dz = np.full((M, 768), 0x7fc0, np.uint16)
+    gemm_nt_lib.gemm_nt(2, vp(_bf16_bits(dy)), vp(_bf16_bits(W2T)), vp(dz), None, vp(_bf16_bits(zsaved)), M, 768, 192, None, None, None, None, 0, 0.0, None, None, 0, 0, 2)
+    zz = zsaved.double().requires_grad_(True)
+    torch.nn.functional.gelu(zz).sum().backward()
+    want = ((dy.double() @ W2T.double().t()) * zz.grad).float()
+    assert float((_from_bits(dz) - want).abs().max()) <= 2.0 ** -8 * float(want.abs().max()) + 1e-4
+    # ---- fp32 output
+    out32 = np.full((M, 192), np.nan, F)
+    Wq = (torch.randn(192, 192, generator=g) * 0.1).to(torch.bfloat16)
+    b192 = torch.randn(192, generator=g)
+    gemm_nt_lib.gemm_nt(3, vp(_bf16_bits(A)), vp(_bf16_bits(Wq)), vp(out32), None, None, M, 192, 192, vp(b192.numpy()), None, None, None, 0, 0.0, None, None, 0, 0, 2)
+    w32 = (A.double() @ Wq.double().t() + b192.double()).float()
+    assert np.abs(out32 - w32.numpy()).max() <= 1e-5 * float(w32.abs().max())
+    # ---- patch embedding: x = patches Wp^T + table[row % 197]; second output LN1(x) in bf16; mean / rstd per row
+    Mp = 2 * 197
+    patches = torch.randn(Mp, 768, generator=g).to(torch.bfloat16)
+    Wp = (torch.randn(192, 768, generator=g) * 0.05).to(torch.bfloat16)
+    table = torch.randn(197, 192, generator=g)
+    gamma, beta = torch.randn(192, generator=g), torch.randn(192, generator=g)
+    x = np.full((Mp, 192), np.nan, F)
+    ln = np.full((Mp, 192), 0x7fc0, np.uint16)
+    mean, rstd = np.full(Mp, np.nan, F), np.full(Mp, np.nan, F)
+    gemm_nt_lib.gemm_nt(4, vp(_bf16_bits(patches)), vp(_bf16_bits(Wp)), vp(x), vp(ln), None, Mp, 192, 768, None, vp(gamma.numpy()), vp(beta.numpy()),
+                        vp(table.numpy()), 197, 1e-6, vp(mean), vp(rstd), 1, 1, 2)
+    xw = (patches.double() @ Wp.double().t() + table.double().repeat(2, 1)).float()
+    assert np.abs(x - xw.numpy()).max() <= 1e-5 * float(xw.abs().max())
+    lw = torch.nn.functional.layer_norm(xw, (192,), gamma, beta, 1e-6)
+    assert float((_from_bits(ln) - lw).abs().max()) <= 2.0 ** -8 * float(lw.abs().max()) + 1e-4
+    assert np.abs(mean - xw.mean(1).numpy()).max() <= 1e-5 and np.abs(rstd - (xw.var(1, unbiased=False) + 1e-6).rsqrt().numpy()).max() <= 1e-4
