@@ -95,6 +95,8 @@ static ucontext_t emu_sched_ctx;
 static EmuFiber* emu_cur = nullptr;
 static std::function<void()> emu_kernel_call;
 static inline void emu_yield() { swapcontext(&emu_cur->ctx, &emu_sched_ctx); }
+static std::vector<std::function<void()>> emu_deferred;   // asynchronous completions: applied at the start of the next scheduler pass
+static const void* emu_wait_on[1024];         // what each thread is parked at (diagnostics of the deadlock message)
 static unsigned long emu_progress = 0;       // barrier arrivals / releases + finished fibers: a scheduler pass without any is a deadlock
 
 class EmuBarrier {
@@ -106,6 +108,7 @@ class EmuBarrier {
     const unsigned long g = gen_;
     ++emu_progress;                                    // an arrival is a state change, released or not
     if (++waiting_ >= expected_) { waiting_ = 0; ++gen_; return; }
+    emu_wait_on[(threadIdx.x + blockDim.x * (threadIdx.y + blockDim.y * threadIdx.z)) & 1023u] = this;
     while (gen_ == g) emu_yield();
     ++emu_progress;                                    // so is leaving a wait
   }
@@ -190,6 +193,12 @@ static void emu_launch(EmuDim grid, EmuDim block, size_t dyn_smem_bytes, F kerne
         unsigned remaining = nthreads;
         while (remaining > 0) {
           const unsigned long before = emu_progress;
+          if (!emu_deferred.empty()) {
+            std::vector<std::function<void()>> due;
+            due.swap(emu_deferred);
+            for (auto& fn : due) fn();
+            ++emu_progress;
+          }
           for (unsigned i = 0; i < nthreads; ++i) {
             const unsigned t = reverse ? nthreads - 1 - i : i;
             EmuFiber& f = fibers[t];
@@ -202,6 +211,8 @@ static void emu_launch(EmuDim grid, EmuDim block, size_t dyn_smem_bytes, F kerne
           if (remaining > 0 && emu_progress == before) {        // every live fiber is parked at a barrier that cannot complete
             std::fprintf(stderr, "cuda_host_emu: deadlock in block (%u,%u,%u): %u threads wait at a barrier the others never reach "
                                  "(divergent __syncthreads / partial-warp shuffle)\n", bx, by, bz, remaining);
+            for (unsigned t = 0; t < nthreads && t < 1024; ++t)
+              if (!fibers[t].done && (t % 32 == 0 || emu_wait_on[t] != emu_wait_on[t - 1])) std::fprintf(stderr, "  thread %u waits on %p\n", t, emu_wait_on[t]);
             std::abort();
           }
         }

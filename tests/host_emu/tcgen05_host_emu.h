@@ -10,8 +10,8 @@
 //   128-byte swizzle          the 16-byte chunk index (address bits 4-6) is XORed with address bits 7-9
 //   K-major operand           element (r, k): (r / 8) * SBO + (r % 8) * 128 + k * 2 inside a 128-byte row (K = 64 per row)
 //   MN-major operand          element (mn, k): (mn / 64) * LBO + (k / 8) * SBO + (k % 8) * 128 + (mn % 64) * 2
-// Everything executes at issue time (a TMA load completes its bytes at once, an MMA is done when umma_commit arrives), which is
-// one legal schedule of the asynchronous hardware; waits are fiber yields.
+// TMA loads and MMAs execute at issue time, tcgen05.commit arrives one scheduler pass later: one legal schedule of the
+// asynchronous hardware; waits are fiber yields.
 #pragma once
 #include <map>
 
@@ -42,7 +42,7 @@ static inline void mbar_arrive(uint64_t* bar) { EmuMbar& b = emu_mbars.at(bar); 
 static inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) { EmuMbar& b = emu_mbars.at(bar); b.tx += bytes; --b.pending; emu_mbar_check(b); }
 static inline void emu_complete_tx(uint64_t* bar, uint32_t bytes) { EmuMbar& b = emu_mbars.at(bar); b.tx -= bytes; emu_mbar_check(b); }
 static inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) { return emu_mbars.at(bar).phase != (parity & 1u); }
-static inline void mbar_wait(uint64_t* bar, uint32_t parity) { while (!mbar_try_wait(bar, parity)) emu_yield(); ++emu_progress; }
+static inline void mbar_wait(uint64_t* bar, uint32_t parity) { emu_wait_on[emu_tid() & 1023u] = bar; while (!mbar_try_wait(bar, parity)) emu_yield(); ++emu_progress; }
 static inline void fence_proxy_async_smem() {}
 static inline void tc_fence_before() {}
 static inline void tc_fence_after() {}
@@ -106,7 +106,11 @@ static inline void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, 
     }
   ++emu_progress;
 }
-static inline void umma_commit(uint64_t* bar) { mbar_arrive(bar); }
+// tcgen05.commit arrives when the MMAs issued so far have FINISHED, i.e. some time after the instruction: applied at the start of
+// the next scheduler pass.  (Applied at once, the elected lane could release a ring stage, the producer refill it and the
+// barrier's phase wrap before the other lanes of the issuer warp -- which the kernels keep within one iteration by __syncwarp --
+// had looked at it; on the hardware a TMA refill cannot overtake lanes that are a few instructions behind.)
+static inline void umma_commit(uint64_t* bar) { emu_deferred.push_back([bar] { mbar_arrive(bar); }); }
 
 // ---- the rest of the single-CTA surface (gemm_nt.cuh): split descriptors, TMA stores, tensor-memory stores
 // common.cuh passes the K-major SW128 descriptor as (low word, constant high word); the test takes umma_desc_lo / kUmmaDescHiSw128
