@@ -6,7 +6,7 @@
 // barrier over the live threads of the block and the warp shuffles exchange through a per-warp barrier, so kernels that reduce
 // with `__shfl_xor_sync`, stage through shared memory and finish with `atomicAdd` run with their real control flow -- and
 // deterministically.  Threads that return early are dropped from the barriers (a CUDA block does not wait for exited threads
-// either).  Not modelled: tensor cores, TMA, mbarriers, inline PTX -- the tcgen05 kernels are tested on the GPU only.
+// either).  Tensor cores, TMA and mbarriers are modelled functionally by tcgen05_host_emu.h (single-CTA kernels); inline PTX is not.
 #pragma once
 #include <algorithm>
 #include <atomic>

@@ -6,9 +6,10 @@ geometry the library uses and compared with the reference-generated vectors, the
 Covered: the CUDA-core kernels -- the fp32 KAN layer kernels and the small-output KAN kernels (forward and every gradient), the
 fused heads + KAN tail in inference and in training (forward, backward, all 23 parameter gradients, dropout), the per-layer linear
 path, the joint-loss kernel with its block reduction, LayerNorm forward / backward, the optimizer's gradient-norm kernel, attention
-probabilities, weight shadows, token table, column sums.  The tcgen05 / TMA kernels (trunk GEMMs, attention, the fused MLP block,
-the tensor-core KAN path) cannot be emulated this way and are tested on the GPU (`-m gpu`); their CUDA-core operand producer is
-covered in tests/test_kernel_constants.py."""
+probabilities, weight shadows, token table, column sums.  The single-CTA tcgen05 GEMMs (gemm_nt in every epilogue mode, gemm_tn) run under a
+FUNCTIONAL emulation of mbarriers / TMA / tensor memory / tcgen05.mma (tests/host_emu/tcgen05_host_emu.h).  Not emulated: the
+kernels with TMEM-resident operands and CTA pairs (attention, the fused MLP block) and the tensor-core KAN kernels (their
+CUDA-core operand producer is covered in tests/test_kernel_constants.py) -- those are tested on the GPU (`-m gpu`)."""
 
 import ctypes
 import os
