@@ -1002,3 +1002,25 @@ def test_forward_gemm_tcgen05_kernel_fused_epilogues_on_the_host(gemm_nt_lib):
     lw = torch.nn.functional.layer_norm(xw, (192,), gamma, beta, 1e-6)
     assert float((_from_bits(ln) - lw).abs().max()) <= 2.0 ** -8 * float(lw.abs().max()) + 1e-4
     assert np.abs(mean - xw.mean(1).numpy()).max() <= 1e-5 and np.abs(rstd - (xw.var(1, unbiased=False) + 1e-6).rsqrt().numpy()).max() <= 1e-4
+
+
+def test_forward_gemm_tcgen05_kernel_residual_by_tma_on_the_host(gemm_nt_lib):
+    """EPI_RES_LN as the training blocks run it for fc2 / the attention projection: K = 768 (twelve K blocks through the 3-stage ring),
+    the fp32 residual stream arrives as TMA-loaded panels in the staging slots, is rewritten in place with acc + bias + residual and
+    leaves by TMA store; the next block's LayerNorm (bf16) and its row statistics come out of the same epilogue."""
+    g = torch.Generator().manual_seed(2)
+    M = 200
+    H = torch.randn(M, 768, generator=g).to(torch.bfloat16)
+    W2 = (torch.randn(192, 768, generator=g) * 0.05).to(torch.bfloat16)
+    b2, gamma, beta = torch.randn(192, generator=g), torch.randn(192, generator=g), torch.randn(192, generator=g)
+    res = torch.randn(M, 192, generator=g)
+    x = np.full((M, 192), np.nan, F)
+    ln = np.full((M, 192), 0x7fc0, np.uint16)
+    mean, rstd = np.full(M, np.nan, F), np.full(M, np.nan, F)
+    gemm_nt_lib.gemm_nt(4, vp(_bf16_bits(H)), vp(_bf16_bits(W2)), vp(x), vp(ln), vp(np.ascontiguousarray(res.numpy())), M, 192, 768, vp(b2.numpy()),
+                        vp(gamma.numpy()), vp(beta.numpy()), None, 0, 1e-6, vp(mean), vp(rstd), 1, 1, 2)
+    xw = (H.double() @ W2.double().t() + b2.double() + res.double()).float()
+    assert np.abs(x - xw.numpy()).max() <= 1e-5 * float(xw.abs().max())
+    lw = torch.nn.functional.layer_norm(xw, (192,), gamma, beta, 1e-6)
+    assert float((_from_bits(ln) - lw).abs().max()) <= 2.0 ** -8 * float(lw.abs().max()) + 1e-4
+    assert np.abs(mean - xw.mean(1).numpy()).max() <= 1e-5 and np.abs(rstd - (xw.var(1, unbiased=False) + 1e-6).rsqrt().numpy()).max() <= 1e-4
