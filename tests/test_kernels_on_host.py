@@ -918,10 +918,20 @@ extern "C" void gemm_nt(int mode, const uint16_t* A, const uint16_t* B, void* ou
   else if (mode == EPI_F32) run_nt<EPI_F32, 3>(A, B, out, out2, aux, p, grid_cap);
   else run_nt<EPI_RES_LN, 3>(A, B, out, out2, aux, p, grid_cap);
 }
+// inference: the fp32 token stream leaves (and a residual arrives) in the tiled layout of common.cuh, straight from / to registers
+extern "C" void gemm_nt_tiled(const uint16_t* A, const uint16_t* B, void* ln_out, int M, int K, const float* bias, const float* gamma,
+                              const float* beta, const float* res_table, int table_rows, const float* res_tiled, float* out_tiled, float eps,
+                              int grid_cap) {
+  GemmNtParams p{};
+  p.M = M; p.N = 192; p.K = K; p.bias = bias; p.gamma = gamma; p.beta = beta; p.res_table = res_table; p.table_rows = table_rows;
+  p.ln_eps = eps; p.has_out2 = 1; p.has_res = 1; p.res_tiled = res_tiled; p.out_tiled = out_tiled;
+  run_nt<EPI_RES_LN, 3>(A, B, nullptr, ln_out, nullptr, p, grid_cap);
+}
 ''')
     lib = compile_host(tmp_path_factory.mktemp('gemm_nt'), 'gemm_nt', body)
     P_, I, Fl = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
     lib.gemm_nt.argtypes = [I, P_, P_, P_, P_, P_, I, I, I, P_, P_, P_, P_, I, Fl, P_, P_, I, I, I]
+    lib.gemm_nt_tiled.argtypes = [P_, P_, P_, I, I, P_, P_, P_, P_, I, P_, P_, Fl, I]
     return lib
 
 
@@ -1024,3 +1034,37 @@ def test_forward_gemm_tcgen05_kernel_residual_by_tma_on_the_host(gemm_nt_lib):
     lw = torch.nn.functional.layer_norm(xw, (192,), gamma, beta, 1e-6)
     assert float((_from_bits(ln) - lw).abs().max()) <= 2.0 ** -8 * float(lw.abs().max()) + 1e-4
     assert np.abs(mean - xw.mean(1).numpy()).max() <= 1e-5 and np.abs(rstd - (xw.var(1, unbiased=False) + 1e-6).rsqrt().numpy()).max() <= 1e-4
+
+
+def test_forward_gemm_tcgen05_kernel_tiled_stream_on_the_host(gemm_nt_lib):
+    """EPI_RES_LN on the INFERENCE path: the patch-embedding GEMM writes the fp32 residual stream in the tiled
+    layout `[M/32][6 panels][8][32 rows][4]` straight from registers (no staging panels, no TMA) plus LayerNorm1 of block 0 in bf16;
+    and the same mode with a tiled residual input (x' = acc + bias + x)."""
+    g = torch.Generator().manual_seed(3)
+    Mp = 2 * 197
+    rows_pad = (Mp + 127) // 128 * 128
+    patches = torch.randn(Mp, 768, generator=g).to(torch.bfloat16)
+    Wp = (torch.randn(192, 768, generator=g) * 0.05).to(torch.bfloat16)
+    table, gamma, beta = torch.randn(197, 192, generator=g), torch.randn(192, generator=g), torch.randn(192, generator=g)
+
+    def untile(buf):           # xt_elem_offset (checked as a bijection in test_kernel_constants.py): [r/32][c/32][(c%32)/4][r%32][c%4]
+        return buf.reshape(rows_pad // 32, 6, 8, 32, 4).transpose(0, 3, 1, 2, 4).reshape(rows_pad, 192)
+
+    xt = np.full(rows_pad * 192, np.nan, F)
+    ln = np.full((Mp, 192), 0x7fc0, np.uint16)
+    gemm_nt_lib.gemm_nt_tiled(vp(_bf16_bits(patches)), vp(_bf16_bits(Wp)), vp(ln), Mp, 768, None, vp(gamma.numpy()), vp(beta.numpy()), vp(table.numpy()), 197,
+                              None, vp(xt), 1e-6, 2)
+    xw = (patches.double() @ Wp.double().t() + table.double().repeat(2, 1)).float()
+    x = untile(xt)[:Mp]
+    assert np.abs(x - xw.numpy()).max() <= 1e-5 * float(xw.abs().max())
+    lw = torch.nn.functional.layer_norm(xw, (192,), gamma, beta, 1e-6)
+    assert float((_from_bits(ln) - lw).abs().max()) <= 2.0 ** -8 * float(lw.abs().max()) + 1e-4
+    # residual from the tiled stream itself, written back in place (x' = x + a W^T + b)
+    A2 = torch.randn(Mp, 192, generator=g).to(torch.bfloat16)
+    W2 = (torch.randn(192, 192, generator=g) * 0.1).to(torch.bfloat16)
+    b2 = torch.randn(192, generator=g)
+    xt2 = xt.copy()
+    gemm_nt_lib.gemm_nt_tiled(vp(_bf16_bits(A2)), vp(_bf16_bits(W2)), vp(ln), Mp, 192, vp(b2.numpy()), vp(gamma.numpy()), vp(beta.numpy()), None, 0,
+                              vp(xt2), vp(xt2), 1e-6, 2)
+    xw2 = (torch.from_numpy(x.copy()).double() + A2.double() @ W2.double().t() + b2.double()).float()
+    assert np.abs(untile(xt2)[:Mp] - xw2.numpy()).max() <= 1e-5 * float(xw2.abs().max())
